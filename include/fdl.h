@@ -1,0 +1,277 @@
+/*
+ * fdl.h -- C ABI of the B200-native detect -> landmark -> iris path.
+ *
+ * This is the drop-in boundary for rs-face-detection-tflite's inference path: every entry point
+ * below replaces one call a reference user makes into `face_detection_lite::*` (which in the
+ * reference fans out into the TFLite C++ interpreter and OpenCV).  Below this header: C++ host
+ * code + hand-written sm_100a CUDA kernels (no TFLite, no OpenCV, no CPU fallback -- a call made
+ * without a usable CUDA device returns FDL_ERR_CUDA).  Above it: the Rust shim crate
+ * (rust_shim/, source only), the C++ mirror (include/fdl.hpp) and the Python ctypes mirror
+ * (rs_face_detection_tflite_b200/api.py).
+ *
+ * Reference citations are relative to /root/reference/src/face_detection_lite/.
+ *
+ * Conventions
+ *   - every function returning `int` returns FDL_OK (0) or a negative FDL_ERR_* code; the message
+ *     is available through fdl_last_error() (thread-local).  Nothing aborts, nothing throws
+ *     across the ABI (the reference mixes anyhow::Error and panics).
+ *   - images are 8UC3 **RGB**, HWC, row-major, like the `Mat` produced by
+ *     utils.rs:8-21 `convert_image_to_mat`; `row_stride` is in bytes.
+ *   - a handle is bound to one CUDA device and one stream; calls on one handle must be
+ *     serialised by the caller, different handles are independent.
+ */
+#ifndef FDL_H_
+#define FDL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define FDL_API
+#else
+#define FDL_API __attribute__((visibility("default")))
+#endif
+
+/* ---------------------------------------------------------------- status codes */
+enum {
+  FDL_OK = 0,
+  FDL_ERR_INVALID = -1,      /* bad argument (null pointer, capacity, "bbox must be normalized" transform.rs:52) */
+  FDL_ERR_IO = -2,           /* model file missing / unreadable (face_detection.rs:188) */
+  FDL_ERR_MODEL = -3,        /* malformed or unsupported .tflite ("unsupported model type" face_detection.rs:184,
+                                "incompatible model" face_landmark.rs:246, iris_landmark.rs:172-184) */
+  FDL_ERR_CUDA = -4,         /* no device / CUDA runtime error: the product never falls back to the CPU */
+  FDL_ERR_CAPACITY = -5,     /* caller-provided output buffer too small */
+  FDL_ERR_INTERNAL = -6
+};
+
+/* ---------------------------------------------------------------- value types (types.rs) */
+
+/* types.rs:24-37 `Rect` (f64 fields; rotation in radians, clockwise). */
+typedef struct fdl_rect {
+  double x_center, y_center, width, height, rotation;
+  int32_t normalized;
+  int32_t _pad;
+} fdl_rect;
+
+/* types.rs:189-246 `Detection`: data = Array2<f32>[8,2] row-major
+ * (row0 = xmin,ymin; row1 = xmax,ymax; rows 2..7 = keypoints, face_detection.rs:91-98) + score.
+ * `anchor` is not in the reference: the SSD anchor index of the NMS cluster's top detection
+ * ("kept index"). */
+typedef struct fdl_detection {
+  float data[16];
+  float score;
+  int32_t anchor;
+} fdl_detection;
+
+/* types.rs:176-187 `Landmark` (f64). */
+typedef struct fdl_landmark {
+  double x, y, z;
+} fdl_landmark;
+
+/* The `&Mat` argument of every infer(): 8UC3 RGB. */
+enum { FDL_MEM_HOST = 0, FDL_MEM_DEVICE = 1 };
+typedef struct fdl_image {
+  const uint8_t* data;
+  int32_t width, height;
+  int64_t row_stride;   /* bytes; 0 means width*3 */
+  int32_t mem;          /* FDL_MEM_HOST (pageable or pinned) or FDL_MEM_DEVICE (on the handle's device) */
+  int32_t _pad;
+} fdl_image;
+
+/* face_detection.rs:117-123 `FaceDetectionModel`. FullSparse (4) is outside the hot-path scope
+ *  and yields FDL_ERR_MODEL. */
+enum {
+  FDL_MODEL_FRONT_CAMERA = 0,
+  FDL_MODEL_BACK_CAMERA = 1,
+  FDL_MODEL_SHORT = 2,
+  FDL_MODEL_FULL = 3,
+  FDL_MODEL_FULL_SPARSE = 4
+};
+
+/* transform.rs:15-24 `SizeMode`; FDL_SIZE_MODE_NONE mirrors `Option::None` (-> SquareLong,
+ * face_landmark.rs:188). */
+enum { FDL_SIZE_MODE_NONE = -1, FDL_SIZE_MODE_DEFAULT = 0, FDL_SIZE_MODE_SQUARE_LONG = 1, FDL_SIZE_MODE_SQUARE_SHORT = 2 };
+
+enum {
+  FDL_NUM_FACE_LANDMARKS = 468,     /* face_landmark.rs:27 */
+  FDL_NUM_EYE_CONTOUR = 71,         /* iris_landmark.rs:206-228: 213 / 3 */
+  FDL_NUM_IRIS = 5,                 /* 15 / 3 */
+  FDL_MAX_DETECTIONS = 32           /* capacity of the on-device NMS output per frame */
+};
+
+typedef struct fdl_detector fdl_detector;
+typedef struct fdl_landmark_model fdl_landmark_model;
+typedef struct fdl_iris_model fdl_iris_model;
+typedef struct fdl_net fdl_net;
+typedef struct fdl_pipeline fdl_pipeline;
+
+/* ---------------------------------------------------------------- library */
+FDL_API const char* fdl_last_error(void);
+FDL_API const char* fdl_version(void);
+/* Number of CUDA devices visible (0 when there is none; never an error). */
+FDL_API int fdl_device_count(void);
+/* Number of kernel launches issued by this library on the calling thread's handles since load
+ * (monotonic; used by bench.py for "gpu_launches"). */
+FDL_API uint64_t fdl_launch_count(void);
+
+/* ---------------------------------------------------------------- FaceDetection */
+/* FaceDetection::new(model_type, model_path) face_detection.rs:153-195.  `model_dir` is a
+ * DIRECTORY (NULL -> "./models") to which the per-variant file name is appended, as in the
+ * reference.  Parses the .tflite flatbuffer, plans fused kernels, uploads weights, builds the
+ * SSD anchor table (ssd_generate_anchors, :366-413) on the device. */
+FDL_API int fdl_detector_create(int model, const char* model_dir, int device, fdl_detector** out);
+FDL_API void fdl_detector_destroy(fdl_detector*);
+FDL_API int fdl_detector_input_size(const fdl_detector*);   /* S: 128 / 256 / 192 */
+FDL_API int fdl_detector_num_anchors(const fdl_detector*);  /* N: 896 / 2304 */
+/* Copy the [N,2] f32 anchor table (x,y centres) to `out_xy` (host). */
+FDL_API int fdl_detector_anchors(const fdl_detector*, float* out_xy, int cap_anchors);
+/* FaceDetection::infer(&self, &Mat, Option<Rect>) face_detection.rs:205-267:
+ * image_to_tensor (letterbox, range -1..1) -> network -> decode_boxes -> sigmoid -> threshold ->
+ * weighted NMS -> letterbox removal, all on the device.  `roi` may be NULL. */
+FDL_API int fdl_detector_infer(fdl_detector*, const fdl_image* image, const fdl_rect* roi,
+                               fdl_detection* out, int cap, int* n_out);
+/* Batched variant: `batch` images of identical size; out[i*cap .. i*cap+n_out[i]). */
+FDL_API int fdl_detector_infer_batch(fdl_detector*, const fdl_image* images, int batch,
+                                     fdl_detection* out, int cap_per_image, int* n_out);
+
+/* Stage-level entry points (parity protocol steps 2 and 3). */
+/* interpreter.invoke() face_detection.rs:235 on caller-provided input tensors: in = host f32
+ * [batch,S,S,3]; regressors = host f32 [batch,N,16]; classificators = host f32 [batch,N,1]. */
+FDL_API int fdl_detector_forward(fdl_detector*, const float* in, int batch, float* regressors, float* classificators);
+/* decode_boxes + get_sigmoid_score + convert_to_detections + non_maximum_suppression +
+ * detection_letterbox_removal (face_detection.rs:259-265) on caller-provided raw tensors.
+ * padding = (left, top, right, bottom) per image (f64, types.rs:10).  Optional outputs, per
+ * image with capacity cap_surv: survivor anchor indices in ascending order and, for each, the
+ * index of the output detection whose cluster absorbed it. */
+FDL_API int fdl_detector_postprocess(fdl_detector*, const float* regressors, const float* classificators, int batch,
+                                     const double* padding4, fdl_detection* out, int cap_per_image, int* n_out,
+                                     int32_t* survivor_anchor, int32_t* survivor_cluster, int cap_surv, int* n_surv);
+
+/* ---------------------------------------------------------------- FaceLandmark */
+/* FaceLandmark::new(model_path) face_landmark.rs:208-222: `model_file` is a FILE path
+ * (NULL -> "./models/face_landmark.tflite"). */
+FDL_API int fdl_landmark_create(const char* model_file, int device, fdl_landmark_model** out);
+FDL_API void fdl_landmark_destroy(fdl_landmark_model*);
+/* FaceLandmark::infer(&self, &Mat, Option<Rect>) face_landmark.rs:232-306.  *n_out = 468, or 0
+ * when sigmoid(face flag) <= 0.5 (:292-296).  `out` must hold 468 entries.  `face_flag_logit`
+ * (optional) receives the raw flag. */
+FDL_API int fdl_landmark_infer(fdl_landmark_model*, const fdl_image* image, const fdl_rect* roi,
+                               fdl_landmark* out, int* n_out, float* face_flag_logit);
+/* invoke() face_landmark.rs:265: in [batch,192,192,3] -> landmarks [batch,1404], flag [batch,1]. */
+FDL_API int fdl_landmark_forward(fdl_landmark_model*, const float* in, int batch, float* landmarks, float* flag);
+
+/* ---------------------------------------------------------------- IrisLandmark */
+/* IrisLandmark::new(model_path) iris_landmark.rs:142-156 (FILE path; NULL -> "./models/iris_landmark.tflite"). */
+FDL_API int fdl_iris_create(const char* model_file, int device, fdl_iris_model** out);
+FDL_API void fdl_iris_destroy(fdl_iris_model*);
+/* IrisLandmark::infer(&self, &Mat, Option<Rect>, Option<bool>) iris_landmark.rs:158-248.
+ * contour: 71 entries (the reference's IrisResults.contour), iris: 5 entries. */
+FDL_API int fdl_iris_infer(fdl_iris_model*, const fdl_image* image, const fdl_rect* roi, int is_right_eye,
+                           fdl_landmark* contour, fdl_landmark* iris);
+/* invoke() iris_landmark.rs:203: in [batch,64,64,3] -> contours [batch,213], iris [batch,15]. */
+FDL_API int fdl_iris_forward(fdl_iris_model*, const float* in, int batch, float* contours, float* iris);
+
+/* ---------------------------------------------------------------- free functions */
+/* face_detection_to_roi(Detection, (w,h), Option<SizeMode>) face_landmark.rs:180-198.
+ * Evaluated on `device` by the same device function the pipeline uses. */
+FDL_API int fdl_face_detection_to_roi(int device, const fdl_detection* det, int image_width, int image_height,
+                                      int size_mode, fdl_rect* out);
+/* iris_roi_from_face_landmarks(Vec<Landmark>, (w,h)) iris_landmark.rs:268-292; `n` must be 468
+ * (the reference indexes 33/133/362/263 and panics on short input; here FDL_ERR_INVALID). */
+FDL_API int fdl_iris_roi_from_face_landmarks(int device, const fdl_landmark* landmarks, int n, int image_width,
+                                             int image_height, fdl_rect* left, fdl_rect* right);
+/* image_to_tensor(...) transform.rs:188-309 (private in the reference; exported for parity
+ * step 1).  out_tensor: host f32 [out_h,out_w,3]; out_u8 (optional): the uint8 image just before
+ * normalisation; padding4: (left,top,right,bottom) f64. */
+FDL_API int fdl_image_to_tensor(int device, const fdl_image* image, const fdl_rect* roi, int out_w, int out_h,
+                                int keep_aspect_ratio, double range_min, double range_max, int flip_horizontal,
+                                float* out_tensor, uint8_t* out_u8, double* padding4);
+/* project_landmarks(...) transform.rs:351-432 (private in the reference; exported for parity
+ * step 3). raw: host f32 [n*3]; out: n entries. roi may be NULL. */
+FDL_API int fdl_project_landmarks(int device, const float* raw, int n, int tensor_w, int tensor_h, int image_w,
+                                  int image_h, const double* padding4, const fdl_rect* roi, int flip_horizontal,
+                                  fdl_landmark* out);
+
+/* ---------------------------------------------------------------- generic network handle */
+/* A planned .tflite graph on one device (what replaces the TFLite interpreter). */
+FDL_API int fdl_net_create(const char* tflite_file, int device, fdl_net** out);
+FDL_API void fdl_net_destroy(fdl_net*);
+FDL_API fdl_net* fdl_detector_net(fdl_detector*);
+FDL_API fdl_net* fdl_landmark_net(fdl_landmark_model*);
+FDL_API fdl_net* fdl_iris_net(fdl_iris_model*);
+FDL_API int fdl_net_num_outputs(const fdl_net*);
+/* Elements per batch item of the input (index -1) or of output `i`. */
+FDL_API int64_t fdl_net_io_elems(const fdl_net*, int i);
+/* Run on host tensors: in [batch, ...]; outs[i] host buffers of batch*fdl_net_io_elems(i). */
+FDL_API int fdl_net_forward(fdl_net*, const float* in, int batch, float* const* outs, int n_outs);
+/* Human-readable launch plan (one line per fused kernel step); returns bytes needed. Works
+ * without a GPU when the handle was created with device = -1 (plan-only, cannot run). */
+FDL_API int64_t fdl_net_describe(const fdl_net*, char* buf, int64_t cap);
+/* Number of kernel launches of one forward pass. */
+FDL_API int fdl_net_num_steps(const fdl_net*);
+/* Select the arithmetic of the pointwise (1x1) contractions: 0 = fp32 FFMA (default for parity
+ * checks), 1 = tensor-core split-TF32 (fp32-equivalent). */
+FDL_API int fdl_net_set_mode(fdl_net*, int mode);
+/* Device-resident benchmark hook: run `iters` forward passes at `batch` on the net's own input
+ * buffer (filled once from `in_or_null`, host f32, or left as is) and return the mean time per
+ * pass in milliseconds measured with CUDA events on the net's stream. */
+FDL_API int fdl_net_time_forward(fdl_net*, const float* in_or_null, int batch, int iters, float* ms_per_pass);
+
+/* ---------------------------------------------------------------- batched pipeline */
+/* detect -> face ROI -> landmark -> eye ROIs -> iris(L,R) exactly as lib.rs:20-40, for a batch of
+ * equally-sized frames, without leaving the device between stages. */
+typedef struct fdl_pipeline_config {
+  int32_t detector_model;   /* FDL_MODEL_* */
+  int32_t device;
+  int32_t max_batch;        /* frames per submit */
+  int32_t max_faces;        /* faces per frame carried into landmark/iris (lib.rs uses faces[0]) */
+  int32_t frame_width, frame_height;
+  int32_t run_landmarks;    /* 0: detection only (BASELINE config 2/3) */
+  int32_t run_iris;         /* 0: stop after landmarks (config 4) */
+  const char* model_dir;    /* directory holding the .tflite files; NULL -> "./models" */
+} fdl_pipeline_config;
+
+/* Per-face result record. */
+typedef struct fdl_face_result {
+  fdl_rect face_roi;                 /* face_detection_to_roi */
+  float face_flag_logit;             /* raw conv2d_30 output */
+  int32_t has_landmarks;             /* sigmoid(flag) > 0.5 */
+  float landmarks[FDL_NUM_FACE_LANDMARKS * 3];      /* projected, normalised (values of Vec<Landmark>) */
+  fdl_rect eye_roi[2];               /* [0] = left (33,133), [1] = right (362,263) */
+  float eye_contour[2][FDL_NUM_EYE_CONTOUR * 3];
+  float iris[2][FDL_NUM_IRIS * 3];
+} fdl_face_result;
+
+typedef struct fdl_frame_result {
+  int32_t n_detections;
+  int32_t n_faces;                   /* min(n_detections, max_faces) */
+  fdl_detection detections[FDL_MAX_DETECTIONS];
+} fdl_frame_result;
+
+FDL_API int fdl_pipeline_create(const fdl_pipeline_config* cfg, fdl_pipeline** out);
+FDL_API void fdl_pipeline_destroy(fdl_pipeline*);
+/* Synchronous: frames[n] (host or device) -> frame_results[n], face_results[n*max_faces]. */
+FDL_API int fdl_pipeline_run(fdl_pipeline*, const fdl_image* frames, int n, fdl_frame_result* frame_results,
+                             fdl_face_result* face_results);
+/* Asynchronous double-buffered form: submit enqueues H2D + all kernels + D2H on the pipeline's
+ * streams and returns a ticket; collect waits for that ticket and copies the results out.  Up to
+ * `fdl_pipeline_depth()` submits may be in flight. */
+FDL_API int fdl_pipeline_depth(const fdl_pipeline*);
+FDL_API int fdl_pipeline_submit(fdl_pipeline*, const fdl_image* frames, int n, int* ticket);
+FDL_API int fdl_pipeline_collect(fdl_pipeline*, int ticket, fdl_frame_result* frame_results,
+                                 fdl_face_result* face_results, int* n);
+/* Device time of the last collected ticket's kernels (excludes copies), milliseconds. */
+FDL_API float fdl_pipeline_last_device_ms(const fdl_pipeline*);
+/* Stage breakdown of the last collected ticket, ms: [0] H2D, [1] detector preprocess, [2] detector
+ * net, [3] SSD post-process, [4] face ROI + warp, [5] landmark net, [6] landmark post + eye warp,
+ * [7] iris net, [8] iris post, [9] D2H. */
+FDL_API int fdl_pipeline_stage_ms(const fdl_pipeline*, float* out10);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDL_H_ */

@@ -1,0 +1,13 @@
+"""B200-native detect -> landmark -> iris path of rs-face-detection-tflite.
+
+Python mirror (ctypes) of the reference's public API over the C ABI in include/fdl.h; all compute is in
+libfdl_b200.so (hand-written sm_100a CUDA).  See DESIGN.md / INTEGRATION.md.
+"""
+from .api import (BBox, Detection, FaceDetection, FaceDetectionModel, FaceIndex, FaceLandmark, FaceResult, FrameResult, IrisLandmark,
+                  IrisResults, Landmark, Net, Pipeline, Rect, SizeMode, device_count, face_detection_to_roi, image_to_tensor,
+                  iris_roi_from_face_landmarks, launch_count, project_landmarks)
+from ._lib import FdlError
+
+__all__ = ["BBox", "Detection", "FaceDetection", "FaceDetectionModel", "FaceIndex", "FaceLandmark", "FaceResult", "FrameResult",
+           "IrisLandmark", "IrisResults", "Landmark", "Net", "Pipeline", "Rect", "SizeMode", "FdlError", "device_count",
+           "face_detection_to_roi", "image_to_tensor", "iris_roi_from_face_landmarks", "launch_count", "project_landmarks"]

@@ -1,0 +1,556 @@
+"""Host-side mirror of the reference's public API over the C ABI (include/fdl.h).
+
+Names, argument meaning and error behaviour follow
+``face_detection_lite::{face_detection, face_landmark, iris_landmark, types}`` of the reference
+(paths relative to /root/reference/src/face_detection_lite/):
+
+* ``FaceDetectionModel``                       face_detection.rs:117-123
+* ``FaceDetection(model_type, model_path)``    face_detection.rs:153  (``model_path`` is a DIRECTORY)
+* ``FaceDetection.infer(image, roi)``          face_detection.rs:205
+* ``FaceLandmark(model_path).infer(image, roi)``          face_landmark.rs:208, :232  (FILE path)
+* ``IrisLandmark(model_path).infer(image, roi, is_right_eye)``  iris_landmark.rs:142, :158
+* ``face_detection_to_roi(detection, image_size, size_mode)``   face_landmark.rs:180
+* ``iris_roi_from_face_landmarks(landmarks, image_size)``       iris_landmark.rs:268
+* ``Rect``, ``BBox``, ``Detection``, ``Landmark``, ``IrisResults``  types.rs, iris_landmark.rs:115-129
+
+Images are ``numpy`` uint8 arrays ``[H, W, 3]`` in RGB order (the ``Mat`` the reference gets from
+``convert_image_to_mat``), or CUDA ``torch`` uint8 tensors of the same shape (no host copy).  Where the
+reference returns ``Err`` this module raises ``FdlError``.  Everything is computed by libfdl_b200.so on
+the GPU; this file only marshals arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import (CDetection, CFaceResult, CFrameResult, CImage, CLandmark, CPipelineConfig, CRect, FdlError, check, lib)
+
+NUM_LANDMARKS = 468          # face_landmark.rs:27
+ROI_SCALE = (1.5, 1.5)       # face_landmark.rs:30
+IRIS_ROI_SCALE = (2.3, 2.3)  # iris_landmark.rs:27
+
+
+class FaceDetectionModel(enum.IntEnum):  # face_detection.rs:117-123
+    FrontCamera = 0
+    BackCamera = 1
+    Short = 2
+    Full = 3
+    FullSparse = 4
+
+
+class SizeMode(enum.IntEnum):  # transform.rs:15-24
+    Default = 0
+    SquareLong = 1
+    SquareShort = 2
+
+
+class FaceIndex(enum.IntEnum):  # face_detection.rs:89-98
+    LeftEye = 0
+    RightEye = 1
+    NoseTip = 2
+    Mouth = 3
+    LeftEyeTragion = 4
+    RightEyeTragion = 5
+
+
+@dataclass
+class Rect:  # types.rs:24-37
+    x_center: float
+    y_center: float
+    width: float
+    height: float
+    rotation: float
+    normalized: bool
+
+    def _c(self) -> CRect:
+        return CRect(self.x_center, self.y_center, self.width, self.height, self.rotation, 1 if self.normalized else 0, 0)
+
+    @staticmethod
+    def _from(c: CRect) -> "Rect":
+        return Rect(c.x_center, c.y_center, c.width, c.height, c.rotation, bool(c.normalized))
+
+
+@dataclass
+class BBox:  # types.rs:99-174
+    xmin: float
+    ymin: float
+    xmax: float
+    ymax: float
+
+    @property
+    def width(self):
+        return self.xmax - self.xmin
+
+    @property
+    def height(self):
+        return self.ymax - self.ymin
+
+
+@dataclass
+class Landmark:  # types.rs:176-187
+    x: float
+    y: float
+    z: float
+
+
+@dataclass
+class Detection:  # types.rs:189-246
+    data: np.ndarray      # [8,2] float32: row0 (xmin,ymin), row1 (xmax,ymax), rows 2..7 keypoints
+    score: float
+    anchor: int = -1      # extension: SSD anchor index of the NMS cluster's top detection
+
+    def bbox(self) -> BBox:  # :215-221
+        d = self.data
+        return BBox(float(d[0, 0]), float(d[0, 1]), float(d[1, 0]), float(d[1, 1]))
+
+    def keypoint(self, k: int):  # :209-212
+        return float(self.data[k + 2, 0]), float(self.data[k + 2, 1])
+
+    def _c(self) -> CDetection:
+        c = CDetection()
+        flat = np.ascontiguousarray(self.data, np.float32).reshape(16)
+        for i in range(16):
+            c.data[i] = float(flat[i])
+        c.score = float(self.score)
+        c.anchor = int(self.anchor)
+        return c
+
+    @staticmethod
+    def _from(c: CDetection) -> "Detection":
+        return Detection(np.array(c.data[:], np.float32).reshape(8, 2), float(np.float32(c.score)), int(c.anchor))
+
+
+@dataclass
+class IrisResults:  # iris_landmark.rs:115-129
+    contour: list   # 71 Landmark
+    iris: list      # 5 Landmark
+
+    def eyeball_contour(self):  # iris_landmark.rs:126-128: first 15 contour points
+        return self.contour[:15]
+
+
+# ------------------------------------------------------------------------------------------------
+def _image(image):
+    """-> (CImage, keepalive).  numpy uint8 [H,W,3] (host) or CUDA torch uint8 tensor [H,W,3]."""
+    if isinstance(image, np.ndarray):
+        if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
+            raise FdlError(_lib.FDL_ERR_INVALID, "image must be uint8 [H,W,3] RGB")
+        if image.strides[2] != 1 or image.strides[1] != 3:
+            image = np.ascontiguousarray(image)
+        return CImage(image.ctypes.data, image.shape[1], image.shape[0], image.strides[0], _lib.MEM_HOST, 0), image
+    # torch tensor (host pinned or CUDA)
+    t = image
+    if t.dim() != 3 or t.shape[2] != 3 or str(t.dtype) != "torch.uint8":
+        raise FdlError(_lib.FDL_ERR_INVALID, "image must be uint8 [H,W,3] RGB")
+    if not t.is_contiguous():
+        t = t.contiguous()
+    mem = _lib.MEM_DEVICE if t.is_cuda else _lib.MEM_HOST
+    return CImage(t.data_ptr(), t.shape[1], t.shape[0], t.shape[1] * 3, mem, 0), t
+
+
+def _landmarks(buf, n):
+    return [Landmark(buf[i].x, buf[i].y, buf[i].z) for i in range(n)]
+
+
+class _Net:
+    """Introspection / stage-level access to a planned graph (parity protocol step 2)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def describe(self) -> str:
+        n = lib().fdl_net_describe(self._h, None, 0)
+        buf = C.create_string_buffer(int(n))
+        lib().fdl_net_describe(self._h, buf, n)
+        return buf.value.decode()
+
+    @property
+    def num_steps(self):
+        return lib().fdl_net_num_steps(self._h)
+
+    def set_mode(self, mode: int):
+        check(lib().fdl_net_set_mode(self._h, mode))
+
+    def forward(self, x: np.ndarray):
+        x = np.ascontiguousarray(x, np.float32)
+        b = x.shape[0]
+        assert x[0].size == lib().fdl_net_io_elems(self._h, -1), "input shape does not match the graph"
+        n_out = lib().fdl_net_num_outputs(self._h)
+        outs = [np.empty((b, lib().fdl_net_io_elems(self._h, i)), np.float32) for i in range(n_out)]
+        ptrs = (C.POINTER(C.c_float) * n_out)(*[o.ctypes.data_as(C.POINTER(C.c_float)) for o in outs])
+        check(lib().fdl_net_forward(self._h, x.ctypes.data_as(C.POINTER(C.c_float)), b, ptrs, n_out))
+        return outs
+
+    def time_forward(self, batch: int, iters: int, x: np.ndarray | None = None) -> float:
+        ms = C.c_float()
+        p = None
+        if x is not None:
+            x = np.ascontiguousarray(x, np.float32)
+            p = x.ctypes.data_as(C.POINTER(C.c_float))
+        check(lib().fdl_net_time_forward(self._h, p, batch, iters, C.byref(ms)))
+        return ms.value
+
+
+class Net(_Net):
+    """A stand-alone planned .tflite graph (``device=-1``: plan only, no GPU needed)."""
+
+    def __init__(self, tflite_file: str, device: int = 0):
+        h = C.c_void_p()
+        check(lib().fdl_net_create(os.fsencode(tflite_file), device, C.byref(h)))
+        super().__init__(h)
+
+    def close(self):
+        if self._h:
+            lib().fdl_net_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+class FaceDetection:
+    """BlazeFace detector.  ``FaceDetection::new`` / ``infer`` (face_detection.rs:153, :205)."""
+
+    def __init__(self, model_type: FaceDetectionModel = FaceDetectionModel.FrontCamera, model_path: str | None = None, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().fdl_detector_create(int(model_type), os.fsencode(model_path) if model_path else None, device, C.byref(self._h)))
+        self.model_type = FaceDetectionModel(int(model_type))
+        self.device = device
+        self.input_size = lib().fdl_detector_input_size(self._h)
+        self.num_anchors = lib().fdl_detector_num_anchors(self._h)
+        self.net = _Net(lib().fdl_detector_net(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fdl_detector_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def anchors(self) -> np.ndarray:
+        """ssd_generate_anchors (face_detection.rs:366-413): [N,2] float32."""
+        a = np.empty((self.num_anchors, 2), np.float32)
+        check(lib().fdl_detector_anchors(self._h, a.ctypes.data_as(C.POINTER(C.c_float)), self.num_anchors))
+        return a
+
+    def infer(self, image, roi: Rect | None = None, max_detections: int = 64):
+        img, _keep = _image(image)
+        out = (CDetection * max_detections)()
+        n = C.c_int()
+        croi = roi._c() if roi is not None else None
+        check(lib().fdl_detector_infer(self._h, C.byref(img), C.byref(croi) if croi is not None else None, out, max_detections, C.byref(n)))
+        return [Detection._from(out[i]) for i in range(n.value)]
+
+    def infer_batch(self, images, max_detections: int = 64):
+        imgs = [_image(i) for i in images]
+        arr = (CImage * len(imgs))(*[i[0] for i in imgs])
+        out = (CDetection * (max_detections * len(imgs)))()
+        n = (C.c_int * len(imgs))()
+        check(lib().fdl_detector_infer_batch(self._h, arr, len(imgs), out, max_detections, n))
+        return [[Detection._from(out[b * max_detections + i]) for i in range(n[b])] for b in range(len(imgs))]
+
+    # -- stage-level hooks (parity protocol) --
+    def forward(self, tensor: np.ndarray):
+        """interpreter.invoke() on caller tensors: [B,S,S,3] -> (regressors [B,N,16], classificators [B,N,1])."""
+        x = np.ascontiguousarray(tensor, np.float32)
+        b = x.shape[0]
+        reg = np.empty((b, self.num_anchors, 16), np.float32)
+        cls = np.empty((b, self.num_anchors, 1), np.float32)
+        fp = C.POINTER(C.c_float)
+        check(lib().fdl_detector_forward(self._h, x.ctypes.data_as(fp), b, reg.ctypes.data_as(fp), cls.ctypes.data_as(fp)))
+        return reg, cls
+
+    def postprocess(self, regressors, classificators, padding=(0.0, 0.0, 0.0, 0.0), max_detections: int = 64, trace: dict | None = None):
+        """decode -> sigmoid -> threshold -> weighted NMS -> letterbox removal on raw tensors of ONE frame
+        ([N,16], [N,1]) or a batch ([B,N,16], [B,N,1]); returns list[Detection] (or a list per frame)."""
+        reg = np.ascontiguousarray(regressors, np.float32)
+        cls = np.ascontiguousarray(classificators, np.float32)
+        single = reg.ndim == 2
+        reg = reg.reshape(-1, self.num_anchors, 16)
+        cls = cls.reshape(-1, self.num_anchors, 1)
+        b = reg.shape[0]
+        pad = np.ascontiguousarray(np.broadcast_to(np.asarray(padding, np.float64).reshape(-1, 4), (b, 4)))
+        out = (CDetection * (max_detections * b))()
+        n = (C.c_int * b)()
+        cap_s = self.num_anchors
+        sa = np.full((b, cap_s), -1, np.int32)
+        sc = np.full((b, cap_s), -1, np.int32)
+        ns = (C.c_int * b)()
+        fp = C.POINTER(C.c_float)
+        ip = C.POINTER(C.c_int32)
+        check(lib().fdl_detector_postprocess(self._h, reg.ctypes.data_as(fp), cls.ctypes.data_as(fp), b, pad.ctypes.data_as(C.POINTER(C.c_double)),
+                                             out, max_detections, n, sa.ctypes.data_as(ip), sc.ctypes.data_as(ip), cap_s, ns))
+        res = [[Detection._from(out[i * max_detections + k]) for k in range(n[i])] for i in range(b)]
+        if trace is not None:
+            trace["survivors"] = [sa[i, :ns[i]].tolist() for i in range(b)]
+            trace["survivor_cluster"] = [sc[i, :ns[i]].tolist() for i in range(b)]
+        return res[0] if single else res
+
+
+class FaceLandmark:
+    """FaceMesh-468.  ``FaceLandmark::new`` / ``infer`` (face_landmark.rs:208, :232)."""
+
+    def __init__(self, model_path: str | None = None, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().fdl_landmark_create(os.fsencode(model_path) if model_path else None, device, C.byref(self._h)))
+        self.device = device
+        self.net = _Net(lib().fdl_landmark_net(self._h))
+        self.last_face_flag = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fdl_landmark_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def infer(self, image, roi: Rect | None = None):
+        img, _keep = _image(image)
+        out = (CLandmark * NUM_LANDMARKS)()
+        n = C.c_int()
+        flag = C.c_float()
+        croi = roi._c() if roi is not None else None
+        check(lib().fdl_landmark_infer(self._h, C.byref(img), C.byref(croi) if croi is not None else None, out, C.byref(n), C.byref(flag)))
+        self.last_face_flag = flag.value
+        return _landmarks(out, n.value)
+
+    def forward(self, tensor: np.ndarray):
+        x = np.ascontiguousarray(tensor, np.float32)
+        b = x.shape[0]
+        lm = np.empty((b, 1404), np.float32)
+        fl = np.empty((b, 1), np.float32)
+        fp = C.POINTER(C.c_float)
+        check(lib().fdl_landmark_forward(self._h, x.ctypes.data_as(fp), b, lm.ctypes.data_as(fp), fl.ctypes.data_as(fp)))
+        return lm, fl
+
+
+class IrisLandmark:
+    """Iris model.  ``IrisLandmark::new`` / ``infer`` (iris_landmark.rs:142, :158)."""
+
+    def __init__(self, model_path: str | None = None, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().fdl_iris_create(os.fsencode(model_path) if model_path else None, device, C.byref(self._h)))
+        self.device = device
+        self.net = _Net(lib().fdl_iris_net(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fdl_iris_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def infer(self, image, roi: Rect | None = None, is_right_eye: bool | None = None) -> IrisResults:
+        img, _keep = _image(image)
+        contour = (CLandmark * _lib.NUM_EYE_CONTOUR)()
+        iris = (CLandmark * _lib.NUM_IRIS)()
+        croi = roi._c() if roi is not None else None
+        check(lib().fdl_iris_infer(self._h, C.byref(img), C.byref(croi) if croi is not None else None, 1 if is_right_eye else 0, contour, iris))
+        return IrisResults(_landmarks(contour, _lib.NUM_EYE_CONTOUR), _landmarks(iris, _lib.NUM_IRIS))
+
+    def forward(self, tensor: np.ndarray):
+        x = np.ascontiguousarray(tensor, np.float32)
+        b = x.shape[0]
+        eye = np.empty((b, 213), np.float32)
+        ir = np.empty((b, 15), np.float32)
+        fp = C.POINTER(C.c_float)
+        check(lib().fdl_iris_forward(self._h, x.ctypes.data_as(fp), b, eye.ctypes.data_as(fp), ir.ctypes.data_as(fp)))
+        return eye, ir
+
+
+# ------------------------------------------------------------------------------------------------
+def face_detection_to_roi(face_detection: Detection, image_size, size_mode: SizeMode | None = None, device: int = 0) -> Rect:
+    """face_landmark.rs:180-198.  ``image_size`` = (width, height)."""
+    out = CRect()
+    det = face_detection._c()
+    check(lib().fdl_face_detection_to_roi(device, C.byref(det), int(image_size[0]), int(image_size[1]),
+                                          -1 if size_mode is None else int(size_mode), C.byref(out)))
+    return Rect._from(out)
+
+
+def iris_roi_from_face_landmarks(face_landmarks, image_size, device: int = 0):
+    """iris_landmark.rs:268-292 -> (left_eye_roi, right_eye_roi)."""
+    n = len(face_landmarks)
+    arr = (CLandmark * max(n, 1))()
+    for i, l in enumerate(face_landmarks):
+        arr[i].x, arr[i].y, arr[i].z = l.x, l.y, l.z
+    left, right = CRect(), CRect()
+    check(lib().fdl_iris_roi_from_face_landmarks(device, arr, n, int(image_size[0]), int(image_size[1]), C.byref(left), C.byref(right)))
+    return Rect._from(left), Rect._from(right)
+
+
+def image_to_tensor(image, roi: Rect | None, output_size, keep_aspect_ratio: bool, output_range=(0.0, 1.0), flip_horizontal: bool = False,
+                    device: int = 0):
+    """transform.rs:188-309 (private in the reference; exposed for parity checks).
+    Returns (tensor f32 [h,w,3], padding (l,t,r,b), uint8 image before normalisation)."""
+    img, _keep = _image(image)
+    w, h = int(output_size[0]), int(output_size[1])
+    tensor = np.empty((h, w, 3), np.float32)
+    u8 = np.empty((h, w, 3), np.uint8)
+    pad = (C.c_double * 4)()
+    croi = roi._c() if roi is not None else None
+    check(lib().fdl_image_to_tensor(device, C.byref(img), C.byref(croi) if croi is not None else None, w, h, 1 if keep_aspect_ratio else 0,
+                                    float(output_range[0]), float(output_range[1]), 1 if flip_horizontal else 0,
+                                    tensor.ctypes.data_as(C.POINTER(C.c_float)), u8.ctypes.data_as(C.POINTER(C.c_uint8)), pad))
+    return tensor, tuple(pad), u8
+
+
+def project_landmarks(data, tensor_size, image_size, padding, roi: Rect | None, flip_horizontal: bool, device: int = 0):
+    """transform.rs:351-432 (private in the reference; exposed for parity checks) -> [K,3] float64."""
+    raw = np.ascontiguousarray(data, np.float32).reshape(-1)
+    n = raw.size // 3
+    out = (CLandmark * n)()
+    pad = (C.c_double * 4)(*[float(p) for p in padding])
+    croi = roi._c() if roi is not None else None
+    check(lib().fdl_project_landmarks(device, raw.ctypes.data_as(C.POINTER(C.c_float)), n, int(tensor_size[0]), int(tensor_size[1]),
+                                      int(image_size[0]), int(image_size[1]), pad, C.byref(croi) if croi is not None else None,
+                                      1 if flip_horizontal else 0, out))
+    return np.array([[out[i].x, out[i].y, out[i].z] for i in range(n)], np.float64)
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class FaceResult:
+    roi: Rect
+    face_flag_logit: float
+    landmarks: np.ndarray | None          # [468,3] float32 or None when the face flag gate rejected the crop
+    left_eye_roi: Rect | None
+    right_eye_roi: Rect | None
+    left_contour: np.ndarray | None       # [71,3]
+    left_iris: np.ndarray | None          # [5,3]
+    right_contour: np.ndarray | None
+    right_iris: np.ndarray | None
+
+
+@dataclass
+class FrameResult:
+    detections: list
+    faces: list
+
+
+class Pipeline:
+    """Batched detect -> landmark -> iris, the call sequence of lib.rs:20-40 for a batch of frames."""
+
+    def __init__(self, detector_model: FaceDetectionModel = FaceDetectionModel.BackCamera, frame_size=(1920, 1080), max_batch: int = 64,
+                 max_faces: int = 1, run_landmarks: bool = True, run_iris: bool = True, model_dir: str | None = None, device: int = 0):
+        self._h = C.c_void_p()
+        self._dir = os.fsencode(model_dir) if model_dir else None
+        cfg = CPipelineConfig(int(detector_model), device, max_batch, max_faces, int(frame_size[0]), int(frame_size[1]),
+                              1 if run_landmarks else 0, 1 if (run_iris and run_landmarks) else 0, self._dir)
+        check(lib().fdl_pipeline_create(C.byref(cfg), C.byref(self._h)))
+        self.max_batch, self.max_faces = max_batch, max_faces
+        self.frame_size = (int(frame_size[0]), int(frame_size[1]))
+        self.run_landmarks, self.run_iris = run_landmarks, run_iris and run_landmarks
+        self.device = device
+        self._frames = (CFrameResult * max_batch)()
+        self._faces = (CFaceResult * (max_batch * max_faces))()
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fdl_pipeline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _images(self, frames):
+        """frames: list of [H,W,3] arrays/tensors, or one [B,H,W,3] numpy array / torch tensor."""
+        keep = frames
+        if hasattr(frames, "shape") and len(frames.shape) == 4:
+            b, h, w, _ = frames.shape
+            if isinstance(frames, np.ndarray):
+                frames = np.ascontiguousarray(frames)
+                base, mem = frames.ctypes.data, _lib.MEM_HOST
+            else:
+                frames = frames.contiguous()
+                base, mem = frames.data_ptr(), (_lib.MEM_DEVICE if frames.is_cuda else _lib.MEM_HOST)
+            keep = frames
+            arr = (CImage * b)()
+            for i in range(b):
+                arr[i] = CImage(base + i * h * w * 3, w, h, w * 3, mem, 0)
+            return arr, b, keep
+        imgs = [_image(f) for f in frames]
+        arr = (CImage * len(imgs))(*[i[0] for i in imgs])
+        return arr, len(imgs), [i[1] for i in imgs]
+
+    def submit(self, frames) -> int:
+        arr, n, keep = self._images(frames)
+        t = C.c_int()
+        check(lib().fdl_pipeline_submit(self._h, arr, n, C.byref(t)))
+        self._keep[t.value] = keep
+        return t.value
+
+    def collect_raw(self, ticket: int) -> int:
+        """Waits for `ticket`; results stay in the ctypes arrays (self._frames / self._faces). Returns n."""
+        n = C.c_int()
+        check(lib().fdl_pipeline_collect(self._h, ticket, self._frames, self._faces, C.byref(n)))
+        self._keep.pop(ticket, None)
+        return n.value
+
+    def collect(self, ticket: int):
+        n = self.collect_raw(ticket)
+        return [self._frame(i) for i in range(n)]
+
+    def run(self, frames):
+        return self.collect(self.submit(frames))
+
+    def _frame(self, i) -> FrameResult:
+        fr = self._frames[i]
+        dets = [Detection._from(fr.detections[k]) for k in range(fr.n_detections)]
+        faces = []
+        if self.run_landmarks:
+            for f in range(fr.n_faces):
+                c = self._faces[i * self.max_faces + f]
+                has = bool(c.has_landmarks)
+                lm = np.array(c.landmarks[:], np.float32).reshape(-1, 3) if has else None
+                iris_ok = has and self.run_iris
+                g = lambda a: np.array(a[:], np.float32).reshape(-1, 3)
+                faces.append(FaceResult(Rect._from(c.face_roi), float(c.face_flag_logit), lm,
+                                        Rect._from(c.eye_roi[0]) if has else None, Rect._from(c.eye_roi[1]) if has else None,
+                                        g(c.eye_contour[0]) if iris_ok else None, g(c.iris[0]) if iris_ok else None,
+                                        g(c.eye_contour[1]) if iris_ok else None, g(c.iris[1]) if iris_ok else None))
+        return FrameResult(dets, faces)
+
+    @property
+    def last_device_ms(self) -> float:
+        return lib().fdl_pipeline_last_device_ms(self._h)
+
+    @property
+    def stage_ms(self):
+        out = (C.c_float * 10)()
+        check(lib().fdl_pipeline_stage_ms(self._h, out))
+        return list(out)
+
+
+def device_count() -> int:
+    return lib().fdl_device_count()
+
+
+def launch_count() -> int:
+    return int(lib().fdl_launch_count())

@@ -1,0 +1,75 @@
+// device_util.h -- small RAII helpers for device / pinned buffers and frame staging.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <string>
+
+#include "fdl_status.h"
+
+namespace fdl {
+
+// Grow-only device buffer.
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) { cudaDeviceSynchronize(); cudaFree(p); p = nullptr; cap = 0; }
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+};
+
+// Grow-only pinned host buffer.
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  ~PinBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) { cudaDeviceSynchronize(); cudaFreeHost(p); p = nullptr; cap = 0; }
+    cudaError_t e = cudaHostAlloc(&p, n * sizeof(T), cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+};
+
+// Copies `n` equally-sized images (host or device) into one contiguous device buffer
+// [n, height, width*3] on `stream`.  Returns FDL_OK or an error code (message set).
+inline int stage_frames(const fdl_image* images, int n, DevBuf<uint8_t>* dst, cudaStream_t stream, int* w_out, int* h_out) {
+  if (!images || n <= 0) return set_error(FDL_ERR_INVALID, "no images given");
+  const int w = images[0].width, h = images[0].height;
+  if (w <= 0 || h <= 0) return set_error(FDL_ERR_INVALID, "image has non-positive size");
+  const size_t row = (size_t)w * 3, frame = row * (size_t)h;
+  for (int i = 0; i < n; ++i) {
+    if (!images[i].data) return set_error(FDL_ERR_INVALID, "image data pointer is null");
+    if (images[i].width != w || images[i].height != h) return set_error(FDL_ERR_INVALID, "all images of a batch must have the same size");
+    if (images[i].row_stride != 0 && (size_t)images[i].row_stride < row) return set_error(FDL_ERR_INVALID, "row_stride smaller than width*3");
+  }
+  FDL_CUDA_TRY(dst->reserve(frame * (size_t)n));
+  // coalesce runs of frames that are contiguous in the caller's memory into one copy
+  int i = 0;
+  while (i < n) {
+    const size_t stride = images[i].row_stride ? (size_t)images[i].row_stride : row;
+    const cudaMemcpyKind kind = images[i].mem == FDL_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    int j = i + 1;
+    if (stride == row) {
+      while (j < n && images[j].mem == images[i].mem && (images[j].row_stride == 0 || (size_t)images[j].row_stride == row) &&
+             images[j].data == images[i].data + (size_t)(j - i) * frame)
+        ++j;
+      FDL_CUDA_TRY(cudaMemcpyAsync(dst->p + (size_t)i * frame, images[i].data, frame * (size_t)(j - i), kind, stream));
+    } else {
+      FDL_CUDA_TRY(cudaMemcpy2DAsync(dst->p + (size_t)i * frame, row, images[i].data, stride, row, (size_t)h, kind, stream));
+    }
+    i = j;
+  }
+  *w_out = w; *h_out = h;
+  return FDL_OK;
+}
+
+}  // namespace fdl

@@ -1,0 +1,640 @@
+// fdl_api.cu -- the C ABI of include/fdl.h: handles, single-stage entry points, free functions.
+// (The batched pipeline lives in pipeline.cu.)
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "device_util.h"
+#include "fdl_status.h"
+#include "net.h"
+#include "prepost_kernels.cuh"
+
+namespace fdl {
+
+static thread_local std::string g_last_error;
+int set_error(int code, const std::string& msg) { g_last_error = msg; return code; }
+void clear_error() { g_last_error.clear(); }
+unsigned long long launch_count_value();
+
+// face_detection.rs:125-129
+static const char* detector_file(int model) {
+  switch (model) {
+    case FDL_MODEL_FRONT_CAMERA: return "face_detection_front.tflite";
+    case FDL_MODEL_BACK_CAMERA: return "face_detection_back.tflite";
+    case FDL_MODEL_SHORT: return "face_detection_short_range.tflite";
+    case FDL_MODEL_FULL: return "face_detection_full_range.tflite";
+    case FDL_MODEL_FULL_SPARSE: return "face_detection_full_range_sparse.tflite";
+    default: return nullptr;
+  }
+}
+
+static int check_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return set_error(FDL_ERR_CUDA, std::string("no CUDA device available (this library has no CPU fallback): ") +
+                                       (e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e)));
+  if (device < 0 || device >= n) return set_error(FDL_ERR_INVALID, "device index out of range");
+  FDL_CUDA_TRY(cudaSetDevice(device));
+  return FDL_OK;
+}
+
+}  // namespace fdl
+
+using namespace fdl;
+
+// ---------------------------------------------------------------------------------------------
+struct fdl_net {
+  Net* net = nullptr;
+  bool owned = true;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+};
+
+struct fdl_detector {
+  fdl_net nh;
+  int model = 0, device = 0;
+  int S = 0, N = 0;
+  SsdOptions opt{};
+  cudaStream_t stream = nullptr;
+  DevBuf<float> anchors;
+  DevBuf<uint8_t> frames;
+  DevBuf<I2TParams> params;
+  DevBuf<fdl_rect> rois;
+  DevBuf<fdl_detection> dets;
+  DevBuf<int> counts;      // [2B]: clamped count, total count
+  DevBuf<double> padding;
+  DevBuf<float> raw_reg, raw_cls;
+  DevBuf<int32_t> surv;    // [2*B*cap]
+  DevBuf<int> nsurv;
+};
+
+struct fdl_landmark_model {
+  fdl_net nh;
+  int device = 0, S = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf<uint8_t> frames;
+  DevBuf<I2TParams> params;
+  DevBuf<fdl_rect> rois;
+  DevBuf<float> out;   // projected landmarks
+  DevBuf<int> flags;
+};
+
+struct fdl_iris_model {
+  fdl_net nh;
+  int device = 0, S = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf<uint8_t> frames;
+  DevBuf<I2TParams> params;
+  DevBuf<fdl_rect> rois;
+  DevBuf<float> out;
+};
+
+extern "C" {
+
+const char* fdl_last_error(void) { return g_last_error.c_str(); }
+const char* fdl_version(void) { return "fdl-b200 0.1 (sm_100a)"; }
+int fdl_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+uint64_t fdl_launch_count(void) { return launch_count_value(); }
+
+// ------------------------------------------------------------------------------------------ net
+static int net_forward_host(Net* net, cudaStream_t stream, const float* in, int batch, float* const* outs, int n_outs) {
+  if (!net || !in || batch <= 0 || !outs) return set_error(FDL_ERR_INVALID, "bad arguments");
+  if (n_outs != net->num_outputs()) return set_error(FDL_ERR_INVALID, "wrong number of output buffers");
+  std::string err;
+  FDL_CUDA_TRY(cudaSetDevice(net->device() < 0 ? 0 : net->device()));
+  if (!net->reserve(batch, &err)) return set_error(FDL_ERR_CUDA, err);
+  TView iv = net->input_view(batch);
+  FDL_CUDA_TRY(cudaMemcpyAsync(iv.p, in, (size_t)batch * net->in_elems() * sizeof(float), cudaMemcpyHostToDevice, stream));
+  FDL_CUDA_TRY(net->forward(batch, stream));
+  for (int i = 0; i < n_outs; ++i) {
+    if (!outs[i]) continue;
+    TView ov = net->output_view(i, batch);
+    // outputs are root buffers: [batch, elems] contiguous
+    FDL_CUDA_TRY(cudaMemcpyAsync(outs[i], ov.p, (size_t)batch * net->out_elems(i) * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  }
+  FDL_CUDA_TRY(cudaStreamSynchronize(stream));
+  return FDL_OK;
+}
+
+int fdl_net_create(const char* tflite_file, int device, fdl_net** out) {
+  if (!tflite_file || !out) return set_error(FDL_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (device >= 0) { int rc = check_device(device); if (rc) return rc; }
+  std::string err; int code = FDL_ERR_INTERNAL;
+  Net* n = Net::create(tflite_file, device, &err, &code);
+  if (!n) return set_error(code, err);
+  fdl_net* h = new fdl_net();
+  h->net = n; h->owned = true;
+  if (device >= 0) {
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete n; delete h; return set_error(FDL_ERR_CUDA, cudaGetErrorString(e)); }
+    h->own_stream = true;
+  }
+  *out = h;
+  return FDL_OK;
+}
+void fdl_net_destroy(fdl_net* h) {
+  if (!h) return;
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (h->owned) delete h->net;
+  delete h;
+}
+fdl_net* fdl_detector_net(fdl_detector* d) { return d ? &d->nh : nullptr; }
+fdl_net* fdl_landmark_net(fdl_landmark_model* m) { return m ? &m->nh : nullptr; }
+fdl_net* fdl_iris_net(fdl_iris_model* m) { return m ? &m->nh : nullptr; }
+int fdl_net_num_outputs(const fdl_net* h) { return h && h->net ? h->net->num_outputs() : 0; }
+int64_t fdl_net_io_elems(const fdl_net* h, int i) {
+  if (!h || !h->net) return 0;
+  if (i < 0) return h->net->in_elems();
+  return i < h->net->num_outputs() ? h->net->out_elems(i) : 0;
+}
+int fdl_net_forward(fdl_net* h, const float* in, int batch, float* const* outs, int n_outs) {
+  if (!h || !h->net) return set_error(FDL_ERR_INVALID, "null handle");
+  return net_forward_host(h->net, h->stream, in, batch, outs, n_outs);
+}
+int64_t fdl_net_describe(const fdl_net* h, char* buf, int64_t cap) {
+  if (!h || !h->net) return 0;
+  std::string s = h->net->plan().describe();
+  if (buf && cap > 0) {
+    size_t n = s.size() < (size_t)cap - 1 ? s.size() : (size_t)cap - 1;
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)s.size() + 1;
+}
+int fdl_net_num_steps(const fdl_net* h) { return h && h->net ? (int)h->net->plan().steps.size() : 0; }
+int fdl_net_set_mode(fdl_net* h, int mode) {
+  if (!h || !h->net) return set_error(FDL_ERR_INVALID, "null handle");
+  if (mode != 0 && mode != 1) return set_error(FDL_ERR_INVALID, "mode must be 0 (fp32) or 1 (split-TF32 tensor cores)");
+  h->net->set_mode(mode);
+  return FDL_OK;
+}
+int fdl_net_time_forward(fdl_net* h, const float* in, int batch, int iters, float* ms_per_pass) {
+  if (!h || !h->net || batch <= 0 || iters <= 0 || !ms_per_pass) return set_error(FDL_ERR_INVALID, "bad arguments");
+  Net* net = h->net;
+  std::string err;
+  if (net->device() < 0) return set_error(FDL_ERR_CUDA, "plan-only handle cannot run");
+  FDL_CUDA_TRY(cudaSetDevice(net->device()));
+  if (!net->reserve(batch, &err)) return set_error(FDL_ERR_CUDA, err);
+  TView iv = net->input_view(batch);
+  if (in) FDL_CUDA_TRY(cudaMemcpyAsync(iv.p, in, (size_t)batch * net->in_elems() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  FDL_CUDA_TRY(net->forward(batch, h->stream));  // warm-up
+  cudaEvent_t e0, e1;
+  FDL_CUDA_TRY(cudaEventCreate(&e0));
+  FDL_CUDA_TRY(cudaEventCreate(&e1));
+  FDL_CUDA_TRY(cudaEventRecord(e0, h->stream));
+  for (int i = 0; i < iters; ++i) FDL_CUDA_TRY(net->forward(batch, h->stream));
+  FDL_CUDA_TRY(cudaEventRecord(e1, h->stream));
+  FDL_CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  FDL_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_pass = ms / (float)iters;
+  return FDL_OK;
+}
+
+// ------------------------------------------------------------------------------------- detector
+int fdl_detector_create(int model, const char* model_dir, int device, fdl_detector** out) {
+  if (!out) return set_error(FDL_ERR_INVALID, "null argument");
+  *out = nullptr;
+  const char* file = detector_file(model);
+  SsdOptions opt;
+  if (!file || !ssd_options_for(model, &opt)) return set_error(FDL_ERR_MODEL, "unsupported model type");   // face_detection.rs:184
+  if (model == FDL_MODEL_FULL_SPARSE)
+    return set_error(FDL_ERR_MODEL, "unsupported model type: FullSparse needs DENSIFY/DEPTH_TO_SPACE, outside the B200 hot path");
+  int rc = check_device(device);
+  if (rc) return rc;
+  std::string path = std::string(model_dir ? model_dir : "./models") + "/" + file;
+  std::string err; int code = FDL_ERR_INTERNAL;
+  Net* net = Net::create(path, device, &err, &code);
+  if (!net) return set_error(code, err);
+  fdl_detector* d = new fdl_detector();
+  d->nh.net = net; d->nh.owned = true;
+  d->model = model; d->device = device; d->opt = opt;
+  d->S = net->plan().input.H;
+  d->N = ssd_num_anchors(opt);
+  auto bail = [&](int c, const std::string& m) { fdl_detector_destroy(d); return set_error(c, m); };
+  if (net->num_outputs() != 2 || net->plan().input.W != d->S || d->S != opt.input_size || net->out_elems(0) != (int64_t)d->N * 16 ||
+      net->out_elems(1) != d->N)
+    return bail(FDL_ERR_MODEL, "incompatible model: expected [1,S,S,3] -> regressors [1,N,16], classificators [1,N,1]");
+  cudaError_t e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = d->anchors.reserve((size_t)d->N * 2);
+  if (e == cudaSuccess) e = launch_anchors(opt, d->anchors.p, d->N, d->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+  if (e != cudaSuccess) return bail(FDL_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+  d->nh.stream = d->stream;
+  *out = d;
+  return FDL_OK;
+}
+void fdl_detector_destroy(fdl_detector* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  if (d->stream) { cudaStreamSynchronize(d->stream); cudaStreamDestroy(d->stream); }
+  delete d->nh.net;
+  delete d;
+}
+int fdl_detector_input_size(const fdl_detector* d) { return d ? d->S : 0; }
+int fdl_detector_num_anchors(const fdl_detector* d) { return d ? d->N : 0; }
+int fdl_detector_anchors(const fdl_detector* d, float* out_xy, int cap_anchors) {
+  if (!d || !out_xy) return set_error(FDL_ERR_INVALID, "null argument");
+  if (cap_anchors < d->N) return set_error(FDL_ERR_CAPACITY, "anchor buffer too small");
+  FDL_CUDA_TRY(cudaSetDevice(d->device));
+  FDL_CUDA_TRY(cudaMemcpy(out_xy, d->anchors.p, (size_t)d->N * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+  return FDL_OK;
+}
+
+// shared tail: SSD post-processing on device tensors + copy-out
+static int detector_post(fdl_detector* d, const float* reg, long long reg_bs, const float* cls, long long cls_bs, int batch,
+                         const I2TParams* params, const double* d_padding, fdl_detection* out, int cap, int* n_out,
+                         int32_t* surv_anchor, int32_t* surv_cluster, int cap_surv, int* n_surv) {
+  int cap_dev = cap < 1 ? 1 : (cap > d->N ? d->N : cap);
+  FDL_CUDA_TRY(d->dets.reserve((size_t)batch * cap_dev));
+  FDL_CUDA_TRY(d->counts.reserve((size_t)batch * 2));
+  SsdPostArgs a;
+  a.reg = reg; a.reg_bstride = reg_bs; a.cls = cls; a.cls_bstride = cls_bs;
+  a.anchors = d->anchors.p; a.N = d->N; a.B = batch; a.scale = (float)d->S;
+  a.params = params; a.padding4 = d_padding;
+  a.det_base = reinterpret_cast<char*>(d->dets.p); a.det_stride = (long long)cap_dev * sizeof(fdl_detection);
+  a.ndet_base = reinterpret_cast<char*>(d->counts.p); a.ndet_stride = sizeof(int);
+  a.max_out = cap_dev; a.n_total = d->counts.p + batch;
+  if (surv_anchor && surv_cluster && cap_surv > 0) {
+    FDL_CUDA_TRY(d->surv.reserve((size_t)batch * cap_surv * 2));
+    FDL_CUDA_TRY(d->nsurv.reserve((size_t)batch));
+    a.surv_anchor = d->surv.p; a.surv_cluster = d->surv.p + (size_t)batch * cap_surv; a.cap_surv = cap_surv; a.n_surv = d->nsurv.p;
+  }
+  FDL_CUDA_TRY(launch_ssd_postprocess(a, d->stream));
+  std::vector<int> counts((size_t)batch * 2);
+  std::vector<fdl_detection> dets((size_t)batch * cap_dev);
+  FDL_CUDA_TRY(cudaMemcpyAsync(counts.data(), d->counts.p, counts.size() * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  FDL_CUDA_TRY(cudaMemcpyAsync(dets.data(), d->dets.p, dets.size() * sizeof(fdl_detection), cudaMemcpyDeviceToHost, d->stream));
+  if (a.surv_anchor) {
+    FDL_CUDA_TRY(cudaMemcpyAsync(surv_anchor, a.surv_anchor, (size_t)batch * cap_surv * sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream));
+    FDL_CUDA_TRY(cudaMemcpyAsync(surv_cluster, a.surv_cluster, (size_t)batch * cap_surv * sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream));
+    if (n_surv) FDL_CUDA_TRY(cudaMemcpyAsync(n_surv, d->nsurv.p, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  }
+  FDL_CUDA_TRY(cudaStreamSynchronize(d->stream));
+  bool overflow = false;
+  for (int b = 0; b < batch; ++b) {
+    int n = counts[b], total = counts[batch + b];
+    if (total > cap) overflow = true;
+    n_out[b] = total;
+    if (out) for (int k = 0; k < n && k < cap; ++k) out[(size_t)b * cap + k] = dets[(size_t)b * cap_dev + k];
+  }
+  if (overflow) return set_error(FDL_ERR_CAPACITY, "more detections than the output capacity (n_out holds the required counts)");
+  return FDL_OK;
+}
+
+static int detector_infer_impl(fdl_detector* d, const fdl_image* images, int batch, const fdl_rect* roi, fdl_detection* out, int cap,
+                               int* n_out) {
+  if (!d || !images || !n_out || batch <= 0 || cap < 0 || (cap > 0 && !out)) return set_error(FDL_ERR_INVALID, "bad arguments");
+  FDL_CUDA_TRY(cudaSetDevice(d->device));
+  int w, h;
+  int rc = stage_frames(images, batch, &d->frames, d->stream, &w, &h);
+  if (rc) return rc;
+  Net* net = d->nh.net;
+  std::string err;
+  if (!net->reserve(batch, &err)) return set_error(FDL_ERR_CUDA, err);
+  FDL_CUDA_TRY(d->params.reserve((size_t)batch));
+  const fdl_rect* d_roi = nullptr;
+  if (roi) {
+    FDL_CUDA_TRY(d->rois.reserve((size_t)batch));
+    std::vector<fdl_rect> r((size_t)batch, *roi);
+    FDL_CUDA_TRY(cudaMemcpyAsync(d->rois.p, r.data(), r.size() * sizeof(fdl_rect), cudaMemcpyHostToDevice, d->stream));
+    FDL_CUDA_TRY(cudaStreamSynchronize(d->stream));
+    d_roi = d->rois.p;
+  }
+  // image_to_tensor(image, roi, (S,S), keep_aspect_ratio=true, (-1,1), flip=false)  face_detection.rs:219
+  FDL_CUDA_TRY(launch_i2t_setup(d_roi, nullptr, nullptr, batch, w, h, d->S, d->S, 1, -1.0, 1.0, 0, d->params.p, nullptr, d->stream));
+  TView iv = net->input_view(batch);
+  FDL_CUDA_TRY(launch_i2t(d->frames.p, (long long)w * 3 * h, (long long)w * 3, d->params.p, batch, d->S, d->S, iv.p, iv.bstride, nullptr,
+                          nullptr, d->stream));
+  FDL_CUDA_TRY(net->forward(batch, d->stream));
+  TView reg = net->output_view(0, batch), cls = net->output_view(1, batch);
+  return detector_post(d, reg.p, reg.bstride, cls.p, cls.bstride, batch, d->params.p, nullptr, out, cap, n_out, nullptr, nullptr, 0, nullptr);
+}
+
+int fdl_detector_infer(fdl_detector* d, const fdl_image* image, const fdl_rect* roi, fdl_detection* out, int cap, int* n_out) {
+  return detector_infer_impl(d, image, 1, roi, out, cap, n_out);
+}
+int fdl_detector_infer_batch(fdl_detector* d, const fdl_image* images, int batch, fdl_detection* out, int cap_per_image, int* n_out) {
+  return detector_infer_impl(d, images, batch, nullptr, out, cap_per_image, n_out);
+}
+int fdl_detector_forward(fdl_detector* d, const float* in, int batch, float* regressors, float* classificators) {
+  if (!d) return set_error(FDL_ERR_INVALID, "null handle");
+  float* outs[2] = {regressors, classificators};
+  return net_forward_host(d->nh.net, d->stream, in, batch, outs, 2);
+}
+int fdl_detector_postprocess(fdl_detector* d, const float* regressors, const float* classificators, int batch, const double* padding4,
+                             fdl_detection* out, int cap_per_image, int* n_out, int32_t* survivor_anchor, int32_t* survivor_cluster,
+                             int cap_surv, int* n_surv) {
+  if (!d || !regressors || !classificators || batch <= 0 || !n_out) return set_error(FDL_ERR_INVALID, "bad arguments");
+  FDL_CUDA_TRY(cudaSetDevice(d->device));
+  FDL_CUDA_TRY(d->raw_reg.reserve((size_t)batch * d->N * 16));
+  FDL_CUDA_TRY(d->raw_cls.reserve((size_t)batch * d->N));
+  FDL_CUDA_TRY(cudaMemcpyAsync(d->raw_reg.p, regressors, (size_t)batch * d->N * 16 * sizeof(float), cudaMemcpyHostToDevice, d->stream));
+  FDL_CUDA_TRY(cudaMemcpyAsync(d->raw_cls.p, classificators, (size_t)batch * d->N * sizeof(float), cudaMemcpyHostToDevice, d->stream));
+  const double* d_pad = nullptr;
+  if (padding4) {
+    FDL_CUDA_TRY(d->padding.reserve((size_t)batch * 4));
+    FDL_CUDA_TRY(cudaMemcpyAsync(d->padding.p, padding4, (size_t)batch * 4 * sizeof(double), cudaMemcpyHostToDevice, d->stream));
+    d_pad = d->padding.p;
+  }
+  return detector_post(d, d->raw_reg.p, (long long)d->N * 16, d->raw_cls.p, d->N, batch, nullptr, d_pad, out, cap_per_image, n_out,
+                       survivor_anchor, survivor_cluster, cap_surv, n_surv);
+}
+
+// ------------------------------------------------------------------------------------- landmark
+int fdl_landmark_create(const char* model_file, int device, fdl_landmark_model** out) {
+  if (!out) return set_error(FDL_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int rc = check_device(device);
+  if (rc) return rc;
+  std::string err; int code = FDL_ERR_INTERNAL;
+  Net* net = Net::create(model_file ? model_file : "./models/face_landmark.tflite", device, &err, &code);   // face_landmark.rs:211-215
+  if (!net) return set_error(code, err);
+  fdl_landmark_model* m = new fdl_landmark_model();
+  m->nh.net = net; m->device = device; m->S = net->plan().input.H;
+  // face_landmark.rs:244-247: last output dim must hold NUM_DIMS * NUM_LANDMARKS values
+  if (net->num_outputs() != 2 || net->out_elems(0) < 3 * FDL_NUM_FACE_LANDMARKS || net->plan().input.W != m->S) {
+    fdl_landmark_destroy(m);
+    return set_error(FDL_ERR_MODEL, "incompatible model: landmark output smaller than 1404 values");
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { fdl_landmark_destroy(m); return set_error(FDL_ERR_CUDA, cudaGetErrorString(e)); }
+  m->nh.stream = m->stream;
+  *out = m;
+  return FDL_OK;
+}
+void fdl_landmark_destroy(fdl_landmark_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+  delete m->nh.net;
+  delete m;
+}
+
+__global__ void flag_gate_kernel(const float* flag, int* has) {
+  // face_landmark.rs:292-296
+  *has = !(sigmoid_f32(*flag) <= 0.5f) ? 1 : 0;
+}
+
+int fdl_landmark_infer(fdl_landmark_model* m, const fdl_image* image, const fdl_rect* roi, fdl_landmark* out, int* n_out,
+                       float* face_flag_logit) {
+  if (!m || !image || !out || !n_out) return set_error(FDL_ERR_INVALID, "bad arguments");
+  FDL_CUDA_TRY(cudaSetDevice(m->device));
+  int w, h;
+  int rc = stage_frames(image, 1, &m->frames, m->stream, &w, &h);
+  if (rc) return rc;
+  Net* net = m->nh.net;
+  std::string err;
+  if (!net->reserve(1, &err)) return set_error(FDL_ERR_CUDA, err);
+  FDL_CUDA_TRY(m->params.reserve(1));
+  FDL_CUDA_TRY(m->rois.reserve(1));
+  FDL_CUDA_TRY(m->out.reserve(3 * FDL_NUM_FACE_LANDMARKS));
+  FDL_CUDA_TRY(m->flags.reserve(2));
+  const fdl_rect* d_roi = nullptr;
+  if (roi) {
+    FDL_CUDA_TRY(cudaMemcpyAsync(m->rois.p, roi, sizeof(fdl_rect), cudaMemcpyHostToDevice, m->stream));
+    FDL_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    d_roi = m->rois.p;
+  }
+  // image_to_tensor(image, roi, (S,S), keep_aspect_ratio=false, (0,1), flip=false)  face_landmark.rs:250
+  FDL_CUDA_TRY(launch_i2t_setup(d_roi, nullptr, nullptr, 1, w, h, m->S, m->S, 0, 0.0, 1.0, 0, m->params.p, nullptr, m->stream));
+  TView iv = net->input_view(1);
+  FDL_CUDA_TRY(launch_i2t(m->frames.p, (long long)w * 3 * h, (long long)w * 3, m->params.p, 1, m->S, m->S, iv.p, iv.bstride, nullptr, nullptr,
+                          m->stream));
+  FDL_CUDA_TRY(net->forward(1, m->stream));
+  TView raw = net->output_view(0, 1), flag = net->output_view(1, 1);
+  // the reference takes the LAST element of the flag tensor (face_landmark.rs:292-293)
+  const float* flag_last = flag.p + net->out_elems(1) - 1;
+  flag_gate_kernel<<<1, 1, 0, m->stream>>>(flag_last, m->flags.p);
+  FDL_CUDA_TRY(cudaGetLastError());
+  const double* d_pad = reinterpret_cast<const double*>(reinterpret_cast<const char*>(m->params.p) + offsetof(I2TParams, pad));
+  FDL_CUDA_TRY(launch_project(raw.p, FDL_NUM_FACE_LANDMARKS, m->S, m->S, w, h, d_pad, d_roi, 0, m->out.p, m->stream));
+  std::vector<float> pts(3 * FDL_NUM_FACE_LANDMARKS);
+  int has = 0; float logit = 0.f; I2TParams P;
+  FDL_CUDA_TRY(cudaMemcpyAsync(pts.data(), m->out.p, pts.size() * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  FDL_CUDA_TRY(cudaMemcpyAsync(&has, m->flags.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  FDL_CUDA_TRY(cudaMemcpyAsync(&logit, flag_last, sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  FDL_CUDA_TRY(cudaMemcpyAsync(&P, m->params.p, sizeof(I2TParams), cudaMemcpyDeviceToHost, m->stream));
+  FDL_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  if (!P.valid) return set_error(FDL_ERR_INVALID, "degenerate ROI: perspective transform is singular or empty");
+  if (face_flag_logit) *face_flag_logit = logit;
+  if (!has) { *n_out = 0; return FDL_OK; }
+  for (int k = 0; k < FDL_NUM_FACE_LANDMARKS; ++k) { out[k].x = pts[3 * k]; out[k].y = pts[3 * k + 1]; out[k].z = pts[3 * k + 2]; }
+  *n_out = FDL_NUM_FACE_LANDMARKS;
+  return FDL_OK;
+}
+int fdl_landmark_forward(fdl_landmark_model* m, const float* in, int batch, float* landmarks, float* flag) {
+  if (!m) return set_error(FDL_ERR_INVALID, "null handle");
+  float* outs[2] = {landmarks, flag};
+  return net_forward_host(m->nh.net, m->stream, in, batch, outs, 2);
+}
+
+// ----------------------------------------------------------------------------------------- iris
+int fdl_iris_create(const char* model_file, int device, fdl_iris_model** out) {
+  if (!out) return set_error(FDL_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int rc = check_device(device);
+  if (rc) return rc;
+  std::string err; int code = FDL_ERR_INTERNAL;
+  Net* net = Net::create(model_file ? model_file : "./models/iris_landmark.tflite", device, &err, &code);   // iris_landmark.rs:145-149
+  if (!net) return set_error(code, err);
+  fdl_iris_model* m = new fdl_iris_model();
+  m->nh.net = net; m->device = device; m->S = net->plan().input.H;
+  // iris_landmark.rs:172-184
+  if (net->num_outputs() != 2 || net->out_elems(0) != 3 * FDL_NUM_EYE_CONTOUR || net->out_elems(1) != 3 * FDL_NUM_IRIS ||
+      net->plan().input.W != m->S) {
+    fdl_iris_destroy(m);
+    return set_error(FDL_ERR_MODEL, "incompatible model: expected outputs [1,213] and [1,15]");
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { fdl_iris_destroy(m); return set_error(FDL_ERR_CUDA, cudaGetErrorString(e)); }
+  m->nh.stream = m->stream;
+  *out = m;
+  return FDL_OK;
+}
+void fdl_iris_destroy(fdl_iris_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+  delete m->nh.net;
+  delete m;
+}
+int fdl_iris_infer(fdl_iris_model* m, const fdl_image* image, const fdl_rect* roi, int is_right_eye, fdl_landmark* contour,
+                   fdl_landmark* iris) {
+  if (!m || !image || !contour || !iris) return set_error(FDL_ERR_INVALID, "bad arguments");
+  FDL_CUDA_TRY(cudaSetDevice(m->device));
+  int w, h;
+  int rc = stage_frames(image, 1, &m->frames, m->stream, &w, &h);
+  if (rc) return rc;
+  Net* net = m->nh.net;
+  std::string err;
+  if (!net->reserve(1, &err)) return set_error(FDL_ERR_CUDA, err);
+  const int K = FDL_NUM_EYE_CONTOUR + FDL_NUM_IRIS;
+  FDL_CUDA_TRY(m->params.reserve(1));
+  FDL_CUDA_TRY(m->rois.reserve(1));
+  FDL_CUDA_TRY(m->out.reserve(3 * K));
+  const fdl_rect* d_roi = nullptr;
+  if (roi) {
+    FDL_CUDA_TRY(cudaMemcpyAsync(m->rois.p, roi, sizeof(fdl_rect), cudaMemcpyHostToDevice, m->stream));
+    FDL_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    d_roi = m->rois.p;
+  }
+  // image_to_tensor(image, roi, (S,S), keep_aspect_ratio=true, (0,1), flip=is_right_eye)  iris_landmark.rs:188-189
+  FDL_CUDA_TRY(launch_i2t_setup(d_roi, nullptr, nullptr, 1, w, h, m->S, m->S, 1, 0.0, 1.0, is_right_eye ? 1 : 0, m->params.p, nullptr,
+                                m->stream));
+  TView iv = net->input_view(1);
+  FDL_CUDA_TRY(launch_i2t(m->frames.p, (long long)w * 3 * h, (long long)w * 3, m->params.p, 1, m->S, m->S, iv.p, iv.bstride, nullptr, nullptr,
+                          m->stream));
+  FDL_CUDA_TRY(net->forward(1, m->stream));
+  TView eye = net->output_view(0, 1), ir = net->output_view(1, 1);
+  const double* d_pad = reinterpret_cast<const double*>(reinterpret_cast<const char*>(m->params.p) + offsetof(I2TParams, pad));
+  FDL_CUDA_TRY(launch_project(eye.p, FDL_NUM_EYE_CONTOUR, m->S, m->S, w, h, d_pad, d_roi, is_right_eye ? 1 : 0, m->out.p, m->stream));
+  FDL_CUDA_TRY(launch_project(ir.p, FDL_NUM_IRIS, m->S, m->S, w, h, d_pad, d_roi, is_right_eye ? 1 : 0, m->out.p + 3 * FDL_NUM_EYE_CONTOUR,
+                              m->stream));
+  std::vector<float> pts(3 * K);
+  I2TParams P;
+  FDL_CUDA_TRY(cudaMemcpyAsync(pts.data(), m->out.p, pts.size() * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+  FDL_CUDA_TRY(cudaMemcpyAsync(&P, m->params.p, sizeof(I2TParams), cudaMemcpyDeviceToHost, m->stream));
+  FDL_CUDA_TRY(cudaStreamSynchronize(m->stream));
+  if (!P.valid) return set_error(FDL_ERR_INVALID, "degenerate ROI: perspective transform is singular or empty");
+  for (int k = 0; k < FDL_NUM_EYE_CONTOUR; ++k) { contour[k].x = pts[3 * k]; contour[k].y = pts[3 * k + 1]; contour[k].z = pts[3 * k + 2]; }
+  for (int k = 0; k < FDL_NUM_IRIS; ++k) {
+    const float* q = &pts[3 * (FDL_NUM_EYE_CONTOUR + k)];
+    iris[k].x = q[0]; iris[k].y = q[1]; iris[k].z = q[2];
+  }
+  return FDL_OK;
+}
+int fdl_iris_forward(fdl_iris_model* m, const float* in, int batch, float* contours, float* iris) {
+  if (!m) return set_error(FDL_ERR_INVALID, "null handle");
+  float* outs[2] = {contours, iris};
+  return net_forward_host(m->nh.net, m->stream, in, batch, outs, 2);
+}
+
+// ------------------------------------------------------------------------------- free functions
+// Small per-call scratch; the work itself is one thread on the device (same code as the pipeline).
+struct Scratch {
+  void* p = nullptr;
+  size_t cap = 0;
+  int rc(size_t n) {
+    if (n <= cap) return FDL_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    FDL_CUDA_TRY(cudaMalloc(&p, n));
+    cap = n;
+    return FDL_OK;
+  }
+};
+
+int fdl_face_detection_to_roi(int device, const fdl_detection* det, int image_width, int image_height, int size_mode, fdl_rect* out) {
+  if (!det || !out) return set_error(FDL_ERR_INVALID, "null argument");
+  if (size_mode < FDL_SIZE_MODE_NONE || size_mode > FDL_SIZE_MODE_SQUARE_SHORT) return set_error(FDL_ERR_INVALID, "bad size mode");
+  int rc = check_device(device);
+  if (rc) return rc;
+  char* buf = nullptr;
+  FDL_CUDA_TRY(cudaMalloc(&buf, 256));
+  fdl_detection* d_det = reinterpret_cast<fdl_detection*>(buf);
+  fdl_rect* d_rect = reinterpret_cast<fdl_rect*>(buf + 128);
+  int* d_ok = reinterpret_cast<int*>(buf + 192);
+  cudaError_t e = cudaMemcpy(d_det, det, sizeof(fdl_detection), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_face_detection_to_roi(d_det, image_width, image_height, size_mode, d_rect, d_ok, 0);
+  int ok = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_rect, sizeof(fdl_rect), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(buf);
+  if (e != cudaSuccess) return set_error(FDL_ERR_CUDA, cudaGetErrorString(e));
+  if (!ok) return set_error(FDL_ERR_INVALID, "bbox must be normalized");   // transform.rs:52
+  return FDL_OK;
+}
+
+int fdl_iris_roi_from_face_landmarks(int device, const fdl_landmark* landmarks, int n, int image_width, int image_height, fdl_rect* left,
+                                     fdl_rect* right) {
+  if (!landmarks || !left || !right) return set_error(FDL_ERR_INVALID, "null argument");
+  if (n <= 362) return set_error(FDL_ERR_INVALID, "landmarks must contain the 468 face landmarks (indices 33,133,362,263 are read)");
+  int rc = check_device(device);
+  if (rc) return rc;
+  const int idx[4] = {33, 133, 362, 263};   // iris_landmark.rs:29-35
+  double xy[8];
+  for (int k = 0; k < 4; ++k) { xy[2 * k] = landmarks[idx[k]].x; xy[2 * k + 1] = landmarks[idx[k]].y; }
+  char* buf = nullptr;
+  FDL_CUDA_TRY(cudaMalloc(&buf, 256));
+  double* d_xy = reinterpret_cast<double*>(buf);
+  fdl_rect* d_rect = reinterpret_cast<fdl_rect*>(buf + 64);
+  int* d_ok = reinterpret_cast<int*>(buf + 192);
+  cudaError_t e = cudaMemcpy(d_xy, xy, sizeof(xy), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = launch_eye_rois(d_xy, image_width, image_height, d_rect, d_ok, 0);
+  fdl_rect r[2]; int ok = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(r, d_rect, sizeof(r), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(buf);
+  if (e != cudaSuccess) return set_error(FDL_ERR_CUDA, cudaGetErrorString(e));
+  if (!ok) return set_error(FDL_ERR_INVALID, "bbox must be normalized");
+  *left = r[0]; *right = r[1];
+  return FDL_OK;
+}
+
+int fdl_image_to_tensor(int device, const fdl_image* image, const fdl_rect* roi, int out_w, int out_h, int keep_aspect_ratio,
+                        double range_min, double range_max, int flip_horizontal, float* out_tensor, uint8_t* out_u8, double* padding4) {
+  if (!image || !out_tensor || out_w <= 0 || out_h <= 0) return set_error(FDL_ERR_INVALID, "bad arguments");
+  if (keep_aspect_ratio && out_w != out_h)
+    return set_error(FDL_ERR_INVALID, "keep_aspect_ratio requires a square output (the reference divides the sizes as integers, transform.rs:240)");
+  int rc = check_device(device);
+  if (rc) return rc;
+  DevBuf<uint8_t> frames; DevBuf<I2TParams> params; DevBuf<fdl_rect> rois; DevBuf<float> out; DevBuf<uint8_t> u8;
+  int w, h;
+  rc = stage_frames(image, 1, &frames, 0, &w, &h);
+  if (rc) return rc;
+  FDL_CUDA_TRY(params.reserve(1));
+  FDL_CUDA_TRY(out.reserve((size_t)out_w * out_h * 3));
+  FDL_CUDA_TRY(u8.reserve((size_t)out_w * out_h * 3));
+  const fdl_rect* d_roi = nullptr;
+  if (roi) {
+    FDL_CUDA_TRY(rois.reserve(1));
+    FDL_CUDA_TRY(cudaMemcpy(rois.p, roi, sizeof(fdl_rect), cudaMemcpyHostToDevice));
+    d_roi = rois.p;
+  }
+  FDL_CUDA_TRY(launch_i2t_setup(d_roi, nullptr, nullptr, 1, w, h, out_w, out_h, keep_aspect_ratio, range_min, range_max, flip_horizontal ? 1 : 0,
+                                params.p, nullptr, 0));
+  FDL_CUDA_TRY(launch_i2t(frames.p, (long long)w * 3 * h, (long long)w * 3, params.p, 1, out_w, out_h, out.p, (long long)out_w * out_h * 3, u8.p,
+                          nullptr, 0));
+  I2TParams P;
+  FDL_CUDA_TRY(cudaMemcpy(out_tensor, out.p, (size_t)out_w * out_h * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+  if (out_u8) FDL_CUDA_TRY(cudaMemcpy(out_u8, u8.p, (size_t)out_w * out_h * 3, cudaMemcpyDeviceToHost));
+  FDL_CUDA_TRY(cudaMemcpy(&P, params.p, sizeof(I2TParams), cudaMemcpyDeviceToHost));
+  if (!P.valid) return set_error(FDL_ERR_INVALID, "degenerate ROI: perspective transform is singular or empty");
+  if (padding4) for (int i = 0; i < 4; ++i) padding4[i] = P.pad[i];
+  return FDL_OK;
+}
+
+int fdl_project_landmarks(int device, const float* raw, int n, int tensor_w, int tensor_h, int image_w, int image_h, const double* padding4,
+                          const fdl_rect* roi, int flip_horizontal, fdl_landmark* out) {
+  if (!raw || !out || n <= 0 || !padding4) return set_error(FDL_ERR_INVALID, "bad arguments");
+  int rc = check_device(device);
+  if (rc) return rc;
+  DevBuf<float> d_raw, d_out; DevBuf<double> d_pad; DevBuf<fdl_rect> d_roi;
+  FDL_CUDA_TRY(d_raw.reserve((size_t)3 * n));
+  FDL_CUDA_TRY(d_out.reserve((size_t)3 * n));
+  FDL_CUDA_TRY(d_pad.reserve(4));
+  FDL_CUDA_TRY(cudaMemcpy(d_raw.p, raw, (size_t)3 * n * sizeof(float), cudaMemcpyHostToDevice));
+  FDL_CUDA_TRY(cudaMemcpy(d_pad.p, padding4, 4 * sizeof(double), cudaMemcpyHostToDevice));
+  if (roi) {
+    FDL_CUDA_TRY(d_roi.reserve(1));
+    FDL_CUDA_TRY(cudaMemcpy(d_roi.p, roi, sizeof(fdl_rect), cudaMemcpyHostToDevice));
+  }
+  FDL_CUDA_TRY(launch_project(d_raw.p, n, tensor_w, tensor_h, image_w, image_h, d_pad.p, roi ? d_roi.p : nullptr, flip_horizontal, d_out.p, 0));
+  std::vector<float> pts((size_t)3 * n);
+  FDL_CUDA_TRY(cudaMemcpy(pts.data(), d_out.p, pts.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < n; ++k) { out[k].x = pts[3 * k]; out[k].y = pts[3 * k + 1]; out[k].z = pts[3 * k + 2]; }
+  return FDL_OK;
+}
+
+}  // extern "C"

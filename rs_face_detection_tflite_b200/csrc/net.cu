@@ -1,0 +1,90 @@
+// net.cu -- see net.h.
+#include "net.h"
+
+#include "fdl_status.h"
+
+namespace fdl {
+
+Net* Net::create(const std::string& path, int device, std::string* err, int* code) {
+  TfModel m;
+  if (!m.load(path, err)) { *code = err->find("cannot open") != std::string::npos ? FDL_ERR_IO : FDL_ERR_MODEL; return nullptr; }
+  Net* n = new Net();
+  if (!n->plan_.build(m, err)) { *code = FDL_ERR_MODEL; delete n; return nullptr; }
+  n->device_ = device;
+  if (device >= 0) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = net_kernels_init();
+    if (e == cudaSuccess) e = cudaMalloc(&n->d_weights_, n->plan_.weights.size() * sizeof(float));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(n->d_weights_, n->plan_.weights.data(), n->plan_.weights.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      *err = std::string("CUDA: ") + cudaGetErrorString(e);
+      *code = FDL_ERR_CUDA;
+      delete n;
+      return nullptr;
+    }
+  }
+  return n;
+}
+
+Net::~Net() {
+  if (device_ >= 0) {
+    cudaSetDevice(device_);
+    if (d_weights_) cudaFree(d_weights_);
+    if (d_arena_) cudaFree(d_arena_);
+  }
+}
+
+bool Net::reserve(int B, std::string* err) {
+  if (device_ < 0) { *err = "plan-only handle cannot run (no CUDA device bound)"; return false; }
+  if (B <= cap_B_) return true;
+  cudaSetDevice(device_);
+  if (d_arena_) { cudaDeviceSynchronize(); cudaFree(d_arena_); d_arena_ = nullptr; cap_B_ = 0; }
+  cudaError_t e = cudaMalloc(&d_arena_, (size_t)plan_.arena_per_item * (size_t)B * sizeof(float));
+  if (e != cudaSuccess) { *err = std::string("CUDA: arena allocation failed: ") + cudaGetErrorString(e); return false; }
+  cap_B_ = B;
+  return true;
+}
+
+TView Net::view(const TensorRef& r, int B) const {
+  TView v;
+  v.p = d_arena_ + r.buf_offset * (int64_t)B + r.offset;
+  v.bstride = r.batch_stride;
+  v.H = r.H; v.W = r.W; v.C = r.C;
+  return v;
+}
+
+cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active) {
+  if (B > cap_B_ || device_ < 0) return cudaErrorInvalidValue;
+  for (const Step& s : plan_.steps) {
+    cudaError_t e;
+    if (s.kind == STEP_CONV || s.kind == STEP_BLOCK) {
+      ConvArgs a;
+      a.in = view(s.in, B); a.out = view(s.out, B);
+      a.mode = s.kind == STEP_BLOCK ? 1 : 0;
+      a.kh = s.kh; a.kw = s.kw; a.stride = s.stride; a.pad_t = s.pad_t; a.pad_l = s.pad_l;
+      a.K = s.K; a.K4 = s.K4; a.N = s.N; a.Npad = s.Npad;
+      a.w = d_weights_ + s.w; a.bias = d_weights_ + s.b;
+      if (s.w_dw >= 0) { a.w_dw = d_weights_ + s.w_dw; a.b_dw = d_weights_ + s.b_dw; }
+      if (s.alpha >= 0) a.alpha = d_weights_ + s.alpha;
+      a.act = s.act;
+      if (s.skip.tensor >= 0) { a.has_skip = 1; a.skip = view(s.skip, B); a.skip_pool = s.skip_pool; a.skip_c = s.skip_c; }
+      a.B = B; a.n_active = n_active; a.mma = mode_;
+      e = launch_fused_conv(a, stream);
+    } else {
+      EltArgs a;
+      a.in = view(s.in, B); a.out = view(s.out, B);
+      a.kind = s.kind; a.stride = s.stride; a.pad_t = s.pad_t; a.pad_l = s.pad_l;
+      if (s.w_dw >= 0) { a.w_dw = d_weights_ + s.w_dw; a.b_dw = d_weights_ + s.b_dw; }
+      if (s.alpha >= 0) a.alpha = d_weights_ + s.alpha;
+      a.act = s.act;
+      if (s.skip.tensor >= 0) { a.has_other = 1; a.other = view(s.skip, B); }
+      a.B = B; a.n_active = n_active;
+      e = launch_elementwise(a, stream);
+    }
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace fdl

@@ -1,0 +1,305 @@
+// pipeline.cu -- batched detect -> face ROI -> landmark -> eye ROIs -> iris(L,R) on one B200.
+//
+// The call sequence is the reference's canonical one (lib.rs:20-40): FaceDetection::infer ->
+// face_detection_to_roi(faces[i]) -> FaceLandmark::infer -> iris_roi_from_face_landmarks ->
+// IrisLandmark::infer (right, left).  Here it runs for a whole batch of frames without leaving the
+// device: the data-dependent fan-out (0..max_faces faces per frame, two eyes per face) is handled
+// with device-side slot lists and counters, never with a host round trip.
+//
+// Streams: one copy-in stream, one compute stream, one copy-out stream; `kDepth` lanes of frame /
+// result buffers so that the H2D copy of batch k+1 and the D2H copy of batch k-1 overlap the
+// kernels of batch k.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "device_util.h"
+#include "fdl_status.h"
+#include "net.h"
+#include "prepost_kernels.cuh"
+
+using namespace fdl;
+
+namespace {
+constexpr int kDepth = 2;
+constexpr int kStages = 10;
+
+struct Lane {
+  DevBuf<uint8_t> frames;
+  DevBuf<fdl_frame_result> d_frames;
+  DevBuf<fdl_face_result> d_faces;
+  PinBuf<fdl_frame_result> h_frames;
+  PinBuf<fdl_face_result> h_faces;
+  cudaEvent_t ev_h2d_start = nullptr, ev_h2d = nullptr, ev_stage[kStages] = {}, ev_done = nullptr;
+  int n = 0;
+  int ticket = -1;
+  bool busy = false;
+};
+}  // namespace
+
+struct fdl_pipeline {
+  fdl_pipeline_config cfg{};
+  std::string model_dir;
+  Net* det = nullptr;
+  Net* lmk = nullptr;
+  Net* iris = nullptr;
+  SsdOptions opt{};
+  int S = 0, N = 0, LS = 0, IS = 0;
+  cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
+  DevBuf<float> anchors;
+  DevBuf<I2TParams> det_params, face_params, eye_params;
+  DevBuf<fdl_rect> face_rois, eye_rois;
+  DevBuf<int> slot_frame, slot_face, face_valid, eye_frame, eye_valid, counters;
+  Lane lanes[kDepth];
+  int next_ticket = 0;
+  float last_device_ms = 0.f;
+  float stage_ms[kStages] = {};
+};
+
+static void pipeline_free(fdl_pipeline* p) {
+  if (!p) return;
+  cudaSetDevice(p->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto& l : p->lanes) {
+    if (l.ev_h2d_start) cudaEventDestroy(l.ev_h2d_start);
+    if (l.ev_h2d) cudaEventDestroy(l.ev_h2d);
+    if (l.ev_done) cudaEventDestroy(l.ev_done);
+    for (auto& e : l.ev_stage) if (e) cudaEventDestroy(e);
+  }
+  if (p->s_in) cudaStreamDestroy(p->s_in);
+  if (p->s_compute) cudaStreamDestroy(p->s_compute);
+  if (p->s_out) cudaStreamDestroy(p->s_out);
+  delete p->det; delete p->lmk; delete p->iris;
+  delete p;
+}
+
+extern "C" {
+
+int fdl_pipeline_create(const fdl_pipeline_config* cfg, fdl_pipeline** out) {
+  if (!cfg || !out) return set_error(FDL_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->max_batch <= 0 || cfg->max_faces <= 0 || cfg->max_faces > FDL_MAX_DETECTIONS || cfg->frame_width <= 0 || cfg->frame_height <= 0)
+    return set_error(FDL_ERR_INVALID, "bad pipeline configuration");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_error(FDL_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return set_error(FDL_ERR_INVALID, "device index out of range");
+  FDL_CUDA_TRY(cudaSetDevice(cfg->device));
+  fdl_pipeline* p = new fdl_pipeline();
+  p->cfg = *cfg;
+  p->model_dir = cfg->model_dir ? cfg->model_dir : "./models";
+  p->cfg.model_dir = nullptr;
+  auto bail = [&](int c, const std::string& m) { pipeline_free(p); return set_error(c, m); };
+  const char* file = nullptr;
+  switch (cfg->detector_model) {
+    case FDL_MODEL_FRONT_CAMERA: file = "face_detection_front.tflite"; break;
+    case FDL_MODEL_BACK_CAMERA: file = "face_detection_back.tflite"; break;
+    case FDL_MODEL_SHORT: file = "face_detection_short_range.tflite"; break;
+    case FDL_MODEL_FULL: file = "face_detection_full_range.tflite"; break;
+    default: return bail(FDL_ERR_MODEL, "unsupported model type");
+  }
+  ssd_options_for(cfg->detector_model, &p->opt);
+  std::string err; int code = FDL_ERR_INTERNAL;
+  p->det = Net::create(p->model_dir + "/" + file, cfg->device, &err, &code);
+  if (!p->det) return bail(code, err);
+  p->S = p->det->plan().input.H; p->N = ssd_num_anchors(p->opt);
+  if (p->det->num_outputs() != 2 || p->det->out_elems(0) != (int64_t)p->N * 16 || p->det->out_elems(1) != p->N || p->S != p->opt.input_size)
+    return bail(FDL_ERR_MODEL, "incompatible detector model");
+  if (cfg->run_landmarks) {
+    p->lmk = Net::create(p->model_dir + "/face_landmark.tflite", cfg->device, &err, &code);
+    if (!p->lmk) return bail(code, err);
+    p->LS = p->lmk->plan().input.H;
+    if (p->lmk->num_outputs() != 2 || p->lmk->out_elems(0) < 3 * FDL_NUM_FACE_LANDMARKS) return bail(FDL_ERR_MODEL, "incompatible landmark model");
+    if (cfg->run_iris) {
+      p->iris = Net::create(p->model_dir + "/iris_landmark.tflite", cfg->device, &err, &code);
+      if (!p->iris) return bail(code, err);
+      p->IS = p->iris->plan().input.H;
+      if (p->iris->num_outputs() != 2 || p->iris->out_elems(0) != 3 * FDL_NUM_EYE_CONTOUR || p->iris->out_elems(1) != 3 * FDL_NUM_IRIS)
+        return bail(FDL_ERR_MODEL, "incompatible iris model");
+    }
+  }
+  const int B = cfg->max_batch, F = B * cfg->max_faces, E = 2 * F;
+  cudaError_t e = cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = p->anchors.reserve((size_t)p->N * 2);
+  if (e == cudaSuccess) e = launch_anchors(p->opt, p->anchors.p, p->N, p->s_compute);
+  if (e == cudaSuccess) e = p->det_params.reserve(B);
+  if (e == cudaSuccess) e = p->face_params.reserve(F);
+  if (e == cudaSuccess) e = p->eye_params.reserve(E);
+  if (e == cudaSuccess) e = p->face_rois.reserve(F);
+  if (e == cudaSuccess) e = p->eye_rois.reserve(E);
+  if (e == cudaSuccess) e = p->slot_frame.reserve(F);
+  if (e == cudaSuccess) e = p->slot_face.reserve(F);
+  if (e == cudaSuccess) e = p->face_valid.reserve(F);
+  if (e == cudaSuccess) e = p->eye_frame.reserve(E);
+  if (e == cudaSuccess) e = p->eye_valid.reserve(E);
+  if (e == cudaSuccess) e = p->counters.reserve(4);
+  if (e == cudaSuccess) e = cudaMemsetAsync(p->counters.p, 0, 4 * sizeof(int), p->s_compute);
+  const size_t frame_bytes = (size_t)cfg->frame_width * 3 * cfg->frame_height;
+  for (auto& l : p->lanes) {
+    if (e == cudaSuccess) e = l.frames.reserve(frame_bytes * B);
+    if (e == cudaSuccess) e = l.d_frames.reserve(B);
+    if (e == cudaSuccess) e = l.d_faces.reserve(F);
+    if (e == cudaSuccess) e = l.h_frames.reserve(B);
+    if (e == cudaSuccess) e = l.h_faces.reserve(F);
+    if (e == cudaSuccess) e = cudaEventCreate(&l.ev_h2d_start);
+    if (e == cudaSuccess) e = cudaEventCreate(&l.ev_h2d);
+    if (e == cudaSuccess) e = cudaEventCreate(&l.ev_done);
+    for (auto& ev : l.ev_stage) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+  }
+  if (e != cudaSuccess) return bail(FDL_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+  if (!p->det->reserve(B, &err) || (p->lmk && !p->lmk->reserve(F, &err)) || (p->iris && !p->iris->reserve(E, &err)))
+    return bail(FDL_ERR_CUDA, err);
+  e = cudaStreamSynchronize(p->s_compute);
+  if (e != cudaSuccess) return bail(FDL_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
+  *out = p;
+  return FDL_OK;
+}
+
+void fdl_pipeline_destroy(fdl_pipeline* p) { pipeline_free(p); }
+int fdl_pipeline_depth(const fdl_pipeline*) { return kDepth; }
+
+int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ticket) {
+  if (!p || !frames || !ticket) return set_error(FDL_ERR_INVALID, "null argument");
+  if (n <= 0 || n > p->cfg.max_batch) return set_error(FDL_ERR_INVALID, "batch size out of range (1..max_batch)");
+  FDL_CUDA_TRY(cudaSetDevice(p->cfg.device));
+  Lane* lane = nullptr;
+  for (auto& l : p->lanes) if (!l.busy) { lane = &l; break; }
+  if (!lane) return set_error(FDL_ERR_INVALID, "all pipeline lanes are in flight: collect a ticket first");
+  const int W = p->cfg.frame_width, H = p->cfg.frame_height, MF = p->cfg.max_faces;
+  for (int i = 0; i < n; ++i)
+    if (frames[i].width != W || frames[i].height != H) return set_error(FDL_ERR_INVALID, "frame size differs from the pipeline configuration");
+
+  // ---- copy-in
+  FDL_CUDA_TRY(cudaEventRecord(lane->ev_h2d_start, p->s_in));
+  int w, h;
+  int rc = stage_frames(frames, n, &lane->frames, p->s_in, &w, &h);
+  if (rc) return rc;
+  FDL_CUDA_TRY(cudaEventRecord(lane->ev_h2d, p->s_in));
+
+  // ---- compute
+  cudaStream_t cs = p->s_compute;
+  FDL_CUDA_TRY(cudaStreamWaitEvent(cs, lane->ev_h2d, 0));
+  const long long row = (long long)W * 3, fstride = row * H;
+  const int F = n * MF, E = 2 * F;
+  int* n_faces = p->counters.p;
+  int* n_eyes = p->counters.p + 1;
+  FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[0], cs));
+  FDL_CUDA_TRY(cudaMemsetAsync(lane->d_frames.p, 0, (size_t)n * sizeof(fdl_frame_result), cs));
+  FDL_CUDA_TRY(cudaMemsetAsync(lane->d_faces.p, 0, (size_t)F * sizeof(fdl_face_result), cs));
+  // FaceDetection::infer: image_to_tensor(keep_aspect, (-1,1)) -> net -> SSD post-processing
+  FDL_CUDA_TRY(launch_i2t_setup(nullptr, nullptr, nullptr, n, W, H, p->S, p->S, 1, -1.0, 1.0, 0, p->det_params.p, nullptr, cs));
+  TView div = p->det->input_view(n);
+  FDL_CUDA_TRY(launch_i2t(lane->frames.p, fstride, row, p->det_params.p, n, p->S, p->S, div.p, div.bstride, nullptr, nullptr, cs));
+  FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[1], cs));
+  FDL_CUDA_TRY(p->det->forward(n, cs));
+  FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[2], cs));
+  {
+    TView reg = p->det->output_view(0, n), cls = p->det->output_view(1, n);
+    SsdPostArgs a;
+    a.reg = reg.p; a.reg_bstride = reg.bstride; a.cls = cls.p; a.cls_bstride = cls.bstride;
+    a.anchors = p->anchors.p; a.N = p->N; a.B = n; a.scale = (float)p->S; a.params = p->det_params.p;
+    a.det_base = reinterpret_cast<char*>(lane->d_frames.p) + offsetof(fdl_frame_result, detections);
+    a.det_stride = sizeof(fdl_frame_result);
+    a.ndet_base = reinterpret_cast<char*>(lane->d_frames.p) + offsetof(fdl_frame_result, n_detections);
+    a.ndet_stride = sizeof(fdl_frame_result);
+    a.max_out = FDL_MAX_DETECTIONS;
+    FDL_CUDA_TRY(launch_ssd_postprocess(a, cs));
+  }
+  FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[3], cs));
+  if (p->lmk) {
+    // face_detection_to_roi + FaceLandmark::infer for the first max_faces detections of every frame
+    FDL_CUDA_TRY(launch_face_select(lane->d_frames.p, n, MF, p->slot_frame.p, p->slot_face.p, n_faces, n_eyes, cs));
+    FDL_CUDA_TRY(launch_face_roi(lane->d_frames.p, p->slot_frame.p, p->slot_face.p, F, MF, W, H, p->face_rois.p, p->face_valid.p,
+                                 lane->d_faces.p, n_faces, cs));
+    FDL_CUDA_TRY(launch_i2t_setup(p->face_rois.p, p->slot_frame.p, p->face_valid.p, F, W, H, p->LS, p->LS, 0, 0.0, 1.0, 0, p->face_params.p,
+                                  n_faces, cs));
+    TView liv = p->lmk->input_view(F);
+    FDL_CUDA_TRY(launch_i2t(lane->frames.p, fstride, row, p->face_params.p, F, p->LS, p->LS, liv.p, liv.bstride, nullptr, n_faces, cs));
+    FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[4], cs));
+    FDL_CUDA_TRY(p->lmk->forward(F, cs, n_faces));
+    FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[5], cs));
+    TView raw = p->lmk->output_view(0, F), flag = p->lmk->output_view(1, F);
+    // the reference reads the LAST element of the flag tensor (face_landmark.rs:292-293)
+    FDL_CUDA_TRY(launch_landmark_post(raw.p, raw.bstride, flag.p + p->lmk->out_elems(1) - 1, flag.bstride, p->face_params.p, p->face_rois.p,
+                                      p->slot_frame.p, p->slot_face.p, F, MF, p->LS, p->LS, lane->d_faces.p, p->eye_rois.p, p->eye_frame.p,
+                                      p->eye_valid.p, n_faces, cs));
+    if (p->iris) {
+      // IrisLandmark::infer for both eyes: image_to_tensor(keep_aspect, (0,1), flip = right eye)
+      FDL_CUDA_TRY(launch_i2t_setup(p->eye_rois.p, p->eye_frame.p, p->eye_valid.p, E, W, H, p->IS, p->IS, 1, 0.0, 1.0, 2, p->eye_params.p, n_eyes,
+                                    cs));
+      TView iiv = p->iris->input_view(E);
+      FDL_CUDA_TRY(launch_i2t(lane->frames.p, fstride, row, p->eye_params.p, E, p->IS, p->IS, iiv.p, iiv.bstride, nullptr, n_eyes, cs));
+      FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[6], cs));
+      FDL_CUDA_TRY(p->iris->forward(E, cs, n_eyes));
+      FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[7], cs));
+      TView ec = p->iris->output_view(0, E), ir = p->iris->output_view(1, E);
+      FDL_CUDA_TRY(launch_iris_post(ec.p, ec.bstride, ir.p, ir.bstride, p->eye_params.p, p->eye_rois.p, p->eye_valid.p, p->slot_frame.p,
+                                    p->slot_face.p, E, MF, p->IS, p->IS, lane->d_faces.p, n_eyes, cs));
+    } else {
+      FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[6], cs));
+      FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[7], cs));
+    }
+  } else {
+    for (int i = 4; i <= 7; ++i) FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[i], cs));
+  }
+  FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[8], cs));
+
+  // ---- copy-out
+  FDL_CUDA_TRY(cudaStreamWaitEvent(p->s_out, lane->ev_stage[8], 0));
+  FDL_CUDA_TRY(cudaMemcpyAsync(lane->h_frames.p, lane->d_frames.p, (size_t)n * sizeof(fdl_frame_result), cudaMemcpyDeviceToHost, p->s_out));
+  if (p->lmk)
+    FDL_CUDA_TRY(cudaMemcpyAsync(lane->h_faces.p, lane->d_faces.p, (size_t)F * sizeof(fdl_face_result), cudaMemcpyDeviceToHost, p->s_out));
+  FDL_CUDA_TRY(cudaEventRecord(lane->ev_done, p->s_out));
+  // the next copy-in into this lane's frame buffer may only start once these kernels are done;
+  // that is guaranteed because the lane stays busy until its ticket is collected.
+  lane->n = n;
+  lane->busy = true;
+  lane->ticket = p->next_ticket++;
+  *ticket = lane->ticket;
+  return FDL_OK;
+}
+
+int fdl_pipeline_collect(fdl_pipeline* p, int ticket, fdl_frame_result* frame_results, fdl_face_result* face_results, int* n_out) {
+  if (!p) return set_error(FDL_ERR_INVALID, "null argument");
+  Lane* lane = nullptr;
+  for (auto& l : p->lanes) if (l.busy && l.ticket == ticket) { lane = &l; break; }
+  if (!lane) return set_error(FDL_ERR_INVALID, "unknown ticket");
+  FDL_CUDA_TRY(cudaSetDevice(p->cfg.device));
+  FDL_CUDA_TRY(cudaEventSynchronize(lane->ev_done));
+  const int n = lane->n, F = n * p->cfg.max_faces;
+  if (frame_results) std::memcpy(frame_results, lane->h_frames.p, (size_t)n * sizeof(fdl_frame_result));
+  if (face_results && p->lmk) std::memcpy(face_results, lane->h_faces.p, (size_t)F * sizeof(fdl_face_result));
+  if (n_out) *n_out = n;
+  float ms = 0.f;
+  cudaEventElapsedTime(&p->stage_ms[0], lane->ev_h2d_start, lane->ev_h2d);
+  for (int i = 0; i < 8; ++i) {
+    cudaEventElapsedTime(&ms, lane->ev_stage[i], lane->ev_stage[i + 1]);
+    p->stage_ms[i + 1] = ms;
+  }
+  cudaEventElapsedTime(&p->stage_ms[9], lane->ev_stage[8], lane->ev_done);
+  cudaEventElapsedTime(&p->last_device_ms, lane->ev_stage[0], lane->ev_stage[8]);
+  lane->busy = false;
+  return FDL_OK;
+}
+
+int fdl_pipeline_run(fdl_pipeline* p, const fdl_image* frames, int n, fdl_frame_result* frame_results, fdl_face_result* face_results) {
+  int ticket = -1;
+  int rc = fdl_pipeline_submit(p, frames, n, &ticket);
+  if (rc) return rc;
+  return fdl_pipeline_collect(p, ticket, frame_results, face_results, nullptr);
+}
+
+float fdl_pipeline_last_device_ms(const fdl_pipeline* p) { return p ? p->last_device_ms : 0.f; }
+int fdl_pipeline_stage_ms(const fdl_pipeline* p, float* out10) {
+  if (!p || !out10) return set_error(FDL_ERR_INVALID, "null argument");
+  // [0] H2D, [1] detector preprocess, [2] detector net, [3] SSD post, [4] face ROI + warp, [5] landmark net,
+  // [6] landmark post + eye warp, [7] iris net, [8] iris post, [9] D2H
+  for (int i = 0; i < kStages; ++i) out10[i] = p->stage_ms[i];
+  return FDL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// plan.h -- turns a parsed .tflite graph into a list of fused kernel launches ("steps").
+//
+// This is what replaces TFLite's InterpreterBuilder/allocate_tensors (face_detection.rs:207-210,
+// face_landmark.rs:233-236, iris_landmark.rs:161-164): instead of interpreting the 97..354 ops one
+// by one, the planner
+//   * folds DEQUANTIZE (f16 -> f32 constants) at load,
+//   * turns RESHAPE / CONCATENATION(axis=1) into aliases so heads write straight into the
+//     [B,N,16] / [B,N,1] outputs,
+//   * pattern-matches  DW3x3 -> CONV1x1 -> [ADD skip] -> [RELU|PRELU]  (BlazeBlock) with
+//     the skip branch's MAX_POOL / channel PAD folded into the epilogue,
+//   * fuses CONV -> [RELU|PRELU] and RESIZE_BILINEAR -> ADD,
+//   * assigns activation buffers by liveness (per-batch-item offsets, scaled by B at run time).
+// The plan is device-independent (pure host data) so it can be inspected and tested without a GPU.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "tflite_model.h"
+
+namespace fdl {
+
+enum StepKind : int {
+  STEP_CONV = 0,     // CONV_2D (any kh,kw,stride) + bias [+ act]                     -> fused_conv kernel
+  STEP_BLOCK = 1,    // DW3x3(stride) + bias -> CONV1x1 + bias [+ skip] [+ act]       -> fused_conv kernel (DW prologue)
+  STEP_DW = 2,       // standalone DEPTHWISE_CONV_2D [+ act]
+  STEP_POOL = 3,     // standalone MAX_POOL_2D
+  STEP_PADC = 4,     // standalone channel PAD
+  STEP_ADD = 5,      // standalone ADD [+ act]
+  STEP_ACT = 6,      // standalone RELU / PRELU
+  STEP_RESIZE = 7    // RESIZE_BILINEAR (half pixel centres) [+ ADD other] [+ act]
+};
+enum ActKind : int { ACT_NONE = 0, ACT_RELU = 1, ACT_PRELU = 2 };
+
+// A view of a [B,H,W,C] f32 tensor inside the activation arena.  Element (b,y,x,c) lives at
+//   arena + buf_offset*B + b*batch_stride + offset + (y*W + x)*C + c
+// (buf_offset, batch_stride, offset in floats; buf_offset is per batch item and scaled by B).
+struct TensorRef {
+  int tensor = -1;           // tflite tensor index (for diagnostics)
+  int64_t buf_offset = 0;    // start of the owning buffer, per batch item
+  int64_t batch_stride = 0;  // floats between consecutive batch items in the owning buffer
+  int64_t offset = 0;        // offset inside one batch item of the owning buffer
+  int H = 0, W = 0, C = 0;
+};
+
+struct Step {
+  int kind = STEP_CONV;
+  TensorRef in, out;
+  TensorRef skip;            // BLOCK: residual source; ADD/RESIZE: second operand (tensor == -1: none)
+  int skip_pool = 0;         // BLOCK: residual = MAX_POOL 2x2 s2 of skip
+  int skip_c = 0;            // BLOCK: channels of the residual source (< out.C: zero channel PAD)
+  int kh = 1, kw = 1, stride = 1, pad_t = 0, pad_l = 0;   // CONV / DW / POOL geometry (DW part of BLOCK)
+  int act = ACT_NONE;
+  // offsets (in floats) into the weight arena; -1 = absent
+  int64_t w_dw = -1, b_dw = -1;   // DW weights [kh*kw][C], bias [C]
+  int64_t w = -1, b = -1;         // CONV/PW weights [K4][Npad] (K = kh*kw*Cin, Npad = roundup(Cout,4)), bias [Npad]
+  int64_t alpha = -1;             // PRELU slopes [C]
+  int K = 0, K4 = 0, N = 0, Npad = 0;  // contraction size (K4 = roundup(K,4) rows stored) / output channels of the CONV/PW part
+  std::vector<int> ops;           // tflite op indices folded into this step
+  std::string text;               // human-readable description
+};
+
+struct Plan {
+  std::vector<Step> steps;
+  std::vector<float> weights;     // host copy of the weight arena
+  TensorRef input;
+  std::vector<TensorRef> outputs; // graph output order == interpreter.outputs() order
+  int64_t arena_per_item = 0;     // floats of activation arena per batch item
+  int64_t algo_bytes_per_item = 0;  // sum over steps of (input + skip + output) bytes: the block-fused floor
+  int64_t flops_per_item = 0;
+  int num_tflite_ops = 0;
+
+  bool build(const TfModel& m, std::string* err);
+  std::string describe() const;
+};
+
+}  // namespace fdl

@@ -1,0 +1,455 @@
+// prepost_kernels.cu -- see prepost_kernels.cuh.  Compiled with -fmad=false.
+#include "prepost_kernels.cuh"
+
+namespace fdl {
+
+void count_launch();
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void anchors_kernel(SsdOptions opt, float* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x, y;
+  ssd_anchor(opt, i, &x, &y);
+  out[2 * i] = x;
+  out[2 * i + 1] = y;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void i2t_setup_kernel(const fdl_rect* rois, const int* slot_frame, const int* slot_valid, int n, int img_w, int img_h,
+                                 int out_w, int out_h, int keep_aspect, double range_min, double range_max, int flip_mode,
+                                 I2TParams* params, const int* n_active) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_active) n = min(n, *n_active);
+  if (i >= n) return;
+  bool flip = flip_mode == 1 || (flip_mode == 2 && (i & 1));
+  int frame = slot_frame ? slot_frame[i] : i;
+  I2TParams P;
+  i2t_setup(rois ? &rois[i] : nullptr, img_w, img_h, out_w, out_h, keep_aspect != 0, range_min, range_max, flip, frame, &P);
+  if (slot_valid && !slot_valid[i]) P.valid = 0;
+  params[i] = P;
+}
+
+// One thread per output pixel (3 channels).  The source taps are gathered straight from the u8
+// frame (L2/texture path); the f32 tensor is written once.
+__global__ void __launch_bounds__(256) i2t_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
+                                                  const I2TParams* __restrict__ params, int n, int out_w, int out_h,
+                                                  float* __restrict__ out, long long out_bstride, uint8_t* __restrict__ out_u8,
+                                                  const int* n_active) {
+  int slot = blockIdx.y;
+  if (n_active) n = min(n, *n_active);
+  if (slot >= n) return;
+  __shared__ I2TParams P;
+  {
+    const int* src = reinterpret_cast<const int*>(&params[slot]);
+    int* dst = reinterpret_cast<int*>(&P);
+    for (int i = threadIdx.x; i < (int)(sizeof(I2TParams) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= out_w * out_h) return;
+  int oy = pix / out_w, ox = pix - oy * out_w;
+  Px3 p;
+  if (P.valid) p = i2t_pixel(P, frames + (long long)P.frame * frame_stride, row_stride, ox, oy);
+  else { p.r = p.g = p.b = 0; }
+  float* o = out + (long long)slot * out_bstride + (long long)pix * 3;
+  o[0] = i2t_normalise(p.r, P.range_min, P.range_max);
+  o[1] = i2t_normalise(p.g, P.range_min, P.range_max);
+  o[2] = i2t_normalise(p.b, P.range_min, P.range_max);
+  if (out_u8) {
+    uint8_t* u = out_u8 + ((long long)slot * out_w * out_h + pix) * 3;
+    u[0] = (uint8_t)p.r; u[1] = (uint8_t)p.g; u[2] = (uint8_t)p.b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SSD post-processing: one CTA per frame.
+constexpr int kPostThreads = 128;
+
+// Ordered compaction inside a CTA: returns this thread's exclusive rank among the flagged threads
+// of the current chunk and the chunk total.  s_warp: kPostThreads/32 ints of scratch.
+__device__ __forceinline__ int block_rank(bool flag, int* s_warp, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned m = __ballot_sync(0xffffffffu, flag);
+  int r = __popc(m & ((1u << lane) - 1u));
+  if (lane == 0) s_warp[warp] = __popc(m);
+  __syncthreads();
+  int off = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kPostThreads / 32; ++w) {
+    int c = s_warp[w];
+    if (w < warp) off += c;
+    tot += c;
+  }
+  __syncthreads();
+  *total = tot;
+  return off + r;
+}
+
+__global__ void __launch_bounds__(kPostThreads) ssd_postprocess_kernel(const SsdPostArgs a) {
+  extern __shared__ int s_mem[];
+  const int N = a.N, tid = threadIdx.x, b = blockIdx.x;
+  int* s_idx = s_mem;                                        // survivor -> anchor index (ascending)
+  float* s_score = reinterpret_cast<float*>(s_mem + N);      // survivor -> score
+  int* s_rem[2] = {s_mem + 2 * N, s_mem + 3 * N};            // remaining lists (survivor positions, score order)
+  int* s_cand = s_mem + 4 * N;                               // candidates of the current cluster
+  __shared__ int s_warp[kPostThreads / 32];
+  __shared__ float s_top[16];
+
+  const float* reg = a.reg + (long long)b * a.reg_bstride;
+  const float* cls = a.cls + (long long)b * a.cls_bstride;
+
+  // 1. get_sigmoid_score + convert_to_detections: survivors in ascending anchor order
+  int n = 0;
+  for (int base = 0; base < N; base += kPostThreads) {
+    int i = base + tid;
+    bool keep = false;
+    float sc = 0.f;
+    if (i < N) {
+      sc = ssd_score(cls[i]);
+      if (sc > 0.5f) {
+        float raw[16], d[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) raw[k] = reg[(long long)i * 16 + k];
+        decode_box(raw, a.anchors[2 * i], a.anchors[2 * i + 1], a.scale, d);
+        keep = d[2] > d[0] && d[3] > d[1];
+      }
+    }
+    int tot;
+    int r = block_rank(keep, s_warp, &tot);
+    if (keep) { s_idx[n + r] = i; s_score[n + r] = sc; }
+    n += tot;
+  }
+  __syncthreads();
+  if (a.n_surv && tid == 0) a.n_surv[b] = n;
+  if (a.surv_anchor) for (int j = tid; j < n && j < a.cap_surv; j += kPostThreads) {
+    a.surv_anchor[(long long)b * a.cap_surv + j] = s_idx[j];
+    a.surv_cluster[(long long)b * a.cap_surv + j] = -1;
+  }
+
+  // 2. stable sort by score, descending (nms.rs:134-137): rank = number of elements that precede
+  for (int j = tid; j < n; j += kPostThreads) {
+    float sj = s_score[j];
+    int rank = 0;
+    for (int k = 0; k < n; ++k) {
+      float sk = s_score[k];
+      rank += (sk > sj || (sk == sj && k < j)) ? 1 : 0;
+    }
+    s_rem[0][rank] = j;
+  }
+  __syncthreads();
+
+  // letterbox removal constants (transform.rs:115-142): scales in f64, cast to f32
+  double pl, pt, pr, pb;
+  if (a.params) { pl = a.params[b].pad[0]; pt = a.params[b].pad[1]; pr = a.params[b].pad[2]; pb = a.params[b].pad[3]; }
+  else if (a.padding4) { pl = a.padding4[4 * b]; pt = a.padding4[4 * b + 1]; pr = a.padding4[4 * b + 2]; pb = a.padding4[4 * b + 3]; }
+  else { pl = pt = pr = pb = 0.0; }
+  const float left = (float)pl, top = (float)pt;
+  const float h_scale = (float)(1.0 - (pl + pr)), v_scale = (float)(1.0 - (pt + pb));
+
+  // 3. weighted_non_maximum_suppression (nms.rs:56-124)
+  int cur = 0, n_rem = n, n_out = 0;
+  const double thr = (double)0.3f;
+  while (n_rem > 0) {
+    const int* rem = s_rem[cur];
+    int* next = s_rem[cur ^ 1];
+    const int top_pos = rem[0];
+    if (tid == 0) {
+      float raw[16];
+      int ti = s_idx[top_pos];
+      for (int k = 0; k < 16; ++k) raw[k] = reg[(long long)ti * 16 + k];
+      decode_box(raw, a.anchors[2 * ti], a.anchors[2 * ti + 1], a.scale, s_top);
+    }
+    __syncthreads();
+    int n_cand = 0, n_next = 0;
+    for (int base = 0; base < n_rem; base += kPostThreads) {
+      int j = base + tid;
+      bool is_cand = false, is_rem = false;
+      int pos = 0;
+      if (j < n_rem) {
+        pos = rem[j];
+        int ai = s_idx[pos];
+        float raw[16], d[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) raw[k] = reg[(long long)ai * 16 + k];
+        decode_box(raw, a.anchors[2 * ai], a.anchors[2 * ai + 1], a.scale, d);
+        double sim = overlap_similarity(d, s_top);
+        is_cand = sim > thr;
+        is_rem = !is_cand;
+      }
+      int tc, tr;
+      int rc = block_rank(is_cand, s_warp, &tc);
+      int rr = block_rank(is_rem, s_warp, &tr);
+      if (is_cand) s_cand[n_cand + rc] = pos;
+      if (is_rem) next[n_next + rr] = pos;
+      n_cand += tc;
+      n_next += tr;
+    }
+    __syncthreads();
+    // weighted merge: thread k < 16 owns coordinate k and accumulates in candidate order, in f32
+    if (tid < 16 && n_out < a.max_out) {
+      float v;
+      if (n_cand > 0) {
+        float w = 0.f, total = 0.f;
+        for (int c = 0; c < n_cand; ++c) {
+          int pos = s_cand[c];
+          int ai = s_idx[pos];
+          float sc = s_score[pos];
+          float raw[16], d[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) raw[k] = reg[(long long)ai * 16 + k];
+          decode_box(raw, a.anchors[2 * ai], a.anchors[2 * ai + 1], a.scale, d);
+          total += sc;
+          float dk = 0.f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) if (k == tid) dk = d[k];
+          w += dk * sc;
+        }
+        v = w / total;
+      } else {
+        v = s_top[tid];
+      }
+      // detection_letterbox_removal
+      v = (tid & 1) ? (v - top) / v_scale : (v - left) / h_scale;
+      fdl_detection* o = reinterpret_cast<fdl_detection*>(a.det_base + (long long)b * a.det_stride) + n_out;
+      o->data[tid] = v;
+      if (tid == 0) { o->score = s_score[top_pos]; o->anchor = s_idx[top_pos]; }
+    }
+    if (a.surv_cluster) for (int c = tid; c < n_cand; c += kPostThreads) {
+      int pos = s_cand[c];
+      if (pos < a.cap_surv) a.surv_cluster[(long long)b * a.cap_surv + pos] = n_out;
+    }
+    ++n_out;
+    __syncthreads();
+    if (n_cand == 0) break;   // "number of indexed scores didn't change" (nms.rs:117-119)
+    n_rem = n_next;
+    cur ^= 1;
+  }
+  if (tid == 0) {
+    *reinterpret_cast<int32_t*>(a.ndet_base + (long long)b * a.ndet_stride) = min(n_out, a.max_out);
+    if (a.n_total) a.n_total[b] = n_out;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void face_select_kernel(fdl_frame_result* frames, int B, int max_faces, int* slot_frame, int* slot_face, int* n_faces,
+                                   int* n_eyes) {
+  // single CTA: exclusive scan of min(n_detections, max_faces) over frames
+  __shared__ int s_part[1024];
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int per = (B + T - 1) / T;
+  int lo = tid * per, hi = min(lo + per, B);
+  int sum = 0;
+  for (int b = lo; b < hi; ++b) sum += min(frames[b].n_detections, max_faces);
+  s_part[tid] = sum;
+  __syncthreads();
+  // Hillis-Steele inclusive scan
+  for (int off = 1; off < T; off <<= 1) {
+    int v = tid >= off ? s_part[tid - off] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int base = s_part[tid] - sum;
+  for (int b = lo; b < hi; ++b) {
+    int nf = min(frames[b].n_detections, max_faces);
+    frames[b].n_faces = nf;
+    for (int f = 0; f < nf; ++f) { slot_frame[base + f] = b; slot_face[base + f] = f; }
+    base += nf;
+  }
+  if (tid == T - 1) { *n_faces = s_part[tid]; *n_eyes = 2 * s_part[tid]; }
+}
+
+__global__ void face_roi_kernel(const fdl_frame_result* frames, const int* slot_frame, const int* slot_face, int max_slots,
+                                int max_faces, int img_w, int img_h, fdl_rect* rois, int* slot_valid, fdl_face_result* faces,
+                                const int* n_faces) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= min(max_slots, *n_faces)) return;
+  int fr = slot_frame[s], fa = slot_face[s];
+  fdl_rect r;
+  bool ok = face_detection_to_roi(frames[fr].detections[fa].data, img_w, img_h, FDL_SIZE_MODE_NONE, &r);
+  if (!ok) { r.x_center = r.y_center = r.width = r.height = r.rotation = 0.0; r.normalized = 1; r._pad = 0; }
+  rois[s] = r;
+  slot_valid[s] = ok ? 1 : 0;
+  faces[(long long)fr * max_faces + fa].face_roi = r;
+}
+
+__global__ void __launch_bounds__(128) landmark_post_kernel(const float* raw, long long raw_bstride, const float* flag,
+                                                            long long flag_bstride, const I2TParams* params, const fdl_rect* rois,
+                                                            const int* slot_frame, const int* slot_face, int max_slots, int max_faces,
+                                                            int tensor_w, int tensor_h, fdl_face_result* faces, fdl_rect* eye_rois,
+                                                            int* eye_frame, int* eye_valid, const int* n_faces) {
+  int s = blockIdx.x;
+  if (s >= min(max_slots, *n_faces)) return;
+  __shared__ ProjectParams pp;
+  __shared__ int s_has;
+  const I2TParams& P = params[s];
+  fdl_face_result* out = &faces[(long long)slot_frame[s] * max_faces + slot_face[s]];
+  const float* r = raw + (long long)s * raw_bstride;
+  if (threadIdx.x == 0) {
+    float logit = flag[(long long)s * flag_bstride];
+    // face_landmark.rs:292-296: sigmoid(flag) <= DETECTION_THRESHOLD -> no landmarks
+    int has = P.valid && !(sigmoid_f32(logit) <= 0.5f);
+    s_has = has;
+    out->face_flag_logit = logit;
+    out->has_landmarks = has;
+    project_setup(tensor_w, tensor_h, P.src_w, P.src_h, P.pad, &rois[s], false, &pp);
+    fdl_rect er[2];
+    bool ok[2] = {false, false};
+    if (has) {
+      const int idx[4] = {33, 133, 362, 263};   // iris_landmark.rs:29-35
+      double xy[8];
+      for (int k = 0; k < 4; ++k) {
+        float q[3];
+        project_point(pp, r + 3 * idx[k], q);
+        xy[2 * k] = (double)q[0]; xy[2 * k + 1] = (double)q[1];
+      }
+      ok[0] = eye_roi(xy[0], xy[1], xy[2], xy[3], P.src_w, P.src_h, &er[0]);
+      ok[1] = eye_roi(xy[4], xy[5], xy[6], xy[7], P.src_w, P.src_h, &er[1]);
+    }
+    for (int e = 0; e < 2; ++e) {
+      if (!ok[e]) { er[e].x_center = er[e].y_center = er[e].width = er[e].height = er[e].rotation = 0.0; er[e].normalized = 1; er[e]._pad = 0; }
+      eye_rois[2 * s + e] = er[e];
+      eye_valid[2 * s + e] = ok[e] ? 1 : 0;
+      eye_frame[2 * s + e] = P.frame;
+      out->eye_roi[e] = er[e];
+    }
+  }
+  __syncthreads();
+  if (!s_has) return;
+  for (int k = threadIdx.x; k < FDL_NUM_FACE_LANDMARKS; k += blockDim.x) project_point(pp, r + 3 * k, out->landmarks + 3 * k);
+}
+
+__global__ void __launch_bounds__(96) iris_post_kernel(const float* contour, long long contour_bstride, const float* iris,
+                                                       long long iris_bstride, const I2TParams* params, const fdl_rect* eye_rois,
+                                                       const int* eye_valid, const int* slot_frame, const int* slot_face,
+                                                       int max_eye_slots, int max_faces, int tensor_w, int tensor_h,
+                                                       fdl_face_result* faces, const int* n_eyes) {
+  int es = blockIdx.x;
+  if (es >= min(max_eye_slots, *n_eyes)) return;
+  if (!eye_valid[es]) return;
+  __shared__ ProjectParams pp;
+  const I2TParams& P = params[es];
+  if (!P.valid) return;
+  int s = es >> 1, e = es & 1;
+  fdl_face_result* out = &faces[(long long)slot_frame[s] * max_faces + slot_face[s]];
+  if (threadIdx.x == 0) project_setup(tensor_w, tensor_h, P.src_w, P.src_h, P.pad, &eye_rois[es], e == 1, &pp);
+  __syncthreads();
+  int k = threadIdx.x;
+  if (k < FDL_NUM_EYE_CONTOUR) project_point(pp, contour + (long long)es * contour_bstride + 3 * k, out->eye_contour[e] + 3 * k);
+  else if (k < FDL_NUM_EYE_CONTOUR + FDL_NUM_IRIS) {
+    int q = k - FDL_NUM_EYE_CONTOUR;
+    project_point(pp, iris + (long long)es * iris_bstride + 3 * q, out->iris[e] + 3 * q);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void face_detection_to_roi_kernel(const fdl_detection* det, int img_w, int img_h, int size_mode, fdl_rect* out, int* ok) {
+  *ok = face_detection_to_roi(det->data, img_w, img_h, size_mode, out) ? 1 : 0;
+}
+__global__ void eye_rois_kernel(const double* xy, int img_w, int img_h, fdl_rect* out2, int* ok) {
+  bool a = eye_roi(xy[0], xy[1], xy[2], xy[3], img_w, img_h, &out2[0]);
+  bool b = eye_roi(xy[4], xy[5], xy[6], xy[7], img_w, img_h, &out2[1]);
+  *ok = (a && b) ? 1 : 0;
+}
+__global__ void project_kernel(const float* raw, int n, int tensor_w, int tensor_h, int img_w, int img_h, const double* pad4,
+                               const fdl_rect* roi, int flip, float* out) {
+  __shared__ ProjectParams pp;
+  if (threadIdx.x == 0) project_setup(tensor_w, tensor_h, img_w, img_h, pad4, roi, flip != 0, &pp);
+  __syncthreads();
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) project_point(pp, raw + 3 * k, out + 3 * k);
+}
+
+}  // namespace
+
+#define FDL_LAUNCHED() (count_launch(), cudaGetLastError())
+
+cudaError_t launch_anchors(const SsdOptions& opt, float* out, int n, cudaStream_t s) {
+  anchors_kernel<<<(n + 255) / 256, 256, 0, s>>>(opt, out, n);
+  return FDL_LAUNCHED();
+}
+
+cudaError_t launch_i2t_setup(const fdl_rect* rois, const int* slot_frame, const int* slot_valid, int n, int img_w, int img_h,
+                             int out_w, int out_h, int keep_aspect, double range_min, double range_max, int flip_mode,
+                             I2TParams* params, const int* n_active, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  i2t_setup_kernel<<<(n + 63) / 64, 64, 0, s>>>(rois, slot_frame, slot_valid, n, img_w, img_h, out_w, out_h, keep_aspect, range_min,
+                                                range_max, flip_mode, params, n_active);
+  return FDL_LAUNCHED();
+}
+
+cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long row_stride, const I2TParams* params, int n,
+                       int out_w, int out_h, float* out, long long out_bstride, uint8_t* out_u8, const int* n_active,
+                       cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  dim3 grid((out_w * out_h + 255) / 256, n);
+  i2t_kernel<<<grid, 256, 0, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, out_u8, n_active);
+  return FDL_LAUNCHED();
+}
+
+cudaError_t launch_ssd_postprocess(const SsdPostArgs& a, cudaStream_t s) {
+  if (a.B <= 0) return cudaSuccess;
+  size_t smem = (size_t)a.N * 5 * sizeof(int);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(ssd_postprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
+  ssd_postprocess_kernel<<<a.B, kPostThreads, smem, s>>>(a);
+  return FDL_LAUNCHED();
+}
+
+cudaError_t launch_face_select(fdl_frame_result* frames, int B, int max_faces, int* slot_frame, int* slot_face, int* n_faces,
+                               int* n_eyes, cudaStream_t s) {
+  face_select_kernel<<<1, 1024, 0, s>>>(frames, B, max_faces, slot_frame, slot_face, n_faces, n_eyes);
+  return FDL_LAUNCHED();
+}
+
+cudaError_t launch_face_roi(const fdl_frame_result* frames, const int* slot_frame, const int* slot_face, int max_slots, int max_faces,
+                            int img_w, int img_h, fdl_rect* rois, int* slot_valid, fdl_face_result* faces, const int* n_faces,
+                            cudaStream_t s) {
+  if (max_slots <= 0) return cudaSuccess;
+  face_roi_kernel<<<(max_slots + 63) / 64, 64, 0, s>>>(frames, slot_frame, slot_face, max_slots, max_faces, img_w, img_h, rois,
+                                                       slot_valid, faces, n_faces);
+  return FDL_LAUNCHED();
+}
+
+cudaError_t launch_landmark_post(const float* raw, long long raw_bstride, const float* flag, long long flag_bstride,
+                                 const I2TParams* params, const fdl_rect* rois, const int* slot_frame, const int* slot_face,
+                                 int max_slots, int max_faces, int tensor_w, int tensor_h, fdl_face_result* faces, fdl_rect* eye_rois,
+                                 int* eye_frame, int* eye_valid, const int* n_faces, cudaStream_t s) {
+  if (max_slots <= 0) return cudaSuccess;
+  landmark_post_kernel<<<max_slots, 128, 0, s>>>(raw, raw_bstride, flag, flag_bstride, params, rois, slot_frame, slot_face, max_slots,
+                                                 max_faces, tensor_w, tensor_h, faces, eye_rois, eye_frame, eye_valid, n_faces);
+  return FDL_LAUNCHED();
+}
+
+cudaError_t launch_iris_post(const float* contour, long long contour_bstride, const float* iris, long long iris_bstride,
+                             const I2TParams* params, const fdl_rect* eye_rois, const int* eye_valid, const int* slot_frame,
+                             const int* slot_face, int max_eye_slots, int max_faces, int tensor_w, int tensor_h,
+                             fdl_face_result* faces, const int* n_eyes, cudaStream_t s) {
+  if (max_eye_slots <= 0) return cudaSuccess;
+  iris_post_kernel<<<max_eye_slots, 96, 0, s>>>(contour, contour_bstride, iris, iris_bstride, params, eye_rois, eye_valid, slot_frame,
+                                                slot_face, max_eye_slots, max_faces, tensor_w, tensor_h, faces, n_eyes);
+  return FDL_LAUNCHED();
+}
+
+cudaError_t launch_face_detection_to_roi(const fdl_detection* det, int img_w, int img_h, int size_mode, fdl_rect* out, int* ok,
+                                         cudaStream_t s) {
+  face_detection_to_roi_kernel<<<1, 1, 0, s>>>(det, img_w, img_h, size_mode, out, ok);
+  return FDL_LAUNCHED();
+}
+cudaError_t launch_eye_rois(const double* lm4xy, int img_w, int img_h, fdl_rect* out2, int* ok, cudaStream_t s) {
+  eye_rois_kernel<<<1, 1, 0, s>>>(lm4xy, img_w, img_h, out2, ok);
+  return FDL_LAUNCHED();
+}
+cudaError_t launch_project(const float* raw, int n, int tensor_w, int tensor_h, int img_w, int img_h, const double* pad4,
+                           const fdl_rect* roi_or_null, int flip, float* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  project_kernel<<<1, 128, 0, s>>>(raw, n, tensor_w, tensor_h, img_w, img_h, pad4, roi_or_null, flip, out);
+  return FDL_LAUNCHED();
+}
+
+}  // namespace fdl

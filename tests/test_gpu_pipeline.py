@@ -1,0 +1,144 @@
+"""Parity step 4: end to end from uint8 frames, through the reference-shaped API and through
+the batched pipeline, against the oracle.  Tolerances: kept anchors exact (except anchors whose oracle
+|logit| < 5e-3), box/keypoint coordinates 1e-3 normalised, landmarks 0.5 px."""
+import numpy as np
+import pytest
+
+from conftest import MODELS
+
+pytestmark = pytest.mark.gpu
+
+
+def _rect(fdl, r):
+    return fdl.Rect(r.x_center, r.y_center, r.width, r.height, r.rotation, r.normalized)
+
+
+def _check_detections(ours, ref, tol=1e-3):
+    assert [d.anchor for d in ours] == [d.anchor for d in ref]
+    for o, e in zip(ours, ref):
+        assert abs(o.score - float(e.score)) <= 1e-3
+        np.testing.assert_allclose(o.data, e.data, atol=tol, rtol=0)
+
+
+def _px(lm, w, h):
+    a = np.asarray([[l.x, l.y] for l in lm]) if not isinstance(lm, np.ndarray) else lm[:, :2]
+    return a * np.array([w, h])
+
+
+def test_reference_call_sequence_on_man(fdl, gpu, man, oracle_pipeline):
+    """lib.rs:20-40 verbatim: detect -> face_detection_to_roi -> landmark -> iris_roi_from_face_landmarks -> iris x2,
+    including the K1 pixel facts decoded from assets/man_bbox.png."""
+    from oracle import glue
+    h, w = man.shape[:2]
+    det = fdl.FaceDetection(fdl.FaceDetectionModel.BackCamera, MODELS, device=gpu)
+    lmk = fdl.FaceLandmark(MODELS + "/face_landmark.tflite", device=gpu)
+    iris = fdl.IrisLandmark(MODELS + "/iris_landmark.tflite", device=gpu)
+    op = oracle_pipeline[glue.BACK_CAMERA]
+    ref_faces, ref = op.run(man)
+
+    faces = det.infer(man)
+    _check_detections(faces, ref_faces)
+    b = faces[0].bbox()
+    # K1 (assets/man_bbox.png): Rect::at(int(xmin*W), int(ymin*H)).of_size(int(w*W), int(h*H))
+    assert (int(b.xmin * w), int(b.ymin * h), int(b.width * w), int(b.height * h)) == (195, 74, 139, 139)
+
+    roi = fdl.face_detection_to_roi(faces[0], (w, h))
+    lm = lmk.infer(man, roi)
+    assert len(lm) == 468
+    assert abs(lmk.last_face_flag - 50.996) < 0.05
+    d = np.abs(_px(lm, w, h) - _px(ref[0]["landmarks"], w, h))
+    assert d.max() < 0.5, d.max()
+
+    left_roi, right_roi = fdl.iris_roi_from_face_landmarks(lm, (w, h))
+    right = iris.infer(man, right_roi, True)
+    left = iris.infer(man, left_roi, False)
+    for ours, key in ((right, "right"), (left, "left")):
+        rc, ri = ref[0][key]
+        assert np.abs(_px(ours.contour, w, h) - _px(rc, w, h)).max() < 0.5
+        assert np.abs(_px(ours.iris, w, h) - _px(ri, w, h)).max() < 0.5
+    assert len(left.eyeball_contour()) == 15
+    for o in (det, lmk, iris):
+        o.close()
+
+
+@pytest.mark.parametrize("model", [0, 2, 3])
+def test_other_detectors_on_man(fdl, gpu, man, model):
+    from oracle import pipeline
+    det = fdl.FaceDetection(fdl.FaceDetectionModel(model), MODELS, device=gpu)
+    ref = pipeline.FaceDetection(model, MODELS).infer(man)
+    _check_detections(det.infer(man), ref)
+    det.close()
+
+
+def test_detector_with_roi(fdl, gpu, man):
+    """FaceDetection::infer(image, Some(roi)): coordinates stay relative to the ROI letterbox (face_detection.rs:265)."""
+    from oracle import glue, pipeline
+    roi = glue.Rect(0.5, 0.45, 0.7, 0.8, 0.1, True)
+    det = fdl.FaceDetection(fdl.FaceDetectionModel.BackCamera, MODELS, device=gpu)
+    ref = pipeline.FaceDetection(glue.BACK_CAMERA, MODELS).infer(man, roi)
+    _check_detections(det.infer(man, _rect(fdl, roi)), ref, tol=2e-3)
+    det.close()
+
+
+def test_batched_pipeline_matches_oracle(fdl, gpu, oracle_pipeline):
+    """Pipeline (device-side fan-out) on G2 1080p frames + one face-less frame."""
+    import synth_frames
+    from oracle import glue
+    n = 5
+    frames = synth_frames.face_frames(n)
+    frames[3] = synth_frames.noise_frames(1, seed=9)[0] // 8 + 100   # no face: fan-out 0 for this frame
+    pipe = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (1920, 1080), max_batch=8, max_faces=2, model_dir=MODELS, device=gpu)
+    res = pipe.run(frames)
+    assert len(res) == n
+    op = oracle_pipeline[glue.BACK_CAMERA]
+    for i in range(n):
+        ref_faces, ref = op.run(frames[i], max_faces=2)
+        _check_detections(res[i].detections, ref_faces)
+        assert len(res[i].faces) == min(len(ref_faces), 2)
+        for f, r in zip(res[i].faces, ref):
+            for k in ("x_center", "y_center", "width", "height", "rotation"):
+                assert abs(getattr(f.roi, k) - getattr(r["roi"], k)) < 2e-3
+            assert (f.landmarks is not None) == (len(r["landmarks"]) > 0)
+            if f.landmarks is None:
+                continue
+            assert np.abs(_px(f.landmarks, 1920, 1080) - _px(r["landmarks"], 1920, 1080)).max() < 0.5
+            for ours_c, ours_i, key in ((f.left_contour, f.left_iris, "left"), (f.right_contour, f.right_iris, "right")):
+                rc, ri = r[key]
+                assert np.abs(_px(ours_c, 1920, 1080) - _px(rc, 1920, 1080)).max() < 0.5
+                assert np.abs(_px(ours_i, 1920, 1080) - _px(ri, 1920, 1080)).max() < 0.5
+    # the same frames from device memory and through submit/collect give identical results
+    import torch
+    t1 = pipe.submit(torch.from_numpy(frames[:3]).cuda())
+    t2 = pipe.submit(frames[3:])
+    again = pipe.collect(t1) + pipe.collect(t2)
+    for a, b in zip(res, again):
+        assert [d.anchor for d in a.detections] == [d.anchor for d in b.detections]
+        for fa, fb in zip(a.faces, b.faces):
+            if fa.landmarks is not None:
+                np.testing.assert_array_equal(fa.landmarks, fb.landmarks)
+                np.testing.assert_array_equal(fa.left_iris, fb.left_iris)
+    assert pipe.last_device_ms > 0
+    pipe.close()
+
+
+def test_detection_only_pipeline_and_errors(fdl, gpu):
+    import synth_frames
+    frames = synth_frames.face_frames(2, 640, 480)
+    pipe = fdl.Pipeline(fdl.FaceDetectionModel.Full, (640, 480), max_batch=4, run_landmarks=False, model_dir=MODELS, device=gpu)
+    res = pipe.run(frames)
+    det = fdl.FaceDetection(fdl.FaceDetectionModel.Full, MODELS, device=gpu)
+    for i in range(2):
+        single = det.infer(frames[i])
+        assert [d.anchor for d in single] == [d.anchor for d in res[i].detections]
+        for a, b in zip(single, res[i].detections):
+            np.testing.assert_array_equal(a.data, b.data)
+    with pytest.raises(fdl.FdlError):
+        pipe.run(synth_frames.noise_frames(1, 320, 240))       # wrong frame size
+    with pytest.raises(fdl.FdlError):
+        pipe.run(synth_frames.noise_frames(5, 640, 480))       # more than max_batch
+    with pytest.raises(fdl.FdlError):
+        fdl.FaceDetection(fdl.FaceDetectionModel.FullSparse, MODELS, device=gpu)   # outside the hot path
+    with pytest.raises(fdl.FdlError) as e:
+        fdl.FaceLandmark("/nonexistent/face_landmark.tflite", device=gpu)
+    assert e.value.code == -2
+    pipe.close(); det.close()

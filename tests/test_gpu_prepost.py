@@ -1,0 +1,216 @@
+"""Parity steps 1 and 3: pre-processing bit-exact with OpenCV, post-processing exact on
+identical raw tensors.  Everything goes through the C ABI (ctypes)."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import MODELS, rng
+
+pytestmark = pytest.mark.gpu
+
+
+def _rect(fdl, r):
+    return fdl.Rect(r.x_center, r.y_center, r.width, r.height, r.rotation, r.normalized)
+
+
+# ---------------------------------------------------------------------------------------------- anchors
+@pytest.mark.parametrize("model,n,sha", [(0, 896, "7527f7bf39f988ed"), (1, 896, "7527f7bf39f988ed"), (2, 896, "7527f7bf39f988ed"),
+                                         (3, 2304, "30f2249dab7a1447")])
+def test_anchors_bit_exact(fdl, gpu, model, n, sha):
+    """ssd_generate_anchors (face_detection.rs:366-413): bit-exact, KAT K3."""
+    import hashlib
+    from oracle import glue
+    det = fdl.FaceDetection(fdl.FaceDetectionModel(model), MODELS, device=gpu)
+    a = det.anchors
+    assert a.shape == (n, 2)
+    assert hashlib.sha256(a.tobytes()).hexdigest()[:16] == sha
+    np.testing.assert_array_equal(a, glue.ssd_generate_anchors(model))
+    det.close()
+
+
+# ------------------------------------------------------------------------------------ image_to_tensor
+def _i2t_case(fdl, image, roi, size, keep, rng_, flip):
+    from oracle import glue
+    ref = glue.image_to_tensor(image, roi, size, keep, rng_, flip)
+    t, pad, u8 = fdl.image_to_tensor(image, _rect(fdl, roi) if roi is not None else None, size, keep, rng_, flip)
+    return ref, t, pad, u8
+
+
+@pytest.mark.parametrize("size", [128, 192, 256])
+def test_letterbox_bit_exact(fdl, gpu, man, size):
+    """Detector mode (roi=None, keep_aspect, (-1,1)) on man.jpg and on 1080p frames: every pixel equal."""
+    import synth_frames
+    for img in (man, synth_frames.face_frame(0), synth_frames.noise_frames(1, seed=5)[0], synth_frames.noise_frames(1, 640, 480, 6)[0],
+                synth_frames.noise_frames(1, 333, 517, 7)[0]):
+        ref, t, pad, u8 = _i2t_case(fdl, img, None, (size, size), True, (-1.0, 1.0), False)
+        assert pad == tuple(ref.padding)
+        np.testing.assert_array_equal(u8, ref.u8)
+        np.testing.assert_array_equal(t, ref.tensor_data)
+
+
+def test_rotated_warp_matches_opencv(fdl, gpu, man):
+    """Landmark mode (keep_aspect=false, (0,1)): rotated ROI warped straight to 192x192.  The 3x3 solve
+    differs from OpenCV's SVD in the last bits, so allow <= 1e-4 of the pixels to differ by one level."""
+    from oracle import glue
+    import synth_frames
+    r = rng(11)
+    frames = [man, synth_frames.face_frame(1)]
+    for k in range(12):
+        img = frames[k % 2]
+        roi = glue.Rect(r.uniform(0.2, 0.8), r.uniform(0.2, 0.8), r.uniform(0.1, 0.9), r.uniform(0.1, 0.9), r.uniform(-math.pi, math.pi), True)
+        ref, t, pad, u8 = _i2t_case(fdl, img, roi, (192, 192), False, (0.0, 1.0), False)
+        diff = np.abs(u8.astype(int) - ref.u8.astype(int))
+        assert diff.max() <= 1 and (diff > 0).mean() <= 1e-4, (k, diff.max(), (diff > 0).mean())
+        assert pad == tuple(ref.padding)
+        same = diff == 0
+        np.testing.assert_array_equal(t[same], ref.tensor_data[same])
+
+
+def test_iris_mode_matches_opencv(fdl, gpu, man):
+    """Iris mode (keep_aspect, (0,1), flip): warp to the ROI's native integer size, resize to 64x64, flip."""
+    from oracle import glue
+    import synth_frames
+    r = rng(12)
+    frames = [man, synth_frames.face_frame(2)]
+    for k in range(16):
+        img = frames[k % 2]
+        h, w = img.shape[:2]
+        side = r.uniform(20, 300)  # px, square in pixels like SquareLong ROIs
+        roi = glue.Rect(r.uniform(0.3, 0.7), r.uniform(0.3, 0.7), side / w, side / h, r.uniform(-0.6, 0.6), True)
+        ref, t, pad, u8 = _i2t_case(fdl, img, roi, (64, 64), True, (0.0, 1.0), bool(k & 1))
+        diff = np.abs(u8.astype(int) - ref.u8.astype(int))
+        assert diff.max() <= 1 and (diff > 0).mean() <= 2e-3, (k, diff.max(), (diff > 0).mean())
+        assert pad == tuple(ref.padding)
+
+
+def test_letterboxed_roi_with_border_stage(fdl, gpu, man):
+    """keep_aspect with a non-square ROI exercises copyMakeBorder + the first resize (transform.rs:251-274)."""
+    from oracle import glue
+    for roi in (glue.Rect(0.5, 0.5, 0.6, 0.3, 0.0, True), glue.Rect(0.45, 0.55, 0.3, 0.7, 0.2, True), glue.Rect(0.5, 0.5, 0.31, 0.47, -0.4, True)):
+        ref, t, pad, u8 = _i2t_case(fdl, man, roi, (128, 128), True, (-1.0, 1.0), False)
+        diff = np.abs(u8.astype(int) - ref.u8.astype(int))
+        assert diff.max() <= 1 and (diff > 0).mean() <= 2e-3
+        assert pad == tuple(ref.padding)
+
+
+# ------------------------------------------------------------------------------------ SSD post-process
+def _oracle_post(det_model, reg, cls, padding):
+    from oracle import glue
+    anchors = glue.ssd_generate_anchors(det_model)
+    size = glue.SSD_OPTIONS[det_model][1]
+    boxes = glue.decode_boxes(reg, anchors, float(size))
+    scores = glue.get_sigmoid_score(cls)
+    dets = glue.convert_to_detections(boxes, scores)
+    clusters = []
+    pruned = glue.non_maximum_suppression(dets, clusters=clusters)
+    return [d.anchor for d in dets], clusters, glue.detection_letterbox_removal(pruned, padding)
+
+
+def _random_raw(r, n, n_faces, size):
+    """Raw tensors with a few clusters of overlapping high-score anchors + background."""
+    from oracle import glue
+    reg = r.normal(0, 20, (n, 16)).astype(np.float32)
+    cls = r.normal(-6, 2, (n, 1)).astype(np.float32)
+    for _ in range(n_faces):
+        c = int(r.integers(0, n))
+        base = r.normal(0, 10, 16).astype(np.float32)
+        base[2:4] = r.uniform(0.15, 0.5, 2) * size
+        for j in range(int(r.integers(1, 7))):
+            k = (c + int(r.integers(-3, 4))) % n
+            reg[k] = base + r.normal(0, 2, 16)
+            cls[k, 0] = r.uniform(0.2, 6)
+    return reg, cls
+
+
+@pytest.mark.parametrize("model", [1, 2, 3])
+def test_postprocess_exact(fdl, gpu, model):
+    """Survivor set, cluster membership and top anchors exact; weighted boxes to 1e-6."""
+    det = fdl.FaceDetection(fdl.FaceDetectionModel(model), MODELS, device=gpu)
+    n, size = det.num_anchors, det.input_size
+    r = rng(100 + model)
+    for case in range(12):
+        reg, cls = _random_raw(r, n, case % 5, size)
+        if case == 7:   # exact score ties: stable sort keeps anchor order (nms.rs:137)
+            idx = np.nonzero(cls[:, 0] > 0)[0]
+            cls[idx, 0] = cls[idx[0], 0] if len(idx) else 0
+        if case == 8:   # zero-area / inverted boxes are dropped (face_detection.rs:322)
+            reg[:, 2] = -np.abs(reg[:, 2])
+        if case == 9:   # everything below threshold
+            cls[:] = -3
+        padding = (0.0, 0.21875, 0.0, 0.21875) if case % 2 else (0.0, 0.0, 0.0, 0.0)
+        surv, clusters, ref = _oracle_post(model, reg, cls, padding)
+        tr = {}
+        ours = det.postprocess(reg, cls, padding, max_detections=256, trace=tr)
+        assert tr["survivors"][0] == surv
+        assert len(ours) == len(ref)
+        anchor_to_cluster = {}
+        for ci, members in enumerate(clusters):
+            for a in members:
+                anchor_to_cluster[a] = ci
+        assert [anchor_to_cluster.get(a, -1) for a in surv] == tr["survivor_cluster"][0]
+        for o, e in zip(ours, ref):
+            assert o.anchor == e.anchor
+            assert o.score == float(e.score)
+            np.testing.assert_allclose(o.data, e.data, atol=1e-6, rtol=0)
+    det.close()
+
+
+def test_postprocess_batch_and_capacity(fdl, gpu):
+    det = fdl.FaceDetection(fdl.FaceDetectionModel.BackCamera, MODELS, device=gpu)
+    r = rng(5)
+    regs, clss = zip(*[_random_raw(r, 896, 3, 256) for _ in range(9)])
+    out = det.postprocess(np.stack(regs), np.stack(clss), (0, 0, 0, 0), max_detections=64)
+    for b in range(9):
+        _, _, ref = _oracle_post(1, regs[b], clss[b], (0, 0, 0, 0))
+        assert [d.anchor for d in out[b]] == [d.anchor for d in ref]
+    # capacity error instead of silent truncation
+    reg, cls = _random_raw(r, 896, 4, 256)
+    _, _, ref = _oracle_post(1, reg, cls, (0, 0, 0, 0))
+    if len(ref) > 1:
+        with pytest.raises(fdl.FdlError) as e:
+            det.postprocess(reg, cls, (0, 0, 0, 0), max_detections=1)
+        assert e.value.code == -5
+    det.close()
+
+
+# ------------------------------------------------------------------------------------ ROI helpers
+def test_roi_functions_match(fdl, gpu):
+    from oracle import glue
+    r = rng(21)
+    for k in range(20):
+        data = r.uniform(0.1, 0.9, (8, 2)).astype(np.float32)
+        data[1] = data[0] + r.uniform(0.05, 0.3, 2).astype(np.float32)
+        size = (int(r.integers(100, 2000)), int(r.integers(100, 2000)))
+        for mode in (None, 0, 1, 2):
+            ref = glue.face_detection_to_roi(glue.Detection(data, np.float32(0.9)), size, mode)
+            ours = fdl.face_detection_to_roi(fdl.Detection(data, 0.9), size, None if mode is None else fdl.SizeMode(mode))
+            for f in ("x_center", "y_center", "width", "height", "rotation"):
+                assert abs(getattr(ours, f) - getattr(ref, f)) <= 1e-12 * max(1.0, abs(getattr(ref, f))), (k, mode, f)
+        lm = r.uniform(0.2, 0.8, (468, 3))
+        rl, rr = glue.iris_roi_from_face_landmarks(lm, size)
+        ol, orr = fdl.iris_roi_from_face_landmarks([fdl.Landmark(*p) for p in lm], size)
+        for a, b in ((ol, rl), (orr, rr)):
+            for f in ("x_center", "y_center", "width", "height", "rotation"):
+                assert abs(getattr(a, f) - getattr(b, f)) <= 1e-12 * max(1.0, abs(getattr(b, f)))
+    # "bbox must be normalized" (transform.rs:52)
+    bad = np.zeros((8, 2), np.float32)
+    bad[0] = (-2.0, 0.0)
+    with pytest.raises(fdl.FdlError):
+        fdl.face_detection_to_roi(fdl.Detection(bad, 0.9), (100, 100))
+    with pytest.raises(fdl.FdlError):
+        fdl.iris_roi_from_face_landmarks([fdl.Landmark(0, 0, 0)] * 10, (100, 100))
+
+
+def test_project_landmarks_match(fdl, gpu):
+    from oracle import glue
+    r = rng(22)
+    for k in range(12):
+        raw = r.uniform(-20, 220, (468 if k % 2 else 71, 3)).astype(np.float32)
+        roi = glue.Rect(r.uniform(0.2, 0.8), r.uniform(0.2, 0.8), r.uniform(0.1, 0.9), r.uniform(0.1, 0.9), r.uniform(-3, 3), True) if k % 3 else None
+        pad = (0.0, 0.0, 0.0, 0.0) if k % 4 else (1.1e-16, 0.0, 1.1e-16, 0.0)
+        if k == 5:
+            pad = (0.0, 0.21875, 0.0, 0.21875)
+        ref = glue.project_landmarks(raw, (192, 192), (540, 360), pad, roi, bool(k & 1))
+        ours = fdl.project_landmarks(raw, (192, 192), (540, 360), pad, _rect(fdl, roi) if roi is not None else None, bool(k & 1))
+        np.testing.assert_allclose(ours, ref, atol=2e-7, rtol=0)
