@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the detect -> landmark -> iris path on synthetic 1080p frames.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A step is one batch of B face-bearing 1080p frames (generator G2) per GPU through the whole
+pipeline of lib.rs:20-40: BlazeFace back-256 detection + decode + weighted NMS, face ROI warp, FaceMesh-192,
+eye ROI warps, iris-64 for both eyes.  One process per GPU, frames sharded by rank, no collective on the
+data path (the path has no exchange step); `value` = frames all ranks processed / max-over-ranks time.
+
+* `value`: inputs already resident in HBM (a [B,1080,1920,3] uint8 CUDA tensor, 1.6 GB at B=256 > L2), timed
+  with CUDA events inside the library on the compute stream.
+* `e2e`:   the same metric through the public API with pinned HOST frames: H2D of every frame and D2H of
+  every result inside the timed region (double-buffered submit/collect), wall clock around the loop with a
+  device synchronize on both sides.
+* `roofline`: the fused conv / BlazeBlock kernel family (every launch of the three networks): algorithmic
+  bytes of its launches (each launch's input + residual + output activations, from the planner) divided by
+  the CUDA-event time of the network stages, against the measured HBM copy peak (MEASURED_PEAKS.json).
+* `cpu_baseline` / `--impl reference`: the restated reference CPU path (oracle/: cv2 + torch-CPU + numpy; the
+  reference's own Rust/TFLite build is impossible here) timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+MODELS = os.path.join(ROOT, "models")
+W, H = 1920, 1080
+METRIC = "frames/sec detect+landmark+iris"
+UNIT = "frames/s"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=3)
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def _dist():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def _plan_numbers():
+    """Algorithmic bytes and flops per item of the three planned graphs (no GPU needed: plan-only handles)."""
+    import rs_face_detection_tflite_b200 as fdl
+    out = {}
+    for key, f in (("det", "face_detection_back.tflite"), ("lmk", "face_landmark.tflite"), ("iris", "iris_landmark.tflite")):
+        n = fdl.Net(os.path.join(MODELS, f), device=-1)
+        d = n.describe()
+        m = re.search(r"-> (\d+) launches.*block-fused floor (\d+) bytes/item; (\d+) flop/item", d)
+        out[key] = {"launches": int(m.group(1)), "bytes": int(m.group(2)), "flops": int(m.group(3))}
+        n.close()
+    return out
+
+
+def cpu_reference_fps(n_frames, frames=None, threads=None):
+    """Restated reference CPU path on `n_frames` G2 frames; returns (frames/s, threads used)."""
+    import cv2
+    import torch
+    import synth_frames
+    from oracle import glue, pipeline
+    if threads:
+        torch.set_num_threads(threads)
+        cv2.setNumThreads(threads)
+    p = pipeline.Pipeline(glue.BACK_CAMERA, MODELS)
+    if frames is None:
+        frames = synth_frames.face_frames(min(n_frames, 4))
+    p.run(frames[0])  # warm-up (oneDNN primitive caches)
+    t0 = time.perf_counter()
+    for i in range(n_frames):
+        p.run(frames[i % len(frames)])
+    dt = time.perf_counter() - t0
+    return n_frames / dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank, world, local = _dist()
+    if rank != 0:
+        return
+    import synth_frames
+    per_step = args.ref_frames
+    frames = synth_frames.face_frames(4)
+    times = []
+    import torch
+    from oracle import glue, pipeline
+    p = pipeline.Pipeline(glue.BACK_CAMERA, MODELS)
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        for i in range(per_step):
+            p.run(frames[i % 4])
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    v = per_step * args.steps / total
+    cores = torch.get_num_threads()
+    sample = "%d G2 1080p frames per step, batch 1, restated reference CPU path (cv2 + torch-CPU f32 + numpy), %d threads of %d host cores" % (
+        per_step, cores, os.cpu_count())
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "full detect(back-256)->landmark(192)->iris(64, L+R) pipeline on synthetic 1080p G2 frames, CPU, batch 1",
+                   "frames_per_step": per_step},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args):
+    import torch
+    import rs_face_detection_tflite_b200 as fdl
+    from rs_face_detection_tflite_b200 import _lib
+    import ctypes
+    import synth_frames
+
+    rank, world, local = _dist()
+    if fdl.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    B = args.batch
+    pipe = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (W, H), max_batch=B, max_faces=1, model_dir=MODELS, device=local)
+
+    # synthetic G2 frames: `uniq` distinct frames tiled to the batch (every frame carries exactly one face)
+    uniq = min(B, args.unique_frames)
+    base = synth_frames.face_frames(uniq, start=rank * uniq)
+    host = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
+    for i in range(B):
+        host[i] = torch.from_numpy(base[i % uniq])
+    host2 = host.clone().pin_memory()
+    dev = host.cuda(non_blocking=False)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident: `value` ----------------
+    for _ in range(args.warmup):
+        pipe.collect_raw(pipe.submit(dev))
+    n_faces = sum(pipe._frames[i].n_faces for i in range(B))
+    n_lm = sum(pipe._faces[i].has_landmarks for i in range(B))
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = fdl.launch_count()
+    dev_ms, stage = [], np.zeros(10)
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        pipe.collect_raw(pipe.submit(dev))
+        dev_ms.append(pipe.last_device_ms)       # CUDA events on the compute stream around all kernels of the step
+        stage += np.array(pipe.stage_ms)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = fdl.launch_count() - launches0
+    total_ms = float(sum(dev_ms))
+    stage /= args.steps
+
+    # ---------------- host-sourced: `e2e` ----------------
+    bufs = [host, host2]
+    for i in range(max(1, args.warmup // 2)):
+        pipe.collect_raw(pipe.submit(bufs[i % 2]))
+    barrier()
+    t0 = time.perf_counter()
+    pending = []
+    for s in range(args.steps):
+        pending.append(pipe.submit(bufs[s % 2]))
+        if len(pending) == 2:
+            pipe.collect_raw(pending.pop(0))
+    while pending:
+        pipe.collect_raw(pending.pop(0))
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d_ms = pipe.stage_ms[0]
+    barrier()
+    clocks = sampler.summary()
+
+    # ---------------- p50 single-frame latency through the API (batch 1, host frame) ----------------
+    lat = []
+    one = host[:1]
+    for i in range(args.latency_iters + 5):
+        t1 = time.perf_counter()
+        pipe.collect_raw(pipe.submit(one))
+        if i >= 5:
+            lat.append(1e3 * (time.perf_counter() - t1))
+
+    # max over ranks
+    t_dev = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    total_ms_max, e2e_s_max = float(t_dev[0]), float(t_dev[1])
+    frames_total = world * B * args.steps
+    value = frames_total / (total_ms_max / 1e3)
+    e2e = frames_total / e2e_s_max
+
+    if rank == 0:
+        plan = _plan_numbers()
+        peak, peak_src = _peaks()
+        # fused conv family: all launches of the three nets (1 face and 2 eyes per frame on G2 frames)
+        algo_bytes = B * (plan["det"]["bytes"] + plan["lmk"]["bytes"] + 2 * plan["iris"]["bytes"])
+        net_ms = float(stage[2] + stage[5] + stage[7])
+        n_launch = plan["det"]["launches"] + plan["lmk"]["launches"] + plan["iris"]["launches"]
+        achieved = algo_bytes / (net_ms / 1e3) / 1e9
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, cores = cpu_reference_fps(args.cpu_frames, base)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "%d G2 1080p frames, batch 1, restated reference CPU path (oracle: cv2 + torch-CPU f32 + numpy; the Rust/TFLite "
+                             "reference cannot be built offline), %d threads of %d host cores" % (args.cpu_frames, cores, os.cpu_count())}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "full detect(back-256)->landmark(192)->iris(64, L+R) pipeline on synthetic 1080p G2 frames (BASELINE config 5; "
+                                   "contains config 2 as its detection stage)",
+                       "frames_per_step_per_gpu": B, "frame": "1920x1080x3 u8", "faces_per_frame": n_faces / B, "landmark_sets_per_frame": n_lm / B,
+                       "l2_policy": "inputs larger than L2: %.2f GB of frames per step" % (B * W * H * 3 / 1e9), "parallelism": "frames sharded by rank, no collective"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * W * H * 3,
+                    "d2h_bytes_per_step": B * (ctypes.sizeof(_lib.CFrameResult) + ctypes.sizeof(_lib.CFaceResult)), "h2d_ms_per_step": h2d_ms},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "fused_conv_kernel (all %d launches of the three networks per step)" % n_launch,
+                         "algorithmic_bytes_per_step": algo_bytes, "kernel_ms_per_step": net_ms, "peak_source": peak_src + " HBM copy"},
+            "stage_ms": {k: float(v) for k, v in zip(("h2d", "det_pre", "det_net", "ssd_post", "face_warp", "lmk_net", "lmk_post_eye_warp", "iris_net",
+                                                      "iris_post", "d2h"), stage)},
+            "p50_frame_latency_ms": float(np.median(lat)),
+            "wall_s_device_loop": t_wall,
+        }
+        if cpu:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out))
+    pipe.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="frames per step per GPU")
+    ap.add_argument("--unique-frames", type=int, default=16)
+    ap.add_argument("--cpu-frames", type=int, default=60, help="frames of the cpu_baseline sample")
+    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of --impl reference")
+    ap.add_argument("--latency-iters", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

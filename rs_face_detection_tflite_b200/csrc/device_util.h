@@ -41,7 +41,10 @@ struct PinBuf {
 
 // Copies `n` equally-sized images (host or device) into one contiguous device buffer
 // [n, height, width*3] on `stream`.  Returns FDL_OK or an error code (message set).
-inline int stage_frames(const fdl_image* images, int n, DevBuf<uint8_t>* dst, cudaStream_t stream, int* w_out, int* h_out) {
+// When `direct` is given and the images are device-resident, tightly packed and contiguous, no copy is
+// made: *direct receives the caller's pointer (which must stay valid until the work is collected).
+inline int stage_frames(const fdl_image* images, int n, DevBuf<uint8_t>* dst, cudaStream_t stream, int* w_out, int* h_out,
+                        const uint8_t** direct = nullptr) {
   if (!images || n <= 0) return set_error(FDL_ERR_INVALID, "no images given");
   const int w = images[0].width, h = images[0].height;
   if (w <= 0 || h <= 0) return set_error(FDL_ERR_INVALID, "image has non-positive size");
@@ -50,6 +53,13 @@ inline int stage_frames(const fdl_image* images, int n, DevBuf<uint8_t>* dst, cu
     if (!images[i].data) return set_error(FDL_ERR_INVALID, "image data pointer is null");
     if (images[i].width != w || images[i].height != h) return set_error(FDL_ERR_INVALID, "all images of a batch must have the same size");
     if (images[i].row_stride != 0 && (size_t)images[i].row_stride < row) return set_error(FDL_ERR_INVALID, "row_stride smaller than width*3");
+  }
+  if (direct) {
+    bool contiguous = true;
+    for (int i = 0; i < n && contiguous; ++i)
+      contiguous = images[i].mem == FDL_MEM_DEVICE && (images[i].row_stride == 0 || (size_t)images[i].row_stride == row) &&
+                   images[i].data == images[0].data + (size_t)i * frame;
+    if (contiguous) { *direct = images[0].data; *w_out = w; *h_out = h; return FDL_OK; }
   }
   FDL_CUDA_TRY(dst->reserve(frame * (size_t)n));
   // coalesce runs of frames that are contiguous in the caller's memory into one copy
@@ -68,6 +78,7 @@ inline int stage_frames(const fdl_image* images, int n, DevBuf<uint8_t>* dst, cu
     }
     i = j;
   }
+  if (direct) *direct = dst->p;
   *w_out = w; *h_out = h;
   return FDL_OK;
 }

@@ -358,7 +358,9 @@ FDL_HD void decode_box(const float* raw, float ax, float ay, float scale, float*
   d[2] = cx + hx; d[3] = cy + hy;
 }
 // get_sigmoid_score (face_detection.rs:300-314) + sigmoid (transform.rs:111-113), f32.
-FDL_HD float sigmoid_f32(float x) { return 1.0f / (1.0f + expf(-x)); }
+// `(-x).exp()` is libm's expf on the reference's host (correctly rounded in practice); CUDA's expf is only
+// good to 2 ulp, so the exponential is evaluated in f64 and rounded once to f32.
+FDL_HD float sigmoid_f32(float x) { return 1.0f / (1.0f + (float)exp(-(double)x)); }
 FDL_HD float ssd_score(float raw) {
   float x = raw < -80.0f ? -80.0f : (raw > 80.0f ? 80.0f : raw);
   return sigmoid_f32(x);

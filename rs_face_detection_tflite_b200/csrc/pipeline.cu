@@ -176,7 +176,8 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
   // ---- copy-in
   FDL_CUDA_TRY(cudaEventRecord(lane->ev_h2d_start, p->s_in));
   int w, h;
-  int rc = stage_frames(frames, n, &lane->frames, p->s_in, &w, &h);
+  const uint8_t* fptr = nullptr;   // lane->frames, or the caller's device memory when it is already contiguous
+  int rc = stage_frames(frames, n, &lane->frames, p->s_in, &w, &h, &fptr);
   if (rc) return rc;
   FDL_CUDA_TRY(cudaEventRecord(lane->ev_h2d, p->s_in));
 
@@ -193,7 +194,7 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
   // FaceDetection::infer: image_to_tensor(keep_aspect, (-1,1)) -> net -> SSD post-processing
   FDL_CUDA_TRY(launch_i2t_setup(nullptr, nullptr, nullptr, n, W, H, p->S, p->S, 1, -1.0, 1.0, 0, p->det_params.p, nullptr, cs));
   TView div = p->det->input_view(n);
-  FDL_CUDA_TRY(launch_i2t(lane->frames.p, fstride, row, p->det_params.p, n, p->S, p->S, div.p, div.bstride, nullptr, nullptr, cs));
+  FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, p->det_params.p, n, p->S, p->S, div.p, div.bstride, nullptr, nullptr, cs));
   FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[1], cs));
   FDL_CUDA_TRY(p->det->forward(n, cs));
   FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[2], cs));
@@ -218,7 +219,7 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
     FDL_CUDA_TRY(launch_i2t_setup(p->face_rois.p, p->slot_frame.p, p->face_valid.p, F, W, H, p->LS, p->LS, 0, 0.0, 1.0, 0, p->face_params.p,
                                   n_faces, cs));
     TView liv = p->lmk->input_view(F);
-    FDL_CUDA_TRY(launch_i2t(lane->frames.p, fstride, row, p->face_params.p, F, p->LS, p->LS, liv.p, liv.bstride, nullptr, n_faces, cs));
+    FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, p->face_params.p, F, p->LS, p->LS, liv.p, liv.bstride, nullptr, n_faces, cs));
     FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[4], cs));
     FDL_CUDA_TRY(p->lmk->forward(F, cs, n_faces));
     FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[5], cs));
@@ -232,7 +233,7 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
       FDL_CUDA_TRY(launch_i2t_setup(p->eye_rois.p, p->eye_frame.p, p->eye_valid.p, E, W, H, p->IS, p->IS, 1, 0.0, 1.0, 2, p->eye_params.p, n_eyes,
                                     cs));
       TView iiv = p->iris->input_view(E);
-      FDL_CUDA_TRY(launch_i2t(lane->frames.p, fstride, row, p->eye_params.p, E, p->IS, p->IS, iiv.p, iiv.bstride, nullptr, n_eyes, cs));
+      FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, p->eye_params.p, E, p->IS, p->IS, iiv.p, iiv.bstride, nullptr, n_eyes, cs));
       FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[6], cs));
       FDL_CUDA_TRY(p->iris->forward(E, cs, n_eyes));
       FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[7], cs));
