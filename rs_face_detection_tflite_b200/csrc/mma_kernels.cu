@@ -1,0 +1,361 @@
+// mma_kernels.cu -- the tensor-core BlazeBlock kernel (sm_100a: TMA + tcgen05 + TMEM).
+//
+// One launch computes, for a batch of NHWC f32 feature maps,
+//     out = act( PW1x1( DW3x3(in) + b_dw ) + b_pw + skip )
+// (SURVEY.md A.2 "Single BlazeBlock" and the two halves of the double / bottleneck blocks) with
+//   * the (TH+2)x(TW+2)xC input halo tile brought in by ONE TMA tensor load per tile (out-of-bounds
+//     coordinates are zero-filled by the TMA unit == TFLite SAME padding), double-buffered on mbarriers,
+//   * the depthwise 3x3 on the CUDA cores straight out of shared memory (sliding 3-row window in
+//     registers), written as the A operand of the pointwise GEMM in the UMMA K-major core-matrix layout,
+//   * the pointwise 1x1 contraction [128 pixels x Cin] x [Cin x Cout] on the 5th-gen tensor cores:
+//     tcgen05.mma kind::tf32, M=128, accumulator in TMEM.  fp32 fidelity is kept by operand splitting:
+//     x = hi + lo with hi = tf32(x), lo = x - hi, so A*W = A_hi*W + A_lo*W (+ A_hi*W_lo when the weights are
+//     not tf32-exact; the detectors' f16-stored weights are) -- error ~2^-22 per product, same order as fp32,
+//   * epilogue out of TMEM (tcgen05.ld): + bias, + residual (identity from the resident input tile, or
+//     direct / MAX_POOL 2x2 / zero-channel-PAD from global), RELU / PRELU, staged in shared memory and
+//     written with ONE TMA tensor store per tile.
+// The depthwise result and the pointwise accumulator never touch HBM: per tile the kernel reads the
+// input tile once and writes the output tile once (the "block-fused floor" of SURVEY.md 8d).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <mutex>
+
+#include <cudaTypedefs.h>
+
+#include "mma_kernels.cuh"
+#include "plan.h"
+#include "sm100_ptx.cuh"
+
+namespace fdl {
+
+void count_launch();
+
+namespace {
+
+constexpr int TH = 8, TW = 16;            // output tile: 128 pixels == UMMA M
+constexpr int kThreads = 192;             // 6 warps; warps 0..3 own the 128 TMEM lanes in the epilogue
+constexpr int kPlanePad = 16;             // bytes added to each 2 KB channel-quad plane of A (bank spreading)
+constexpr int kPlaneBytes = TH * TW * 16 + kPlanePad;   // LBO of the A operand
+
+struct SmemLayout {
+  int bias, alpha, in0, in_stage, a_hi, a_lo, w, out, total;
+};
+
+__host__ __device__ inline int align_up_i(int v, int a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline SmemLayout smem_layout(int C, int N, int Np, int stages, int wsplit) {
+  SmemLayout L;
+  int off = 64;                                   // barriers + tmem pointer
+  L.bias = off; off += Np * 4;
+  L.alpha = off; off += Np * 4;
+  off = align_up_i(off, 128);
+  L.in_stage = align_up_i((TH + 2) * (TW + 2) * C * 4, 128);
+  L.in0 = off; off += stages * L.in_stage;
+  L.a_hi = off; off += (C / 4) * kPlaneBytes;
+  off = align_up_i(off, 128);
+  L.a_lo = off; off += (C / 4) * kPlaneBytes;
+  off = align_up_i(off, 128);
+  L.w = off; off += wsplit * (C / 4) * Np * 16;
+  off = align_up_i(off, 128);
+  L.out = off; off += TH * TW * N * 4;
+  L.total = align_up_i(off, 128);
+  return L;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w) {
+  a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y); a.z = fmaf(x.z, w.z, a.z); a.w = fmaf(x.w, w.w, a.w);
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+__global__ void __launch_bounds__(kThreads) blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in,
+                                                                  const __grid_constant__ CUtensorMap tm_out, const BlockTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int C = a.C, N = a.N, Np = a.Np, Q = C >> 2;
+  const SmemLayout L = smem_layout(C, N, Np, a.stages, a.wsplit);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);          // [2]
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 32);
+  float* s_bias = reinterpret_cast<float*>(smem + L.bias);
+  float* s_alpha = reinterpret_cast<float*>(smem + L.alpha);
+  uint8_t* s_ahi = smem + L.a_hi;
+  uint8_t* s_alo = smem + L.a_lo;
+  float* s_w = reinterpret_cast<float*>(smem + L.w);
+  float* s_out = reinterpret_cast<float*>(smem + L.out);
+
+  int nb = a.B;
+  if (a.n_active) nb = min(nb, *a.n_active);
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const int ntiles = nb * tiles_per_img;
+  if ((int)blockIdx.x >= ntiles) return;
+
+  // ---- one-time setup ----
+  if (tid == 0) {
+    ptx::prefetch_tmap(&tm_in);
+    ptx::prefetch_tmap(&tm_out);
+    ptx::mbar_init(&full_bar[0], 1);
+    ptx::mbar_init(&full_bar[1], 1);
+    ptx::mbar_init(mma_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+  for (int i = tid; i < Np; i += kThreads) {
+    s_bias[i] = i < N ? a.bias[i] : 0.f;
+    s_alpha[i] = (a.alpha && i < N) ? a.alpha[i] : 0.f;
+  }
+  {  // pointwise weights: already in UMMA core-matrix order in global memory -> straight copy
+    const int n4 = a.wsplit * Q * Np;   // float4 count
+    const float4* src = reinterpret_cast<const float4*>(a.w_umma);
+    float4* dst = reinterpret_cast<float4*>(s_w);
+    for (int i = tid; i < n4; i += kThreads) dst[i] = __ldg(src + i);
+  }
+  // depthwise weights of this thread's channel quad (kThreads % Q == 0, so the quad is fixed per thread)
+  const int q = tid % Q;
+  float4 wd[9], bd;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wd[k] = __ldg(reinterpret_cast<const float4*>(a.w_dw + k * C) + q);
+  bd = __ldg(reinterpret_cast<const float4*>(a.b_dw) + q);
+
+  ptx::fence_proxy_async_smem();   // s_w was written through the generic proxy, the MMA reads it through the async proxy
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t in_bytes = (uint32_t)((TH + 2) * (TW + 2) * C * 4);
+  auto issue_load = [&](int tile, int stage) {
+    int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+    int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+    ptx::mbar_arrive_expect_tx(&full_bar[stage], in_bytes);
+    ptx::tma_load_4d(smem + L.in0 + stage * L.in_stage, &tm_in, &full_bar[stage], 0, tx * TW - 1, ty * TH - 1, b);
+  };
+  if (tid == 0) issue_load(blockIdx.x, 0);
+
+  const uint32_t idesc = ptx::umma_idesc_tf32(128, Np);
+  const uint32_t ahi_addr = ptx::smem_u32(s_ahi), alo_addr = ptx::smem_u32(s_alo), w_addr = ptx::smem_u32(s_w);
+  const uint32_t w_lbo = (uint32_t)Np * 16u;
+  const int nitems = Q * 2 * TW;
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int stage = a.stages == 2 ? (it & 1) : 0;
+    const uint32_t full_parity = a.stages == 2 ? ((it >> 1) & 1) : (it & 1);
+    const int next = tile + gridDim.x;
+    if (a.stages == 2 && tid == 0 && next < ntiles) issue_load(next, stage ^ 1);
+    ptx::mbar_wait(&full_bar[stage], full_parity);
+    const float* s_in = reinterpret_cast<const float*>(smem + L.in0 + stage * L.in_stage);
+
+    // ---- depthwise 3x3 (stride 1) -> A operand (hi / lo planes) ----
+    for (int item = tid; item < nitems; item += kThreads) {
+      const int xr = item / Q;           // item % Q == q
+      const int x = xr % TW, half = xr / TW;
+      float4 acc[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) acc[o] = bd;
+      const float* base = s_in + ((half * 4) * (TW + 2) + x) * C + 4 * q;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        const float* rp = base + r * (TW + 2) * C;
+        float4 v0 = ld4(rp), v1 = ld4(rp + C), v2 = ld4(rp + 2 * C);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int ky = r - o;
+          if (ky >= 0 && ky < 3) {
+            fma4(acc[o], v0, wd[ky * 3 + 0]);
+            fma4(acc[o], v1, wd[ky * 3 + 1]);
+            fma4(acc[o], v2, wd[ky * 3 + 2]);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int p = (half * 4 + o) * TW + x;
+        float4 v = acc[o], hi, lo;
+        hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+        lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+        *reinterpret_cast<float4*>(s_ahi + q * kPlaneBytes + p * 16) = hi;
+        *reinterpret_cast<float4*>(s_alo + q * kPlaneBytes + p * 16) = lo;
+      }
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+
+    // ---- pointwise 1x1 on the tensor cores: one thread issues, completion arrives on mma_bar ----
+    if (tid == 0) {
+      ptx::tc_fence_after_sync();
+      uint32_t acc_flag = 0;
+      const int ksteps = C >> 3;
+      for (int pass = 0; pass < (a.wsplit == 2 ? 3 : 2); ++pass) {
+        // pass 0: A_lo * W_hi, pass 1: A_hi * W_hi, pass 2: A_hi * W_lo
+        const uint32_t a_base = pass == 0 ? alo_addr : ahi_addr;
+        const uint32_t b_base = pass == 2 ? w_addr + (uint32_t)(Q * Np * 16) : w_addr;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          uint64_t ad = ptx::umma_desc_kmajor(a_base + (uint32_t)(ks * 2 * kPlaneBytes), kPlaneBytes, 128);
+          uint64_t bdsc = ptx::umma_desc_kmajor(b_base + (uint32_t)ks * 2u * w_lbo, w_lbo, 128);
+          ptx::mma_tf32(tmem_base, ad, bdsc, idesc, acc_flag);
+          acc_flag = 1;
+        }
+      }
+      ptx::mma_commit(mma_bar);
+    }
+
+    // ---- epilogue: TMEM -> registers -> (+bias, +skip, act) -> smem -> TMA store ----
+    if (warp < 4) {
+      ptx::mbar_wait(mma_bar, (uint32_t)(it & 1));
+      ptx::tc_fence_after_sync();
+      if (tid == 0) ptx::tma_store_wait_read0();     // the previous tile's store has finished reading s_out
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int p = tid;                             // TMEM lane == pixel in tile
+      const int py = p / TW, px = p - py * TW;
+      int b = tile / tiles_per_img, rr = tile - b * tiles_per_img;
+      int ty = rr / a.tiles_x, tx = rr - ty * a.tiles_x;
+      const int oy = ty * TH + py, ox = tx * TW + px;
+      const bool inside = oy < a.H && ox < a.W;
+      const float* skip_smem = s_in + ((py + 1) * (TW + 2) + (px + 1)) * C;   // centre pixel of the resident input tile
+      const float* skip_g = nullptr;
+      if (a.skip_mode >= 2 && inside) {
+        if (a.skip_mode == 2) skip_g = a.skip + (long long)b * a.skip_bstride + ((long long)oy * a.W + ox) * a.skip_c;
+        else skip_g = a.skip + (long long)b * a.skip_bstride + ((long long)(2 * oy) * (2 * a.W) + 2 * ox) * a.skip_c;
+      }
+      for (int c0 = 0; c0 < Np; c0 += 16) {
+        float v[16];
+        ptx::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const int n = c0 + j;
+          if (n >= N) break;
+          float o4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o4[e] = v[j + e] + s_bias[n + e];
+          if (a.skip_mode == 1) {
+            if (n < a.skip_c) {
+              float4 s = ld4(skip_smem + n);
+              o4[0] += s.x; o4[1] += s.y; o4[2] += s.z; o4[3] += s.w;
+            }
+          } else if (a.skip_mode == 2) {
+            if (n < a.skip_c && skip_g) {
+              float4 s = __ldg(reinterpret_cast<const float4*>(skip_g + n));
+              o4[0] += s.x; o4[1] += s.y; o4[2] += s.z; o4[3] += s.w;
+            }
+          } else if (a.skip_mode == 3) {
+            if (n < a.skip_c && skip_g) {
+              const long long rs = (long long)2 * a.W * a.skip_c;
+              float4 s0 = __ldg(reinterpret_cast<const float4*>(skip_g + n));
+              float4 s1 = __ldg(reinterpret_cast<const float4*>(skip_g + a.skip_c + n));
+              float4 s2 = __ldg(reinterpret_cast<const float4*>(skip_g + rs + n));
+              float4 s3 = __ldg(reinterpret_cast<const float4*>(skip_g + rs + a.skip_c + n));
+              o4[0] += fmaxf(fmaxf(s0.x, s1.x), fmaxf(s2.x, s3.x));
+              o4[1] += fmaxf(fmaxf(s0.y, s1.y), fmaxf(s2.y, s3.y));
+              o4[2] += fmaxf(fmaxf(s0.z, s1.z), fmaxf(s2.z, s3.z));
+              o4[3] += fmaxf(fmaxf(s0.w, s1.w), fmaxf(s2.w, s3.w));
+            }
+          }
+          if (a.act == ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o4[e] = fmaxf(o4[e], 0.f);
+          } else if (a.act == ACT_PRELU) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o4[e] = o4[e] >= 0.f ? o4[e] : o4[e] * s_alpha[n + e];
+          }
+          *reinterpret_cast<float4*>(s_out + p * N + n) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before_sync();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 0) {
+        ptx::tma_store_4d(&tm_out, s_out, 0, tx * TW, ty * TH, b);
+        ptx::tma_store_commit();
+      }
+    }
+    __syncthreads();   // input stage, A planes and the TMEM accumulator are free again
+    if (a.stages == 1 && tid == 0 && next < ntiles) issue_load(next, 0);
+  }
+
+  if (tid == 0) ptx::tma_store_wait_all0();
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+std::once_flag g_encode_once;
+constexpr int kMaxSmemTc = 227 * 1024;
+
+bool encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, long long bstride, int box_h, int box_w) {
+  if (!g_encode) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)bstride * 4};
+  cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+cudaError_t mma_kernels_init() {
+  cudaError_t err = cudaSuccess;
+  std::call_once(g_encode_once, [&]() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (err == cudaSuccess && q == cudaDriverEntryPointSuccess) g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  });
+  if (err != cudaSuccess) return err;
+  return cudaFuncSetAttribute(blaze_block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTc);
+}
+
+bool block_tc_supported(const Step& s, int* stages_out) {
+  if (s.kind != STEP_BLOCK || s.stride != 1 || s.w_umma < 0) return false;
+  const int C = s.in.C, N = s.out.C;
+  if (C % 8 != 0 || N % 4 != 0 || C < 16 || (kThreads % (C / 4)) != 0) return false;
+  if (s.Np > 128 || s.in.H < TH || s.in.W < TW) return false;
+  if (s.in.H != s.out.H || s.in.W != s.out.W) return false;
+  if (s.in.offset != 0 || s.out.offset != 0 || s.in.batch_stride != (int64_t)s.in.H * s.in.W * C ||
+      s.out.batch_stride != (int64_t)s.out.H * s.out.W * N)
+    return false;
+  if (s.skip.tensor >= 0 && (s.skip_c % 4 != 0 || s.skip.offset != 0)) return false;
+  for (int stages = 2; stages >= 1; --stages) {
+    SmemLayout L = smem_layout(C, N, s.Np, stages, s.wsplit);
+    if (L.total <= kMaxSmemTc) {
+      // prefer the deepest pipeline that still lets two CTAs share an SM; otherwise whatever fits
+      if (stages == 2 && 2 * (L.total + 1024) > 228 * 1024) {
+        SmemLayout L1 = smem_layout(C, N, s.Np, 1, s.wsplit);
+        if (2 * (L1.total + 1024) <= 228 * 1024) { *stages_out = 1; return true; }
+      }
+      *stages_out = stages;
+      return true;
+    }
+  }
+  return false;
+}
+
+cudaError_t launch_block_tc(const BlockTcLaunch& l, cudaStream_t stream) {
+  if (!g_encode) return cudaErrorNotSupported;
+  BlockTcArgs a = l.args;
+  CUtensorMap tm_in, tm_out;
+  if (!encode_nhwc(&tm_in, l.in, a.B, a.H, a.W, a.C, (long long)a.H * a.W * a.C, TH + 2, TW + 2)) return cudaErrorInvalidValue;
+  if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW)) return cudaErrorInvalidValue;
+  a.tiles_x = (a.W + TW - 1) / TW;
+  a.tiles_y = (a.H + TH - 1) / TH;
+  a.tmem_cols = a.Np <= 32 ? 32 : (a.Np <= 64 ? 64 : 128);
+  SmemLayout L = smem_layout(a.C, a.N, a.Np, a.stages, a.wsplit);
+  const int ntiles = a.B * a.tiles_x * a.tiles_y;
+  int per_sm = (228 * 1024) / (L.total + 1024);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  int grid = 148 * per_sm;
+  if (grid > ntiles) grid = ntiles;
+  blaze_block_tc_kernel<<<grid, kThreads, L.total, stream>>>(tm_in, tm_out, a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace fdl

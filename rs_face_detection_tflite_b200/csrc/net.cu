@@ -2,6 +2,7 @@
 #include "net.h"
 
 #include "fdl_status.h"
+#include "mma_kernels.cuh"
 
 namespace fdl {
 
@@ -14,6 +15,7 @@ Net* Net::create(const std::string& path, int device, std::string* err, int* cod
   if (device >= 0) {
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = net_kernels_init();
+    if (e == cudaSuccess) e = mma_kernels_init();
     if (e == cudaSuccess) e = cudaMalloc(&n->d_weights_, n->plan_.weights.size() * sizeof(float));
     if (e == cudaSuccess)
       e = cudaMemcpy(n->d_weights_, n->plan_.weights.data(), n->plan_.weights.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -58,7 +60,25 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active) {
   if (B > cap_B_ || device_ < 0) return cudaErrorInvalidValue;
   for (const Step& s : plan_.steps) {
     cudaError_t e;
-    if (s.kind == STEP_CONV || s.kind == STEP_BLOCK) {
+    int tc_stages = 0;
+    if (mode_ == 1 && block_tc_supported(s, &tc_stages)) {
+      BlockTcLaunch l;
+      TView in = view(s.in, B), out = view(s.out, B);
+      l.in = in.p; l.out = out.p;
+      BlockTcArgs& a = l.args;
+      a.w_umma = d_weights_ + s.w_umma; a.bias = d_weights_ + s.b; a.w_dw = d_weights_ + s.w_dw; a.b_dw = d_weights_ + s.b_dw;
+      a.alpha = s.alpha >= 0 ? d_weights_ + s.alpha : nullptr;
+      a.C = s.in.C; a.N = s.out.C; a.Np = s.Np; a.H = s.out.H; a.W = s.out.W; a.B = B;
+      a.act = s.act; a.stages = tc_stages; a.wsplit = s.wsplit; a.n_active = n_active;
+      if (s.skip.tensor >= 0) {
+        TView sk = view(s.skip, B);
+        a.skip_c = s.skip_c;
+        if (s.skip_pool) { a.skip_mode = 3; a.skip = sk.p; a.skip_bstride = sk.bstride; }
+        else if (s.skip.tensor == s.in.tensor) a.skip_mode = 1;
+        else { a.skip_mode = 2; a.skip = sk.p; a.skip_bstride = sk.bstride; }
+      }
+      e = launch_block_tc(l, stream);
+    } else if (s.kind == STEP_CONV || s.kind == STEP_BLOCK) {
       ConvArgs a;
       a.in = view(s.in, B); a.out = view(s.out, B);
       a.mode = s.kind == STEP_BLOCK ? 1 : 0;

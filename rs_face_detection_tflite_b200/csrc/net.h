@@ -41,7 +41,7 @@ class Net {
   Net() = default;
   Plan plan_;
   int device_ = -1;
-  int mode_ = 0;
+  int mode_ = 1;   // 1: tensor-core BlazeBlock kernel where it applies (default), 0: fp32 FFMA kernels only
   float* d_weights_ = nullptr;
   float* d_arena_ = nullptr;
   int cap_B_ = 0;

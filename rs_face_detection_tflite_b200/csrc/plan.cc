@@ -378,6 +378,24 @@ bool Plan::build(const TfModel& m, std::string* err) {
       s.w = push(wt);
       s.b = push(bp);
       flops_per_item += 2LL * s.K * co * oh * ow;
+      if (g.kind == STEP_BLOCK && ci % 8 == 0) {
+        // tensor-core packing: plane q (4 input channels) x output channel n x 4 floats
+        s.Np = (int)align_up(co, 16);
+        auto hi_of = [](float v) { uint32_t u; std::memcpy(&u, &v, 4); u &= 0xffffe000u; float r; std::memcpy(&r, &u, 4); return r; };
+        bool exact = true;
+        for (float v : w) if (hi_of(v) != v) { exact = false; break; }
+        s.wsplit = exact ? 1 : 2;
+        const int Q = ci / 4;
+        std::vector<float> pk((size_t)s.wsplit * Q * s.Np * 4, 0.f);
+        for (int o = 0; o < co; ++o)
+          for (int k = 0; k < ci; ++k) {
+            float v = w[(size_t)o * ci + k], h = hi_of(v);
+            size_t at = ((size_t)(k / 4) * s.Np + o) * 4 + (k % 4);
+            pk[at] = h;
+            if (s.wsplit == 2) pk[(size_t)Q * s.Np * 4 + at] = v - h;
+          }
+        s.w_umma = push(pk);
+      }
     }
     if (g.kind == STEP_RESIZE) {
       if (s.out.C != s.in.C) { *err = "resize channel mismatch"; return false; }

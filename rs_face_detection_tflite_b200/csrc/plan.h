@@ -55,6 +55,11 @@ struct Step {
   int64_t w_dw = -1, b_dw = -1;   // DW weights [kh*kw][C], bias [C]
   int64_t w = -1, b = -1;         // CONV/PW weights [K4][Npad] (K = kh*kw*Cin, Npad = roundup(Cout,4)), bias [Npad]
   int64_t alpha = -1;             // PRELU slopes [C]
+  // BLOCK steps also carry the pointwise weights packed for tcgen05 (UMMA K-major core matrices):
+  // [wsplit][Cin/4][Np][4] floats; wsplit == 1 when every weight is tf32-exact (f16-stored detectors),
+  // else 2 = (tf32(w), w - tf32(w)).  -1 when Cin % 8 != 0.
+  int64_t w_umma = -1;
+  int Np = 0, wsplit = 1;
   int K = 0, K4 = 0, N = 0, Npad = 0;  // contraction size (K4 = roundup(K,4) rows stored) / output channels of the CONV/PW part
   std::vector<int> ops;           // tflite op indices folded into this step
   std::string text;               // human-readable description
