@@ -169,7 +169,10 @@ def decode_boxes(raw_boxes: np.ndarray, anchors: np.ndarray, scale: float) -> np
 def sigmoid_f32(x):
     """transform.rs:111-113 in f32."""
     x = np.asarray(x, np.float32)
-    return (f32(1.0) / (f32(1.0) + np.exp(-x, dtype=np.float32))).astype(np.float32)
+    # Rust's f32::exp is the host libm's expf (glibc: correctly rounded in practice).  numpy's float32 exp is a
+    # SIMD approximation good to ~2 ulp, so evaluate in f64 and round once to f32 to model the correctly rounded value.
+    e = np.exp(-x.astype(np.float64)).astype(np.float32)
+    return (f32(1.0) / (f32(1.0) + e)).astype(np.float32)
 
 
 def get_sigmoid_score(raw_scores: np.ndarray) -> np.ndarray:

@@ -1,0 +1,43 @@
+//! Raw bindings to include/fdl.h (the subset the shim needs).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int};
+
+#[repr(C)] #[derive(Clone, Copy, Debug)]
+pub struct fdl_rect { pub x_center: f64, pub y_center: f64, pub width: f64, pub height: f64, pub rotation: f64, pub normalized: i32, pub _pad: i32 }
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct fdl_detection { pub data: [f32; 16], pub score: f32, pub anchor: i32 }
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct fdl_landmark { pub x: f64, pub y: f64, pub z: f64 }
+#[repr(C)]
+pub struct fdl_image { pub data: *const u8, pub width: i32, pub height: i32, pub row_stride: i64, pub mem: i32, pub _pad: i32 }
+pub enum fdl_detector {}
+pub enum fdl_landmark_model {}
+pub enum fdl_iris_model {}
+
+extern "C" {
+    pub fn fdl_last_error() -> *const c_char;
+    pub fn fdl_detector_create(model: c_int, model_dir: *const c_char, device: c_int, out: *mut *mut fdl_detector) -> c_int;
+    pub fn fdl_detector_destroy(d: *mut fdl_detector);
+    pub fn fdl_detector_infer(d: *mut fdl_detector, image: *const fdl_image, roi: *const fdl_rect, out: *mut fdl_detection, cap: c_int, n: *mut c_int) -> c_int;
+    pub fn fdl_landmark_create(file: *const c_char, device: c_int, out: *mut *mut fdl_landmark_model) -> c_int;
+    pub fn fdl_landmark_destroy(m: *mut fdl_landmark_model);
+    pub fn fdl_landmark_infer(m: *mut fdl_landmark_model, image: *const fdl_image, roi: *const fdl_rect, out: *mut fdl_landmark, n: *mut c_int, flag: *mut f32) -> c_int;
+    pub fn fdl_iris_create(file: *const c_char, device: c_int, out: *mut *mut fdl_iris_model) -> c_int;
+    pub fn fdl_iris_destroy(m: *mut fdl_iris_model);
+    pub fn fdl_iris_infer(m: *mut fdl_iris_model, image: *const fdl_image, roi: *const fdl_rect, is_right_eye: c_int, contour: *mut fdl_landmark, iris: *mut fdl_landmark) -> c_int;
+    pub fn fdl_face_detection_to_roi(device: c_int, det: *const fdl_detection, w: c_int, h: c_int, size_mode: c_int, out: *mut fdl_rect) -> c_int;
+    pub fn fdl_iris_roi_from_face_landmarks(device: c_int, lm: *const fdl_landmark, n: c_int, w: c_int, h: c_int, left: *mut fdl_rect, right: *mut fdl_rect) -> c_int;
+}
+
+pub fn check(rc: c_int) -> Result<(), anyhow::Error> {
+    if rc == 0 { return Ok(()); }
+    let msg = unsafe { std::ffi::CStr::from_ptr(fdl_last_error()) }.to_string_lossy().into_owned();
+    Err(anyhow::Error::msg(msg))
+}
+
+/// `&Mat` (8UC3, RGB) -> fdl_image without copying.
+pub fn image_of(mat: &opencv::core::Mat) -> Result<fdl_image, anyhow::Error> {
+    use opencv::prelude::*;
+    let size = mat.size()?;
+    Ok(fdl_image { data: mat.data(), width: size.width, height: size.height, row_stride: mat.step1(0)? as i64, mem: 0, _pad: 0 })
+}

@@ -1,0 +1,43 @@
+//! iris_roi_from_face_landmarks, IrisLandmark::new / infer, IrisResults (reference iris_landmark.rs:115-292) over the C ABI.
+use super::{ffi, types::{Landmark, Rect}};
+use anyhow::Error;
+use opencv::core::Mat;
+use std::ffi::CString;
+
+pub struct IrisResults { contour: Vec<Landmark>, iris: Vec<Landmark> }
+impl IrisResults {
+    pub fn eyeball_contour(&self) -> Vec<Landmark> { self.contour[..15].to_vec() }
+    pub fn contour(&self) -> &[Landmark] { &self.contour }
+    pub fn iris(&self) -> &[Landmark] { &self.iris }
+}
+
+pub fn iris_roi_from_face_landmarks(face_landmarks: Vec<Landmark>, image_size: (i32, i32)) -> Result<(Rect, Rect), Error> {
+    let lm: Vec<ffi::fdl_landmark> = face_landmarks.iter().map(|l| ffi::fdl_landmark { x: l.x, y: l.y, z: l.z }).collect();
+    let zero = Rect { x_center: 0.0, y_center: 0.0, width: 0.0, height: 0.0, rotation: 0.0, normalized: true }.to_c();
+    let (mut l, mut r) = (zero, zero);
+    ffi::check(unsafe { ffi::fdl_iris_roi_from_face_landmarks(0, lm.as_ptr(), lm.len() as i32, image_size.0, image_size.1, &mut l, &mut r) })?;
+    Ok((Rect::from_c(&l), Rect::from_c(&r)))
+}
+
+pub struct IrisLandmark { handle: *mut ffi::fdl_iris_model }
+unsafe impl Send for IrisLandmark {}
+
+impl IrisLandmark {
+    pub fn new(model_path: Option<String>) -> Result<IrisLandmark, Error> {
+        let file = model_path.map(|p| CString::new(p).unwrap());
+        let mut h = std::ptr::null_mut();
+        ffi::check(unsafe { ffi::fdl_iris_create(file.as_ref().map_or(std::ptr::null(), |c| c.as_ptr()), 0, &mut h) })?;
+        Ok(IrisLandmark { handle: h })
+    }
+    pub fn infer(&self, image: &Mat, roi: Option<Rect>, is_right_eye: Option<bool>) -> Result<IrisResults, Error> {
+        let img = ffi::image_of(image)?;
+        let croi = roi.map(|r| r.to_c());
+        let mut contour = vec![ffi::fdl_landmark::default(); 71];
+        let mut iris = vec![ffi::fdl_landmark::default(); 5];
+        ffi::check(unsafe { ffi::fdl_iris_infer(self.handle, &img, croi.as_ref().map_or(std::ptr::null(), |r| r as *const _), is_right_eye.unwrap_or(false) as i32,
+                                                 contour.as_mut_ptr(), iris.as_mut_ptr()) })?;
+        let f = |v: &Vec<ffi::fdl_landmark>| v.iter().map(|l| Landmark { x: l.x, y: l.y, z: l.z }).collect();
+        Ok(IrisResults { contour: f(&contour), iris: f(&iris) })
+    }
+}
+impl Drop for IrisLandmark { fn drop(&mut self) { unsafe { ffi::fdl_iris_destroy(self.handle) } } }

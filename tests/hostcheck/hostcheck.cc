@@ -1,0 +1,100 @@
+// hostcheck.cc -- TEST INFRASTRUCTURE ONLY.  Compiles csrc/glue_math.h (the very header the CUDA kernels
+// call on the device) for the host with g++ -ffp-contract=off, so that the arithmetic of the pre/post-
+// processing kernels can be checked against the oracle on a CPU-only box.  Never part of libfdl_b200.so.
+#include <cstring>
+#include <vector>
+
+#include "../../rs_face_detection_tflite_b200/csrc/glue_math.h"
+
+using namespace fdl;
+
+extern "C" {
+
+int hc_anchors(int model, float* out, int cap) {
+  SsdOptions o;
+  if (!ssd_options_for(model, &o)) return -1;
+  int n = ssd_num_anchors(o);
+  if (n > cap) return -2;
+  for (int i = 0; i < n; ++i) ssd_anchor(o, i, &out[2 * i], &out[2 * i + 1]);
+  return n;
+}
+
+// image_to_tensor on the host through the same per-pixel functions the i2t kernel uses.
+int hc_image_to_tensor(const uint8_t* img, int w, int h, const fdl_rect* roi, int out_w, int out_h, int keep, double rmin, double rmax,
+                       int flip, float* out, uint8_t* out_u8, double* pad4) {
+  I2TParams P;
+  i2t_setup(roi, w, h, out_w, out_h, keep != 0, rmin, rmax, flip != 0, 0, &P);
+  if (!P.valid) return -1;
+  for (int y = 0; y < out_h; ++y)
+    for (int x = 0; x < out_w; ++x) {
+      Px3 p = i2t_pixel(P, img, (long long)w * 3, x, y);
+      size_t o = ((size_t)y * out_w + x) * 3;
+      out[o] = i2t_normalise(p.r, rmin, rmax); out[o + 1] = i2t_normalise(p.g, rmin, rmax); out[o + 2] = i2t_normalise(p.b, rmin, rmax);
+      out_u8[o] = (uint8_t)p.r; out_u8[o + 1] = (uint8_t)p.g; out_u8[o + 2] = (uint8_t)p.b;
+    }
+  for (int i = 0; i < 4; ++i) pad4[i] = P.pad[i];
+  return 0;
+}
+
+// Sequential restatement of what ssd_postprocess_kernel does, built from the same scalar functions
+// (decode_box, ssd_score, overlap_similarity); returns the number of output detections.
+int hc_ssd_postprocess(int model, const float* reg, const float* cls, const double* pad4, fdl_detection* out, int cap, int* surv, int* n_surv) {
+  SsdOptions o;
+  if (!ssd_options_for(model, &o)) return -1;
+  const int N = ssd_num_anchors(o);
+  const float scale = (float)o.input_size;
+  std::vector<int> idx; std::vector<float> score; std::vector<std::vector<float>> box;
+  for (int i = 0; i < N; ++i) {
+    float sc = ssd_score(cls[i]);
+    if (!(sc > 0.5f)) continue;
+    float ax, ay, d[16];
+    ssd_anchor(o, i, &ax, &ay);
+    decode_box(reg + 16 * i, ax, ay, scale, d);
+    if (d[2] > d[0] && d[3] > d[1]) { idx.push_back(i); score.push_back(sc); box.emplace_back(d, d + 16); }
+  }
+  *n_surv = (int)idx.size();
+  for (size_t i = 0; i < idx.size(); ++i) surv[i] = idx[i];
+  const int n = (int)idx.size();
+  std::vector<int> rem(n);
+  for (int j = 0; j < n; ++j) {
+    int rank = 0;
+    for (int k = 0; k < n; ++k) rank += (score[k] > score[j] || (score[k] == score[j] && k < j)) ? 1 : 0;
+    rem[rank] = j;
+  }
+  const float left = (float)pad4[0], top = (float)pad4[1];
+  const float hs = (float)(1.0 - (pad4[0] + pad4[2])), vs = (float)(1.0 - (pad4[1] + pad4[3]));
+  int n_out = 0;
+  const double thr = (double)0.3f;
+  while (!rem.empty()) {
+    int t = rem[0];
+    std::vector<int> cand, next;
+    for (int j : rem) (overlap_similarity(box[j].data(), box[t].data()) > thr ? cand : next).push_back(j);
+    float v[16];
+    if (!cand.empty()) {
+      for (int k = 0; k < 16; ++k) {
+        float w = 0.f, total = 0.f;
+        for (int c : cand) { total += score[c]; w += box[c][k] * score[c]; }
+        v[k] = w / total;
+      }
+    } else {
+      for (int k = 0; k < 16; ++k) v[k] = box[t][k];
+    }
+    if (n_out < cap) {
+      for (int k = 0; k < 16; ++k) out[n_out].data[k] = (k & 1) ? (v[k] - top) / vs : (v[k] - left) / hs;
+      out[n_out].score = score[t]; out[n_out].anchor = idx[t];
+    }
+    ++n_out;
+    if (cand.empty()) break;
+    rem.swap(next);
+  }
+  return n_out;
+}
+
+int hc_face_detection_to_roi(const float* data16, int w, int h, int mode, fdl_rect* out) { return face_detection_to_roi(data16, w, h, mode, out) ? 0 : -1; }
+int hc_eye_roi(double ax, double ay, double bx, double by, int w, int h, fdl_rect* out) { return eye_roi(ax, ay, bx, by, w, h, out) ? 0 : -1; }
+void hc_project(const float* raw, int n, int tw, int th, int iw, int ih, const double* pad4, const fdl_rect* roi, int flip, float* out) {
+  ProjectParams pp;
+  project_setup(tw, th, iw, ih, pad4, roi, flip != 0, &pp);
+  for (int k = 0; k < n; ++k) project_point(pp, raw + 3 * k, out + 3 * k);
+}
+}

@@ -1,0 +1,226 @@
+"""Host logic without a GPU: the C ABI loads and exports every symbol of include/fdl.h, the C++ flatbuffer
+reader + planner agree with the oracle's independent reader, the glue arithmetic compiled for the host matches
+the oracle, calls that need a device fail loudly, and the rank-sharding used by bench.py works under gloo."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import MODELS, ROOT, rng
+
+MODEL_FILES = ["face_detection_short_range", "face_detection_front", "face_detection_back", "face_detection_full_range", "face_landmark",
+               "iris_landmark"]
+
+
+def test_library_exports_every_declared_symbol(fdl):
+    from rs_face_detection_tflite_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "fdl.h")).read()
+    declared = set(re.findall(r"FDL_API\s+[^;{]*?\b(fdl_\w+)\s*\(", hdr))
+    assert len(declared) >= 40
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (fdl_\w+)", out))
+    assert declared <= exported
+    assert lib.fdl_version().startswith(b"fdl-b200")
+
+
+def test_struct_layouts_match_header(fdl):
+    from rs_face_detection_tflite_b200 import _lib
+    assert C.sizeof(_lib.CRect) == 48 and C.sizeof(_lib.CDetection) == 72 and C.sizeof(_lib.CLandmark) == 24
+    assert C.sizeof(_lib.CImage) == 32
+    assert C.sizeof(_lib.CFrameResult) == 8 + 32 * 72
+    assert C.sizeof(_lib.CFaceResult) == 48 + 8 + 468 * 12 + 96 + 2 * 71 * 12 + 2 * 5 * 12
+
+
+@pytest.mark.skipif("torch.cuda.is_available()", reason="checks the no-GPU error path")
+def test_no_device_is_an_error_not_a_fallback(fdl):
+    import torch  # noqa: F401
+    assert fdl.device_count() == 0
+    for make in (lambda: fdl.FaceDetection(fdl.FaceDetectionModel.BackCamera, MODELS), lambda: fdl.FaceLandmark(MODELS + "/face_landmark.tflite"),
+                 lambda: fdl.IrisLandmark(MODELS + "/iris_landmark.tflite"), lambda: fdl.Pipeline(model_dir=MODELS),
+                 lambda: fdl.face_detection_to_roi(fdl.Detection(np.zeros((8, 2), np.float32), 0.9), (10, 10)),
+                 lambda: fdl.image_to_tensor(np.zeros((8, 8, 3), np.uint8), None, (4, 4), True)):
+        with pytest.raises(fdl.FdlError) as e:
+            make()
+        assert e.value.code == -4 and "no CPU fallback" in e.value.message
+
+
+try:
+    import torch  # noqa: F401
+except Exception:  # pragma: no cover
+    torch = None
+
+
+@pytest.mark.parametrize("name", MODEL_FILES)
+def test_planner_covers_every_op_and_matches_oracle_reader(fdl, name):
+    """Plan-only handle (device -1): every non-constant tflite op lands in exactly one launch; shapes, launch counts and
+    FLOPs agree with what the oracle's independent flatbuffer reader sees."""
+    from oracle import tflite_reader as T
+    path = os.path.join(MODELS, name + ".tflite")
+    net = fdl.Net(path, device=-1)
+    text = net.describe()
+    m = T.load(path)
+    head = re.search(r"plan: (\d+) tflite ops -> (\d+) launches; arena (\d+) floats/item; weights (\d+) floats; block-fused floor (\d+) bytes/item; (\d+) flop/item", text)
+    n_ops, n_launch, arena, weights, floor, flops = map(int, head.groups())
+    assert n_ops == len(m.ops) and n_launch == net.num_steps
+    covered = []
+    for line in text.splitlines()[1:]:
+        covered += [int(v) for v in re.search(r"ops=\[([\d,]*)\]", line).group(1).split(",") if v]
+    folded = {T.DEQUANTIZE, T.RESHAPE, T.CONCATENATION}
+    expect = [i for i, op in enumerate(m.ops) if op.code not in folded]
+    assert sorted(covered) == expect
+    # FLOPs of conv + depthwise ops from the oracle reader
+    ref_flops = 0
+    for op in m.ops:
+        if op.code in (T.CONV_2D, T.DEPTHWISE_CONV_2D):
+            w = m.tensors[op.inputs[1]].shape
+            o = m.tensors[op.outputs[0]].shape
+            k = w[1] * w[2] * (w[3] if op.code == T.CONV_2D else 1)
+            ref_flops += 2 * k * o[1] * o[2] * o[3]
+    assert flops == ref_flops
+    assert floor > 0 and arena > 0
+    with pytest.raises(fdl.FdlError):
+        net.forward(np.zeros([1] + m.tensors[m.inputs[0]].shape[1:], np.float32))   # plan-only handles cannot run
+    net.close()
+
+
+def test_planner_fuses_blaze_blocks(fdl):
+    net = fdl.Net(os.path.join(MODELS, "face_detection_back.tflite"), device=-1)
+    text = net.describe()
+    assert net.num_steps == 37                       # 282 tflite ops
+    assert text.count("BLOCK dw3x3/s1+pw 24->24 in 128x128") == 7
+    assert "skip=maxpool+chanpad" in text and "CONV 5x5/s2 3->24" in text
+    assert "block-fused floor 37293568 bytes/item" in text and "377499648 flop/item" in text
+    net.close()
+
+
+def test_bad_models_are_rejected(fdl, tmp_path):
+    with pytest.raises(fdl.FdlError) as e:
+        fdl.Net(str(tmp_path / "missing.tflite"), device=-1)
+    assert e.value.code == -2
+    bad = tmp_path / "bad.tflite"
+    bad.write_bytes(b"\x00" * 64)
+    with pytest.raises(fdl.FdlError) as e:
+        fdl.Net(str(bad), device=-1)
+    assert e.value.code == -3
+    # a truncated real file must be rejected by the bounds checks, not crash
+    data = open(os.path.join(MODELS, "face_detection_back.tflite"), "rb").read()
+    cut = tmp_path / "cut.tflite"
+    cut.write_bytes(data[: len(data) // 3])
+    with pytest.raises(fdl.FdlError):
+        fdl.Net(str(cut), device=-1)
+
+
+# ---- glue arithmetic (csrc/glue_math.h, host build) against the oracle --------------------------------
+@pytest.fixture(scope="module")
+def hc():
+    import hostcheck
+    return hostcheck.load()
+
+
+def test_host_anchors_bit_exact(hc):
+    from oracle import glue
+    for model in (0, 1, 2, 3):
+        ref = glue.ssd_generate_anchors(model)
+        out = np.empty_like(ref)
+        assert hc.hc_anchors(model, out.ctypes.data_as(C.c_void_p), len(ref)) == len(ref)
+        np.testing.assert_array_equal(out, ref)
+
+
+def test_host_postprocess_matches_oracle(hc, fdl):
+    from oracle import glue
+    from rs_face_detection_tflite_b200._lib import CDetection
+    r = rng(77)
+    for model, n, size in ((1, 896, 256), (3, 2304, 192)):
+        anchors = glue.ssd_generate_anchors(model)
+        for case in range(8):
+            reg = r.normal(0, 20, (n, 16)).astype(np.float32)
+            cls = r.normal(-6, 2, (n, 1)).astype(np.float32)
+            for _ in range(case % 4 + 1):
+                c = int(r.integers(0, n))
+                base = r.normal(0, 10, 16).astype(np.float32)
+                base[2:4] = r.uniform(0.15, 0.5, 2) * size
+                for j in range(int(r.integers(1, 7))):
+                    k = (c + int(r.integers(-3, 4))) % n
+                    reg[k] = base + r.normal(0, 2, 16)
+                    cls[k, 0] = r.uniform(0.2, 6)
+            pad = (0.0, 0.21875, 0.0, 0.21875) if case % 2 else (0.0, 0.0, 0.0, 0.0)
+            dets = glue.convert_to_detections(glue.decode_boxes(reg, anchors, float(size)), glue.get_sigmoid_score(cls))
+            ref = glue.detection_letterbox_removal(glue.non_maximum_suppression(dets), pad)
+            out = (CDetection * 64)()
+            surv = (C.c_int * n)()
+            ns = C.c_int()
+            cnt = hc.hc_ssd_postprocess(model, reg.ctypes.data_as(C.c_void_p), cls.ctypes.data_as(C.c_void_p), (C.c_double * 4)(*pad), out, 64, surv,
+                                        C.byref(ns))
+            assert list(surv[:ns.value]) == [d.anchor for d in dets]
+            assert cnt == len(ref)
+            for k, e in enumerate(ref):
+                assert out[k].anchor == e.anchor and np.float32(out[k].score) == e.score
+                np.testing.assert_allclose(np.array(out[k].data[:], np.float32).reshape(8, 2), e.data, atol=1e-6, rtol=0)
+
+
+def test_host_roi_and_projection_match_oracle(hc):
+    from oracle import glue
+    from rs_face_detection_tflite_b200._lib import CRect
+    r = rng(5)
+    for k in range(20):
+        data = r.uniform(0.1, 0.9, (8, 2)).astype(np.float32)
+        data[1] = data[0] + r.uniform(0.05, 0.3, 2).astype(np.float32)
+        size = (int(r.integers(100, 2000)), int(r.integers(100, 2000)))
+        ref = glue.face_detection_to_roi(glue.Detection(data, np.float32(0.9)), size)
+        out = CRect()
+        assert hc.hc_face_detection_to_roi(data.ctypes.data_as(C.c_void_p), size[0], size[1], -1, C.byref(out)) == 0
+        for f in ("x_center", "y_center", "width", "height", "rotation"):
+            assert abs(getattr(out, f) - getattr(ref, f)) <= 1e-13 * max(1.0, abs(getattr(ref, f)))
+        raw = r.uniform(-20, 220, (71, 3)).astype(np.float32)
+        roi = glue.Rect(r.uniform(0.2, 0.8), r.uniform(0.2, 0.8), r.uniform(0.1, 0.9), r.uniform(0.1, 0.9), r.uniform(-3, 3), True)
+        pad = (1.1e-16, 0.0, 1.1e-16, 0.0) if k % 2 else (0.0, 0.0, 0.0, 0.0)
+        refp = glue.project_landmarks(raw, (64, 64), size, pad, roi, bool(k & 2))
+        outp = np.empty((71, 3), np.float32)
+        croi = CRect(roi.x_center, roi.y_center, roi.width, roi.height, roi.rotation, 1, 0)
+        hc.hc_project(raw.ctypes.data_as(C.c_void_p), 71, 64, 64, size[0], size[1], (C.c_double * 4)(*pad), C.byref(croi), int(bool(k & 2)),
+                      outp.ctypes.data_as(C.c_void_p))
+        np.testing.assert_allclose(outp, refp, atol=2e-7, rtol=0)
+
+
+# ---- multi-process plumbing (gloo, world size 2) -------------------------------------------------------
+_WORKER = r"""
+import os, sys, json
+import torch, torch.distributed as dist
+sys.path.insert(0, %r)
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+import synth_frames
+# frames are sharded by rank exactly as bench.py does (start = rank * uniq); no data-path collective
+uniq = 2
+mine = synth_frames.face_frames(uniq, 320, 180, start=rank * uniq)
+digest = torch.tensor([int(mine.astype("int64").sum())], dtype=torch.int64)
+gathered = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(gathered, digest)
+t = torch.tensor([1.0 + rank], dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)      # max-over-ranks timing, as in bench.py
+dist.barrier()
+if rank == 0:
+    print(json.dumps({"digests": [int(g) for g in gathered], "tmax": float(t)}))
+dist.destroy_process_group()
+"""
+
+
+def test_rank_sharding_under_gloo(tmp_path):
+    import json
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29531", str(script)], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(line)
+    assert len(res["digests"]) == 2 and res["digests"][0] != res["digests"][1]   # ranks work on different frames
+    assert res["tmax"] == 2.0
