@@ -1,28 +1,29 @@
 // mma_kernels.cu -- the tensor-core BlazeBlock kernel (sm_100a: TMA + tcgen05 + TMEM).
 //
 // One launch computes, for a batch of NHWC f32 feature maps,
-//     out = act( PW1x1( DW3x3(in) + b_dw ) + b_pw + skip )
+//     out = act( PW1x1( DW3x3_s(in) + b_dw ) + b_pw + skip )          s = 1 or 2
 // (SURVEY.md A.2 "Single BlazeBlock" and the two halves of the double / bottleneck blocks) with
-//   * the (TH+2)x(TW+2)xC input halo tile brought in by ONE TMA tensor load per tile (out-of-bounds
-//     coordinates are zero-filled by the TMA unit == TFLite SAME padding), double-buffered on mbarriers,
-//   * the depthwise 3x3 on the CUDA cores straight out of shared memory (sliding 3-row window in
-//     registers), written as the A operand of the pointwise GEMM in the UMMA K-major core-matrix layout,
+//   * the input halo tile ((TH-1)s+3) x ((TW-1)s+3) x C brought in by ONE TMA tensor load per tile
+//     (out-of-bounds coordinates are zero-filled by the TMA unit == TFLite SAME padding), double-buffered on
+//     mbarriers when shared memory allows,
+//   * the depthwise 3x3 on the CUDA cores straight out of shared memory (sliding row window in registers,
+//     float4 channel quads), written as the A operand of the pointwise GEMM in the UMMA K-major
+//     core-matrix layout,
 //   * the pointwise 1x1 contraction [128 pixels x Cin] x [Cin x Cout] on the 5th-gen tensor cores:
 //     tcgen05.mma kind::tf32, M=128, accumulator in TMEM.  fp32 fidelity is kept by operand splitting:
 //     x = hi + lo with hi = tf32(x), lo = x - hi, so A*W = A_hi*W + A_lo*W (+ A_hi*W_lo when the weights are
 //     not tf32-exact; the detectors' f16-stored weights are) -- error ~2^-22 per product, same order as fp32,
-//   * epilogue out of TMEM (tcgen05.ld): + bias, + residual (identity from the resident input tile, or
-//     direct / MAX_POOL 2x2 / zero-channel-PAD from global), RELU / PRELU, staged in shared memory and
-//     written with ONE TMA tensor store per tile.
+//   * epilogue out of TMEM (tcgen05.ld): + bias, + residual (identity or MAX_POOL 2x2 from the resident
+//     input tile, or direct / MAX_POOL 2x2 from global; zero channel PAD), RELU / PRELU, staged in shared
+//     memory and written with ONE TMA tensor store per tile.
 // The depthwise result and the pointwise accumulator never touch HBM: per tile the kernel reads the
 // input tile once and writes the output tile once (the "block-fused floor" of SURVEY.md 8d).
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cudaTypedefs.h>
 
 #include <cstdio>
 #include <mutex>
-
-#include <cudaTypedefs.h>
 
 #include "mma_kernels.cuh"
 #include "plan.h"
@@ -44,22 +45,24 @@ struct SmemLayout {
 };
 
 __host__ __device__ inline int align_up_i(int v, int a) { return (v + a - 1) / a * a; }
+__host__ __device__ inline int in_tile_h(int S) { return (TH - 1) * S + 3; }
+__host__ __device__ inline int in_tile_w(int S) { return (TW - 1) * S + 3; }
 
-__host__ __device__ inline SmemLayout smem_layout(int C, int N, int Np, int stages, int wsplit) {
+__host__ __device__ inline SmemLayout smem_layout(int C, int N, int Np, int S, int stages, int wsplit, int alias_out) {
   SmemLayout L;
   int off = 64;                                   // barriers + tmem pointer
   L.bias = off; off += Np * 4;
   L.alpha = off; off += Np * 4;
   off = align_up_i(off, 128);
-  L.in_stage = align_up_i((TH + 2) * (TW + 2) * C * 4, 128);
+  L.in_stage = align_up_i(in_tile_h(S) * in_tile_w(S) * C * 4, 128);
   L.in0 = off; off += stages * L.in_stage;
   L.a_hi = off; off += (C / 4) * kPlaneBytes;
-  off = align_up_i(off, 128);
-  L.a_lo = off; off += (C / 4) * kPlaneBytes;
+  L.a_lo = off; off += (C / 4) * kPlaneBytes;     // contiguous with a_hi (kPlaneBytes is a multiple of 16)
   off = align_up_i(off, 128);
   L.w = off; off += wsplit * (C / 4) * Np * 16;
   off = align_up_i(off, 128);
-  L.out = off; off += TH * TW * N * 4;
+  if (alias_out) { L.out = L.a_hi; }              // the output tile reuses the A planes (dead once the MMA has completed)
+  else { L.out = off; off += TH * TW * N * 4; }
   L.total = align_up_i(off, 128);
   return L;
 }
@@ -68,14 +71,19 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w) {
   a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y); a.z = fmaf(x.z, w.z, a.z); a.w = fmaf(x.w, w.w, a.w);
 }
+__device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
+template <int S>
 __global__ void __launch_bounds__(kThreads) blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in,
                                                                   const __grid_constant__ CUtensorMap tm_out, const BlockTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int ITH = (TH - 1) * S + 3, ITW = (TW - 1) * S + 3;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int C = a.C, N = a.N, Np = a.Np, Q = C >> 2;
-  const SmemLayout L = smem_layout(C, N, Np, a.stages, a.wsplit);
+  const SmemLayout L = smem_layout(C, N, Np, S, a.stages, a.wsplit, a.alias_out);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);          // [2]
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + 16);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 32);
@@ -125,12 +133,12 @@ __global__ void __launch_bounds__(kThreads) blaze_block_tc_kernel(const __grid_c
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  const uint32_t in_bytes = (uint32_t)((TH + 2) * (TW + 2) * C * 4);
+  const uint32_t in_bytes = (uint32_t)(ITH * ITW * C * 4);
   auto issue_load = [&](int tile, int stage) {
     int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
     int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
     ptx::mbar_arrive_expect_tx(&full_bar[stage], in_bytes);
-    ptx::tma_load_4d(smem + L.in0 + stage * L.in_stage, &tm_in, &full_bar[stage], 0, tx * TW - 1, ty * TH - 1, b);
+    ptx::tma_load_4d(smem + L.in0 + stage * L.in_stage, &tm_in, &full_bar[stage], 0, tx * TW * S - a.pad, ty * TH * S - a.pad, b);
   };
   if (tid == 0) issue_load(blockIdx.x, 0);
 
@@ -145,24 +153,29 @@ __global__ void __launch_bounds__(kThreads) blaze_block_tc_kernel(const __grid_c
     const uint32_t full_parity = a.stages == 2 ? ((it >> 1) & 1) : (it & 1);
     const int next = tile + gridDim.x;
     if (a.stages == 2 && tid == 0 && next < ntiles) issue_load(next, stage ^ 1);
+    if (a.alias_out) {
+      // the previous tile's TMA store reads the region the depthwise is about to overwrite
+      if (tid == 0) ptx::tma_store_wait_read0();
+      __syncthreads();
+    }
     ptx::mbar_wait(&full_bar[stage], full_parity);
     const float* s_in = reinterpret_cast<const float*>(smem + L.in0 + stage * L.in_stage);
 
-    // ---- depthwise 3x3 (stride 1) -> A operand (hi / lo planes) ----
+    // ---- depthwise 3x3 -> A operand (hi / lo planes) ----
     for (int item = tid; item < nitems; item += kThreads) {
       const int xr = item / Q;           // item % Q == q
       const int x = xr % TW, half = xr / TW;
       float4 acc[4];
 #pragma unroll
       for (int o = 0; o < 4; ++o) acc[o] = bd;
-      const float* base = s_in + ((half * 4) * (TW + 2) + x) * C + 4 * q;
+      const float* base = s_in + ((half * 4 * S) * ITW + x * S) * C + 4 * q;
 #pragma unroll
-      for (int r = 0; r < 6; ++r) {
-        const float* rp = base + r * (TW + 2) * C;
+      for (int r = 0; r < 3 * S + 3; ++r) {          // input rows feeding 4 consecutive output rows
+        const float* rp = base + r * ITW * C;
         float4 v0 = ld4(rp), v1 = ld4(rp + C), v2 = ld4(rp + 2 * C);
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
-          const int ky = r - o;
+          const int ky = r - o * S;
           if (ky >= 0 && ky < 3) {
             fma4(acc[o], v0, wd[ky * 3 + 0]);
             fma4(acc[o], v1, wd[ky * 3 + 1]);
@@ -207,17 +220,20 @@ __global__ void __launch_bounds__(kThreads) blaze_block_tc_kernel(const __grid_c
     if (warp < 4) {
       ptx::mbar_wait(mma_bar, (uint32_t)(it & 1));
       ptx::tc_fence_after_sync();
-      if (tid == 0) ptx::tma_store_wait_read0();     // the previous tile's store has finished reading s_out
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (!a.alias_out) {
+        if (tid == 0) ptx::tma_store_wait_read0();   // the previous tile's store has finished reading s_out
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
       const int p = tid;                             // TMEM lane == pixel in tile
       const int py = p / TW, px = p - py * TW;
       int b = tile / tiles_per_img, rr = tile - b * tiles_per_img;
       int ty = rr / a.tiles_x, tx = rr - ty * a.tiles_x;
       const int oy = ty * TH + py, ox = tx * TW + px;
       const bool inside = oy < a.H && ox < a.W;
-      const float* skip_smem = s_in + ((py + 1) * (TW + 2) + (px + 1)) * C;   // centre pixel of the resident input tile
+      // residual sources inside the resident input tile: centre pixel (stride 1) / 2x2 window (stride 2, pad 0)
+      const float* skip_smem = S == 1 ? s_in + ((py + 1) * ITW + (px + 1)) * C : s_in + ((2 * py) * ITW + 2 * px) * C;
       const float* skip_g = nullptr;
-      if (a.skip_mode >= 2 && inside) {
+      if ((a.skip_mode == 2 || a.skip_mode == 3) && inside) {
         if (a.skip_mode == 2) skip_g = a.skip + (long long)b * a.skip_bstride + ((long long)oy * a.W + ox) * a.skip_c;
         else skip_g = a.skip + (long long)b * a.skip_bstride + ((long long)(2 * oy) * (2 * a.W) + 2 * ox) * a.skip_c;
       }
@@ -231,27 +247,26 @@ __global__ void __launch_bounds__(kThreads) blaze_block_tc_kernel(const __grid_c
           float o4[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) o4[e] = v[j + e] + s_bias[n + e];
-          if (a.skip_mode == 1) {
-            if (n < a.skip_c) {
+          if (n < a.skip_c) {
+            if (a.skip_mode == 1) {
               float4 s = ld4(skip_smem + n);
               o4[0] += s.x; o4[1] += s.y; o4[2] += s.z; o4[3] += s.w;
-            }
-          } else if (a.skip_mode == 2) {
-            if (n < a.skip_c && skip_g) {
-              float4 s = __ldg(reinterpret_cast<const float4*>(skip_g + n));
+            } else if (a.skip_mode == 4) {
+              float4 s = max4(max4(ld4(skip_smem + n), ld4(skip_smem + C + n)), max4(ld4(skip_smem + ITW * C + n), ld4(skip_smem + (ITW + 1) * C + n)));
               o4[0] += s.x; o4[1] += s.y; o4[2] += s.z; o4[3] += s.w;
-            }
-          } else if (a.skip_mode == 3) {
-            if (n < a.skip_c && skip_g) {
-              const long long rs = (long long)2 * a.W * a.skip_c;
-              float4 s0 = __ldg(reinterpret_cast<const float4*>(skip_g + n));
-              float4 s1 = __ldg(reinterpret_cast<const float4*>(skip_g + a.skip_c + n));
-              float4 s2 = __ldg(reinterpret_cast<const float4*>(skip_g + rs + n));
-              float4 s3 = __ldg(reinterpret_cast<const float4*>(skip_g + rs + a.skip_c + n));
-              o4[0] += fmaxf(fmaxf(s0.x, s1.x), fmaxf(s2.x, s3.x));
-              o4[1] += fmaxf(fmaxf(s0.y, s1.y), fmaxf(s2.y, s3.y));
-              o4[2] += fmaxf(fmaxf(s0.z, s1.z), fmaxf(s2.z, s3.z));
-              o4[3] += fmaxf(fmaxf(s0.w, s1.w), fmaxf(s2.w, s3.w));
+            } else if (a.skip_mode == 2) {
+              if (skip_g) {
+                float4 s = __ldg(reinterpret_cast<const float4*>(skip_g + n));
+                o4[0] += s.x; o4[1] += s.y; o4[2] += s.z; o4[3] += s.w;
+              }
+            } else if (a.skip_mode == 3) {
+              if (skip_g) {
+                const long long rs = (long long)2 * a.W * a.skip_c;
+                float4 s = max4(max4(__ldg(reinterpret_cast<const float4*>(skip_g + n)), __ldg(reinterpret_cast<const float4*>(skip_g + a.skip_c + n))),
+                                max4(__ldg(reinterpret_cast<const float4*>(skip_g + rs + n)),
+                                     __ldg(reinterpret_cast<const float4*>(skip_g + rs + a.skip_c + n))));
+                o4[0] += s.x; o4[1] += s.y; o4[2] += s.z; o4[3] += s.w;
+              }
             }
           }
           if (a.act == ACT_RELU) {
@@ -298,6 +313,26 @@ bool encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, 
   return r == CUDA_SUCCESS;
 }
 
+// Picks (stages, alias_out) for a block; returns false when it cannot fit in shared memory.
+bool pick_smem(int C, int N, int Np, int S, int wsplit, int* stages, int* alias_out, int* total) {
+  const bool can_alias = TH * TW * N * 4 <= 2 * (C / 4) * kPlaneBytes;
+  int best = -1, best_per_sm = 0;
+  // candidate configurations in order of preference at equal occupancy
+  const int cand[4][2] = {{2, 0}, {2, 1}, {1, 0}, {1, 1}};
+  for (int i = 0; i < 4; ++i) {
+    if (cand[i][1] && !can_alias) continue;
+    SmemLayout L = smem_layout(C, N, Np, S, cand[i][0], wsplit, cand[i][1]);
+    if (L.total > kMaxSmemTc) continue;
+    int per_sm = (228 * 1024) / (L.total + 1024);
+    if (per_sm > 3) per_sm = 3;
+    if (per_sm > best_per_sm) { best_per_sm = per_sm; best = i; }
+  }
+  if (best < 0) return false;
+  *stages = cand[best][0]; *alias_out = cand[best][1];
+  *total = smem_layout(C, N, Np, S, *stages, wsplit, *alias_out).total;
+  return true;
+}
+
 }  // namespace
 
 cudaError_t mma_kernels_init() {
@@ -309,51 +344,48 @@ cudaError_t mma_kernels_init() {
     if (err == cudaSuccess && q == cudaDriverEntryPointSuccess) g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   });
   if (err != cudaSuccess) return err;
-  return cudaFuncSetAttribute(blaze_block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTc);
+  err = cudaFuncSetAttribute(blaze_block_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTc);
+  if (err != cudaSuccess) return err;
+  return cudaFuncSetAttribute(blaze_block_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTc);
 }
 
-bool block_tc_supported(const Step& s, int* stages_out) {
-  if (s.kind != STEP_BLOCK || s.stride != 1 || s.w_umma < 0) return false;
+bool block_tc_supported(const Step& s) {
+  if (s.kind != STEP_BLOCK || s.w_umma < 0) return false;
+  if (s.stride != 1 && s.stride != 2) return false;
   const int C = s.in.C, N = s.out.C;
   if (C % 8 != 0 || N % 4 != 0 || C < 16 || (kThreads % (C / 4)) != 0) return false;
-  if (s.Np > 128 || s.in.H < TH || s.in.W < TW) return false;
-  if (s.in.H != s.out.H || s.in.W != s.out.W) return false;
+  if (s.Np > 128 || s.out.H < TH || s.out.W < TW) return false;
+  if (s.stride == 1 && (s.pad_t != 1 || s.pad_l != 1 || s.in.H != s.out.H || s.in.W != s.out.W)) return false;
+  if (s.stride == 2 && (s.pad_t != 0 || s.pad_l != 0 || s.in.H != 2 * s.out.H || s.in.W != 2 * s.out.W)) return false;
   if (s.in.offset != 0 || s.out.offset != 0 || s.in.batch_stride != (int64_t)s.in.H * s.in.W * C ||
       s.out.batch_stride != (int64_t)s.out.H * s.out.W * N)
     return false;
   if (s.skip.tensor >= 0 && (s.skip_c % 4 != 0 || s.skip.offset != 0)) return false;
-  for (int stages = 2; stages >= 1; --stages) {
-    SmemLayout L = smem_layout(C, N, s.Np, stages, s.wsplit);
-    if (L.total <= kMaxSmemTc) {
-      // prefer the deepest pipeline that still lets two CTAs share an SM; otherwise whatever fits
-      if (stages == 2 && 2 * (L.total + 1024) > 228 * 1024) {
-        SmemLayout L1 = smem_layout(C, N, s.Np, 1, s.wsplit);
-        if (2 * (L1.total + 1024) <= 228 * 1024) { *stages_out = 1; return true; }
-      }
-      *stages_out = stages;
-      return true;
-    }
-  }
-  return false;
+  int stages, alias, total;
+  return pick_smem(C, N, s.Np, s.stride, s.wsplit, &stages, &alias, &total);
 }
 
 cudaError_t launch_block_tc(const BlockTcLaunch& l, cudaStream_t stream) {
   if (!g_encode) return cudaErrorNotSupported;
   BlockTcArgs a = l.args;
+  const int S = a.stride;
+  int total = 0;
+  if (!pick_smem(a.C, a.N, a.Np, S, a.wsplit, &a.stages, &a.alias_out, &total)) return cudaErrorInvalidConfiguration;
+  a.pad = S == 1 ? 1 : 0;
   CUtensorMap tm_in, tm_out;
-  if (!encode_nhwc(&tm_in, l.in, a.B, a.H, a.W, a.C, (long long)a.H * a.W * a.C, TH + 2, TW + 2)) return cudaErrorInvalidValue;
+  if (!encode_nhwc(&tm_in, l.in, a.B, a.H * S, a.W * S, a.C, (long long)a.H * S * a.W * S * a.C, in_tile_h(S), in_tile_w(S))) return cudaErrorInvalidValue;
   if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW)) return cudaErrorInvalidValue;
   a.tiles_x = (a.W + TW - 1) / TW;
   a.tiles_y = (a.H + TH - 1) / TH;
   a.tmem_cols = a.Np <= 32 ? 32 : (a.Np <= 64 ? 64 : 128);
-  SmemLayout L = smem_layout(a.C, a.N, a.Np, a.stages, a.wsplit);
   const int ntiles = a.B * a.tiles_x * a.tiles_y;
-  int per_sm = (228 * 1024) / (L.total + 1024);
+  int per_sm = (228 * 1024) / (total + 1024);
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
+  if (per_sm > 3) per_sm = 3;
   int grid = 148 * per_sm;
   if (grid > ntiles) grid = ntiles;
-  blaze_block_tc_kernel<<<grid, kThreads, L.total, stream>>>(tm_in, tm_out, a);
+  if (S == 1) blaze_block_tc_kernel<1><<<grid, kThreads, total, stream>>>(tm_in, tm_out, a);
+  else blaze_block_tc_kernel<2><<<grid, kThreads, total, stream>>>(tm_in, tm_out, a);
   count_launch();
   return cudaGetLastError();
 }

@@ -18,7 +18,11 @@ struct BlockTcArgs {
   int H = 0, W = 0, B = 0;
   int tiles_x = 0, tiles_y = 0;
   int act = 0;
-  int skip_mode = 0;               // 0 none, 1 identity from the resident input tile, 2 direct from global, 3 MAX_POOL 2x2 from global
+  int stride = 1;                  // depthwise stride (1: SAME pad 1; 2: SAME pad 0 before / 1 after on even sizes)
+  int pad = 1;
+  int alias_out = 0;               // output staging tile shares the A planes (large channel counts)
+  int skip_mode = 0;               // 0 none, 1 identity from the resident input tile, 2 direct from global, 3 MAX_POOL 2x2 from global,
+                                   // 4 MAX_POOL 2x2 from the resident input tile (stride-2 blocks)
   int skip_c = 0;                  // channels of the residual source (< N: zero channel PAD)
   int stages = 2;                  // input tile buffers
   int wsplit = 1;                  // 1: weights are tf32-exact (A split only); 2: W_hi + W_lo
@@ -33,7 +37,7 @@ struct BlockTcLaunch {
 };
 
 cudaError_t mma_kernels_init();                             // once per device
-bool block_tc_supported(const Step& s, int* stages_out);    // can this planned step run on the tensor-core kernel?
+bool block_tc_supported(const Step& s);    // can this planned step run on the tensor-core kernel?
 cudaError_t launch_block_tc(const BlockTcLaunch& l, cudaStream_t stream);
 
 }  // namespace fdl

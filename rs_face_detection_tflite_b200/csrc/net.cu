@@ -60,8 +60,7 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active) {
   if (B > cap_B_ || device_ < 0) return cudaErrorInvalidValue;
   for (const Step& s : plan_.steps) {
     cudaError_t e;
-    int tc_stages = 0;
-    if (mode_ == 1 && block_tc_supported(s, &tc_stages)) {
+    if (mode_ == 1 && block_tc_supported(s)) {
       BlockTcLaunch l;
       TView in = view(s.in, B), out = view(s.out, B);
       l.in = in.p; l.out = out.p;
@@ -69,12 +68,13 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active) {
       a.w_umma = d_weights_ + s.w_umma; a.bias = d_weights_ + s.b; a.w_dw = d_weights_ + s.w_dw; a.b_dw = d_weights_ + s.b_dw;
       a.alpha = s.alpha >= 0 ? d_weights_ + s.alpha : nullptr;
       a.C = s.in.C; a.N = s.out.C; a.Np = s.Np; a.H = s.out.H; a.W = s.out.W; a.B = B;
-      a.act = s.act; a.stages = tc_stages; a.wsplit = s.wsplit; a.n_active = n_active;
+      a.act = s.act; a.stride = s.stride; a.wsplit = s.wsplit; a.n_active = n_active;
       if (s.skip.tensor >= 0) {
         TView sk = view(s.skip, B);
         a.skip_c = s.skip_c;
-        if (s.skip_pool) { a.skip_mode = 3; a.skip = sk.p; a.skip_bstride = sk.bstride; }
-        else if (s.skip.tensor == s.in.tensor) a.skip_mode = 1;
+        if (s.skip_pool && s.skip.tensor == s.in.tensor && s.stride == 2) a.skip_mode = 4;
+        else if (s.skip_pool) { a.skip_mode = 3; a.skip = sk.p; a.skip_bstride = sk.bstride; }
+        else if (s.skip.tensor == s.in.tensor && s.stride == 1) a.skip_mode = 1;
         else { a.skip_mode = 2; a.skip = sk.p; a.skip_bstride = sk.bstride; }
       }
       e = launch_block_tc(l, stream);

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kThreads) fused_conv_kernel(const ConvArgs a) 
   constexpr int BNp = TX * 4;            // channels per pass
   const int tx = tid % TX, ty = tid / TX;
   const int N = a.N, Npad = a.Npad;
-  for (int n0 = 0; n0 < Npad; n0 += BNp) {
+  for (int n0 = blockIdx.y * BNp; n0 < Npad; n0 += gridDim.y * BNp) {
     const int n = n0 + tx * 4;
     float acc[4][4];
 #pragma unroll
@@ -251,19 +251,25 @@ cudaError_t net_kernels_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(fused_conv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   if (e != cudaSuccess) return e;
+  e = stem_kernels_init();
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(fused_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
 }
 
 cudaError_t launch_fused_conv(const ConvArgs& a, cudaStream_t stream) {
   const long long M = (long long)a.B * a.out.H * a.out.W;
   if (M <= 0) return cudaSuccess;
+  if (stem_supported(a)) return launch_stem_conv(a, stream);
   const int ldA = a.K4 + 4;
   // pick the pixel tile: as large as shared memory allows, smaller when the problem is tiny
   int BM = 64;
   while (BM > 16 && ((size_t)BM * ldA * 4 > (size_t)kMaxSmem || M <= BM * 74)) BM >>= 1;
   size_t smem = (size_t)BM * ldA * sizeof(float);
   if (smem > (size_t)kMaxSmem) return cudaErrorInvalidConfiguration;
-  unsigned grid = (unsigned)((M + BM - 1) / BM);
+  dim3 grid((unsigned)((M + BM - 1) / BM), 1, 1);
+  // few pixel tiles but many output channels (dense tails: M = batch): split the channel passes across CTAs
+  const int BNp = (kThreads / (BM / 4)) * 4;
+  if (grid.x < 148) grid.y = (unsigned)((a.Npad + BNp - 1) / BNp);
   if (BM == 64) fused_conv_kernel<64><<<grid, kThreads, smem, stream>>>(a);
   else if (BM == 32) fused_conv_kernel<32><<<grid, kThreads, smem, stream>>>(a);
   else fused_conv_kernel<16><<<grid, kThreads, smem, stream>>>(a);

@@ -48,6 +48,10 @@ struct EltArgs {
 // Returns cudaSuccess or the launch error.  `stream` is the handle's stream.
 cudaError_t launch_fused_conv(const ConvArgs& a, cudaStream_t stream);
 cudaError_t launch_elementwise(const EltArgs& a, cudaStream_t stream);
+// RGB stem convolutions (stem_kernel.cu)
+bool stem_supported(const ConvArgs& a);
+cudaError_t launch_stem_conv(const ConvArgs& a, cudaStream_t stream);
+cudaError_t stem_kernels_init();
 cudaError_t net_kernels_init();   // opt-in shared memory sizes; call once per device
 
 void count_launch();              // bumps the library-wide launch counter (fdl_launch_count)
