@@ -28,6 +28,7 @@ SOURCES = {
     "net_kernels.cu": [],
     "mma_kernels.cu": [],
     "stem_kernel.cu": [],
+    "conv_tc_kernel.cu": [],
     # the glue arithmetic must not contract a*b+c into FMA (the reference's scalar Rust never does)
     "prepost_kernels.cu": ["-fmad=false"],
     "fdl_api.cu": [],

@@ -1,0 +1,284 @@
+// conv_tc_kernel.cu -- general tensor-core convolution (sm_100a: tcgen05 + TMEM), for everything the TMA-tiled
+// BlazeBlock kernel does not take: CONV_2D 1x1 / 2x2 s2 / dense tails (k x k VALID over the whole map) / heads, and
+// BlazeBlocks on small feature maps (16x16 .. 2x2) where the parallelism has to come from the batch.
+//
+//   out[M = B*OH*OW pixels][N] = act( A[M][K] * W[K][N] + bias + skip )
+//
+// Pixels are flattened over the batch, so a 128-row MMA tile spans as many images as it needs.  The A tile is
+// gathered by the CTA's threads with 16-byte loads (im2col on the fly, or the depthwise 3x3 of a BlazeBlock
+// evaluated in registers), split into tf32 hi / lo parts (see mma_kernels.cu) and stored in shared memory in the
+// UMMA K-major core-matrix layout, 32 K-values at a time, double buffered: while tcgen05.mma consumes chunk c the
+// threads gather chunk c+1.  The accumulator lives in TMEM; the epilogue (tcgen05.ld, + bias, + residual,
+// RELU / PRELU) writes straight to global memory, which also covers the aliased head outputs ([B,N,16] / [B,N,1]).
+#include <cuda_runtime.h>
+
+#include "mma_kernels.cuh"
+#include "plan.h"
+#include "sm100_ptx.cuh"
+
+namespace fdl {
+
+void count_launch();
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int KC = 32;                               // K values per chunk
+constexpr int QC = KC / 4;                           // channel quads (A planes) per chunk
+constexpr int kPlaneBytes = 128 * 16 + 16;           // one A plane: 128 pixels x 16 B (+16 B bank skew)
+constexpr int kABytes = QC * kPlaneBytes;            // hi (or lo) planes of one chunk
+
+struct Layout { int bias, alpha, dw, a0, w0, a_stage, w_stage, total; };
+
+__host__ __device__ inline int align_up_c(int v, int a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline Layout layout(int Nt, int wsplit, int dw_c) {
+  Layout L;
+  int off = 64;
+  L.bias = off; off += Nt * 4;
+  L.alpha = off; off += Nt * 4;
+  off = align_up_c(off, 16);
+  L.dw = off; off += dw_c * 10 * 4;                 // depthwise weights [9][C] + bias [C] (BLOCK mode)
+  off = align_up_c(off, 128);
+  L.a_stage = 2 * kABytes;                          // hi + lo
+  L.a0 = off; off += 2 * L.a_stage;
+  off = align_up_c(off, 128);
+  L.w_stage = wsplit * QC * Nt * 16;
+  L.w0 = off; off += 2 * L.w_stage;
+  L.total = align_up_c(off, 128);
+  return L;
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w) {
+  a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y); a.z = fmaf(x.z, w.z, a.z); a.w = fmaf(x.w, w.w, a.w);
+}
+
+__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int Nt = a.Nt;
+  const Layout L = layout(Nt, a.wsplit, a.mode == 1 ? a.in.C : 0);
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem);           // [2]: chunk buffer free / all done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 32);
+  float* s_bias = reinterpret_cast<float*>(smem + L.bias);
+  float* s_alpha = reinterpret_cast<float*>(smem + L.alpha);
+  float* s_dw = reinterpret_cast<float*>(smem + L.dw);
+
+  const int OHW = a.out.H * a.out.W;
+  int nb = a.B;
+  if (a.n_active) nb = min(nb, *a.n_active);
+  const long long M = (long long)nb * OHW;
+  const long long m0 = (long long)blockIdx.x * 128;
+  if (m0 >= M) return;
+  const int nt = blockIdx.y;                       // N tile
+  const int n_base = nt * Nt;
+
+  if (tid == 0) {
+    ptx::mbar_init(&mma_bar[0], 1);
+    ptx::mbar_init(&mma_bar[1], 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+  for (int i = tid; i < Nt; i += kThreads) {
+    const int n = n_base + i;
+    s_bias[i] = n < a.N ? a.bias[n] : 0.f;
+    s_alpha[i] = (a.alpha && n < a.N) ? a.alpha[n] : 0.f;
+  }
+  if (a.mode == 1) {
+    const int C = a.in.C;
+    for (int i = tid; i < 9 * C; i += kThreads) s_dw[i] = a.w_dw[i];
+    for (int i = tid; i < C; i += kThreads) s_dw[9 * C + i] = a.b_dw[i];
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this thread's gather slots: quad j (fixed) of pixels p0 + 32*i
+  const int j = tid & (QC - 1);
+  const int p0 = tid >> 3;
+  int pb[4], py[4], px[4];
+  bool pv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    long long m = m0 + p0 + 32 * i;
+    pv[i] = m < M;
+    long long mm = pv[i] ? m : 0;
+    pb[i] = (int)(mm / OHW);
+    int pix = (int)(mm - (long long)pb[i] * OHW);
+    py[i] = pix / a.out.W;
+    px[i] = pix - py[i] * a.out.W;
+  }
+  const int Cin = a.in.C, IH = a.in.H, IW = a.in.W;
+  const int nchunks = a.Kp / KC;
+  const uint32_t idesc = ptx::umma_idesc_tf32(128, Nt);
+  const uint32_t w_lbo = (uint32_t)Nt * 16u;
+  const float4* wsrc = reinterpret_cast<const float4*>(a.w_tc) + (size_t)nt * a.wsplit * (a.Kp / 4) * Nt;   // this N tile
+  const int w4_per_chunk = QC * Nt;                 // float4s of one (hi or lo) chunk
+  const size_t w4_lo_off = (size_t)(a.Kp / 4) * Nt; // offset of the lo copy inside the N tile
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1;
+    // the MMAs that read this buffer two chunks ago must have completed
+    if (c >= 2) ptx::mbar_wait(&mma_bar[buf], (uint32_t)(((c >> 1) - 1) & 1));
+    uint8_t* s_a = smem + L.a0 + buf * L.a_stage;
+    float4* s_w = reinterpret_cast<float4*>(smem + L.w0 + buf * L.w_stage);
+    // ---- weights of this chunk (already in UMMA order) ----
+    for (int i = tid; i < w4_per_chunk; i += kThreads) {
+      s_w[i] = __ldg(wsrc + (size_t)c * w4_per_chunk + i);
+      if (a.wsplit == 2) s_w[w4_per_chunk + i] = __ldg(wsrc + w4_lo_off + (size_t)c * w4_per_chunk + i);
+    }
+    // ---- gather the A chunk ----
+    const int k = c * KC + 4 * j;                   // first K index of this thread's quad
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pv[i] && k < a.K) {
+        const float* img = a.in.p + (long long)pb[i] * a.in.bstride;
+        if (a.mode == 0) {
+          const int kwc = a.kw * Cin;
+          const int ky = k / kwc, r = k - ky * kwc;
+          const int kx = r / Cin, ci = r - kx * Cin;
+          const int iy = py[i] * a.stride - a.pad_t + ky, ix = px[i] * a.stride - a.pad_l + kx;
+          if (iy >= 0 && iy < IH && ix >= 0 && ix < IW) v = __ldg(reinterpret_cast<const float4*>(img + ((long long)iy * IW + ix) * Cin + ci));
+        } else {
+          // depthwise 3x3 (+bias) of channel quad k..k+3 at this pixel
+          v = *reinterpret_cast<const float4*>(s_dw + 9 * Cin + k);
+          const int iy0 = py[i] * a.stride - a.pad_t, ix0 = px[i] * a.stride - a.pad_l;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int iy = iy0 + ky;
+            if (iy < 0 || iy >= IH) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int ix = ix0 + kx;
+              if (ix < 0 || ix >= IW) continue;
+              fma4(v, __ldg(reinterpret_cast<const float4*>(img + ((long long)iy * IW + ix) * Cin + k)),
+                   *reinterpret_cast<const float4*>(s_dw + (ky * 3 + kx) * Cin + k));
+            }
+          }
+        }
+      }
+      float4 hi, lo;
+      hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+      lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+      const int p = p0 + 32 * i;
+      *reinterpret_cast<float4*>(s_a + j * kPlaneBytes + p * 16) = hi;
+      *reinterpret_cast<float4*>(s_a + kABytes + j * kPlaneBytes + p * 16) = lo;
+    }
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      ptx::tc_fence_after_sync();
+      const uint32_t ahi = ptx::smem_u32(s_a), alo = ahi + kABytes, wb = ptx::smem_u32(s_w);
+      for (int pass = 0; pass < (a.wsplit == 2 ? 3 : 2); ++pass) {
+        const uint32_t a_base = pass == 0 ? alo : ahi;
+        const uint32_t b_base = pass == 2 ? wb + (uint32_t)(w4_per_chunk * 16) : wb;
+#pragma unroll
+        for (int ks = 0; ks < KC / 8; ++ks) {
+          uint64_t ad = ptx::umma_desc_kmajor(a_base + (uint32_t)(ks * 2 * kPlaneBytes), kPlaneBytes, 128);
+          uint64_t bd = ptx::umma_desc_kmajor(b_base + (uint32_t)ks * 2u * w_lbo, w_lbo, 128);
+          ptx::mma_tf32(tmem_base, ad, bd, idesc, (c > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+        }
+      }
+      ptx::mma_commit(&mma_bar[buf]);               // frees this buffer; the last commit also signals the epilogue
+    }
+  }
+
+  // ---- epilogue ----
+  if (warp < 4) {
+    const int last = nchunks - 1;
+    ptx::mbar_wait(&mma_bar[last & 1], (uint32_t)((last >> 1) & 1));
+    ptx::tc_fence_after_sync();
+    const int p = tid;
+    const long long m = m0 + p;
+    const bool valid = m < M;
+    const long long mm = valid ? m : 0;
+    const int b = (int)(mm / OHW);
+    const int pix = (int)(mm - (long long)b * OHW);
+    const int N = a.N;
+    float* op = a.out.p + (long long)b * a.out.bstride + (long long)pix * N;
+    const float* sp = nullptr;
+    long long srow = 0;
+    if (a.has_skip && valid) {
+      if (a.skip_pool) {
+        const int oy = pix / a.out.W, ox = pix - oy * a.out.W;
+        sp = a.skip.p + (long long)b * a.skip.bstride + ((long long)(2 * oy) * a.skip.W + 2 * ox) * a.skip.C;
+        srow = (long long)a.skip.W * a.skip.C;
+      } else {
+        sp = a.skip.p + (long long)b * a.skip.bstride + (long long)pix * a.skip.C;
+      }
+    }
+    for (int c0 = 0; c0 < Nt; c0 += 16) {
+      float v[16];
+      ptx::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      if (!valid) continue;
+#pragma unroll
+      for (int q4 = 0; q4 < 16; q4 += 4) {
+        const int n = n_base + c0 + q4;
+        if (n >= N) break;
+        float o4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o4[e] = v[q4 + e] + s_bias[c0 + q4 + e];
+        if (sp) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int ch = n + e;
+            if (ch < a.skip_c) {
+              if (a.skip_pool) o4[e] += fmaxf(fmaxf(__ldg(sp + ch), __ldg(sp + a.skip.C + ch)), fmaxf(__ldg(sp + srow + ch), __ldg(sp + srow + a.skip.C + ch)));
+              else o4[e] += __ldg(sp + ch);
+            }
+          }
+        }
+        if (a.act == ACT_RELU) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o4[e] = fmaxf(o4[e], 0.f);
+        } else if (a.act == ACT_PRELU) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o4[e] = o4[e] >= 0.f ? o4[e] : o4[e] * s_alpha[c0 + q4 + e];
+        }
+        if ((N & 3) == 0) {
+          *reinterpret_cast<float4*>(op + n) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (n + e < N) op[n + e] = o4[e];
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+}
+
+}  // namespace
+
+cudaError_t conv_tc_init() {
+  return cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
+bool conv_tc_supported(const Step& s) {
+  if (s.kind != STEP_CONV && s.kind != STEP_BLOCK) return false;
+  if (s.w_tc < 0 || s.in.C % 4 != 0) return false;
+  if (s.in.offset != 0) return false;
+  if (s.kind == STEP_BLOCK && (s.in.C > 256)) return false;
+  if (s.skip.tensor >= 0 && s.skip.offset != 0) return false;
+  Layout L = layout(s.Nt, s.wsplit, s.kind == STEP_BLOCK ? s.in.C : 0);
+  return L.total <= 200 * 1024;
+}
+
+cudaError_t launch_conv_tc(const ConvTcArgs& a0, cudaStream_t stream) {
+  ConvTcArgs a = a0;
+  a.tmem_cols = a.Nt <= 32 ? 32 : (a.Nt <= 64 ? 64 : 128);
+  const long long M = (long long)a.B * a.out.H * a.out.W;
+  if (M <= 0) return cudaSuccess;
+  Layout L = layout(a.Nt, a.wsplit, a.mode == 1 ? a.in.C : 0);
+  dim3 grid((unsigned)((M + 127) / 128), (unsigned)a.n_tiles, 1);
+  conv_tc_kernel<<<grid, kThreads, L.total, stream>>>(a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace fdl

@@ -36,6 +36,29 @@ struct BlockTcLaunch {
   float* out = nullptr;            // [B,H,W,N]
 };
 
+// ---- general tensor-core convolution (conv_tc_kernel.cu) ----
+struct TViewC { const float* p = nullptr; long long bstride = 0; int H = 0, W = 0, C = 0; };
+struct TViewM { float* p = nullptr; long long bstride = 0; int H = 0, W = 0, C = 0; };
+struct ConvTcArgs {
+  TViewC in, skip;
+  TViewM out;
+  int mode = 0;                    // 0: CONV_2D (im2col gather), 1: BlazeBlock (depthwise 3x3 evaluated in the gather)
+  int kh = 1, kw = 1, stride = 1, pad_t = 0, pad_l = 0;
+  int K = 0, Kp = 0, N = 0, Nt = 0, n_tiles = 1;
+  const float* w_tc = nullptr;     // [n_tiles][wsplit][Kp/4][Nt][4]
+  const float* bias = nullptr;
+  const float* w_dw = nullptr;
+  const float* b_dw = nullptr;
+  const float* alpha = nullptr;
+  int act = 0, has_skip = 0, skip_pool = 0, skip_c = 0;
+  int wsplit = 1, tmem_cols = 32;
+  int B = 0;
+  const int* n_active = nullptr;
+};
+cudaError_t conv_tc_init();
+bool conv_tc_supported(const Step& s);
+cudaError_t launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
+
 cudaError_t mma_kernels_init();                             // once per device
 bool block_tc_supported(const Step& s);    // can this planned step run on the tensor-core kernel?
 cudaError_t launch_block_tc(const BlockTcLaunch& l, cudaStream_t stream);

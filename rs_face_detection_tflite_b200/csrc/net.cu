@@ -16,6 +16,7 @@ Net* Net::create(const std::string& path, int device, std::string* err, int* cod
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = net_kernels_init();
     if (e == cudaSuccess) e = mma_kernels_init();
+    if (e == cudaSuccess) e = conv_tc_init();
     if (e == cudaSuccess) e = cudaMalloc(&n->d_weights_, n->plan_.weights.size() * sizeof(float));
     if (e == cudaSuccess)
       e = cudaMemcpy(n->d_weights_, n->plan_.weights.data(), n->plan_.weights.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -78,6 +79,25 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active) {
         else { a.skip_mode = 2; a.skip = sk.p; a.skip_bstride = sk.bstride; }
       }
       e = launch_block_tc(l, stream);
+    } else if (mode_ == 1 && conv_tc_supported(s)) {
+      ConvTcArgs a;
+      TView in = view(s.in, B), out = view(s.out, B);
+      a.in.p = in.p; a.in.bstride = in.bstride; a.in.H = in.H; a.in.W = in.W; a.in.C = in.C;
+      a.out.p = out.p; a.out.bstride = out.bstride; a.out.H = out.H; a.out.W = out.W; a.out.C = out.C;
+      a.mode = s.kind == STEP_BLOCK ? 1 : 0;
+      a.kh = s.kh; a.kw = s.kw; a.stride = s.stride; a.pad_t = s.pad_t; a.pad_l = s.pad_l;
+      a.K = s.K; a.Kp = s.Kp; a.N = s.N; a.Nt = s.Nt; a.n_tiles = s.n_tiles;
+      a.w_tc = d_weights_ + s.w_tc; a.bias = d_weights_ + s.b;
+      if (s.w_dw >= 0) { a.w_dw = d_weights_ + s.w_dw; a.b_dw = d_weights_ + s.b_dw; }
+      if (s.alpha >= 0) a.alpha = d_weights_ + s.alpha;
+      a.act = s.act; a.wsplit = s.wsplit;
+      if (s.skip.tensor >= 0) {
+        TView sk = view(s.skip, B);
+        a.has_skip = 1; a.skip.p = sk.p; a.skip.bstride = sk.bstride; a.skip.H = sk.H; a.skip.W = sk.W; a.skip.C = sk.C;
+        a.skip_pool = s.skip_pool; a.skip_c = s.skip_c;
+      }
+      a.B = B; a.n_active = n_active;
+      e = launch_conv_tc(a, stream);
     } else if (s.kind == STEP_CONV || s.kind == STEP_BLOCK) {
       ConvArgs a;
       a.in = view(s.in, B); a.out = view(s.out, B);

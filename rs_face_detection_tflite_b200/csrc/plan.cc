@@ -378,6 +378,28 @@ bool Plan::build(const TfModel& m, std::string* err) {
       s.w = push(wt);
       s.b = push(bp);
       flops_per_item += 2LL * s.K * co * oh * ow;
+      if (ci % 4 == 0) {
+        auto hi_of = [](float v) { uint32_t u; std::memcpy(&u, &v, 4); u &= 0xffffe000u; float r; std::memcpy(&r, &u, 4); return r; };
+        bool exact = true;
+        for (float v : w) if (hi_of(v) != v) { exact = false; break; }
+        const int ws = exact ? 1 : 2;
+        s.Kp = (int)align_up(s.K, 32);
+        s.Nt = std::min((int)align_up(co, 16), 128);
+        s.n_tiles = (co + s.Nt - 1) / s.Nt;
+        const size_t plane = (size_t)(s.Kp / 4) * s.Nt * 4;       // floats of one (hi or lo) copy of one N tile
+        std::vector<float> pk((size_t)s.n_tiles * ws * plane, 0.f);
+        for (int o = 0; o < co; ++o) {
+          const int t = o / s.Nt, nn = o - t * s.Nt;
+          for (int k = 0; k < s.K; ++k) {
+            float v = w[(size_t)o * s.K + k], h = hi_of(v);
+            size_t at = (size_t)t * ws * plane + ((size_t)(k / 4) * s.Nt + nn) * 4 + (k % 4);
+            pk[at] = h;
+            if (ws == 2) pk[at + plane] = v - h;
+          }
+        }
+        s.w_tc = push(pk);
+        s.wsplit = ws;
+      }
       if (g.kind == STEP_BLOCK && ci % 8 == 0) {
         // tensor-core packing: plane q (4 input channels) x output channel n x 4 floats
         s.Np = (int)align_up(co, 16);

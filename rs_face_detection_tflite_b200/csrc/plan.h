@@ -60,6 +60,10 @@ struct Step {
   // else 2 = (tf32(w), w - tf32(w)).  -1 when Cin % 8 != 0.
   int64_t w_umma = -1;
   int Np = 0, wsplit = 1;
+  // CONV and BLOCK steps with Cin % 4 == 0: weights for the general tensor-core kernel,
+  // [n_tiles][wsplit][Kp/4][Nt][4] with Kp = roundup(K,32), Nt = min(roundup(N,16),128).
+  int64_t w_tc = -1;
+  int Kp = 0, Nt = 0, n_tiles = 0;
   int K = 0, K4 = 0, N = 0, Npad = 0;  // contraction size (K4 = roundup(K,4) rows stored) / output channels of the CONV/PW part
   std::vector<int> ops;           // tflite op indices folded into this step
   std::string text;               // human-readable description
