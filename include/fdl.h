@@ -233,6 +233,8 @@ typedef struct fdl_pipeline_config {
   int32_t run_landmarks;    /* 0: detection only (BASELINE config 2/3) */
   int32_t run_iris;         /* 0: stop after landmarks (config 4) */
   const char* model_dir;    /* directory holding the .tflite files; NULL -> "./models" */
+  int32_t zero_copy_host;   /* 1: contiguous PINNED host frames are read in place by the kernels (no whole-frame H2D copy) */
+  int32_t _pad;
 } fdl_pipeline_config;
 
 /* Per-face result record. */

@@ -42,7 +42,7 @@ class CImage(C.Structure):
 class CPipelineConfig(C.Structure):
     _fields_ = [("detector_model", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_int32), ("max_faces", C.c_int32),
                 ("frame_width", C.c_int32), ("frame_height", C.c_int32), ("run_landmarks", C.c_int32), ("run_iris", C.c_int32),
-                ("model_dir", C.c_char_p)]
+                ("model_dir", C.c_char_p), ("zero_copy_host", C.c_int32), ("_pad", C.c_int32)]
 
 
 class CFaceResult(C.Structure):

@@ -454,11 +454,12 @@ class Pipeline:
     """Batched detect -> landmark -> iris, the call sequence of lib.rs:20-40 for a batch of frames."""
 
     def __init__(self, detector_model: FaceDetectionModel = FaceDetectionModel.BackCamera, frame_size=(1920, 1080), max_batch: int = 64,
-                 max_faces: int = 1, run_landmarks: bool = True, run_iris: bool = True, model_dir: str | None = None, device: int = 0):
+                 max_faces: int = 1, run_landmarks: bool = True, run_iris: bool = True, model_dir: str | None = None, device: int = 0,
+                 zero_copy_host: bool = False):
         self._h = C.c_void_p()
         self._dir = os.fsencode(model_dir) if model_dir else None
         cfg = CPipelineConfig(int(detector_model), device, max_batch, max_faces, int(frame_size[0]), int(frame_size[1]),
-                              1 if run_landmarks else 0, 1 if (run_iris and run_landmarks) else 0, self._dir)
+                              1 if run_landmarks else 0, 1 if (run_iris and run_landmarks) else 0, self._dir, 1 if zero_copy_host else 0, 0)
         check(lib().fdl_pipeline_create(C.byref(cfg), C.byref(self._h)))
         self.max_batch, self.max_faces = max_batch, max_faces
         self.frame_size = (int(frame_size[0]), int(frame_size[1]))

@@ -44,7 +44,7 @@ struct PinBuf {
 // When `direct` is given and the images are device-resident, tightly packed and contiguous, no copy is
 // made: *direct receives the caller's pointer (which must stay valid until the work is collected).
 inline int stage_frames(const fdl_image* images, int n, DevBuf<uint8_t>* dst, cudaStream_t stream, int* w_out, int* h_out,
-                        const uint8_t** direct = nullptr) {
+                        const uint8_t** direct = nullptr, bool host_zero_copy = false, bool* used_host = nullptr) {
   if (!images || n <= 0) return set_error(FDL_ERR_INVALID, "no images given");
   const int w = images[0].width, h = images[0].height;
   if (w <= 0 || h <= 0) return set_error(FDL_ERR_INVALID, "image has non-positive size");
@@ -60,6 +60,24 @@ inline int stage_frames(const fdl_image* images, int n, DevBuf<uint8_t>* dst, cu
       contiguous = images[i].mem == FDL_MEM_DEVICE && (images[i].row_stride == 0 || (size_t)images[i].row_stride == row) &&
                    images[i].data == images[0].data + (size_t)i * frame;
     if (contiguous) { *direct = images[0].data; *w_out = w; *h_out = h; return FDL_OK; }
+    if (host_zero_copy) {
+      // pinned (page-locked, mapped) host frames: let the kernels read them in place over PCIe instead of
+      // copying whole frames -- the letterbox touches 27 % of a 1080p frame, the ROI warps a few hundred KB
+      bool hc = true;
+      for (int i = 0; i < n && hc; ++i)
+        hc = images[i].mem == FDL_MEM_HOST && (images[i].row_stride == 0 || (size_t)images[i].row_stride == row) &&
+             images[i].data == images[0].data + (size_t)i * frame;
+      if (hc) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, images[0].data) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+          *direct = static_cast<const uint8_t*>(at.devicePointer);
+          if (used_host) *used_host = true;
+          *w_out = w; *h_out = h;
+          return FDL_OK;
+        }
+        cudaGetLastError();
+      }
+    }
   }
   FDL_CUDA_TRY(dst->reserve(frame * (size_t)n));
   // coalesce runs of frames that are contiguous in the caller's memory into one copy

@@ -315,7 +315,7 @@ static int detector_infer_impl(fdl_detector* d, const fdl_image* images, int bat
   FDL_CUDA_TRY(launch_i2t_setup(d_roi, nullptr, nullptr, batch, w, h, d->S, d->S, 1, -1.0, 1.0, 0, d->params.p, nullptr, d->stream));
   TView iv = net->input_view(batch);
   FDL_CUDA_TRY(launch_i2t(d->frames.p, (long long)w * 3 * h, (long long)w * 3, d->params.p, batch, d->S, d->S, iv.p, iv.bstride, nullptr,
-                          nullptr, d->stream));
+                          nullptr, d->stream, 1, w));
   FDL_CUDA_TRY(net->forward(batch, d->stream));
   TView reg = net->output_view(0, batch), cls = net->output_view(1, batch);
   return detector_post(d, reg.p, reg.bstride, cls.p, cls.bstride, batch, d->params.p, nullptr, out, cap, n_out, nullptr, nullptr, 0, nullptr);

@@ -186,15 +186,31 @@ FDL_HD void i2t_setup(const fdl_rect* roi_or_null, int img_w, int img_h, int out
 // ------------------------------------------------------------------------------------------------
 struct Px3 { int r, g, b; };
 
-// One u8 RGB pixel of the source frame (row stride in bytes).
-FDL_HD Px3 load_px(const uint8_t* img, long long stride, int x, int y) {
-  const uint8_t* p = img + (long long)y * stride + 3 * x;
+// Where source pixels come from: the frame in (global / mapped host) memory, optionally shadowed by a staged copy
+// of the rectangle [tx0,tx1] x [ty0,ty1] (a kernel's shared-memory tile; row r of the tile holds the frame bytes
+// [tsb, tsb + tpitch) of frame row ty0 + r).  Pixels outside the staged rectangle fall through to `img`.
+struct ImgSrc {
+  const uint8_t* img;
+  long long stride;          // bytes between frame rows
+  const uint8_t* tile;       // nullptr: no staged copy
+  int tx0, ty0, tx1, ty1;    // staged pixel rectangle (inclusive)
+  int tpitch, tsb;
+};
+FDL_HD ImgSrc img_src(const uint8_t* img, long long stride) {
+  ImgSrc s; s.img = img; s.stride = stride; s.tile = nullptr; s.tx0 = s.ty0 = 0; s.tx1 = s.ty1 = -1; s.tpitch = 0; s.tsb = 0;
+  return s;
+}
+// One u8 RGB pixel of the source frame.
+FDL_HD Px3 load_px(const ImgSrc& s, int x, int y) {
+  const uint8_t* p;
+  if (s.tile && x >= s.tx0 && x <= s.tx1 && y >= s.ty0 && y <= s.ty1) p = s.tile + (long long)(y - s.ty0) * s.tpitch + (3 * x - s.tsb);
+  else p = s.img + (long long)y * s.stride + 3 * x;
   Px3 o; o.r = p[0]; o.g = p[1]; o.b = p[2];
   return o;
 }
 
 // cv::warpPerspective(INTER_LINEAR, BORDER_CONSTANT 0) at destination pixel (x,y): SURVEY.md B.2.
-FDL_HD Px3 warp_px(const I2TParams& P, const uint8_t* img, long long stride, int x, int y) {
+FDL_HD Px3 warp_px(const I2TParams& P, const ImgSrc& src, int x, int y) {
   const double* Mi = P.Mi;
   double W = Mi[6] * x + Mi[7] * y + Mi[8];
   W = W != 0.0 ? 32.0 / W : 0.0;
@@ -216,10 +232,10 @@ FDL_HD Px3 warp_px(const I2TParams& P, const uint8_t* img, long long stride, int
   int r = 0, g = 0, b = 0;
   bool x0 = sx >= 0 && sx < P.src_w, x1 = sx + 1 >= 0 && sx + 1 < P.src_w;
   bool y0 = sy >= 0 && sy < P.src_h, y1 = sy + 1 >= 0 && sy + 1 < P.src_h;
-  if (w00 && x0 && y0) { Px3 p = load_px(img, stride, sx, sy); r += p.r * w00; g += p.g * w00; b += p.b * w00; }
-  if (w01 && x1 && y0) { Px3 p = load_px(img, stride, sx + 1, sy); r += p.r * w01; g += p.g * w01; b += p.b * w01; }
-  if (w10 && x0 && y1) { Px3 p = load_px(img, stride, sx, sy + 1); r += p.r * w10; g += p.g * w10; b += p.b * w10; }
-  if (w11 && x1 && y1) { Px3 p = load_px(img, stride, sx + 1, sy + 1); r += p.r * w11; g += p.g * w11; b += p.b * w11; }
+  if (w00 && x0 && y0) { Px3 p = load_px(src, sx, sy); r += p.r * w00; g += p.g * w00; b += p.b * w00; }
+  if (w01 && x1 && y0) { Px3 p = load_px(src, sx + 1, sy); r += p.r * w01; g += p.g * w01; b += p.b * w01; }
+  if (w10 && x0 && y1) { Px3 p = load_px(src, sx, sy + 1); r += p.r * w10; g += p.g * w10; b += p.b * w10; }
+  if (w11 && x1 && y1) { Px3 p = load_px(src, sx + 1, sy + 1); r += p.r * w11; g += p.g * w11; b += p.b * w11; }
   Px3 o;
   o.r = (r + (1 << 14)) >> 15; o.g = (g + (1 << 14)) >> 15; o.b = (b + (1 << 14)) >> 15;
   return o;
@@ -249,22 +265,22 @@ FDL_HD int resize_mix(int p00, int p01, int p10, int p11, int a0, int a1, int b0
 }
 
 // pixel of the copyMakeBorder'ed warp (constant 0 border)
-FDL_HD Px3 border_px(const I2TParams& P, const uint8_t* img, long long stride, int x, int y) {
+FDL_HD Px3 border_px(const I2TParams& P, const ImgSrc& src, int x, int y) {
   int wx = x - P.pad_h, wy = y - P.pad_v;
   if (wx < 0 || wy < 0 || wx >= P.warp_w || wy >= P.warp_h) { Px3 z; z.r = z.g = z.b = 0; return z; }
-  return warp_px(P, img, stride, wx, wy);
+  return warp_px(P, src, wx, wy);
 }
 
 // pixel of the image after the optional first resize stage (size r1_w x r1_h)
-FDL_HD Px3 stage1_px(const I2TParams& P, const uint8_t* img, long long stride, int x, int y) {
-  if (!P.has_r1) return warp_px(P, img, stride, x, y);
+FDL_HD Px3 stage1_px(const I2TParams& P, const ImgSrc& src, int x, int y) {
+  if (!P.has_r1) return warp_px(P, src, x, y);
   int bw = P.warp_w + 2 * P.pad_h, bh = P.warp_h + 2 * P.pad_v;
-  if (bw == P.r1_w && bh == P.r1_h) return border_px(P, img, stride, x, y);   // cv::resize to the same size is a copy
+  if (bw == P.r1_w && bh == P.r1_h) return border_px(P, src, x, y);   // cv::resize to the same size is a copy
   int x0, x1, a0, a1, y0, y1, b0, b1;
   resize_coeff(x, P.r1_w, bw, true, &x0, &x1, &a0, &a1);
   resize_coeff(y, P.r1_h, bh, false, &y0, &y1, &b0, &b1);
-  Px3 p00 = border_px(P, img, stride, x0, y0), p01 = border_px(P, img, stride, x1, y0);
-  Px3 p10 = border_px(P, img, stride, x0, y1), p11 = border_px(P, img, stride, x1, y1);
+  Px3 p00 = border_px(P, src, x0, y0), p01 = border_px(P, src, x1, y0);
+  Px3 p10 = border_px(P, src, x0, y1), p11 = border_px(P, src, x1, y1);
   Px3 o;
   o.r = resize_mix(p00.r, p01.r, p10.r, p11.r, a0, a1, b0, b1);
   o.g = resize_mix(p00.g, p01.g, p10.g, p11.g, a0, a1, b0, b1);
@@ -273,15 +289,15 @@ FDL_HD Px3 stage1_px(const I2TParams& P, const uint8_t* img, long long stride, i
 }
 
 // final uint8 pixel of image_to_tensor's `roi_image` at output position (ox, oy) (after the flip)
-FDL_HD Px3 i2t_pixel(const I2TParams& P, const uint8_t* img, long long stride, int ox, int oy) {
+FDL_HD Px3 i2t_pixel(const I2TParams& P, const ImgSrc& src, int ox, int oy) {
   int x = P.flip ? P.out_w - 1 - ox : ox;
-  if (!P.has_r2) return warp_px(P, img, stride, x, oy);
-  if (P.r1_w == P.out_w && P.r1_h == P.out_h) return stage1_px(P, img, stride, x, oy);
+  if (!P.has_r2) return warp_px(P, src, x, oy);
+  if (P.r1_w == P.out_w && P.r1_h == P.out_h) return stage1_px(P, src, x, oy);
   int x0, x1, a0, a1, y0, y1, b0, b1;
   resize_coeff(x, P.out_w, P.r1_w, true, &x0, &x1, &a0, &a1);
   resize_coeff(oy, P.out_h, P.r1_h, false, &y0, &y1, &b0, &b1);
-  Px3 p00 = stage1_px(P, img, stride, x0, y0), p01 = stage1_px(P, img, stride, x1, y0);
-  Px3 p10 = stage1_px(P, img, stride, x0, y1), p11 = stage1_px(P, img, stride, x1, y1);
+  Px3 p00 = stage1_px(P, src, x0, y0), p01 = stage1_px(P, src, x1, y0);
+  Px3 p10 = stage1_px(P, src, x0, y1), p11 = stage1_px(P, src, x1, y1);
   Px3 o;
   o.r = resize_mix(p00.r, p01.r, p10.r, p11.r, a0, a1, b0, b1);
   o.g = resize_mix(p00.g, p01.g, p10.g, p11.g, a0, a1, b0, b1);

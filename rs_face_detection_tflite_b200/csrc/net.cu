@@ -57,13 +57,18 @@ TView Net::view(const TensorRef& r, int B) const {
   return v;
 }
 
-cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active) {
+cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const float* input_override) {
+  auto in_view = [&](const Step& st) {
+    TView v = view(st.in, B);
+    if (input_override && st.in.tensor == plan_.input.tensor) { v.p = const_cast<float*>(input_override); v.bstride = in_elems(); }
+    return v;
+  };
   if (B > cap_B_ || device_ < 0) return cudaErrorInvalidValue;
   for (const Step& s : plan_.steps) {
     cudaError_t e;
     if (mode_ == 1 && block_tc_supported(s)) {
       BlockTcLaunch l;
-      TView in = view(s.in, B), out = view(s.out, B);
+      TView in = in_view(s), out = view(s.out, B);
       l.in = in.p; l.out = out.p;
       BlockTcArgs& a = l.args;
       a.w_umma = d_weights_ + s.w_umma; a.bias = d_weights_ + s.b; a.w_dw = d_weights_ + s.w_dw; a.b_dw = d_weights_ + s.b_dw;
@@ -81,7 +86,7 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active) {
       e = launch_block_tc(l, stream);
     } else if (mode_ == 1 && conv_tc_supported(s)) {
       ConvTcArgs a;
-      TView in = view(s.in, B), out = view(s.out, B);
+      TView in = in_view(s), out = view(s.out, B);
       a.in.p = in.p; a.in.bstride = in.bstride; a.in.H = in.H; a.in.W = in.W; a.in.C = in.C;
       a.out.p = out.p; a.out.bstride = out.bstride; a.out.H = out.H; a.out.W = out.W; a.out.C = out.C;
       a.mode = s.kind == STEP_BLOCK ? 1 : 0;
@@ -100,7 +105,7 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active) {
       e = launch_conv_tc(a, stream);
     } else if (s.kind == STEP_CONV || s.kind == STEP_BLOCK) {
       ConvArgs a;
-      a.in = view(s.in, B); a.out = view(s.out, B);
+      a.in = in_view(s); a.out = view(s.out, B);
       a.mode = s.kind == STEP_BLOCK ? 1 : 0;
       a.kh = s.kh; a.kw = s.kw; a.stride = s.stride; a.pad_t = s.pad_t; a.pad_l = s.pad_l;
       a.K = s.K; a.K4 = s.K4; a.N = s.N; a.Npad = s.Npad;
@@ -113,7 +118,7 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active) {
       e = launch_fused_conv(a, stream);
     } else {
       EltArgs a;
-      a.in = view(s.in, B); a.out = view(s.out, B);
+      a.in = in_view(s); a.out = view(s.out, B);
       a.kind = s.kind; a.stride = s.stride; a.pad_t = s.pad_t; a.pad_l = s.pad_l;
       if (s.w_dw >= 0) { a.w_dw = d_weights_ + s.w_dw; a.b_dw = d_weights_ + s.b_dw; }
       if (s.alpha >= 0) a.alpha = d_weights_ + s.alpha;

@@ -35,7 +35,8 @@ class Net {
 
   // Enqueue every step for batch B on `stream`.  n_active (optional, device pointer): only the
   // first *n_active items are computed (data-dependent fan-out without a host round trip).
-  cudaError_t forward(int B, cudaStream_t stream, const int* n_active = nullptr);
+  // input_override (optional): read the network input from this [B, in_elems] buffer instead of the arena.
+  cudaError_t forward(int B, cudaStream_t stream, const int* n_active = nullptr, const float* input_override = nullptr);
 
  private:
   Net() = default;

@@ -6,9 +6,11 @@
 // device: the data-dependent fan-out (0..max_faces faces per frame, two eyes per face) is handled
 // with device-side slot lists and counters, never with a host round trip.
 //
-// Streams: one copy-in stream, one compute stream, one copy-out stream; `kDepth` lanes of frame /
-// result buffers so that the H2D copy of batch k+1 and the D2H copy of batch k-1 overlap the
-// kernels of batch k.
+// Concurrency: `kDepth` lanes, each with its own stream, frame buffer, network-input buffers, ROI / slot
+// scratch and result buffers.  A lane's stream runs copy-in (or, in zero-copy mode, kernels that read the
+// pinned host frames in place over PCIe), all kernels and the copy-out of one batch in order; two lanes in
+// flight overlap one batch's PCIe traffic with the other's compute.  The three networks (weights +
+// activation arenas) are shared: a per-network event serialises their use across lanes.
 #include <cuda_runtime.h>
 
 #include <cstring>
@@ -23,16 +25,21 @@
 using namespace fdl;
 
 namespace {
-constexpr int kDepth = 2;
+constexpr int kDepth = 4;
 constexpr int kStages = 10;
 
 struct Lane {
+  cudaStream_t stream = nullptr;
   DevBuf<uint8_t> frames;
+  DevBuf<float> det_in, lmk_in, iris_in;       // image_to_tensor outputs (network inputs), private to the lane
+  DevBuf<I2TParams> det_params, face_params, eye_params;
+  DevBuf<fdl_rect> face_rois, eye_rois;
+  DevBuf<int> slot_frame, slot_face, face_valid, eye_frame, eye_valid, counters;
   DevBuf<fdl_frame_result> d_frames;
   DevBuf<fdl_face_result> d_faces;
   PinBuf<fdl_frame_result> h_frames;
   PinBuf<fdl_face_result> h_faces;
-  cudaEvent_t ev_h2d_start = nullptr, ev_h2d = nullptr, ev_stage[kStages] = {}, ev_done = nullptr;
+  cudaEvent_t ev_h2d_start = nullptr, ev_stage[kStages] = {}, ev_done = nullptr;
   int n = 0;
   int ticket = -1;
   bool busy = false;
@@ -45,13 +52,10 @@ struct fdl_pipeline {
   Net* det = nullptr;
   Net* lmk = nullptr;
   Net* iris = nullptr;
+  cudaEvent_t guard[3] = {};     // last use of det / lmk / iris by any lane
   SsdOptions opt{};
   int S = 0, N = 0, LS = 0, IS = 0;
-  cudaStream_t s_in = nullptr, s_compute = nullptr, s_out = nullptr;
   DevBuf<float> anchors;
-  DevBuf<I2TParams> det_params, face_params, eye_params;
-  DevBuf<fdl_rect> face_rois, eye_rois;
-  DevBuf<int> slot_frame, slot_face, face_valid, eye_frame, eye_valid, counters;
   Lane lanes[kDepth];
   int next_ticket = 0;
   float last_device_ms = 0.f;
@@ -64,13 +68,11 @@ static void pipeline_free(fdl_pipeline* p) {
   cudaDeviceSynchronize();
   for (auto& l : p->lanes) {
     if (l.ev_h2d_start) cudaEventDestroy(l.ev_h2d_start);
-    if (l.ev_h2d) cudaEventDestroy(l.ev_h2d);
     if (l.ev_done) cudaEventDestroy(l.ev_done);
     for (auto& e : l.ev_stage) if (e) cudaEventDestroy(e);
+    if (l.stream) cudaStreamDestroy(l.stream);
   }
-  if (p->s_in) cudaStreamDestroy(p->s_in);
-  if (p->s_compute) cudaStreamDestroy(p->s_compute);
-  if (p->s_out) cudaStreamDestroy(p->s_out);
+  for (auto& g : p->guard) if (g) cudaEventDestroy(g);
   delete p->det; delete p->lmk; delete p->iris;
   delete p;
 }
@@ -121,39 +123,40 @@ int fdl_pipeline_create(const fdl_pipeline_config* cfg, fdl_pipeline** out) {
     }
   }
   const int B = cfg->max_batch, F = B * cfg->max_faces, E = 2 * F;
-  cudaError_t e = cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_compute, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = p->anchors.reserve((size_t)p->N * 2);
-  if (e == cudaSuccess) e = launch_anchors(p->opt, p->anchors.p, p->N, p->s_compute);
-  if (e == cudaSuccess) e = p->det_params.reserve(B);
-  if (e == cudaSuccess) e = p->face_params.reserve(F);
-  if (e == cudaSuccess) e = p->eye_params.reserve(E);
-  if (e == cudaSuccess) e = p->face_rois.reserve(F);
-  if (e == cudaSuccess) e = p->eye_rois.reserve(E);
-  if (e == cudaSuccess) e = p->slot_frame.reserve(F);
-  if (e == cudaSuccess) e = p->slot_face.reserve(F);
-  if (e == cudaSuccess) e = p->face_valid.reserve(F);
-  if (e == cudaSuccess) e = p->eye_frame.reserve(E);
-  if (e == cudaSuccess) e = p->eye_valid.reserve(E);
-  if (e == cudaSuccess) e = p->counters.reserve(4);
-  if (e == cudaSuccess) e = cudaMemsetAsync(p->counters.p, 0, 4 * sizeof(int), p->s_compute);
+  cudaError_t e = p->anchors.reserve((size_t)p->N * 2);
+  for (auto& g : p->guard) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g, cudaEventDisableTiming);
   const size_t frame_bytes = (size_t)cfg->frame_width * 3 * cfg->frame_height;
   for (auto& l : p->lanes) {
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = l.frames.reserve(frame_bytes * B);
+    if (e == cudaSuccess) e = l.det_in.reserve((size_t)B * p->S * p->S * 3);
+    if (e == cudaSuccess && p->lmk) e = l.lmk_in.reserve((size_t)F * p->LS * p->LS * 3);
+    if (e == cudaSuccess && p->iris) e = l.iris_in.reserve((size_t)E * p->IS * p->IS * 3);
+    if (e == cudaSuccess) e = l.det_params.reserve(B);
+    if (e == cudaSuccess) e = l.face_params.reserve(F);
+    if (e == cudaSuccess) e = l.eye_params.reserve(E);
+    if (e == cudaSuccess) e = l.face_rois.reserve(F);
+    if (e == cudaSuccess) e = l.eye_rois.reserve(E);
+    if (e == cudaSuccess) e = l.slot_frame.reserve(F);
+    if (e == cudaSuccess) e = l.slot_face.reserve(F);
+    if (e == cudaSuccess) e = l.face_valid.reserve(F);
+    if (e == cudaSuccess) e = l.eye_frame.reserve(E);
+    if (e == cudaSuccess) e = l.eye_valid.reserve(E);
+    if (e == cudaSuccess) e = l.counters.reserve(4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(l.counters.p, 0, 4 * sizeof(int), l.stream);
     if (e == cudaSuccess) e = l.d_frames.reserve(B);
     if (e == cudaSuccess) e = l.d_faces.reserve(F);
     if (e == cudaSuccess) e = l.h_frames.reserve(B);
     if (e == cudaSuccess) e = l.h_faces.reserve(F);
     if (e == cudaSuccess) e = cudaEventCreate(&l.ev_h2d_start);
-    if (e == cudaSuccess) e = cudaEventCreate(&l.ev_h2d);
     if (e == cudaSuccess) e = cudaEventCreate(&l.ev_done);
     for (auto& ev : l.ev_stage) if (e == cudaSuccess) e = cudaEventCreate(&ev);
   }
+  if (e == cudaSuccess) e = launch_anchors(p->opt, p->anchors.p, p->N, p->lanes[0].stream);
   if (e != cudaSuccess) return bail(FDL_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
   if (!p->det->reserve(B, &err) || (p->lmk && !p->lmk->reserve(F, &err)) || (p->iris && !p->iris->reserve(E, &err)))
     return bail(FDL_ERR_CUDA, err);
-  e = cudaStreamSynchronize(p->s_compute);
+  e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return bail(FDL_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
   *out = p;
   return FDL_OK;
@@ -172,37 +175,36 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
   const int W = p->cfg.frame_width, H = p->cfg.frame_height, MF = p->cfg.max_faces;
   for (int i = 0; i < n; ++i)
     if (frames[i].width != W || frames[i].height != H) return set_error(FDL_ERR_INVALID, "frame size differs from the pipeline configuration");
+  cudaStream_t cs = lane->stream;
 
-  // ---- copy-in
-  FDL_CUDA_TRY(cudaEventRecord(lane->ev_h2d_start, p->s_in));
+  // ---- copy-in (skipped for contiguous device frames and, in zero-copy mode, for pinned host frames)
+  FDL_CUDA_TRY(cudaEventRecord(lane->ev_h2d_start, cs));
   int w, h;
-  const uint8_t* fptr = nullptr;   // lane->frames, or the caller's device memory when it is already contiguous
-  int rc = stage_frames(frames, n, &lane->frames, p->s_in, &w, &h, &fptr);
+  const uint8_t* fptr = nullptr;
+  bool used_host = false;
+  int rc = stage_frames(frames, n, &lane->frames, cs, &w, &h, &fptr, p->cfg.zero_copy_host != 0, &used_host);
   if (rc) return rc;
-  FDL_CUDA_TRY(cudaEventRecord(lane->ev_h2d, p->s_in));
 
-  // ---- compute
-  cudaStream_t cs = p->s_compute;
-  FDL_CUDA_TRY(cudaStreamWaitEvent(cs, lane->ev_h2d, 0));
   const long long row = (long long)W * 3, fstride = row * H;
+  const int zc_ctas = used_host ? 96 : 0;   // persistent CTAs for kernels that read host memory over PCIe
   const int F = n * MF, E = 2 * F;
-  int* n_faces = p->counters.p;
-  int* n_eyes = p->counters.p + 1;
+  int* n_faces = lane->counters.p;
+  int* n_eyes = lane->counters.p + 1;
   FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[0], cs));
   FDL_CUDA_TRY(cudaMemsetAsync(lane->d_frames.p, 0, (size_t)n * sizeof(fdl_frame_result), cs));
   FDL_CUDA_TRY(cudaMemsetAsync(lane->d_faces.p, 0, (size_t)F * sizeof(fdl_face_result), cs));
   // FaceDetection::infer: image_to_tensor(keep_aspect, (-1,1)) -> net -> SSD post-processing
-  FDL_CUDA_TRY(launch_i2t_setup(nullptr, nullptr, nullptr, n, W, H, p->S, p->S, 1, -1.0, 1.0, 0, p->det_params.p, nullptr, cs));
-  TView div = p->det->input_view(n);
-  FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, p->det_params.p, n, p->S, p->S, div.p, div.bstride, nullptr, nullptr, cs));
+  FDL_CUDA_TRY(launch_i2t_setup(nullptr, nullptr, nullptr, n, W, H, p->S, p->S, 1, -1.0, 1.0, 0, lane->det_params.p, nullptr, cs));
+  FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, lane->det_params.p, n, p->S, p->S, lane->det_in.p, (long long)p->S * p->S * 3, nullptr, nullptr, cs, 1, W, zc_ctas));
   FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[1], cs));
-  FDL_CUDA_TRY(p->det->forward(n, cs));
+  FDL_CUDA_TRY(cudaStreamWaitEvent(cs, p->guard[0], 0));
+  FDL_CUDA_TRY(p->det->forward(n, cs, nullptr, lane->det_in.p));
   FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[2], cs));
   {
     TView reg = p->det->output_view(0, n), cls = p->det->output_view(1, n);
     SsdPostArgs a;
     a.reg = reg.p; a.reg_bstride = reg.bstride; a.cls = cls.p; a.cls_bstride = cls.bstride;
-    a.anchors = p->anchors.p; a.N = p->N; a.B = n; a.scale = (float)p->S; a.params = p->det_params.p;
+    a.anchors = p->anchors.p; a.N = p->N; a.B = n; a.scale = (float)p->S; a.params = lane->det_params.p;
     a.det_base = reinterpret_cast<char*>(lane->d_frames.p) + offsetof(fdl_frame_result, detections);
     a.det_stride = sizeof(fdl_frame_result);
     a.ndet_base = reinterpret_cast<char*>(lane->d_frames.p) + offsetof(fdl_frame_result, n_detections);
@@ -210,36 +212,39 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
     a.max_out = FDL_MAX_DETECTIONS;
     FDL_CUDA_TRY(launch_ssd_postprocess(a, cs));
   }
+  FDL_CUDA_TRY(cudaEventRecord(p->guard[0], cs));
   FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[3], cs));
   if (p->lmk) {
     // face_detection_to_roi + FaceLandmark::infer for the first max_faces detections of every frame
-    FDL_CUDA_TRY(launch_face_select(lane->d_frames.p, n, MF, p->slot_frame.p, p->slot_face.p, n_faces, n_eyes, cs));
-    FDL_CUDA_TRY(launch_face_roi(lane->d_frames.p, p->slot_frame.p, p->slot_face.p, F, MF, W, H, p->face_rois.p, p->face_valid.p,
+    FDL_CUDA_TRY(launch_face_select(lane->d_frames.p, n, MF, lane->slot_frame.p, lane->slot_face.p, n_faces, n_eyes, cs));
+    FDL_CUDA_TRY(launch_face_roi(lane->d_frames.p, lane->slot_frame.p, lane->slot_face.p, F, MF, W, H, lane->face_rois.p, lane->face_valid.p,
                                  lane->d_faces.p, n_faces, cs));
-    FDL_CUDA_TRY(launch_i2t_setup(p->face_rois.p, p->slot_frame.p, p->face_valid.p, F, W, H, p->LS, p->LS, 0, 0.0, 1.0, 0, p->face_params.p,
-                                  n_faces, cs));
-    TView liv = p->lmk->input_view(F);
-    FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, p->face_params.p, F, p->LS, p->LS, liv.p, liv.bstride, nullptr, n_faces, cs));
+    FDL_CUDA_TRY(launch_i2t_setup(lane->face_rois.p, lane->slot_frame.p, lane->face_valid.p, F, W, H, p->LS, p->LS, 0, 0.0, 1.0, 0,
+                                  lane->face_params.p, n_faces, cs));
+    FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, lane->face_params.p, F, p->LS, p->LS, lane->lmk_in.p, (long long)p->LS * p->LS * 3, nullptr, n_faces, cs, 0, 0, zc_ctas));
     FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[4], cs));
-    FDL_CUDA_TRY(p->lmk->forward(F, cs, n_faces));
+    FDL_CUDA_TRY(cudaStreamWaitEvent(cs, p->guard[1], 0));
+    FDL_CUDA_TRY(p->lmk->forward(F, cs, n_faces, lane->lmk_in.p));
     FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[5], cs));
     TView raw = p->lmk->output_view(0, F), flag = p->lmk->output_view(1, F);
     // the reference reads the LAST element of the flag tensor (face_landmark.rs:292-293)
-    FDL_CUDA_TRY(launch_landmark_post(raw.p, raw.bstride, flag.p + p->lmk->out_elems(1) - 1, flag.bstride, p->face_params.p, p->face_rois.p,
-                                      p->slot_frame.p, p->slot_face.p, F, MF, p->LS, p->LS, lane->d_faces.p, p->eye_rois.p, p->eye_frame.p,
-                                      p->eye_valid.p, n_faces, cs));
+    FDL_CUDA_TRY(launch_landmark_post(raw.p, raw.bstride, flag.p + p->lmk->out_elems(1) - 1, flag.bstride, lane->face_params.p, lane->face_rois.p,
+                                      lane->slot_frame.p, lane->slot_face.p, F, MF, p->LS, p->LS, lane->d_faces.p, lane->eye_rois.p,
+                                      lane->eye_frame.p, lane->eye_valid.p, n_faces, cs));
+    FDL_CUDA_TRY(cudaEventRecord(p->guard[1], cs));
     if (p->iris) {
       // IrisLandmark::infer for both eyes: image_to_tensor(keep_aspect, (0,1), flip = right eye)
-      FDL_CUDA_TRY(launch_i2t_setup(p->eye_rois.p, p->eye_frame.p, p->eye_valid.p, E, W, H, p->IS, p->IS, 1, 0.0, 1.0, 2, p->eye_params.p, n_eyes,
-                                    cs));
-      TView iiv = p->iris->input_view(E);
-      FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, p->eye_params.p, E, p->IS, p->IS, iiv.p, iiv.bstride, nullptr, n_eyes, cs));
+      FDL_CUDA_TRY(launch_i2t_setup(lane->eye_rois.p, lane->eye_frame.p, lane->eye_valid.p, E, W, H, p->IS, p->IS, 1, 0.0, 1.0, 2,
+                                    lane->eye_params.p, n_eyes, cs));
+      FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, lane->eye_params.p, E, p->IS, p->IS, lane->iris_in.p, (long long)p->IS * p->IS * 3, nullptr, n_eyes, cs, 0, 0, zc_ctas));
       FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[6], cs));
-      FDL_CUDA_TRY(p->iris->forward(E, cs, n_eyes));
+      FDL_CUDA_TRY(cudaStreamWaitEvent(cs, p->guard[2], 0));
+      FDL_CUDA_TRY(p->iris->forward(E, cs, n_eyes, lane->iris_in.p));
       FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[7], cs));
       TView ec = p->iris->output_view(0, E), ir = p->iris->output_view(1, E);
-      FDL_CUDA_TRY(launch_iris_post(ec.p, ec.bstride, ir.p, ir.bstride, p->eye_params.p, p->eye_rois.p, p->eye_valid.p, p->slot_frame.p,
-                                    p->slot_face.p, E, MF, p->IS, p->IS, lane->d_faces.p, n_eyes, cs));
+      FDL_CUDA_TRY(launch_iris_post(ec.p, ec.bstride, ir.p, ir.bstride, lane->eye_params.p, lane->eye_rois.p, lane->eye_valid.p, lane->slot_frame.p,
+                                    lane->slot_face.p, E, MF, p->IS, p->IS, lane->d_faces.p, n_eyes, cs));
+      FDL_CUDA_TRY(cudaEventRecord(p->guard[2], cs));
     } else {
       FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[6], cs));
       FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[7], cs));
@@ -250,13 +255,10 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
   FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[8], cs));
 
   // ---- copy-out
-  FDL_CUDA_TRY(cudaStreamWaitEvent(p->s_out, lane->ev_stage[8], 0));
-  FDL_CUDA_TRY(cudaMemcpyAsync(lane->h_frames.p, lane->d_frames.p, (size_t)n * sizeof(fdl_frame_result), cudaMemcpyDeviceToHost, p->s_out));
+  FDL_CUDA_TRY(cudaMemcpyAsync(lane->h_frames.p, lane->d_frames.p, (size_t)n * sizeof(fdl_frame_result), cudaMemcpyDeviceToHost, cs));
   if (p->lmk)
-    FDL_CUDA_TRY(cudaMemcpyAsync(lane->h_faces.p, lane->d_faces.p, (size_t)F * sizeof(fdl_face_result), cudaMemcpyDeviceToHost, p->s_out));
-  FDL_CUDA_TRY(cudaEventRecord(lane->ev_done, p->s_out));
-  // the next copy-in into this lane's frame buffer may only start once these kernels are done;
-  // that is guaranteed because the lane stays busy until its ticket is collected.
+    FDL_CUDA_TRY(cudaMemcpyAsync(lane->h_faces.p, lane->d_faces.p, (size_t)F * sizeof(fdl_face_result), cudaMemcpyDeviceToHost, cs));
+  FDL_CUDA_TRY(cudaEventRecord(lane->ev_done, cs));
   lane->n = n;
   lane->busy = true;
   lane->ticket = p->next_ticket++;
@@ -276,7 +278,7 @@ int fdl_pipeline_collect(fdl_pipeline* p, int ticket, fdl_frame_result* frame_re
   if (face_results && p->lmk) std::memcpy(face_results, lane->h_faces.p, (size_t)F * sizeof(fdl_face_result));
   if (n_out) *n_out = n;
   float ms = 0.f;
-  cudaEventElapsedTime(&p->stage_ms[0], lane->ev_h2d_start, lane->ev_h2d);
+  cudaEventElapsedTime(&p->stage_ms[0], lane->ev_h2d_start, lane->ev_stage[0]);
   for (int i = 0; i < 8; ++i) {
     cudaEventElapsedTime(&ms, lane->ev_stage[i], lane->ev_stage[i + 1]);
     p->stage_ms[i + 1] = ms;

@@ -38,29 +38,242 @@ __global__ void __launch_bounds__(256) i2t_kernel(const uint8_t* __restrict__ fr
                                                   const I2TParams* __restrict__ params, int n, int out_w, int out_h,
                                                   float* __restrict__ out, long long out_bstride, uint8_t* __restrict__ out_u8,
                                                   const int* n_active) {
-  int slot = blockIdx.y;
   if (n_active) n = min(n, *n_active);
-  if (slot >= n) return;
   __shared__ I2TParams P;
+  const int blocks_per_slot = (out_w * out_h + 255) / 256;
+  const long long items = (long long)n * blocks_per_slot;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int slot = (int)(item / blocks_per_slot), blk = (int)(item - (long long)slot * blocks_per_slot);
+    __syncthreads();
+    {
+      const int* src = reinterpret_cast<const int*>(&params[slot]);
+      int* dst = reinterpret_cast<int*>(&P);
+      for (int i = threadIdx.x; i < (int)(sizeof(I2TParams) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    int pix = blk * blockDim.x + threadIdx.x;
+    if (pix >= out_w * out_h) continue;
+    int oy = pix / out_w, ox = pix - oy * out_w;
+    Px3 p;
+    if (P.valid) p = i2t_pixel(P, img_src(frames + (long long)P.frame * frame_stride, row_stride), ox, oy);
+    else { p.r = p.g = p.b = 0; }
+    float* o = out + (long long)slot * out_bstride + (long long)pix * 3;
+    o[0] = i2t_normalise(p.r, P.range_min, P.range_max);
+    o[1] = i2t_normalise(p.g, P.range_min, P.range_max);
+    o[2] = i2t_normalise(p.b, P.range_min, P.range_max);
+    if (out_u8) {
+      uint8_t* u = out_u8 + ((long long)slot * out_w * out_h + pix) * 3;
+      u[0] = (uint8_t)p.r; u[1] = (uint8_t)p.g; u[2] = (uint8_t)p.b;
+    }
+  }
+}
+
+// Row-staged variant for the detector's letterbox (roi = None): one CTA per output row.  When the slot's
+// transform is the plain letterbox (identity warp, border, ONE real resize, no flip) the CTA stages the two
+// source rows this output row interpolates between in shared memory with fully coalesced 16-byte loads --
+// every source byte crosses the memory system (HBM, or PCIe when `frames` is mapped pinned host memory) exactly
+// once, and only the rows the 2x2-tap resize touches are read at all (27 % of a 1080p frame at S = 256).
+// The arithmetic is the same fixed-point resize as i2t_pixel (bit-exact); any other slot takes the generic
+// per-pixel path inside the same kernel.
+__global__ void __launch_bounds__(256) i2t_rows_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
+                                                       const I2TParams* __restrict__ params, int n, int out_w, int out_h,
+                                                       float* __restrict__ out, long long out_bstride, const int* n_active) {
+  extern __shared__ __align__(16) uint8_t s_rows[];
+  if (n_active) n = min(n, *n_active);
+  __shared__ I2TParams P;
+  const long long items = (long long)n * out_h;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+  const int slot = (int)(item / out_h), oy = (int)(item - (long long)slot * out_h);
+  __syncthreads();
   {
     const int* src = reinterpret_cast<const int*>(&params[slot]);
     int* dst = reinterpret_cast<int*>(&P);
     for (int i = threadIdx.x; i < (int)(sizeof(I2TParams) / 4); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= out_w * out_h) return;
-  int oy = pix / out_w, ox = pix - oy * out_w;
-  Px3 p;
-  if (P.valid) p = i2t_pixel(P, frames + (long long)P.frame * frame_stride, row_stride, ox, oy);
-  else { p.r = p.g = p.b = 0; }
-  float* o = out + (long long)slot * out_bstride + (long long)pix * 3;
-  o[0] = i2t_normalise(p.r, P.range_min, P.range_max);
-  o[1] = i2t_normalise(p.g, P.range_min, P.range_max);
-  o[2] = i2t_normalise(p.b, P.range_min, P.range_max);
-  if (out_u8) {
-    uint8_t* u = out_u8 + ((long long)slot * out_w * out_h + pix) * 3;
-    u[0] = (uint8_t)p.r; u[1] = (uint8_t)p.g; u[2] = (uint8_t)p.b;
+  float* orow = out + (long long)slot * out_bstride + (long long)oy * out_w * 3;
+  const uint8_t* img = frames + (long long)P.frame * frame_stride;
+  const int bw = P.warp_w + 2 * P.pad_h, bh = P.warp_h + 2 * P.pad_v;
+  bool simple = P.valid && P.has_r2 && !P.flip && P.warp_w == P.src_w && P.warp_h == P.src_h &&
+                (!P.has_r1 || (bw == P.r1_w && bh == P.r1_h)) && !(P.r1_w == out_w && P.r1_h == out_h);
+  if (simple) {
+    const double e = 1e-9;   // identity warp: the solve reproduces I up to rounding (exact copy)
+    simple = fabs(P.Mi[0] - 1.0) < e && fabs(P.Mi[4] - 1.0) < e && fabs(P.Mi[8] - 1.0) < e && fabs(P.Mi[1]) < e && fabs(P.Mi[2]) < e * P.src_w &&
+             fabs(P.Mi[3]) < e && fabs(P.Mi[5]) < e * P.src_h && fabs(P.Mi[6]) < e && fabs(P.Mi[7]) < e;
+  }
+  if (!simple) {
+    for (int ox = threadIdx.x; ox < out_w; ox += blockDim.x) {
+      Px3 p;
+      if (P.valid) p = i2t_pixel(P, img_src(img, row_stride), ox, oy);
+      else { p.r = p.g = p.b = 0; }
+      orow[3 * ox] = i2t_normalise(p.r, P.range_min, P.range_max);
+      orow[3 * ox + 1] = i2t_normalise(p.g, P.range_min, P.range_max);
+      orow[3 * ox + 2] = i2t_normalise(p.b, P.range_min, P.range_max);
+    }
+    continue;
+  }
+  const int ph = P.has_r1 ? P.pad_h : 0, pv = P.has_r1 ? P.pad_v : 0;
+  int y0, y1, b0, b1;
+  resize_coeff(oy, out_h, P.r1_h, false, &y0, &y1, &b0, &b1);
+  const int sy0 = y0 - pv, sy1 = y1 - pv;                        // source rows (outside the frame: constant-0 border)
+  const bool in0 = sy0 >= 0 && sy0 < P.src_h, in1 = sy1 >= 0 && sy1 < P.src_h;
+  const int row_bytes = P.src_w * 3;
+  const int row_pad = (row_bytes + 15) & ~15;
+  uint8_t* r0 = s_rows;
+  uint8_t* r1 = s_rows + row_pad;
+  if (in0 || in1) {
+    const uint8_t* g0 = img + (long long)sy0 * row_stride;
+    const uint8_t* g1 = img + (long long)sy1 * row_stride;
+    const bool vec = ((reinterpret_cast<uintptr_t>(img) | (uintptr_t)row_stride) & 15) == 0;
+    if (vec) {
+      const int nv = row_bytes >> 4;
+      for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        if (in0) reinterpret_cast<uint4*>(r0)[i] = __ldg(reinterpret_cast<const uint4*>(g0) + i);
+        if (in1) reinterpret_cast<uint4*>(r1)[i] = __ldg(reinterpret_cast<const uint4*>(g1) + i);
+      }
+      for (int i = (nv << 4) + threadIdx.x; i < row_bytes; i += blockDim.x) {
+        if (in0) r0[i] = g0[i];
+        if (in1) r1[i] = g1[i];
+      }
+    } else {
+      for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) {
+        if (in0) r0[i] = g0[i];
+        if (in1) r1[i] = g1[i];
+      }
+    }
+  }
+  __syncthreads();
+  for (int ox = threadIdx.x; ox < out_w; ox += blockDim.x) {
+    int x0, x1, a0, a1;
+    resize_coeff(ox, out_w, P.r1_w, true, &x0, &x1, &a0, &a1);
+    const int sx0 = x0 - ph, sx1 = x1 - ph;
+    const bool cx0 = sx0 >= 0 && sx0 < P.src_w, cx1 = sx1 >= 0 && sx1 < P.src_w;
+    int v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int p00 = (in0 && cx0) ? r0[3 * sx0 + c] : 0, p01 = (in0 && cx1) ? r0[3 * sx1 + c] : 0;
+      const int p10 = (in1 && cx0) ? r1[3 * sx0 + c] : 0, p11 = (in1 && cx1) ? r1[3 * sx1 + c] : 0;
+      v[c] = resize_mix(p00, p01, p10, p11, a0, a1, b0, b1);
+    }
+    orow[3 * ox] = i2t_normalise(v[0], P.range_min, P.range_max);
+    orow[3 * ox + 1] = i2t_normalise(v[1], P.range_min, P.range_max);
+    orow[3 * ox + 2] = i2t_normalise(v[2], P.range_min, P.range_max);
+  }
+  }  // item loop
+}
+
+// Tile-staged variant for ROI warps whose frames live in mapped pinned host memory: one 32x32 output tile per
+// work item.  The source bounding box of the tile (the rectangle of warp space it samples, pushed through the
+// inverse perspective matrix) is copied into shared memory with aligned 16-byte loads -- each source byte crosses
+// PCIe once per tile instead of once per tap -- and the pixels are then evaluated by the very same i2t_pixel code
+// reading through ImgSrc (anything outside the staged box falls back to a direct load, so staging is purely a
+// traffic optimisation and cannot change a result).
+constexpr int kTile = 32;
+constexpr int kTileSmem = 64 * 1024;
+
+__global__ void __launch_bounds__(256) i2t_tile_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
+                                                       const I2TParams* __restrict__ params, int n, int out_w, int out_h,
+                                                       float* __restrict__ out, long long out_bstride, const int* n_active) {
+  extern __shared__ __align__(16) uint8_t s_tile[];
+  if (n_active) n = min(n, *n_active);
+  __shared__ I2TParams P;
+  __shared__ int s_box[6];   // x0, y0, x1, y1 (pixels, inclusive; x1 < x0: nothing staged), start byte, pitch
+  const int tiles_x = (out_w + kTile - 1) / kTile, tiles_y = (out_h + kTile - 1) / kTile;
+  const long long items = (long long)n * tiles_x * tiles_y;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int slot = (int)(item / (tiles_x * tiles_y));
+    const int t = (int)(item - (long long)slot * tiles_x * tiles_y);
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    __syncthreads();
+    {
+      const int* src = reinterpret_cast<const int*>(&params[slot]);
+      int* dst = reinterpret_cast<int*>(&P);
+      for (int i = threadIdx.x; i < (int)(sizeof(I2TParams) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint8_t* img = frames + (long long)P.frame * frame_stride;
+    const int ox0 = tx * kTile, oy0 = ty * kTile, ox1 = min(ox0 + kTile, out_w) - 1, oy1 = min(oy0 + kTile, out_h) - 1;
+    if (threadIdx.x == 0) {
+      s_box[0] = 0; s_box[1] = 0; s_box[2] = -1; s_box[3] = -1; s_box[4] = 0; s_box[5] = 0;
+      bool ok = P.valid != 0;
+      // output tile -> rectangle of warp space it samples
+      int wx0 = P.flip ? P.out_w - 1 - ox1 : ox0, wx1 = P.flip ? P.out_w - 1 - ox0 : ox1, wy0 = oy0, wy1 = oy1;
+      if (ok && P.has_r2 && !(P.r1_w == P.out_w && P.r1_h == P.out_h)) {
+        int a, b2, c0, c1;
+        resize_coeff(wx0, P.out_w, P.r1_w, true, &a, &b2, &c0, &c1); const int nx0 = a;
+        resize_coeff(wx1, P.out_w, P.r1_w, true, &a, &b2, &c0, &c1); const int nx1 = b2;
+        resize_coeff(wy0, P.out_h, P.r1_h, false, &a, &b2, &c0, &c1); const int ny0 = a;
+        resize_coeff(wy1, P.out_h, P.r1_h, false, &a, &b2, &c0, &c1); const int ny1 = b2;
+        wx0 = nx0; wx1 = nx1; wy0 = ny0; wy1 = ny1;
+      }
+      if (ok && P.has_r2 && P.has_r1) {
+        const int bw = P.warp_w + 2 * P.pad_h, bh = P.warp_h + 2 * P.pad_v;
+        if (bw == P.r1_w && bh == P.r1_h) {
+          wx0 = max(wx0 - P.pad_h, 0); wx1 = min(wx1 - P.pad_h, P.warp_w - 1);
+          wy0 = max(wy0 - P.pad_v, 0); wy1 = min(wy1 - P.pad_v, P.warp_h - 1);
+          if (wx1 < wx0 || wy1 < wy0) ok = false;   // the tile lies entirely in the letterbox border
+        } else {
+          ok = false;                               // a real first resize: not staged (direct loads)
+        }
+      }
+      if (ok) {
+        double lox = 1e30, loy = 1e30, hix = -1e30, hiy = -1e30;
+        for (int c = 0; c < 4; ++c) {
+          const double x = (c & 1) ? wx1 : wx0, y = (c & 2) ? wy1 : wy0;
+          const double w = P.Mi[6] * x + P.Mi[7] * y + P.Mi[8];
+          if (!(w > 1e-6)) { ok = false; break; }
+          const double sx = (P.Mi[0] * x + P.Mi[1] * y + P.Mi[2]) / w, sy = (P.Mi[3] * x + P.Mi[4] * y + P.Mi[5]) / w;
+          lox = dmin(lox, sx); hix = dmax(hix, sx); loy = dmin(loy, sy); hiy = dmax(hiy, sy);
+        }
+        if (ok && hix - lox < 4096.0 && hiy - loy < 4096.0 && lox > -1e6 && loy > -1e6) {
+          const int x0 = max((int)floor(lox) - 1, 0), y0 = max((int)floor(loy) - 1, 0);
+          const int x1 = min((int)ceil(hix) + 2, P.src_w - 1), y1 = min((int)ceil(hiy) + 2, P.src_h - 1);
+          if (x1 >= x0 && y1 >= y0) {
+            const int sb = (3 * x0) & ~15;
+            int eb = (3 * (x1 + 1) + 15) & ~15;
+            if (eb > (int)row_stride) eb = (int)row_stride;
+            const int pitch = eb - sb;
+            if ((long long)pitch * (y1 - y0 + 1) <= kTileSmem && pitch > 0) {
+              s_box[0] = x0; s_box[1] = y0; s_box[2] = x1; s_box[3] = y1; s_box[4] = sb; s_box[5] = pitch;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    ImgSrc src = img_src(img, row_stride);
+    if (s_box[2] >= s_box[0]) {
+      const int y0 = s_box[1], rows = s_box[3] - s_box[1] + 1, sb = s_box[4], pitch = s_box[5];
+      const bool vec = ((reinterpret_cast<uintptr_t>(img) | (uintptr_t)row_stride) & 15) == 0 && (pitch & 15) == 0;
+      if (vec) {
+        const int per_row = pitch >> 4;
+        for (int i = threadIdx.x; i < per_row * rows; i += blockDim.x) {
+          const int r = i / per_row, c = i - r * per_row;
+          reinterpret_cast<uint4*>(s_tile + (long long)r * pitch)[c] = __ldg(reinterpret_cast<const uint4*>(img + (long long)(y0 + r) * row_stride + sb) + c);
+        }
+      } else {
+        for (int i = threadIdx.x; i < pitch * rows; i += blockDim.x) {
+          const int r = i / pitch, c = i - r * pitch;
+          s_tile[(long long)r * pitch + c] = img[(long long)(y0 + r) * row_stride + sb + c];
+        }
+      }
+      src.tile = s_tile; src.tx0 = s_box[0]; src.ty0 = y0; src.tx1 = s_box[2]; src.ty1 = s_box[3]; src.tpitch = pitch; src.tsb = sb;
+      // pixels of the box whose bytes were clipped by the row end are served by the fallback path
+      src.tx1 = min(src.tx1, (sb + pitch) / 3 - 1);
+    }
+    __syncthreads();
+    const int tw = ox1 - ox0 + 1, th = oy1 - oy0 + 1;
+    for (int i = threadIdx.x; i < tw * th; i += blockDim.x) {
+      const int py = i / tw, px = i - py * tw;
+      const int ox = ox0 + px, oy = oy0 + py;
+      Px3 p;
+      if (P.valid) p = i2t_pixel(P, src, ox, oy);
+      else { p.r = p.g = p.b = 0; }
+      float* o = out + (long long)slot * out_bstride + ((long long)oy * out_w + ox) * 3;
+      o[0] = i2t_normalise(p.r, P.range_min, P.range_max);
+      o[1] = i2t_normalise(p.g, P.range_min, P.range_max);
+      o[2] = i2t_normalise(p.b, P.range_min, P.range_max);
+    }
   }
 }
 
@@ -382,10 +595,33 @@ cudaError_t launch_i2t_setup(const fdl_rect* rois, const int* slot_frame, const 
 
 cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long row_stride, const I2TParams* params, int n,
                        int out_w, int out_h, float* out, long long out_bstride, uint8_t* out_u8, const int* n_active,
-                       cudaStream_t s) {
+                       cudaStream_t s, int rows_mode, int src_w, int max_ctas) {
   if (n <= 0) return cudaSuccess;
-  dim3 grid((out_w * out_h + 255) / 256, n);
-  i2t_kernel<<<grid, 256, 0, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, out_u8, n_active);
+  // max_ctas > 0 (frames are mapped pinned host memory): a few persistent CTAs keep PCIe busy without occupying the SMs
+  // another lane's network kernels need
+  if (rows_mode && !out_u8) {
+    const size_t smem = 2 * (size_t)((src_w * 3 + 15) & ~15);
+    if (smem <= 48 * 1024) {
+      long long items = (long long)n * out_h;
+      if (max_ctas > 0 && items > max_ctas) items = max_ctas;
+      i2t_rows_kernel<<<(unsigned)items, 256, smem, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, n_active);
+      return FDL_LAUNCHED();
+    }
+  }
+  if (max_ctas > 0 && !out_u8) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(i2t_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
+      attr_done = true;
+    }
+    long long items = (long long)n * ((out_w + kTile - 1) / kTile) * ((out_h + kTile - 1) / kTile);
+    if (items > max_ctas) items = max_ctas;
+    i2t_tile_kernel<<<(unsigned)items, 256, kTileSmem, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, n_active);
+    return FDL_LAUNCHED();
+  }
+  long long grid = (long long)n * ((out_w * out_h + 255) / 256);
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  i2t_kernel<<<(unsigned)grid, 256, 0, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, out_u8, n_active);
   return FDL_LAUNCHED();
 }
 

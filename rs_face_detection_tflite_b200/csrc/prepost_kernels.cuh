@@ -29,7 +29,8 @@ cudaError_t launch_i2t_setup(const fdl_rect* rois, const int* slot_frame, const 
 // (batch stride out_bstride floats); out_u8 optional [n, out_h, out_w, 3].
 cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long row_stride, const I2TParams* params, int n,
                        int out_w, int out_h, float* out, long long out_bstride, uint8_t* out_u8, const int* n_active,
-                       cudaStream_t s);
+                       cudaStream_t s, int rows_mode = 0, int src_w = 0, int max_ctas = 0);
+// rows_mode = 1 (detector letterbox): one CTA per output row, source rows staged in shared memory (see i2t_rows_kernel).
 
 struct SsdPostArgs {
   const float* reg = nullptr; long long reg_bstride = 0;   // [B,N,16]

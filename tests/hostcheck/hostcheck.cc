@@ -27,7 +27,7 @@ int hc_image_to_tensor(const uint8_t* img, int w, int h, const fdl_rect* roi, in
   if (!P.valid) return -1;
   for (int y = 0; y < out_h; ++y)
     for (int x = 0; x < out_w; ++x) {
-      Px3 p = i2t_pixel(P, img, (long long)w * 3, x, y);
+      Px3 p = i2t_pixel(P, img_src(img, (long long)w * 3), x, y);
       size_t o = ((size_t)y * out_w + x) * 3;
       out[o] = i2t_normalise(p.r, rmin, rmax); out[o + 1] = i2t_normalise(p.g, rmin, rmax); out[o + 2] = i2t_normalise(p.b, rmin, rmax);
       out_u8[o] = (uint8_t)p.r; out_u8[o + 1] = (uint8_t)p.g; out_u8[o + 2] = (uint8_t)p.b;

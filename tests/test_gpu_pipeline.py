@@ -119,6 +119,23 @@ def test_batched_pipeline_matches_oracle(fdl, gpu, oracle_pipeline):
                 np.testing.assert_array_equal(fa.left_iris, fb.left_iris)
     assert pipe.last_device_ms > 0
     pipe.close()
+    # zero-copy mode: pinned host frames read in place by the row-staged / tile-staged kernels -> identical results
+    zc = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (1920, 1080), max_batch=8, max_faces=2, model_dir=MODELS, device=gpu, zero_copy_host=True)
+    pinned = torch.from_numpy(frames).pin_memory()
+    tickets = [zc.submit(pinned[:2]), zc.submit(pinned[2:4]), zc.submit(pinned[4:])]
+    zres = sum((zc.collect(t) for t in tickets), [])
+    assert len(zres) == n
+    for a, b in zip(res, zres):
+        assert [d.anchor for d in a.detections] == [d.anchor for d in b.detections]
+        for da, db in zip(a.detections, b.detections):
+            np.testing.assert_array_equal(da.data, db.data)
+        for fa, fb in zip(a.faces, b.faces):
+            assert (fa.landmarks is None) == (fb.landmarks is None)
+            if fa.landmarks is not None:
+                np.testing.assert_array_equal(fa.landmarks, fb.landmarks)
+                np.testing.assert_array_equal(fa.left_contour, fb.left_contour)
+                np.testing.assert_array_equal(fa.right_iris, fb.right_iris)
+    zc.close()
 
 
 def test_detection_only_pipeline_and_errors(fdl, gpu):
