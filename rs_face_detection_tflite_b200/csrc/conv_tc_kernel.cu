@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
   const int Nt = a.Nt;
   const Layout L = layout(Nt, a.wsplit, a.mode == 1 ? a.in.C : 0);
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem);           // [2]: chunk buffer free / all done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 32);
+  uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + 16);        // [2]: weight chunk landed (bulk copy)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 48);
   float* s_bias = reinterpret_cast<float*>(smem + L.bias);
   float* s_alpha = reinterpret_cast<float*>(smem + L.alpha);
   float* s_dw = reinterpret_cast<float*>(smem + L.dw);
@@ -77,6 +78,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
   if (tid == 0) {
     ptx::mbar_init(&mma_bar[0], 1);
     ptx::mbar_init(&mma_bar[1], 1);
+    ptx::mbar_init(&w_bar[0], 1);
+    ptx::mbar_init(&w_bar[1], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
@@ -118,48 +121,74 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
   const int w4_per_chunk = QC * Nt;                 // float4s of one (hi or lo) chunk
   const size_t w4_lo_off = (size_t)(a.Kp / 4) * Nt; // offset of the lo copy inside the N tile
 
+  // im2col gather of one chunk into registers: all four 16-byte loads are issued back to back (branch-free), so
+  // their latencies overlap; the loop below prefetches chunk c+1 while chunk c is converted, stored and multiplied.
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto gather_conv = [&](int c, float4 (&v)[4]) {
+    const int k = c * KC + 4 * j;
+    const int kwc = a.kw * Cin;
+    const int ky = k / kwc, r = k - ky * kwc;
+    const int kx = r / Cin, ci = r - kx * Cin;
+    const bool kok = k < a.K;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int iy = py[i] * a.stride - a.pad_t + ky, ix = px[i] * a.stride - a.pad_l + kx;
+      const bool ok = kok && pv[i] && iy >= 0 && iy < IH && ix >= 0 && ix < IW;
+      const float4* ptr = reinterpret_cast<const float4*>(a.in.p + (long long)pb[i] * a.in.bstride + ((long long)iy * IW + ix) * Cin + ci);
+      v[i] = ok ? __ldg(ptr) : zero4;
+    }
+  };
+  float4 pre[4];
+  if (a.mode == 0) gather_conv(0, pre);
+
   for (int c = 0; c < nchunks; ++c) {
     const int buf = c & 1;
     // the MMAs that read this buffer two chunks ago must have completed
     if (c >= 2) ptx::mbar_wait(&mma_bar[buf], (uint32_t)(((c >> 1) - 1) & 1));
     uint8_t* s_a = smem + L.a0 + buf * L.a_stage;
     float4* s_w = reinterpret_cast<float4*>(smem + L.w0 + buf * L.w_stage);
-    // ---- weights of this chunk (already in UMMA order) ----
-    for (int i = tid; i < w4_per_chunk; i += kThreads) {
-      s_w[i] = __ldg(wsrc + (size_t)c * w4_per_chunk + i);
-      if (a.wsplit == 2) s_w[w4_per_chunk + i] = __ldg(wsrc + w4_lo_off + (size_t)c * w4_per_chunk + i);
+    // ---- weights of this chunk: already in UMMA order in global memory -> one or two bulk async copies ----
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)w4_per_chunk * 16u;
+      ptx::mbar_arrive_expect_tx(&w_bar[buf], bytes * (uint32_t)a.wsplit);
+      ptx::bulk_load_1d(s_w, wsrc + (size_t)c * w4_per_chunk, bytes, &w_bar[buf]);
+      if (a.wsplit == 2) ptx::bulk_load_1d(s_w + w4_per_chunk, wsrc + w4_lo_off + (size_t)c * w4_per_chunk, bytes, &w_bar[buf]);
     }
-    // ---- gather the A chunk ----
+    // ---- the A chunk ----
     const int k = c * KC + 4 * j;                   // first K index of this thread's quad
+    float4 cur[4];
+    if (a.mode == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cur[i] = pre[i];
+      if (c + 1 < nchunks) gather_conv(c + 1, pre);
+    } else {
+      // depthwise 3x3 (+bias) of channel quad k..k+3 at each of the four pixels; loads predicated, not branched
+      const bool kok = k < a.K;
+      const float4 bdw = kok ? *reinterpret_cast<const float4*>(s_dw + 9 * Cin + k) : zero4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float* img = a.in.p + (long long)pb[i] * a.in.bstride + k;
+        const int iy0 = py[i] * a.stride - a.pad_t, ix0 = px[i] * a.stride - a.pad_l;
+        float4 t[9];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int iy = iy0 + ky, ix = ix0 + kx;
+            const bool ok = kok && pv[i] && iy >= 0 && iy < IH && ix >= 0 && ix < IW;
+            t[ky * 3 + kx] = ok ? __ldg(reinterpret_cast<const float4*>(img + ((long long)iy * IW + ix) * Cin)) : zero4;
+          }
+        float4 v = (pv[i] && kok) ? bdw : zero4;
+        if (kok) {
+#pragma unroll
+          for (int q = 0; q < 9; ++q) fma4(v, t[q], *reinterpret_cast<const float4*>(s_dw + q * Cin + k));
+        }
+        cur[i] = v;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (pv[i] && k < a.K) {
-        const float* img = a.in.p + (long long)pb[i] * a.in.bstride;
-        if (a.mode == 0) {
-          const int kwc = a.kw * Cin;
-          const int ky = k / kwc, r = k - ky * kwc;
-          const int kx = r / Cin, ci = r - kx * Cin;
-          const int iy = py[i] * a.stride - a.pad_t + ky, ix = px[i] * a.stride - a.pad_l + kx;
-          if (iy >= 0 && iy < IH && ix >= 0 && ix < IW) v = __ldg(reinterpret_cast<const float4*>(img + ((long long)iy * IW + ix) * Cin + ci));
-        } else {
-          // depthwise 3x3 (+bias) of channel quad k..k+3 at this pixel
-          v = *reinterpret_cast<const float4*>(s_dw + 9 * Cin + k);
-          const int iy0 = py[i] * a.stride - a.pad_t, ix0 = px[i] * a.stride - a.pad_l;
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            const int iy = iy0 + ky;
-            if (iy < 0 || iy >= IH) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const int ix = ix0 + kx;
-              if (ix < 0 || ix >= IW) continue;
-              fma4(v, __ldg(reinterpret_cast<const float4*>(img + ((long long)iy * IW + ix) * Cin + k)),
-                   *reinterpret_cast<const float4*>(s_dw + (ky * 3 + kx) * Cin + k));
-            }
-          }
-        }
-      }
+      const float4 v = cur[i];
       float4 hi, lo;
       hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
       lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
@@ -171,6 +200,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
     ptx::tc_fence_before_sync();
     __syncthreads();
     if (tid == 0) {
+      ptx::mbar_wait(&w_bar[buf], (uint32_t)((c >> 1) & 1));
       ptx::tc_fence_after_sync();
       const uint32_t ahi = ptx::smem_u32(s_a), alo = ahi + kABytes, wb = ptx::smem_u32(s_w);
       for (int pass = 0; pass < (a.wsplit == 2 ? 3 : 2); ++pass) {
