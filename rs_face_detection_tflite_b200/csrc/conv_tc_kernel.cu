@@ -138,8 +138,36 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
       v[i] = ok ? __ldg(ptr) : zero4;
     }
   };
+  // same for input channel counts that are not a multiple of 4 (the RGB stems): element-wise gather, 16 scalar loads
+  auto gather_scalar = [&](int c, float4 (&v)[4]) {
+    const int k0 = c * KC + 4 * j;
+    const int kwc = a.kw * Cin;
+    int dy[4], dx[4], dc[4];
+    bool kok[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = k0 + e;
+      const int ky = k / kwc, r = k - ky * kwc;
+      dy[e] = ky; dx[e] = r / Cin; dc[e] = r - dx[e] * Cin;
+      kok[e] = k < a.K;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float* img = a.in.p + (long long)pb[i] * a.in.bstride;
+      const int iy0 = py[i] * a.stride - a.pad_t, ix0 = px[i] * a.stride - a.pad_l;
+      float t[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int iy = iy0 + dy[e], ix = ix0 + dx[e];
+        const bool ok = kok[e] && pv[i] && iy >= 0 && iy < IH && ix >= 0 && ix < IW;
+        t[e] = ok ? __ldg(img + ((long long)iy * IW + ix) * Cin + dc[e]) : 0.f;
+      }
+      v[i] = make_float4(t[0], t[1], t[2], t[3]);
+    }
+  };
   float4 pre[4];
   if (a.mode == 0) gather_conv(0, pre);
+  else if (a.mode == 2) gather_scalar(0, pre);
 
   for (int c = 0; c < nchunks; ++c) {
     const int buf = c & 1;
@@ -157,10 +185,13 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
     // ---- the A chunk ----
     const int k = c * KC + 4 * j;                   // first K index of this thread's quad
     float4 cur[4];
-    if (a.mode == 0) {
+    if (a.mode != 1) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) cur[i] = pre[i];
-      if (c + 1 < nchunks) gather_conv(c + 1, pre);
+      if (c + 1 < nchunks) {
+        if (a.mode == 0) gather_conv(c + 1, pre);
+        else gather_scalar(c + 1, pre);
+      }
     } else {
       // depthwise 3x3 (+bias) of channel quad k..k+3 at each of the four pixels; loads predicated, not branched
       const bool kok = k < a.K;
@@ -291,7 +322,9 @@ cudaError_t conv_tc_init() {
 
 bool conv_tc_supported(const Step& s) {
   if (s.kind != STEP_CONV && s.kind != STEP_BLOCK) return false;
-  if (s.w_tc < 0 || s.in.C % 4 != 0) return false;
+  if (s.w_tc < 0) return false;
+  if (s.in.C % 4 != 0 && s.kind != STEP_CONV) return false;   // odd channel counts: scalar im2col gather (mode 2), CONV only
+  if (s.in.C == 3) return false;   // RGB stems: the FFMA stem kernel (stem_kernel.cu) is faster than a scalar gather (measured)
   if (s.in.offset != 0) return false;
   if (s.kind == STEP_BLOCK && (s.in.C > 256)) return false;
   if (s.skip.tensor >= 0 && s.skip.offset != 0) return false;

@@ -89,7 +89,7 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const 
       TView in = in_view(s), out = view(s.out, B);
       a.in.p = in.p; a.in.bstride = in.bstride; a.in.H = in.H; a.in.W = in.W; a.in.C = in.C;
       a.out.p = out.p; a.out.bstride = out.bstride; a.out.H = out.H; a.out.W = out.W; a.out.C = out.C;
-      a.mode = s.kind == STEP_BLOCK ? 1 : 0;
+      a.mode = s.kind == STEP_BLOCK ? 1 : (s.in.C % 4 == 0 ? 0 : 2);
       a.kh = s.kh; a.kw = s.kw; a.stride = s.stride; a.pad_t = s.pad_t; a.pad_l = s.pad_l;
       a.K = s.K; a.Kp = s.Kp; a.N = s.N; a.Nt = s.Nt; a.n_tiles = s.n_tiles;
       a.w_tc = d_weights_ + s.w_tc; a.bias = d_weights_ + s.b;

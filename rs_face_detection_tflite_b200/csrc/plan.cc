@@ -378,7 +378,7 @@ bool Plan::build(const TfModel& m, std::string* err) {
       s.w = push(wt);
       s.b = push(bp);
       flops_per_item += 2LL * s.K * co * oh * ow;
-      if (ci % 4 == 0) {
+      if (ci % 4 == 0 || g.kind == STEP_CONV) {
         auto hi_of = [](float v) { uint32_t u; std::memcpy(&u, &v, 4); u &= 0xffffe000u; float r; std::memcpy(&r, &u, 4); return r; };
         bool exact = true;
         for (float v : w) if (hi_of(v) != v) { exact = false; break; }
