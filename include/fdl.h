@@ -214,12 +214,18 @@ FDL_API int64_t fdl_net_describe(const fdl_net*, char* buf, int64_t cap);
 /* Number of kernel launches of one forward pass. */
 FDL_API int fdl_net_num_steps(const fdl_net*);
 /* Select the arithmetic of the pointwise (1x1) contractions: 0 = fp32 FFMA (default for parity
- * checks), 1 = tensor-core split-TF32 (fp32-equivalent). */
+ * checks), 1 = tensor-core split-TF32 (fp32-equivalent; the default), 2 = as 1 but
+ * without the warp-specialised BlazeBlock kernel (every block on the serial tensor-core kernel;
+ * bit-identical to 1, kept for A/B timing and as a race check). */
 FDL_API int fdl_net_set_mode(fdl_net*, int mode);
 /* Device-resident benchmark hook: run `iters` forward passes at `batch` on the net's own input
  * buffer (filled once from `in_or_null`, host f32, or left as is) and return the mean time per
  * pass in milliseconds measured with CUDA events on the net's stream. */
 FDL_API int fdl_net_time_forward(fdl_net*, const float* in_or_null, int batch, int iters, float* ms_per_pass);
+/* Per-launch timing inside whole forward passes: CUDA events recorded on the net's stream before
+ * every planned step and after the last; ms_per_step[i] = mean duration of step i over `iters`
+ * passes (cap >= fdl_net_num_steps).  bench.py uses it for the roofline of the dominant kernel. */
+FDL_API int fdl_net_time_steps(fdl_net*, const float* in_or_null, int batch, int iters, float* ms_per_step, int cap);
 
 /* ---------------------------------------------------------------- batched pipeline */
 /* detect -> face ROI -> landmark -> eye ROIs -> iris(L,R) exactly as lib.rs:20-40, for a batch of

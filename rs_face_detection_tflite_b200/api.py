@@ -195,6 +195,17 @@ class _Net:
         check(lib().fdl_net_time_forward(self._h, p, batch, iters, C.byref(ms)))
         return ms.value
 
+    def time_steps(self, batch: int, iters: int, x: np.ndarray | None = None) -> np.ndarray:
+        """Mean duration (ms) of every planned launch inside whole forward passes (CUDA events on the net's stream)."""
+        n = self.num_steps
+        out = (C.c_float * n)()
+        p = None
+        if x is not None:
+            x = np.ascontiguousarray(x, np.float32)
+            p = x.ctypes.data_as(C.POINTER(C.c_float))
+        check(lib().fdl_net_time_steps(self._h, p, batch, iters, out, n))
+        return np.array(out[:], np.float32)
+
 
 class Net(_Net):
     """A stand-alone planned .tflite graph (``device=-1``: plan only, no GPU needed)."""

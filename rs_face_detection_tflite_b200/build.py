@@ -27,6 +27,7 @@ SOURCES = {
     "net.cu": [],
     "net_kernels.cu": [],
     "mma_kernels.cu": [],
+    "block_ws_kernel.cu": [],
     "stem_kernel.cu": [],
     "conv_tc_kernel.cu": [],
     # the glue arithmetic must not contract a*b+c into FMA (the reference's scalar Rust never does)

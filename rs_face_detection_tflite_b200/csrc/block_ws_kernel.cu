@@ -1,0 +1,475 @@
+// block_ws_kernel.cu -- warp-specialised, software-pipelined BlazeBlock kernel for stride-1 blocks (sm_100a).
+//
+//     out = act( PW1x1( DW3x3(in) + b_dw ) + b_pw + skip )
+//
+// Same arithmetic as blaze_block_tc_kernel (mma_kernels.cu): depthwise 3x3 on the CUDA cores, pointwise 1x1 on the
+// tensor cores (tcgen05.mma kind::tf32 with hi/lo operand splitting, accumulator in TMEM).
+// What changes is the schedule.  One persistent CTA per SM runs two kinds of warps that work on DIFFERENT tiles at
+// the same time, connected by mbarrier rings:
+//
+//   warps 4..   depthwise  G groups; group g takes the CTA's tiles g, g+G, ...: waits for the TMA'd 10 x 18 x C halo
+//                          tile, 3x3 depthwise with packed FFMA2 (fma.rn.f32x2), tf32 hi/lo split, A operand written
+//                          in the UMMA K-major core-matrix layout into the group's own A buffer.  The group's first
+//                          thread then issues the tcgen05.mma chain for the tile into one of two TMEM accumulators
+//                          (tcgen05.commit -> "accumulator full" and "A buffer free") and moves on to its next tile.
+//   warps 0-3   epilogue   tcgen05.ld of the accumulator, + residual (prefetched from the resident input tile or from
+//                          global memory), RELU / PRELU, 16-byte stores straight to global memory (NHWC).  When all
+//                          four warps are done with a tile its input stage is refilled at once: thread 0 issues the
+//                          TMA load of the tile NS places ahead.
+//
+// so the depthwise of tiles i+1..i+G overlaps the MMA and the epilogue of tile i, and NS tiles of TMA loads are in
+// flight.  The pointwise bias rides on the tensor cores as one more K step (A rows (1,1,0,..), B rows (b_hi,b_lo,0,..)).
+// Per tile the kernel reads the input tile once and writes the output tile once.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "mma_kernels.cuh"
+#include "plan.h"
+#include "sm100_ptx.cuh"
+
+namespace fdl {
+
+void count_launch();
+bool encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, long long bstride, int box_h, int box_w, int box_c = 0);
+
+namespace {
+
+typedef unsigned long long ull;
+
+constexpr int TH = 8, TW = 16;                 // output tile: 128 pixels == UMMA M
+constexpr int ITH = TH + 2, ITW = TW + 2;      // input halo tile
+constexpr int kPlaneBytes = TH * TW * 16 + 16; // one channel-quad plane of A (+16 B bank skew) == LBO
+constexpr int kEpiThreads = 128;               // 4 epilogue warps: one per TMEM lane quarter
+constexpr int kMaxThreads = 512;
+constexpr int kMaxStages = 6, kMaxGroups = 3;
+constexpr int kMaxSmemWs = 227 * 1024;
+
+struct WsCfg { int G, ipt, ndwg, NS, OB, threads, total, ctas, in_pad; };
+struct WsLayout { int alpha, w, wb, ones, in0, in_stage, a0, a_buf, out0, out_stage, total; };
+
+__host__ __device__ inline int align_up_w(int v, int a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline WsLayout ws_layout(int C, int N, int Np, int wsplit, int NS, int G, int OB, int in_pad) {
+  WsLayout L;
+  int off = 256;                                // barriers + tmem slot
+  L.alpha = off; off += Np * 4;
+  off = align_up_w(off, 128);
+  L.w = off; off += wsplit * (C / 4) * Np * 16;
+  L.wb = off; off += 2 * Np * 16;               // bias as one more K step of B: [2 quads][Np][4] = (b_hi, b_lo, 0, 0), 0
+  off = align_up_w(off, 128);
+  L.ones = off; off += 2 * kPlaneBytes;         // the matching A planes: (1, 1, 0, 0) for every pixel, then zeros
+  off = align_up_w(off, 128);
+  L.in_stage = align_up_w(ITH * ITW * (in_pad ? ((C / 4) | 1) * 4 : C) * 4, 128);   // in_pad: pixel stride = odd number of 16-byte quads
+  L.in0 = off; off += NS * L.in_stage;
+  L.a_buf = align_up_w(2 * (C / 4) * kPlaneBytes, 128);   // hi planes then lo planes
+  L.a0 = off; off += G * L.a_buf;
+  L.out_stage = align_up_w(TH * TW * ((N / 4) | 1) * 16, 128);   // raw accumulator tile, pixel stride = odd number of quads
+  L.out0 = off; off += OB * L.out_stage;
+  L.total = align_up_w(off, 128);
+  return L;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ ull fma2(ull a, ull b, ull c) {
+  ull d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int kMaxT, int kMinB>
+__global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
+                                                                  const BlockTcArgs a, long long* __restrict__ dbg) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = a.C, N = a.N, Np = a.Np, Q = C >> 2;
+  const int NS = a.stages, G = a.groups, ndwg = a.dw_threads;
+  const WsLayout L = ws_layout(C, N, Np, a.wsplit, NS, G, a.out_bufs, a.in_pad);
+  const int T = G > 2 ? G : 2;                  // TMEM accumulators: tile it -> buffer it % T (== its group when G >= 2, so each
+                                                // buffer has ONE issuing thread and its full/empty phases stay in lockstep)
+  uint64_t* in_full = reinterpret_cast<uint64_t*>(smem);             // [kMaxStages]  TMA tile landed
+  uint64_t* a_full = in_full + kMaxStages;                           // [kMaxGroups]  A operand of the group written
+  uint64_t* a_empty = a_full + kMaxGroups;                           // [kMaxGroups]  MMAs done reading the group's A buffer
+  uint64_t* acc_full = a_empty + kMaxGroups;                         // [kMaxGroups]  accumulator complete
+  uint64_t* acc_empty = acc_full + kMaxGroups;                       // [kMaxGroups]  accumulator drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kMaxGroups);
+  float* s_w = reinterpret_cast<float*>(smem + L.w);
+
+  int nb = a.B;
+  if (a.n_active) nb = min(nb, *a.n_active);
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const int ntiles = nb * tiles_per_img;
+  if ((int)blockIdx.x >= ntiles) return;
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  const int CP = a.in_pad ? (((C >> 2) | 1) << 2) : C;   // pixel stride (floats) of the input tile in shared memory
+  const uint32_t in_bytes = (uint32_t)(ITH * ITW * CP * 4);
+  auto issue_load = [&](int it) {               // the CTA's it-th tile -> stage it % NS
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    const int s = it % NS;
+    const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+    const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
+    ptx::mbar_arrive_expect_tx(&in_full[s], in_bytes);
+    ptx::tma_load_4d(smem + L.in0 + s * L.in_stage, &tm_in, &in_full[s], 0, tx * TW - 1, ty * TH - 1, b);
+  };
+
+  // ---- one-time setup ----
+  if (tid == 0) {
+    ptx::prefetch_tmap(&tm_in);
+    ptx::prefetch_tmap(&tm_out);
+    for (int s = 0; s < NS; ++s) ptx::mbar_init(&in_full[s], 1);
+    for (int g = 0; g < G; ++g) { ptx::mbar_init(&a_full[g], (uint32_t)ndwg); ptx::mbar_init(&a_empty[g], 1); }
+    for (int t = 0; t < T; ++t) { ptx::mbar_init(&acc_full[t], 1); ptx::mbar_init(&acc_empty[t], 4); }
+    ptx::fence_mbar_init();
+    for (int it = 0; it < NS && it < my_tiles; ++it) issue_load(it);
+  }
+  if (warp == 0) ptx::tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+  for (int i = tid; i < Np; i += blockDim.x) {
+    const float bv = i < N ? a.bias[i] : 0.f;
+    const float bh = __uint_as_float(__float_as_uint(bv) & 0xffffe000u);
+    reinterpret_cast<float4*>(smem + L.wb)[i] = make_float4(bh, bv - bh, 0.f, 0.f);
+    reinterpret_cast<float4*>(smem + L.wb)[Np + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int i = tid; i < TH * TW; i += blockDim.x) {
+    *reinterpret_cast<float4*>(smem + L.ones + i * 16) = make_float4(1.f, 1.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(smem + L.ones + kPlaneBytes + i * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  {  // pointwise weights: already in UMMA core-matrix order in global memory -> straight copy
+    const int n4 = a.wsplit * Q * Np;
+    const float4* src = reinterpret_cast<const float4*>(a.w_umma);
+    float4* dst = reinterpret_cast<float4*>(s_w);
+    for (int i = tid; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int acc_cols = a.acc_cols;              // columns per accumulator buffer
+
+  if (warp < 4) {
+    // ================= epilogue: TMEM -> (+skip, act) -> staging tile -> TMA store; refills the input ring =================
+    // thread == TMEM lane == pixel.  Both the input tile (TMA load with a box wider than the tensor: the tail of each
+    // pixel is zero-filled) and the output staging tile (TMA store with the same trick: the tail is clipped) have a
+    // pixel stride of an ODD number of 16-byte quads, so the per-pixel 16-byte accesses are bank-conflict free.
+    const int p = tid;                          // TMEM lane (warp w may access lanes 32w..32w+31)
+    const int py = p / TW, px = p - py * TW;
+    const int NPf = ((N >> 2) | 1) << 2;        // staging pixel stride (floats)
+    int tile = blockIdx.x;
+    int pb = 0, pty = 0, ptx_ = 0;              // coordinates of the previous tile (its TMA store is issued one tile late)
+    long long t_wacc = 0, t_bar1 = 0, t_chunks = 0, t_tail = 0, t0 = clock64();
+    for (int it = 0; it < my_tiles; ++it, tile += gridDim.x) {
+      const int s = it % NS, t = it % T, ob = it & 1;
+      const int b = tile / tiles_per_img, rr = tile - b * tiles_per_img;
+      const int ty = rr / a.tiles_x, tx = rr - ty * a.tiles_x;
+      const int oy = ty * TH + py, ox = tx * TW + px;
+      const bool inside = oy < a.H && ox < a.W;
+      const float* skip_smem = reinterpret_cast<const float*>(smem + L.in0 + s * L.in_stage) + ((py + 1) * ITW + (px + 1)) * CP;
+      const float* skip_g = (a.skip_mode == 2 && inside) ? a.skip + (long long)b * a.skip_bstride + ((long long)oy * a.W + ox) * a.skip_c : nullptr;
+      float* s_o = reinterpret_cast<float*>(smem + L.out0 + ob * L.out_stage) + p * NPf;
+      // Residual of 32 channels at a time.  The first batch is requested BEFORE waiting for the accumulator: the
+      // shared-memory pipe is kept saturated by the depthwise warps, so a load issued here takes hundreds of cycles.
+      float4 res[8], resn[8];
+      auto load_res = [&](int c0, float4 (&d)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int n = c0 + 4 * j;
+          d[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n < a.skip_c) {
+            if (a.skip_mode == 1) d[j] = ld4(skip_smem + n);
+            else if (skip_g) d[j] = __ldg(reinterpret_cast<const float4*>(skip_g + n));
+          }
+        }
+      };
+      if (a.skip_mode == 1) ptx::mbar_wait(&in_full[s], (uint32_t)((it / NS) & 1));
+      load_res(0, res);
+      { const long long c0 = clock64(); ptx::mbar_wait(&acc_full[t], (uint32_t)((it / T) & 1)); t_wacc += clock64() - c0; }
+      ptx::tc_fence_after_sync();
+      // ---- deferred TMA store of the PREVIOUS tile: its staging writes have had a whole tile to drain ----
+      {
+        const long long c0 = clock64();
+        ptx::fence_proxy_async_smem();
+        if (tid == 0) ptx::tma_store_wait_read0();            // the store of tile it-2 has finished reading buffer `ob`
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0 && it > 0) {
+          ptx::tma_store_4d(&tm_out, smem + L.out0 + (ob ^ 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
+          ptx::tma_store_commit();
+          // every epilogue warp is past its residual reads of the previous tile's stage: refill it
+          if (it - 1 + NS < my_tiles) issue_load(it - 1 + NS);
+        }
+        t_bar1 += clock64() - c0;
+      }
+      pb = b; pty = ty; ptx_ = tx;
+      const long long c_chunks = clock64();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * acc_cols);
+      for (int c0 = 0; c0 < Np; c0 += 32) {
+        if (c0 + 32 < Np) load_res(c0 + 32, resn);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int ch = c0 + 16 * h;
+          if (ch >= Np) break;
+          uint32_t r[16];
+          ptx::tmem_ld16_issue(taddr + (uint32_t)ch, r);
+          ptx::tmem_ld_wait16(r);
+          if (ch + 16 >= Np) {                    // accumulator drained: hand it back to the issuing thread
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[t]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = ch + 4 * j;
+            if (n >= N) break;
+            const float4 rs = res[4 * h + j];
+            float4 o = make_float4(__uint_as_float(r[4 * j]) + rs.x, __uint_as_float(r[4 * j + 1]) + rs.y, __uint_as_float(r[4 * j + 2]) + rs.z,
+                                   __uint_as_float(r[4 * j + 3]) + rs.w);
+            if (a.act == ACT_RELU) {
+              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            } else if (a.act == ACT_PRELU) {      // slopes come from the kernel parameters (constant bank), not shared memory
+              o.x = o.x >= 0.f ? o.x : o.x * a.alpha_c[n]; o.y = o.y >= 0.f ? o.y : o.y * a.alpha_c[n + 1];
+              o.z = o.z >= 0.f ? o.z : o.z * a.alpha_c[n + 2]; o.w = o.w >= 0.f ? o.w : o.w * a.alpha_c[n + 3];
+            }
+            *reinterpret_cast<float4*>(s_o + n) = o;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) res[j] = resn[j];
+      }
+      t_chunks += clock64() - c_chunks;
+    }
+    // the last tile's store
+    ptx::fence_proxy_async_smem();
+    if (tid == 0) ptx::tma_store_wait_read0();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (tid == 0) {
+      ptx::tma_store_4d(&tm_out, smem + L.out0 + ((my_tiles - 1) & 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
+      ptx::tma_store_commit();
+      ptx::tma_store_wait_all0();
+    }
+    if (dbg && tid == 0) { dbg[blockIdx.x * 32 + 5] = clock64() - t0; dbg[blockIdx.x * 32 + 6] = t_wacc; dbg[blockIdx.x * 32 + 31] = my_tiles;
+      dbg[blockIdx.x * 32 + 16] = t_bar1; dbg[blockIdx.x * 32 + 17] = t_chunks; dbg[blockIdx.x * 32 + 18] = t_tail; }
+  } else {
+    // ================= depthwise 3x3 -> A operand (hi / lo planes) -> MMA issue =================
+    const int dtid = tid - kEpiThreads;
+    const int g = dtid / ndwg, gt = dtid - g * ndwg;
+    const int q = gt % Q;                       // ndwg % Q == 0: the channel quad is fixed per thread
+    ull wd[9][2], bd[2];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const ulonglong2 w = __ldg(reinterpret_cast<const ulonglong2*>(a.w_dw + k * C) + q);
+      wd[k][0] = w.x; wd[k][1] = w.y;
+    }
+    {
+      const ulonglong2 w = __ldg(reinterpret_cast<const ulonglong2*>(a.b_dw) + q);
+      bd[0] = w.x; bd[1] = w.y;
+    }
+    const ull kMaskHi = 0xffffe000ffffe000ull;
+    const float2 neg1f = make_float2(-1.f, -1.f);
+    const ull kNeg1 = *reinterpret_cast<const ull*>(&neg1f);
+    uint8_t* s_ahi = smem + L.a0 + g * L.a_buf;
+    uint8_t* s_alo = s_ahi + Q * kPlaneBytes;
+    const int nitems = Q * 2 * TW;
+    // MMA issue state (used by the group's first thread only)
+    const uint32_t idesc = ptx::umma_idesc_tf32(128, Np);
+    const uint32_t w_addr = ptx::smem_u32(s_w), wb_addr = ptx::smem_u32(smem + L.wb), ones_addr = ptx::smem_u32(smem + L.ones);
+    const uint32_t w_lbo = (uint32_t)Np * 16u;
+    const uint32_t ahi_addr = ptx::smem_u32(s_ahi), alo_addr = ahi_addr + (uint32_t)(Q * kPlaneBytes);
+    long long t_win = 0, t_wae = 0, t_mma = 0, t_comp = 0, t_store = 0, t_fence = 0, t0 = clock64();
+    for (int it = g; it < my_tiles; it += G) {
+      const int s = it % NS, kg = it / G, t = it % T;
+      { const long long c0 = clock64(); ptx::mbar_wait(&in_full[s], (uint32_t)((it / NS) & 1)); t_win += clock64() - c0; }
+      const float* s_in = reinterpret_cast<const float*>(smem + L.in0 + s * L.in_stage);
+      long long c_a = clock64();
+      for (int item = gt, ii = 0; item < nitems; item += ndwg, ++ii) {
+        const int xr = item / Q;                // item % Q == q
+        const int x = xr % TW, half = xr / TW;
+        ull acc[4][2];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) { acc[o][0] = bd[0]; acc[o][1] = bd[1]; }
+        const float* base = s_in + ((half * 4) * ITW + x) * CP + 4 * q;
+        ulonglong2 v[3][3];                     // ring of three input rows (x, x+1, x+2): loads run two rows ahead
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float* rp = base + r * ITW * CP;
+          v[r][0] = *reinterpret_cast<const ulonglong2*>(rp);
+          v[r][1] = *reinterpret_cast<const ulonglong2*>(rp + CP);
+          v[r][2] = *reinterpret_cast<const ulonglong2*>(rp + 2 * CP);
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {           // input rows feeding 4 consecutive output rows
+          if (r + 2 < 6) {
+            const float* rp = base + (r + 2) * ITW * CP;
+            v[(r + 2) % 3][0] = *reinterpret_cast<const ulonglong2*>(rp);
+            v[(r + 2) % 3][1] = *reinterpret_cast<const ulonglong2*>(rp + CP);
+            v[(r + 2) % 3][2] = *reinterpret_cast<const ulonglong2*>(rp + 2 * CP);
+          }
+          const ulonglong2 v0 = v[r % 3][0], v1 = v[r % 3][1], v2 = v[r % 3][2];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const int ky = r - o;
+            if (ky >= 0 && ky < 3) {
+              acc[o][0] = fma2(v0.x, wd[ky * 3 + 0][0], acc[o][0]); acc[o][1] = fma2(v0.y, wd[ky * 3 + 0][1], acc[o][1]);
+              acc[o][0] = fma2(v1.x, wd[ky * 3 + 1][0], acc[o][0]); acc[o][1] = fma2(v1.y, wd[ky * 3 + 1][1], acc[o][1]);
+              acc[o][0] = fma2(v2.x, wd[ky * 3 + 2][0], acc[o][0]); acc[o][1] = fma2(v2.y, wd[ky * 3 + 2][1], acc[o][1]);
+            }
+          }
+        }
+        // the MMAs of this group's previous tile must have finished reading the A buffer
+        { const long long c0 = clock64(); t_comp += c0 - c_a; if (ii == 0 && kg > 0) { ptx::mbar_wait(&a_empty[g], (uint32_t)((kg - 1) & 1)); } c_a = clock64(); t_wae += c_a - c0; }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int p = (half * 4 + o) * TW + x;
+          ulonglong2 hi, lo;
+          hi.x = acc[o][0] & kMaskHi; hi.y = acc[o][1] & kMaskHi;
+          lo.x = fma2(hi.x, kNeg1, acc[o][0]); lo.y = fma2(hi.y, kNeg1, acc[o][1]);
+          *reinterpret_cast<ulonglong2*>(s_ahi + q * kPlaneBytes + p * 16) = hi;
+          *reinterpret_cast<ulonglong2*>(s_alo + q * kPlaneBytes + p * 16) = lo;
+        }
+        { const long long c0 = clock64(); t_store += c0 - c_a; c_a = c0; }
+      }
+      ptx::fence_proxy_async_smem();            // generic-proxy writes of A -> visible to the tensor core (async proxy)
+      mbar_arrive(&a_full[g]);
+      t_fence += clock64() - c_a;
+      if (gt == 0) {
+        // ---- this tile's MMA chain, issued by one thread ----
+        const long long c0 = clock64();
+        ptx::mbar_wait(&a_full[g], (uint32_t)(kg & 1));
+        if (it >= T) ptx::mbar_wait(&acc_empty[t], (uint32_t)(((it / T) - 1) & 1));
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(t * acc_cols);
+        // bias K step first (overwrites the accumulator), then the hi / lo passes accumulate
+        ptx::mma_tf32(d_tmem, ptx::umma_desc_kmajor(ones_addr, kPlaneBytes, 128), ptx::umma_desc_kmajor(wb_addr, w_lbo, 128), idesc, 0u);
+        const int ksteps = C >> 3;
+        const int npass = a.wsplit == 2 ? 3 : 2;
+        for (int pass = 0; pass < npass; ++pass) {
+          // pass 0: A_lo * W_hi, pass 1: A_hi * W_hi, pass 2: A_hi * W_lo
+          const uint32_t a_base = pass == 0 ? alo_addr : ahi_addr;
+          const uint32_t b_base = pass == 2 ? w_addr + (uint32_t)(Q * Np * 16) : w_addr;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t ad = ptx::umma_desc_kmajor(a_base + (uint32_t)(ks * 2 * kPlaneBytes), kPlaneBytes, 128);
+            const uint64_t bdsc = ptx::umma_desc_kmajor(b_base + (uint32_t)ks * 2u * w_lbo, w_lbo, 128);
+            ptx::mma_tf32(d_tmem, ad, bdsc, idesc, 1u);
+          }
+        }
+        ptx::mma_commit(&acc_full[t]);
+        ptx::mma_commit(&a_empty[g]);
+        t_mma += clock64() - c0;
+      }
+    }
+    if (dbg && gt == 0) {
+      dbg[blockIdx.x * 32 + 7 + 3 * g] = clock64() - t0; dbg[blockIdx.x * 32 + 8 + 3 * g] = t_win; dbg[blockIdx.x * 32 + 9 + 3 * g] = t_wae;
+      dbg[blockIdx.x * 32 + g] = t_mma;
+      if (g == 0) { dbg[blockIdx.x * 32 + 19] = t_comp; dbg[blockIdx.x * 32 + 20] = t_store; dbg[blockIdx.x * 32 + 21] = t_fence; }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+}
+
+// Depthwise thread organisation per channel-quad count: G groups of ndwg threads, ipt items per thread and tile, and
+// how many CTAs share an SM.  Small channel counts (little work per tile, latency-dominated) run TWO smaller CTAs per SM
+// so that two epilogues and two depthwise groups are in flight; larger ones run one CTA with up to 12 depthwise warps.
+bool pick_cfg(int C, int N, int Np, int wsplit, WsCfg* cfg) {
+  const int Q = C / 4;
+  int G = 1, ipt = 1, ctas = 1;
+  switch (Q) {
+    case 4: G = 1; ipt = 1; ctas = 2; break;
+    case 6: G = 1; ipt = 1; ctas = 2; break;
+    case 8: G = 3; ipt = 2; break;
+    default:
+      ipt = 1;
+      while ((32 * Q) / ipt > kMaxThreads - kEpiThreads || (32 * Q) % ipt != 0 || ((32 * Q) / ipt) % 32 != 0 || ((32 * Q) / ipt) % Q != 0) {
+        if (++ipt > 8) return false;
+      }
+      break;
+  }
+  const int in_pad = (Q % 8 == 0) ? 1 : 0;     // padding the pixel stride keeps the depthwise loads conflict-free only when Q % 8 == 0
+  const int budget = ctas == 2 ? (233472 / 2 - 1024) : kMaxSmemWs;
+  for (; G >= 1; --G) {
+    const int ndwg = 32 * Q / ipt;
+    if (kEpiThreads + G * ndwg > (ctas == 2 ? 320 : kMaxThreads)) continue;
+    for (int NS = (G + 3 < kMaxStages ? G + 3 : kMaxStages); NS >= G + 2; --NS) {   // the refill of a stage trails its tile by one epilogue
+      WsLayout L = ws_layout(C, N, Np, wsplit, NS, G, 2, in_pad);
+      if (L.total <= budget) {
+        cfg->G = G; cfg->ipt = ipt; cfg->ndwg = ndwg; cfg->NS = NS; cfg->OB = 2; cfg->threads = kEpiThreads + G * ndwg; cfg->total = L.total;
+        cfg->ctas = ctas; cfg->in_pad = in_pad;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+}  // namespace
+
+cudaError_t block_ws_init() {
+  cudaError_t e = cudaFuncSetAttribute(block_ws_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(block_ws_kernel<320, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
+}
+
+bool block_ws_supported(const Step& s) {
+  if (s.kind != STEP_BLOCK || s.w_umma < 0 || s.stride != 1) return false;
+  const int C = s.in.C, N = s.out.C;
+  if (C % 8 != 0 || N % 4 != 0 || C < 16 || C > 64) return false;
+  if (s.Np > 128 || s.out.H < TH || s.out.W < TW) return false;
+  if (s.pad_t != 1 || s.pad_l != 1 || s.in.H != s.out.H || s.in.W != s.out.W) return false;
+  if (s.in.offset != 0 || s.out.offset != 0 || s.in.batch_stride != (int64_t)s.in.H * s.in.W * C ||
+      s.out.batch_stride != (int64_t)s.out.H * s.out.W * N)
+    return false;
+  if (s.skip.tensor >= 0 && (s.skip_pool || s.skip_c % 4 != 0 || s.skip.offset != 0)) return false;
+  WsCfg cfg;
+  return pick_cfg(C, N, s.Np, s.wsplit, &cfg);
+}
+
+cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
+  BlockTcArgs a = l.args;
+  WsCfg cfg;
+  if (!pick_cfg(a.C, a.N, a.Np, a.wsplit, &cfg)) return cudaErrorInvalidConfiguration;
+  a.stages = cfg.NS; a.groups = cfg.G; a.dw_threads = cfg.ndwg; a.out_bufs = cfg.OB; a.in_pad = cfg.in_pad;
+  a.pad = 1;
+  for (int i = 0; i < 128; ++i) a.alpha_c[i] = (l.alpha_host && i < a.N) ? l.alpha_host[i] : 0.f;
+  CUtensorMap tm_in, tm_out;
+  if (!encode_nhwc(&tm_in, l.in, a.B, a.H, a.W, a.C, (long long)a.H * a.W * a.C, ITH, ITW, cfg.in_pad ? ((a.C / 4) | 1) * 4 : a.C)) return cudaErrorInvalidValue;
+  if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW, ((a.N / 4) | 1) * 4)) return cudaErrorInvalidValue;
+  a.tiles_x = (a.W + TW - 1) / TW;
+  a.tiles_y = (a.H + TH - 1) / TH;
+  a.acc_cols = a.Np <= 32 ? 32 : (a.Np <= 64 ? 64 : 128);
+  {
+    const int need = (cfg.G > 2 ? cfg.G : 2) * a.acc_cols;
+    a.tmem_cols = 32;
+    while (a.tmem_cols < need) a.tmem_cols *= 2;
+  }
+  const int ntiles = a.B * a.tiles_x * a.tiles_y;
+  int grid = 148 * cfg.ctas;
+  if (grid > ntiles) grid = ntiles;
+  static const bool debug = getenv("FDL_WS_DEBUG") != nullptr;
+  long long* dbg = nullptr;
+  if (debug) { cudaMalloc(&dbg, 296 * 32 * sizeof(long long)); cudaMemset(dbg, 0, 296 * 32 * sizeof(long long)); }
+  if (cfg.ctas == 2) block_ws_kernel<320, 2><<<grid, cfg.threads, cfg.total, stream>>>(tm_in, tm_out, a, dbg);
+  else block_ws_kernel<512, 1><<<grid, cfg.threads, cfg.total, stream>>>(tm_in, tm_out, a, dbg);
+  count_launch();
+  if (debug) {   // per-role cycle accounting (diagnostics only: synchronises the stream)
+    static long long h[296 * 32];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(dbg);
+    double s[32] = {0};
+    for (int b = 0; b < grid; ++b) for (int k = 0; k < 32; ++k) s[k] += (double)h[b * 32 + k] / grid;
+    const double nt = s[31] > 0 ? s[31] : 1;
+    fprintf(stderr, "[ws C=%d N=%d %dx%d G=%d NS=%d ctas=%d thr=%d smem=%d] cycles per CTA tile: epi %.0f (wait acc_full %.0f) | dw0 %.0f (wait in_full %.0f, a_empty %.0f, mma %.0f)"
+            " dw1 %.0f (%.0f, %.0f, %.0f) dw2 %.0f (%.0f, %.0f, %.0f); epi detail: store+bar %.0f chunks %.0f (unused %.0f); dw0 detail: compute %.0f store %.0f fence+arrive %.0f; tiles/CTA %.1f\n",
+            a.C, a.N, a.H, a.W, cfg.G, cfg.NS, cfg.ctas, cfg.threads, cfg.total, s[5] / nt, s[6] / nt, s[7] / nt, s[8] / nt, s[9] / nt, s[0] / nt, s[10] / nt, s[11] / nt, s[12] / nt,
+            s[1] / nt, s[13] / nt, s[14] / nt, s[15] / nt, s[2] / nt, s[16] / nt, s[17] / nt, s[18] / nt, s[19] / nt, s[20] / nt, s[21] / nt, nt);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace fdl

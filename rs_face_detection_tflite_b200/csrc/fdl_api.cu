@@ -173,7 +173,7 @@ int64_t fdl_net_describe(const fdl_net* h, char* buf, int64_t cap) {
 int fdl_net_num_steps(const fdl_net* h) { return h && h->net ? (int)h->net->plan().steps.size() : 0; }
 int fdl_net_set_mode(fdl_net* h, int mode) {
   if (!h || !h->net) return set_error(FDL_ERR_INVALID, "null handle");
-  if (mode != 0 && mode != 1) return set_error(FDL_ERR_INVALID, "mode must be 0 (fp32) or 1 (split-TF32 tensor cores)");
+  if (mode < 0 || mode > 2) return set_error(FDL_ERR_INVALID, "mode must be 0 (fp32), 1 (split-TF32 tensor cores) or 2 (same, serial BlazeBlock kernel only)");
   h->net->set_mode(mode);
   return FDL_OK;
 }
@@ -198,6 +198,34 @@ int fdl_net_time_forward(fdl_net* h, const float* in, int batch, int iters, floa
   FDL_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   *ms_per_pass = ms / (float)iters;
+  return FDL_OK;
+}
+
+int fdl_net_time_steps(fdl_net* h, const float* in, int batch, int iters, float* ms_per_step, int cap) {
+  if (!h || !h->net || batch <= 0 || iters <= 0 || !ms_per_step) return set_error(FDL_ERR_INVALID, "bad arguments");
+  Net* net = h->net;
+  const int n = (int)net->plan().steps.size();
+  if (cap < n) return set_error(FDL_ERR_CAPACITY, "ms_per_step too small");
+  std::string err;
+  if (net->device() < 0) return set_error(FDL_ERR_CUDA, "plan-only handle cannot run");
+  FDL_CUDA_TRY(cudaSetDevice(net->device()));
+  if (!net->reserve(batch, &err)) return set_error(FDL_ERR_CUDA, err);
+  TView iv = net->input_view(batch);
+  if (in) FDL_CUDA_TRY(cudaMemcpyAsync(iv.p, in, (size_t)batch * net->in_elems() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  FDL_CUDA_TRY(net->forward(batch, h->stream));  // warm-up
+  std::vector<cudaEvent_t> ev((size_t)n + 1);
+  for (auto& e : ev) FDL_CUDA_TRY(cudaEventCreate(&e));
+  for (int i = 0; i < n; ++i) ms_per_step[i] = 0.f;
+  for (int it = 0; it < iters; ++it) {
+    FDL_CUDA_TRY(net->forward(batch, h->stream, nullptr, nullptr, ev.data()));
+    FDL_CUDA_TRY(cudaEventSynchronize(ev[n]));
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.f;
+      FDL_CUDA_TRY(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      ms_per_step[i] += ms / (float)iters;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
   return FDL_OK;
 }
 

@@ -32,6 +32,7 @@
 namespace fdl {
 
 void count_launch();
+bool encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, long long bstride, int box_h, int box_w, int box_c = 0);
 
 namespace {
 
@@ -302,16 +303,21 @@ PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 std::once_flag g_encode_once;
 constexpr int kMaxSmemTc = 227 * 1024;
 
-bool encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, long long bstride, int box_h, int box_w) {
+}  // namespace
+
+bool encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, long long bstride, int box_h, int box_w, int box_c) {
   if (!g_encode) return false;
+  if (box_c <= 0) box_c = C;   // box_c > C: the tile's pixel stride in shared memory is padded (loads zero-fill, stores clip)
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)bstride * 4};
-  cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
+
+namespace {
 
 // Picks (stages, alias_out) for a block; returns false when it cannot fit in shared memory.
 bool pick_smem(int C, int N, int Np, int S, int wsplit, int* stages, int* alias_out, int* total) {

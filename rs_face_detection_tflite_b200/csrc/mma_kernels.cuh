@@ -27,11 +27,18 @@ struct BlockTcArgs {
   int stages = 2;                  // input tile buffers
   int wsplit = 1;                  // 1: weights are tf32-exact (A split only); 2: W_hi + W_lo
   int tmem_cols = 32;
+  int groups = 1;                  // block_ws_kernel: depthwise warp groups (tiles in flight on the CUDA cores)
+  int dw_threads = 0;              // block_ws_kernel: threads per depthwise group
+  int out_bufs = 1;                // block_ws_kernel: output staging buffers (TMA store of tile i overlaps the epilogue of i+1)
+  int acc_cols = 32;               // block_ws_kernel: TMEM columns per accumulator buffer
+  int in_pad = 0;                  // block_ws_kernel: input tile pixel stride padded to an odd number of quads
   const int* n_active = nullptr;
+  float alpha_c[128] = {};         // block_ws_kernel: PRELU slopes by value (read through the constant bank in the epilogue)
 };
 
 struct BlockTcLaunch {
   BlockTcArgs args;
+  const float* alpha_host = nullptr;   // host copy of the PRELU slopes [N] (block_ws_kernel passes them as kernel parameters)
   const float* in = nullptr;       // [B,H,W,C]
   float* out = nullptr;            // [B,H,W,N]
 };
@@ -62,5 +69,10 @@ cudaError_t launch_conv_tc(const ConvTcArgs& a, cudaStream_t stream);
 cudaError_t mma_kernels_init();                             // once per device
 bool block_tc_supported(const Step& s);    // can this planned step run on the tensor-core kernel?
 cudaError_t launch_block_tc(const BlockTcLaunch& l, cudaStream_t stream);
+
+// ---- warp-specialised stride-1 BlazeBlock kernel (block_ws_kernel.cu) ----
+cudaError_t block_ws_init();
+bool block_ws_supported(const Step& s);
+cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream);
 
 }  // namespace fdl

@@ -17,6 +17,7 @@ Net* Net::create(const std::string& path, int device, std::string* err, int* cod
     if (e == cudaSuccess) e = net_kernels_init();
     if (e == cudaSuccess) e = mma_kernels_init();
     if (e == cudaSuccess) e = conv_tc_init();
+    if (e == cudaSuccess) e = block_ws_init();
     if (e == cudaSuccess) e = cudaMalloc(&n->d_weights_, n->plan_.weights.size() * sizeof(float));
     if (e == cudaSuccess)
       e = cudaMemcpy(n->d_weights_, n->plan_.weights.data(), n->plan_.weights.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -57,22 +58,25 @@ TView Net::view(const TensorRef& r, int B) const {
   return v;
 }
 
-cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const float* input_override) {
+cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const float* input_override, cudaEvent_t* step_events) {
   auto in_view = [&](const Step& st) {
     TView v = view(st.in, B);
     if (input_override && st.in.tensor == plan_.input.tensor) { v.p = const_cast<float*>(input_override); v.bstride = in_elems(); }
     return v;
   };
   if (B > cap_B_ || device_ < 0) return cudaErrorInvalidValue;
+  size_t step_index = 0;
   for (const Step& s : plan_.steps) {
     cudaError_t e;
-    if (mode_ == 1 && block_tc_supported(s)) {
+    if (step_events && (e = cudaEventRecord(step_events[step_index++], stream)) != cudaSuccess) return e;
+    if (mode_ >= 1 && block_tc_supported(s)) {
       BlockTcLaunch l;
       TView in = in_view(s), out = view(s.out, B);
       l.in = in.p; l.out = out.p;
       BlockTcArgs& a = l.args;
       a.w_umma = d_weights_ + s.w_umma; a.bias = d_weights_ + s.b; a.w_dw = d_weights_ + s.w_dw; a.b_dw = d_weights_ + s.b_dw;
       a.alpha = s.alpha >= 0 ? d_weights_ + s.alpha : nullptr;
+      l.alpha_host = s.alpha >= 0 ? plan_.weights.data() + s.alpha : nullptr;
       a.C = s.in.C; a.N = s.out.C; a.Np = s.Np; a.H = s.out.H; a.W = s.out.W; a.B = B;
       a.act = s.act; a.stride = s.stride; a.wsplit = s.wsplit; a.n_active = n_active;
       if (s.skip.tensor >= 0) {
@@ -83,8 +87,8 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const 
         else if (s.skip.tensor == s.in.tensor && s.stride == 1) a.skip_mode = 1;
         else { a.skip_mode = 2; a.skip = sk.p; a.skip_bstride = sk.bstride; }
       }
-      e = launch_block_tc(l, stream);
-    } else if (mode_ == 1 && conv_tc_supported(s)) {
+      e = (mode_ == 1 && block_ws_supported(s)) ? launch_block_ws(l, stream) : launch_block_tc(l, stream);
+    } else if (mode_ >= 1 && conv_tc_supported(s)) {
       ConvTcArgs a;
       TView in = in_view(s), out = view(s.out, B);
       a.in.p = in.p; a.in.bstride = in.bstride; a.in.H = in.H; a.in.W = in.W; a.in.C = in.C;
@@ -114,7 +118,7 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const 
       if (s.alpha >= 0) a.alpha = d_weights_ + s.alpha;
       a.act = s.act;
       if (s.skip.tensor >= 0) { a.has_skip = 1; a.skip = view(s.skip, B); a.skip_pool = s.skip_pool; a.skip_c = s.skip_c; }
-      a.B = B; a.n_active = n_active; a.mma = mode_;
+      a.B = B; a.n_active = n_active; a.mma = mode_ >= 1 ? 1 : 0;
       e = launch_fused_conv(a, stream);
     } else {
       EltArgs a;
@@ -129,6 +133,7 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const 
     }
     if (e != cudaSuccess) return e;
   }
+  if (step_events) return cudaEventRecord(step_events[step_index], stream);
   return cudaSuccess;
 }
 

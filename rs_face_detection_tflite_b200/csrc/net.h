@@ -36,7 +36,9 @@ class Net {
   // Enqueue every step for batch B on `stream`.  n_active (optional, device pointer): only the
   // first *n_active items are computed (data-dependent fan-out without a host round trip).
   // input_override (optional): read the network input from this [B, in_elems] buffer instead of the arena.
-  cudaError_t forward(int B, cudaStream_t stream, const int* n_active = nullptr, const float* input_override = nullptr);
+  // step_events (optional): num_steps + 1 events, recorded before every step and after the last one.
+  cudaError_t forward(int B, cudaStream_t stream, const int* n_active = nullptr, const float* input_override = nullptr,
+                      cudaEvent_t* step_events = nullptr);
 
  private:
   Net() = default;

@@ -47,7 +47,7 @@ def _check(name, ours, ref, size):
 
 
 @pytest.mark.parametrize("name", list(NETS))
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_forward_matches_oracle(fdl, gpu, man, name, mode):
     from oracle.graph_exec import GraphExecutor
     size = NETS[name]
@@ -85,3 +85,24 @@ def test_f64_reference_bounds_the_oracle(man):
     assert np.abs(a[0] - b[0]).max() < 1e-2
     keep = np.abs(b[1]) < 20
     assert np.abs(a[1] - b[1])[keep].max() < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(NETS))
+def test_pipelined_block_kernel_matches_the_serial_one(fdl, gpu, man, name):
+    """block_ws_kernel (mode 1: warp-specialised, several tiles in flight per CTA, bias added on the tensor cores) against
+    blaze_block_tc_kernel (mode 2) on a batch large enough to wrap every mbarrier ring many times: same results up to the
+    rounding of the bias term (2^-22 relative), and bit-identical from run to run (any race would show up here)."""
+    size = NETS[name]
+    net = fdl.Net(os.path.join(MODELS, name + ".tflite"), device=gpu)
+    x = _inputs(name, size, 96 if size <= 192 else 48, 7, man)
+    net.set_mode(2)
+    ref = net.forward(x)
+    net.set_mode(1)
+    first = net.forward(x)
+    for a, b in zip(first, ref):
+        np.testing.assert_allclose(a, b, atol=2e-4 * max(1.0, float(np.abs(b).max())), rtol=0)
+    for _ in range(3):
+        for a, b in zip(net.forward(x), first):
+            np.testing.assert_array_equal(a, b)
+    net.close()
