@@ -13,12 +13,14 @@
 // activation arenas) are shared: a per-network event serialises their use across lanes.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "device_util.h"
 #include "fdl_status.h"
+#include "glue_math.h"
 #include "net.h"
 #include "prepost_kernels.cuh"
 
@@ -28,9 +30,73 @@ namespace {
 constexpr int kDepth = 4;
 constexpr int kStages = 10;
 
+// Zero-copy host mode: the detector's letterbox (image_to_tensor with roi = None, transform.rs:239-280) interpolates
+// between only a few source rows (2 of every 7.5 for 1080p -> 256).  Those rows form a periodic pattern, so the COPY
+// ENGINE can gather exactly them with a handful of strided 2-D copies (no SM involved, full PCIe rate, overlaps any
+// kernel); the letterbox kernel then reads the compact copy from HBM.  The ROI warps keep reading the pinned frames
+// in place.
+struct RowFamily { int src_row0, rows, dst_row0; };
+struct RowGather {
+  bool ok = false;
+  int rows_per_frame = 0;      // compact rows per frame
+  int period_src_rows = 0;     // source rows per period (the pattern repeats every so many rows)
+  int periods_per_frame = 0;
+  int rows_per_period = 0;     // compact rows per period
+  std::vector<RowFamily> fam;  // one strided copy per family
+  DevBuf<int> row_pos;         // [H] source row -> compact row (-1: not gathered)
+};
+
+bool plan_row_gather(int W, int H, int S, RowGather* g, std::vector<int>* row_pos_host) {
+  I2TParams P;
+  i2t_setup(nullptr, W, H, S, S, true, -1.0, 1.0, false, 0, &P);
+  const int bw = P.warp_w + 2 * P.pad_h, bh = P.warp_h + 2 * P.pad_v;
+  const bool simple = P.valid && P.has_r2 && !P.flip && P.warp_w == P.src_w && P.warp_h == P.src_h && (!P.has_r1 || (bw == P.r1_w && bh == P.r1_h)) &&
+                      !(P.r1_w == S && P.r1_h == S);
+  if (!simple) return false;
+  const int pv = P.has_r1 ? P.pad_v : 0;
+  std::vector<char> need((size_t)H, 0);
+  for (int oy = 0; oy < S; ++oy) {
+    int y0, y1, b0, b1;
+    resize_coeff(oy, S, P.r1_h, false, &y0, &y1, &b0, &b1);
+    const int sy0 = y0 - pv, sy1 = y1 - pv;
+    if (sy0 >= 0 && sy0 < H) need[(size_t)sy0] = 1;
+    if (sy1 >= 0 && sy1 < H) need[(size_t)sy1] = 1;
+  }
+  std::vector<int> start, len;
+  for (int r = 0; r < H;) {
+    if (!need[(size_t)r]) { ++r; continue; }
+    int e = r;
+    while (e < H && need[(size_t)e]) ++e;
+    start.push_back(r); len.push_back(e - r);
+    r = e;
+  }
+  const int nruns = (int)start.size();
+  int total = 0;
+  for (int l : len) total += l;
+  if (nruns == 0 || total * 10 > H * 6) return false;     // most of the frame is needed: nothing to gain
+  for (int p = 1; p <= 8 && p <= nruns; ++p) {
+    if (nruns % p) continue;
+    bool good = true;
+    const int D = nruns > p ? start[(size_t)p] - start[0] : H;
+    for (int i = 0; i + p < nruns && good; ++i) good = start[(size_t)(i + p)] - start[(size_t)i] == D && len[(size_t)(i + p)] == len[(size_t)i];
+    if (!good || (long long)D * (nruns / p) != H) continue;   // the pattern must continue seamlessly into the next frame
+    g->fam.clear();
+    int prefix = 0;
+    for (int k = 0; k < p; ++k) { g->fam.push_back({start[(size_t)k], len[(size_t)k], prefix}); prefix += len[(size_t)k]; }
+    g->rows_per_period = prefix; g->period_src_rows = D; g->periods_per_frame = nruns / p; g->rows_per_frame = prefix * (nruns / p);
+    row_pos_host->assign((size_t)H, -1);
+    for (int i = 0; i < nruns; ++i)
+      for (int j = 0; j < len[(size_t)i]; ++j) (*row_pos_host)[(size_t)(start[(size_t)i] + j)] = (i / p) * prefix + g->fam[(size_t)(i % p)].dst_row0 + j;
+    g->ok = true;
+    return true;
+  }
+  return false;
+}
+
 struct Lane {
   cudaStream_t stream = nullptr;
   DevBuf<uint8_t> frames;
+  DevBuf<uint8_t> rows;                        // copy-engine gather of the letterbox source rows (zero-copy host mode)
   DevBuf<float> det_in, lmk_in, iris_in;       // image_to_tensor outputs (network inputs), private to the lane
   DevBuf<I2TParams> det_params, face_params, eye_params;
   DevBuf<fdl_rect> face_rois, eye_rois;
@@ -56,6 +122,7 @@ struct fdl_pipeline {
   SsdOptions opt{};
   int S = 0, N = 0, LS = 0, IS = 0;
   DevBuf<float> anchors;
+  RowGather gather;
   Lane lanes[kDepth];
   int next_ticket = 0;
   float last_device_ms = 0.f;
@@ -152,6 +219,15 @@ int fdl_pipeline_create(const fdl_pipeline_config* cfg, fdl_pipeline** out) {
     if (e == cudaSuccess) e = cudaEventCreate(&l.ev_done);
     for (auto& ev : l.ev_stage) if (e == cudaSuccess) e = cudaEventCreate(&ev);
   }
+  if (e == cudaSuccess && cfg->zero_copy_host) {
+    std::vector<int> rp;
+    if (plan_row_gather(cfg->frame_width, cfg->frame_height, p->S, &p->gather, &rp)) {
+      e = p->gather.row_pos.reserve(rp.size());
+      if (e == cudaSuccess) e = cudaMemcpy(p->gather.row_pos.p, rp.data(), rp.size() * sizeof(int), cudaMemcpyHostToDevice);
+      for (auto& l : p->lanes)
+        if (e == cudaSuccess) e = l.rows.reserve((size_t)B * p->gather.rows_per_frame * cfg->frame_width * 3);
+    }
+  }
   if (e == cudaSuccess) e = launch_anchors(p->opt, p->anchors.p, p->N, p->lanes[0].stream);
   if (e != cudaSuccess) return bail(FDL_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
   if (!p->det->reserve(B, &err) || (p->lmk && !p->lmk->reserve(F, &err)) || (p->iris && !p->iris->reserve(E, &err)))
@@ -186,7 +262,16 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
   if (rc) return rc;
 
   const long long row = (long long)W * 3, fstride = row * H;
-  const int zc_ctas = used_host ? 96 : 0;   // persistent CTAs for kernels that read host memory over PCIe
+  static const int zc_env = getenv("FDL_ZC_CTAS") ? atoi(getenv("FDL_ZC_CTAS")) : 96;
+  const int zc_ctas = used_host ? zc_env : 0;   // persistent CTAs for kernels that read host memory over PCIe
+  const bool gathered = used_host && p->gather.ok;
+  if (gathered) {
+    // the copy engine gathers the source rows of the letterbox: one strided 2-D copy per row family for the whole batch
+    const RowGather& g = p->gather;
+    for (const RowFamily& f : g.fam)
+      FDL_CUDA_TRY(cudaMemcpy2DAsync(lane->rows.p + (size_t)f.dst_row0 * row, (size_t)g.rows_per_period * row, frames[0].data + (size_t)f.src_row0 * row,
+                                     (size_t)g.period_src_rows * row, (size_t)f.rows * row, (size_t)n * g.periods_per_frame, cudaMemcpyHostToDevice, cs));
+  }
   const int F = n * MF, E = 2 * F;
   int* n_faces = lane->counters.p;
   int* n_eyes = lane->counters.p + 1;
@@ -195,7 +280,9 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
   FDL_CUDA_TRY(cudaMemsetAsync(lane->d_faces.p, 0, (size_t)F * sizeof(fdl_face_result), cs));
   // FaceDetection::infer: image_to_tensor(keep_aspect, (-1,1)) -> net -> SSD post-processing
   FDL_CUDA_TRY(launch_i2t_setup(nullptr, nullptr, nullptr, n, W, H, p->S, p->S, 1, -1.0, 1.0, 0, lane->det_params.p, nullptr, cs));
-  FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, lane->det_params.p, n, p->S, p->S, lane->det_in.p, (long long)p->S * p->S * 3, nullptr, nullptr, cs, 1, W, zc_ctas));
+  FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, lane->det_params.p, n, p->S, p->S, lane->det_in.p, (long long)p->S * p->S * 3, nullptr, nullptr, cs, 1, W,
+                          gathered ? 0 : zc_ctas, gathered ? lane->rows.p : nullptr, gathered ? p->gather.row_pos.p : nullptr,
+                          gathered ? (long long)p->gather.rows_per_frame * row : 0));
   FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[1], cs));
   FDL_CUDA_TRY(cudaStreamWaitEvent(cs, p->guard[0], 0));
   FDL_CUDA_TRY(p->det->forward(n, cs, nullptr, lane->det_in.p));

@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(256) i2t_kernel(const uint8_t* __restrict__ fr
 // per-pixel path inside the same kernel.
 __global__ void __launch_bounds__(256) i2t_rows_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
                                                        const I2TParams* __restrict__ params, int n, int out_w, int out_h,
-                                                       float* __restrict__ out, long long out_bstride, const int* n_active) {
+                                                       float* __restrict__ out, long long out_bstride, const int* n_active,
+                                                       const uint8_t* __restrict__ compact, const int* __restrict__ row_pos, long long compact_fstride) {
   extern __shared__ __align__(16) uint8_t s_rows[];
   if (n_active) n = min(n, *n_active);
   __shared__ I2TParams P;
@@ -124,7 +125,12 @@ __global__ void __launch_bounds__(256) i2t_rows_kernel(const uint8_t* __restrict
   if (in0 || in1) {
     const uint8_t* g0 = img + (long long)sy0 * row_stride;
     const uint8_t* g1 = img + (long long)sy1 * row_stride;
-    const bool vec = ((reinterpret_cast<uintptr_t>(img) | (uintptr_t)row_stride) & 15) == 0;
+    if (row_pos) {   // rows gathered into device memory by the copy engine (anything missing is still read in place)
+      const uint8_t* cf = compact + (long long)P.frame * compact_fstride;
+      if (in0 && row_pos[sy0] >= 0) g0 = cf + (long long)row_pos[sy0] * row_bytes;
+      if (in1 && row_pos[sy1] >= 0) g1 = cf + (long long)row_pos[sy1] * row_bytes;
+    }
+    const bool vec = (((in0 ? reinterpret_cast<uintptr_t>(g0) : 0) | (in1 ? reinterpret_cast<uintptr_t>(g1) : 0)) & 15) == 0;
     if (vec) {
       const int nv = row_bytes >> 4;
       for (int i = threadIdx.x; i < nv; i += blockDim.x) {
@@ -595,7 +601,8 @@ cudaError_t launch_i2t_setup(const fdl_rect* rois, const int* slot_frame, const 
 
 cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long row_stride, const I2TParams* params, int n,
                        int out_w, int out_h, float* out, long long out_bstride, uint8_t* out_u8, const int* n_active,
-                       cudaStream_t s, int rows_mode, int src_w, int max_ctas) {
+                       cudaStream_t s, int rows_mode, int src_w, int max_ctas, const uint8_t* compact, const int* row_pos,
+                       long long compact_fstride) {
   if (n <= 0) return cudaSuccess;
   // max_ctas > 0 (frames are mapped pinned host memory): a few persistent CTAs keep PCIe busy without occupying the SMs
   // another lane's network kernels need
@@ -604,7 +611,8 @@ cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long 
     if (smem <= 48 * 1024) {
       long long items = (long long)n * out_h;
       if (max_ctas > 0 && items > max_ctas) items = max_ctas;
-      i2t_rows_kernel<<<(unsigned)items, 256, smem, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, n_active);
+      i2t_rows_kernel<<<(unsigned)items, 256, smem, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, n_active, compact,
+                                                         row_pos, compact_fstride);
       return FDL_LAUNCHED();
     }
   }

@@ -27,9 +27,12 @@ cudaError_t launch_i2t_setup(const fdl_rect* rois, const int* slot_frame, const 
                              I2TParams* params, const int* n_active, cudaStream_t s);
 // image_to_tensor pixels: frames = base of [F, img_h, row_stride] u8; out = [n, out_h, out_w, 3] f32
 // (batch stride out_bstride floats); out_u8 optional [n, out_h, out_w, 3].
+// compact / row_pos / compact_fstride (optional, rows_mode only): a device-resident copy of just the source rows the
+// letterbox touches ([frame][compact row][row bytes], gathered by the copy engine); row_pos[src row] = compact row or -1.
 cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long row_stride, const I2TParams* params, int n,
                        int out_w, int out_h, float* out, long long out_bstride, uint8_t* out_u8, const int* n_active,
-                       cudaStream_t s, int rows_mode = 0, int src_w = 0, int max_ctas = 0);
+                       cudaStream_t s, int rows_mode = 0, int src_w = 0, int max_ctas = 0,
+                       const uint8_t* compact = nullptr, const int* row_pos = nullptr, long long compact_fstride = 0);
 // rows_mode = 1 (detector letterbox): one CTA per output row, source rows staged in shared memory (see i2t_rows_kernel).
 
 struct SsdPostArgs {
