@@ -272,39 +272,67 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
         sp = a.skip.p + (long long)b * a.skip.bstride + (long long)pix * a.skip.C;
       }
     }
-    for (int c0 = 0; c0 < Nt; c0 += 16) {
-      float v[16];
-      ptx::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      if (!valid) continue;
+    // Residual values are fetched 64 channels at a time with 16-byte loads, ALL issued before the accumulator columns
+    // are read, so the batch costs one global-memory round trip instead of one per channel quad (this kernel runs the
+    // small feature maps, where a CTA is a single latency chain).
+    const bool vec_skip = sp && (a.skip.C & 3) == 0 && (a.skip_c & 3) == 0 && (N & 3) == 0;
+    for (int b0 = 0; b0 < Nt; b0 += 64) {
+      float4 sk[16];
 #pragma unroll
-      for (int q4 = 0; q4 < 16; q4 += 4) {
-        const int n = n_base + c0 + q4;
-        if (n >= N) break;
-        float o4[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o4[e] = v[q4 + e] + s_bias[c0 + q4 + e];
-        if (sp) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int ch = n + e;
-            if (ch < a.skip_c) {
-              if (a.skip_pool) o4[e] += fmaxf(fmaxf(__ldg(sp + ch), __ldg(sp + a.skip.C + ch)), fmaxf(__ldg(sp + srow + ch), __ldg(sp + srow + a.skip.C + ch)));
-              else o4[e] += __ldg(sp + ch);
-            }
+      for (int j = 0; j < 16; ++j) {
+        sk[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int ch = n_base + b0 + 4 * j;
+        if (vec_skip && b0 + 4 * j < Nt && ch < a.skip_c) {
+          if (a.skip_pool) {
+            const float4 s00 = __ldg(reinterpret_cast<const float4*>(sp + ch)), s01 = __ldg(reinterpret_cast<const float4*>(sp + a.skip.C + ch));
+            const float4 s10 = __ldg(reinterpret_cast<const float4*>(sp + srow + ch)), s11 = __ldg(reinterpret_cast<const float4*>(sp + srow + a.skip.C + ch));
+            sk[j] = make_float4(fmaxf(fmaxf(s00.x, s01.x), fmaxf(s10.x, s11.x)), fmaxf(fmaxf(s00.y, s01.y), fmaxf(s10.y, s11.y)),
+                                fmaxf(fmaxf(s00.z, s01.z), fmaxf(s10.z, s11.z)), fmaxf(fmaxf(s00.w, s01.w), fmaxf(s10.w, s11.w)));
+          } else {
+            sk[j] = __ldg(reinterpret_cast<const float4*>(sp + ch));
           }
         }
-        if (a.act == ACT_RELU) {
+      }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o4[e] = fmaxf(o4[e], 0.f);
-        } else if (a.act == ACT_PRELU) {
+      for (int cc = 0; cc < 64; cc += 16) {
+        const int c0 = b0 + cc;
+        if (c0 >= Nt) break;
+        float v[16];
+        ptx::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        if (!valid) continue;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o4[e] = o4[e] >= 0.f ? o4[e] : o4[e] * s_alpha[c0 + q4 + e];
-        }
-        if ((N & 3) == 0) {
-          *reinterpret_cast<float4*>(op + n) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-        } else {
+        for (int q4 = 0; q4 < 16; q4 += 4) {
+          const int n = n_base + c0 + q4;
+          if (n >= N) break;
+          float o4[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) if (n + e < N) op[n + e] = o4[e];
+          for (int e = 0; e < 4; ++e) o4[e] = v[q4 + e] + s_bias[c0 + q4 + e];
+          if (vec_skip) {
+            const float4 s4 = sk[(cc + q4) >> 2];
+            o4[0] += s4.x; o4[1] += s4.y; o4[2] += s4.z; o4[3] += s4.w;
+          } else if (sp) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int ch = n + e;
+              if (ch < a.skip_c) {
+                if (a.skip_pool) o4[e] += fmaxf(fmaxf(__ldg(sp + ch), __ldg(sp + a.skip.C + ch)), fmaxf(__ldg(sp + srow + ch), __ldg(sp + srow + a.skip.C + ch)));
+                else o4[e] += __ldg(sp + ch);
+              }
+            }
+          }
+          if (a.act == ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o4[e] = fmaxf(o4[e], 0.f);
+          } else if (a.act == ACT_PRELU) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o4[e] = o4[e] >= 0.f ? o4[e] : o4[e] * s_alpha[c0 + q4 + e];
+          }
+          if ((N & 3) == 0) {
+            *reinterpret_cast<float4*>(op + n) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (n + e < N) op[n + e] = o4[e];
+          }
         }
       }
     }
