@@ -75,24 +75,33 @@ __global__ void __launch_bounds__(256) i2t_kernel(const uint8_t* __restrict__ fr
 // once, and only the rows the 2x2-tap resize touches are read at all (27 % of a 1080p frame at S = 256).
 // The arithmetic is the same fixed-point resize as i2t_pixel (bit-exact); any other slot takes the generic
 // per-pixel path inside the same kernel.
+constexpr int kRowsPerItem = 4;    // output rows per work item of the row-staged letterbox kernel
+
 __global__ void __launch_bounds__(256) i2t_rows_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
                                                        const I2TParams* __restrict__ params, int n, int out_w, int out_h,
                                                        float* __restrict__ out, long long out_bstride, const int* n_active,
-                                                       const uint8_t* __restrict__ compact, const int* __restrict__ row_pos, long long compact_fstride) {
-  extern __shared__ __align__(16) uint8_t s_rows[];
+                                                       const uint8_t* __restrict__ compact, const int* __restrict__ row_pos, long long compact_fstride,
+                                                       int rows_per_item) {
+  extern __shared__ __align__(16) uint8_t s_rows[];     // [2 * rows_per_item][row_pad]
   if (n_active) n = min(n, *n_active);
   __shared__ I2TParams P;
-  const long long items = (long long)n * out_h;
+  __shared__ float s_lut[256];                          // i2t_normalise for every grey level (exact: same f64 expression)
+  const int groups = (out_h + rows_per_item - 1) / rows_per_item;
+  const long long items = (long long)n * groups;
+  int cur_slot = -1;
   for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-  const int slot = (int)(item / out_h), oy = (int)(item - (long long)slot * out_h);
+  const int slot = (int)(item / groups), oy_first = (int)(item - (long long)slot * groups) * rows_per_item;
+  const int nrows = min(rows_per_item, out_h - oy_first);
   __syncthreads();
-  {
+  if (slot != cur_slot) {
     const int* src = reinterpret_cast<const int*>(&params[slot]);
     int* dst = reinterpret_cast<int*>(&P);
     for (int i = threadIdx.x; i < (int)(sizeof(I2TParams) / 4); i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = i2t_normalise(i, P.range_min, P.range_max);
+    cur_slot = slot;
+    __syncthreads();
   }
-  __syncthreads();
-  float* orow = out + (long long)slot * out_bstride + (long long)oy * out_w * 3;
   const uint8_t* img = frames + (long long)P.frame * frame_stride;
   const int bw = P.warp_w + 2 * P.pad_h, bh = P.warp_h + 2 * P.pad_v;
   bool simple = P.valid && P.has_r2 && !P.flip && P.warp_w == P.src_w && P.warp_h == P.src_h &&
@@ -103,67 +112,75 @@ __global__ void __launch_bounds__(256) i2t_rows_kernel(const uint8_t* __restrict
              fabs(P.Mi[3]) < e && fabs(P.Mi[5]) < e * P.src_h && fabs(P.Mi[6]) < e && fabs(P.Mi[7]) < e;
   }
   if (!simple) {
-    for (int ox = threadIdx.x; ox < out_w; ox += blockDim.x) {
-      Px3 p;
-      if (P.valid) p = i2t_pixel(P, img_src(img, row_stride), ox, oy);
-      else { p.r = p.g = p.b = 0; }
-      orow[3 * ox] = i2t_normalise(p.r, P.range_min, P.range_max);
-      orow[3 * ox + 1] = i2t_normalise(p.g, P.range_min, P.range_max);
-      orow[3 * ox + 2] = i2t_normalise(p.b, P.range_min, P.range_max);
+    for (int r = 0; r < nrows; ++r) {
+      const int oy = oy_first + r;
+      float* orow = out + (long long)slot * out_bstride + (long long)oy * out_w * 3;
+      for (int ox = threadIdx.x; ox < out_w; ox += blockDim.x) {
+        Px3 p;
+        if (P.valid) p = i2t_pixel(P, img_src(img, row_stride), ox, oy);
+        else { p.r = p.g = p.b = 0; }
+        orow[3 * ox] = i2t_normalise(p.r, P.range_min, P.range_max);
+        orow[3 * ox + 1] = i2t_normalise(p.g, P.range_min, P.range_max);
+        orow[3 * ox + 2] = i2t_normalise(p.b, P.range_min, P.range_max);
+      }
     }
     continue;
   }
   const int ph = P.has_r1 ? P.pad_h : 0, pv = P.has_r1 ? P.pad_v : 0;
-  int y0, y1, b0, b1;
-  resize_coeff(oy, out_h, P.r1_h, false, &y0, &y1, &b0, &b1);
-  const int sy0 = y0 - pv, sy1 = y1 - pv;                        // source rows (outside the frame: constant-0 border)
-  const bool in0 = sy0 >= 0 && sy0 < P.src_h, in1 = sy1 >= 0 && sy1 < P.src_h;
   const int row_bytes = P.src_w * 3;
   const int row_pad = (row_bytes + 15) & ~15;
-  uint8_t* r0 = s_rows;
-  uint8_t* r1 = s_rows + row_pad;
-  if (in0 || in1) {
-    const uint8_t* g0 = img + (long long)sy0 * row_stride;
-    const uint8_t* g1 = img + (long long)sy1 * row_stride;
-    if (row_pos) {   // rows gathered into device memory by the copy engine (anything missing is still read in place)
-      const uint8_t* cf = compact + (long long)P.frame * compact_fstride;
-      if (in0 && row_pos[sy0] >= 0) g0 = cf + (long long)row_pos[sy0] * row_bytes;
-      if (in1 && row_pos[sy1] >= 0) g1 = cf + (long long)row_pos[sy1] * row_bytes;
-    }
-    const bool vec = (((in0 ? reinterpret_cast<uintptr_t>(g0) : 0) | (in1 ? reinterpret_cast<uintptr_t>(g1) : 0)) & 15) == 0;
-    if (vec) {
-      const int nv = row_bytes >> 4;
-      for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-        if (in0) reinterpret_cast<uint4*>(r0)[i] = __ldg(reinterpret_cast<const uint4*>(g0) + i);
-        if (in1) reinterpret_cast<uint4*>(r1)[i] = __ldg(reinterpret_cast<const uint4*>(g1) + i);
-      }
-      for (int i = (nv << 4) + threadIdx.x; i < row_bytes; i += blockDim.x) {
-        if (in0) r0[i] = g0[i];
-        if (in1) r1[i] = g1[i];
-      }
-    } else {
-      for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) {
-        if (in0) r0[i] = g0[i];
-        if (in1) r1[i] = g1[i];
+  // ---- stage the (up to) 2 * nrows source rows: every load of the item is issued before the barrier ----
+  for (int r = 0; r < nrows; ++r) {
+    int y0, y1, b0, b1;
+    resize_coeff(oy_first + r, out_h, P.r1_h, false, &y0, &y1, &b0, &b1);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int sy = (h ? y1 : y0) - pv;                          // source row (outside the frame: constant-0 border)
+      if (sy < 0 || sy >= P.src_h) continue;
+      const uint8_t* g = img + (long long)sy * row_stride;
+      if (row_pos && row_pos[sy] >= 0)   // rows gathered into device memory by the copy engine (anything missing is still read in place)
+        g = compact + (long long)P.frame * compact_fstride + (long long)row_pos[sy] * row_bytes;
+      uint8_t* d = s_rows + (2 * r + h) * row_pad;
+      if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+        // asynchronous 16-byte copies: nothing waits until every row of the item has been requested
+        const int nv = row_bytes >> 4;
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+          const unsigned sd = (unsigned)__cvta_generic_to_shared(d + 16 * i);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sd), "l"(g + 16 * (size_t)i) : "memory");
+        }
+        for (int i = (nv << 4) + threadIdx.x; i < row_bytes; i += blockDim.x) d[i] = g[i];
+      } else {
+        for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) d[i] = g[i];
       }
     }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   for (int ox = threadIdx.x; ox < out_w; ox += blockDim.x) {
     int x0, x1, a0, a1;
     resize_coeff(ox, out_w, P.r1_w, true, &x0, &x1, &a0, &a1);
     const int sx0 = x0 - ph, sx1 = x1 - ph;
     const bool cx0 = sx0 >= 0 && sx0 < P.src_w, cx1 = sx1 >= 0 && sx1 < P.src_w;
-    int v[3];
+    for (int r = 0; r < nrows; ++r) {
+      const int oy = oy_first + r;
+      int y0, y1, b0, b1;
+      resize_coeff(oy, out_h, P.r1_h, false, &y0, &y1, &b0, &b1);
+      const int sy0 = y0 - pv, sy1 = y1 - pv;
+      const bool in0 = sy0 >= 0 && sy0 < P.src_h, in1 = sy1 >= 0 && sy1 < P.src_h;
+      const uint8_t* r0 = s_rows + (2 * r) * row_pad;
+      const uint8_t* r1 = r0 + row_pad;
+      float* orow = out + (long long)slot * out_bstride + (long long)oy * out_w * 3;
+      int v[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const int p00 = (in0 && cx0) ? r0[3 * sx0 + c] : 0, p01 = (in0 && cx1) ? r0[3 * sx1 + c] : 0;
-      const int p10 = (in1 && cx0) ? r1[3 * sx0 + c] : 0, p11 = (in1 && cx1) ? r1[3 * sx1 + c] : 0;
-      v[c] = resize_mix(p00, p01, p10, p11, a0, a1, b0, b1);
+      for (int c = 0; c < 3; ++c) {
+        const int p00 = (in0 && cx0) ? r0[3 * sx0 + c] : 0, p01 = (in0 && cx1) ? r0[3 * sx1 + c] : 0;
+        const int p10 = (in1 && cx0) ? r1[3 * sx0 + c] : 0, p11 = (in1 && cx1) ? r1[3 * sx1 + c] : 0;
+        v[c] = resize_mix(p00, p01, p10, p11, a0, a1, b0, b1);
+      }
+      orow[3 * ox] = s_lut[v[0] & 255];
+      orow[3 * ox + 1] = s_lut[v[1] & 255];
+      orow[3 * ox + 2] = s_lut[v[2] & 255];
     }
-    orow[3 * ox] = i2t_normalise(v[0], P.range_min, P.range_max);
-    orow[3 * ox + 1] = i2t_normalise(v[1], P.range_min, P.range_max);
-    orow[3 * ox + 2] = i2t_normalise(v[2], P.range_min, P.range_max);
   }
   }  // item loop
 }
@@ -607,12 +624,16 @@ cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long 
   // max_ctas > 0 (frames are mapped pinned host memory): a few persistent CTAs keep PCIe busy without occupying the SMs
   // another lane's network kernels need
   if (rows_mode && !out_u8) {
-    const size_t smem = 2 * (size_t)((src_w * 3 + 15) & ~15);
+    const size_t row_pad = (size_t)((src_w * 3 + 15) & ~15);
+    int rpi = kRowsPerItem;
+    while (rpi > 1 && 2 * rpi * row_pad > 48 * 1024) rpi >>= 1;
+    const size_t smem = 2 * rpi * row_pad;
     if (smem <= 48 * 1024) {
-      long long items = (long long)n * out_h;
-      if (max_ctas > 0 && items > max_ctas) items = max_ctas;
+      long long items = (long long)n * ((out_h + rpi - 1) / rpi);
+      const long long cap = max_ctas > 0 ? max_ctas : 148LL * 4;      // persistent CTAs (items are strided over the grid)
+      if (items > cap) items = cap;
       i2t_rows_kernel<<<(unsigned)items, 256, smem, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, n_active, compact,
-                                                         row_pos, compact_fstride);
+                                                         row_pos, compact_fstride, rpi);
       return FDL_LAUNCHED();
     }
   }
