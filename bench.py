@@ -371,7 +371,7 @@ def main():
     ap.add_argument("--latency-iters", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-zero-copy", action="store_true", help="skip the zero-copy e2e leg")
-    ap.add_argument("--inflight", type=int, default=3, help="batches in flight in the e2e loop (<= pipeline depth 4)")
+    ap.add_argument("--inflight", type=int, default=4, help="batches in flight in the e2e loop (<= pipeline depth 4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -262,7 +262,7 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
   if (rc) return rc;
 
   const long long row = (long long)W * 3, fstride = row * H;
-  static const int zc_env = getenv("FDL_ZC_CTAS") ? atoi(getenv("FDL_ZC_CTAS")) : 96;
+  static const int zc_env = getenv("FDL_ZC_CTAS") ? atoi(getenv("FDL_ZC_CTAS")) : 148;
   const int zc_ctas = used_host ? zc_env : 0;   // persistent CTAs for kernels that read host memory over PCIe
   const bool gathered = used_host && p->gather.ok;
   if (gathered) {

@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(256) i2t_rows_kernel(const uint8_t* __restrict
 // PCIe once per tile instead of once per tap -- and the pixels are then evaluated by the very same i2t_pixel code
 // reading through ImgSrc (anything outside the staged box falls back to a direct load, so staging is purely a
 // traffic optimisation and cannot change a result).
-constexpr int kTile = 32;
-constexpr int kTileSmem = 64 * 1024;
+constexpr int kTileW = 64, kTileH = 32;   // wide tiles: longer source row segments => fewer partially used 128-byte lines over PCIe
+constexpr int kTileSmem = 96 * 1024;
 
 __global__ void __launch_bounds__(256) i2t_tile_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
                                                        const I2TParams* __restrict__ params, int n, int out_w, int out_h,
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) i2t_tile_kernel(const uint8_t* __restrict
   if (n_active) n = min(n, *n_active);
   __shared__ I2TParams P;
   __shared__ int s_box[6];   // x0, y0, x1, y1 (pixels, inclusive; x1 < x0: nothing staged), start byte, pitch
-  const int tiles_x = (out_w + kTile - 1) / kTile, tiles_y = (out_h + kTile - 1) / kTile;
+  const int tiles_x = (out_w + kTileW - 1) / kTileW, tiles_y = (out_h + kTileH - 1) / kTileH;
   const long long items = (long long)n * tiles_x * tiles_y;
   for (long long item = blockIdx.x; item < items; item += gridDim.x) {
     const int slot = (int)(item / (tiles_x * tiles_y));
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) i2t_tile_kernel(const uint8_t* __restrict
     }
     __syncthreads();
     const uint8_t* img = frames + (long long)P.frame * frame_stride;
-    const int ox0 = tx * kTile, oy0 = ty * kTile, ox1 = min(ox0 + kTile, out_w) - 1, oy1 = min(oy0 + kTile, out_h) - 1;
+    const int ox0 = tx * kTileW, oy0 = ty * kTileH, ox1 = min(ox0 + kTileW, out_w) - 1, oy1 = min(oy0 + kTileH, out_h) - 1;
     if (threadIdx.x == 0) {
       s_box[0] = 0; s_box[1] = 0; s_box[2] = -1; s_box[3] = -1; s_box[4] = 0; s_box[5] = 0;
       bool ok = P.valid != 0;
@@ -643,7 +643,7 @@ cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long 
       cudaFuncSetAttribute(i2t_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
       attr_done = true;
     }
-    long long items = (long long)n * ((out_w + kTile - 1) / kTile) * ((out_h + kTile - 1) / kTile);
+    long long items = (long long)n * ((out_w + kTileW - 1) / kTileW) * ((out_h + kTileH - 1) / kTileH);
     if (items > max_ctas) items = max_ctas;
     i2t_tile_kernel<<<(unsigned)items, 256, kTileSmem, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, n_active);
     return FDL_LAUNCHED();
