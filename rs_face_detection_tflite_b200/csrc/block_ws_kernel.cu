@@ -84,7 +84,7 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 
 template <int kMaxT, int kMinB>
 __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
-                                                                  const BlockTcArgs a, long long* __restrict__ dbg) {
+                                                                  const BlockTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = a.C, N = a.N, Np = a.Np, Q = C >> 2;
@@ -162,7 +162,6 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     const int NPf = ((N >> 2) | 1) << 2;        // staging pixel stride (floats)
     int tile = blockIdx.x;
     int pb = 0, pty = 0, ptx_ = 0;              // coordinates of the previous tile (its TMA store is issued one tile late)
-    long long t_wacc = 0, t_bar1 = 0, t_chunks = 0, t_tail = 0, t0 = clock64();
     for (int it = 0; it < my_tiles; ++it, tile += gridDim.x) {
       const int s = it % NS, t = it % T, ob = it & 1;
       const int b = tile / tiles_per_img, rr = tile - b * tiles_per_img;
@@ -188,11 +187,10 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       };
       if (a.skip_mode == 1) ptx::mbar_wait(&in_full[s], (uint32_t)((it / NS) & 1));
       load_res(0, res);
-      { const long long c0 = clock64(); ptx::mbar_wait(&acc_full[t], (uint32_t)((it / T) & 1)); t_wacc += clock64() - c0; }
+      ptx::mbar_wait(&acc_full[t], (uint32_t)((it / T) & 1));
       ptx::tc_fence_after_sync();
       // ---- deferred TMA store of the PREVIOUS tile: its staging writes have had a whole tile to drain ----
       {
-        const long long c0 = clock64();
         ptx::fence_proxy_async_smem();
         if (tid == 0) ptx::tma_store_wait_read0();            // the store of tile it-2 has finished reading buffer `ob`
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -202,10 +200,8 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
           // every epilogue warp is past its residual reads of the previous tile's stage: refill it
           if (it - 1 + NS < my_tiles) issue_load(it - 1 + NS);
         }
-        t_bar1 += clock64() - c0;
       }
       pb = b; pty = ty; ptx_ = tx;
-      const long long c_chunks = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * acc_cols);
       for (int c0 = 0; c0 < Np; c0 += 32) {
         if (c0 + 32 < Np) load_res(c0 + 32, resn);
@@ -240,7 +236,6 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 8; ++j) res[j] = resn[j];
       }
-      t_chunks += clock64() - c_chunks;
     }
     // the last tile's store
     ptx::fence_proxy_async_smem();
@@ -251,8 +246,6 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       ptx::tma_store_commit();
       ptx::tma_store_wait_all0();
     }
-    if (dbg && tid == 0) { dbg[blockIdx.x * 32 + 5] = clock64() - t0; dbg[blockIdx.x * 32 + 6] = t_wacc; dbg[blockIdx.x * 32 + 31] = my_tiles;
-      dbg[blockIdx.x * 32 + 16] = t_bar1; dbg[blockIdx.x * 32 + 17] = t_chunks; dbg[blockIdx.x * 32 + 18] = t_tail; }
   } else {
     // ================= depthwise 3x3 -> A operand (hi / lo planes) -> MMA issue =================
     const int dtid = tid - kEpiThreads;
@@ -279,12 +272,10 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     const uint32_t w_addr = ptx::smem_u32(s_w), wb_addr = ptx::smem_u32(smem + L.wb), ones_addr = ptx::smem_u32(smem + L.ones);
     const uint32_t w_lbo = (uint32_t)Np * 16u;
     const uint32_t ahi_addr = ptx::smem_u32(s_ahi), alo_addr = ahi_addr + (uint32_t)(Q * kPlaneBytes);
-    long long t_win = 0, t_wae = 0, t_mma = 0, t_comp = 0, t_store = 0, t_fence = 0, t0 = clock64();
     for (int it = g; it < my_tiles; it += G) {
       const int s = it % NS, kg = it / G, t = it % T;
-      { const long long c0 = clock64(); ptx::mbar_wait(&in_full[s], (uint32_t)((it / NS) & 1)); t_win += clock64() - c0; }
+      ptx::mbar_wait(&in_full[s], (uint32_t)((it / NS) & 1));
       const float* s_in = reinterpret_cast<const float*>(smem + L.in0 + s * L.in_stage);
-      long long c_a = clock64();
       for (int item = gt, ii = 0; item < nitems; item += ndwg, ++ii) {
         const int xr = item / Q;                // item % Q == q
         const int x = xr % TW, half = xr / TW;
@@ -320,7 +311,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
           }
         }
         // the MMAs of this group's previous tile must have finished reading the A buffer
-        { const long long c0 = clock64(); t_comp += c0 - c_a; if (ii == 0 && kg > 0) { ptx::mbar_wait(&a_empty[g], (uint32_t)((kg - 1) & 1)); } c_a = clock64(); t_wae += c_a - c0; }
+        if (ii == 0 && kg > 0) ptx::mbar_wait(&a_empty[g], (uint32_t)((kg - 1) & 1));
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
           const int p = (half * 4 + o) * TW + x;
@@ -330,14 +321,11 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
           *reinterpret_cast<ulonglong2*>(s_ahi + q * kPlaneBytes + p * 16) = hi;
           *reinterpret_cast<ulonglong2*>(s_alo + q * kPlaneBytes + p * 16) = lo;
         }
-        { const long long c0 = clock64(); t_store += c0 - c_a; c_a = c0; }
       }
       ptx::fence_proxy_async_smem();            // generic-proxy writes of A -> visible to the tensor core (async proxy)
       mbar_arrive(&a_full[g]);
-      t_fence += clock64() - c_a;
       if (gt == 0) {
         // ---- this tile's MMA chain, issued by one thread ----
-        const long long c0 = clock64();
         ptx::mbar_wait(&a_full[g], (uint32_t)(kg & 1));
         if (it >= T) ptx::mbar_wait(&acc_empty[t], (uint32_t)(((it / T) - 1) & 1));
         ptx::tc_fence_after_sync();
@@ -358,13 +346,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
         }
         ptx::mma_commit(&acc_full[t]);
         ptx::mma_commit(&a_empty[g]);
-        t_mma += clock64() - c0;
       }
-    }
-    if (dbg && gt == 0) {
-      dbg[blockIdx.x * 32 + 7 + 3 * g] = clock64() - t0; dbg[blockIdx.x * 32 + 8 + 3 * g] = t_win; dbg[blockIdx.x * 32 + 9 + 3 * g] = t_wae;
-      dbg[blockIdx.x * 32 + g] = t_mma;
-      if (g == 0) { dbg[blockIdx.x * 32 + 19] = t_comp; dbg[blockIdx.x * 32 + 20] = t_store; dbg[blockIdx.x * 32 + 21] = t_fence; }
     }
   }
 
@@ -450,25 +432,13 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   const int ntiles = a.B * a.tiles_x * a.tiles_y;
   int grid = 148 * cfg.ctas;
   if (grid > ntiles) grid = ntiles;
-  static const bool debug = getenv("FDL_WS_DEBUG") != nullptr;
-  long long* dbg = nullptr;
-  if (debug) { cudaMalloc(&dbg, 296 * 32 * sizeof(long long)); cudaMemset(dbg, 0, 296 * 32 * sizeof(long long)); }
-  if (cfg.ctas == 2) block_ws_kernel<320, 2><<<grid, cfg.threads, cfg.total, stream>>>(tm_in, tm_out, a, dbg);
-  else block_ws_kernel<512, 1><<<grid, cfg.threads, cfg.total, stream>>>(tm_in, tm_out, a, dbg);
+  if (cfg.ctas == 2) block_ws_kernel<320, 2><<<grid, cfg.threads, cfg.total, stream>>>(tm_in, tm_out, a);
+  else block_ws_kernel<512, 1><<<grid, cfg.threads, cfg.total, stream>>>(tm_in, tm_out, a);
   count_launch();
-  if (debug) {   // per-role cycle accounting (diagnostics only: synchronises the stream)
-    static long long h[296 * 32];
-    cudaStreamSynchronize(stream);
-    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
-    cudaFree(dbg);
-    double s[32] = {0};
-    for (int b = 0; b < grid; ++b) for (int k = 0; k < 32; ++k) s[k] += (double)h[b * 32 + k] / grid;
-    const double nt = s[31] > 0 ? s[31] : 1;
-    fprintf(stderr, "[ws C=%d N=%d %dx%d G=%d NS=%d ctas=%d thr=%d smem=%d] cycles per CTA tile: epi %.0f (wait acc_full %.0f) | dw0 %.0f (wait in_full %.0f, a_empty %.0f, mma %.0f)"
-            " dw1 %.0f (%.0f, %.0f, %.0f) dw2 %.0f (%.0f, %.0f, %.0f); epi detail: store+bar %.0f chunks %.0f (unused %.0f); dw0 detail: compute %.0f store %.0f fence+arrive %.0f; tiles/CTA %.1f\n",
-            a.C, a.N, a.H, a.W, cfg.G, cfg.NS, cfg.ctas, cfg.threads, cfg.total, s[5] / nt, s[6] / nt, s[7] / nt, s[8] / nt, s[9] / nt, s[0] / nt, s[10] / nt, s[11] / nt, s[12] / nt,
-            s[1] / nt, s[13] / nt, s[14] / nt, s[15] / nt, s[2] / nt, s[16] / nt, s[17] / nt, s[18] / nt, s[19] / nt, s[20] / nt, s[21] / nt, nt);
-  }
+  static const bool verbose = getenv("FDL_WS_VERBOSE") != nullptr;
+  if (verbose)
+    fprintf(stderr, "[ws C=%d N=%d %dx%d G=%d NS=%d ctas=%d thr=%d smem=%d in_pad=%d]\n", a.C, a.N, a.H, a.W, cfg.G, cfg.NS, cfg.ctas, cfg.threads, cfg.total,
+            cfg.in_pad);
   return cudaGetLastError();
 }
 
