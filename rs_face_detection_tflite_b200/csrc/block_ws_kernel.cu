@@ -39,9 +39,20 @@ namespace {
 
 typedef unsigned long long ull;
 
+// Depthwise work assignment for Q = 6 channel quads (C = 24): item j of a half tile -> (quad | x << 4).  With the plain
+// "quad fastest, then x" order a quarter warp's A-plane stores collide two-fold; this order (found by exhaustive search)
+// keeps BOTH the 16-byte input loads ((6x + q) mod 8) and the plane stores ((q + x) mod 8) of every 8 consecutive lanes
+// in 8 different bank groups.
+__constant__ unsigned char kMapQ6[96] = {
+    0, 16, 32, 48, 49, 65, 81, 97, 64, 80, 96, 112, 1, 17, 33, 113, 128, 144, 160, 176, 177, 193, 209, 225, 192, 208, 224, 240, 129, 145, 161, 241,
+    2, 18, 34, 50, 51, 67, 83, 99, 66, 82, 98, 114, 3, 19, 35, 115, 130, 146, 162, 178, 179, 195, 211, 227, 194, 210, 226, 242, 131, 147, 163, 243,
+    4, 20, 36, 52, 53, 69, 85, 101, 68, 84, 100, 116, 5, 21, 37, 117, 132, 148, 164, 180, 181, 197, 213, 229, 196, 212, 228, 244, 133, 149, 165, 245};
+
 constexpr int TH = 8, TW = 16;                 // output tile: 128 pixels == UMMA M
 constexpr int ITH = TH + 2, ITW = TW + 2;      // input halo tile
-constexpr int kPlaneBytes = TH * TW * 16 + 16; // one channel-quad plane of A (+16 B bank skew) == LBO
+constexpr int kPlaneData = TH * TW * 16;      // one channel-quad plane of A: 128 pixels x 16 B
+// Plane stride (== LBO) = kPlaneData + 16 B of bank skew between consecutive channel-quad planes.
+__host__ __device__ inline int plane_bytes(int) { return kPlaneData + 16; }
 constexpr int kEpiThreads = 128;               // 4 epilogue warps: one per TMEM lane quarter
 constexpr int kMaxThreads = 512;
 constexpr int kMaxStages = 6, kMaxGroups = 3;
@@ -60,11 +71,11 @@ __host__ __device__ inline WsLayout ws_layout(int C, int N, int Np, int wsplit, 
   L.w = off; off += wsplit * (C / 4) * Np * 16;
   L.wb = off; off += 2 * Np * 16;               // bias as one more K step of B: [2 quads][Np][4] = (b_hi, b_lo, 0, 0), 0
   off = align_up_w(off, 128);
-  L.ones = off; off += 2 * kPlaneBytes;         // the matching A planes: (1, 1, 0, 0) for every pixel, then zeros
+  L.ones = off; off += 2 * plane_bytes(C);         // the matching A planes: (1, 1, 0, 0) for every pixel, then zeros
   off = align_up_w(off, 128);
   L.in_stage = align_up_w(ITH * ITW * (in_pad ? ((C / 4) | 1) * 4 : C) * 4, 128);   // in_pad: pixel stride = odd number of 16-byte quads
   L.in0 = off; off += NS * L.in_stage;
-  L.a_buf = align_up_w(2 * (C / 4) * kPlaneBytes, 128);   // hi planes then lo planes
+  L.a_buf = align_up_w(2 * (C / 4) * plane_bytes(C), 128);   // hi planes then lo planes
   L.a0 = off; off += G * L.a_buf;
   L.out_stage = align_up_w(TH * TW * ((N / 4) | 1) * 16, 128);   // raw accumulator tile, pixel stride = odd number of quads
   L.out0 = off; off += OB * L.out_stage;
@@ -89,6 +100,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = a.C, N = a.N, Np = a.Np, Q = C >> 2;
   const int NS = a.stages, G = a.groups, ndwg = a.dw_threads;
+  const int kPlaneBytes = plane_bytes(C);
   const WsLayout L = ws_layout(C, N, Np, a.wsplit, NS, G, a.out_bufs, a.in_pad);
   const int T = G > 2 ? G : 2;                  // TMEM accumulators: tile it -> buffer it % T (== its group when G >= 2, so each
                                                 // buffer has ONE issuing thread and its full/empty phases stay in lockstep)
@@ -250,7 +262,9 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     // ================= depthwise 3x3 -> A operand (hi / lo planes) -> MMA issue =================
     const int dtid = tid - kEpiThreads;
     const int g = dtid / ndwg, gt = dtid - g * ndwg;
-    const int q = gt % Q;                       // ndwg % Q == 0: the channel quad is fixed per thread
+    const bool map6 = Q == 6 && ndwg == 192;    // one item per thread, remapped for conflict-free stores (see kMapQ6)
+    const int m6 = map6 ? kMapQ6[gt % 96] : 0;
+    const int q = map6 ? (m6 & 15) : gt % Q;    // ndwg % Q == 0: the channel quad is fixed per thread
     ull wd[9][2], bd[2];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
@@ -278,7 +292,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       const float* s_in = reinterpret_cast<const float*>(smem + L.in0 + s * L.in_stage);
       for (int item = gt, ii = 0; item < nitems; item += ndwg, ++ii) {
         const int xr = item / Q;                // item % Q == q
-        const int x = xr % TW, half = xr / TW;
+        const int x = map6 ? (m6 >> 4) : xr % TW, half = map6 ? item / 96 : xr / TW;
         ull acc[4][2];
 #pragma unroll
         for (int o = 0; o < 4; ++o) { acc[o][0] = bd[0]; acc[o][1] = bd[1]; }
