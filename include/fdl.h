@@ -273,6 +273,14 @@ FDL_API int fdl_pipeline_submit(fdl_pipeline*, const fdl_image* frames, int n, i
 FDL_API int fdl_pipeline_collect(fdl_pipeline*, int ticket, fdl_frame_result* frame_results,
                                  fdl_face_result* face_results, int* n);
 /* Device time of the last collected ticket's kernels (excludes copies), milliseconds. */
+/* Host-only introspection of the zero-copy ingest plan (no GPU needed): which source rows of a
+ * frame_width x frame_height frame the detector's letterbox (image_to_tensor with roi = None,
+ * transform.rs:239-280, INTER_LINEAR 2x2 taps) reads for an input_size x input_size tensor, and how
+ * the copy engine gathers them.  Returns 1 and fills row_pos[frame_height] (compact row index or
+ * -1) and info4 = {compact rows per frame, source rows per period, periods per frame, strided
+ * copies per batch} when the rows form a periodic pattern that continues across contiguous
+ * frames; 0 when the pipeline reads the frames in place instead; negative on error. */
+FDL_API int fdl_letterbox_row_plan(int frame_width, int frame_height, int input_size, int32_t* row_pos, int32_t* info4);
 FDL_API float fdl_pipeline_last_device_ms(const fdl_pipeline*);
 /* Stage breakdown of the last collected ticket, ms: [0] H2D, [1] detector preprocess, [2] detector
  * net, [3] SSD post-process, [4] face ROI + warp, [5] landmark net, [6] landmark post + eye warp,

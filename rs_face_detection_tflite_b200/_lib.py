@@ -100,6 +100,7 @@ SYMBOLS = {
     "fdl_net_set_mode": (C.c_int, [_vp, C.c_int]),
     "fdl_net_time_forward": (C.c_int, [_vp, _P(C.c_float), C.c_int, C.c_int, _P(C.c_float)]),
     "fdl_net_time_steps": (C.c_int, [_vp, _P(C.c_float), C.c_int, C.c_int, _P(C.c_float), C.c_int]),
+    "fdl_letterbox_row_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, _P(C.c_int32), _P(C.c_int32)]),
     "fdl_pipeline_create": (C.c_int, [_P(CPipelineConfig), _P(_vp)]),
     "fdl_pipeline_destroy": (None, [_vp]),
     "fdl_pipeline_run": (C.c_int, [_vp, _P(CImage), C.c_int, _P(CFrameResult), _P(CFaceResult)]),

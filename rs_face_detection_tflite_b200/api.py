@@ -560,6 +560,19 @@ class Pipeline:
         return list(out)
 
 
+def letterbox_row_plan(frame_size, input_size: int):
+    """Zero-copy ingest plan of the detector letterbox: ``(row_pos[H], info)`` or ``None`` when the rows are not gathered."""
+    w, h = frame_size
+    rp = (C.c_int32 * h)()
+    info = (C.c_int32 * 4)()
+    rc = lib().fdl_letterbox_row_plan(w, h, input_size, rp, info)
+    if rc < 0:
+        check(rc)
+    if rc == 0:
+        return None
+    return np.array(rp[:], np.int32), {"rows_per_frame": info[0], "period_src_rows": info[1], "periods_per_frame": info[2], "copies": info[3]}
+
+
 def device_count() -> int:
     return lib().fdl_device_count()
 

@@ -383,6 +383,19 @@ int fdl_pipeline_run(fdl_pipeline* p, const fdl_image* frames, int n, fdl_frame_
   return fdl_pipeline_collect(p, ticket, frame_results, face_results, nullptr);
 }
 
+int fdl_letterbox_row_plan(int frame_width, int frame_height, int input_size, int32_t* row_pos, int32_t* info4) {
+  if (frame_width <= 0 || frame_height <= 0 || input_size <= 0) return set_error(FDL_ERR_INVALID, "bad arguments");
+  RowGather g;
+  std::vector<int> rp;
+  if (!plan_row_gather(frame_width, frame_height, input_size, &g, &rp)) {
+    if (info4) info4[0] = info4[1] = info4[2] = info4[3] = 0;
+    return 0;
+  }
+  if (row_pos) for (int i = 0; i < frame_height; ++i) row_pos[i] = rp[(size_t)i];
+  if (info4) { info4[0] = g.rows_per_frame; info4[1] = g.period_src_rows; info4[2] = g.periods_per_frame; info4[3] = (int)g.fam.size(); }
+  return 1;
+}
+
 float fdl_pipeline_last_device_ms(const fdl_pipeline* p) { return p ? p->last_device_ms : 0.f; }
 int fdl_pipeline_stage_ms(const fdl_pipeline* p, float* out10) {
   if (!p || !out10) return set_error(FDL_ERR_INVALID, "null argument");

@@ -224,3 +224,35 @@ def test_rank_sharding_under_gloo(tmp_path):
     res = json.loads(line)
     assert len(res["digests"]) == 2 and res["digests"][0] != res["digests"][1]   # ranks work on different frames
     assert res["tmax"] == 2.0
+
+
+@pytest.mark.parametrize("size,s", [((1920, 1080), 256), ((1280, 720), 256), ((3840, 2160), 256), ((1920, 1080), 128), ((2560, 1440), 192)])
+def test_letterbox_row_plan_covers_exactly_the_rows_opencv_reads(fdl, size, s):
+    """Zero-copy ingest (pipeline.cu plan_row_gather): the copy engine must gather every source row the letterbox resize
+    interpolates between -- checked against the oracle's restatement of OpenCV's INTER_LINEAR row mapping (cv_ops.py, B.1)
+    -- and nothing else, and the pattern must be periodic across contiguous frames."""
+    from oracle import cv_ops
+    w, h = size
+    plan = fdl.letterbox_row_plan(size, s)
+    assert plan is not None, "16:9 frames have a periodic row pattern"
+    row_pos, info = plan
+    # transform.rs:239-280 for roi = None: bordered square of side w (pad_v rows above and below), one resize to s
+    pad_v = int((1.0 - (h / w) / 1.0) / 2.0 * w)
+    y0, _, _ = cv_ops._resize_axis_coeffs(s, w, clamp_frac=False)
+    need = set()
+    for y in y0:
+        for r in (min(max(int(y), 0), w - 1), min(max(int(y) + 1, 0), w - 1)):
+            if 0 <= r - pad_v < h:
+                need.add(r - pad_v)
+    got = {r for r in range(h) if row_pos[r] >= 0}
+    assert got == need
+    # compact indices are a bijection onto 0..rows_per_frame-1, ascending with the source row
+    idx = [int(row_pos[r]) for r in sorted(got)]
+    assert idx == list(range(info["rows_per_frame"]))
+    assert info["period_src_rows"] * info["periods_per_frame"] == h      # continues seamlessly into the next frame
+    assert len(need) < 0.6 * h and 1 <= info["copies"] <= 8
+
+
+def test_letterbox_row_plan_declines_when_nothing_is_gained(fdl):
+    assert fdl.letterbox_row_plan((256, 256), 256) is None        # no resize at all
+    assert fdl.letterbox_row_plan((300, 200), 256) is None        # nearly every row is read
