@@ -426,3 +426,57 @@ def iris_roi_from_face_landmarks(lmks: np.ndarray, image_size):
         kps = [(l.x, l.y) for l in two]
         out.append(bbox_to_roi(bbox, image_size, kps, IRIS_ROI_SCALE, SQUARE_LONG))
     return out[0], out[1]
+
+
+# --------------------------------------------------------------------------------------------------
+# Iris refinement: iris_landmark.rs:64-95 index maps, :380-433 functions.
+LEFT_EYE_TO_FACE_LANDMARK_INDEX = np.array([  # iris_landmark.rs:64-78
+    33, 7, 163, 144, 145, 153, 154, 155, 133, 246, 161, 160, 159, 158, 157, 173,
+    130, 25, 110, 24, 23, 22, 26, 112, 243, 247, 30, 29, 27, 28, 56, 190,
+    226, 31, 228, 229, 230, 231, 232, 233, 244, 113, 225, 224, 223, 222, 221, 189,
+    35, 124, 46, 53, 52, 65, 143, 111, 117, 118, 119, 120, 121, 128, 245,
+    156, 70, 63, 105, 66, 107, 55, 193], np.int32)
+RIGHT_EYE_TO_FACE_LANDMARK_INDEX = np.array([  # iris_landmark.rs:80-95
+    263, 249, 390, 373, 374, 380, 381, 382, 362, 466, 388, 387, 386, 385, 384, 398,
+    359, 255, 339, 254, 253, 252, 256, 341, 463, 467, 260, 259, 257, 258, 286, 414,
+    446, 261, 448, 449, 450, 451, 452, 453, 464, 342, 445, 444, 443, 442, 441, 413,
+    265, 353, 276, 283, 282, 295, 372, 340, 346, 347, 348, 349, 350, 357, 465,
+    383, 300, 293, 334, 296, 336, 285, 417], np.int32)
+IRIS_SIZE_IN_MM = 11.8            # iris_landmark.rs:100
+IRIS_CENTER, IRIS_LEFT, IRIS_TOP, IRIS_RIGHT, IRIS_BOTTOM = range(5)   # iris_landmark.rs:104-110 `IrisIndex`
+NUM_FACE_LANDMARKS = 468
+
+
+def update_face_landmarks_with_iris_results(face_landmarks, left_contour, right_contour):
+    """iris_landmark.rs:380-398: contour point n of each eye replaces face landmark INDEX[n] (x, y and z)."""
+    face_landmarks = np.asarray(face_landmarks, np.float64)
+    if face_landmarks.shape[0] != NUM_FACE_LANDMARKS:
+        raise ValueError("unexpected number of items in face_landmarks")
+    refined = face_landmarks.copy()
+    left_contour, right_contour = np.asarray(left_contour, np.float64), np.asarray(right_contour, np.float64)
+    refined[LEFT_EYE_TO_FACE_LANDMARK_INDEX[:len(left_contour)]] = left_contour
+    refined[RIGHT_EYE_TO_FACE_LANDMARK_INDEX[:len(right_contour)]] = right_contour
+    return refined
+
+
+def get_iris_diameter(iris_landmarks, image_size) -> float:
+    """iris_landmark.rs:401-418: mean of the horizontal (Left-Right) and vertical (Top-Bottom) extents in pixels, f64."""
+    w, h = image_size
+    p = np.asarray(iris_landmarks, np.float64)
+
+    def dist(a, b):
+        x0, y0, x1, y1 = a[0] * float(w), a[1] * float(h), b[0] * float(w), b[1] * float(h)
+        return float(np.sqrt((x0 - x1) ** 2 + (y0 - y1) ** 2))
+
+    return (dist(p[IRIS_TOP], p[IRIS_BOTTOM]) + dist(p[IRIS_LEFT], p[IRIS_RIGHT])) / 2.0
+
+
+def get_iris_depth(iris_landmarks, focal_length_mm: float, iris_size_px: float, image_size) -> float:
+    """iris_landmark.rs:421-433.  The image centre is (width / 2, height / 2) with INTEGER division (:426)."""
+    w, h = image_size
+    c = np.asarray(iris_landmarks, np.float64)[IRIS_CENTER]
+    x0, y0 = float(int(w) // 2), float(int(h) // 2)
+    x1, y1 = c[0] * float(w), c[1] * float(h)
+    y = float(np.sqrt((x0 - x1) ** 2 + (y0 - y1) ** 2))
+    x = float(np.sqrt(float(focal_length_mm) ** 2 + y ** 2))
+    return IRIS_SIZE_IN_MM * x / float(iris_size_px)

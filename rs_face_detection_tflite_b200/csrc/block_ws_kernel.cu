@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "mma_kernels.cuh"
+#include "pdl.h"
 #include "plan.h"
 #include "sm100_ptx.cuh"
 
@@ -112,12 +113,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kMaxGroups);
   float* s_w = reinterpret_cast<float*>(smem + L.w);
 
-  int nb = a.B;
-  if (a.n_active) nb = min(nb, *a.n_active);
   const int tiles_per_img = a.tiles_x * a.tiles_y;
-  const int ntiles = nb * tiles_per_img;
-  if ((int)blockIdx.x >= ntiles) return;
-  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   const int CP = a.in_pad ? (((C >> 2) | 1) << 2) : C;   // pixel stride (floats) of the input tile in shared memory
   const uint32_t in_bytes = (uint32_t)(ITH * ITW * CP * 4);
@@ -130,7 +126,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     ptx::tma_load_4d(smem + L.in0 + s * L.in_stage, &tm_in, &in_full[s], 0, tx * TW - 1, ty * TH - 1, b);
   };
 
-  // ---- one-time setup ----
+  // ---- one-time setup: nothing here depends on the previous launch (PDL, see pdl.h) ----
   if (tid == 0) {
     ptx::prefetch_tmap(&tm_in);
     ptx::prefetch_tmap(&tm_out);
@@ -138,7 +134,6 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     for (int g = 0; g < G; ++g) { ptx::mbar_init(&a_full[g], (uint32_t)ndwg); ptx::mbar_init(&a_empty[g], 1); }
     for (int t = 0; t < T; ++t) { ptx::mbar_init(&acc_full[t], 1); ptx::mbar_init(&acc_empty[t], 4); }
     ptx::fence_mbar_init();
-    for (int it = 0; it < NS && it < my_tiles; ++it) issue_load(it);
   }
   if (warp == 0) ptx::tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   for (int i = tid; i < Np; i += blockDim.x) {
@@ -163,8 +158,18 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const int acc_cols = a.acc_cols;              // columns per accumulator buffer
+  pdl_launch_dependents();
+  pdl_wait();                                   // the previous launch's activations (and *n_active) are visible from here on
+  int nb = a.B;
+  if (a.n_active) nb = min(nb, *a.n_active);
+  const int ntiles = nb * tiles_per_img;
+  const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  if (tid == 0)
+    for (int it = 0; it < NS && it < my_tiles; ++it) issue_load(it);
 
-  if (warp < 4) {
+  if (my_tiles == 0) {
+    // nothing to do (fewer active items than CTAs)
+  } else if (warp < 4) {
     // ================= epilogue: TMEM -> (+skip, act) -> staging tile -> TMA store; refills the input ring =================
     // thread == TMEM lane == pixel.  Both the input tile (TMA load with a box wider than the tensor: the tail of each
     // pixel is zero-filled) and the output staging tile (TMA store with the same trick: the tail is clipped) have a
@@ -446,14 +451,15 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   const int ntiles = a.B * a.tiles_x * a.tiles_y;
   int grid = 148 * cfg.ctas;
   if (grid > ntiles) grid = ntiles;
-  if (cfg.ctas == 2) block_ws_kernel<320, 2><<<grid, cfg.threads, cfg.total, stream>>>(tm_in, tm_out, a);
-  else block_ws_kernel<512, 1><<<grid, cfg.threads, cfg.total, stream>>>(tm_in, tm_out, a);
+  cudaError_t e;
+  if (cfg.ctas == 2) e = launch_pdl(block_ws_kernel<320, 2>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
+  else e = launch_pdl(block_ws_kernel<512, 1>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
   count_launch();
   static const bool verbose = getenv("FDL_WS_VERBOSE") != nullptr;
   if (verbose)
     fprintf(stderr, "[ws C=%d N=%d %dx%d G=%d NS=%d ctas=%d thr=%d smem=%d in_pad=%d]\n", a.C, a.N, a.H, a.W, cfg.G, cfg.NS, cfg.ctas, cfg.threads, cfg.total,
             cfg.in_pad);
-  return cudaGetLastError();
+  return e;
 }
 
 }  // namespace fdl

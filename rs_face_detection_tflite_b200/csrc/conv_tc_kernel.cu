@@ -12,7 +12,10 @@
 // RELU / PRELU) writes straight to global memory, which also covers the aliased head outputs ([B,N,16] / [B,N,1]).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "mma_kernels.cuh"
+#include "pdl.h"
 #include "plan.h"
 #include "sm100_ptx.cuh"
 
@@ -23,16 +26,17 @@ void count_launch();
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int KC = 32;                               // K values per chunk
-constexpr int QC = KC / 4;                           // channel quads (A planes) per chunk
+// K values per chunk: KC = 4 * QC, QC = channel quads (A planes) per chunk.  Two instantiations: QC = 8 (32 K values per
+// chunk) and QC = 4 (16 per chunk: half the shared memory per CTA, so twice the CTAs per SM -- these CTAs are single
+// latency chains (gather -> planes -> MMA -> epilogue), and the SM hides the chain of one behind the others).
 constexpr int kPlaneBytes = 128 * 16 + 16;           // one A plane: 128 pixels x 16 B (+16 B bank skew)
-constexpr int kABytes = QC * kPlaneBytes;            // hi (or lo) planes of one chunk
 
 struct Layout { int bias, alpha, dw, a0, w0, a_stage, w_stage, total; };
 
 __host__ __device__ inline int align_up_c(int v, int a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline Layout layout(int Nt, int wsplit, int dw_c) {
+__host__ __device__ inline Layout layout(int Nt, int wsplit, int dw_c, int QC) {
+  const int kABytes = QC * kPlaneBytes;              // hi (or lo) planes of one chunk
   Layout L;
   int off = 64;
   L.bias = off; off += Nt * 4;
@@ -54,11 +58,16 @@ __device__ __forceinline__ void fma4(float4& a, const float4& x, const float4& w
   a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y); a.z = fmaf(x.z, w.z, a.z); a.w = fmaf(x.w, w.w, a.w);
 }
 
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
+template <int QC>
+__global__ void __launch_bounds__(kThreads, QC == 4 ? 3 : 0) conv_tc_kernel(const ConvTcArgs a) {
+  constexpr int KC = 4 * QC;                         // K values per chunk
+  constexpr int kABytes = QC * kPlaneBytes;          // hi (or lo) planes of one chunk
+  constexpr int PPT = QC / 2;                        // pixels per thread and chunk: 256 threads = (256 / QC) pixel slots x QC quads
+  constexpr int PSTEP = kThreads / QC;               // pixel slots
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int Nt = a.Nt;
-  const Layout L = layout(Nt, a.wsplit, a.mode == 1 ? a.in.C : 0);
+  const Layout L = layout(Nt, a.wsplit, a.mode == 1 ? a.in.C : 0, QC);
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem);           // [2]: chunk buffer free / all done
   uint64_t* w_bar = reinterpret_cast<uint64_t*>(smem + 16);        // [2]: weight chunk landed (bulk copy)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 48);
@@ -67,14 +76,11 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
   float* s_dw = reinterpret_cast<float*>(smem + L.dw);
 
   const int OHW = a.out.H * a.out.W;
-  int nb = a.B;
-  if (a.n_active) nb = min(nb, *a.n_active);
-  const long long M = (long long)nb * OHW;
   const long long m0 = (long long)blockIdx.x * 128;
-  if (m0 >= M) return;
   const int nt = blockIdx.y;                       // N tile
   const int n_base = nt * Nt;
 
+  // ---- prologue: nothing here depends on the previous launch (PDL, see pdl.h) ----
   if (tid == 0) {
     ptx::mbar_init(&mma_bar[0], 1);
     ptx::mbar_init(&mma_bar[1], 1);
@@ -97,15 +103,21 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();                                      // the previous launch's activations (and *n_active) are visible from here on
+  int nb = a.B;
+  if (a.n_active) nb = min(nb, *a.n_active);
+  const long long M = (long long)nb * OHW;
+  if (m0 < M) {                                    // CTA-uniform
 
-  // this thread's gather slots: quad j (fixed) of pixels p0 + 32*i
+  // this thread's gather slots: quad j (fixed) of pixels p0 + PSTEP*i
   const int j = tid & (QC - 1);
-  const int p0 = tid >> 3;
-  int pb[4], py[4], px[4];
-  bool pv[4];
+  const int p0 = tid / QC;
+  int pb[PPT], py[PPT], px[PPT];
+  bool pv[PPT];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    long long m = m0 + p0 + 32 * i;
+  for (int i = 0; i < PPT; ++i) {
+    long long m = m0 + p0 + PSTEP * i;
     pv[i] = m < M;
     long long mm = pv[i] ? m : 0;
     pb[i] = (int)(mm / OHW);
@@ -124,14 +136,14 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
   // im2col gather of one chunk into registers: all four 16-byte loads are issued back to back (branch-free), so
   // their latencies overlap; the loop below prefetches chunk c+1 while chunk c is converted, stored and multiplied.
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto gather_conv = [&](int c, float4 (&v)[4]) {
+  auto gather_conv = [&](int c, float4 (&v)[PPT]) {
     const int k = c * KC + 4 * j;
     const int kwc = a.kw * Cin;
     const int ky = k / kwc, r = k - ky * kwc;
     const int kx = r / Cin, ci = r - kx * Cin;
     const bool kok = k < a.K;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < PPT; ++i) {
       const int iy = py[i] * a.stride - a.pad_t + ky, ix = px[i] * a.stride - a.pad_l + kx;
       const bool ok = kok && pv[i] && iy >= 0 && iy < IH && ix >= 0 && ix < IW;
       const float4* ptr = reinterpret_cast<const float4*>(a.in.p + (long long)pb[i] * a.in.bstride + ((long long)iy * IW + ix) * Cin + ci);
@@ -139,7 +151,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
     }
   };
   // same for input channel counts that are not a multiple of 4 (the RGB stems): element-wise gather, 16 scalar loads
-  auto gather_scalar = [&](int c, float4 (&v)[4]) {
+  auto gather_scalar = [&](int c, float4 (&v)[PPT]) {
     const int k0 = c * KC + 4 * j;
     const int kwc = a.kw * Cin;
     int dy[4], dx[4], dc[4];
@@ -152,7 +164,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
       kok[e] = k < a.K;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < PPT; ++i) {
       const float* img = a.in.p + (long long)pb[i] * a.in.bstride;
       const int iy0 = py[i] * a.stride - a.pad_t, ix0 = px[i] * a.stride - a.pad_l;
       float t[4];
@@ -165,7 +177,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
       v[i] = make_float4(t[0], t[1], t[2], t[3]);
     }
   };
-  float4 pre[4];
+  float4 pre[PPT];
   if (a.mode == 0) gather_conv(0, pre);
   else if (a.mode == 2) gather_scalar(0, pre);
 
@@ -184,10 +196,10 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
     }
     // ---- the A chunk ----
     const int k = c * KC + 4 * j;                   // first K index of this thread's quad
-    float4 cur[4];
+    float4 cur[PPT];
     if (a.mode != 1) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) cur[i] = pre[i];
+      for (int i = 0; i < PPT; ++i) cur[i] = pre[i];
       if (c + 1 < nchunks) {
         if (a.mode == 0) gather_conv(c + 1, pre);
         else gather_scalar(c + 1, pre);
@@ -197,7 +209,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
       const bool kok = k < a.K;
       const float4 bdw = kok ? *reinterpret_cast<const float4*>(s_dw + 9 * Cin + k) : zero4;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < PPT; ++i) {
         const float* img = a.in.p + (long long)pb[i] * a.in.bstride + k;
         const int iy0 = py[i] * a.stride - a.pad_t, ix0 = px[i] * a.stride - a.pad_l;
         float4 t[9];
@@ -218,12 +230,12 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < PPT; ++i) {
       const float4 v = cur[i];
       float4 hi, lo;
       hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
       lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
-      const int p = p0 + 32 * i;
+      const int p = p0 + PSTEP * i;
       *reinterpret_cast<float4*>(s_a + j * kPlaneBytes + p * 16) = hi;
       *reinterpret_cast<float4*>(s_a + kABytes + j * kPlaneBytes + p * 16) = lo;
     }
@@ -276,10 +288,11 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
     // are read, so the batch costs one global-memory round trip instead of one per channel quad (this kernel runs the
     // small feature maps, where a CTA is a single latency chain).
     const bool vec_skip = sp && (a.skip.C & 3) == 0 && (a.skip_c & 3) == 0 && (N & 3) == 0;
-    for (int b0 = 0; b0 < Nt; b0 += 64) {
-      float4 sk[16];
+    constexpr int EB = QC == 4 ? 32 : 64;          // residual channels fetched per batch (register budget of the variant)
+    for (int b0 = 0; b0 < Nt; b0 += EB) {
+      float4 sk[EB / 4];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < EB / 4; ++j) {
         sk[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         const int ch = n_base + b0 + 4 * j;
         if (vec_skip && b0 + 4 * j < Nt && ch < a.skip_c) {
@@ -294,7 +307,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
         }
       }
 #pragma unroll
-      for (int cc = 0; cc < 64; cc += 16) {
+      for (int cc = 0; cc < EB; cc += 16) {
         const int c0 = b0 + cc;
         if (c0 >= Nt) break;
         float v[16];
@@ -337,6 +350,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
       }
     }
   }
+  }  // m0 < M
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
@@ -345,7 +359,9 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvTcArgs a) {
 }  // namespace
 
 cudaError_t conv_tc_init() {
-  return cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 }
 
 bool conv_tc_supported(const Step& s) {
@@ -356,7 +372,7 @@ bool conv_tc_supported(const Step& s) {
   if (s.in.offset != 0) return false;
   if (s.kind == STEP_BLOCK && (s.in.C > 256)) return false;
   if (s.skip.tensor >= 0 && s.skip.offset != 0) return false;
-  Layout L = layout(s.Nt, s.wsplit, s.kind == STEP_BLOCK ? s.in.C : 0);
+  Layout L = layout(s.Nt, s.wsplit, s.kind == STEP_BLOCK ? s.in.C : 0, 4);
   return L.total <= 200 * 1024;
 }
 
@@ -365,11 +381,22 @@ cudaError_t launch_conv_tc(const ConvTcArgs& a0, cudaStream_t stream) {
   a.tmem_cols = a.Nt <= 32 ? 32 : (a.Nt <= 64 ? 64 : 128);
   const long long M = (long long)a.B * a.out.H * a.out.W;
   if (M <= 0) return cudaSuccess;
-  Layout L = layout(a.Nt, a.wsplit, a.mode == 1 ? a.in.C : 0);
+  const int dw_c = a.mode == 1 ? a.in.C : 0;
+  const Layout L8 = layout(a.Nt, a.wsplit, dw_c, 8), L4 = layout(a.Nt, a.wsplit, dw_c, 4);
   dim3 grid((unsigned)((M + 127) / 128), (unsigned)a.n_tiles, 1);
-  conv_tc_kernel<<<grid, kThreads, L.total, stream>>>(a);
+  // Chunk size: 32 K-values per chunk unless that leaves CTAs waiting for a slot -- then 16 per chunk (half the shared
+  // memory, twice the resident CTAs).  FDL_CONV_QC = 4 / 8 forces one (A/B timing).
+  static const int qc_env = getenv("FDL_CONV_QC") ? atoi(getenv("FDL_CONV_QC")) : 0;
+  // resident CTAs per SM: shared memory, and registers (128 per thread -> 2 CTAs for <8>; 80 -> 3 for <4>, see __launch_bounds__)
+  auto per_sm = [](int smem, int reg_cap) { int n = (228 * 1024) / (smem + 1024); return n > reg_cap ? reg_cap : n; };
+  const long long ctas = (long long)grid.x * grid.y;
+  bool small = L8.total > 200 * 1024 || (ctas > 148LL * per_sm(L8.total, 2) && per_sm(L4.total, 3) > per_sm(L8.total, 2));
+  if (qc_env == 8 && L8.total <= 200 * 1024) small = false;
+  if (qc_env == 4) small = true;
+  cudaError_t e = small ? launch_pdl(conv_tc_kernel<4>, grid, dim3(kThreads), (size_t)L4.total, stream, a)
+                        : launch_pdl(conv_tc_kernel<8>, grid, dim3(kThreads), (size_t)L8.total, stream, a);
   count_launch();
-  return cudaGetLastError();
+  return e;
 }
 
 }  // namespace fdl

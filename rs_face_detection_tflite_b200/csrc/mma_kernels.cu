@@ -23,9 +23,11 @@
 #include <cudaTypedefs.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "mma_kernels.cuh"
+#include "pdl.h"
 #include "plan.h"
 #include "sm100_ptx.cuh"
 
@@ -37,7 +39,10 @@ bool encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, 
 namespace {
 
 constexpr int TH = 8, TW = 16;            // output tile: 128 pixels == UMMA M
-constexpr int kThreads = 192;             // 6 warps; warps 0..3 own the 128 TMEM lanes in the epilogue
+// CTA size: 6 warps.  A 12-warp variant for the one-CTA-per-SM configurations is kept for A/B timing (FDL_TC_THREADS=384):
+// measured no faster on B200 (the tile's latency chain, not the depthwise issue rate, bounds this serial kernel).
+// Warps 0..3 own the 128 TMEM lanes in the epilogue.
+constexpr int kThreadsSmall = 192, kThreadsBig = 384;
 constexpr int kPlanePad = 16;             // bytes added to each 2 KB channel-quad plane of A (bank spreading)
 constexpr int kPlaneBytes = TH * TW * 16 + kPlanePad;   // LBO of the A operand
 
@@ -49,13 +54,20 @@ __host__ __device__ inline int align_up_i(int v, int a) { return (v + a - 1) / a
 __host__ __device__ inline int in_tile_h(int S) { return (TH - 1) * S + 3; }
 __host__ __device__ inline int in_tile_w(int S) { return (TW - 1) * S + 3; }
 
+// Pixel strides of the input and the output staging tile in shared memory: an ODD number of 16-byte quads, so that the
+// epilogue's per-pixel 16-byte accesses (thread == pixel) spread over all banks instead of colliding 8-fold when the channel
+// count is a multiple of 32.  The TMA boxes are simply wider than the tensors: loads zero-fill the tail, stores clip it.
+// (Only when the quad count is a multiple of 4: that is where the collisions are 4- and 8-fold; for 6 or 7 quads the plain
+// stride is already within 2x of conflict-free and keeps the depthwise loads, which walk quads first, perfectly linear.)
+__host__ __device__ inline int pad_quads(int c) { return ((c >> 2) & 3) == 0 ? c + 4 : c; }
+
 __host__ __device__ inline SmemLayout smem_layout(int C, int N, int Np, int S, int stages, int wsplit, int alias_out) {
   SmemLayout L;
   int off = 64;                                   // barriers + tmem pointer
   L.bias = off; off += Np * 4;
   L.alpha = off; off += Np * 4;
   off = align_up_i(off, 128);
-  L.in_stage = align_up_i(in_tile_h(S) * in_tile_w(S) * C * 4, 128);
+  L.in_stage = align_up_i(in_tile_h(S) * in_tile_w(S) * pad_quads(C) * 4, 128);
   L.in0 = off; off += stages * L.in_stage;
   L.a_hi = off; off += (C / 4) * kPlaneBytes;
   L.a_lo = off; off += (C / 4) * kPlaneBytes;     // contiguous with a_hi (kPlaneBytes is a multiple of 16)
@@ -63,7 +75,7 @@ __host__ __device__ inline SmemLayout smem_layout(int C, int N, int Np, int S, i
   L.w = off; off += wsplit * (C / 4) * Np * 16;
   off = align_up_i(off, 128);
   if (alias_out) { L.out = L.a_hi; }              // the output tile reuses the A planes (dead once the MMA has completed)
-  else { L.out = off; off += TH * TW * N * 4; }
+  else { L.out = off; off += TH * TW * pad_quads(N) * 4; }
   L.total = align_up_i(off, 128);
   return L;
 }
@@ -77,8 +89,8 @@ __device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
-template <int S>
-__global__ void __launch_bounds__(kThreads) blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in,
+template <int S, int kThreads>
+__global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in,
                                                                   const __grid_constant__ CUtensorMap tm_out, const BlockTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int ITH = (TH - 1) * S + 3, ITW = (TW - 1) * S + 3;
@@ -95,13 +107,7 @@ __global__ void __launch_bounds__(kThreads) blaze_block_tc_kernel(const __grid_c
   float* s_w = reinterpret_cast<float*>(smem + L.w);
   float* s_out = reinterpret_cast<float*>(smem + L.out);
 
-  int nb = a.B;
-  if (a.n_active) nb = min(nb, *a.n_active);
-  const int tiles_per_img = a.tiles_x * a.tiles_y;
-  const int ntiles = nb * tiles_per_img;
-  if ((int)blockIdx.x >= ntiles) return;
-
-  // ---- one-time setup ----
+  // ---- one-time setup: nothing here depends on the previous launch (PDL, see pdl.h) ----
   if (tid == 0) {
     ptx::prefetch_tmap(&tm_in);
     ptx::prefetch_tmap(&tm_out);
@@ -133,15 +139,22 @@ __global__ void __launch_bounds__(kThreads) blaze_block_tc_kernel(const __grid_c
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();                                       // the previous launch's activations (and *n_active) are visible from here on
+  int nb = a.B;
+  if (a.n_active) nb = min(nb, *a.n_active);
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
+  const int ntiles = nb * tiles_per_img;
 
-  const uint32_t in_bytes = (uint32_t)(ITH * ITW * C * 4);
+  const int CP = pad_quads(C), NPf = pad_quads(N);   // pixel strides (floats) of the input / output staging tiles
+  const uint32_t in_bytes = (uint32_t)(ITH * ITW * CP * 4);
   auto issue_load = [&](int tile, int stage) {
     int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
     int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
     ptx::mbar_arrive_expect_tx(&full_bar[stage], in_bytes);
     ptx::tma_load_4d(smem + L.in0 + stage * L.in_stage, &tm_in, &full_bar[stage], 0, tx * TW * S - a.pad, ty * TH * S - a.pad, b);
   };
-  if (tid == 0) issue_load(blockIdx.x, 0);
+  if (tid == 0 && (int)blockIdx.x < ntiles) issue_load(blockIdx.x, 0);
 
   const uint32_t idesc = ptx::umma_idesc_tf32(128, Np);
   const uint32_t ahi_addr = ptx::smem_u32(s_ahi), alo_addr = ptx::smem_u32(s_alo), w_addr = ptx::smem_u32(s_w);
@@ -169,11 +182,11 @@ __global__ void __launch_bounds__(kThreads) blaze_block_tc_kernel(const __grid_c
       float4 acc[4];
 #pragma unroll
       for (int o = 0; o < 4; ++o) acc[o] = bd;
-      const float* base = s_in + ((half * 4 * S) * ITW + x * S) * C + 4 * q;
+      const float* base = s_in + ((half * 4 * S) * ITW + x * S) * CP + 4 * q;
 #pragma unroll
       for (int r = 0; r < 3 * S + 3; ++r) {          // input rows feeding 4 consecutive output rows
-        const float* rp = base + r * ITW * C;
-        float4 v0 = ld4(rp), v1 = ld4(rp + C), v2 = ld4(rp + 2 * C);
+        const float* rp = base + r * ITW * CP;
+        float4 v0 = ld4(rp), v1 = ld4(rp + CP), v2 = ld4(rp + 2 * CP);
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
           const int ky = r - o * S;
@@ -232,52 +245,87 @@ __global__ void __launch_bounds__(kThreads) blaze_block_tc_kernel(const __grid_c
       const int oy = ty * TH + py, ox = tx * TW + px;
       const bool inside = oy < a.H && ox < a.W;
       // residual sources inside the resident input tile: centre pixel (stride 1) / 2x2 window (stride 2, pad 0)
-      const float* skip_smem = S == 1 ? s_in + ((py + 1) * ITW + (px + 1)) * C : s_in + ((2 * py) * ITW + 2 * px) * C;
+      const float* skip_smem = S == 1 ? s_in + ((py + 1) * ITW + (px + 1)) * CP : s_in + ((2 * py) * ITW + 2 * px) * CP;
       const float* skip_g = nullptr;
       if ((a.skip_mode == 2 || a.skip_mode == 3) && inside) {
         if (a.skip_mode == 2) skip_g = a.skip + (long long)b * a.skip_bstride + ((long long)oy * a.W + ox) * a.skip_c;
         else skip_g = a.skip + (long long)b * a.skip_bstride + ((long long)(2 * oy) * (2 * a.W) + 2 * ox) * a.skip_c;
       }
-      for (int c0 = 0; c0 < Np; c0 += 16) {
-        float v[16];
-        ptx::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      if (a.skip_mode == 2 || a.skip_mode == 3) {
+        // Residuals that live in global memory (the bottleneck blocks of the iris net: skip != block input) are fetched 64
+        // channels at a time, ALL loads issued before the accumulator columns are read: one global round trip per batch
+        // instead of one per channel quad (the ncu source view had the epilogue's FADDs waiting on these loads one by one).
+        const long long rs = (long long)2 * a.W * a.skip_c;   // row stride of the MAX_POOL source (skip_mode 3)
+        for (int b0 = 0; b0 < Np; b0 += 64) {
+          float4 sk[16];
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const int n = c0 + j;
-          if (n >= N) break;
-          float o4[4];
+          for (int j = 0; j < 16; ++j) {
+            sk[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int n = b0 + 4 * j;
+            if (skip_g && a.skip_mode == 2 && n < a.skip_c) sk[j] = __ldg(reinterpret_cast<const float4*>(skip_g + n));
+          }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o4[e] = v[j + e] + s_bias[n + e];
-          if (n < a.skip_c) {
-            if (a.skip_mode == 1) {
-              float4 s = ld4(skip_smem + n);
-              o4[0] += s.x; o4[1] += s.y; o4[2] += s.z; o4[3] += s.w;
-            } else if (a.skip_mode == 4) {
-              float4 s = max4(max4(ld4(skip_smem + n), ld4(skip_smem + C + n)), max4(ld4(skip_smem + ITW * C + n), ld4(skip_smem + (ITW + 1) * C + n)));
-              o4[0] += s.x; o4[1] += s.y; o4[2] += s.z; o4[3] += s.w;
-            } else if (a.skip_mode == 2) {
-              if (skip_g) {
-                float4 s = __ldg(reinterpret_cast<const float4*>(skip_g + n));
-                o4[0] += s.x; o4[1] += s.y; o4[2] += s.z; o4[3] += s.w;
+          for (int cc = 0; cc < 64; cc += 16) {
+            const int c0 = b0 + cc;
+            if (c0 >= Np) break;
+            if (skip_g && a.skip_mode == 3) {     // MAX_POOL 2x2 source: four loads per quad -> 16 channels (16 loads) per round trip
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int n = c0 + 4 * j;
+                if (n < a.skip_c)
+                  sk[(cc >> 2) + j] = max4(max4(__ldg(reinterpret_cast<const float4*>(skip_g + n)), __ldg(reinterpret_cast<const float4*>(skip_g + a.skip_c + n))),
+                                           max4(__ldg(reinterpret_cast<const float4*>(skip_g + rs + n)), __ldg(reinterpret_cast<const float4*>(skip_g + rs + a.skip_c + n))));
               }
-            } else if (a.skip_mode == 3) {
-              if (skip_g) {
-                const long long rs = (long long)2 * a.W * a.skip_c;
-                float4 s = max4(max4(__ldg(reinterpret_cast<const float4*>(skip_g + n)), __ldg(reinterpret_cast<const float4*>(skip_g + a.skip_c + n))),
-                                max4(__ldg(reinterpret_cast<const float4*>(skip_g + rs + n)),
-                                     __ldg(reinterpret_cast<const float4*>(skip_g + rs + a.skip_c + n))));
+            }
+            float v[16];
+            ptx::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const int n = c0 + j;
+              if (n >= N) break;
+              const float4 s = sk[(cc + j) >> 2];
+              float o4[4] = {v[j] + s_bias[n] + s.x, v[j + 1] + s_bias[n + 1] + s.y, v[j + 2] + s_bias[n + 2] + s.z, v[j + 3] + s_bias[n + 3] + s.w};
+              if (a.act == ACT_RELU) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o4[e] = fmaxf(o4[e], 0.f);
+              } else if (a.act == ACT_PRELU) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o4[e] = o4[e] >= 0.f ? o4[e] : o4[e] * s_alpha[n + e];
+              }
+              *reinterpret_cast<float4*>(s_out + p * NPf + n) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            }
+          }
+        }
+      } else {
+        // residual inside the resident input tile (or none)
+        for (int c0 = 0; c0 < Np; c0 += 16) {
+          float v[16];
+          ptx::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const int n = c0 + j;
+            if (n >= N) break;
+            float o4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o4[e] = v[j + e] + s_bias[n + e];
+            if (n < a.skip_c) {
+              if (a.skip_mode == 1) {
+                float4 s = ld4(skip_smem + n);
+                o4[0] += s.x; o4[1] += s.y; o4[2] += s.z; o4[3] += s.w;
+              } else if (a.skip_mode == 4) {
+                float4 s = max4(max4(ld4(skip_smem + n), ld4(skip_smem + CP + n)), max4(ld4(skip_smem + ITW * CP + n), ld4(skip_smem + (ITW + 1) * CP + n)));
                 o4[0] += s.x; o4[1] += s.y; o4[2] += s.z; o4[3] += s.w;
               }
             }
-          }
-          if (a.act == ACT_RELU) {
+            if (a.act == ACT_RELU) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o4[e] = fmaxf(o4[e], 0.f);
-          } else if (a.act == ACT_PRELU) {
+              for (int e = 0; e < 4; ++e) o4[e] = fmaxf(o4[e], 0.f);
+            } else if (a.act == ACT_PRELU) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o4[e] = o4[e] >= 0.f ? o4[e] : o4[e] * s_alpha[n + e];
+              for (int e = 0; e < 4; ++e) o4[e] = o4[e] >= 0.f ? o4[e] : o4[e] * s_alpha[n + e];
+            }
+            *reinterpret_cast<float4*>(s_out + p * NPf + n) = make_float4(o4[0], o4[1], o4[2], o4[3]);
           }
-          *reinterpret_cast<float4*>(s_out + p * N + n) = make_float4(o4[0], o4[1], o4[2], o4[3]);
         }
       }
       ptx::fence_proxy_async_smem();
@@ -321,7 +369,7 @@ namespace {
 
 // Picks (stages, alias_out) for a block; returns false when it cannot fit in shared memory.
 bool pick_smem(int C, int N, int Np, int S, int wsplit, int* stages, int* alias_out, int* total) {
-  const bool can_alias = TH * TW * N * 4 <= 2 * (C / 4) * kPlaneBytes;
+  const bool can_alias = TH * TW * pad_quads(N) * 4 <= 2 * (C / 4) * kPlaneBytes;
   int best = -1, best_per_sm = 0;
   // candidate configurations in order of preference at equal occupancy
   const int cand[4][2] = {{2, 0}, {2, 1}, {1, 0}, {1, 1}};
@@ -330,7 +378,7 @@ bool pick_smem(int C, int N, int Np, int S, int wsplit, int* stages, int* alias_
     SmemLayout L = smem_layout(C, N, Np, S, cand[i][0], wsplit, cand[i][1]);
     if (L.total > kMaxSmemTc) continue;
     int per_sm = (228 * 1024) / (L.total + 1024);
-    if (per_sm > 3) per_sm = 3;
+    if (per_sm > 2) per_sm = 2;
     if (per_sm > best_per_sm) { best_per_sm = per_sm; best = i; }
   }
   if (best < 0) return false;
@@ -350,16 +398,18 @@ cudaError_t mma_kernels_init() {
     if (err == cudaSuccess && q == cudaDriverEntryPointSuccess) g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   });
   if (err != cudaSuccess) return err;
-  err = cudaFuncSetAttribute(blaze_block_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTc);
-  if (err != cudaSuccess) return err;
-  return cudaFuncSetAttribute(blaze_block_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTc);
+  err = cudaFuncSetAttribute(blaze_block_tc_kernel<1, kThreadsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTc);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(blaze_block_tc_kernel<2, kThreadsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTc);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(blaze_block_tc_kernel<1, kThreadsBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTc);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(blaze_block_tc_kernel<2, kThreadsBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemTc);
+  return err;
 }
 
 bool block_tc_supported(const Step& s) {
   if (s.kind != STEP_BLOCK || s.w_umma < 0) return false;
   if (s.stride != 1 && s.stride != 2) return false;
   const int C = s.in.C, N = s.out.C;
-  if (C % 8 != 0 || N % 4 != 0 || C < 16 || (kThreads % (C / 4)) != 0) return false;
+  if (C % 8 != 0 || N % 4 != 0 || C < 16 || (kThreadsSmall % (C / 4)) != 0 || (kThreadsBig % (C / 4)) != 0) return false;
   if (s.Np > 128 || s.out.H < TH || s.out.W < TW) return false;
   if (s.stride == 1 && (s.pad_t != 1 || s.pad_l != 1 || s.in.H != s.out.H || s.in.W != s.out.W)) return false;
   if (s.stride == 2 && (s.pad_t != 0 || s.pad_l != 0 || s.in.H != 2 * s.out.H || s.in.W != 2 * s.out.W)) return false;
@@ -379,21 +429,27 @@ cudaError_t launch_block_tc(const BlockTcLaunch& l, cudaStream_t stream) {
   if (!pick_smem(a.C, a.N, a.Np, S, a.wsplit, &a.stages, &a.alias_out, &total)) return cudaErrorInvalidConfiguration;
   a.pad = S == 1 ? 1 : 0;
   CUtensorMap tm_in, tm_out;
-  if (!encode_nhwc(&tm_in, l.in, a.B, a.H * S, a.W * S, a.C, (long long)a.H * S * a.W * S * a.C, in_tile_h(S), in_tile_w(S))) return cudaErrorInvalidValue;
-  if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW)) return cudaErrorInvalidValue;
+  if (!encode_nhwc(&tm_in, l.in, a.B, a.H * S, a.W * S, a.C, (long long)a.H * S * a.W * S * a.C, in_tile_h(S), in_tile_w(S), pad_quads(a.C)))
+    return cudaErrorInvalidValue;
+  if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW, pad_quads(a.N))) return cudaErrorInvalidValue;
   a.tiles_x = (a.W + TW - 1) / TW;
   a.tiles_y = (a.H + TH - 1) / TH;
   a.tmem_cols = a.Np <= 32 ? 32 : (a.Np <= 64 ? 64 : 128);
   const int ntiles = a.B * a.tiles_x * a.tiles_y;
   int per_sm = (228 * 1024) / (total + 1024);
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 3) per_sm = 3;
+  if (per_sm > 2) per_sm = 2;                       // 168 registers x 192 threads: two resident CTAs per SM
   int grid = 148 * per_sm;
   if (grid > ntiles) grid = ntiles;
-  if (S == 1) blaze_block_tc_kernel<1><<<grid, kThreads, total, stream>>>(tm_in, tm_out, a);
-  else blaze_block_tc_kernel<2><<<grid, kThreads, total, stream>>>(tm_in, tm_out, a);
+  static const int big_env = getenv("FDL_TC_THREADS") ? atoi(getenv("FDL_TC_THREADS")) : kThreadsSmall;   // 384 measured no faster (r01v)
+  const bool big = per_sm == 1 && big_env == kThreadsBig;
+  cudaError_t e;
+  if (S == 1 && big) e = launch_pdl(blaze_block_tc_kernel<1, kThreadsBig>, dim3(grid), dim3(kThreadsBig), (size_t)total, stream, tm_in, tm_out, a);
+  else if (S == 1) e = launch_pdl(blaze_block_tc_kernel<1, kThreadsSmall>, dim3(grid), dim3(kThreadsSmall), (size_t)total, stream, tm_in, tm_out, a);
+  else if (big) e = launch_pdl(blaze_block_tc_kernel<2, kThreadsBig>, dim3(grid), dim3(kThreadsBig), (size_t)total, stream, tm_in, tm_out, a);
+  else e = launch_pdl(blaze_block_tc_kernel<2, kThreadsSmall>, dim3(grid), dim3(kThreadsSmall), (size_t)total, stream, tm_in, tm_out, a);
   count_launch();
-  return cudaGetLastError();
+  return e;
 }
 
 }  // namespace fdl

@@ -11,6 +11,7 @@
 #include <cstdint>
 
 #include "net_kernels.cuh"
+#include "pdl.h"
 #include "plan.h"
 
 namespace fdl {
@@ -46,11 +47,18 @@ __global__ void __launch_bounds__(512) stem_conv_kernel(const ConvArgs a, const 
   float* s_w = sm;                              // [K][N]
   float* s_patch0 = sm + ((K * N + 3) & ~3);    // 2 x [PR][PCp]
 
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  // the weights do not depend on the previous launch: staged before the PDL wait (see pdl.h)
+  for (int i = tid; i < K * N; i += nthreads) {
+    int k = i / N, n = i - k * N;
+    s_w[i] = __ldg(a.w + (long long)k * a.Npad + n);
+  }
+  pdl_launch_dependents();
+  pdl_wait();
   int nb = a.B;
   if (a.n_active) nb = min(nb, *a.n_active);
   const int tiles_per_img = tiles_x * tiles_y;
   const int total = nb * tiles_per_img;
-  const int tid = threadIdx.x, nthreads = blockDim.x;
   if ((int)blockIdx.x >= total) return;
 
   const int row_floats = a.in.W * 3;
@@ -70,10 +78,6 @@ __global__ void __launch_bounds__(512) stem_conv_kernel(const ConvArgs a, const 
     cp_async_commit();
   };
   issue_patch(blockIdx.x, 0);
-  for (int i = tid; i < K * N; i += nthreads) {
-    int k = i / N, n = i - k * N;
-    s_w[i] = __ldg(a.w + (long long)k * a.Npad + n);
-  }
 
   const int G = kTileH * (TWo / 4);             // pixel groups per CTA (multiple of 32: the channel group is warp-uniform)
   const int g = tid % G, cg = tid / G;
@@ -197,10 +201,11 @@ cudaError_t launch_stem_conv(const ConvArgs& a, cudaStream_t stream) {
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stem_conv_kernel<3, 3, 0>, c.threads, c.smem);
   if (per_sm < 1) per_sm = 1;
   const unsigned grid = (unsigned)(total < 148LL * per_sm ? total : 148LL * per_sm);     // persistent CTAs
-  if (a.kh == 5) stem_conv_kernel<5, 5, 1><<<grid, c.threads, c.smem, stream>>>(a, c.TWo, c.tiles_x, c.tiles_y);
-  else stem_conv_kernel<3, 3, 0><<<grid, c.threads, c.smem, stream>>>(a, c.TWo, c.tiles_x, c.tiles_y);
+  cudaError_t e;
+  if (a.kh == 5) e = launch_pdl(stem_conv_kernel<5, 5, 1>, dim3(grid), dim3(c.threads), c.smem, stream, a, c.TWo, c.tiles_x, c.tiles_y);
+  else e = launch_pdl(stem_conv_kernel<3, 3, 0>, dim3(grid), dim3(c.threads), c.smem, stream, a, c.TWo, c.tiles_x, c.tiles_y);
   count_launch();
-  return cudaGetLastError();
+  return e;
 }
 
 }  // namespace fdl
