@@ -196,6 +196,23 @@ FDL_API int fdl_project_landmarks(int device, const float* raw, int n, int tenso
                                   int image_h, const double* padding4, const fdl_rect* roi, int flip_horizontal,
                                   fdl_landmark* out);
 
+/* update_face_landmarks_with_iris_results(face_landmarks, iris_left, iris_right) iris_landmark.rs:380-398
+ * (SURVEY.md 8f rank 1): contour point k of each eye replaces face landmark
+ * LEFT_/RIGHT_EYE_TO_FACE_LANDMARK_INDEX[k] (:64-95).  n must be 468 ("unexpected number of items in
+ * face_landmarks" -> FDL_ERR_INVALID); n_left / n_right <= 71.  refined: 468 entries. */
+FDL_API int fdl_update_face_landmarks_with_iris_results(int device, const fdl_landmark* face_landmarks, int n,
+                                                        const fdl_landmark* left_contour, int n_left,
+                                                        const fdl_landmark* right_contour, int n_right, fdl_landmark* refined);
+/* The two index maps themselves (host copy of the table the kernels use): out71[k] = face landmark index. */
+FDL_API int fdl_eye_to_face_landmark_index(int is_right_eye, int32_t* out71);
+/* get_iris_diameter(&iris_landmarks, image_size) iris_landmark.rs:401-418 (private in the reference): mean of the
+ * Left-Right and Top-Bottom extents in pixels.  iris: 5 entries in IrisIndex order (:104-110). */
+FDL_API int fdl_iris_diameter(int device, const fdl_landmark* iris, int n, int image_width, int image_height, double* diameter_px);
+/* get_iris_depth(iris_landmarks, focal_length_mm, iris_size_px, image_size) iris_landmark.rs:421-433 (private, unused
+ * in the reference): distance of the iris in mm from the 11.8 mm average human iris size. */
+FDL_API int fdl_iris_depth(int device, const fdl_landmark* iris, int n, double focal_length_mm, double iris_size_px,
+                           int image_width, int image_height, double* depth_mm);
+
 /* ---------------------------------------------------------------- generic network handle */
 /* A planned .tflite graph on one device (what replaces the TFLite interpreter). */
 FDL_API int fdl_net_create(const char* tflite_file, int device, fdl_net** out);
@@ -240,7 +257,9 @@ typedef struct fdl_pipeline_config {
   int32_t run_iris;         /* 0: stop after landmarks (config 4) */
   const char* model_dir;    /* directory holding the .tflite files; NULL -> "./models" */
   int32_t zero_copy_host;   /* 1: contiguous PINNED host frames are read in place by the kernels (no whole-frame H2D copy) */
-  int32_t _pad;
+  int32_t refine_landmarks; /* 1: also fill fdl_face_result.refined_landmarks (update_face_landmarks_with_iris_results,
+                               iris_landmark.rs:380-398) on the device; needs run_iris */
+  double focal_length_mm;   /* > 0: also fill iris_depth_mm (get_iris_depth, iris_landmark.rs:421-433) */
 } fdl_pipeline_config;
 
 /* Per-face result record. */
@@ -252,6 +271,10 @@ typedef struct fdl_face_result {
   fdl_rect eye_roi[2];               /* [0] = left (33,133), [1] = right (362,263) */
   float eye_contour[2][FDL_NUM_EYE_CONTOUR * 3];
   float iris[2][FDL_NUM_IRIS * 3];
+  /* iris refinement */
+  float refined_landmarks[FDL_NUM_FACE_LANDMARKS * 3];   /* landmarks with both eye contours scattered in (cfg.refine_landmarks) */
+  double iris_diameter_px[2];        /* get_iris_diameter per eye ([0] left, [1] right); 0 when the eye was not processed */
+  double iris_depth_mm[2];           /* get_iris_depth per eye; 0 unless cfg.focal_length_mm > 0 */
 } fdl_face_result;
 
 typedef struct fdl_frame_result {

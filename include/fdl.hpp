@@ -89,6 +89,28 @@ struct IrisResults {              // iris_landmark.rs:115-129
   std::vector<Landmark> eyeball_contour() const { return {contour.begin(), contour.begin() + 15}; }
 };
 
+// update_face_landmarks_with_iris_results (iris_landmark.rs:380-398)
+inline std::vector<Landmark> update_face_landmarks_with_iris_results(const std::vector<Landmark>& face_landmarks, const IrisResults& iris_data_left,
+                                                                     const IrisResults& iris_data_right, int device = 0) {
+  std::vector<Landmark> out(FDL_NUM_FACE_LANDMARKS);
+  check(fdl_update_face_landmarks_with_iris_results(device, face_landmarks.data(), (int)face_landmarks.size(), iris_data_left.contour.data(),
+                                                    (int)iris_data_left.contour.size(), iris_data_right.contour.data(),
+                                                    (int)iris_data_right.contour.size(), out.data()));
+  return out;
+}
+// get_iris_diameter / get_iris_depth (iris_landmark.rs:401-433; private in the reference)
+inline double get_iris_diameter(const std::vector<Landmark>& iris_landmarks, std::pair<int, int> image_size, int device = 0) {
+  double d = 0.0;
+  check(fdl_iris_diameter(device, iris_landmarks.data(), (int)iris_landmarks.size(), image_size.first, image_size.second, &d));
+  return d;
+}
+inline double get_iris_depth(const std::vector<Landmark>& iris_landmarks, double focal_length_mm, double iris_size_px, std::pair<int, int> image_size,
+                             int device = 0) {
+  double d = 0.0;
+  check(fdl_iris_depth(device, iris_landmarks.data(), (int)iris_landmarks.size(), focal_length_mm, iris_size_px, image_size.first, image_size.second, &d));
+  return d;
+}
+
 class IrisLandmark {              // iris_landmark.rs:131-248
  public:
   explicit IrisLandmark(std::optional<std::string> model_path = std::nullopt, int device = 0) {

@@ -465,8 +465,9 @@ def get_iris_diameter(iris_landmarks, image_size) -> float:
     p = np.asarray(iris_landmarks, np.float64)
 
     def dist(a, b):
-        x0, y0, x1, y1 = a[0] * float(w), a[1] * float(h), b[0] * float(w), b[1] * float(h)
-        return float(np.sqrt((x0 - x1) ** 2 + (y0 - y1) ** 2))
+        x0, y0, x1, y1 = float(a[0]) * float(w), float(a[1]) * float(h), float(b[0]) * float(w), float(b[1]) * float(h)
+        dx, dy = x0 - x1, y0 - y1
+        return math.sqrt(dx * dx + dy * dy)        # f64::powi(2) is an exact multiply (numpy's scalar ** 2 is not always)
 
     return (dist(p[IRIS_TOP], p[IRIS_BOTTOM]) + dist(p[IRIS_LEFT], p[IRIS_RIGHT])) / 2.0
 
@@ -476,7 +477,8 @@ def get_iris_depth(iris_landmarks, focal_length_mm: float, iris_size_px: float, 
     w, h = image_size
     c = np.asarray(iris_landmarks, np.float64)[IRIS_CENTER]
     x0, y0 = float(int(w) // 2), float(int(h) // 2)
-    x1, y1 = c[0] * float(w), c[1] * float(h)
-    y = float(np.sqrt((x0 - x1) ** 2 + (y0 - y1) ** 2))
-    x = float(np.sqrt(float(focal_length_mm) ** 2 + y ** 2))
+    x1, y1 = float(c[0]) * float(w), float(c[1]) * float(h)
+    dx, dy, f = x0 - x1, y0 - y1, float(focal_length_mm)
+    y = math.sqrt(dx * dx + dy * dy)
+    x = math.sqrt(f * f + y * y)
     return IRIS_SIZE_IN_MM * x / float(iris_size_px)

@@ -42,13 +42,16 @@ class CImage(C.Structure):
 class CPipelineConfig(C.Structure):
     _fields_ = [("detector_model", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_int32), ("max_faces", C.c_int32),
                 ("frame_width", C.c_int32), ("frame_height", C.c_int32), ("run_landmarks", C.c_int32), ("run_iris", C.c_int32),
-                ("model_dir", C.c_char_p), ("zero_copy_host", C.c_int32), ("_pad", C.c_int32)]
+                ("model_dir", C.c_char_p), ("zero_copy_host", C.c_int32), ("refine_landmarks", C.c_int32),
+                ("focal_length_mm", C.c_double)]
 
 
 class CFaceResult(C.Structure):
     _fields_ = [("face_roi", CRect), ("face_flag_logit", C.c_float), ("has_landmarks", C.c_int32),
                 ("landmarks", C.c_float * (NUM_FACE_LANDMARKS * 3)), ("eye_roi", CRect * 2),
-                ("eye_contour", (C.c_float * (NUM_EYE_CONTOUR * 3)) * 2), ("iris", (C.c_float * (NUM_IRIS * 3)) * 2)]
+                ("eye_contour", (C.c_float * (NUM_EYE_CONTOUR * 3)) * 2), ("iris", (C.c_float * (NUM_IRIS * 3)) * 2),
+                ("refined_landmarks", C.c_float * (NUM_FACE_LANDMARKS * 3)), ("iris_diameter_px", C.c_double * 2),
+                ("iris_depth_mm", C.c_double * 2)]
 
 
 class CFrameResult(C.Structure):
@@ -87,6 +90,11 @@ SYMBOLS = {
                                       _P(C.c_float), _P(C.c_uint8), _P(C.c_double)]),
     "fdl_project_landmarks": (C.c_int, [C.c_int, _P(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P(C.c_double), _P(CRect),
                                         C.c_int, _P(CLandmark)]),
+    "fdl_update_face_landmarks_with_iris_results": (C.c_int, [C.c_int, _P(CLandmark), C.c_int, _P(CLandmark), C.c_int, _P(CLandmark), C.c_int,
+                                                              _P(CLandmark)]),
+    "fdl_eye_to_face_landmark_index": (C.c_int, [C.c_int, _P(C.c_int32)]),
+    "fdl_iris_diameter": (C.c_int, [C.c_int, _P(CLandmark), C.c_int, C.c_int, C.c_int, _P(C.c_double)]),
+    "fdl_iris_depth": (C.c_int, [C.c_int, _P(CLandmark), C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, _P(C.c_double)]),
     "fdl_net_create": (C.c_int, [C.c_char_p, C.c_int, _P(_vp)]),
     "fdl_net_destroy": (None, [_vp]),
     "fdl_detector_net": (_vp, [_vp]),

@@ -412,6 +412,51 @@ def iris_roi_from_face_landmarks(face_landmarks, image_size, device: int = 0):
     return Rect._from(left), Rect._from(right)
 
 
+def _landmark_array(points):
+    """list[Landmark] / [n,3] array -> (CLandmark * n)."""
+    n = len(points)
+    arr = (CLandmark * max(n, 1))()
+    for i, l in enumerate(points):
+        if hasattr(l, "x"):
+            arr[i].x, arr[i].y, arr[i].z = l.x, l.y, l.z
+        else:
+            arr[i].x, arr[i].y, arr[i].z = float(l[0]), float(l[1]), float(l[2])
+    return arr, n
+
+
+def eye_to_face_landmark_index(is_right_eye: bool) -> np.ndarray:
+    """LEFT_/RIGHT_EYE_TO_FACE_LANDMARK_INDEX (iris_landmark.rs:64-95) as the library holds them."""
+    out = (C.c_int32 * _lib.NUM_EYE_CONTOUR)()
+    check(lib().fdl_eye_to_face_landmark_index(1 if is_right_eye else 0, out))
+    return np.array(out[:], np.int32)
+
+
+def update_face_landmarks_with_iris_results(face_landmarks, iris_data_left, iris_data_right, device: int = 0):
+    """iris_landmark.rs:380-398.  ``iris_data_*``: IrisResults (or a [<=71,3] contour array).  -> list[Landmark] (468)."""
+    face, n = _landmark_array(face_landmarks)
+    lc, nl = _landmark_array(iris_data_left.contour if isinstance(iris_data_left, IrisResults) else iris_data_left)
+    rc_, nr = _landmark_array(iris_data_right.contour if isinstance(iris_data_right, IrisResults) else iris_data_right)
+    out = (CLandmark * _lib.NUM_FACE_LANDMARKS)()
+    check(lib().fdl_update_face_landmarks_with_iris_results(device, face, n, lc, nl, rc_, nr, out))
+    return _landmarks(out, _lib.NUM_FACE_LANDMARKS)
+
+
+def get_iris_diameter(iris_landmarks, image_size, device: int = 0) -> float:
+    """iris_landmark.rs:401-418 (private in the reference): iris diameter in pixels."""
+    arr, n = _landmark_array(iris_landmarks)
+    out = C.c_double()
+    check(lib().fdl_iris_diameter(device, arr, n, int(image_size[0]), int(image_size[1]), C.byref(out)))
+    return out.value
+
+
+def get_iris_depth(iris_landmarks, focal_length_mm: float, iris_size_px: float, image_size, device: int = 0) -> float:
+    """iris_landmark.rs:421-433 (private in the reference): iris distance in millimetres."""
+    arr, n = _landmark_array(iris_landmarks)
+    out = C.c_double()
+    check(lib().fdl_iris_depth(device, arr, n, float(focal_length_mm), float(iris_size_px), int(image_size[0]), int(image_size[1]), C.byref(out)))
+    return out.value
+
+
 def image_to_tensor(image, roi: Rect | None, output_size, keep_aspect_ratio: bool, output_range=(0.0, 1.0), flip_horizontal: bool = False,
                     device: int = 0):
     """transform.rs:188-309 (private in the reference; exposed for parity checks).
@@ -453,6 +498,9 @@ class FaceResult:
     left_iris: np.ndarray | None          # [5,3]
     right_contour: np.ndarray | None
     right_iris: np.ndarray | None
+    refined_landmarks: np.ndarray | None = None   # [468,3]: update_face_landmarks_with_iris_results (Pipeline(refine_landmarks=True))
+    iris_diameter_px: tuple | None = None         # (left, right): get_iris_diameter
+    iris_depth_mm: tuple | None = None            # (left, right): get_iris_depth (Pipeline(focal_length_mm=...))
 
 
 @dataclass
@@ -466,11 +514,13 @@ class Pipeline:
 
     def __init__(self, detector_model: FaceDetectionModel = FaceDetectionModel.BackCamera, frame_size=(1920, 1080), max_batch: int = 64,
                  max_faces: int = 1, run_landmarks: bool = True, run_iris: bool = True, model_dir: str | None = None, device: int = 0,
-                 zero_copy_host: bool = False):
+                 zero_copy_host: bool = False, refine_landmarks: bool = False, focal_length_mm: float = 0.0):
         self._h = C.c_void_p()
         self._dir = os.fsencode(model_dir) if model_dir else None
         cfg = CPipelineConfig(int(detector_model), device, max_batch, max_faces, int(frame_size[0]), int(frame_size[1]),
-                              1 if run_landmarks else 0, 1 if (run_iris and run_landmarks) else 0, self._dir, 1 if zero_copy_host else 0, 0)
+                              1 if run_landmarks else 0, 1 if (run_iris and run_landmarks) else 0, self._dir, 1 if zero_copy_host else 0,
+                              1 if refine_landmarks else 0, float(focal_length_mm))
+        self.refine_landmarks, self.focal_length_mm = bool(refine_landmarks), float(focal_length_mm)
         check(lib().fdl_pipeline_create(C.byref(cfg), C.byref(self._h)))
         self.max_batch, self.max_faces = max_batch, max_faces
         self.frame_size = (int(frame_size[0]), int(frame_size[1]))
@@ -546,7 +596,10 @@ class Pipeline:
                 faces.append(FaceResult(Rect._from(c.face_roi), float(c.face_flag_logit), lm,
                                         Rect._from(c.eye_roi[0]) if has else None, Rect._from(c.eye_roi[1]) if has else None,
                                         g(c.eye_contour[0]) if iris_ok else None, g(c.iris[0]) if iris_ok else None,
-                                        g(c.eye_contour[1]) if iris_ok else None, g(c.iris[1]) if iris_ok else None))
+                                        g(c.eye_contour[1]) if iris_ok else None, g(c.iris[1]) if iris_ok else None,
+                                        g(c.refined_landmarks) if (iris_ok and self.refine_landmarks) else None,
+                                        (c.iris_diameter_px[0], c.iris_diameter_px[1]) if iris_ok else None,
+                                        (c.iris_depth_mm[0], c.iris_depth_mm[1]) if (iris_ok and self.focal_length_mm > 0) else None))
         return FrameResult(dets, faces)
 
     @property

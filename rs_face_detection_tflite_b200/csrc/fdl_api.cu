@@ -610,6 +610,67 @@ int fdl_iris_roi_from_face_landmarks(int device, const fdl_landmark* landmarks, 
   return FDL_OK;
 }
 
+int fdl_update_face_landmarks_with_iris_results(int device, const fdl_landmark* face_landmarks, int n, const fdl_landmark* left_contour, int n_left,
+                                                const fdl_landmark* right_contour, int n_right, fdl_landmark* refined) {
+  if (!face_landmarks || !refined || (n_left > 0 && !left_contour) || (n_right > 0 && !right_contour)) return set_error(FDL_ERR_INVALID, "null argument");
+  if (n != FDL_NUM_FACE_LANDMARKS) return set_error(FDL_ERR_INVALID, "unexpected number of items in face_landmarks");   // iris_landmark.rs:383-385
+  if (n_left < 0 || n_left > FDL_NUM_EYE_CONTOUR || n_right < 0 || n_right > FDL_NUM_EYE_CONTOUR)
+    return set_error(FDL_ERR_INVALID, "an eye contour has at most 71 points");
+  int rc = check_device(device);
+  if (rc) return rc;
+  static_assert(sizeof(fdl_landmark) == 3 * sizeof(double), "fdl_landmark is three packed doubles");
+  DevBuf<double> d;
+  const size_t nf = 3 * FDL_NUM_FACE_LANDMARKS, ne = 3 * FDL_NUM_EYE_CONTOUR;
+  FDL_CUDA_TRY(d.reserve(2 * nf + 2 * ne));
+  double *d_face = d.p, *d_left = d.p + nf, *d_right = d_left + ne, *d_out = d_right + ne;
+  FDL_CUDA_TRY(cudaMemcpy(d_face, face_landmarks, nf * sizeof(double), cudaMemcpyHostToDevice));
+  if (n_left) FDL_CUDA_TRY(cudaMemcpy(d_left, left_contour, (size_t)3 * n_left * sizeof(double), cudaMemcpyHostToDevice));
+  if (n_right) FDL_CUDA_TRY(cudaMemcpy(d_right, right_contour, (size_t)3 * n_right * sizeof(double), cudaMemcpyHostToDevice));
+  FDL_CUDA_TRY(launch_refine_landmarks(d_face, d_left, n_left, d_right, n_right, d_out, 0));
+  FDL_CUDA_TRY(cudaMemcpy(refined, d_out, nf * sizeof(double), cudaMemcpyDeviceToHost));
+  return FDL_OK;
+}
+
+int fdl_eye_to_face_landmark_index(int is_right_eye, int32_t* out71) {
+  if (!out71) return set_error(FDL_ERR_INVALID, "null argument");
+  for (int k = 0; k < FDL_NUM_EYE_CONTOUR; ++k) out71[k] = eye_to_face_landmark_index(is_right_eye ? 1 : 0, k);
+  return FDL_OK;
+}
+
+static int iris_metrics(int device, const fdl_landmark* iris, int n, double focal_length_mm, double iris_size_px, int w, int h, double* out2) {
+  if (!iris) return set_error(FDL_ERR_INVALID, "null argument");
+  if (n < FDL_NUM_IRIS) return set_error(FDL_ERR_INVALID, "iris landmarks must hold the 5 IrisIndex points");   // the reference indexes [0..4] and panics
+  if (w <= 0 || h <= 0) return set_error(FDL_ERR_INVALID, "image size must be positive");
+  int rc = check_device(device);
+  if (rc) return rc;
+  DevBuf<double> d;
+  FDL_CUDA_TRY(d.reserve(3 * FDL_NUM_IRIS + 2));
+  FDL_CUDA_TRY(cudaMemcpy(d.p, iris, 3 * FDL_NUM_IRIS * sizeof(double), cudaMemcpyHostToDevice));
+  FDL_CUDA_TRY(launch_iris_metrics(d.p, w, h, focal_length_mm, iris_size_px, d.p + 3 * FDL_NUM_IRIS, 0));
+  FDL_CUDA_TRY(cudaMemcpy(out2, d.p + 3 * FDL_NUM_IRIS, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+  return FDL_OK;
+}
+
+int fdl_iris_diameter(int device, const fdl_landmark* iris, int n, int image_width, int image_height, double* diameter_px) {
+  if (!diameter_px) return set_error(FDL_ERR_INVALID, "null argument");
+  double o[2];
+  int rc = iris_metrics(device, iris, n, 0.0, 0.0, image_width, image_height, o);
+  if (rc) return rc;
+  *diameter_px = o[0];
+  return FDL_OK;
+}
+
+int fdl_iris_depth(int device, const fdl_landmark* iris, int n, double focal_length_mm, double iris_size_px, int image_width, int image_height,
+                   double* depth_mm) {
+  if (!depth_mm) return set_error(FDL_ERR_INVALID, "null argument");
+  if (!(iris_size_px > 0.0)) return set_error(FDL_ERR_INVALID, "iris_size_px must be positive");
+  double o[2];
+  int rc = iris_metrics(device, iris, n, focal_length_mm, iris_size_px, image_width, image_height, o);
+  if (rc) return rc;
+  *depth_mm = o[1];
+  return FDL_OK;
+}
+
 int fdl_image_to_tensor(int device, const fdl_image* image, const fdl_rect* roi, int out_w, int out_h, int keep_aspect_ratio,
                         double range_min, double range_max, int flip_horizontal, float* out_tensor, uint8_t* out_u8, double* padding4) {
   if (!image || !out_tensor || out_w <= 0 || out_h <= 0) return set_error(FDL_ERR_INVALID, "bad arguments");

@@ -483,4 +483,41 @@ FDL_HD void project_point(const ProjectParams& p, const float* raw, float* out) 
   out[0] = x; out[1] = y; out[2] = z;
 }
 
+// ------------------------------------------------------------------------------------------------
+// iris refinement: iris_landmark.rs:64-95, :380-433
+// ------------------------------------------------------------------------------------------------
+// LEFT_/RIGHT_EYE_TO_FACE_LANDMARK_INDEX (iris_landmark.rs:64-95): eye contour point n of eye `eye`
+// (0 = left, 1 = right) replaces this face landmark in update_face_landmarks_with_iris_results (:380-398).
+FDL_HD int eye_to_face_landmark_index(int eye, int n) {
+  const int16_t kLeft[FDL_NUM_EYE_CONTOUR] = {
+      33,  7,   163, 144, 145, 153, 154, 155, 133, 246, 161, 160, 159, 158, 157, 173, 130, 25,  110, 24,  23,  22,  26,  112,
+      243, 247, 30,  29,  27,  28,  56,  190, 226, 31,  228, 229, 230, 231, 232, 233, 244, 113, 225, 224, 223, 222, 221, 189,
+      35,  124, 46,  53,  52,  65,  143, 111, 117, 118, 119, 120, 121, 128, 245, 156, 70,  63,  105, 66,  107, 55,  193};
+  const int16_t kRight[FDL_NUM_EYE_CONTOUR] = {
+      263, 249, 390, 373, 374, 380, 381, 382, 362, 466, 388, 387, 386, 385, 384, 398, 359, 255, 339, 254, 253, 252, 256, 341,
+      463, 467, 260, 259, 257, 258, 286, 414, 446, 261, 448, 449, 450, 451, 452, 453, 464, 342, 445, 444, 443, 442, 441, 413,
+      265, 353, 276, 283, 282, 295, 372, 340, 346, 347, 348, 349, 350, 357, 465, 383, 300, 293, 334, 296, 336, 285, 417};
+  return eye ? kRight[n] : kLeft[n];
+}
+// get_iris_diameter (iris_landmark.rs:401-418): iris = 5 x (x, y, z) normalised landmarks in IrisIndex order
+// (Center, Left, Top, Right, Bottom :104-110); the Landmark fields are f64 holding f32 values.
+template <typename T>
+FDL_HD double iris_diameter(const T* iris, int img_w, int img_h) {
+  const double w = (double)img_w, h = (double)img_h;
+  double dx = (double)iris[3 * 1] * w - (double)iris[3 * 3] * w, dy = (double)iris[3 * 1 + 1] * h - (double)iris[3 * 3 + 1] * h;
+  const double horiz = sqrt(dx * dx + dy * dy);                 // Left - Right
+  dx = (double)iris[3 * 2] * w - (double)iris[3 * 4] * w; dy = (double)iris[3 * 2 + 1] * h - (double)iris[3 * 4 + 1] * h;
+  const double vert = sqrt(dx * dx + dy * dy);                  // Top - Bottom
+  return (vert + horiz) / 2.0;
+}
+// get_iris_depth (iris_landmark.rs:421-433); the image centre is (width / 2, height / 2) in INTEGER arithmetic (:426).
+template <typename T>
+FDL_HD double iris_depth(const T* iris, double focal_length_mm, double iris_size_px, int img_w, int img_h) {
+  const double x0 = (double)(img_w / 2), y0 = (double)(img_h / 2);
+  const double x1 = (double)iris[0] * (double)img_w, y1 = (double)iris[1] * (double)img_h;
+  const double y = sqrt((x0 - x1) * (x0 - x1) + (y0 - y1) * (y0 - y1));
+  const double x = sqrt(focal_length_mm * focal_length_mm + y * y);
+  return 11.8 * x / iris_size_px;                               // IRIS_SIZE_IN_MM :100
+}
+
 }  // namespace fdl

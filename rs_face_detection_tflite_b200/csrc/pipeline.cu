@@ -317,7 +317,7 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
     // the reference reads the LAST element of the flag tensor (face_landmark.rs:292-293)
     FDL_CUDA_TRY(launch_landmark_post(raw.p, raw.bstride, flag.p + p->lmk->out_elems(1) - 1, flag.bstride, lane->face_params.p, lane->face_rois.p,
                                       lane->slot_frame.p, lane->slot_face.p, F, MF, p->LS, p->LS, lane->d_faces.p, lane->eye_rois.p,
-                                      lane->eye_frame.p, lane->eye_valid.p, n_faces, cs));
+                                      lane->eye_frame.p, lane->eye_valid.p, n_faces, cs, (p->iris && p->cfg.refine_landmarks) ? 1 : 0));
     FDL_CUDA_TRY(cudaEventRecord(p->guard[1], cs));
     if (p->iris) {
       // IrisLandmark::infer for both eyes: image_to_tensor(keep_aspect, (0,1), flip = right eye)
@@ -330,7 +330,8 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
       FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[7], cs));
       TView ec = p->iris->output_view(0, E), ir = p->iris->output_view(1, E);
       FDL_CUDA_TRY(launch_iris_post(ec.p, ec.bstride, ir.p, ir.bstride, lane->eye_params.p, lane->eye_rois.p, lane->eye_valid.p, lane->slot_frame.p,
-                                    lane->slot_face.p, E, MF, p->IS, p->IS, lane->d_faces.p, n_eyes, cs));
+                                    lane->slot_face.p, E, MF, p->IS, p->IS, lane->d_faces.p, n_eyes, cs, p->cfg.refine_landmarks ? 1 : 0,
+                                    p->cfg.focal_length_mm));
       FDL_CUDA_TRY(cudaEventRecord(p->guard[2], cs));
     } else {
       FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[6], cs));

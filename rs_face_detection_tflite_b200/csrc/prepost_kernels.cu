@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(128) landmark_post_kernel(const float* raw, lo
                                                             long long flag_bstride, const I2TParams* params, const fdl_rect* rois,
                                                             const int* slot_frame, const int* slot_face, int max_slots, int max_faces,
                                                             int tensor_w, int tensor_h, fdl_face_result* faces, fdl_rect* eye_rois,
-                                                            int* eye_frame, int* eye_valid, const int* n_faces) {
+                                                            int* eye_frame, int* eye_valid, const int* n_faces, int refine) {
   int s = blockIdx.x;
   if (s >= min(max_slots, *n_faces)) return;
   __shared__ ProjectParams pp;
@@ -555,14 +555,21 @@ __global__ void __launch_bounds__(128) landmark_post_kernel(const float* raw, lo
   }
   __syncthreads();
   if (!s_has) return;
-  for (int k = threadIdx.x; k < FDL_NUM_FACE_LANDMARKS; k += blockDim.x) project_point(pp, r + 3 * k, out->landmarks + 3 * k);
+  for (int k = threadIdx.x; k < FDL_NUM_FACE_LANDMARKS; k += blockDim.x) {
+    float q[3];
+    project_point(pp, r + 3 * k, q);
+    out->landmarks[3 * k] = q[0]; out->landmarks[3 * k + 1] = q[1]; out->landmarks[3 * k + 2] = q[2];
+    // update_face_landmarks_with_iris_results starts from a clone of the face landmarks (iris_landmark.rs:387); the eye
+    // contours are scattered over it by iris_post_kernel
+    if (refine) { out->refined_landmarks[3 * k] = q[0]; out->refined_landmarks[3 * k + 1] = q[1]; out->refined_landmarks[3 * k + 2] = q[2]; }
+  }
 }
 
 __global__ void __launch_bounds__(96) iris_post_kernel(const float* contour, long long contour_bstride, const float* iris,
                                                        long long iris_bstride, const I2TParams* params, const fdl_rect* eye_rois,
                                                        const int* eye_valid, const int* slot_frame, const int* slot_face,
                                                        int max_eye_slots, int max_faces, int tensor_w, int tensor_h,
-                                                       fdl_face_result* faces, const int* n_eyes) {
+                                                       fdl_face_result* faces, const int* n_eyes, int refine, double focal_length_mm) {
   int es = blockIdx.x;
   if (es >= min(max_eye_slots, *n_eyes)) return;
   if (!eye_valid[es]) return;
@@ -573,12 +580,53 @@ __global__ void __launch_bounds__(96) iris_post_kernel(const float* contour, lon
   fdl_face_result* out = &faces[(long long)slot_frame[s] * max_faces + slot_face[s]];
   if (threadIdx.x == 0) project_setup(tensor_w, tensor_h, P.src_w, P.src_h, P.pad, &eye_rois[es], e == 1, &pp);
   __syncthreads();
+  __shared__ float s_iris[FDL_NUM_IRIS * 3];
   int k = threadIdx.x;
-  if (k < FDL_NUM_EYE_CONTOUR) project_point(pp, contour + (long long)es * contour_bstride + 3 * k, out->eye_contour[e] + 3 * k);
-  else if (k < FDL_NUM_EYE_CONTOUR + FDL_NUM_IRIS) {
+  if (k < FDL_NUM_EYE_CONTOUR) {
+    float q[3];
+    project_point(pp, contour + (long long)es * contour_bstride + 3 * k, q);
+    float* dst = out->eye_contour[e] + 3 * k;
+    dst[0] = q[0]; dst[1] = q[1]; dst[2] = q[2];
+    if (refine) {
+      // update_face_landmarks_with_iris_results (iris_landmark.rs:389-396): contour point k replaces face landmark
+      // LEFT_/RIGHT_EYE_TO_FACE_LANDMARK_INDEX[k]; the two eyes' index sets are disjoint, so the two eye blocks of a
+      // face never write the same landmark
+      float* rl = out->refined_landmarks + 3 * eye_to_face_landmark_index(e, k);
+      rl[0] = q[0]; rl[1] = q[1]; rl[2] = q[2];
+    }
+  } else if (k < FDL_NUM_EYE_CONTOUR + FDL_NUM_IRIS) {
     int q = k - FDL_NUM_EYE_CONTOUR;
-    project_point(pp, iris + (long long)es * iris_bstride + 3 * q, out->iris[e] + 3 * q);
+    float v[3];
+    project_point(pp, iris + (long long)es * iris_bstride + 3 * q, v);
+    float* dst = out->iris[e] + 3 * q;
+    dst[0] = v[0]; dst[1] = v[1]; dst[2] = v[2];
+    s_iris[3 * q] = v[0]; s_iris[3 * q + 1] = v[1]; s_iris[3 * q + 2] = v[2];
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // get_iris_diameter / get_iris_depth (iris_landmark.rs:401-433) in image pixels / millimetres
+    const double d = iris_diameter(s_iris, P.src_w, P.src_h);
+    out->iris_diameter_px[e] = d;
+    out->iris_depth_mm[e] = focal_length_mm > 0.0 ? iris_depth(s_iris, focal_length_mm, d, P.src_w, P.src_h) : 0.0;
+  }
+}
+
+// Stand-alone forms of the refinement helpers (f64 Landmark values, as the reference's signatures).
+__global__ void refine_landmarks_kernel(const double* face, const double* left, int n_left, const double* right, int n_right, double* out) {
+  for (int k = threadIdx.x; k < 3 * FDL_NUM_FACE_LANDMARKS; k += blockDim.x) out[k] = face[k];
+  __syncthreads();
+  for (int k = threadIdx.x; k < n_left; k += blockDim.x) {
+    const int t = eye_to_face_landmark_index(0, k);
+    out[3 * t] = left[3 * k]; out[3 * t + 1] = left[3 * k + 1]; out[3 * t + 2] = left[3 * k + 2];
+  }
+  for (int k = threadIdx.x; k < n_right; k += blockDim.x) {
+    const int t = eye_to_face_landmark_index(1, k);
+    out[3 * t] = right[3 * k]; out[3 * t + 1] = right[3 * k + 1]; out[3 * t + 2] = right[3 * k + 2];
+  }
+}
+__global__ void iris_metrics_kernel(const double* iris, int img_w, int img_h, double focal_length_mm, double iris_size_px, double* out2) {
+  out2[0] = iris_diameter(iris, img_w, img_h);
+  out2[1] = iris_size_px > 0.0 ? iris_depth(iris, focal_length_mm, iris_size_px, img_w, img_h) : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -684,20 +732,30 @@ cudaError_t launch_face_roi(const fdl_frame_result* frames, const int* slot_fram
 cudaError_t launch_landmark_post(const float* raw, long long raw_bstride, const float* flag, long long flag_bstride,
                                  const I2TParams* params, const fdl_rect* rois, const int* slot_frame, const int* slot_face,
                                  int max_slots, int max_faces, int tensor_w, int tensor_h, fdl_face_result* faces, fdl_rect* eye_rois,
-                                 int* eye_frame, int* eye_valid, const int* n_faces, cudaStream_t s) {
+                                 int* eye_frame, int* eye_valid, const int* n_faces, cudaStream_t s, int refine) {
   if (max_slots <= 0) return cudaSuccess;
   landmark_post_kernel<<<max_slots, 128, 0, s>>>(raw, raw_bstride, flag, flag_bstride, params, rois, slot_frame, slot_face, max_slots,
-                                                 max_faces, tensor_w, tensor_h, faces, eye_rois, eye_frame, eye_valid, n_faces);
+                                                 max_faces, tensor_w, tensor_h, faces, eye_rois, eye_frame, eye_valid, n_faces, refine);
   return FDL_LAUNCHED();
 }
 
 cudaError_t launch_iris_post(const float* contour, long long contour_bstride, const float* iris, long long iris_bstride,
                              const I2TParams* params, const fdl_rect* eye_rois, const int* eye_valid, const int* slot_frame,
                              const int* slot_face, int max_eye_slots, int max_faces, int tensor_w, int tensor_h,
-                             fdl_face_result* faces, const int* n_eyes, cudaStream_t s) {
+                             fdl_face_result* faces, const int* n_eyes, cudaStream_t s, int refine, double focal_length_mm) {
   if (max_eye_slots <= 0) return cudaSuccess;
   iris_post_kernel<<<max_eye_slots, 96, 0, s>>>(contour, contour_bstride, iris, iris_bstride, params, eye_rois, eye_valid, slot_frame,
-                                                slot_face, max_eye_slots, max_faces, tensor_w, tensor_h, faces, n_eyes);
+                                                slot_face, max_eye_slots, max_faces, tensor_w, tensor_h, faces, n_eyes, refine, focal_length_mm);
+  return FDL_LAUNCHED();
+}
+cudaError_t launch_refine_landmarks(const double* face, const double* left, int n_left, const double* right, int n_right, double* out,
+                                    cudaStream_t s) {
+  refine_landmarks_kernel<<<1, 256, 0, s>>>(face, left, n_left, right, n_right, out);
+  return FDL_LAUNCHED();
+}
+cudaError_t launch_iris_metrics(const double* iris, int img_w, int img_h, double focal_length_mm, double iris_size_px, double* out2,
+                                cudaStream_t s) {
+  iris_metrics_kernel<<<1, 1, 0, s>>>(iris, img_w, img_h, focal_length_mm, iris_size_px, out2);
   return FDL_LAUNCHED();
 }
 

@@ -65,12 +65,17 @@ cudaError_t launch_face_roi(const fdl_frame_result* frames, const int* slot_fram
 cudaError_t launch_landmark_post(const float* raw, long long raw_bstride, const float* flag, long long flag_bstride,
                                  const I2TParams* params, const fdl_rect* rois, const int* slot_frame, const int* slot_face,
                                  int max_slots, int max_faces, int tensor_w, int tensor_h, fdl_face_result* faces, fdl_rect* eye_rois,
-                                 int* eye_frame, int* eye_valid, const int* n_faces, cudaStream_t s);
+                                 int* eye_frame, int* eye_valid, const int* n_faces, cudaStream_t s, int refine = 0);
 // Iris post-processing per eye slot: project 71 + 5 landmarks (flip for right eyes).
 cudaError_t launch_iris_post(const float* contour, long long contour_bstride, const float* iris, long long iris_bstride,
                              const I2TParams* params, const fdl_rect* eye_rois, const int* eye_valid, const int* slot_frame,
                              const int* slot_face, int max_eye_slots, int max_faces, int tensor_w, int tensor_h,
-                             fdl_face_result* faces, const int* n_eyes, cudaStream_t s);
+                             fdl_face_result* faces, const int* n_eyes, cudaStream_t s, int refine = 0, double focal_length_mm = 0.0);
+// Stand-alone iris refinement helpers (iris_landmark.rs:380-433) on f64 landmark triples.
+cudaError_t launch_refine_landmarks(const double* face, const double* left, int n_left, const double* right, int n_right, double* out,
+                                    cudaStream_t s);
+cudaError_t launch_iris_metrics(const double* iris, int img_w, int img_h, double focal_length_mm, double iris_size_px, double* out2,
+                                cudaStream_t s);
 
 // Stand-alone helpers behind the free functions of the C ABI (one thread each).
 cudaError_t launch_face_detection_to_roi(const fdl_detection* det, int img_w, int img_h, int size_mode, fdl_rect* out, int* ok,

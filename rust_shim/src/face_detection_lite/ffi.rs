@@ -27,6 +27,10 @@ extern "C" {
     pub fn fdl_iris_infer(m: *mut fdl_iris_model, image: *const fdl_image, roi: *const fdl_rect, is_right_eye: c_int, contour: *mut fdl_landmark, iris: *mut fdl_landmark) -> c_int;
     pub fn fdl_face_detection_to_roi(device: c_int, det: *const fdl_detection, w: c_int, h: c_int, size_mode: c_int, out: *mut fdl_rect) -> c_int;
     pub fn fdl_iris_roi_from_face_landmarks(device: c_int, lm: *const fdl_landmark, n: c_int, w: c_int, h: c_int, left: *mut fdl_rect, right: *mut fdl_rect) -> c_int;
+    pub fn fdl_update_face_landmarks_with_iris_results(device: c_int, face: *const fdl_landmark, n: c_int, left: *const fdl_landmark, n_left: c_int,
+                                                       right: *const fdl_landmark, n_right: c_int, refined: *mut fdl_landmark) -> c_int;
+    pub fn fdl_iris_diameter(device: c_int, iris: *const fdl_landmark, n: c_int, w: c_int, h: c_int, out: *mut f64) -> c_int;
+    pub fn fdl_iris_depth(device: c_int, iris: *const fdl_landmark, n: c_int, focal_length_mm: f64, iris_size_px: f64, w: c_int, h: c_int, out: *mut f64) -> c_int;
 }
 
 pub fn check(rc: c_int) -> Result<(), anyhow::Error> {

@@ -1,4 +1,5 @@
-//! iris_roi_from_face_landmarks, IrisLandmark::new / infer, IrisResults (reference iris_landmark.rs:115-292) over the C ABI.
+//! iris_roi_from_face_landmarks, IrisLandmark::new / infer, IrisResults, update_face_landmarks_with_iris_results and the iris
+//! diameter / depth helpers (reference iris_landmark.rs:115-433) over the C ABI.
 use super::{ffi, types::{Landmark, Rect}};
 use anyhow::Error;
 use opencv::core::Mat;
@@ -41,3 +42,32 @@ impl IrisLandmark {
     }
 }
 impl Drop for IrisLandmark { fn drop(&mut self) { unsafe { ffi::fdl_iris_destroy(self.handle) } } }
+
+fn to_c(v: &[Landmark]) -> Vec<ffi::fdl_landmark> { v.iter().map(|l| ffi::fdl_landmark { x: l.x, y: l.y, z: l.z }).collect() }
+
+/// Update face landmarks with iris detection results (reference iris_landmark.rs:380-398).
+pub fn update_face_landmarks_with_iris_results(
+    face_landmarks: Vec<Landmark>, iris_data_left: IrisResults, iris_data_right: IrisResults,
+) -> Result<Vec<Landmark>, Error> {
+    let (face, left, right) = (to_c(&face_landmarks), to_c(&iris_data_left.contour), to_c(&iris_data_right.contour));
+    let mut out = vec![ffi::fdl_landmark::default(); 468];
+    ffi::check(unsafe {
+        ffi::fdl_update_face_landmarks_with_iris_results(0, face.as_ptr(), face.len() as i32, left.as_ptr(), left.len() as i32, right.as_ptr(),
+                                                         right.len() as i32, out.as_mut_ptr())
+    })?;
+    Ok(out.iter().map(|l| Landmark { x: l.x, y: l.y, z: l.z }).collect())
+}
+
+/// Iris diameter in pixels (reference iris_landmark.rs:401-418; private there).
+pub fn get_iris_diameter(iris_landmarks: &Vec<Landmark>, image_size: (i32, i32)) -> Result<f64, Error> {
+    let (iris, mut d) = (to_c(iris_landmarks), 0.0f64);
+    ffi::check(unsafe { ffi::fdl_iris_diameter(0, iris.as_ptr(), iris.len() as i32, image_size.0, image_size.1, &mut d) })?;
+    Ok(d)
+}
+
+/// Iris depth in mm from the lens focal length in mm (reference iris_landmark.rs:421-433; private there).
+pub fn get_iris_depth(iris_landmarks: Vec<Landmark>, focal_length_mm: f64, iris_size_px: f64, image_size: (i32, i32)) -> Result<f64, Error> {
+    let (iris, mut d) = (to_c(&iris_landmarks), 0.0f64);
+    ffi::check(unsafe { ffi::fdl_iris_depth(0, iris.as_ptr(), iris.len() as i32, focal_length_mm, iris_size_px, image_size.0, image_size.1, &mut d) })?;
+    Ok(d)
+}

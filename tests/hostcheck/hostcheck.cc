@@ -97,4 +97,19 @@ void hc_project(const float* raw, int n, int tw, int th, int iw, int ih, const d
   project_setup(tw, th, iw, ih, pad4, roi, flip != 0, &pp);
   for (int k = 0; k < n; ++k) project_point(pp, raw + 3 * k, out + 3 * k);
 }
+
+// iris refinement helpers (iris_landmark.rs:64-95, :401-433) through the same header functions the kernels call
+int hc_eye_index(int eye, int* out71) {
+  for (int k = 0; k < FDL_NUM_EYE_CONTOUR; ++k) out71[k] = eye_to_face_landmark_index(eye, k);
+  return FDL_NUM_EYE_CONTOUR;
+}
+void hc_iris_metrics(const double* iris15, int w, int h, double focal, double* out2) {
+  out2[0] = iris_diameter(iris15, w, h);
+  out2[1] = iris_depth(iris15, focal, out2[0], w, h);
+}
+void hc_iris_metrics_f32(const float* iris15, int w, int h, double focal, double* out2) {
+  out2[0] = iris_diameter(iris15, w, h);
+  out2[1] = iris_depth(iris15, focal, out2[0], w, h);
+}
+
 }

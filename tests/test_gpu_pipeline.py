@@ -159,3 +159,63 @@ def test_detection_only_pipeline_and_errors(fdl, gpu):
         fdl.FaceLandmark("/nonexistent/face_landmark.tflite", device=gpu)
     assert e.value.code == -2
     pipe.close(); det.close()
+
+
+# ---- iris refinement: iris_landmark.rs:380-433 -----------------------------------------------------
+def test_iris_refinement_free_functions(fdl, gpu):
+    """update_face_landmarks_with_iris_results / get_iris_diameter / get_iris_depth through the C ABI (evaluated on the
+    device) == the oracle, bit for bit (pure index scatter and f64 arithmetic), plus the reference's error case."""
+    from conftest import rng
+    from oracle import glue
+    r = rng(21)
+    face, left, right = r.random((468, 3)), r.random((71, 3)) + 2, r.random((71, 3)) + 4
+    mk = lambda a: [fdl.Landmark(*map(float, p)) for p in a]
+    out = fdl.update_face_landmarks_with_iris_results(mk(face), fdl.IrisResults(mk(left), mk(left[:5])), fdl.IrisResults(mk(right), mk(right[:5])),
+                                                      device=gpu)
+    ref = glue.update_face_landmarks_with_iris_results(face, left, right)
+    np.testing.assert_array_equal(np.array([[l.x, l.y, l.z] for l in out]), ref)
+    with pytest.raises(fdl.FdlError) as e:
+        fdl.update_face_landmarks_with_iris_results(mk(face[:100]), left, right, device=gpu)
+    assert "unexpected number of items in face_landmarks" in e.value.message      # iris_landmark.rs:383-385
+    for (w, h) in ((540, 360), (1920, 1080), (641, 479)):
+        for _ in range(5):
+            iris = r.random((5, 3)).astype(np.float32).astype(np.float64)
+            d = fdl.get_iris_diameter(iris, (w, h), device=gpu)
+            assert d == glue.get_iris_diameter(iris, (w, h))
+            assert fdl.get_iris_depth(iris, 4.3, d, (w, h), device=gpu) == glue.get_iris_depth(iris, 4.3, d, (w, h))
+    with pytest.raises(fdl.FdlError):
+        fdl.get_iris_diameter(np.zeros((3, 3)), (10, 10), device=gpu)             # the reference indexes [0..4] and panics
+
+
+def test_pipeline_refined_landmarks_and_iris_metrics(fdl, gpu, man, oracle_pipeline):
+    """Pipeline(refine_landmarks, focal_length_mm): the on-device scatter and metrics against the oracle applied (a) to the
+    pipeline's own landmarks (exact) and (b) to the oracle pipeline's landmarks (0.5 px / 2 %)."""
+    import synth_frames
+    from oracle import glue
+    op = oracle_pipeline[glue.BACK_CAMERA]
+    focal = 4.3
+    for frames, (w, h) in ((np.stack([man, man]), (man.shape[1], man.shape[0])), (synth_frames.face_frames(3), (1920, 1080))):
+        pipe = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (w, h), max_batch=4, max_faces=1, model_dir=MODELS, device=gpu,
+                            refine_landmarks=True, focal_length_mm=focal)
+        plain = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (w, h), max_batch=4, max_faces=1, model_dir=MODELS, device=gpu)
+        res, res0 = pipe.run(frames), plain.run(frames)
+        for i, (fr, fr0) in enumerate(zip(res, res0)):
+            f, f0 = fr.faces[0], fr0.faces[0]
+            assert f.landmarks is not None and f0.refined_landmarks is None and f0.iris_depth_mm is None
+            np.testing.assert_array_equal(f.landmarks, f0.landmarks)               # the raw landmarks are untouched by the refinement
+            # (a) exact: scatter of its own contours over its own landmarks; metrics of its own iris points
+            np.testing.assert_array_equal(f.refined_landmarks,
+                                          glue.update_face_landmarks_with_iris_results(f.landmarks, f.left_contour, f.right_contour).astype(np.float32))
+            for e, ir in enumerate((f.left_iris, f.right_iris)):
+                d = glue.get_iris_diameter(ir.astype(np.float64), (w, h))
+                assert f.iris_diameter_px[e] == d and f0.iris_diameter_px[e] == d
+                assert f.iris_depth_mm[e] == glue.get_iris_depth(ir.astype(np.float64), focal, d, (w, h))
+            # (b) against the oracle's own pipeline
+            _, ref = op.run(frames[i])
+            rl = glue.update_face_landmarks_with_iris_results(ref[0]["landmarks"], ref[0]["left"][0], ref[0]["right"][0])
+            assert np.abs(_px(f.refined_landmarks, w, h) - _px(rl, w, h)).max() < 0.5
+            for e, key in enumerate(("left", "right")):
+                d = glue.get_iris_diameter(ref[0][key][1], (w, h))
+                assert abs(f.iris_diameter_px[e] - d) < 0.5
+                assert abs(f.iris_depth_mm[e] / glue.get_iris_depth(ref[0][key][1], focal, d, (w, h)) - 1) < 0.02
+        pipe.close(); plain.close()

@@ -36,7 +36,8 @@ def test_struct_layouts_match_header(fdl):
     assert C.sizeof(_lib.CRect) == 48 and C.sizeof(_lib.CDetection) == 72 and C.sizeof(_lib.CLandmark) == 24
     assert C.sizeof(_lib.CImage) == 32
     assert C.sizeof(_lib.CFrameResult) == 8 + 32 * 72
-    assert C.sizeof(_lib.CFaceResult) == 48 + 8 + 468 * 12 + 96 + 2 * 71 * 12 + 2 * 5 * 12
+    assert C.sizeof(_lib.CFaceResult) == 48 + 8 + 468 * 12 + 96 + 2 * 71 * 12 + 2 * 5 * 12 + 468 * 12 + 16 + 16
+    assert C.sizeof(_lib.CPipelineConfig) == 8 * 4 + 8 + 2 * 4 + 8
 
 
 @pytest.mark.skipif("torch.cuda.is_available()", reason="checks the no-GPU error path")
@@ -256,3 +257,66 @@ def test_letterbox_row_plan_covers_exactly_the_rows_opencv_reads(fdl, size, s):
 def test_letterbox_row_plan_declines_when_nothing_is_gained(fdl):
     assert fdl.letterbox_row_plan((256, 256), 256) is None        # no resize at all
     assert fdl.letterbox_row_plan((300, 200), 256) is None        # nearly every row is read
+
+
+# ---- iris refinement: index maps, diameter, depth -------------------------------------------------
+def test_eye_to_face_landmark_index_tables(fdl):
+    """The oracle's tables, the library's host copy and the header the kernels use agree; when the reference tree is
+    present (this container, not the GPU box) they are also checked against iris_landmark.rs:64-95 itself."""
+    from oracle import glue
+    import hostcheck
+    hc = hostcheck.load()
+    for eye, tab in ((0, glue.LEFT_EYE_TO_FACE_LANDMARK_INDEX), (1, glue.RIGHT_EYE_TO_FACE_LANDMARK_INDEX)):
+        out = (C.c_int * 71)()
+        assert hc.hc_eye_index(eye, out) == 71
+        np.testing.assert_array_equal(np.array(out[:]), tab)
+        np.testing.assert_array_equal(fdl.eye_to_face_landmark_index(bool(eye)), tab)
+    assert not set(glue.LEFT_EYE_TO_FACE_LANDMARK_INDEX) & set(glue.RIGHT_EYE_TO_FACE_LANDMARK_INDEX)
+    ref = "/root/reference/src/face_detection_lite/iris_landmark.rs"
+    if os.path.exists(ref):
+        src = open(ref).read()
+        for name, tab in (("LEFT_EYE_TO_FACE_LANDMARK_INDEX", glue.LEFT_EYE_TO_FACE_LANDMARK_INDEX),
+                          ("RIGHT_EYE_TO_FACE_LANDMARK_INDEX", glue.RIGHT_EYE_TO_FACE_LANDMARK_INDEX)):
+            body = re.search(name + r": \[i32; 71\] = \[(.*?)\];", src, re.S).group(1)
+            vals = [int(v) for v in re.findall(r"\d+", re.sub(r"//[^\n]*", "", body))]
+            np.testing.assert_array_equal(np.array(vals), tab)
+
+
+def test_oracle_update_face_landmarks_with_iris_results():
+    from oracle import glue
+    r = rng(5)
+    face, left, right = r.random((468, 3)), r.random((71, 3)) + 2, r.random((71, 3)) + 4
+    out = glue.update_face_landmarks_with_iris_results(face, left, right)
+    li, ri = glue.LEFT_EYE_TO_FACE_LANDMARK_INDEX, glue.RIGHT_EYE_TO_FACE_LANDMARK_INDEX
+    np.testing.assert_array_equal(out[li], left)
+    np.testing.assert_array_equal(out[ri], right)
+    rest = np.setdiff1d(np.arange(468), np.concatenate([li, ri]))
+    assert len(rest) == 468 - 142
+    np.testing.assert_array_equal(out[rest], face[rest])
+    with pytest.raises(ValueError):
+        glue.update_face_landmarks_with_iris_results(face[:100], left, right)
+
+
+def test_iris_metrics_host_math_matches_oracle():
+    """iris_diameter / iris_depth of csrc/glue_math.h (compiled for the host) == the oracle's f64 restatement, bit for bit,
+    including the integer image centre of iris_landmark.rs:426 on odd sizes."""
+    from oracle import glue
+    import hostcheck
+    hc = hostcheck.load()
+    r = rng(11)
+    for (w, h) in ((540, 360), (1920, 1080), (641, 479)):
+        for _ in range(20):
+            iris = r.random((5, 3)).astype(np.float32)
+            d = glue.get_iris_diameter(iris.astype(np.float64), (w, h))
+            z = glue.get_iris_depth(iris.astype(np.float64), 4.3, d, (w, h))
+            out = (C.c_double * 2)()
+            hc.hc_iris_metrics_f32(iris.ctypes.data_as(C.POINTER(C.c_float)), w, h, C.c_double(4.3), out)
+            assert (out[0], out[1]) == (d, z)
+            i64 = np.ascontiguousarray(iris, np.float64)
+            hc.hc_iris_metrics(i64.ctypes.data_as(C.POINTER(C.c_double)), w, h, C.c_double(4.3), out)
+            assert (out[0], out[1]) == (d, z)
+    # closed form: a 10 px wide, 6 px high iris centred on the image centre, focal length f -> depth = 11.8 * f / 8
+    w, h = 200, 100
+    iris = np.array([[0.5, 0.5, 0], [0.475, 0.5, 0], [0.5, 0.47, 0], [0.525, 0.5, 0], [0.5, 0.53, 0]])
+    assert abs(glue.get_iris_diameter(iris, (w, h)) - 8.0) < 1e-12
+    assert abs(glue.get_iris_depth(iris, 5.0, 8.0, (w, h)) - 11.8 * 5.0 / 8.0) < 1e-12
