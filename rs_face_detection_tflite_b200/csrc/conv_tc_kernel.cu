@@ -181,18 +181,28 @@ __global__ void __launch_bounds__(kThreads, QC == 4 ? 3 : 0) conv_tc_kernel(cons
   if (a.mode == 0) gather_conv(0, pre);
   else if (a.mode == 2) gather_scalar(0, pre);
 
+  // Weights of a chunk: already in UMMA order in global memory -> one or two bulk async copies, requested ONE CHUNK AHEAD
+  // (a CTA is a single latency chain; a load requested in the iteration that needs it costs a full L2 round trip per chunk).
+  auto issue_w = [&](int c) {
+    const int wb = c & 1;
+    float4* dst = reinterpret_cast<float4*>(smem + L.w0 + wb * L.w_stage);
+    const uint32_t bytes = (uint32_t)w4_per_chunk * 16u;
+    ptx::mbar_arrive_expect_tx(&w_bar[wb], bytes * (uint32_t)a.wsplit);
+    ptx::bulk_load_1d(dst, wsrc + (size_t)c * w4_per_chunk, bytes, &w_bar[wb]);
+    if (a.wsplit == 2) ptx::bulk_load_1d(dst + w4_per_chunk, wsrc + w4_lo_off + (size_t)c * w4_per_chunk, bytes, &w_bar[wb]);
+  };
+  if (tid == 0) issue_w(0);
+
   for (int c = 0; c < nchunks; ++c) {
     const int buf = c & 1;
     // the MMAs that read this buffer two chunks ago must have completed
     if (c >= 2) ptx::mbar_wait(&mma_bar[buf], (uint32_t)(((c >> 1) - 1) & 1));
     uint8_t* s_a = smem + L.a0 + buf * L.a_stage;
     float4* s_w = reinterpret_cast<float4*>(smem + L.w0 + buf * L.w_stage);
-    // ---- weights of this chunk: already in UMMA order in global memory -> one or two bulk async copies ----
-    if (tid == 0) {
-      const uint32_t bytes = (uint32_t)w4_per_chunk * 16u;
-      ptx::mbar_arrive_expect_tx(&w_bar[buf], bytes * (uint32_t)a.wsplit);
-      ptx::bulk_load_1d(s_w, wsrc + (size_t)c * w4_per_chunk, bytes, &w_bar[buf]);
-      if (a.wsplit == 2) ptx::bulk_load_1d(s_w + w4_per_chunk, wsrc + w4_lo_off + (size_t)c * w4_per_chunk, bytes, &w_bar[buf]);
+    if (tid == 0 && c + 1 < nchunks) {
+      // the other weight buffer was last read by the MMAs of chunk c-1 (issued a moment ago by this thread)
+      if (c >= 1) ptx::mbar_wait(&mma_bar[buf ^ 1], (uint32_t)(((c - 1) >> 1) & 1));
+      issue_w(c + 1);
     }
     // ---- the A chunk ----
     const int k = c * KC + 4 * j;                   // first K index of this thread's quad
