@@ -449,7 +449,7 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
     while (a.tmem_cols < need) a.tmem_cols *= 2;
   }
   const int ntiles = a.B * a.tiles_x * a.tiles_y;
-  int grid = 148 * cfg.ctas;
+  int grid = persist_sms() * cfg.ctas;
   if (grid > ntiles) grid = ntiles;
   cudaError_t e;
   if (cfg.ctas == 2) e = launch_pdl(block_ws_kernel<320, 2>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);

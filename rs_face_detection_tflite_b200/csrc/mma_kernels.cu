@@ -61,13 +61,13 @@ __host__ __device__ inline int in_tile_w(int S) { return (TW - 1) * S + 3; }
 // stride is already within 2x of conflict-free and keeps the depthwise loads, which walk quads first, perfectly linear.)
 __host__ __device__ inline int pad_quads(int c) { return ((c >> 2) & 3) == 0 ? c + 4 : c; }
 
-__host__ __device__ inline SmemLayout smem_layout(int C, int N, int Np, int S, int stages, int wsplit, int alias_out) {
+__host__ __device__ inline SmemLayout smem_layout(int C, int N, int Np, int S, int stages, int wsplit, int alias_out, int CP, int NP) {
   SmemLayout L;
   int off = 64;                                   // barriers + tmem pointer
   L.bias = off; off += Np * 4;
   L.alpha = off; off += Np * 4;
   off = align_up_i(off, 128);
-  L.in_stage = align_up_i(in_tile_h(S) * in_tile_w(S) * pad_quads(C) * 4, 128);
+  L.in_stage = align_up_i(in_tile_h(S) * in_tile_w(S) * CP * 4, 128);
   L.in0 = off; off += stages * L.in_stage;
   L.a_hi = off; off += (C / 4) * kPlaneBytes;
   L.a_lo = off; off += (C / 4) * kPlaneBytes;     // contiguous with a_hi (kPlaneBytes is a multiple of 16)
@@ -75,7 +75,7 @@ __host__ __device__ inline SmemLayout smem_layout(int C, int N, int Np, int S, i
   L.w = off; off += wsplit * (C / 4) * Np * 16;
   off = align_up_i(off, 128);
   if (alias_out) { L.out = L.a_hi; }              // the output tile reuses the A planes (dead once the MMA has completed)
-  else { L.out = off; off += TH * TW * pad_quads(N) * 4; }
+  else { L.out = off; off += TH * TW * NP * 4; }
   L.total = align_up_i(off, 128);
   return L;
 }
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
   constexpr int ITH = (TH - 1) * S + 3, ITW = (TW - 1) * S + 3;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int C = a.C, N = a.N, Np = a.Np, Q = C >> 2;
-  const SmemLayout L = smem_layout(C, N, Np, S, a.stages, a.wsplit, a.alias_out);
+  const SmemLayout L = smem_layout(C, N, Np, S, a.stages, a.wsplit, a.alias_out, a.tc_cp, a.tc_np);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);          // [2]
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + 16);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 32);
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
   const int tiles_per_img = a.tiles_x * a.tiles_y;
   const int ntiles = nb * tiles_per_img;
 
-  const int CP = pad_quads(C), NPf = pad_quads(N);   // pixel strides (floats) of the input / output staging tiles
+  const int CP = a.tc_cp, NPf = a.tc_np;            // pixel strides (floats) of the input / output staging tiles
   const uint32_t in_bytes = (uint32_t)(ITH * ITW * CP * 4);
   auto issue_load = [&](int tile, int stage) {
     int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
@@ -367,23 +367,38 @@ bool encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, 
 
 namespace {
 
-// Picks (stages, alias_out) for a block; returns false when it cannot fit in shared memory.
-bool pick_smem(int C, int N, int Np, int S, int wsplit, int* stages, int* alias_out, int* total) {
-  const bool can_alias = TH * TW * pad_quads(N) * 4 <= 2 * (C / 4) * kPlaneBytes;
-  int best = -1, best_per_sm = 0;
+// Picks (stages, alias_out, pixel strides) for a block; returns false when it cannot fit in shared memory.  The padded
+// pixel strides are used only where they cost neither a pipeline stage nor a resident CTA.
+bool pick_smem(int C, int N, int Np, int S, int wsplit, int* stages, int* alias_out, int* total, int* cp_out, int* np_out) {
   // candidate configurations in order of preference at equal occupancy
   const int cand[4][2] = {{2, 0}, {2, 1}, {1, 0}, {1, 1}};
-  for (int i = 0; i < 4; ++i) {
-    if (cand[i][1] && !can_alias) continue;
-    SmemLayout L = smem_layout(C, N, Np, S, cand[i][0], wsplit, cand[i][1]);
-    if (L.total > kMaxSmemTc) continue;
-    int per_sm = (228 * 1024) / (L.total + 1024);
-    if (per_sm > 2) per_sm = 2;
-    if (per_sm > best_per_sm) { best_per_sm = per_sm; best = i; }
+  auto best_for = [&](int CP, int NP, int* per_sm_out) {
+    const bool can_alias = TH * TW * NP * 4 <= 2 * (C / 4) * kPlaneBytes;
+    int best = -1, best_per_sm = 0;
+    for (int i = 0; i < 4; ++i) {
+      if (cand[i][1] && !can_alias) continue;
+      SmemLayout L = smem_layout(C, N, Np, S, cand[i][0], wsplit, cand[i][1], CP, NP);
+      if (L.total > kMaxSmemTc) continue;
+      int per_sm = (228 * 1024) / (L.total + 1024);
+      if (per_sm > 2) per_sm = 2;
+      if (per_sm > best_per_sm) { best_per_sm = per_sm; best = i; }
+    }
+    *per_sm_out = best_per_sm;
+    return best;
+  };
+  int ps0 = 0;
+  const int plain = best_for(C, N, &ps0);
+  if (plain < 0) return false;
+  int best = plain, CP = C, NP = N;
+  const int opts[3][2] = {{pad_quads(C), pad_quads(N)}, {pad_quads(C), N}, {C, pad_quads(N)}};
+  for (int o = 0; o < 3; ++o) {
+    if (opts[o][0] == C && opts[o][1] == N) continue;
+    int ps = 0;
+    const int b = best_for(opts[o][0], opts[o][1], &ps);
+    if (b >= 0 && ps >= ps0 && cand[b][0] >= cand[plain][0]) { best = b; CP = opts[o][0]; NP = opts[o][1]; break; }
   }
-  if (best < 0) return false;
-  *stages = cand[best][0]; *alias_out = cand[best][1];
-  *total = smem_layout(C, N, Np, S, *stages, wsplit, *alias_out).total;
+  *stages = cand[best][0]; *alias_out = cand[best][1]; *cp_out = CP; *np_out = NP;
+  *total = smem_layout(C, N, Np, S, *stages, wsplit, *alias_out, CP, NP).total;
   return true;
 }
 
@@ -417,8 +432,10 @@ bool block_tc_supported(const Step& s) {
       s.out.batch_stride != (int64_t)s.out.H * s.out.W * N)
     return false;
   if (s.skip.tensor >= 0 && (s.skip_c % 4 != 0 || s.skip.offset != 0)) return false;
-  int stages, alias, total;
-  return pick_smem(C, N, s.Np, s.stride, s.wsplit, &stages, &alias, &total);
+  static const int max_n = getenv("FDL_BLOCK_TC_MAX_N") ? atoi(getenv("FDL_BLOCK_TC_MAX_N")) : 1 << 30;   // A/B timing against conv_tc
+  if (N > max_n) return false;
+  int stages, alias, total, cp, np;
+  return pick_smem(C, N, s.Np, s.stride, s.wsplit, &stages, &alias, &total, &cp, &np);
 }
 
 cudaError_t launch_block_tc(const BlockTcLaunch& l, cudaStream_t stream) {
@@ -426,12 +443,12 @@ cudaError_t launch_block_tc(const BlockTcLaunch& l, cudaStream_t stream) {
   BlockTcArgs a = l.args;
   const int S = a.stride;
   int total = 0;
-  if (!pick_smem(a.C, a.N, a.Np, S, a.wsplit, &a.stages, &a.alias_out, &total)) return cudaErrorInvalidConfiguration;
+  if (!pick_smem(a.C, a.N, a.Np, S, a.wsplit, &a.stages, &a.alias_out, &total, &a.tc_cp, &a.tc_np)) return cudaErrorInvalidConfiguration;
   a.pad = S == 1 ? 1 : 0;
   CUtensorMap tm_in, tm_out;
-  if (!encode_nhwc(&tm_in, l.in, a.B, a.H * S, a.W * S, a.C, (long long)a.H * S * a.W * S * a.C, in_tile_h(S), in_tile_w(S), pad_quads(a.C)))
+  if (!encode_nhwc(&tm_in, l.in, a.B, a.H * S, a.W * S, a.C, (long long)a.H * S * a.W * S * a.C, in_tile_h(S), in_tile_w(S), a.tc_cp))
     return cudaErrorInvalidValue;
-  if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW, pad_quads(a.N))) return cudaErrorInvalidValue;
+  if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW, a.tc_np)) return cudaErrorInvalidValue;
   a.tiles_x = (a.W + TW - 1) / TW;
   a.tiles_y = (a.H + TH - 1) / TH;
   a.tmem_cols = a.Np <= 32 ? 32 : (a.Np <= 64 ? 64 : 128);
@@ -439,7 +456,7 @@ cudaError_t launch_block_tc(const BlockTcLaunch& l, cudaStream_t stream) {
   int per_sm = (228 * 1024) / (total + 1024);
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 2) per_sm = 2;                       // 168 registers x 192 threads: two resident CTAs per SM
-  int grid = 148 * per_sm;
+  int grid = persist_sms() * per_sm;
   if (grid > ntiles) grid = ntiles;
   static const int big_env = getenv("FDL_TC_THREADS") ? atoi(getenv("FDL_TC_THREADS")) : kThreadsSmall;   // 384 measured no faster (r01v)
   const bool big = per_sm == 1 && big_env == kThreadsBig;

@@ -32,6 +32,7 @@ struct BlockTcArgs {
   int out_bufs = 1;                // block_ws_kernel: output staging buffers (TMA store of tile i overlaps the epilogue of i+1)
   int acc_cols = 32;               // block_ws_kernel: TMEM columns per accumulator buffer
   int in_pad = 0;                  // block_ws_kernel: input tile pixel stride padded to an odd number of quads
+  int tc_cp = 0, tc_np = 0;        // blaze_block_tc_kernel: pixel strides (floats) of the input / output staging tiles (>= C / N)
   const int* n_active = nullptr;
   float alpha_c[128] = {};         // block_ws_kernel: PRELU slopes by value (read through the constant bank in the epilogue)
 };

@@ -1,6 +1,9 @@
 // net.cu -- see net.h.
 #include "net.h"
 
+#include <cstdlib>
+#include <utility>
+
 #include "fdl_status.h"
 #include "mma_kernels.cuh"
 
@@ -21,6 +24,14 @@ Net* Net::create(const std::string& path, int device, std::string* err, int* cod
     if (e == cudaSuccess) e = cudaMalloc(&n->d_weights_, n->plan_.weights.size() * sizeof(float));
     if (e == cudaSuccess)
       e = cudaMemcpy(n->d_weights_, n->plan_.weights.data(), n->plan_.weights.size() * sizeof(float), cudaMemcpyHostToDevice);
+    static const bool branch_streams = getenv("FDL_BRANCH_STREAMS") ? atoi(getenv("FDL_BRANCH_STREAMS")) != 0 : true;
+    for (int k = 1; branch_streams && k < n->plan_.num_streams && e == cudaSuccess; ++k) {
+      cudaStream_t st = nullptr; cudaEvent_t f = nullptr, j = nullptr;
+      e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f, cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&j, cudaEventDisableTiming);
+      n->aux_.push_back(st); n->ev_fork_.push_back(f); n->ev_join_.push_back(j);
+    }
     if (e != cudaSuccess) {
       *err = std::string("CUDA: ") + cudaGetErrorString(e);
       *code = FDL_ERR_CUDA;
@@ -36,6 +47,9 @@ Net::~Net() {
     cudaSetDevice(device_);
     if (d_weights_) cudaFree(d_weights_);
     if (d_arena_) cudaFree(d_arena_);
+    for (cudaEvent_t e : ev_fork_) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_join_) if (e) cudaEventDestroy(e);
+    for (cudaStream_t st : aux_) if (st) cudaStreamDestroy(st);
   }
 }
 
@@ -66,8 +80,38 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const 
   };
   if (B > cap_B_ || device_ < 0) return cudaErrorInvalidValue;
   size_t step_index = 0;
+  // Branch streams: per-launch timing (step_events) keeps everything on the caller's stream.
+  cudaStream_t const main_stream = stream;
+  const bool multi = !aux_.empty() && !step_events;
+  std::vector<int> synced(aux_.size() + 1, -2);      // last step of the main stream each auxiliary stream has waited for
+  std::vector<char> used(aux_.size() + 1, 0);
+  std::vector<std::pair<int64_t, int>> main_writes;  // (root buffer, step) written on the main stream so far
+  int main_last = -1;                                // last step enqueued on the main stream
+  int si = -1;
   for (const Step& s : plan_.steps) {
     cudaError_t e;
+    ++si;
+    stream = main_stream;
+    if (multi && s.stream >= 1 && s.stream <= (int)aux_.size()) {
+      const int k = s.stream;
+      stream = aux_[k - 1];
+      // read-after-write across streams: the newest main-stream writer of the buffers this step reads (the network input,
+      // *n_active and anything else produced before this pass count as "before step 0")
+      int need = -1;
+      for (const TensorRef* r : {&s.in, &s.skip}) {
+        if (r->tensor < 0) continue;
+        for (const auto& w : main_writes) if (w.first == r->buf_offset && w.second > need) need = w.second;
+      }
+      if (need > synced[k]) {
+        if ((e = cudaEventRecord(ev_fork_[k - 1], main_stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(stream, ev_fork_[k - 1], 0)) != cudaSuccess) return e;
+        synced[k] = main_last;
+      }
+      used[k] = 1;
+    } else if (multi) {
+      main_writes.push_back({s.out.buf_offset, si});
+      main_last = si;
+    }
     if (step_events && (e = cudaEventRecord(step_events[step_index++], stream)) != cudaSuccess) return e;
     if (mode_ >= 1 && block_tc_supported(s)) {
       BlockTcLaunch l;
@@ -131,6 +175,13 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const 
       a.B = B; a.n_active = n_active;
       e = launch_elementwise(a, stream);
     }
+    if (e != cudaSuccess) return e;
+  }
+  stream = main_stream;
+  for (size_t k = 1; k < used.size(); ++k) {
+    if (!used[k]) continue;
+    cudaError_t e = cudaEventRecord(ev_join_[k - 1], aux_[k - 1]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(main_stream, ev_join_[k - 1], 0);
     if (e != cudaSuccess) return e;
   }
   if (step_events) return cudaEventRecord(step_events[step_index], stream);

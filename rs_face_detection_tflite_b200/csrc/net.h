@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <vector>
 
 #include "net_kernels.cuh"
 #include "plan.h"
@@ -48,6 +49,10 @@ class Net {
   float* d_weights_ = nullptr;
   float* d_arena_ = nullptr;
   int cap_B_ = 0;
+  // Branch streams (Step::stream >= 1): the steps that feed only graph output k run on aux_[k-1], forked from / joined
+  // into the caller's stream with events, so the two heads of the landmark / iris / detector graphs run side by side.
+  std::vector<cudaStream_t> aux_;
+  std::vector<cudaEvent_t> ev_fork_, ev_join_;
 };
 
 }  // namespace fdl

@@ -24,6 +24,13 @@ inline bool pdl_enabled() {
   return on;
 }
 
+// SMs the persistent kernels spread over.  148 by default; a smaller number (FDL_PERSIST_SMS) leaves SMs free for the
+// small launches of other pipeline lanes' streams to run beside a persistent kernel instead of queueing behind it.
+inline int persist_sms() {
+  static const int n = [] { const char* e = getenv("FDL_PERSIST_SMS"); int v = e ? atoi(e) : 148; return v < 1 ? 1 : (v > 148 ? 148 : v); }();
+  return n;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

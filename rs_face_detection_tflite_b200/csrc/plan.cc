@@ -443,6 +443,35 @@ bool Plan::build(const TfModel& m, std::string* err) {
   for (int o : m.outputs) last_use[b.root[o]] = INT32_MAX;
   last_use[b.root[in_t]] = std::max(last_use[b.root[in_t]], 0);
 
+  // ---- branches: which graph outputs does each step feed? ----------------------------------------
+  // (FaceMesh: landmarks / face flag from the 6x6 map on; iris: eye contour / iris from the 8x8 map on; detectors: the
+  // regressor / classificator heads.)  Steps are in topological order, so one reverse sweep propagates the output sets.
+  num_streams = 1;
+  if (m.outputs.size() >= 2 && m.outputs.size() <= 32) {
+    std::vector<uint32_t> reach(nt, 0u);
+    for (size_t k = 0; k < m.outputs.size(); ++k) reach[b.root[m.outputs[k]]] |= 1u << k;
+    for (size_t si = steps.size(); si-- > 0;) {
+      Step& s = steps[si];
+      const uint32_t mask = reach[b.root[s.out.tensor]];
+      reach[b.root[s.in.tensor]] |= mask;
+      if (s.skip.tensor >= 0) reach[b.root[s.skip.tensor]] |= mask;
+      s.stream = 0;
+      if (mask && (mask & (mask - 1)) == 0) {          // exactly one output
+        int k = 0;
+        while (!((mask >> k) & 1u)) ++k;
+        s.stream = k;
+      }
+      num_streams = std::max(num_streams, s.stream + 1);
+    }
+    // buffers touched by an auxiliary-stream step are never recycled: no write-after-read hazards between streams
+    for (const Step& s : steps) {
+      if (s.stream == 0) continue;
+      last_use[b.root[s.out.tensor]] = INT32_MAX;
+      last_use[b.root[s.in.tensor]] = INT32_MAX;
+      if (s.skip.tensor >= 0) last_use[b.root[s.skip.tensor]] = INT32_MAX;
+    }
+  }
+
   std::vector<int64_t> buf_off(nt, -1);
   std::vector<std::pair<int, Interval>> live;  // (root tensor, interval)
   int64_t high = 0;
@@ -543,6 +572,7 @@ bool Plan::build(const TfModel& m, std::string* err) {
       default: buf[0] = 0;
     }
     s.text = buf;
+    if (s.stream > 0) s.text += " stream=" + std::to_string(s.stream);
   }
   return true;
 }

@@ -65,6 +65,10 @@ struct Step {
   int64_t w_tc = -1;
   int Kp = 0, Nt = 0, n_tiles = 0;
   int K = 0, K4 = 0, N = 0, Npad = 0;  // contraction size (K4 = roundup(K,4) rows stored) / output channels of the CONV/PW part
+  // Branch of the step: 0 = trunk (the step feeds several graph outputs) or the branch of graph output 0; k >= 1 = the step
+  // feeds graph output k only.  Steps with stream >= 1 may run on an auxiliary CUDA stream beside the others (Net::forward):
+  // the planner never recycles a buffer such a step reads or writes, so stream order is the only ordering they need.
+  int stream = 0;
   std::vector<int> ops;           // tflite op indices folded into this step
   std::string text;               // human-readable description
 };
@@ -78,6 +82,7 @@ struct Plan {
   int64_t algo_bytes_per_item = 0;  // sum over steps of (input + skip + output) bytes: the block-fused floor
   int64_t flops_per_item = 0;
   int num_tflite_ops = 0;
+  int num_streams = 1;            // 1 + number of auxiliary branches (see Step::stream)
 
   bool build(const TfModel& m, std::string* err);
   std::string describe() const;

@@ -200,7 +200,7 @@ cudaError_t launch_stem_conv(const ConvArgs& a, cudaStream_t stream) {
   if (a.kh == 5) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stem_conv_kernel<5, 5, 1>, c.threads, c.smem);
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stem_conv_kernel<3, 3, 0>, c.threads, c.smem);
   if (per_sm < 1) per_sm = 1;
-  const unsigned grid = (unsigned)(total < 148LL * per_sm ? total : 148LL * per_sm);     // persistent CTAs
+  const unsigned grid = (unsigned)(total < (long long)persist_sms() * per_sm ? total : (long long)persist_sms() * per_sm);     // persistent CTAs
   cudaError_t e;
   if (a.kh == 5) e = launch_pdl(stem_conv_kernel<5, 5, 1>, dim3(grid), dim3(c.threads), c.smem, stream, a, c.TWo, c.tiles_x, c.tiles_y);
   else e = launch_pdl(stem_conv_kernel<3, 3, 0>, dim3(grid), dim3(c.threads), c.smem, stream, a, c.TWo, c.tiles_x, c.tiles_y);
