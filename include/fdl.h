@@ -82,8 +82,8 @@ typedef struct fdl_image {
   int32_t _pad;
 } fdl_image;
 
-/* face_detection.rs:117-123 `FaceDetectionModel`. FullSparse (4) is outside the hot-path scope
- *  and yields FDL_ERR_MODEL. */
+/* face_detection.rs:117-123 `FaceDetectionModel`.  FullSparse (4): the planner folds DENSIFY (CSR
+ * f16 weights) and the spatial PADs at load and runs DEPTH_TO_SPACE on the device. */
 enum {
   FDL_MODEL_FRONT_CAMERA = 0,
   FDL_MODEL_BACK_CAMERA = 1,

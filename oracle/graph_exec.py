@@ -1,4 +1,4 @@
-"""torch-CPU fp32 executor for the five dense .tflite graphs -- oracle side.
+"""torch-CPU fp32 executor for the .tflite graphs (five dense ones + the sparse full-range detector) -- oracle side.
 
 Test infrastructure; see ``oracle/__init__.py``.  Restates what
 ``interpreter.invoke()`` computes at face_detection.rs:235, face_landmark.rs:265
@@ -48,10 +48,12 @@ class GraphExecutor:
         for t in m.tensors:
             if t.data is not None:
                 self.const[t.index] = t.data
-        # fold DEQUANTIZE of constants
+        # fold DENSIFY (sparse -> dense, same type) and DEQUANTIZE (f16 -> f32) of constants
         self.ops = []
         for op in m.ops:
-            if op.code == T.DEQUANTIZE and op.inputs[0] in self.const:
+            if op.code == T.DENSIFY and op.inputs[0] in self.const:
+                self.const[op.outputs[0]] = T.densify(m.tensors[op.inputs[0]])
+            elif op.code == T.DEQUANTIZE and op.inputs[0] in self.const:
                 self.const[op.outputs[0]] = self.const[op.inputs[0]].astype(np.float32)
             else:
                 self.ops.append(op)
@@ -84,6 +86,11 @@ class GraphExecutor:
         def get(i):
             return vals[i] if i in vals else self._c(i)
 
+        def fused(y, act):
+            # fused_activation_function: 0 NONE, 1 RELU (the only ones the reference's models use)
+            assert act in (0, 1), act
+            return torch.relu(y) if act == 1 else y
+
         for op in self.ops:
             o = op.opts
             c = op.code
@@ -97,12 +104,11 @@ class GraphExecutor:
                     xi = F.pad(xi, (pl, pr, pt, pb))
                 y = F.conv2d(xi, w.permute(0, 3, 1, 2).contiguous(), b,
                              stride=(o["stride_h"], o["stride_w"]))
-                assert o["act"] == 0
-                r = _nhwc(y)
+                r = fused(_nhwc(y), o["act"])
             elif c == T.DEPTHWISE_CONV_2D:
                 inp, w, b = get(op.inputs[0]), get(op.inputs[1]), get(op.inputs[2])
                 kh, kw, C = w.shape[1], w.shape[2], w.shape[3]
-                assert o["depth_multiplier"] == 1 and o["act"] == 0
+                assert o["depth_multiplier"] == 1
                 xi = _nchw(inp)
                 if o["padding"] == 0:
                     pt, pb = _same_pad(inp.shape[1], kh, o["stride_h"])
@@ -110,7 +116,7 @@ class GraphExecutor:
                     xi = F.pad(xi, (pl, pr, pt, pb))
                 wt = w[0].permute(2, 0, 1).unsqueeze(1).contiguous()  # [C,1,kh,kw]
                 y = F.conv2d(xi, wt, b, stride=(o["stride_h"], o["stride_w"]), groups=C)
-                r = _nhwc(y)
+                r = fused(_nhwc(y), o["act"])
             elif c == T.MAX_POOL_2D:
                 inp = get(op.inputs[0])
                 xi = _nchw(inp)
@@ -123,8 +129,8 @@ class GraphExecutor:
                 r = _nhwc(y)
             elif c == T.ADD:
                 a, b2 = get(op.inputs[0]), get(op.inputs[1])
-                assert a.shape == b2.shape and o["act"] == 0
-                r = a + b2
+                assert a.shape == b2.shape
+                r = fused(a + b2, o["act"])
             elif c == T.RELU:
                 r = torch.relu(get(op.inputs[0]))
             elif c == T.PRELU:
@@ -153,6 +159,13 @@ class GraphExecutor:
                 size = [int(v) for v in self.const[op.inputs[1]].reshape(-1)]
                 assert o["half_pixel_centers"] == 1 and o["align_corners"] == 0
                 r = _nhwc(F.interpolate(_nchw(a), size=size, mode="bilinear", align_corners=False))
+            elif c == T.DEPTH_TO_SPACE:
+                # out[n, h*b + i, w*b + j, c] = in[n, h, w, (i*b + j)*Cout + c]  (tensorflow/lite/kernels/internal/reference/depth_to_space.h)
+                a = get(op.inputs[0])
+                bs = o["block_size"]
+                n_, h_, w_, c_ = a.shape
+                co = c_ // (bs * bs)
+                r = a.reshape(n_, h_, w_, bs, bs, co).permute(0, 1, 3, 2, 4, 5).reshape(n_, h_ * bs, w_ * bs, co).contiguous()
             else:
                 raise NotImplementedError(op.name)
             vals[op.outputs[0]] = r

@@ -20,7 +20,7 @@ DEFAULT_MODEL_DIR = os.path.join(os.path.dirname(_HERE), "models")
 
 class FaceDetection:
     def __init__(self, model_type=glue.BACK_CAMERA, model_dir=None):
-        if model_type not in glue.MODEL_FILES or model_type == glue.FULL_SPARSE:
+        if model_type not in glue.MODEL_FILES:
             raise ValueError("unsupported model type")
         self.model_type = model_type
         self.net = GraphExecutor(os.path.join(model_dir or DEFAULT_MODEL_DIR, glue.MODEL_FILES[model_type]))

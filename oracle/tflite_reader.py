@@ -19,6 +19,8 @@ import numpy as np
 # builtin operator codes used by the five dense graphs
 ADD, CONCATENATION, CONV_2D, DEPTHWISE_CONV_2D, DEQUANTIZE = 0, 2, 3, 4, 6
 MAX_POOL_2D, RELU, RESHAPE, RESIZE_BILINEAR, PAD, PRELU = 17, 19, 22, 23, 34, 54
+# the sparse full-range detector adds two
+DEPTH_TO_SPACE, DENSIFY = 5, 124
 OP_NAMES = {
     ADD: "ADD", CONCATENATION: "CONCATENATION", CONV_2D: "CONV_2D",
     DEPTHWISE_CONV_2D: "DEPTHWISE_CONV_2D", DEQUANTIZE: "DEQUANTIZE",
@@ -97,7 +99,8 @@ class Tensor:
     shape: list
     dtype: type
     buffer: int
-    data: np.ndarray | None = None  # constant payload, if any
+    data: np.ndarray | None = None  # constant payload, if any (the stored VALUES only when `sparsity` is set)
+    sparsity: dict | None = None    # SparsityParameters: traversal_order, block_map, dims=[(format, dense_size, segments, indices)]
 
 
 @dataclass
@@ -145,7 +148,57 @@ def _parse_options(fb: _FB, code: int, t) -> dict:
         return dict(new_shape=fb.vec_i32(t, 0))
     if code == RESIZE_BILINEAR:
         return dict(align_corners=fb.scalar(t, 2, "u8"), half_pixel_centers=fb.scalar(t, 3, "u8"))
+    if code == DEPTH_TO_SPACE:
+        return dict(block_size=fb.scalar(t, 0, "i32"))
     return {}
+
+
+def _sparse_index_vector(fb: _FB, table, type_fid, value_fid):
+    """SparseIndexVector union (schema.fbs): 1 Int32Vector, 2 Uint16Vector, 3 Uint8Vector, each {0: values}."""
+    kind = fb.scalar(table, type_fid, "u8")
+    tb = fb.table(table, value_fid)
+    if kind == 0 or tb is None:
+        return None
+    s, n = fb.vector(tb, 0)
+    fmt = {1: "<%di", 2: "<%dH", 3: "<%dB"}[kind]
+    return np.array(struct.unpack_from(fmt % n, fb.b, s), np.int64)
+
+
+def _parse_sparsity(fb: _FB, t):
+    """Tensor.sparsity (field 6): SparsityParameters{0: traversal_order, 1: block_map, 2: dim_metadata[]},
+    DimensionMetadata{0: format (0 DENSE, 1 SPARSE_CSR), 1: dense_size, 2/3: array_segments, 4/5: array_indices}."""
+    sp = fb.table(t, 6)
+    if sp is None:
+        return None
+    dims = []
+    for d in fb.vec_tables(sp, 2):
+        dims.append((fb.scalar(d, 0, "i8"), fb.scalar(d, 1, "i32"), _sparse_index_vector(fb, d, 2, 3), _sparse_index_vector(fb, d, 4, 5)))
+    return dict(traversal_order=fb.vec_i32(sp, 0), block_map=fb.vec_i32(sp, 1), dims=dims)
+
+
+def densify(t: "Tensor") -> np.ndarray:
+    """What the DENSIFY op computes (tensorflow/lite/kernels/densify.cc -> FormatConverter::SparseToDense) for the layout
+    the reference's sparse model uses: identity traversal order, no block map, every dimension DENSE except the last,
+    which is SPARSE_CSR (segments over the flattened outer dimensions, indices = positions in the last dimension)."""
+    sp = t.sparsity
+    rank = len(t.shape)
+    if sp["traversal_order"] != list(range(rank)) or sp["block_map"] or len(sp["dims"]) != rank:
+        raise NotImplementedError("sparse layout other than row-major CSR on the last dimension")
+    for d, (fmt, size, _, _) in enumerate(sp["dims"][:-1]):
+        if fmt != 0 or size != t.shape[d]:
+            raise NotImplementedError("sparse layout other than row-major CSR on the last dimension")
+    fmt, _, seg, idx = sp["dims"][-1]
+    if fmt != 1 or seg is None or idx is None:
+        raise NotImplementedError("last dimension is not SPARSE_CSR")
+    rows = int(np.prod(t.shape[:-1]))
+    values = t.data.reshape(-1)
+    if len(seg) != rows + 1 or seg[-1] != len(idx) or len(values) < len(idx):
+        raise ValueError("inconsistent sparsity metadata")
+    out = np.zeros((rows, t.shape[-1]), t.dtype)
+    for r in range(rows):
+        a, b = int(seg[r]), int(seg[r + 1])
+        out[r, idx[a:b]] = values[a:b]
+    return out.reshape(t.shape)
 
 
 def load(path: str) -> Model:
@@ -172,10 +225,12 @@ def load(path: str) -> Model:
         dtype = TENSOR_TYPES[ttype]
         data = None
         s, n = buffers[bidx] if bidx < len(buffers) else (None, 0)
+        sparsity = _parse_sparsity(fb, t)
         if s is not None and n > 0:
-            data = np.frombuffer(buf, dtype=dtype, count=n // np.dtype(dtype).itemsize,
-                                 offset=s).reshape(shape).copy()
-        tensors.append(Tensor(i, fb.string(t, 3), shape, dtype, bidx, data))
+            data = np.frombuffer(buf, dtype=dtype, count=n // np.dtype(dtype).itemsize, offset=s).copy()
+            if sparsity is None:
+                data = data.reshape(shape)
+        tensors.append(Tensor(i, fb.string(t, 3), shape, dtype, bidx, data, sparsity))
     ops = []
     for o in fb.vec_tables(sub, 3):
         code = codes[fb.scalar(o, 0, "u32")]

@@ -236,8 +236,6 @@ int fdl_detector_create(int model, const char* model_dir, int device, fdl_detect
   const char* file = detector_file(model);
   SsdOptions opt;
   if (!file || !ssd_options_for(model, &opt)) return set_error(FDL_ERR_MODEL, "unsupported model type");   // face_detection.rs:184
-  if (model == FDL_MODEL_FULL_SPARSE)
-    return set_error(FDL_ERR_MODEL, "unsupported model type: FullSparse needs DENSIFY/DEPTH_TO_SPACE, outside the B200 hot path");
   int rc = check_device(device);
   if (rc) return rc;
   std::string path = std::string(model_dir ? model_dir : "./models") + "/" + file;

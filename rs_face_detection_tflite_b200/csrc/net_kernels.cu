@@ -221,6 +221,13 @@ __global__ void elementwise_kernel(const EltArgs a) {
       case STEP_ACT:
         v = __ldg(ip + (long long)pix * C + c);
         break;
+      case STEP_D2S: {
+        // DEPTH_TO_SPACE, block size a.stride: out[oy, ox, c] = in[oy / bs, ox / bs, ((oy % bs) * bs + ox % bs) * C + c]
+        const int bs = a.stride;
+        const int iy = oy / bs, ix = ox / bs;
+        v = __ldg(ip + ((long long)iy * a.in.W + ix) * a.in.C + ((oy - iy * bs) * bs + (ox - ix * bs)) * C + c);
+        break;
+      }
       case STEP_RESIZE: {
         // TFLite RESIZE_BILINEAR, align_corners = false, half_pixel_centers = true
         float sy = (oy + 0.5f) * ((float)a.in.H / (float)OH) - 0.5f;

@@ -167,6 +167,7 @@ int fdl_pipeline_create(const fdl_pipeline_config* cfg, fdl_pipeline** out) {
     case FDL_MODEL_BACK_CAMERA: file = "face_detection_back.tflite"; break;
     case FDL_MODEL_SHORT: file = "face_detection_short_range.tflite"; break;
     case FDL_MODEL_FULL: file = "face_detection_full_range.tflite"; break;
+    case FDL_MODEL_FULL_SPARSE: file = "face_detection_full_range_sparse.tflite"; break;   // face_detection.rs:180-183
     default: return bail(FDL_ERR_MODEL, "unsupported model type");
   }
   ssd_options_for(cfg->detector_model, &p->opt);

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 
 namespace fdl {
@@ -23,6 +24,9 @@ struct Group {
   int add_op = -1;
   int in_tensor = -1, out_tensor = -1;
   int skip_tensor = -1, skip_pool = 0, skip_c = 0;
+  int pad_op = -1;            // spatial PAD folded into the (VALID) depthwise / convolution: explicit padding
+  int pad_t = 0, pad_b = 0, pad_l = 0, pad_r = 0;
+  int fused_relu = 0;         // fused_activation_function = RELU on the group's last CONV_2D / ADD
 };
 
 struct Builder {
@@ -83,6 +87,11 @@ struct Builder {
       if (op.code == OP_DEQUANTIZE) {
         if (op.inputs.empty() || !is_const[op.inputs[0]]) return fail("DEQUANTIZE of a non-constant tensor is unsupported");
         is_const[op.outputs[0]] = 2;  // 2 = via dequantize
+      } else if (op.code == OP_DENSIFY) {
+        if (op.inputs.empty() || !is_const[op.inputs[0]]) return fail("DENSIFY of a non-constant tensor is unsupported");
+        if (!m.tensors[op.inputs[0]].has_sparsity || !m.tensors[op.inputs[0]].sparse_ok)
+          return fail("DENSIFY: only row-major CSR on the last dimension is supported");
+        is_const[op.outputs[0]] = 2;  // via densify (ops are in topological order: a DEQUANTIZE of it comes later)
       }
     }
     // rebuild consumers without the now-constant tensors
@@ -94,8 +103,36 @@ struct Builder {
 
   // constant tensor -> f32 values, looking through a DEQUANTIZE
   bool const_values(int t, std::vector<float>* out) const {
-    if (is_const[t] == 2) return m.const_f32(m.ops[producer[t]].inputs[0], out);
+    while (is_const[t] == 2) t = m.ops[producer[t]].inputs[0];   // through DEQUANTIZE and DENSIFY
     return m.const_f32(t, out);
+  }
+  // PAD with paddings [[0,0],[t,b],[l,r],[0,0]]
+  bool check_spatial_pad(const TfOp& op, int* pt, int* pb, int* pl, int* pr) const {
+    std::vector<int> p;
+    if (op.inputs.size() < 2 || !m.const_i32(op.inputs[1], &p) || p.size() != 8) return false;
+    if (p[0] || p[1] || p[6] || p[7]) return false;
+    *pt = p[2]; *pb = p[3]; *pl = p[4]; *pr = p[5];
+    return p[2] >= 0 && p[3] >= 0 && p[4] >= 0 && p[5] >= 0 && (p[2] + p[3] + p[4] + p[5]) > 0;
+  }
+  // Is op `i` a spatial PAD whose only consumer is a VALID depthwise / convolution?  (Then that consumer's group takes it.)
+  bool pad_feeds_valid_conv(int i) const {
+    const TfOp& op = m.ops[i];
+    int pt, pb, pl, pr;
+    if (op.code != OP_PAD || !check_spatial_pad(op, &pt, &pb, &pl, &pr)) return false;
+    const int c = sole_consumer(op.outputs[0]);
+    if (c < 0) return false;
+    const TfOp& cv = m.ops[c];
+    return (cv.code == OP_DEPTHWISE_CONV_2D || cv.code == OP_CONV_2D) && cv.padding == 1 && cv.inputs[0] == op.outputs[0];
+  }
+  // If the (VALID) conv op `c` reads a foldable spatial PAD, fold it: the group reads the PAD's input with explicit padding.
+  void fold_input_pad(int c, Group* g, const std::function<void(int)>& take) {
+    const int in = m.ops[c].inputs[0];
+    const int p = producer[in];
+    if (p < 0 || group_of[p] != -1 || !pad_feeds_valid_conv(p)) return;
+    check_spatial_pad(m.ops[p], &g->pad_t, &g->pad_b, &g->pad_l, &g->pad_r);
+    g->pad_op = p;
+    g->in_tensor = m.ops[p].inputs[0];
+    take(p);
   }
 
   bool check_channel_pad(const TfOp& op, int* extra) const {
@@ -120,7 +157,7 @@ struct Builder {
     group_of.assign(m.ops.size(), -1);
     for (int i = (int)m.ops.size() - 1; i >= 0; --i) {
       const TfOp& op = m.ops[i];
-      if (op.code == OP_DEQUANTIZE) { group_of[i] = -2; continue; }
+      if (op.code == OP_DEQUANTIZE || op.code == OP_DENSIFY) { group_of[i] = -2; continue; }
       if (op.code == OP_RESHAPE) {
         int in = op.inputs[0], out = op.outputs[0];
         if (is_const[in]) return fail("RESHAPE of a constant is unsupported");
@@ -154,8 +191,9 @@ struct Builder {
     for (int i = 0; i < (int)m.ops.size(); ++i) {
       if (group_of[i] != -1) continue;
       const TfOp& op = m.ops[i];
+      if (pad_feeds_valid_conv(i)) continue;       // taken by the group of the conv that consumes it
       Group g;
-      auto take = [&](int o) { g.ops.push_back(o); group_of[o] = (int)groups.size(); g.last_op = std::max(g.last_op, o); };
+      std::function<void(int)> take = [&](int o) { g.ops.push_back(o); group_of[o] = (int)groups.size(); g.last_op = std::max(g.last_op, o); };
       auto take_act = [&](int t) {  // fuse a trailing RELU/PRELU consuming tensor t; returns the new tail tensor
         int c = sole_consumer(t);
         if (c >= 0 && group_of[c] == -1 && is_act(c)) { g.act_op = c; take(c); return m.ops[c].outputs[0]; }
@@ -170,13 +208,14 @@ struct Builder {
           g.in_tensor = op.inputs[0];
           g.dw_op = i;
           take(i);
+          fold_input_pad(i, &g, take);
           int d = op.outputs[0];
           int c = sole_consumer(d);
           bool pw = false;
           if (c >= 0 && group_of[c] == -1 && m.ops[c].code == OP_CONV_2D) {
             const TfOp& cv = m.ops[c];
             const auto& cs = shape(cv.inputs[1]);
-            pw = cs.size() == 4 && cs[1] == 1 && cs[2] == 1 && cv.stride_w == 1 && cv.stride_h == 1 && cv.fused_act == 0 &&
+            pw = cs.size() == 4 && cs[1] == 1 && cs[2] == 1 && cv.stride_w == 1 && cv.stride_h == 1 && (cv.fused_act == 0 || cv.fused_act == 1) &&
                  cv.inputs[0] == d;
           }
           if (!pw) {
@@ -187,8 +226,9 @@ struct Builder {
           g.kind = STEP_BLOCK; g.main_op = c;
           take(c);
           int t = m.ops[c].outputs[0];
+          if (m.ops[c].fused_act == 1) { g.fused_relu = 1; g.out_tensor = t; break; }   // RELU before anything else: no residual to fuse
           int a = sole_consumer(t);
-          if (a >= 0 && group_of[a] == -1 && m.ops[a].code == OP_ADD && m.ops[a].fused_act == 0) {
+          if (a >= 0 && group_of[a] == -1 && m.ops[a].code == OP_ADD && (m.ops[a].fused_act == 0 || m.ops[a].fused_act == 1)) {
             const TfOp& add = m.ops[a];
             int other = add.inputs[0] == t ? add.inputs[1] : add.inputs[0];
             if (other != t && !is_const[other]) {
@@ -211,6 +251,7 @@ struct Builder {
                 if (pool_op >= 0) take(pool_op);
                 take(a);
                 t = add.outputs[0];
+                if (add.fused_act == 1) { g.fused_relu = 1; g.out_tensor = t; break; }
               }
             }
           }
@@ -218,10 +259,12 @@ struct Builder {
           break;
         }
         case OP_CONV_2D: {
-          if (op.dil_w != 1 || op.dil_h != 1 || op.fused_act != 0 || op.stride_w != op.stride_h)
+          if (op.dil_w != 1 || op.dil_h != 1 || (op.fused_act != 0 && op.fused_act != 1) || op.stride_w != op.stride_h)
             return fail("unsupported CONV_2D options");
           g.kind = STEP_CONV; g.main_op = i; g.in_tensor = op.inputs[0];
           take(i);
+          fold_input_pad(i, &g, take);
+          if (op.fused_act == 1) { g.fused_relu = 1; g.out_tensor = op.outputs[0]; break; }
           g.out_tensor = take_act(op.outputs[0]);
           break;
         }
@@ -241,10 +284,11 @@ struct Builder {
           break;
         }
         case OP_ADD: {
-          if (op.fused_act != 0 || is_const[op.inputs[0]] || is_const[op.inputs[1]] || elems(op.inputs[0]) != elems(op.inputs[1]))
+          if ((op.fused_act != 0 && op.fused_act != 1) || is_const[op.inputs[0]] || is_const[op.inputs[1]] || elems(op.inputs[0]) != elems(op.inputs[1]))
             return fail("unsupported ADD");
           g.kind = STEP_ADD; g.main_op = i; g.in_tensor = op.inputs[0]; g.skip_tensor = op.inputs[1];
           take(i);
+          if (op.fused_act == 1) { g.fused_relu = 1; g.out_tensor = op.outputs[0]; break; }
           g.out_tensor = take_act(op.outputs[0]);
           break;
         }
@@ -260,16 +304,27 @@ struct Builder {
           take(i);
           int t = op.outputs[0];
           int a = sole_consumer(t);
-          if (a >= 0 && group_of[a] == -1 && m.ops[a].code == OP_ADD && m.ops[a].fused_act == 0) {
+          if (a >= 0 && group_of[a] == -1 && m.ops[a].code == OP_ADD && (m.ops[a].fused_act == 0 || m.ops[a].fused_act == 1)) {
             const TfOp& add = m.ops[a];
             int other = add.inputs[0] == t ? add.inputs[1] : add.inputs[0];
             if (other != t && !is_const[other] && elems(other) == elems(t)) {
               g.skip_tensor = other; g.add_op = a;
               take(a);
               t = add.outputs[0];
+              if (add.fused_act == 1) { g.fused_relu = 1; g.out_tensor = t; break; }
             }
           }
           g.out_tensor = take_act(t);
+          break;
+        }
+        case OP_DEPTH_TO_SPACE: {
+          int H, W, C, OH, OW, OC;
+          const int bs = op.block_size;
+          if (bs < 1 || !nhwc(op.inputs[0], &H, &W, &C) || !nhwc(op.outputs[0], &OH, &OW, &OC) || OH != H * bs || OW != W * bs || OC * bs * bs != C)
+            return fail("unsupported DEPTH_TO_SPACE");
+          g.kind = STEP_D2S; g.main_op = i; g.in_tensor = op.inputs[0];
+          take(i);
+          g.out_tensor = op.outputs[0];
           break;
         }
         default:
@@ -277,6 +332,8 @@ struct Builder {
       }
       groups.push_back(std::move(g));
     }
+    for (size_t i = 0; i < m.ops.size(); ++i)
+      if (group_of[i] == -1) return fail(std::string("internal: ") + op_name(m.ops[i].code) + " was left out of every fused step");
     return true;
   }
 };
@@ -325,6 +382,7 @@ bool Plan::build(const TfModel& m, std::string* err) {
       int total = std::max(0, (out - 1) * stride + k - in);
       *before = total / 2;
     };
+    if (g.fused_relu) s.act = ACT_RELU;
     if (g.act_op >= 0) {
       const TfOp& a = m.ops[g.act_op];
       if (a.code == OP_RELU) s.act = ACT_RELU;
@@ -344,10 +402,11 @@ bool Plan::build(const TfModel& m, std::string* err) {
       int dh = 0, dwid = 0, dc = 0;
       b.nhwc(dw.outputs[0], &dh, &dwid, &dc);
       if (dw.padding == 0) { same_pad(s.in.H, 3, s.stride, dh, &s.pad_t); same_pad(s.in.W, 3, s.stride, dwid, &s.pad_l); }
-      else { s.pad_t = s.pad_l = 0; }
-      // output-size sanity (SAME: ceil(in/stride); VALID: (in-k)/stride+1)
-      int eh = dw.padding == 0 ? (s.in.H + s.stride - 1) / s.stride : (s.in.H - 3) / s.stride + 1;
-      if (eh != dh || dc != s.in.C) { *err = "depthwise output shape mismatch"; return false; }
+      else { s.pad_t = g.pad_t; s.pad_l = g.pad_l; }   // VALID: no padding, or the folded spatial PAD's
+      // output-size sanity (SAME: ceil(in/stride); VALID: (in + pads - k)/stride + 1)
+      int eh = dw.padding == 0 ? (s.in.H + s.stride - 1) / s.stride : (s.in.H + g.pad_t + g.pad_b - 3) / s.stride + 1;
+      int ew = dw.padding == 0 ? (s.in.W + s.stride - 1) / s.stride : (s.in.W + g.pad_l + g.pad_r - 3) / s.stride + 1;
+      if (eh != dh || ew != dwid || dc != s.in.C) { *err = "depthwise output shape mismatch"; return false; }
       s.w_dw = push(w);   // tflite layout [1,3,3,C] == [9][C]
       s.b_dw = push(bias);
       flops_per_item += 2LL * 9 * dc * dh * dwid;
@@ -359,14 +418,15 @@ bool Plan::build(const TfModel& m, std::string* err) {
       if (ws.size() != 4 || !b.const_values(cv.inputs[1], &w) || !b.const_values(cv.inputs[2], &bias)) { *err = "bad conv weights"; return false; }
       int co = ws[0], kh = ws[1], kw = ws[2], ci = ws[3];
       int ih = 0, iw = 0, ic = 0, oh = 0, ow = 0, oc = 0;
-      b.nhwc(cv.inputs[0], &ih, &iw, &ic);
+      b.nhwc(g.kind == STEP_CONV ? g.in_tensor : cv.inputs[0], &ih, &iw, &ic);   // STEP_CONV: the folded PAD's input, if any
       b.nhwc(cv.outputs[0], &oh, &ow, &oc);
       if (ic != ci || oc != co || (int)bias.size() != co) { *err = "conv shape mismatch"; return false; }
       if (g.kind == STEP_CONV) {
         s.kh = kh; s.kw = kw; s.stride = cv.stride_w;
         if (cv.padding == 0) { same_pad(ih, kh, s.stride, oh, &s.pad_t); same_pad(iw, kw, s.stride, ow, &s.pad_l); }
-        int eh = cv.padding == 0 ? (ih + s.stride - 1) / s.stride : (ih - kh) / s.stride + 1;
-        int ew = cv.padding == 0 ? (iw + s.stride - 1) / s.stride : (iw - kw) / s.stride + 1;
+        else { s.pad_t = g.pad_t; s.pad_l = g.pad_l; }
+        int eh = cv.padding == 0 ? (ih + s.stride - 1) / s.stride : (ih + g.pad_t + g.pad_b - kh) / s.stride + 1;
+        int ew = cv.padding == 0 ? (iw + s.stride - 1) / s.stride : (iw + g.pad_l + g.pad_r - kw) / s.stride + 1;
         if (eh != oh || ew != ow) { *err = "conv output shape mismatch"; return false; }
       }
       s.K = kh * kw * ci; s.K4 = (int)align_up(s.K, 4); s.N = co; s.Npad = (int)align_up(co, 4);
@@ -422,6 +482,7 @@ bool Plan::build(const TfModel& m, std::string* err) {
     if (g.kind == STEP_RESIZE) {
       if (s.out.C != s.in.C) { *err = "resize channel mismatch"; return false; }
     }
+    if (g.kind == STEP_D2S) s.stride = m.ops[g.main_op].block_size;
     steps.push_back(std::move(s));
   }
 
@@ -564,6 +625,10 @@ bool Plan::build(const TfModel& m, std::string* err) {
         break;
       case STEP_ACT:
         std::snprintf(buf, sizeof buf, "#%zu ACT %s c%d @%dx%d ops=[%s]", si, kActName[s.act], s.out.C, s.out.H, s.out.W, ops.c_str());
+        break;
+      case STEP_D2S:
+        std::snprintf(buf, sizeof buf, "#%zu DEPTH_TO_SPACE x%d %dx%dx%d->%dx%dx%d ops=[%s]", si, s.stride, s.in.H, s.in.W, s.in.C, s.out.H, s.out.W,
+                      s.out.C, ops.c_str());
         break;
       case STEP_RESIZE:
         std::snprintf(buf, sizeof buf, "#%zu RESIZE_BILINEAR %dx%d->%dx%d c%d add=%s act=%s ops=[%s]", si, s.in.H, s.in.W, s.out.H, s.out.W,

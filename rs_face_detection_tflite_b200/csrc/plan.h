@@ -3,7 +3,9 @@
 // This is what replaces TFLite's InterpreterBuilder/allocate_tensors (face_detection.rs:207-210,
 // face_landmark.rs:233-236, iris_landmark.rs:161-164): instead of interpreting the 97..354 ops one
 // by one, the planner
-//   * folds DEQUANTIZE (f16 -> f32 constants) at load,
+//   * folds DEQUANTIZE (f16 -> f32 constants) and DENSIFY (CSR -> dense constants) at load,
+//   * folds a spatial zero PAD into the VALID depthwise / convolution that consumes it (explicit padding) and a fused
+//     RELU of CONV_2D / ADD into the step's activation (both forms occur in the sparse full-range detector),
 //   * turns RESHAPE / CONCATENATION(axis=1) into aliases so heads write straight into the
 //     [B,N,16] / [B,N,1] outputs,
 //   * pattern-matches  DW3x3 -> CONV1x1 -> [ADD skip] -> [RELU|PRELU]  (BlazeBlock) with
@@ -28,7 +30,8 @@ enum StepKind : int {
   STEP_PADC = 4,     // standalone channel PAD
   STEP_ADD = 5,      // standalone ADD [+ act]
   STEP_ACT = 6,      // standalone RELU / PRELU
-  STEP_RESIZE = 7    // RESIZE_BILINEAR (half pixel centres) [+ ADD other] [+ act]
+  STEP_RESIZE = 7,   // RESIZE_BILINEAR (half pixel centres) [+ ADD other] [+ act]
+  STEP_D2S = 8       // DEPTH_TO_SPACE (block size in `stride`): the sparse full-range detector's heads
 };
 enum ActKind : int { ACT_NONE = 0, ACT_RELU = 1, ACT_PRELU = 2 };
 

@@ -153,6 +153,47 @@ bool TfModel::load(const std::string& path, std::string* err) {
     tt.buffer = fb.scalar<uint32_t>(t, 2, 0);
     tt.name = fb.str(t, 3);
     tt.has_sparsity = fb.field(t, 6) != 0;
+    if (tt.has_sparsity) {
+      // SparsityParameters{0: traversal_order, 1: block_map, 2: dim_metadata[]};
+      // DimensionMetadata{0: format (0 DENSE, 1 SPARSE_CSR), 1: dense_size, 2/3: array_segments (union), 4/5: array_indices (union)};
+      // SparseIndexVector union: 1 Int32Vector, 2 Uint16Vector, 3 Uint8Vector, each {0: values}.
+      const size_t sp = fb.table(t, 6);
+      const std::vector<int> order = sp ? fb.vec_i32(sp, 0) : std::vector<int>();
+      const std::vector<int> bmap = sp ? fb.vec_i32(sp, 1) : std::vector<int>();
+      const std::vector<size_t> dims = sp ? fb.vec_tables(sp, 2) : std::vector<size_t>();
+      const size_t rank = tt.shape.size();
+      bool good = sp && rank >= 1 && order.size() == rank && bmap.empty() && dims.size() == rank;
+      for (size_t d = 0; good && d < rank; ++d) good = order[d] == (int)d;
+      for (size_t d = 0; good && d + 1 < rank; ++d)
+        good = fb.scalar<int8_t>(dims[d], 0, 0) == 0 && fb.scalar<int32_t>(dims[d], 1, 0) == tt.shape[d];
+      auto index_vector = [&](size_t dm, int type_fid, int value_fid, std::vector<int32_t>* out) {
+        const int kind = fb.scalar<uint8_t>(dm, type_fid, 0);
+        const size_t tb = fb.table(dm, value_fid);
+        size_t s; uint32_t c;
+        if (kind < 1 || kind > 3 || !tb || !fb.vec(tb, 0, &s, &c)) return false;
+        const size_t width = kind == 1 ? 4 : (kind == 2 ? 2 : 1);
+        if (s + (size_t)c * width > file.size()) return false;
+        out->resize(c);
+        for (uint32_t i = 0; i < c; ++i) {
+          if (kind == 1) { int32_t v; std::memcpy(&v, file.data() + s + 4ull * i, 4); (*out)[i] = v; }
+          else if (kind == 2) { uint16_t v; std::memcpy(&v, file.data() + s + 2ull * i, 2); (*out)[i] = v; }
+          else (*out)[i] = file[s + i];
+        }
+        return true;
+      };
+      if (good) {
+        const size_t last = dims[rank - 1];
+        good = fb.scalar<int8_t>(last, 0, 0) == 1 && index_vector(last, 2, 3, &tt.sp_segments) && index_vector(last, 4, 5, &tt.sp_indices);
+      }
+      if (good) {
+        int64_t rows = 1;
+        for (size_t d = 0; d + 1 < rank; ++d) rows *= tt.shape[d];
+        good = (int64_t)tt.sp_segments.size() == rows + 1 && tt.sp_segments.front() == 0 && tt.sp_segments.back() == (int32_t)tt.sp_indices.size();
+        for (size_t i = 0; good && i + 1 < tt.sp_segments.size(); ++i) good = tt.sp_segments[i] <= tt.sp_segments[i + 1];
+        for (size_t i = 0; good && i < tt.sp_indices.size(); ++i) good = tt.sp_indices[i] >= 0 && tt.sp_indices[i] < tt.shape[rank - 1];
+      }
+      tt.sparse_ok = good;
+    }
     if (tt.buffer < bufs.size() && bufs[tt.buffer].start && bufs[tt.buffer].len) {
       tt.data = file.data() + bufs[tt.buffer].start;
       tt.nbytes = bufs[tt.buffer].len;
@@ -204,6 +245,9 @@ bool TfModel::load(const std::string& path, std::string* err) {
         case OP_RESHAPE:
           op.new_shape = fb.vec_i32(t, 0);
           break;
+        case OP_DEPTH_TO_SPACE:
+          op.block_size = fb.scalar<int32_t>(t, 0, 0);
+          break;
         case OP_RESIZE_BILINEAR:
           op.align_corners = fb.scalar<uint8_t>(t, 2, 0) != 0;
           op.half_pixel_centers = fb.scalar<uint8_t>(t, 3, 0) != 0;
@@ -226,8 +270,24 @@ bool TfModel::load(const std::string& path, std::string* err) {
 bool TfModel::const_f32(int t, std::vector<float>* out) const {
   if (t < 0 || t >= (int)tensors.size()) return false;
   const TfTensor& tt = tensors[t];
-  if (!tt.data || tt.has_sparsity) return false;
+  if (!tt.data) return false;
   int64_t n = tt.elems();
+  if (tt.has_sparsity) {
+    // DENSIFY folded at load: scatter the stored values of every CSR row into a zero tensor
+    if (!tt.sparse_ok || (tt.type != TT_F32 && tt.type != TT_F16)) return false;
+    const size_t nnz = tt.sp_indices.size(), width = tt.type == TT_F32 ? 4 : 2;
+    if (tt.nbytes < nnz * width) return false;
+    out->assign((size_t)n, 0.f);
+    const int64_t cols = tt.shape.back();
+    for (size_t r = 0; r + 1 < tt.sp_segments.size(); ++r)
+      for (int32_t k = tt.sp_segments[r]; k < tt.sp_segments[r + 1]; ++k) {
+        float v;
+        if (tt.type == TT_F32) std::memcpy(&v, tt.data + 4ull * (size_t)k, 4);
+        else { uint16_t h; std::memcpy(&h, tt.data + 2ull * (size_t)k, 2); v = half_to_float(h); }
+        (*out)[(size_t)((int64_t)r * cols + tt.sp_indices[(size_t)k])] = v;
+      }
+    return true;
+  }
   out->resize((size_t)n);
   if (tt.type == TT_F32) {
     if ((int64_t)tt.nbytes < n * 4) return false;

@@ -29,6 +29,11 @@ struct TfTensor {
   const uint8_t* data = nullptr;
   size_t nbytes = 0;
   bool has_sparsity = false;
+  // SparsityParameters (Tensor field 6) of the sparse full-range detector's 1x1 weights: row-major CSR on the last
+  // dimension -- `segments` over the flattened outer dimensions, `indices` = positions in the last dimension; `data`
+  // then holds only the stored values.  sparse_ok is false for any other layout (-> the model is rejected).
+  bool sparse_ok = false;
+  std::vector<int32_t> sp_segments, sp_indices;
   int64_t elems() const { int64_t n = 1; for (int d : shape) n *= d; return n; }
 };
 
@@ -43,6 +48,7 @@ struct TfOp {
   int filter_w = 0, filter_h = 0;
   int fused_act = 0;
   int axis = 0;
+  int block_size = 0;       // DEPTH_TO_SPACE
   std::vector<int> new_shape;
   bool align_corners = false, half_pixel_centers = false;
 };
@@ -56,7 +62,8 @@ struct TfModel {
 
   // Returns false and fills `err` on any malformed offset / unsupported construct.
   bool load(const std::string& path, std::string* err);
-  // Constant tensor as f32 (widening f16 exactly, i.e. a folded DEQUANTIZE).
+  // Constant tensor as f32 (widening f16 exactly, i.e. a folded DEQUANTIZE; sparse tensors are expanded first, i.e. a
+  // folded DENSIFY: tensorflow/lite/kernels/densify.cc).
   bool const_f32(int tensor, std::vector<float>* out) const;
   bool const_i32(int tensor, std::vector<int>* out) const;
 };

@@ -21,6 +21,7 @@ NETS = {
     "face_detection_full_range": 192,
     "face_landmark": 192,
     "iris_landmark": 64,
+    "face_detection_full_range_sparse": 192,     # DENSIFY / spatial PAD / fused RELU / DEPTH_TO_SPACE
 }
 
 

@@ -61,7 +61,7 @@ def test_reference_call_sequence_on_man(fdl, gpu, man, oracle_pipeline):
         o.close()
 
 
-@pytest.mark.parametrize("model", [0, 2, 3])
+@pytest.mark.parametrize("model", [0, 2, 3, 4])
 def test_other_detectors_on_man(fdl, gpu, man, model):
     from oracle import pipeline
     det = fdl.FaceDetection(fdl.FaceDetectionModel(model), MODELS, device=gpu)
@@ -154,7 +154,7 @@ def test_detection_only_pipeline_and_errors(fdl, gpu):
     with pytest.raises(fdl.FdlError):
         pipe.run(synth_frames.noise_frames(5, 640, 480))       # more than max_batch
     with pytest.raises(fdl.FdlError):
-        fdl.FaceDetection(fdl.FaceDetectionModel.FullSparse, MODELS, device=gpu)   # outside the hot path
+        fdl.FaceDetection(7, MODELS, device=gpu)                # "unsupported model type" (face_detection.rs:184)
     with pytest.raises(fdl.FdlError) as e:
         fdl.FaceLandmark("/nonexistent/face_landmark.tflite", device=gpu)
     assert e.value.code == -2

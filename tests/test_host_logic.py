@@ -13,7 +13,7 @@ import pytest
 from conftest import MODELS, ROOT, rng
 
 MODEL_FILES = ["face_detection_short_range", "face_detection_front", "face_detection_back", "face_detection_full_range", "face_landmark",
-               "iris_landmark"]
+               "iris_landmark", "face_detection_full_range_sparse"]
 
 
 def test_library_exports_every_declared_symbol(fdl):
@@ -74,7 +74,7 @@ def test_planner_covers_every_op_and_matches_oracle_reader(fdl, name):
     covered = []
     for line in text.splitlines()[1:]:
         covered += [int(v) for v in re.search(r"ops=\[([\d,]*)\]", line).group(1).split(",") if v]
-    folded = {T.DEQUANTIZE, T.RESHAPE, T.CONCATENATION}
+    folded = {T.DEQUANTIZE, T.RESHAPE, T.CONCATENATION, T.DENSIFY}
     expect = [i for i, op in enumerate(m.ops) if op.code not in folded]
     assert sorted(covered) == expect
     # FLOPs of conv + depthwise ops from the oracle reader
@@ -320,3 +320,41 @@ def test_iris_metrics_host_math_matches_oracle():
     iris = np.array([[0.5, 0.5, 0], [0.475, 0.5, 0], [0.5, 0.47, 0], [0.525, 0.5, 0], [0.5, 0.53, 0]])
     assert abs(glue.get_iris_diameter(iris, (w, h)) - 8.0) < 1e-12
     assert abs(glue.get_iris_depth(iris, 5.0, 8.0, (w, h)) - 11.8 * 5.0 / 8.0) < 1e-12
+
+
+# ---- sparse full-range detector: DENSIFY, spatial PAD, fused RELU, DEPTH_TO_SPACE ------------------
+def test_sparse_model_densify_and_plan(fdl):
+    """The oracle's CSR decode of the 46 sparse f16 weight tensors (277 552 B stored) gives dense tensors of the dense
+    model's shapes with the stored number of non-zeros; the C++ planner folds DENSIFY / spatial PAD / fused RELU and
+    plans DEPTH_TO_SPACE; both detectors' heads end up as branch streams."""
+    from oracle import tflite_reader as T
+    m = T.load(os.path.join(MODELS, "face_detection_full_range_sparse.tflite"))
+    sparse = [t for t in m.tensors if t.sparsity is not None]
+    assert len(sparse) == 46 and all(t.dtype == np.float16 for t in sparse)
+    stored = 0
+    for t in sparse:
+        d = T.densify(t)
+        assert list(d.shape) == t.shape and d.dtype == np.float16
+        nnz = len(t.sparsity["dims"][-1][3])
+        assert np.count_nonzero(d) <= nnz <= d.size          # stored entries may themselves be zero
+        # every stored value sits where the index vector says
+        seg, idx = t.sparsity["dims"][-1][2], t.sparsity["dims"][-1][3]
+        flat = d.reshape(-1, t.shape[-1])
+        r = int(np.searchsorted(seg, nnz // 2, side="right") - 1)
+        assert flat[r, idx[nnz // 2]] == t.data.reshape(-1)[nnz // 2]
+        stored += nnz
+    dense_elems = sum(int(np.prod(t.shape)) for t in sparse)
+    assert stored < 0.5 * dense_elems                        # the model really is pruned
+    from collections import Counter
+    hist = Counter(op.code for op in m.ops)
+    assert hist[T.DENSIFY] == 46 and hist[T.DEPTH_TO_SPACE] == 2 and hist[T.PAD] == 43
+    net = fdl.Net(os.path.join(MODELS, "face_detection_full_range_sparse.tflite"), device=-1)
+    text = net.describe()
+    assert text.count("DEPTH_TO_SPACE x2") == 2 and "CONV 3x3/s2 3->32 in 192x192 out 96x96 pad(t1,l1) act=relu" in text
+    assert "stream=1" in text and net.num_steps < 60
+    net.close()
+    # unsupported sparse layouts are rejected, not mis-read
+    t = sparse[0]
+    bad = T.Tensor(t.index, t.name, t.shape, t.dtype, t.buffer, t.data, dict(t.sparsity, traversal_order=[3, 2, 1, 0]))
+    with pytest.raises(NotImplementedError):
+        T.densify(bad)

@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import rs_face_detection_tflite_b200 as fdl
-SIZES = {'face_detection_back': 256, 'face_landmark': 192, 'iris_landmark': 64, 'face_detection_full_range': 192, 'face_detection_short_range': 128}
+SIZES = {'face_detection_back': 256, 'face_landmark': 192, 'iris_landmark': 64, 'face_detection_full_range': 192, 'face_detection_short_range': 128, 'face_detection_full_range_sparse': 192}
 name, batch = sys.argv[1], int(sys.argv[2])
 mode = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 5
