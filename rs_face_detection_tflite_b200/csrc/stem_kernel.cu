@@ -182,12 +182,14 @@ bool stem_supported(const ConvArgs& a) {
   // 16-byte cp.async of the input rows: row length, batch stride and base must be multiples of 4 floats
   if ((a.in.W * 3) % 4 != 0 || a.in.bstride % 4 != 0 || (reinterpret_cast<uintptr_t>(a.in.p) & 15) != 0) return false;
   StemCfg c = stem_cfg(a);
-  if (c.shift != (a.kh == 5 ? 1 : 0)) return false;   // instantiated: <5,5,1> (SAME pad 1) and <3,3,0> (pad 0)
+  // instantiated: <5,5,1> (SAME, pad 1), <3,3,0> (SAME on even sizes, pad 0) and <3,3,1> (explicit pad 1: sparse full-range stem)
+  if (!((a.kh == 5 && c.shift == 1) || (a.kh == 3 && (c.shift == 0 || c.shift == 1)))) return false;
   return c.threads <= 512 && c.threads % 32 == 0 && c.smem <= 96 * 1024;
 }
 
 cudaError_t stem_kernels_init() {
   cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel<5, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_conv_kernel<3, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(stem_conv_kernel<3, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
 }
@@ -198,11 +200,13 @@ cudaError_t launch_stem_conv(const ConvArgs& a, cudaStream_t stream) {
   if (total == 0) return cudaSuccess;
   int per_sm = 1;
   if (a.kh == 5) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stem_conv_kernel<5, 5, 1>, c.threads, c.smem);
+  else if (c.shift == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stem_conv_kernel<3, 3, 1>, c.threads, c.smem);
   else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stem_conv_kernel<3, 3, 0>, c.threads, c.smem);
   if (per_sm < 1) per_sm = 1;
   const unsigned grid = (unsigned)(total < (long long)persist_sms() * per_sm ? total : (long long)persist_sms() * per_sm);     // persistent CTAs
   cudaError_t e;
   if (a.kh == 5) e = launch_pdl(stem_conv_kernel<5, 5, 1>, dim3(grid), dim3(c.threads), c.smem, stream, a, c.TWo, c.tiles_x, c.tiles_y);
+  else if (c.shift == 1) e = launch_pdl(stem_conv_kernel<3, 3, 1>, dim3(grid), dim3(c.threads), c.smem, stream, a, c.TWo, c.tiles_x, c.tiles_y);
   else e = launch_pdl(stem_conv_kernel<3, 3, 0>, dim3(grid), dim3(c.threads), c.smem, stream, a, c.TWo, c.tiles_x, c.tiles_y);
   count_launch();
   return e;
