@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "net_kernels.cuh"
 #include "pdl.h"
@@ -160,7 +161,9 @@ StemCfg stem_cfg(const ConvArgs& a) {
   StemCfg c;
   const int cgs = a.N / 8;
   // widest tile that keeps the CTA at <= 512 threads; prefer the one that wastes fewer columns
+  static const int tw_env = getenv("FDL_STEM_TW") ? atoi(getenv("FDL_STEM_TW")) : 0;   // A/B timing: force 32- or 64-wide tiles
   c.TWo = (a.out.W % 64 == 0 && kTileH * 16 * cgs <= 512) ? 64 : 32;
+  if (tw_env == 32 || (tw_env == 64 && a.out.W % 64 == 0 && kTileH * 16 * cgs <= 512)) c.TWo = tw_env;
   c.threads = kTileH * (c.TWo / 4) * cgs;
   c.tiles_x = (a.out.W + c.TWo - 1) / c.TWo;
   c.tiles_y = (a.out.H + kTileH - 1) / kTileH;
