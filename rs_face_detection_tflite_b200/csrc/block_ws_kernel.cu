@@ -59,24 +59,26 @@ constexpr int kMaxThreads = 512;
 constexpr int kMaxStages = 6, kMaxGroups = 3;
 constexpr int kMaxSmemWs = 227 * 1024;
 
-struct WsCfg { int G, ipt, ndwg, NS, OB, threads, total, ctas, in_pad; };
+struct WsCfg { int G, ipt, ndwg, NS, OB, threads, total, ctas, in_pad, f16; };
 struct WsLayout { int alpha, w, wb, ones, in0, in_stage, a0, a_buf, out0, out_stage, total; };
 
 __host__ __device__ inline int align_up_w(int v, int a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline WsLayout ws_layout(int C, int N, int Np, int wsplit, int NS, int G, int OB, int in_pad) {
+// f16: the A operand is one plane set of (f16 hi, f16 lo) pairs (half the bytes), `wsplit` counts the f16 weight copies, and
+// the bias is added in the epilogue (no bias K step: no `wb` / `ones` regions).
+__host__ __device__ inline WsLayout ws_layout(int C, int N, int Np, int wsplit, int NS, int G, int OB, int in_pad, int f16) {
   WsLayout L;
   int off = 256;                                // barriers + tmem slot
   L.alpha = off; off += Np * 4;
   off = align_up_w(off, 128);
   L.w = off; off += wsplit * (C / 4) * Np * 16;
-  L.wb = off; off += 2 * Np * 16;               // bias as one more K step of B: [2 quads][Np][4] = (b_hi, b_lo, 0, 0), 0
+  L.wb = off; if (!f16) off += 2 * Np * 16;     // bias as one more K step of B: [2 quads][Np][4] = (b_hi, b_lo, 0, 0), 0
   off = align_up_w(off, 128);
-  L.ones = off; off += 2 * plane_bytes(C);         // the matching A planes: (1, 1, 0, 0) for every pixel, then zeros
+  L.ones = off; if (!f16) off += 2 * plane_bytes(C);   // the matching A planes: (1, 1, 0, 0) for every pixel, then zeros
   off = align_up_w(off, 128);
   L.in_stage = align_up_w(ITH * ITW * (in_pad ? ((C / 4) | 1) * 4 : C) * 4, 128);   // in_pad: pixel stride = odd number of 16-byte quads
   L.in0 = off; off += NS * L.in_stage;
-  L.a_buf = align_up_w(2 * (C / 4) * plane_bytes(C), 128);   // hi planes then lo planes
+  L.a_buf = align_up_w((f16 ? 1 : 2) * (C / 4) * plane_bytes(C), 128);   // tf32: hi planes then lo planes; f16: one set of (hi, lo) planes
   L.a0 = off; off += G * L.a_buf;
   L.out_stage = align_up_w(TH * TW * ((N / 4) | 1) * 16, 128);   // raw accumulator tile, pixel stride = odd number of quads
   L.out0 = off; off += OB * L.out_stage;
@@ -93,6 +95,17 @@ __device__ __forceinline__ ull fma2(ull a, ull b, ull c) {
   return d;
 }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// (c0, c1) -> f16x2 with c0 in the low half (the lower address), round to nearest even, saturating instead of overflowing
+__device__ __forceinline__ uint32_t pack_f16x2(float c0, float c1) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(c1), "f"(c0));
+  return d;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t d) {
+  float2 r;
+  asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}\n" : "=f"(r.x), "=f"(r.y) : "r"(d));
+  return r;
+}
 
 template <int kMaxT, int kMinB>
 __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
@@ -102,7 +115,9 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
   const int C = a.C, N = a.N, Np = a.Np, Q = C >> 2;
   const int NS = a.stages, G = a.groups, ndwg = a.dw_threads;
   const int kPlaneBytes = plane_bytes(C);
-  const WsLayout L = ws_layout(C, N, Np, a.wsplit, NS, G, a.out_bufs, a.in_pad);
+  const bool f16 = a.f16 != 0;
+  const int wcopies = f16 ? a.wsplit16 : a.wsplit;
+  const WsLayout L = ws_layout(C, N, Np, wcopies, NS, G, a.out_bufs, a.in_pad, a.f16);
   const int T = G > 2 ? G : 2;                  // TMEM accumulators: tile it -> buffer it % T (== its group when G >= 2, so each
                                                 // buffer has ONE issuing thread and its full/empty phases stay in lockstep)
   uint64_t* in_full = reinterpret_cast<uint64_t*>(smem);             // [kMaxStages]  TMA tile landed
@@ -136,19 +151,21 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     ptx::fence_mbar_init();
   }
   if (warp == 0) ptx::tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
-  for (int i = tid; i < Np; i += blockDim.x) {
-    const float bv = i < N ? a.bias[i] : 0.f;
-    const float bh = __uint_as_float(__float_as_uint(bv) & 0xffffe000u);
-    reinterpret_cast<float4*>(smem + L.wb)[i] = make_float4(bh, bv - bh, 0.f, 0.f);
-    reinterpret_cast<float4*>(smem + L.wb)[Np + i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  for (int i = tid; i < TH * TW; i += blockDim.x) {
-    *reinterpret_cast<float4*>(smem + L.ones + i * 16) = make_float4(1.f, 1.f, 0.f, 0.f);
-    *reinterpret_cast<float4*>(smem + L.ones + kPlaneBytes + i * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!f16) {
+    for (int i = tid; i < Np; i += blockDim.x) {
+      const float bv = i < N ? a.bias[i] : 0.f;
+      const float bh = __uint_as_float(__float_as_uint(bv) & 0xffffe000u);
+      reinterpret_cast<float4*>(smem + L.wb)[i] = make_float4(bh, bv - bh, 0.f, 0.f);
+      reinterpret_cast<float4*>(smem + L.wb)[Np + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = tid; i < TH * TW; i += blockDim.x) {
+      *reinterpret_cast<float4*>(smem + L.ones + i * 16) = make_float4(1.f, 1.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(smem + L.ones + kPlaneBytes + i * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   {  // pointwise weights: already in UMMA core-matrix order in global memory -> straight copy
-    const int n4 = a.wsplit * Q * Np;
-    const float4* src = reinterpret_cast<const float4*>(a.w_umma);
+    const int n4 = wcopies * Q * Np;
+    const float4* src = reinterpret_cast<const float4*>(f16 ? a.w_f16 : a.w_umma);
     float4* dst = reinterpret_cast<float4*>(s_w);
     for (int i = tid; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
   }
@@ -177,12 +194,22 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     const int p = tid;                          // TMEM lane (warp w may access lanes 32w..32w+31)
     const int py = p / TW, px = p - py * TW;
     const int NPf = ((N >> 2) | 1) << 2;        // staging pixel stride (floats)
-    int tile = blockIdx.x;
     int pb = 0, pty = 0, ptx_ = 0;              // coordinates of the previous tile (its TMA store is issued one tile late)
-    for (int it = 0; it < my_tiles; ++it, tile += gridDim.x) {
+    // tile coordinates advance by a fixed (image, row, column) step per iteration: no divisions inside the loop
+    int b, ty, tx;
+    {
+      const int t0 = (int)blockIdx.x, r0 = t0 % tiles_per_img;
+      b = t0 / tiles_per_img; ty = r0 / a.tiles_x; tx = r0 - ty * a.tiles_x;
+    }
+    const int step_b = (int)gridDim.x / tiles_per_img, step_r = (int)gridDim.x - step_b * tiles_per_img;
+    const int step_y = step_r / a.tiles_x, step_x = step_r - step_y * a.tiles_x;
+    for (int it = 0; it < my_tiles; ++it) {
       const int s = it % NS, t = it % T, ob = it & 1;
-      const int b = tile / tiles_per_img, rr = tile - b * tiles_per_img;
-      const int ty = rr / a.tiles_x, tx = rr - ty * a.tiles_x;
+      if (it > 0) {
+        tx += step_x; ty += step_y; b += step_b;
+        if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
+        if (ty >= a.tiles_y) { ty -= a.tiles_y; ++b; }
+      }
       const int oy = ty * TH + py, ox = tx * TW + px;
       const bool inside = oy < a.H && ox < a.W;
       const float* skip_smem = reinterpret_cast<const float*>(smem + L.in0 + s * L.in_stage) + ((py + 1) * ITW + (px + 1)) * CP;
@@ -206,20 +233,44 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       load_res(0, res);
       ptx::mbar_wait(&acc_full[t], (uint32_t)((it / T) & 1));
       ptx::tc_fence_after_sync();
+      // Early refill (FDL_WS_EARLY=1; off by default -- like a fourth input stage it measured SLOWER, 246 vs 237 us on the 128x128x24
+      // stage: the kernel is not short of loads in flight): when the whole residual of this tile is already in registers (one batch: <= 32 channels) or does not
+      // come from the input stage at all, the stage of THIS tile is dead once the accumulator is complete (the depthwise warps
+      // have read it, or the MMAs could not have run) -- so the load NS tiles ahead is issued here, one whole tile period
+      // earlier than "after the epilogue of the tile".  The residual registers are consumed first so that their shared-memory
+      // loads have landed before the barrier below lets thread 0 hand the stage back to the TMA unit.
+      const bool early = a.early_refill && (a.skip_mode != 1 || a.skip_c <= 32);
+      if (early && a.skip_mode == 1) {
+        float chk = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) chk += res[j].x;
+        asm volatile("" ::"f"(chk) : "memory");
+      }
       // ---- deferred TMA store of the PREVIOUS tile: its staging writes have had a whole tile to drain ----
       {
         ptx::fence_proxy_async_smem();
         if (tid == 0) ptx::tma_store_wait_read0();            // the store of tile it-2 has finished reading buffer `ob`
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid == 0 && it > 0) {
-          ptx::tma_store_4d(&tm_out, smem + L.out0 + (ob ^ 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
-          ptx::tma_store_commit();
-          // every epilogue warp is past its residual reads of the previous tile's stage: refill it
-          if (it - 1 + NS < my_tiles) issue_load(it - 1 + NS);
+        if (tid == 0) {
+          if (it > 0) {
+            ptx::tma_store_4d(&tm_out, smem + L.out0 + (ob ^ 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
+            ptx::tma_store_commit();
+          }
+          if (early) {
+            if (it + NS < my_tiles) issue_load(it + NS);
+          } else if (it > 0 && it - 1 + NS < my_tiles) {
+            issue_load(it - 1 + NS);   // every epilogue warp is past its residual reads of the PREVIOUS tile's stage: refill that one
+          }
         }
       }
       pb = b; pty = ty; ptx_ = tx;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * acc_cols);
+      if (a.dbg & 4) {
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[t]);
+        continue;
+      }
       for (int c0 = 0; c0 < Np; c0 += 32) {
         if (c0 + 32 < Np) load_res(c0 + 32, resn);
 #pragma unroll
@@ -238,7 +289,8 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
           for (int j = 0; j < 4; ++j) {
             const int n = ch + 4 * j;
             if (n >= N) break;
-            const float4 rs = res[4 * h + j];
+            float4 rs = res[4 * h + j];
+            if (f16) { rs.x += a.bias_c[n]; rs.y += a.bias_c[n + 1]; rs.z += a.bias_c[n + 2]; rs.w += a.bias_c[n + 3]; }   // tf32 mode: bias came as a K step
             float4 o = make_float4(__uint_as_float(r[4 * j]) + rs.x, __uint_as_float(r[4 * j + 1]) + rs.y, __uint_as_float(r[4 * j + 2]) + rs.z,
                                    __uint_as_float(r[4 * j + 3]) + rs.w);
             if (a.act == ACT_RELU) {
@@ -267,9 +319,12 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     // ================= depthwise 3x3 -> A operand (hi / lo planes) -> MMA issue =================
     const int dtid = tid - kEpiThreads;
     const int g = dtid / ndwg, gt = dtid - g * ndwg;
-    const bool map6 = Q == 6 && ndwg == 192;    // one item per thread, remapped for conflict-free stores (see kMapQ6)
+    // Q == 6, one item per thread: with the plain 6-quad pixel stride the items are remapped for conflict-free stores (kMapQ6);
+    // with the padded 7-quad stride (f16 mode: shared memory allows it) "x fastest" is conflict-free for loads AND stores.
+    const bool xfast = Q == 6 && ndwg == 192 && a.in_pad;
+    const bool map6 = Q == 6 && ndwg == 192 && !a.in_pad;
     const int m6 = map6 ? kMapQ6[gt % 96] : 0;
-    const int q = map6 ? (m6 & 15) : gt % Q;    // ndwg % Q == 0: the channel quad is fixed per thread
+    const int q = map6 ? (m6 & 15) : (xfast ? (gt / TW) % Q : gt % Q);    // the channel quad is fixed per thread
     ull wd[9][2], bd[2];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
@@ -284,10 +339,10 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     const float2 neg1f = make_float2(-1.f, -1.f);
     const ull kNeg1 = *reinterpret_cast<const ull*>(&neg1f);
     uint8_t* s_ahi = smem + L.a0 + g * L.a_buf;
-    uint8_t* s_alo = s_ahi + Q * kPlaneBytes;
+    uint8_t* s_alo = s_ahi + Q * kPlaneBytes;   // tf32 mode only
     const int nitems = Q * 2 * TW;
     // MMA issue state (used by the group's first thread only)
-    const uint32_t idesc = ptx::umma_idesc_tf32(128, Np);
+    const uint32_t idesc = f16 ? ptx::umma_idesc_f16(128, Np) : ptx::umma_idesc_tf32(128, Np);
     const uint32_t w_addr = ptx::smem_u32(s_w), wb_addr = ptx::smem_u32(smem + L.wb), ones_addr = ptx::smem_u32(smem + L.ones);
     const uint32_t w_lbo = (uint32_t)Np * 16u;
     const uint32_t ahi_addr = ptx::smem_u32(s_ahi), alo_addr = ahi_addr + (uint32_t)(Q * kPlaneBytes);
@@ -295,9 +350,12 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       const int s = it % NS, kg = it / G, t = it % T;
       ptx::mbar_wait(&in_full[s], (uint32_t)((it / NS) & 1));
       const float* s_in = reinterpret_cast<const float*>(smem + L.in0 + s * L.in_stage);
-      for (int item = gt, ii = 0; item < nitems; item += ndwg, ++ii) {
-        const int xr = item / Q;                // item % Q == q
-        const int x = map6 ? (m6 >> 4) : xr % TW, half = map6 ? item / 96 : xr / TW;
+      if ((a.dbg & 1) && kg > 0) ptx::mbar_wait(&a_empty[g], (uint32_t)((kg - 1) & 1));
+      for (int item = gt, ii = 0; item < nitems && !(a.dbg & 1); item += ndwg, ++ii) {
+        int x, half;                            // (runtime divisions by Q only on the generic path)
+        if (map6) { x = m6 >> 4; half = item / 96; }
+        else if (xfast) { x = item % TW; half = item / 96; }
+        else { const int xr = item / Q; x = xr % TW; half = xr / TW; }   // item % Q == q
         ull acc[4][2];
 #pragma unroll
         for (int o = 0; o < 4; ++o) { acc[o][0] = bd[0]; acc[o][1] = bd[1]; }
@@ -331,14 +389,28 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
         }
         // the MMAs of this group's previous tile must have finished reading the A buffer
         if (ii == 0 && kg > 0) ptx::mbar_wait(&a_empty[g], (uint32_t)((kg - 1) & 1));
+        if (f16) {
+          // (f16 hi, f16 lo) of the four channels in ONE 16-byte core-matrix row: K' = (hi c0..c3, lo c0..c3)
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-          const int p = (half * 4 + o) * TW + x;
-          ulonglong2 hi, lo;
-          hi.x = acc[o][0] & kMaskHi; hi.y = acc[o][1] & kMaskHi;
-          lo.x = fma2(hi.x, kNeg1, acc[o][0]); lo.y = fma2(hi.y, kNeg1, acc[o][1]);
-          *reinterpret_cast<ulonglong2*>(s_ahi + q * kPlaneBytes + p * 16) = hi;
-          *reinterpret_cast<ulonglong2*>(s_alo + q * kPlaneBytes + p * 16) = lo;
+          for (int o = 0; o < 4; ++o) {
+            const int p = (half * 4 + o) * TW + x;
+            const float2 c01 = *reinterpret_cast<const float2*>(&acc[o][0]), c23 = *reinterpret_cast<const float2*>(&acc[o][1]);
+            uint4 v;
+            v.x = pack_f16x2(c01.x, c01.y); v.y = pack_f16x2(c23.x, c23.y);
+            const float2 h01 = unpack_f16x2(v.x), h23 = unpack_f16x2(v.y);
+            v.z = pack_f16x2(c01.x - h01.x, c01.y - h01.y); v.w = pack_f16x2(c23.x - h23.x, c23.y - h23.y);
+            *reinterpret_cast<uint4*>(s_ahi + q * kPlaneBytes + p * 16) = v;
+          }
+        } else {
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const int p = (half * 4 + o) * TW + x;
+            ulonglong2 hi, lo;
+            hi.x = acc[o][0] & kMaskHi; hi.y = acc[o][1] & kMaskHi;
+            lo.x = fma2(hi.x, kNeg1, acc[o][0]); lo.y = fma2(hi.y, kNeg1, acc[o][1]);
+            *reinterpret_cast<ulonglong2*>(s_ahi + q * kPlaneBytes + p * 16) = hi;
+            *reinterpret_cast<ulonglong2*>(s_alo + q * kPlaneBytes + p * 16) = lo;
+          }
         }
       }
       ptx::fence_proxy_async_smem();            // generic-proxy writes of A -> visible to the tensor core (async proxy)
@@ -349,6 +421,26 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
         if (it >= T) ptx::mbar_wait(&acc_empty[t], (uint32_t)(((it / T) - 1) & 1));
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(t * acc_cols);
+        if (a.dbg & 2) {
+          ptx::mma_commit(&acc_full[t]);
+          ptx::mma_commit(&a_empty[g]);
+          continue;
+        }
+        if (f16) {
+          // kind::f16, K = 16 = two planes = two channel quads x (hi, lo); pass 0: (A_hi, A_lo) * (W, W), pass 1: (A_hi, A_lo) * (W_lo, 0)
+          const int ksteps16 = Q >> 1;
+          for (int pass = 0; pass < a.wsplit16; ++pass) {
+            const uint32_t b_base = w_addr + (uint32_t)(pass * Q * Np * 16);
+            for (int ks = 0; ks < ksteps16; ++ks) {
+              const uint64_t ad = ptx::umma_desc_kmajor(ahi_addr + (uint32_t)(ks * 2 * kPlaneBytes), kPlaneBytes, 128);
+              const uint64_t bdsc = ptx::umma_desc_kmajor(b_base + (uint32_t)ks * 2u * w_lbo, w_lbo, 128);
+              ptx::mma_f16(d_tmem, ad, bdsc, idesc, (pass | ks) ? 1u : 0u);
+            }
+          }
+          ptx::mma_commit(&acc_full[t]);
+          ptx::mma_commit(&a_empty[g]);
+          continue;
+        }
         // bias K step first (overwrites the accumulator), then the hi / lo passes accumulate
         ptx::mma_tf32(d_tmem, ptx::umma_desc_kmajor(ones_addr, kPlaneBytes, 128), ptx::umma_desc_kmajor(wb_addr, w_lbo, 128), idesc, 0u);
         const int ksteps = C >> 3;
@@ -377,7 +469,13 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
 // Depthwise thread organisation per channel-quad count: G groups of ndwg threads, ipt items per thread and tile, and
 // how many CTAs share an SM.  Small channel counts (little work per tile, latency-dominated) run TWO smaller CTAs per SM
 // so that two epilogues and two depthwise groups are in flight; larger ones run one CTA with up to 12 depthwise warps.
-bool pick_cfg(int C, int N, int Np, int wsplit, WsCfg* cfg) {
+// f16-split A operand (FDL_WS_F16, default on): see BlockTcArgs::f16.
+bool ws_f16_enabled() {
+  static const bool on = [] { const char* e = getenv("FDL_WS_F16"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
+
+bool pick_cfg(int C, int N, int Np, int wsplit, int f16, WsCfg* cfg) {
   const int Q = C / 4;
   int G = 1, ipt = 1, ctas = 1;
   switch (Q) {
@@ -391,16 +489,20 @@ bool pick_cfg(int C, int N, int Np, int wsplit, WsCfg* cfg) {
       }
       break;
   }
-  const int in_pad = (Q % 8 == 0) ? 1 : 0;     // padding the pixel stride keeps the depthwise loads conflict-free only when Q % 8 == 0
+  // Padding the pixel stride to an odd number of quads makes the epilogue's residual reads conflict-free.  The depthwise loads
+  // stay conflict-free with it when Q % 8 == 0 (quad-fastest items) and, for Q == 6, with "x fastest" items -- which only fits
+  // next to two CTAs per SM in f16 mode (smaller A operand, no bias planes).
+  static const int pad6 = getenv("FDL_WS_PAD6") ? atoi(getenv("FDL_WS_PAD6")) : 1;   // A/B: padded stride + 3 stages vs plain stride + 4 stages
+  const int in_pad = (Q % 8 == 0 || (f16 && Q == 6 && pad6)) ? 1 : 0;
   const int budget = ctas == 2 ? (233472 / 2 - 1024) : kMaxSmemWs;
   for (; G >= 1; --G) {
     const int ndwg = 32 * Q / ipt;
     if (kEpiThreads + G * ndwg > (ctas == 2 ? 320 : kMaxThreads)) continue;
     for (int NS = (G + 3 < kMaxStages ? G + 3 : kMaxStages); NS >= G + 2; --NS) {   // the refill of a stage trails its tile by one epilogue
-      WsLayout L = ws_layout(C, N, Np, wsplit, NS, G, 2, in_pad);
+      WsLayout L = ws_layout(C, N, Np, wsplit, NS, G, 2, in_pad, f16);
       if (L.total <= budget) {
         cfg->G = G; cfg->ipt = ipt; cfg->ndwg = ndwg; cfg->NS = NS; cfg->OB = 2; cfg->threads = kEpiThreads + G * ndwg; cfg->total = L.total;
-        cfg->ctas = ctas; cfg->in_pad = in_pad;
+        cfg->ctas = ctas; cfg->in_pad = in_pad; cfg->f16 = f16;
         return true;
       }
     }
@@ -427,16 +529,23 @@ bool block_ws_supported(const Step& s) {
     return false;
   if (s.skip.tensor >= 0 && (s.skip_pool || s.skip_c % 4 != 0 || s.skip.offset != 0)) return false;
   WsCfg cfg;
-  return pick_cfg(C, N, s.Np, s.wsplit, &cfg);
+  const int f16 = (ws_f16_enabled() && s.w_f16 >= 0) ? 1 : 0;
+  return pick_cfg(C, N, s.Np, f16 ? s.wsplit16 : s.wsplit, f16, &cfg);
 }
 
 cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   BlockTcArgs a = l.args;
   WsCfg cfg;
-  if (!pick_cfg(a.C, a.N, a.Np, a.wsplit, &cfg)) return cudaErrorInvalidConfiguration;
+  a.f16 = (ws_f16_enabled() && a.w_f16 != nullptr && l.bias_host != nullptr) ? 1 : 0;
+  if (!pick_cfg(a.C, a.N, a.Np, a.f16 ? a.wsplit16 : a.wsplit, a.f16, &cfg)) return cudaErrorInvalidConfiguration;
   a.stages = cfg.NS; a.groups = cfg.G; a.dw_threads = cfg.ndwg; a.out_bufs = cfg.OB; a.in_pad = cfg.in_pad;
   a.pad = 1;
+  static const int dbg_env = getenv("FDL_WS_DBG") ? atoi(getenv("FDL_WS_DBG")) : 0;
+  a.dbg = dbg_env;
+  static const int early_env = getenv("FDL_WS_EARLY") ? atoi(getenv("FDL_WS_EARLY")) : 0;   // measured slower on B200 (r01ag): off by default
+  a.early_refill = early_env;
   for (int i = 0; i < 128; ++i) a.alpha_c[i] = (l.alpha_host && i < a.N) ? l.alpha_host[i] : 0.f;
+  for (int i = 0; i < 128; ++i) a.bias_c[i] = (a.f16 && i < a.N) ? l.bias_host[i] : 0.f;
   CUtensorMap tm_in, tm_out;
   if (!encode_nhwc(&tm_in, l.in, a.B, a.H, a.W, a.C, (long long)a.H * a.W * a.C, ITH, ITW, cfg.in_pad ? ((a.C / 4) | 1) * 4 : a.C)) return cudaErrorInvalidValue;
   if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW, ((a.N / 4) | 1) * 4)) return cudaErrorInvalidValue;
@@ -457,8 +566,8 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   count_launch();
   static const bool verbose = getenv("FDL_WS_VERBOSE") != nullptr;
   if (verbose)
-    fprintf(stderr, "[ws C=%d N=%d %dx%d G=%d NS=%d ctas=%d thr=%d smem=%d in_pad=%d]\n", a.C, a.N, a.H, a.W, cfg.G, cfg.NS, cfg.ctas, cfg.threads, cfg.total,
-            cfg.in_pad);
+    fprintf(stderr, "[ws C=%d N=%d %dx%d G=%d NS=%d ctas=%d thr=%d smem=%d in_pad=%d f16=%d]\n", a.C, a.N, a.H, a.W, cfg.G, cfg.NS, cfg.ctas, cfg.threads,
+            cfg.total, cfg.in_pad, cfg.f16);
   return e;
 }
 

@@ -33,6 +33,15 @@ struct BlockTcArgs {
   int acc_cols = 32;               // block_ws_kernel: TMEM columns per accumulator buffer
   int in_pad = 0;                  // block_ws_kernel: input tile pixel stride padded to an odd number of quads
   int tc_cp = 0, tc_np = 0;        // blaze_block_tc_kernel: pixel strides (floats) of the input / output staging tiles (>= C / N)
+  // block_ws_kernel, f16-split mode: the depthwise result is written as ONE plane set of (f16 hi, f16 lo) pairs and multiplied
+  // with tcgen05 kind::f16 (half the A-operand bytes in shared memory of the tf32 hi / lo planes, same 2^-22 fidelity)
+  int early_refill = 0;            // block_ws_kernel: refill a tile's input stage as soon as its accumulator is complete (see the kernel)
+  int dbg = 0;                     // block_ws_kernel, FDL_WS_DBG (timing experiments only, results are garbage): 1 skip the depthwise,
+                                   // 2 skip the MMAs, 4 skip the epilogue's accumulator read / arithmetic / staging stores
+  int f16 = 0;
+  int wsplit16 = 1;                // 1: weights f16-exact; 2: + (w - f16(w)) against the hi half
+  const float* w_f16 = nullptr;    // [wsplit16][C/4][Np][8 halves] (Step::w_f16)
+  float bias_c[128] = {};          // f16 mode: pointwise bias by value (added in the epilogue, not as a K step)
   const int* n_active = nullptr;
   float alpha_c[128] = {};         // block_ws_kernel: PRELU slopes by value (read through the constant bank in the epilogue)
 };
@@ -40,6 +49,7 @@ struct BlockTcArgs {
 struct BlockTcLaunch {
   BlockTcArgs args;
   const float* alpha_host = nullptr;   // host copy of the PRELU slopes [N] (block_ws_kernel passes them as kernel parameters)
+  const float* bias_host = nullptr;    // host copy of the pointwise bias [N] (block_ws_kernel, f16 mode)
   const float* in = nullptr;       // [B,H,W,C]
   float* out = nullptr;            // [B,H,W,N]
 };

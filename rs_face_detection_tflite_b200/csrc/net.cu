@@ -121,6 +121,8 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const 
       a.w_umma = d_weights_ + s.w_umma; a.bias = d_weights_ + s.b; a.w_dw = d_weights_ + s.w_dw; a.b_dw = d_weights_ + s.b_dw;
       a.alpha = s.alpha >= 0 ? d_weights_ + s.alpha : nullptr;
       l.alpha_host = s.alpha >= 0 ? plan_.weights.data() + s.alpha : nullptr;
+      l.bias_host = plan_.weights.data() + s.b;
+      if (s.w_f16 >= 0) { a.w_f16 = d_weights_ + s.w_f16; a.wsplit16 = s.wsplit16; }
       a.C = s.in.C; a.N = s.out.C; a.Np = s.Np; a.H = s.out.H; a.W = s.out.W; a.B = B;
       a.act = s.act; a.stride = s.stride; a.wsplit = s.wsplit; a.n_active = n_active;
       if (s.skip.tensor >= 0) {

@@ -477,6 +477,22 @@ bool Plan::build(const TfModel& m, std::string* err) {
             if (s.wsplit == 2) pk[(size_t)Q * s.Np * 4 + at] = v - h;
           }
         s.w_umma = push(pk);
+        // f16-split packing (block_ws_kernel, kind::f16)
+        bool exact16 = true;
+        for (float v : w) if (half_to_float(float_to_half(v)) != v) { exact16 = false; break; }
+        s.wsplit16 = exact16 ? 1 : 2;
+        std::vector<uint16_t> hk((size_t)s.wsplit16 * Q * s.Np * 8, 0);
+        for (int o = 0; o < co; ++o)
+          for (int k = 0; k < ci; ++k) {
+            const float v = w[(size_t)o * ci + k];
+            const uint16_t h = float_to_half(v);
+            const size_t at = ((size_t)(k / 4) * s.Np + o) * 8 + (k % 4);
+            hk[at] = h; hk[at + 4] = h;                       // against the hi half and against the lo half of the activation
+            if (s.wsplit16 == 2) hk[(size_t)Q * s.Np * 8 + at] = float_to_half(v - half_to_float(h));   // (w_lo, 0): only the hi half
+          }
+        std::vector<float> hf(hk.size() / 2);
+        std::memcpy(hf.data(), hk.data(), hk.size() * 2);
+        s.w_f16 = push(hf);
       }
     }
     if (g.kind == STEP_RESIZE) {

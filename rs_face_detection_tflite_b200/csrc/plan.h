@@ -63,6 +63,12 @@ struct Step {
   // else 2 = (tf32(w), w - tf32(w)).  -1 when Cin % 8 != 0.
   int64_t w_umma = -1;
   int Np = 0, wsplit = 1;
+  // The same pointwise weights for tcgen05 kind::f16 with the A operand split as (f16 hi, f16 lo): K' = 2*Cin, plane q holds,
+  // for output channel n, the 8 halves (w[4q..4q+3], w[4q..4q+3]) -- the same weight against the hi and the lo half of the
+  // activation.  [wsplit16][Cin/4][Np][8 halves]; wsplit16 == 1 when every weight is f16-exact (the f16-stored detectors),
+  // else 2: second copy = (w - f16(w) as f16, 0).  Stored as raw bits, two halves per float.  -1 when Cin % 8 != 0.
+  int64_t w_f16 = -1;
+  int wsplit16 = 1;
   // CONV and BLOCK steps with Cin % 4 == 0: weights for the general tensor-core kernel,
   // [n_tiles][wsplit][Kp/4][Nt][4] with Kp = roundup(K,32), Nt = min(roundup(N,16),128).
   int64_t w_tc = -1;

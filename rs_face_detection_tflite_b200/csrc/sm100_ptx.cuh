@@ -18,17 +18,20 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes (or the hint
+// expires) instead of re-issuing try_wait / branch pairs -- in the warp-specialised kernels a third of all issued instructions
+// were such spins (ncu source view), competing for issue slots with the warps that had work.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra.uni WAIT_DONE;\n"
       "bra.uni WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 
@@ -83,6 +86,17 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the same with kind::f16 (A and B f16, fp32 accumulate; K = 16 per instruction)
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -142,6 +156,15 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
   d |= 1u << 4;                      // c_format = F32
   d |= 2u << 7;                      // a_format = TF32
   d |= 2u << 10;                     // b_format = TF32
+  d |= (uint32_t)(N >> 3) << 17;     // n_dim
+  d |= (uint32_t)(M >> 4) << 24;     // m_dim
+  return d;
+}
+
+// instruction descriptor for kind::f16 with f16 operands, fp32 accumulate, A and B K-major
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                      // c_format = F32; a_format = b_format = 0 (F16)
   d |= (uint32_t)(N >> 3) << 17;     // n_dim
   d |= (uint32_t)(M >> 4) << 24;     // m_dim
   return d;

@@ -49,6 +49,23 @@ float half_to_float(uint16_t h) {
   return f;
 }
 
+uint16_t float_to_half(float f) {
+  uint32_t x;
+  std::memcpy(&x, &f, 4);
+  const uint16_t sign = (uint16_t)((x >> 16) & 0x8000u);
+  const uint32_t ax = x & 0x7fffffffu;
+  if (ax > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);                 // NaN
+  if (ax >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);                // >= 65520 rounds past the largest half: saturate
+  if (ax < 0x33000001u) return sign;                                       // <= 2^-25: rounds to zero
+  int e = (int)(ax >> 23) - 127;
+  uint32_t man = (ax & 0x7fffffu) | 0x800000u;                             // 24-bit significand
+  int shift = e >= -14 ? 13 : 13 + (-14 - e);                              // bits dropped (subnormal halves drop more)
+  uint32_t q = man >> shift, rem = man & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+  if (rem > halfway || (rem == halfway && (q & 1u))) ++q;
+  uint32_t h = e >= -14 ? (((uint32_t)(e + 15) << 10) + (q - 0x400u)) : q;  // a carry out of the significand bumps the exponent
+  return (uint16_t)(sign | h);
+}
+
 namespace {
 
 // Cursor over the file image; every access is bounds-checked and failure is sticky.

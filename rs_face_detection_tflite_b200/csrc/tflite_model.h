@@ -69,5 +69,7 @@ struct TfModel {
 };
 
 float half_to_float(uint16_t h);
+// f32 -> f16, round to nearest even, saturating to the largest finite half (NaN stays NaN).
+uint16_t float_to_half(float f);
 
 }  // namespace fdl

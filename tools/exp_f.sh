@@ -1,0 +1,12 @@
+#!/bin/bash
+O=gpurun_out/${1:-r01ag}
+mkdir -p $O
+for e in 0 1; do
+  echo "EARLY=$e" >> $O/out.txt
+  FDL_WS_EARLY=$e timeout 120 python tools/step_times.py face_detection_back 256 1 10 2>&1 | grep -E "total|#1 |#9 |#17 |#25" >> $O/out.txt
+  FDL_WS_EARLY=$e timeout 120 python tools/step_times.py face_landmark 256 1 10 2>&1 | grep -E "total|#1 |#4 " >> $O/out.txt
+  FDL_WS_EARLY=$e timeout 120 python tools/step_times.py iris_landmark 512 1 10 2>&1 | grep -E "total|#2 " >> $O/out.txt
+done
+cat $O/out.txt
+timeout 600 python -m pytest tests/test_gpu_net.py -m gpu -x -q > $O/pytest_net.log 2>&1; echo "pytest exit $?" >> $O/pytest_net.log
+tail -4 $O/pytest_net.log
