@@ -35,6 +35,7 @@ namespace fdl {
 
 void count_launch();
 bool encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, long long bstride, int box_h, int box_w, int box_c = 0);
+bool encode_rows(CUtensorMap* m, const float* base, int B, int H, int W, int C, long long bstride, int box_h, int box_w);
 
 namespace {
 
@@ -59,14 +60,14 @@ constexpr int kMaxThreads = 512;
 constexpr int kMaxStages = 6, kMaxGroups = 3;
 constexpr int kMaxSmemWs = 227 * 1024;
 
-struct WsCfg { int G, ipt, ndwg, NS, OB, threads, total, ctas, in_pad, f16; };
+struct WsCfg { int G, ipt, ndwg, NS, OB, threads, total, ctas, in_pad, f16, rows; };
 struct WsLayout { int alpha, w, wb, ones, in0, in_stage, a0, a_buf, out0, out_stage, total; };
 
 __host__ __device__ inline int align_up_w(int v, int a) { return (v + a - 1) / a * a; }
 
 // f16: the A operand is one plane set of (f16 hi, f16 lo) pairs (half the bytes), `wsplit` counts the f16 weight copies, and
 // the bias is added in the epilogue (no bias K step: no `wb` / `ones` regions).
-__host__ __device__ inline WsLayout ws_layout(int C, int N, int Np, int wsplit, int NS, int G, int OB, int in_pad, int f16) {
+__host__ __device__ inline WsLayout ws_layout(int C, int N, int Np, int wsplit, int NS, int G, int OB, int in_pad, int f16, int rows) {
   WsLayout L;
   int off = 256;                                // barriers + tmem slot
   L.alpha = off; off += Np * 4;
@@ -80,7 +81,7 @@ __host__ __device__ inline WsLayout ws_layout(int C, int N, int Np, int wsplit, 
   L.in0 = off; off += NS * L.in_stage;
   L.a_buf = align_up_w((f16 ? 1 : 2) * (C / 4) * plane_bytes(C), 128);   // tf32: hi planes then lo planes; f16: one set of (hi, lo) planes
   L.a0 = off; off += G * L.a_buf;
-  L.out_stage = align_up_w(TH * TW * ((N / 4) | 1) * 16, 128);   // raw accumulator tile, pixel stride = odd number of quads
+  L.out_stage = align_up_w(rows ? TH * TW * N * 4 : TH * TW * ((N / 4) | 1) * 16, 128);   // output tile: dense (row-merged TMA) or pixel stride = odd number of quads
   L.out0 = off; off += OB * L.out_stage;
   L.total = align_up_w(off, 128);
   return L;
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
   const int kPlaneBytes = plane_bytes(C);
   const bool f16 = a.f16 != 0;
   const int wcopies = f16 ? a.wsplit16 : a.wsplit;
-  const WsLayout L = ws_layout(C, N, Np, wcopies, NS, G, a.out_bufs, a.in_pad, a.f16);
+  const WsLayout L = ws_layout(C, N, Np, wcopies, NS, G, a.out_bufs, a.in_pad, a.f16, a.row_tma);
   const int T = G > 2 ? G : 2;                  // TMEM accumulators: tile it -> buffer it % T (== its group when G >= 2, so each
                                                 // buffer has ONE issuing thread and its full/empty phases stay in lockstep)
   uint64_t* in_full = reinterpret_cast<uint64_t*>(smem);             // [kMaxStages]  TMA tile landed
@@ -138,7 +139,8 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
     const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
     ptx::mbar_arrive_expect_tx(&in_full[s], in_bytes);
-    ptx::tma_load_4d(smem + L.in0 + s * L.in_stage, &tm_in, &in_full[s], 0, tx * TW - 1, ty * TH - 1, b);
+    if (a.row_tma) ptx::tma_load_3d(smem + L.in0 + s * L.in_stage, &tm_in, &in_full[s], (tx * TW - 1) * (C >> 1), ty * TH - 1, b);
+    else ptx::tma_load_4d(smem + L.in0 + s * L.in_stage, &tm_in, &in_full[s], 0, tx * TW - 1, ty * TH - 1, b);
   };
 
   // ---- one-time setup: nothing here depends on the previous launch (PDL, see pdl.h) ----
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     // pixel stride of an ODD number of 16-byte quads, so the per-pixel 16-byte accesses are bank-conflict free.
     const int p = tid;                          // TMEM lane (warp w may access lanes 32w..32w+31)
     const int py = p / TW, px = p - py * TW;
-    const int NPf = ((N >> 2) | 1) << 2;        // staging pixel stride (floats)
+    const int NPf = a.row_tma ? N : ((N >> 2) | 1) << 2;   // staging pixel stride (floats): dense for the row-merged store
     int pb = 0, pty = 0, ptx_ = 0;              // coordinates of the previous tile (its TMA store is issued one tile late)
     // tile coordinates advance by a fixed (image, row, column) step per iteration: no divisions inside the loop
     int b, ty, tx;
@@ -252,8 +254,9 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
         if (tid == 0) ptx::tma_store_wait_read0();            // the store of tile it-2 has finished reading buffer `ob`
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (tid == 0) {
-          if (it > 0) {
-            ptx::tma_store_4d(&tm_out, smem + L.out0 + (ob ^ 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
+          if (it > 0 && !(a.dbg & 8)) {
+            if (a.row_tma) ptx::tma_store_3d(&tm_out, smem + L.out0 + (ob ^ 1) * L.out_stage, ptx_ * TW * (N >> 1), pty * TH, pb);
+            else ptx::tma_store_4d(&tm_out, smem + L.out0 + (ob ^ 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
             ptx::tma_store_commit();
           }
           if (early) {
@@ -311,7 +314,8 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     if (tid == 0) ptx::tma_store_wait_read0();
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (tid == 0) {
-      ptx::tma_store_4d(&tm_out, smem + L.out0 + ((my_tiles - 1) & 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
+      if (a.row_tma) ptx::tma_store_3d(&tm_out, smem + L.out0 + ((my_tiles - 1) & 1) * L.out_stage, ptx_ * TW * (N >> 1), pty * TH, pb);
+      else ptx::tma_store_4d(&tm_out, smem + L.out0 + ((my_tiles - 1) & 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
       ptx::tma_store_commit();
       ptx::tma_store_wait_all0();
     }
@@ -493,16 +497,22 @@ bool pick_cfg(int C, int N, int Np, int wsplit, int f16, WsCfg* cfg) {
   // stay conflict-free with it when Q % 8 == 0 (quad-fastest items) and, for Q == 6, with "x fastest" items -- which only fits
   // next to two CTAs per SM in f16 mode (smaller A operand, no bias planes).
   static const int pad6 = getenv("FDL_WS_PAD6") ? atoi(getenv("FDL_WS_PAD6")) : 1;   // A/B: padded stride + 3 stages vs plain stride + 4 stages
-  const int in_pad = (Q % 8 == 0 || (f16 && Q == 6 && pad6)) ? 1 : 0;
+  // Row-merged tensor maps (FDL_WS_ROWS=1; off by default: measured equal, 244 vs 245 us, so the TMA request granularity is
+  // not what bounds the kernel) need dense tiles and rows of at most 256 8-byte elements.
+  static const int rows_env = getenv("FDL_WS_ROWS") ? atoi(getenv("FDL_WS_ROWS")) : 0;
+  const int rows = (rows_env && C * ITW <= 512 && N * TW <= 512) ? 1 : 0;
+  const int in_pad = (!rows && (Q % 8 == 0 || (f16 && Q == 6 && pad6))) ? 1 : 0;
+  static const int ns_cap = getenv("FDL_WS_NS") ? atoi(getenv("FDL_WS_NS")) : 0;
   const int budget = ctas == 2 ? (233472 / 2 - 1024) : kMaxSmemWs;
   for (; G >= 1; --G) {
     const int ndwg = 32 * Q / ipt;
     if (kEpiThreads + G * ndwg > (ctas == 2 ? 320 : kMaxThreads)) continue;
     for (int NS = (G + 3 < kMaxStages ? G + 3 : kMaxStages); NS >= G + 2; --NS) {   // the refill of a stage trails its tile by one epilogue
-      WsLayout L = ws_layout(C, N, Np, wsplit, NS, G, 2, in_pad, f16);
+      if (ns_cap && NS > ns_cap && NS > G + 2) continue;
+      WsLayout L = ws_layout(C, N, Np, wsplit, NS, G, 2, in_pad, f16, rows);
       if (L.total <= budget) {
         cfg->G = G; cfg->ipt = ipt; cfg->ndwg = ndwg; cfg->NS = NS; cfg->OB = 2; cfg->threads = kEpiThreads + G * ndwg; cfg->total = L.total;
-        cfg->ctas = ctas; cfg->in_pad = in_pad; cfg->f16 = f16;
+        cfg->ctas = ctas; cfg->in_pad = in_pad; cfg->f16 = f16; cfg->rows = rows;
         return true;
       }
     }
@@ -538,7 +548,7 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   WsCfg cfg;
   a.f16 = (ws_f16_enabled() && a.w_f16 != nullptr && l.bias_host != nullptr) ? 1 : 0;
   if (!pick_cfg(a.C, a.N, a.Np, a.f16 ? a.wsplit16 : a.wsplit, a.f16, &cfg)) return cudaErrorInvalidConfiguration;
-  a.stages = cfg.NS; a.groups = cfg.G; a.dw_threads = cfg.ndwg; a.out_bufs = cfg.OB; a.in_pad = cfg.in_pad;
+  a.stages = cfg.NS; a.groups = cfg.G; a.dw_threads = cfg.ndwg; a.out_bufs = cfg.OB; a.in_pad = cfg.in_pad; a.row_tma = cfg.rows;
   a.pad = 1;
   static const int dbg_env = getenv("FDL_WS_DBG") ? atoi(getenv("FDL_WS_DBG")) : 0;
   a.dbg = dbg_env;
@@ -547,8 +557,13 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   for (int i = 0; i < 128; ++i) a.alpha_c[i] = (l.alpha_host && i < a.N) ? l.alpha_host[i] : 0.f;
   for (int i = 0; i < 128; ++i) a.bias_c[i] = (a.f16 && i < a.N) ? l.bias_host[i] : 0.f;
   CUtensorMap tm_in, tm_out;
-  if (!encode_nhwc(&tm_in, l.in, a.B, a.H, a.W, a.C, (long long)a.H * a.W * a.C, ITH, ITW, cfg.in_pad ? ((a.C / 4) | 1) * 4 : a.C)) return cudaErrorInvalidValue;
-  if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW, ((a.N / 4) | 1) * 4)) return cudaErrorInvalidValue;
+  if (cfg.rows) {
+    if (!encode_rows(&tm_in, l.in, a.B, a.H, a.W, a.C, (long long)a.H * a.W * a.C, ITH, ITW)) return cudaErrorInvalidValue;
+    if (!encode_rows(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW)) return cudaErrorInvalidValue;
+  } else {
+    if (!encode_nhwc(&tm_in, l.in, a.B, a.H, a.W, a.C, (long long)a.H * a.W * a.C, ITH, ITW, cfg.in_pad ? ((a.C / 4) | 1) * 4 : a.C)) return cudaErrorInvalidValue;
+    if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW, ((a.N / 4) | 1) * 4)) return cudaErrorInvalidValue;
+  }
   a.tiles_x = (a.W + TW - 1) / TW;
   a.tiles_y = (a.H + TH - 1) / TH;
   a.acc_cols = a.Np <= 32 ? 32 : (a.Np <= 64 ? 64 : 128);
@@ -566,8 +581,8 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   count_launch();
   static const bool verbose = getenv("FDL_WS_VERBOSE") != nullptr;
   if (verbose)
-    fprintf(stderr, "[ws C=%d N=%d %dx%d G=%d NS=%d ctas=%d thr=%d smem=%d in_pad=%d f16=%d]\n", a.C, a.N, a.H, a.W, cfg.G, cfg.NS, cfg.ctas, cfg.threads,
-            cfg.total, cfg.in_pad, cfg.f16);
+    fprintf(stderr, "[ws C=%d N=%d %dx%d G=%d NS=%d ctas=%d thr=%d smem=%d in_pad=%d f16=%d rows=%d]\n", a.C, a.N, a.H, a.W, cfg.G, cfg.NS, cfg.ctas, cfg.threads,
+            cfg.total, cfg.in_pad, cfg.f16, cfg.rows);
   return e;
 }
 
