@@ -61,7 +61,8 @@ __host__ __device__ inline int in_tile_w(int S) { return (TW - 1) * S + 3; }
 // stride is already within 2x of conflict-free and keeps the depthwise loads, which walk quads first, perfectly linear.)
 __host__ __device__ inline int pad_quads(int c) { return ((c >> 2) & 3) == 0 ? c + 4 : c; }
 
-__host__ __device__ inline SmemLayout smem_layout(int C, int N, int Np, int S, int stages, int wsplit, int alias_out, int CP, int NP) {
+// f16: the A operand is ONE plane set of (f16 hi, f16 lo) pairs (see BlockTcArgs::f16) and `wsplit` counts f16 weight copies.
+__host__ __device__ inline SmemLayout smem_layout(int C, int N, int Np, int S, int stages, int wsplit, int alias_out, int CP, int NP, int f16 = 0) {
   SmemLayout L;
   int off = 64;                                   // barriers + tmem pointer
   L.bias = off; off += Np * 4;
@@ -70,7 +71,7 @@ __host__ __device__ inline SmemLayout smem_layout(int C, int N, int Np, int S, i
   L.in_stage = align_up_i(in_tile_h(S) * in_tile_w(S) * CP * 4, 128);
   L.in0 = off; off += stages * L.in_stage;
   L.a_hi = off; off += (C / 4) * kPlaneBytes;
-  L.a_lo = off; off += (C / 4) * kPlaneBytes;     // contiguous with a_hi (kPlaneBytes is a multiple of 16)
+  L.a_lo = off; if (!f16) off += (C / 4) * kPlaneBytes;     // contiguous with a_hi (kPlaneBytes is a multiple of 16); absent in f16 mode
   off = align_up_i(off, 128);
   L.w = off; off += wsplit * (C / 4) * Np * 16;
   off = align_up_i(off, 128);
@@ -88,6 +89,17 @@ __device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// (c0, c1) -> f16x2 with c0 in the low half, round to nearest even, saturating instead of overflowing; and back
+__device__ __forceinline__ uint32_t pack_f16x2(float c0, float c1) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(c1), "f"(c0));
+  return d;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t d) {
+  float2 r;
+  asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}\n" : "=f"(r.x), "=f"(r.y) : "r"(d));
+  return r;
+}
 
 template <int S, int kThreads>
 __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in,
@@ -96,7 +108,9 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
   constexpr int ITH = (TH - 1) * S + 3, ITW = (TW - 1) * S + 3;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int C = a.C, N = a.N, Np = a.Np, Q = C >> 2;
-  const SmemLayout L = smem_layout(C, N, Np, S, a.stages, a.wsplit, a.alias_out, a.tc_cp, a.tc_np);
+  const bool f16 = a.f16 != 0;
+  const int wcopies = f16 ? a.wsplit16 : a.wsplit;
+  const SmemLayout L = smem_layout(C, N, Np, S, a.stages, wcopies, a.alias_out, a.tc_cp, a.tc_np, a.f16);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);          // [2]
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + 16);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 32);
@@ -122,8 +136,8 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
     s_alpha[i] = (a.alpha && i < N) ? a.alpha[i] : 0.f;
   }
   {  // pointwise weights: already in UMMA core-matrix order in global memory -> straight copy
-    const int n4 = a.wsplit * Q * Np;   // float4 count
-    const float4* src = reinterpret_cast<const float4*>(a.w_umma);
+    const int n4 = wcopies * Q * Np;   // float4 count
+    const float4* src = reinterpret_cast<const float4*>(f16 ? a.w_f16 : a.w_umma);
     float4* dst = reinterpret_cast<float4*>(s_w);
     for (int i = tid; i < n4; i += kThreads) dst[i] = __ldg(src + i);
   }
@@ -156,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
   };
   if (tid == 0 && (int)blockIdx.x < ntiles) issue_load(blockIdx.x, 0);
 
-  const uint32_t idesc = ptx::umma_idesc_tf32(128, Np);
+  const uint32_t idesc = f16 ? ptx::umma_idesc_f16(128, Np) : ptx::umma_idesc_tf32(128, Np);
   const uint32_t ahi_addr = ptx::smem_u32(s_ahi), alo_addr = ptx::smem_u32(s_alo), w_addr = ptx::smem_u32(s_w);
   const uint32_t w_lbo = (uint32_t)Np * 16u;
   const int nitems = Q * 2 * TW;
@@ -201,6 +215,15 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
       for (int o = 0; o < 4; ++o) {
         const int p = (half * 4 + o) * TW + x;
         float4 v = acc[o], hi, lo;
+        if (f16) {
+          // (f16 hi, f16 lo) of the four channels in ONE 16-byte core-matrix row: K' = (hi c0..c3, lo c0..c3)
+          uint4 u;
+          u.x = pack_f16x2(v.x, v.y); u.y = pack_f16x2(v.z, v.w);
+          const float2 h01 = unpack_f16x2(u.x), h23 = unpack_f16x2(u.y);
+          u.z = pack_f16x2(v.x - h01.x, v.y - h01.y); u.w = pack_f16x2(v.z - h23.x, v.w - h23.y);
+          *reinterpret_cast<uint4*>(s_ahi + q * kPlaneBytes + p * 16) = u;
+          continue;
+        }
         hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
         lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
         *reinterpret_cast<float4*>(s_ahi + q * kPlaneBytes + p * 16) = hi;
@@ -215,8 +238,20 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
     if (tid == 0) {
       ptx::tc_fence_after_sync();
       uint32_t acc_flag = 0;
+      if (f16) {
+        // kind::f16, K = 16 = two planes = two channel quads x (hi, lo); pass 0: (A_hi, A_lo) * (W, W), pass 1: (A_hi, A_lo) * (W_lo, 0)
+        for (int pass = 0; pass < a.wsplit16; ++pass) {
+          const uint32_t b_base = w_addr + (uint32_t)(pass * Q * Np * 16);
+          for (int ks = 0; ks < (Q >> 1); ++ks) {
+            uint64_t ad = ptx::umma_desc_kmajor(ahi_addr + (uint32_t)(ks * 2 * kPlaneBytes), kPlaneBytes, 128);
+            uint64_t bdsc = ptx::umma_desc_kmajor(b_base + (uint32_t)ks * 2u * w_lbo, w_lbo, 128);
+            ptx::mma_f16(tmem_base, ad, bdsc, idesc, acc_flag);
+            acc_flag = 1;
+          }
+        }
+      }
       const int ksteps = C >> 3;
-      for (int pass = 0; pass < (a.wsplit == 2 ? 3 : 2); ++pass) {
+      for (int pass = 0; pass < (a.wsplit == 2 ? 3 : 2) && !f16; ++pass) {
         // pass 0: A_lo * W_hi, pass 1: A_hi * W_hi, pass 2: A_hi * W_lo
         const uint32_t a_base = pass == 0 ? alo_addr : ahi_addr;
         const uint32_t b_base = pass == 2 ? w_addr + (uint32_t)(Q * Np * 16) : w_addr;
@@ -381,17 +416,24 @@ bool encode_rows(CUtensorMap* m, const float* base, int B, int H, int W, int C, 
 
 namespace {
 
+// f16-split A operand in the serial kernel too (FDL_TC_F16, default on): half the A-plane bytes -> room for a second input stage /
+// a second resident CTA for the wide blocks.
+bool tc_f16_enabled() {
+  static const bool on = [] { const char* e = getenv("FDL_TC_F16"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
+
 // Picks (stages, alias_out, pixel strides) for a block; returns false when it cannot fit in shared memory.  The padded
 // pixel strides are used only where they cost neither a pipeline stage nor a resident CTA.
-bool pick_smem(int C, int N, int Np, int S, int wsplit, int* stages, int* alias_out, int* total, int* cp_out, int* np_out) {
+bool pick_smem(int C, int N, int Np, int S, int wsplit, int f16, int* stages, int* alias_out, int* total, int* cp_out, int* np_out) {
   // candidate configurations in order of preference at equal occupancy
   const int cand[4][2] = {{2, 0}, {2, 1}, {1, 0}, {1, 1}};
   auto best_for = [&](int CP, int NP, int* per_sm_out) {
-    const bool can_alias = TH * TW * NP * 4 <= 2 * (C / 4) * kPlaneBytes;
+    const bool can_alias = TH * TW * NP * 4 <= (f16 ? 1 : 2) * (C / 4) * kPlaneBytes;
     int best = -1, best_per_sm = 0;
     for (int i = 0; i < 4; ++i) {
       if (cand[i][1] && !can_alias) continue;
-      SmemLayout L = smem_layout(C, N, Np, S, cand[i][0], wsplit, cand[i][1], CP, NP);
+      SmemLayout L = smem_layout(C, N, Np, S, cand[i][0], wsplit, cand[i][1], CP, NP, f16);
       if (L.total > kMaxSmemTc) continue;
       int per_sm = (228 * 1024) / (L.total + 1024);
       if (per_sm > 2) per_sm = 2;
@@ -412,7 +454,7 @@ bool pick_smem(int C, int N, int Np, int S, int wsplit, int* stages, int* alias_
     if (b >= 0 && ps >= ps0 && cand[b][0] >= cand[plain][0]) { best = b; CP = opts[o][0]; NP = opts[o][1]; break; }
   }
   *stages = cand[best][0]; *alias_out = cand[best][1]; *cp_out = CP; *np_out = NP;
-  *total = smem_layout(C, N, Np, S, *stages, wsplit, *alias_out, CP, NP).total;
+  *total = smem_layout(C, N, Np, S, *stages, wsplit, *alias_out, CP, NP, f16).total;
   return true;
 }
 
@@ -449,7 +491,8 @@ bool block_tc_supported(const Step& s) {
   static const int max_n = getenv("FDL_BLOCK_TC_MAX_N") ? atoi(getenv("FDL_BLOCK_TC_MAX_N")) : 1 << 30;   // A/B timing against conv_tc
   if (N > max_n) return false;
   int stages, alias, total, cp, np;
-  return pick_smem(C, N, s.Np, s.stride, s.wsplit, &stages, &alias, &total, &cp, &np);
+  const int f16 = (tc_f16_enabled() && s.w_f16 >= 0) ? 1 : 0;
+  return pick_smem(C, N, s.Np, s.stride, f16 ? s.wsplit16 : s.wsplit, f16, &stages, &alias, &total, &cp, &np);
 }
 
 cudaError_t launch_block_tc(const BlockTcLaunch& l, cudaStream_t stream) {
@@ -457,7 +500,8 @@ cudaError_t launch_block_tc(const BlockTcLaunch& l, cudaStream_t stream) {
   BlockTcArgs a = l.args;
   const int S = a.stride;
   int total = 0;
-  if (!pick_smem(a.C, a.N, a.Np, S, a.wsplit, &a.stages, &a.alias_out, &total, &a.tc_cp, &a.tc_np)) return cudaErrorInvalidConfiguration;
+  a.f16 = (tc_f16_enabled() && a.w_f16 != nullptr) ? 1 : 0;
+  if (!pick_smem(a.C, a.N, a.Np, S, a.f16 ? a.wsplit16 : a.wsplit, a.f16, &a.stages, &a.alias_out, &total, &a.tc_cp, &a.tc_np)) return cudaErrorInvalidConfiguration;
   a.pad = S == 1 ? 1 : 0;
   CUtensorMap tm_in, tm_out;
   if (!encode_nhwc(&tm_in, l.in, a.B, a.H * S, a.W * S, a.C, (long long)a.H * S * a.W * S * a.C, in_tile_h(S), in_tile_w(S), a.tc_cp))
