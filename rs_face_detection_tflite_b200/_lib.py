@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfdl_b200.so")
+# FDL_LIB: an alternative build of the same library (A/B timing of kernel variants); the default is the in-tree build
+LIB_PATH = os.environ.get("FDL_LIB") or os.path.join(HERE, "libfdl_b200.so")
 
 FDL_OK = 0
 FDL_ERR_INVALID, FDL_ERR_IO, FDL_ERR_MODEL, FDL_ERR_CUDA, FDL_ERR_CAPACITY, FDL_ERR_INTERNAL = -1, -2, -3, -4, -5, -6

@@ -35,7 +35,6 @@ namespace fdl {
 
 void count_launch();
 bool encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, long long bstride, int box_h, int box_w, int box_c = 0);
-bool encode_rows(CUtensorMap* m, const float* base, int B, int H, int W, int C, long long bstride, int box_h, int box_w);
 
 namespace {
 
@@ -60,14 +59,14 @@ constexpr int kMaxThreads = 512;
 constexpr int kMaxStages = 6, kMaxGroups = 3;
 constexpr int kMaxSmemWs = 227 * 1024;
 
-struct WsCfg { int G, ipt, ndwg, NS, OB, threads, total, ctas, in_pad, f16, rows; };
+struct WsCfg { int G, ipt, ndwg, NS, OB, threads, total, ctas, in_pad, f16; };
 struct WsLayout { int alpha, w, wb, ones, in0, in_stage, a0, a_buf, out0, out_stage, total; };
 
 __host__ __device__ inline int align_up_w(int v, int a) { return (v + a - 1) / a * a; }
 
 // f16: the A operand is one plane set of (f16 hi, f16 lo) pairs (half the bytes), `wsplit` counts the f16 weight copies, and
 // the bias is added in the epilogue (no bias K step: no `wb` / `ones` regions).
-__host__ __device__ inline WsLayout ws_layout(int C, int N, int Np, int wsplit, int NS, int G, int OB, int in_pad, int f16, int rows) {
+__host__ __device__ inline WsLayout ws_layout(int C, int N, int Np, int wsplit, int NS, int G, int OB, int in_pad, int f16) {
   WsLayout L;
   int off = 256;                                // barriers + tmem slot
   L.alpha = off; off += Np * 4;
@@ -81,7 +80,7 @@ __host__ __device__ inline WsLayout ws_layout(int C, int N, int Np, int wsplit, 
   L.in0 = off; off += NS * L.in_stage;
   L.a_buf = align_up_w((f16 ? 1 : 2) * (C / 4) * plane_bytes(C), 128);   // tf32: hi planes then lo planes; f16: one set of (hi, lo) planes
   L.a0 = off; off += G * L.a_buf;
-  L.out_stage = align_up_w(rows ? TH * TW * N * 4 : TH * TW * ((N / 4) | 1) * 16, 128);   // output tile: dense (row-merged TMA) or pixel stride = odd number of quads
+  L.out_stage = align_up_w(TH * TW * ((N / 4) | 1) * 16, 128);   // raw accumulator tile, pixel stride = odd number of quads
   L.out0 = off; off += OB * L.out_stage;
   L.total = align_up_w(off, 128);
   return L;
@@ -108,7 +107,7 @@ __device__ __forceinline__ float2 unpack_f16x2(uint32_t d) {
   return r;
 }
 
-template <int kMaxT, int kMinB>
+template <int kMaxT, int kMinB, bool kF16>
 __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                                                                   const BlockTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -116,9 +115,9 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
   const int C = a.C, N = a.N, Np = a.Np, Q = C >> 2;
   const int NS = a.stages, G = a.groups, ndwg = a.dw_threads;
   const int kPlaneBytes = plane_bytes(C);
-  const bool f16 = a.f16 != 0;
+  constexpr bool f16 = kF16;                    // compile-time: the two operand formats must not share registers / code
   const int wcopies = f16 ? a.wsplit16 : a.wsplit;
-  const WsLayout L = ws_layout(C, N, Np, wcopies, NS, G, a.out_bufs, a.in_pad, a.f16, a.row_tma);
+  const WsLayout L = ws_layout(C, N, Np, wcopies, NS, G, a.out_bufs, a.in_pad, f16 ? 1 : 0);
   const int T = G > 2 ? G : 2;                  // TMEM accumulators: tile it -> buffer it % T (== its group when G >= 2, so each
                                                 // buffer has ONE issuing thread and its full/empty phases stay in lockstep)
   uint64_t* in_full = reinterpret_cast<uint64_t*>(smem);             // [kMaxStages]  TMA tile landed
@@ -139,8 +138,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
     const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
     ptx::mbar_arrive_expect_tx(&in_full[s], in_bytes);
-    if (a.row_tma) ptx::tma_load_3d(smem + L.in0 + s * L.in_stage, &tm_in, &in_full[s], (tx * TW - 1) * (C >> 1), ty * TH - 1, b);
-    else ptx::tma_load_4d(smem + L.in0 + s * L.in_stage, &tm_in, &in_full[s], 0, tx * TW - 1, ty * TH - 1, b);
+    ptx::tma_load_4d(smem + L.in0 + s * L.in_stage, &tm_in, &in_full[s], 0, tx * TW - 1, ty * TH - 1, b);
   };
 
   // ---- one-time setup: nothing here depends on the previous launch (PDL, see pdl.h) ----
@@ -195,7 +193,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     // pixel stride of an ODD number of 16-byte quads, so the per-pixel 16-byte accesses are bank-conflict free.
     const int p = tid;                          // TMEM lane (warp w may access lanes 32w..32w+31)
     const int py = p / TW, px = p - py * TW;
-    const int NPf = a.row_tma ? N : ((N >> 2) | 1) << 2;   // staging pixel stride (floats): dense for the row-merged store
+    const int NPf = ((N >> 2) | 1) << 2;        // staging pixel stride (floats)
     int pb = 0, pty = 0, ptx_ = 0;              // coordinates of the previous tile (its TMA store is issued one tile late)
     // tile coordinates advance by a fixed (image, row, column) step per iteration: no divisions inside the loop
     int b, ty, tx;
@@ -235,45 +233,22 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       load_res(0, res);
       ptx::mbar_wait(&acc_full[t], (uint32_t)((it / T) & 1));
       ptx::tc_fence_after_sync();
-      // Early refill (FDL_WS_EARLY=1; off by default -- like a fourth input stage it measured SLOWER, 246 vs 237 us on the 128x128x24
-      // stage: the kernel is not short of loads in flight): when the whole residual of this tile is already in registers (one batch: <= 32 channels) or does not
-      // come from the input stage at all, the stage of THIS tile is dead once the accumulator is complete (the depthwise warps
-      // have read it, or the MMAs could not have run) -- so the load NS tiles ahead is issued here, one whole tile period
-      // earlier than "after the epilogue of the tile".  The residual registers are consumed first so that their shared-memory
-      // loads have landed before the barrier below lets thread 0 hand the stage back to the TMA unit.
-      const bool early = a.early_refill && (a.skip_mode != 1 || a.skip_c <= 32);
-      if (early && a.skip_mode == 1) {
-        float chk = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) chk += res[j].x;
-        asm volatile("" ::"f"(chk) : "memory");
-      }
       // ---- deferred TMA store of the PREVIOUS tile: its staging writes have had a whole tile to drain ----
       {
         ptx::fence_proxy_async_smem();
         if (tid == 0) ptx::tma_store_wait_read0();            // the store of tile it-2 has finished reading buffer `ob`
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid == 0) {
-          if (it > 0 && !(a.dbg & 8)) {
-            if (a.row_tma) ptx::tma_store_3d(&tm_out, smem + L.out0 + (ob ^ 1) * L.out_stage, ptx_ * TW * (N >> 1), pty * TH, pb);
-            else ptx::tma_store_4d(&tm_out, smem + L.out0 + (ob ^ 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
-            ptx::tma_store_commit();
-          }
-          if (early) {
-            if (it + NS < my_tiles) issue_load(it + NS);
-          } else if (it > 0 && it - 1 + NS < my_tiles) {
-            issue_load(it - 1 + NS);   // every epilogue warp is past its residual reads of the PREVIOUS tile's stage: refill that one
-          }
+        if (tid == 0 && it > 0) {
+          ptx::tma_store_4d(&tm_out, smem + L.out0 + (ob ^ 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
+          ptx::tma_store_commit();
+          // every epilogue warp is past its residual reads of the previous tile's stage: refill it.  (Refilling the CURRENT
+          // tile's stage here -- legal once its accumulator is complete and its residual is in registers -- or a fourth stage
+          // both measured SLOWER, 246 / 243 vs 237 us: the kernel is not short of loads in flight.)
+          if (it - 1 + NS < my_tiles) issue_load(it - 1 + NS);
         }
       }
       pb = b; pty = ty; ptx_ = tx;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * acc_cols);
-      if (a.dbg & 4) {
-        ptx::tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[t]);
-        continue;
-      }
       for (int c0 = 0; c0 < Np; c0 += 32) {
         if (c0 + 32 < Np) load_res(c0 + 32, resn);
 #pragma unroll
@@ -314,8 +289,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     if (tid == 0) ptx::tma_store_wait_read0();
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (tid == 0) {
-      if (a.row_tma) ptx::tma_store_3d(&tm_out, smem + L.out0 + ((my_tiles - 1) & 1) * L.out_stage, ptx_ * TW * (N >> 1), pty * TH, pb);
-      else ptx::tma_store_4d(&tm_out, smem + L.out0 + ((my_tiles - 1) & 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
+      ptx::tma_store_4d(&tm_out, smem + L.out0 + ((my_tiles - 1) & 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
       ptx::tma_store_commit();
       ptx::tma_store_wait_all0();
     }
@@ -354,8 +328,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       const int s = it % NS, kg = it / G, t = it % T;
       ptx::mbar_wait(&in_full[s], (uint32_t)((it / NS) & 1));
       const float* s_in = reinterpret_cast<const float*>(smem + L.in0 + s * L.in_stage);
-      if ((a.dbg & 1) && kg > 0) ptx::mbar_wait(&a_empty[g], (uint32_t)((kg - 1) & 1));
-      for (int item = gt, ii = 0; item < nitems && !(a.dbg & 1); item += ndwg, ++ii) {
+      for (int item = gt, ii = 0; item < nitems; item += ndwg, ++ii) {
         int x, half;                            // (runtime divisions by Q only on the generic path)
         if (map6) { x = m6 >> 4; half = item / 96; }
         else if (xfast) { x = item % TW; half = item / 96; }
@@ -425,11 +398,6 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
         if (it >= T) ptx::mbar_wait(&acc_empty[t], (uint32_t)(((it / T) - 1) & 1));
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(t * acc_cols);
-        if (a.dbg & 2) {
-          ptx::mma_commit(&acc_full[t]);
-          ptx::mma_commit(&a_empty[g]);
-          continue;
-        }
         if (f16) {
           // kind::f16, K = 16 = two planes = two channel quads x (hi, lo); pass 0: (A_hi, A_lo) * (W, W), pass 1: (A_hi, A_lo) * (W_lo, 0)
           const int ksteps16 = Q >> 1;
@@ -473,9 +441,11 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
 // Depthwise thread organisation per channel-quad count: G groups of ndwg threads, ipt items per thread and tile, and
 // how many CTAs share an SM.  Small channel counts (little work per tile, latency-dominated) run TWO smaller CTAs per SM
 // so that two epilogues and two depthwise groups are in flight; larger ones run one CTA with up to 12 depthwise warps.
-// f16-split A operand (FDL_WS_F16, default on): see BlockTcArgs::f16.
+// f16-split A operand (FDL_WS_F16=1; off by default): see BlockTcArgs::f16.  It removes 27 % of the kernel's shared-memory
+// wavefronts and all its bank conflicts, and measures no faster (229.9 vs 227.6 us on the 128x128x24 stage, 47 vs 45 us at 32x32x48):
+// the kernel is not bound by shared-memory bandwidth.  The serial kernel does use it (room for a second stage).
 bool ws_f16_enabled() {
-  static const bool on = [] { const char* e = getenv("FDL_WS_F16"); return e ? atoi(e) != 0 : true; }();
+  static const bool on = [] { const char* e = getenv("FDL_WS_F16"); return e ? atoi(e) != 0 : false; }();
   return on;
 }
 
@@ -497,11 +467,7 @@ bool pick_cfg(int C, int N, int Np, int wsplit, int f16, WsCfg* cfg) {
   // stay conflict-free with it when Q % 8 == 0 (quad-fastest items) and, for Q == 6, with "x fastest" items -- which only fits
   // next to two CTAs per SM in f16 mode (smaller A operand, no bias planes).
   static const int pad6 = getenv("FDL_WS_PAD6") ? atoi(getenv("FDL_WS_PAD6")) : 1;   // A/B: padded stride + 3 stages vs plain stride + 4 stages
-  // Row-merged tensor maps (FDL_WS_ROWS=1; off by default: measured equal, 244 vs 245 us, so the TMA request granularity is
-  // not what bounds the kernel) need dense tiles and rows of at most 256 8-byte elements.
-  static const int rows_env = getenv("FDL_WS_ROWS") ? atoi(getenv("FDL_WS_ROWS")) : 0;
-  const int rows = (rows_env && C * ITW <= 512 && N * TW <= 512) ? 1 : 0;
-  const int in_pad = (!rows && (Q % 8 == 0 || (f16 && Q == 6 && pad6))) ? 1 : 0;
+  const int in_pad = (Q % 8 == 0 || (f16 && Q == 6 && pad6)) ? 1 : 0;
   static const int ns_cap = getenv("FDL_WS_NS") ? atoi(getenv("FDL_WS_NS")) : 0;
   const int budget = ctas == 2 ? (233472 / 2 - 1024) : kMaxSmemWs;
   for (; G >= 1; --G) {
@@ -509,10 +475,10 @@ bool pick_cfg(int C, int N, int Np, int wsplit, int f16, WsCfg* cfg) {
     if (kEpiThreads + G * ndwg > (ctas == 2 ? 320 : kMaxThreads)) continue;
     for (int NS = (G + 3 < kMaxStages ? G + 3 : kMaxStages); NS >= G + 2; --NS) {   // the refill of a stage trails its tile by one epilogue
       if (ns_cap && NS > ns_cap && NS > G + 2) continue;
-      WsLayout L = ws_layout(C, N, Np, wsplit, NS, G, 2, in_pad, f16, rows);
+      WsLayout L = ws_layout(C, N, Np, wsplit, NS, G, 2, in_pad, f16);
       if (L.total <= budget) {
         cfg->G = G; cfg->ipt = ipt; cfg->ndwg = ndwg; cfg->NS = NS; cfg->OB = 2; cfg->threads = kEpiThreads + G * ndwg; cfg->total = L.total;
-        cfg->ctas = ctas; cfg->in_pad = in_pad; cfg->f16 = f16; cfg->rows = rows;
+        cfg->ctas = ctas; cfg->in_pad = in_pad; cfg->f16 = f16;
         return true;
       }
     }
@@ -523,9 +489,11 @@ bool pick_cfg(int C, int N, int Np, int wsplit, int f16, WsCfg* cfg) {
 }  // namespace
 
 cudaError_t block_ws_init() {
-  cudaError_t e = cudaFuncSetAttribute(block_ws_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
+  cudaError_t e = cudaFuncSetAttribute(block_ws_kernel<512, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<512, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<320, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(block_ws_kernel<320, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
+  return cudaFuncSetAttribute(block_ws_kernel<320, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
 }
 
 bool block_ws_supported(const Step& s) {
@@ -548,22 +516,13 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   WsCfg cfg;
   a.f16 = (ws_f16_enabled() && a.w_f16 != nullptr && l.bias_host != nullptr) ? 1 : 0;
   if (!pick_cfg(a.C, a.N, a.Np, a.f16 ? a.wsplit16 : a.wsplit, a.f16, &cfg)) return cudaErrorInvalidConfiguration;
-  a.stages = cfg.NS; a.groups = cfg.G; a.dw_threads = cfg.ndwg; a.out_bufs = cfg.OB; a.in_pad = cfg.in_pad; a.row_tma = cfg.rows;
+  a.stages = cfg.NS; a.groups = cfg.G; a.dw_threads = cfg.ndwg; a.out_bufs = cfg.OB; a.in_pad = cfg.in_pad;
   a.pad = 1;
-  static const int dbg_env = getenv("FDL_WS_DBG") ? atoi(getenv("FDL_WS_DBG")) : 0;
-  a.dbg = dbg_env;
-  static const int early_env = getenv("FDL_WS_EARLY") ? atoi(getenv("FDL_WS_EARLY")) : 0;   // measured slower on B200 (r01ag): off by default
-  a.early_refill = early_env;
   for (int i = 0; i < 128; ++i) a.alpha_c[i] = (l.alpha_host && i < a.N) ? l.alpha_host[i] : 0.f;
   for (int i = 0; i < 128; ++i) a.bias_c[i] = (a.f16 && i < a.N) ? l.bias_host[i] : 0.f;
   CUtensorMap tm_in, tm_out;
-  if (cfg.rows) {
-    if (!encode_rows(&tm_in, l.in, a.B, a.H, a.W, a.C, (long long)a.H * a.W * a.C, ITH, ITW)) return cudaErrorInvalidValue;
-    if (!encode_rows(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW)) return cudaErrorInvalidValue;
-  } else {
-    if (!encode_nhwc(&tm_in, l.in, a.B, a.H, a.W, a.C, (long long)a.H * a.W * a.C, ITH, ITW, cfg.in_pad ? ((a.C / 4) | 1) * 4 : a.C)) return cudaErrorInvalidValue;
-    if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW, ((a.N / 4) | 1) * 4)) return cudaErrorInvalidValue;
-  }
+  if (!encode_nhwc(&tm_in, l.in, a.B, a.H, a.W, a.C, (long long)a.H * a.W * a.C, ITH, ITW, cfg.in_pad ? ((a.C / 4) | 1) * 4 : a.C)) return cudaErrorInvalidValue;
+  if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW, ((a.N / 4) | 1) * 4)) return cudaErrorInvalidValue;
   a.tiles_x = (a.W + TW - 1) / TW;
   a.tiles_y = (a.H + TH - 1) / TH;
   a.acc_cols = a.Np <= 32 ? 32 : (a.Np <= 64 ? 64 : 128);
@@ -576,13 +535,15 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   int grid = persist_sms() * cfg.ctas;
   if (grid > ntiles) grid = ntiles;
   cudaError_t e;
-  if (cfg.ctas == 2) e = launch_pdl(block_ws_kernel<320, 2>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
-  else e = launch_pdl(block_ws_kernel<512, 1>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
+  if (cfg.ctas == 2 && a.f16) e = launch_pdl(block_ws_kernel<320, 2, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
+  else if (cfg.ctas == 2) e = launch_pdl(block_ws_kernel<320, 2, false>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
+  else if (a.f16) e = launch_pdl(block_ws_kernel<512, 1, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
+  else e = launch_pdl(block_ws_kernel<512, 1, false>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
   count_launch();
   static const bool verbose = getenv("FDL_WS_VERBOSE") != nullptr;
   if (verbose)
-    fprintf(stderr, "[ws C=%d N=%d %dx%d G=%d NS=%d ctas=%d thr=%d smem=%d in_pad=%d f16=%d rows=%d]\n", a.C, a.N, a.H, a.W, cfg.G, cfg.NS, cfg.ctas, cfg.threads,
-            cfg.total, cfg.in_pad, cfg.f16, cfg.rows);
+    fprintf(stderr, "[ws C=%d N=%d %dx%d G=%d NS=%d ctas=%d thr=%d smem=%d in_pad=%d f16=%d]\n", a.C, a.N, a.H, a.W, cfg.G, cfg.NS, cfg.ctas, cfg.threads,
+            cfg.total, cfg.in_pad, cfg.f16);
   return e;
 }
 

@@ -400,20 +400,6 @@ bool encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, 
   return r == CUDA_SUCCESS;
 }
 
-// Row-merged map of an NHWC f32 tensor: dimensions {W*C/2 (8-byte elements), H, B}, box {box_w*C/2, box_h, 1}.  The TMA unit works
-// one innermost-dimension row at a time; with the channel dimension innermost a 10 x 18 x 24 tile is 180 requests of 96 bytes
-// (each straddling sectors), with the image row innermost it is 10 requests of 1728 bytes.  Needs box_w*C/2 <= 256 elements.
-bool encode_rows(CUtensorMap* m, const float* base, int B, int H, int W, int C, long long bstride, int box_h, int box_w) {
-  if (!g_encode || (C & 1) || (long long)box_w * C / 2 > 256) return false;
-  cuuint64_t dims[3] = {(cuuint64_t)W * C / 2, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)W * C * 4, (cuuint64_t)bstride * 4};
-  cuuint32_t box[3] = {(cuuint32_t)(box_w * C / 2), (cuuint32_t)box_h, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
 namespace {
 
 // f16-split A operand in the serial kernel too (FDL_TC_F16, default on): half the A-plane bytes -> room for a second input stage /

@@ -35,10 +35,6 @@ struct BlockTcArgs {
   int tc_cp = 0, tc_np = 0;        // blaze_block_tc_kernel: pixel strides (floats) of the input / output staging tiles (>= C / N)
   // block_ws_kernel, f16-split mode: the depthwise result is written as ONE plane set of (f16 hi, f16 lo) pairs and multiplied
   // with tcgen05 kind::f16 (half the A-operand bytes in shared memory of the tf32 hi / lo planes, same 2^-22 fidelity)
-  int row_tma = 0;                 // block_ws_kernel: row-merged tensor maps (image row innermost; dense tiles) -- see encode_rows
-  int early_refill = 0;            // block_ws_kernel: refill a tile's input stage as soon as its accumulator is complete (see the kernel)
-  int dbg = 0;                     // block_ws_kernel, FDL_WS_DBG (timing experiments only, results are garbage): 1 skip the depthwise,
-                                   // 2 skip the MMAs, 4 skip the epilogue's accumulator read / arithmetic / staging stores, 8 skip the TMA stores
   int f16 = 0;
   int wsplit16 = 1;                // 1: weights f16-exact; 2: + (w - f16(w)) against the hi half
   const float* w_f16 = nullptr;    // [wsplit16][C/4][Np][8 halves] (Step::w_f16)

@@ -18,20 +18,19 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// try_wait with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes (or the hint
-// expires) instead of re-issuing try_wait / branch pairs -- in the warp-specialised kernels a third of all issued instructions
-// were such spins (ncu source view), competing for issue slots with the warps that had work.
+// (A suspend-time hint on try_wait -- which makes ptxas emit NANOSLEEP back-off loops -- was measured: no gain on the 128x128x24
+// stage, 4 % slower on the latency-sensitive one-CTA-per-SM configurations.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra.uni WAIT_DONE;\n"
       "bra.uni WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity), "r"(0x989680u)
+      "r"(parity)
       : "memory");
 }
 
@@ -55,18 +54,6 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-// 3-D forms (row-merged tensor maps: {W*C as 8-byte elements, H, B})
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
