@@ -91,6 +91,25 @@ def _dist():
     return rank, world, local
 
 
+def _pin_to_gpu_numa_node(index):
+    """One process per GPU: run on (and therefore first-touch the pinned frame buffers on) the CPU cores NVML reports as local
+    to this GPU, so that host-sourced frames do not cross the socket interconnect on their way to the PCIe root port."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n = (os.cpu_count() + 63) // 64
+        masks = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = [64 * i + b for i, m in enumerate(masks) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
 def _plan_numbers():
     """Algorithmic bytes and flops per item of the three planned graphs (no GPU needed: plan-only handles)."""
     import rs_face_detection_tflite_b200 as fdl
@@ -222,9 +241,13 @@ def run_ours(args):
     rank, world, local = _dist()
     if fdl.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    numa = _pin_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
@@ -372,7 +395,7 @@ def run_ours(args):
                                    "contains config 2 as its detection stage)",
                        "frames_per_step_per_gpu": B, "frame": "1920x1080x3 u8", "faces_per_frame": n_faces / B, "landmark_sets_per_frame": n_lm / B,
                        "l2_policy": "inputs larger than L2: %.2f GB of frames per step" % (B * W * H * 3 / 1e9), "parallelism": "frames sharded by rank, no collective",
-                       "batches_in_flight": args.dev_inflight},
+                       "batches_in_flight": args.dev_inflight, "cpu_affinity": ("GPU-local cores (%d)" % numa) if numa else "inherited"},
             "e2e": {"value": e2e, "unit": UNIT,
                     "h2d_bytes_per_step": B * W * H * 3 if (e2e_zc_s is None or e2e_copy_s <= e2e_zc_s) else B * zero_copy_bytes_per_frame(),
                     "d2h_bytes_per_step": B * (ctypes.sizeof(_lib.CFrameResult) + ctypes.sizeof(_lib.CFaceResult)),
