@@ -13,6 +13,7 @@
 // activation arenas) are shared: a per-network event serialises their use across lanes.
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -98,7 +99,8 @@ struct Lane {
   DevBuf<uint8_t> frames;
   DevBuf<uint8_t> rows;                        // copy-engine gather of the letterbox source rows (zero-copy host mode)
   DevBuf<float> det_in, lmk_in, iris_in;       // image_to_tensor outputs (network inputs), private to the lane
-  DevBuf<I2TParams> det_params, face_params, eye_params;
+  DevBuf<I2TParams> det_params, face_params, eye_params, eye_params_dev, eye_params_host;
+  DevBuf<SrcBox> face_boxes;                   // zero-copy host mode: the frame rectangle staged on the device per face slot
   DevBuf<fdl_rect> face_rois, eye_rois;
   DevBuf<int> slot_frame, slot_face, face_valid, eye_frame, eye_valid, counters;
   DevBuf<fdl_frame_result> d_frames;
@@ -203,6 +205,9 @@ int fdl_pipeline_create(const fdl_pipeline_config* cfg, fdl_pipeline** out) {
     if (e == cudaSuccess) e = l.det_params.reserve(B);
     if (e == cudaSuccess) e = l.face_params.reserve(F);
     if (e == cudaSuccess) e = l.eye_params.reserve(E);
+    if (e == cudaSuccess && cfg->zero_copy_host) e = l.eye_params_dev.reserve(E);
+    if (e == cudaSuccess && cfg->zero_copy_host) e = l.eye_params_host.reserve(E);
+    if (e == cudaSuccess && cfg->zero_copy_host) e = l.face_boxes.reserve(F);
     if (e == cudaSuccess) e = l.face_rois.reserve(F);
     if (e == cudaSuccess) e = l.eye_rois.reserve(E);
     if (e == cudaSuccess) e = l.slot_frame.reserve(F);
@@ -309,7 +314,17 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
                                  lane->d_faces.p, n_faces, cs));
     FDL_CUDA_TRY(launch_i2t_setup(lane->face_rois.p, lane->slot_frame.p, lane->face_valid.p, F, W, H, p->LS, p->LS, 0, 0.0, 1.0, 0,
                                   lane->face_params.p, n_faces, cs));
-    FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, lane->face_params.p, F, p->LS, p->LS, lane->lmk_in.p, (long long)p->LS * p->LS * 3, nullptr, n_faces, cs, 0, 0, zc_ctas));
+    // zero-copy host frames: stage the faces' source rectangles on the device once; the face warp and (normally) both eye warps
+    // then read the device copy instead of fetching their taps over PCIe
+    static const int crop_env = getenv("FDL_ZC_CROP") ? atoi(getenv("FDL_ZC_CROP")) : 1;
+    const bool crop = used_host && crop_env && lane->face_boxes.p && lane->frames.cap >= (size_t)fstride * n && (row & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(fptr) & 15) == 0;     // 16-byte row copies
+    if (crop) {
+      FDL_CUDA_TRY(launch_roi_fill(fptr, lane->frames.p, fstride, row, lane->face_params.p, F, n_faces, lane->face_boxes.p, H, zc_ctas * 4, cs));
+      FDL_CUDA_TRY(launch_i2t(lane->frames.p, fstride, row, lane->face_params.p, F, p->LS, p->LS, lane->lmk_in.p, (long long)p->LS * p->LS * 3, nullptr, n_faces, cs, 0, 0, 0));
+    } else {
+      FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, lane->face_params.p, F, p->LS, p->LS, lane->lmk_in.p, (long long)p->LS * p->LS * 3, nullptr, n_faces, cs, 0, 0, zc_ctas));
+    }
     FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[4], cs));
     FDL_CUDA_TRY(cudaStreamWaitEvent(cs, p->guard[1], 0));
     FDL_CUDA_TRY(p->lmk->forward(F, cs, n_faces, lane->lmk_in.p));
@@ -324,7 +339,13 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
       // IrisLandmark::infer for both eyes: image_to_tensor(keep_aspect, (0,1), flip = right eye)
       FDL_CUDA_TRY(launch_i2t_setup(lane->eye_rois.p, lane->eye_frame.p, lane->eye_valid.p, E, W, H, p->IS, p->IS, 1, 0.0, 1.0, 2,
                                     lane->eye_params.p, n_eyes, cs));
-      FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, lane->eye_params.p, E, p->IS, p->IS, lane->iris_in.p, (long long)p->IS * p->IS * 3, nullptr, n_eyes, cs, 0, 0, zc_ctas));
+      if (crop) {
+        FDL_CUDA_TRY(launch_eye_split(lane->eye_params.p, lane->face_boxes.p, E, n_eyes, lane->eye_params_dev.p, lane->eye_params_host.p, cs));
+        FDL_CUDA_TRY(launch_i2t(lane->frames.p, fstride, row, lane->eye_params_dev.p, E, p->IS, p->IS, lane->iris_in.p, (long long)p->IS * p->IS * 3, nullptr, n_eyes, cs, 0, 0, 0));
+        FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, lane->eye_params_host.p, E, p->IS, p->IS, lane->iris_in.p, (long long)p->IS * p->IS * 3, nullptr, n_eyes, cs, 0, 0, zc_ctas));
+      } else {
+        FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, lane->eye_params.p, E, p->IS, p->IS, lane->iris_in.p, (long long)p->IS * p->IS * 3, nullptr, n_eyes, cs, 0, 0, zc_ctas));
+      }
       FDL_CUDA_TRY(cudaEventRecord(lane->ev_stage[6], cs));
       FDL_CUDA_TRY(cudaStreamWaitEvent(cs, p->guard[2], 0));
       FDL_CUDA_TRY(p->iris->forward(E, cs, n_eyes, lane->iris_in.p));

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256) i2t_kernel(const uint8_t* __restrict__ fr
       for (int i = threadIdx.x; i < (int)(sizeof(I2TParams) / 4); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
+    if (P.valid == 2) continue;                  // another launch owns this slot (see eye_split_kernel)
     int pix = blk * blockDim.x + threadIdx.x;
     if (pix >= out_w * out_h) continue;
     int oy = pix / out_w, ox = pix - oy * out_w;
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(256) i2t_tile_kernel(const uint8_t* __restrict
       for (int i = threadIdx.x; i < (int)(sizeof(I2TParams) / 4); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
+    if (P.valid == 2) continue;                  // another launch owns this slot (see eye_split_kernel)
     const uint8_t* img = frames + (long long)P.frame * frame_stride;
     const int ox0 = tx * kTileW, oy0 = ty * kTileH, ox1 = min(ox0 + kTileW, out_w) - 1, oy1 = min(oy0 + kTileH, out_h) - 1;
     if (threadIdx.x == 0) {
@@ -630,6 +632,91 @@ __global__ void iris_metrics_kernel(const double* iris, int img_w, int img_h, do
 }
 
 // ------------------------------------------------------------------------------------------------
+// Zero-copy host frames: ROI staging.  The face warp and the two eye warps of a face sample (almost always) the same
+// neighbourhood of the frame.  Instead of letting each warp kernel fetch its taps over PCIe (overlapping tiles re-read, 32 GB/s
+// effective), the source rectangle of the face warp, grown by a margin, is copied ONCE with fully coalesced 16-byte loads into
+// the lane's device frame buffer AT THE SAME OFFSETS; the warps then run on that buffer with unchanged coordinates (so their
+// arithmetic is untouched).  Eye warps whose own source rectangle is not inside the copied one keep reading the host frame.
+__device__ __forceinline__ SrcBox warp_src_box(const I2TParams& P) {
+  // the corners of warp space through the inverse matrix: every tap of the warp lies in [floor(lo) - 1, ceil(hi) + 2]
+  SrcBox b; b.x0 = 0; b.y0 = 0; b.x1 = -1; b.y1 = -1;
+  if (P.valid != 1) return b;
+  double lox = 1e30, loy = 1e30, hix = -1e30, hiy = -1e30;
+  for (int c = 0; c < 4; ++c) {
+    const double x = (c & 1) ? (double)(P.warp_w - 1) : 0.0, y = (c & 2) ? (double)(P.warp_h - 1) : 0.0;
+    const double w = P.Mi[6] * x + P.Mi[7] * y + P.Mi[8];
+    if (!(w > 1e-6)) return b;
+    const double sx = (P.Mi[0] * x + P.Mi[1] * y + P.Mi[2]) / w, sy = (P.Mi[3] * x + P.Mi[4] * y + P.Mi[5]) / w;
+    lox = dmin(lox, sx); hix = dmax(hix, sx); loy = dmin(loy, sy); hiy = dmax(hiy, sy);
+  }
+  if (!(hix - lox < 1e5 && hiy - loy < 1e5 && lox > -1e6 && loy > -1e6)) return b;
+  b.x0 = (int)floor(lox) - 1; b.y0 = (int)floor(loy) - 1; b.x1 = (int)ceil(hix) + 2; b.y1 = (int)ceil(hiy) + 2;
+  return b;
+}
+
+constexpr int kFillRows = 16;      // frame rows per work item of roi_fill_kernel
+
+__global__ void __launch_bounds__(256) roi_fill_kernel(const uint8_t* __restrict__ host_frames, uint8_t* __restrict__ dev_frames,
+                                                       long long frame_stride, long long row_stride, const I2TParams* __restrict__ params,
+                                                       int n, const int* n_active, SrcBox* boxes, int frame_h, int fill_margin_pct) {
+  if (n_active) n = min(n, *n_active);
+  __shared__ SrcBox s_box;
+  __shared__ int s_frame;
+  const int chunks = (frame_h + kFillRows - 1) / kFillRows;
+  const long long items = (long long)n * chunks;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int slot = (int)(item / chunks), ch = (int)(item - (long long)slot * chunks);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const I2TParams& P = params[slot];
+      SrcBox b = warp_src_box(P);
+      if (b.x1 >= b.x0) {
+        // a small margin (the eye ROIs lie well inside the face ROI; an eye that does not keeps reading the host frame), clipped
+        // to the frame.  A 12 % margin cost more PCIe time than it saved: the face rectangles of 1080p frames are large.
+        const int m = (max(b.x1 - b.x0, b.y1 - b.y0) * fill_margin_pct) / 100 + 2;
+        b.x0 = max(b.x0 - m, 0); b.y0 = max(b.y0 - m, 0); b.x1 = min(b.x1 + m, P.src_w - 1); b.y1 = min(b.y1 + m, P.src_h - 1);
+      }
+      s_box = b; s_frame = P.frame;
+      if (ch == 0) boxes[slot] = b;
+    }
+    __syncthreads();
+    const SrcBox b = s_box;
+    if (b.x1 < b.x0 || b.y1 < b.y0) continue;
+    const int r0 = max(b.y0, ch * kFillRows), r1 = min(b.y1, ch * kFillRows + kFillRows - 1);
+    if (r1 < r0) continue;
+    const int sb = (3 * b.x0) & ~15;
+    int eb = (3 * (b.x1 + 1) + 15) & ~15;
+    if (eb > (int)row_stride) eb = (int)row_stride;
+    const int nq = (eb - sb) >> 4;               // 16-byte pieces per row
+    const long long base = (long long)s_frame * frame_stride + sb;
+    for (int r = r0 + warp; r <= r1; r += 8) {
+      const uint4* src = reinterpret_cast<const uint4*>(host_frames + base + (long long)r * row_stride);
+      uint4* dst = reinterpret_cast<uint4*>(dev_frames + base + (long long)r * row_stride);
+      for (int q = lane; q < nq; q += 32) dst[q] = __ldg(src + q);
+    }
+  }
+}
+
+// Eye slots whose source rectangle lies inside their face's copied rectangle run on the device copy, the others on the host frame:
+// the two launches get complementary parameter arrays (valid == 2: "not yours").
+__global__ void eye_split_kernel(const I2TParams* __restrict__ eye_params, const SrcBox* __restrict__ face_boxes, int n, const int* n_active,
+                                 I2TParams* p_dev, I2TParams* p_host) {
+  if (n_active) n = min(n, *n_active);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  I2TParams P = eye_params[i];
+  const SrcBox e = warp_src_box(P), f = face_boxes[i >> 1];
+  const bool inside = P.valid != 1 ||          // invalid slots just get their zero tensor from the device launch
+                      (e.x1 >= e.x0 && f.x1 >= f.x0 && max(e.x0, 0) >= f.x0 && max(e.y0, 0) >= f.y0 && min(e.x1, P.src_w - 1) <= f.x1 &&
+                       min(e.y1, P.src_h - 1) <= f.y1);
+  I2TParams Q = P;
+  Q.valid = 2;
+  p_dev[i] = inside ? P : Q;
+  p_host[i] = inside ? Q : P;
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void face_detection_to_roi_kernel(const fdl_detection* det, int img_w, int img_h, int size_mode, fdl_rect* out, int* ok) {
   *ok = face_detection_to_roi(det->data, img_w, img_h, size_mode, out) ? 1 : 0;
 }
@@ -756,6 +843,22 @@ cudaError_t launch_refine_landmarks(const double* face, const double* left, int 
 cudaError_t launch_iris_metrics(const double* iris, int img_w, int img_h, double focal_length_mm, double iris_size_px, double* out2,
                                 cudaStream_t s) {
   iris_metrics_kernel<<<1, 1, 0, s>>>(iris, img_w, img_h, focal_length_mm, iris_size_px, out2);
+  return FDL_LAUNCHED();
+}
+
+cudaError_t launch_roi_fill(const uint8_t* host_frames, uint8_t* dev_frames, long long frame_stride, long long row_stride, const I2TParams* params,
+                            int n, const int* n_active, SrcBox* boxes, int frame_h, int max_ctas, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  long long items = (long long)n * ((frame_h + kFillRows - 1) / kFillRows);
+  if (max_ctas > 0 && items > max_ctas) items = max_ctas;
+  static const int margin_env = getenv("FDL_ZC_MARGIN") ? atoi(getenv("FDL_ZC_MARGIN")) : 0;
+  roi_fill_kernel<<<(unsigned)items, 256, 0, s>>>(host_frames, dev_frames, frame_stride, row_stride, params, n, n_active, boxes, frame_h, margin_env);
+  return FDL_LAUNCHED();
+}
+cudaError_t launch_eye_split(const I2TParams* eye_params, const SrcBox* face_boxes, int n, const int* n_active, I2TParams* p_dev, I2TParams* p_host,
+                             cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  eye_split_kernel<<<(n + 127) / 128, 128, 0, s>>>(eye_params, face_boxes, n, n_active, p_dev, p_host);
   return FDL_LAUNCHED();
 }
 

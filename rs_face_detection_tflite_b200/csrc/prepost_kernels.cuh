@@ -29,6 +29,14 @@ cudaError_t launch_i2t_setup(const fdl_rect* rois, const int* slot_frame, const 
 // (batch stride out_bstride floats); out_u8 optional [n, out_h, out_w, 3].
 // compact / row_pos / compact_fstride (optional, rows_mode only): a device-resident copy of just the source rows the
 // letterbox touches ([frame][compact row][row bytes], gathered by the copy engine); row_pos[src row] = compact row or -1.
+// Source rectangle of a warp in frame pixels (inclusive; x1 < x0: empty).
+struct SrcBox { int x0, y0, x1, y1; };
+// Zero-copy host frames: copy the (margin-grown) source rectangle of every face warp from the pinned host frames into the device
+// frame buffer at the same offsets, and split the eye slots between the device copy and the host frames (see prepost_kernels.cu).
+cudaError_t launch_roi_fill(const uint8_t* host_frames, uint8_t* dev_frames, long long frame_stride, long long row_stride, const I2TParams* params,
+                            int n, const int* n_active, SrcBox* boxes, int frame_h, int max_ctas, cudaStream_t s);
+cudaError_t launch_eye_split(const I2TParams* eye_params, const SrcBox* face_boxes, int n, const int* n_active, I2TParams* p_dev, I2TParams* p_host,
+                             cudaStream_t s);
 cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long row_stride, const I2TParams* params, int n,
                        int out_w, int out_h, float* out, long long out_bstride, uint8_t* out_u8, const int* n_active,
                        cudaStream_t s, int rows_mode = 0, int src_w = 0, int max_ctas = 0,
