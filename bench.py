@@ -144,10 +144,28 @@ def _dominant_kernel(B, device):
             "ms": float(np.mean(ms[idx])), "algo_bytes": 2 * B * 128 * 128 * 24 * 4, "traffic": traffic, "traffic_source": src}
 
 
-def zero_copy_bytes_per_frame():
-    """Host bytes the kernels read per 1080p frame in zero-copy mode: the source rows the 256x256 letterbox
-    interpolates between (whole rows are staged) plus an upper bound for the ROI warps (4 taps x 3 B per output
-    pixel of the 192x192 face crop, 16 taps for the two-stage 64x64 eye crops)."""
+def roi_rect_bytes(roi, margin=2):
+    """Bytes roi_fill_kernel copies for one face: the bounding rectangle of the rotated face ROI in frame pixels (+ the warp's
+    -1 / +2 tap slack and the 2 px margin), clipped to the frame, rows widened to 16-byte pieces."""
+    import math
+    w, h = roi.width * W, roi.height * H
+    c, s_ = abs(math.cos(roi.rotation)), abs(math.sin(roi.rotation))
+    bw, bh = w * c + h * s_, w * s_ + h * c
+    x0 = max(int(math.floor(roi.x_center * W - bw / 2)) - 1 - margin, 0)
+    x1 = min(int(math.ceil(roi.x_center * W + bw / 2)) + 2 + margin, W - 1)
+    y0 = max(int(math.floor(roi.y_center * H - bh / 2)) - 1 - margin, 0)
+    y1 = min(int(math.ceil(roi.y_center * H + bh / 2)) + 2 + margin, H - 1)
+    if x1 < x0 or y1 < y0:
+        return 0
+    sb, eb = (3 * x0) & ~15, min((3 * (x1 + 1) + 15) & ~15, 3 * W)
+    return (eb - sb) * (y1 - y0 + 1)
+
+
+def zero_copy_bytes_per_frame(face_rect_bytes=None):
+    """Host bytes that cross PCIe per 1080p frame in zero-copy mode: the source rows the 256x256 letterbox interpolates between
+    (gathered by the copy engine) plus the face rectangle roi_fill_kernel stages on the device (measured from the last batch's
+    face ROIs); without that measurement, an upper bound for in-place ROI warps (4 taps x 3 B per output pixel of the 192x192
+    face crop, 16 taps for the two-stage 64x64 eye crops)."""
     rows = set()
     for dy in range(256):
         f = np.float32((dy + 0.5) * (1920.0 / 256.0) - 0.5)
@@ -155,6 +173,8 @@ def zero_copy_bytes_per_frame():
         for r in (min(max(s, 0), 1919) - 420, min(max(s + 1, 0), 1919) - 420):
             if 0 <= r < H:
                 rows.add(r)
+    if face_rect_bytes is not None:
+        return len(rows) * W * 3 + int(face_rect_bytes)
     return len(rows) * W * 3 + 192 * 192 * 4 * 3 + 2 * 64 * 64 * 16 * 3
 
 
@@ -335,13 +355,15 @@ def run_ours(args):
 
     e2e_copy_s = e2e_loop(pipe)
     h2d_ms = pipe.stage_ms[0]
-    e2e_zc_s = None
+    e2e_zc_s, zc_rect_bytes = None, None
     if not args.no_zero_copy:
         pipe_zc = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (W, H), max_batch=B, max_faces=1, model_dir=MODELS, device=local,
                                zero_copy_host=True)
         e2e_zc_s = e2e_loop(pipe_zc)
         zc_faces = sum(pipe_zc._frames[i].n_faces for i in range(B))
         assert zc_faces == n_faces, "zero-copy path disagrees with the copy path"
+        zc_rect_bytes = float(np.mean([sum(roi_rect_bytes(pipe_zc._faces[i * pipe_zc.max_faces + f].face_roi)
+                                           for f in range(pipe_zc._frames[i].n_faces)) for i in range(B)]))
         pipe_zc.close()
     e2e_s = min(e2e_copy_s, e2e_zc_s) if e2e_zc_s is not None else e2e_copy_s
     clocks = sampler.summary()
@@ -397,7 +419,7 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2: %.2f GB of frames per step" % (B * W * H * 3 / 1e9), "parallelism": "frames sharded by rank, no collective",
                        "batches_in_flight": args.dev_inflight, "cpu_affinity": ("GPU-local cores (%d)" % numa) if numa else "inherited"},
             "e2e": {"value": e2e, "unit": UNIT,
-                    "h2d_bytes_per_step": B * W * H * 3 if (e2e_zc_s is None or e2e_copy_s <= e2e_zc_s) else B * zero_copy_bytes_per_frame(),
+                    "h2d_bytes_per_step": B * W * H * 3 if (e2e_zc_s is None or e2e_copy_s <= e2e_zc_s) else B * zero_copy_bytes_per_frame(zc_rect_bytes),
                     "d2h_bytes_per_step": B * (ctypes.sizeof(_lib.CFrameResult) + ctypes.sizeof(_lib.CFaceResult)),
                     "mode": "copy" if (e2e_zc_s is None or e2e_copy_s <= e2e_zc_s) else "zero-copy (kernels read pinned host frames in place)",
                     "copy_mode_value": frames_total / e2e_copy_max, "copy_mode_h2d_ms_per_step": h2d_ms,
