@@ -760,12 +760,14 @@ cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long 
   // another lane's network kernels need
   if (rows_mode && !out_u8) {
     const size_t row_pad = (size_t)((src_w * 3 + 15) & ~15);
-    int rpi = kRowsPerItem;
+    static const int rpi_env = getenv("FDL_I2T_RPI") ? atoi(getenv("FDL_I2T_RPI")) : 0;   // A/B: output rows per work item
+    int rpi = (rpi_env >= 1 && rpi_env <= kRowsPerItem) ? rpi_env : kRowsPerItem;
     while (rpi > 1 && 2 * rpi * row_pad > 48 * 1024) rpi >>= 1;
     const size_t smem = 2 * rpi * row_pad;
     if (smem <= 48 * 1024) {
       long long items = (long long)n * ((out_h + rpi - 1) / rpi);
-      const long long cap = max_ctas > 0 ? max_ctas : 148LL * 4;      // persistent CTAs (items are strided over the grid)
+      const long long per_sm = (long long)((200 * 1024) / (smem + 1024)) < 8 ? (long long)((200 * 1024) / (smem + 1024)) : 8;
+      const long long cap = max_ctas > 0 ? max_ctas : 148LL * (per_sm < 4 ? 4 : per_sm);      // persistent CTAs (items are strided over the grid)
       if (items > cap) items = cap;
       i2t_rows_kernel<<<(unsigned)items, 256, smem, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, n_active, compact,
                                                          row_pos, compact_fstride, rpi);

@@ -141,14 +141,18 @@ def test_batched_pipeline_matches_oracle(fdl, gpu, oracle_pipeline):
 def test_detection_only_pipeline_and_errors(fdl, gpu):
     import synth_frames
     frames = synth_frames.face_frames(2, 640, 480)
-    pipe = fdl.Pipeline(fdl.FaceDetectionModel.Full, (640, 480), max_batch=4, run_landmarks=False, model_dir=MODELS, device=gpu)
-    res = pipe.run(frames)
-    det = fdl.FaceDetection(fdl.FaceDetectionModel.Full, MODELS, device=gpu)
-    for i in range(2):
-        single = det.infer(frames[i])
-        assert [d.anchor for d in single] == [d.anchor for d in res[i].detections]
-        for a, b in zip(single, res[i].detections):
-            np.testing.assert_array_equal(a.data, b.data)
+    for model in (fdl.FaceDetectionModel.FullSparse, fdl.FaceDetectionModel.Full):    # BASELINE config 3 and its sparse sibling
+        pipe = fdl.Pipeline(model, (640, 480), max_batch=4, run_landmarks=False, model_dir=MODELS, device=gpu)
+        res = pipe.run(frames)
+        det = fdl.FaceDetection(model, MODELS, device=gpu)
+        for i in range(2):
+            single = det.infer(frames[i])
+            assert len(single) >= 1
+            assert [d.anchor for d in single] == [d.anchor for d in res[i].detections]
+            for a, b in zip(single, res[i].detections):
+                np.testing.assert_array_equal(a.data, b.data)
+        if model != fdl.FaceDetectionModel.Full:
+            pipe.close(); det.close()
     with pytest.raises(fdl.FdlError):
         pipe.run(synth_frames.noise_frames(1, 320, 240))       # wrong frame size
     with pytest.raises(fdl.FdlError):
