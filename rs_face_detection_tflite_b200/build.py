@@ -30,6 +30,7 @@ SOURCES = {
     "block_ws_kernel.cu": [],
     "stem_kernel.cu": [],
     "conv_tc_kernel.cu": [],
+    "pw_kernel.cu": [],
     # the glue arithmetic must not contract a*b+c into FMA (the reference's scalar Rust never does)
     "prepost_kernels.cu": ["-fmad=false"],
     "fdl_api.cu": [],

@@ -21,6 +21,7 @@ Net* Net::create(const std::string& path, int device, std::string* err, int* cod
     if (e == cudaSuccess) e = mma_kernels_init();
     if (e == cudaSuccess) e = conv_tc_init();
     if (e == cudaSuccess) e = block_ws_init();
+    if (e == cudaSuccess) e = pw_stream_init();
     if (e == cudaSuccess) e = cudaMalloc(&n->d_weights_, n->plan_.weights.size() * sizeof(float));
     if (e == cudaSuccess)
       e = cudaMemcpy(n->d_weights_, n->plan_.weights.data(), n->plan_.weights.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -134,6 +135,14 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const 
         else { a.skip_mode = 2; a.skip = sk.p; a.skip_bstride = sk.bstride; }
       }
       e = (mode_ == 1 && block_ws_supported(s)) ? launch_block_ws(l, stream) : launch_block_tc(l, stream);
+    } else if (mode_ >= 1 && pw_stream_supported(s, B)) {
+      ConvArgs a;
+      a.in = in_view(s); a.out = view(s.out, B);
+      a.kh = a.kw = 1; a.K = s.K; a.K4 = s.K4; a.N = s.N; a.Npad = s.Npad;
+      a.w = d_weights_ + s.w; a.bias = d_weights_ + s.b;
+      if (s.alpha >= 0) a.alpha = d_weights_ + s.alpha;
+      a.act = s.act; a.B = B; a.n_active = n_active;
+      e = launch_pw_stream(a, stream);
     } else if (mode_ >= 1 && conv_tc_supported(s)) {
       ConvTcArgs a;
       TView in = in_view(s), out = view(s.out, B);

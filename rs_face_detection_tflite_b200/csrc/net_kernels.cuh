@@ -45,6 +45,12 @@ struct EltArgs {
   const int* n_active = nullptr;
 };
 
+// Streaming fp32 pointwise convolution for the large maps (pw_kernel.cu).
+struct Step;
+cudaError_t pw_stream_init();
+bool pw_stream_supported(const Step& s, int B);
+cudaError_t launch_pw_stream(const ConvArgs& a, cudaStream_t stream);
+
 // Returns cudaSuccess or the launch error.  `stream` is the handle's stream.
 cudaError_t launch_fused_conv(const ConvArgs& a, cudaStream_t stream);
 cudaError_t launch_elementwise(const EltArgs& a, cudaStream_t stream);
