@@ -218,11 +218,11 @@ FDL_HD Px3 warp_px(const I2TParams& P, const ImgSrc& src, int x, int y) {
   double fY = (Mi[3] * x + Mi[4] * y + Mi[5]) * W;
   fX = dmax(-2147483648.0, dmin(2147483647.0, fX));
   fY = dmax(-2147483648.0, dmin(2147483647.0, fY));
-  long long X = (long long)rint(fX), Y = (long long)rint(fY);
-  long long sxl = X >> 5, syl = Y >> 5;
-  int sx = (int)(sxl < -32768 ? -32768 : (sxl > 32767 ? 32767 : sxl));   // saturate_cast<short>
-  int sy = (int)(syl < -32768 ? -32768 : (syl > 32767 ? 32767 : syl));
-  int ax = (int)(X & 31), ay = (int)(Y & 31);
+  int X = (int)rint(fX), Y = (int)rint(fY);            // clamped to the int32 range above: the conversion is exact
+  int sxl = X >> 5, syl = Y >> 5;
+  int sx = sxl < -32768 ? -32768 : (sxl > 32767 ? 32767 : sxl);   // saturate_cast<short>
+  int sy = syl < -32768 ? -32768 : (syl > 32767 ? 32767 : syl);
+  int ax = X & 31, ay = Y & 31;
   // OpenCV's bilinear table: float32 products of (1-fy),(fy) x (1-fx),(fx), scaled by 32768 and rounded
   float fx = (float)ax * (1.f / 32.f), fy = (float)ay * (1.f / 32.f);
   int w00 = (int)rintf((1.f - fy) * (1.f - fx) * 32768.f);
@@ -241,9 +241,9 @@ FDL_HD Px3 warp_px(const I2TParams& P, const ImgSrc& src, int x, int y) {
   return o;
 }
 
-// cv::resize(INTER_LINEAR) coefficients for one axis. clamp_frac: x axis.
-FDL_HD void resize_coeff(int d, int dn, int sn, bool clamp_frac, int* s0, int* s1, int* c0, int* c1) {
-  double scale = (double)sn / (double)dn;
+// cv::resize(INTER_LINEAR) coefficients for one axis. clamp_frac: x axis.  `scale` = (double)sn / (double)dn
+// (callers that evaluate many coordinates of one axis divide once).
+FDL_HD void resize_coeff_scaled(int d, double scale, int sn, bool clamp_frac, int* s0, int* s1, int* c0, int* c1) {
   float f = (float)(((double)d + 0.5) * scale - 0.5);
   int s = (int)floorf(f);
   float fr = f - (float)s;
@@ -256,6 +256,9 @@ FDL_HD void resize_coeff(int d, int dn, int sn, bool clamp_frac, int* s0, int* s
   }
   *c0 = (int)rintf((1.f - fr) * 2048.f);
   *c1 = (int)rintf(fr * 2048.f);
+}
+FDL_HD void resize_coeff(int d, int dn, int sn, bool clamp_frac, int* s0, int* s1, int* c0, int* c1) {
+  resize_coeff_scaled(d, (double)sn / (double)dn, sn, clamp_frac, s0, s1, c0, c1);
 }
 
 FDL_HD int resize_mix(int p00, int p01, int p10, int p11, int a0, int a1, int b0, int b1) {

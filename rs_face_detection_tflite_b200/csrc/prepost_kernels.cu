@@ -32,16 +32,22 @@ __global__ void i2t_setup_kernel(const fdl_rect* rois, const int* slot_frame, co
   params[i] = P;
 }
 
-// One thread per output pixel (3 channels).  The source taps are gathered straight from the u8
-// frame (L2/texture path); the f32 tensor is written once.
-__global__ void __launch_bounds__(256) i2t_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
+// kPxPerThread output pixels (3 channels) per thread and work item (all in flight together).  The source taps are gathered straight from the u8
+// frame (L2/texture path); the f32 tensor is written once.  The normalisation goes through a 256-entry table of the
+// exact f64 expression (one f64 division per thread and CTA instead of three per pixel).
+template <int kPxPerThread>
+__global__ void __launch_bounds__(256, 4) i2t_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
                                                   const I2TParams* __restrict__ params, int n, int out_w, int out_h,
                                                   float* __restrict__ out, long long out_bstride, uint8_t* __restrict__ out_u8,
                                                   const int* n_active) {
   if (n_active) n = min(n, *n_active);
   __shared__ I2TParams P;
-  const int blocks_per_slot = (out_w * out_h + 255) / 256;
+  __shared__ float s_lut[256];
+  const int px_per_item = 256 * kPxPerThread;
+  const int blocks_per_slot = (out_w * out_h + px_per_item - 1) / px_per_item;
   const long long items = (long long)n * blocks_per_slot;
+  double lut_min = 0.0, lut_max = 0.0;
+  bool lut_built = false;
   for (long long item = blockIdx.x; item < items; item += gridDim.x) {
     const int slot = (int)(item / blocks_per_slot), blk = (int)(item - (long long)slot * blocks_per_slot);
     __syncthreads();
@@ -52,19 +58,28 @@ __global__ void __launch_bounds__(256) i2t_kernel(const uint8_t* __restrict__ fr
     }
     __syncthreads();
     if (P.valid == 2) continue;                  // another launch owns this slot (see eye_split_kernel)
-    int pix = blk * blockDim.x + threadIdx.x;
-    if (pix >= out_w * out_h) continue;
-    int oy = pix / out_w, ox = pix - oy * out_w;
-    Px3 p;
-    if (P.valid) p = i2t_pixel(P, img_src(frames + (long long)P.frame * frame_stride, row_stride), ox, oy);
-    else { p.r = p.g = p.b = 0; }
-    float* o = out + (long long)slot * out_bstride + (long long)pix * 3;
-    o[0] = i2t_normalise(p.r, P.range_min, P.range_max);
-    o[1] = i2t_normalise(p.g, P.range_min, P.range_max);
-    o[2] = i2t_normalise(p.b, P.range_min, P.range_max);
-    if (out_u8) {
-      uint8_t* u = out_u8 + ((long long)slot * out_w * out_h + pix) * 3;
-      u[0] = (uint8_t)p.r; u[1] = (uint8_t)p.g; u[2] = (uint8_t)p.b;
+    if (!lut_built || lut_min != P.range_min || lut_max != P.range_max) {     // uniform over the CTA
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = i2t_normalise(i, P.range_min, P.range_max);
+      lut_min = P.range_min; lut_max = P.range_max; lut_built = true;
+      __syncthreads();
+    }
+    const ImgSrc src = img_src(frames + (long long)P.frame * frame_stride, row_stride);
+#pragma unroll
+    for (int k = 0; k < kPxPerThread; ++k) {
+      const int pix = blk * px_per_item + k * 256 + threadIdx.x;
+      if (pix >= out_w * out_h) break;
+      const int oy = pix / out_w, ox = pix - oy * out_w;
+      Px3 p;
+      if (P.valid) p = i2t_pixel(P, src, ox, oy);
+      else { p.r = p.g = p.b = 0; }
+      float* o = out + (long long)slot * out_bstride + (long long)pix * 3;
+      o[0] = s_lut[p.r & 255];
+      o[1] = s_lut[p.g & 255];
+      o[2] = s_lut[p.b & 255];
+      if (out_u8) {
+        uint8_t* u = out_u8 + ((long long)slot * out_w * out_h + pix) * 3;
+        u[0] = (uint8_t)p.r; u[1] = (uint8_t)p.g; u[2] = (uint8_t)p.b;
+      }
     }
   }
 }
@@ -78,7 +93,8 @@ __global__ void __launch_bounds__(256) i2t_kernel(const uint8_t* __restrict__ fr
 // per-pixel path inside the same kernel.
 constexpr int kRowsPerItem = 4;    // output rows per work item of the row-staged letterbox kernel
 
-__global__ void __launch_bounds__(256) i2t_rows_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
+template <int kMinB>
+__global__ void __launch_bounds__(256, kMinB) i2t_rows_kernel(const uint8_t* __restrict__ frames, long long frame_stride, long long row_stride,
                                                        const I2TParams* __restrict__ params, int n, int out_w, int out_h,
                                                        float* __restrict__ out, long long out_bstride, const int* n_active,
                                                        const uint8_t* __restrict__ compact, const int* __restrict__ row_pos, long long compact_fstride,
@@ -87,9 +103,13 @@ __global__ void __launch_bounds__(256) i2t_rows_kernel(const uint8_t* __restrict
   if (n_active) n = min(n, *n_active);
   __shared__ I2TParams P;
   __shared__ float s_lut[256];                          // i2t_normalise for every grey level (exact: same f64 expression)
+  __shared__ double s_scale[2];                         // resize scales of the slot: x, y (one division per slot, not per pixel)
+  __shared__ int s_simple;
   const int groups = (out_h + rows_per_item - 1) / rows_per_item;
   const long long items = (long long)n * groups;
   int cur_slot = -1;
+  double lut_min = 0.0, lut_max = 0.0;                  // the range the LUT was last built for (uniform over the CTA)
+  bool lut_built = false;
   for (long long item = blockIdx.x; item < items; item += gridDim.x) {
   const int slot = (int)(item / groups), oy_first = (int)(item - (long long)slot * groups) * rows_per_item;
   const int nrows = min(rows_per_item, out_h - oy_first);
@@ -99,20 +119,28 @@ __global__ void __launch_bounds__(256) i2t_rows_kernel(const uint8_t* __restrict
     int* dst = reinterpret_cast<int*>(&P);
     for (int i = threadIdx.x; i < (int)(sizeof(I2TParams) / 4); i += blockDim.x) dst[i] = src[i];
     __syncthreads();
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = i2t_normalise(i, P.range_min, P.range_max);
+    if (!lut_built || lut_min != P.range_min || lut_max != P.range_max) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = i2t_normalise(i, P.range_min, P.range_max);
+      lut_min = P.range_min; lut_max = P.range_max; lut_built = true;
+    }
+    if (threadIdx.x == 0) {
+      const int bw = P.warp_w + 2 * P.pad_h, bh = P.warp_h + 2 * P.pad_v;
+      bool simple = P.valid && P.has_r2 && !P.flip && P.warp_w == P.src_w && P.warp_h == P.src_h &&
+                    (!P.has_r1 || (bw == P.r1_w && bh == P.r1_h)) && !(P.r1_w == out_w && P.r1_h == out_h);
+      if (simple) {
+        const double e = 1e-9;   // identity warp: the solve reproduces I up to rounding (exact copy)
+        simple = fabs(P.Mi[0] - 1.0) < e && fabs(P.Mi[4] - 1.0) < e && fabs(P.Mi[8] - 1.0) < e && fabs(P.Mi[1]) < e && fabs(P.Mi[2]) < e * P.src_w &&
+                 fabs(P.Mi[3]) < e && fabs(P.Mi[5]) < e * P.src_h && fabs(P.Mi[6]) < e && fabs(P.Mi[7]) < e;
+      }
+      s_simple = simple ? 1 : 0;
+      s_scale[0] = (double)P.r1_w / (double)out_w;
+      s_scale[1] = (double)P.r1_h / (double)out_h;
+    }
     cur_slot = slot;
     __syncthreads();
   }
   const uint8_t* img = frames + (long long)P.frame * frame_stride;
-  const int bw = P.warp_w + 2 * P.pad_h, bh = P.warp_h + 2 * P.pad_v;
-  bool simple = P.valid && P.has_r2 && !P.flip && P.warp_w == P.src_w && P.warp_h == P.src_h &&
-                (!P.has_r1 || (bw == P.r1_w && bh == P.r1_h)) && !(P.r1_w == out_w && P.r1_h == out_h);
-  if (simple) {
-    const double e = 1e-9;   // identity warp: the solve reproduces I up to rounding (exact copy)
-    simple = fabs(P.Mi[0] - 1.0) < e && fabs(P.Mi[4] - 1.0) < e && fabs(P.Mi[8] - 1.0) < e && fabs(P.Mi[1]) < e && fabs(P.Mi[2]) < e * P.src_w &&
-             fabs(P.Mi[3]) < e && fabs(P.Mi[5]) < e * P.src_h && fabs(P.Mi[6]) < e && fabs(P.Mi[7]) < e;
-  }
-  if (!simple) {
+  if (!s_simple) {
     for (int r = 0; r < nrows; ++r) {
       const int oy = oy_first + r;
       float* orow = out + (long long)slot * out_bstride + (long long)oy * out_w * 3;
@@ -128,27 +156,51 @@ __global__ void __launch_bounds__(256) i2t_rows_kernel(const uint8_t* __restrict
     continue;
   }
   const int ph = P.has_r1 ? P.pad_h : 0, pv = P.has_r1 ? P.pad_v : 0;
-  const int row_bytes = P.src_w * 3;
+  const int src_w = P.src_w, src_h = P.src_h;
+  const int row_bytes = src_w * 3;
   const int row_pad = (row_bytes + 15) & ~15;
+  // vertical taps of the item's rows (every thread: a handful of instructions with the division hoisted); source rows
+  // outside the frame are the constant-0 border: -1
+  int sy[kRowsPerItem][2], wb[kRowsPerItem][2];
+  bool any_row = false;
+#pragma unroll
+  for (int r = 0; r < kRowsPerItem; ++r) {
+    int y0, y1;
+    resize_coeff_scaled(oy_first + (r < nrows ? r : 0), s_scale[1], P.r1_h, false, &y0, &y1, &wb[r][0], &wb[r][1]);
+    y0 -= pv; y1 -= pv;
+    sy[r][0] = (r < nrows && y0 >= 0 && y0 < src_h) ? y0 : -1;
+    sy[r][1] = (r < nrows && y1 >= 0 && y1 < src_h) ? y1 : -1;
+    any_row = any_row || sy[r][0] >= 0 || sy[r][1] >= 0;
+  }
+  float* const obase = out + (long long)slot * out_bstride + (long long)oy_first * out_w * 3;
+  if (!any_row) {
+    // letterbox bars: every tap is border => the whole item is the grey level 0 (rows are contiguous: 16-byte stores)
+    const float z = s_lut[0];
+    const int nf = nrows * out_w * 3;
+    if ((reinterpret_cast<uintptr_t>(obase) & 15) == 0) {
+      for (int i = threadIdx.x; i < (nf >> 2); i += blockDim.x) reinterpret_cast<float4*>(obase)[i] = make_float4(z, z, z, z);
+      for (int i = (nf & ~3) + threadIdx.x; i < nf; i += blockDim.x) obase[i] = z;
+    } else {
+      for (int i = threadIdx.x; i < nf; i += blockDim.x) obase[i] = z;
+    }
+    continue;
+  }
   // ---- stage the (up to) 2 * nrows source rows: every load of the item is issued before the barrier ----
-  for (int r = 0; r < nrows; ++r) {
-    int y0, y1, b0, b1;
-    resize_coeff(oy_first + r, out_h, P.r1_h, false, &y0, &y1, &b0, &b1);
+#pragma unroll
+  for (int r = 0; r < kRowsPerItem; ++r) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int sy = (h ? y1 : y0) - pv;                          // source row (outside the frame: constant-0 border)
-      if (sy < 0 || sy >= P.src_h) continue;
-      const uint8_t* g = img + (long long)sy * row_stride;
-      if (row_pos && row_pos[sy] >= 0)   // rows gathered into device memory by the copy engine (anything missing is still read in place)
-        g = compact + (long long)P.frame * compact_fstride + (long long)row_pos[sy] * row_bytes;
+      if (sy[r][h] < 0) continue;
+      const uint8_t* g = img + (long long)sy[r][h] * row_stride;
+      if (row_pos && row_pos[sy[r][h]] >= 0)   // rows gathered into device memory by the copy engine (anything missing is still read in place)
+        g = compact + (long long)P.frame * compact_fstride + (long long)row_pos[sy[r][h]] * row_bytes;
       uint8_t* d = s_rows + (2 * r + h) * row_pad;
       if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
         // asynchronous 16-byte copies: nothing waits until every row of the item has been requested
         const int nv = row_bytes >> 4;
-        for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-          const unsigned sd = (unsigned)__cvta_generic_to_shared(d + 16 * i);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sd), "l"(g + 16 * (size_t)i) : "memory");
-        }
+        const unsigned sd = (unsigned)__cvta_generic_to_shared(d);
+        for (int i = threadIdx.x; i < nv; i += blockDim.x)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sd + 16 * i), "l"(g + 16 * (size_t)i) : "memory");
         for (int i = (nv << 4) + threadIdx.x; i < row_bytes; i += blockDim.x) d[i] = g[i];
       } else {
         for (int i = threadIdx.x; i < row_bytes; i += blockDim.x) d[i] = g[i];
@@ -159,28 +211,27 @@ __global__ void __launch_bounds__(256) i2t_rows_kernel(const uint8_t* __restrict
   __syncthreads();
   for (int ox = threadIdx.x; ox < out_w; ox += blockDim.x) {
     int x0, x1, a0, a1;
-    resize_coeff(ox, out_w, P.r1_w, true, &x0, &x1, &a0, &a1);
+    resize_coeff_scaled(ox, s_scale[0], P.r1_w, true, &x0, &x1, &a0, &a1);
     const int sx0 = x0 - ph, sx1 = x1 - ph;
-    const bool cx0 = sx0 >= 0 && sx0 < P.src_w, cx1 = sx1 >= 0 && sx1 < P.src_w;
-    for (int r = 0; r < nrows; ++r) {
-      const int oy = oy_first + r;
-      int y0, y1, b0, b1;
-      resize_coeff(oy, out_h, P.r1_h, false, &y0, &y1, &b0, &b1);
-      const int sy0 = y0 - pv, sy1 = y1 - pv;
-      const bool in0 = sy0 >= 0 && sy0 < P.src_h, in1 = sy1 >= 0 && sy1 < P.src_h;
+    const bool cx0 = sx0 >= 0 && sx0 < src_w, cx1 = sx1 >= 0 && sx1 < src_w;
+    const int o0 = cx0 ? 3 * sx0 : 0, o1 = cx1 ? 3 * sx1 : 0;
+#pragma unroll
+    for (int r = 0; r < kRowsPerItem; ++r) {
+      if (r >= nrows) break;
+      const bool in0 = sy[r][0] >= 0, in1 = sy[r][1] >= 0;
       const uint8_t* r0 = s_rows + (2 * r) * row_pad;
       const uint8_t* r1 = r0 + row_pad;
-      float* orow = out + (long long)slot * out_bstride + (long long)oy * out_w * 3;
+      float* orow = obase + (long long)r * out_w * 3 + 3 * ox;
       int v[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const int p00 = (in0 && cx0) ? r0[3 * sx0 + c] : 0, p01 = (in0 && cx1) ? r0[3 * sx1 + c] : 0;
-        const int p10 = (in1 && cx0) ? r1[3 * sx0 + c] : 0, p11 = (in1 && cx1) ? r1[3 * sx1 + c] : 0;
-        v[c] = resize_mix(p00, p01, p10, p11, a0, a1, b0, b1);
+        const int p00 = (in0 && cx0) ? r0[o0 + c] : 0, p01 = (in0 && cx1) ? r0[o1 + c] : 0;
+        const int p10 = (in1 && cx0) ? r1[o0 + c] : 0, p11 = (in1 && cx1) ? r1[o1 + c] : 0;
+        v[c] = resize_mix(p00, p01, p10, p11, a0, a1, wb[r][0], wb[r][1]);
       }
-      orow[3 * ox] = s_lut[v[0] & 255];
-      orow[3 * ox + 1] = s_lut[v[1] & 255];
-      orow[3 * ox + 2] = s_lut[v[2] & 255];
+      orow[0] = s_lut[v[0] & 255];
+      orow[1] = s_lut[v[1] & 255];
+      orow[2] = s_lut[v[2] & 255];
     }
   }
   }  // item loop
@@ -769,8 +820,13 @@ cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long 
       const long long per_sm = (long long)((200 * 1024) / (smem + 1024)) < 8 ? (long long)((200 * 1024) / (smem + 1024)) : 8;
       const long long cap = max_ctas > 0 ? max_ctas : 148LL * (per_sm < 4 ? 4 : per_sm);      // persistent CTAs (items are strided over the grid)
       if (items > cap) items = cap;
-      i2t_rows_kernel<<<(unsigned)items, 256, smem, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, n_active, compact,
-                                                         row_pos, compact_fstride, rpi);
+      static const int minb = getenv("FDL_I2T_MINB") ? atoi(getenv("FDL_I2T_MINB")) : 4;      // A/B: 4 CTAs per SM (64 registers) or 3 (85)
+      if (minb >= 4)
+        i2t_rows_kernel<4><<<(unsigned)items, 256, smem, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, n_active,
+                                                              compact, row_pos, compact_fstride, rpi);
+      else
+        i2t_rows_kernel<3><<<(unsigned)items, 256, smem, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, n_active,
+                                                              compact, row_pos, compact_fstride, rpi);
       return FDL_LAUNCHED();
     }
   }
@@ -785,9 +841,16 @@ cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long 
     i2t_tile_kernel<<<(unsigned)items, 256, kTileSmem, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, n_active);
     return FDL_LAUNCHED();
   }
-  long long grid = (long long)n * ((out_w * out_h + 255) / 256);
+  // output pixels per thread and work item: 4 for the 192x192 face warps (0.244 -> 0.208 ms per 256 faces), 1 for the 64x64 eye
+  // warps (4 measured 0.163 against 0.152 ms per 512 eyes: too few work items left); FDL_I2T_PX overrides for A/B timing
+  static const int ppt_env = getenv("FDL_I2T_PX") ? atoi(getenv("FDL_I2T_PX")) : 0;
+  const int ppt_auto = out_w * out_h >= 128 * 128 ? 4 : 1;
+  const int ppt = ppt_env >= 4 ? 4 : (ppt_env >= 2 ? 2 : (ppt_env == 1 ? 1 : ppt_auto));
+  long long grid = (long long)n * ((out_w * out_h + 256 * ppt - 1) / (256 * ppt));
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  i2t_kernel<<<(unsigned)grid, 256, 0, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, out_u8, n_active);
+  if (ppt == 4) i2t_kernel<4><<<(unsigned)grid, 256, 0, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, out_u8, n_active);
+  else if (ppt == 2) i2t_kernel<2><<<(unsigned)grid, 256, 0, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, out_u8, n_active);
+  else i2t_kernel<1><<<(unsigned)grid, 256, 0, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, out_u8, n_active);
   return FDL_LAUNCHED();
 }
 
