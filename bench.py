@@ -144,9 +144,22 @@ def _dominant_kernel(B, device):
             "ms": float(np.mean(ms[idx])), "algo_bytes": 2 * B * 128 * 128 * 24 * 4, "traffic": traffic, "traffic_source": src}
 
 
-def roi_rect_bytes(roi, margin=2):
-    """Bytes roi_fill_kernel copies for one face: the bounding rectangle of the rotated face ROI in frame pixels (+ the warp's
-    -1 / +2 tap slack and the 2 px margin), clipped to the frame, rows widened to 16-byte pieces."""
+def letterbox_rows():
+    """Source rows of a 1080p frame the 256x256 letterbox interpolates between (the rows the copy engine gathers)."""
+    rows = set()
+    for dy in range(256):
+        f = np.float32((dy + 0.5) * (1920.0 / 256.0) - 0.5)
+        s = int(np.floor(f))
+        for r in (min(max(s, 0), 1919) - 420, min(max(s + 1, 0), 1919) - 420):
+            if 0 <= r < H:
+                rows.add(r)
+    return rows
+
+
+def roi_rect_bytes(roi, margin=2, on_device=frozenset()):
+    """Host bytes roi_fill_kernel copies for one face: the bounding rectangle of the rotated face ROI in frame pixels (+ the
+    warp's -1 / +2 tap slack and the 2 px margin), clipped to the frame, rows widened to 16-byte pieces; rows in `on_device`
+    (already gathered for the letterbox) are copied device-to-device and do not count."""
     import math
     w, h = roi.width * W, roi.height * H
     c, s_ = abs(math.cos(roi.rotation)), abs(math.sin(roi.rotation))
@@ -158,7 +171,7 @@ def roi_rect_bytes(roi, margin=2):
     if x1 < x0 or y1 < y0:
         return 0
     sb, eb = (3 * x0) & ~15, min((3 * (x1 + 1) + 15) & ~15, 3 * W)
-    return (eb - sb) * (y1 - y0 + 1)
+    return (eb - sb) * sum(1 for y in range(y0, y1 + 1) if y not in on_device)
 
 
 def zero_copy_bytes_per_frame(face_rect_bytes=None):
@@ -166,13 +179,7 @@ def zero_copy_bytes_per_frame(face_rect_bytes=None):
     (gathered by the copy engine) plus the face rectangle roi_fill_kernel stages on the device (measured from the last batch's
     face ROIs); without that measurement, an upper bound for in-place ROI warps (4 taps x 3 B per output pixel of the 192x192
     face crop, 16 taps for the two-stage 64x64 eye crops)."""
-    rows = set()
-    for dy in range(256):
-        f = np.float32((dy + 0.5) * (1920.0 / 256.0) - 0.5)
-        s = int(np.floor(f))
-        for r in (min(max(s, 0), 1919) - 420, min(max(s + 1, 0), 1919) - 420):
-            if 0 <= r < H:
-                rows.add(r)
+    rows = letterbox_rows()
     if face_rect_bytes is not None:
         return len(rows) * W * 3 + int(face_rect_bytes)
     return len(rows) * W * 3 + 192 * 192 * 4 * 3 + 2 * 64 * 64 * 16 * 3
@@ -362,7 +369,8 @@ def run_ours(args):
         e2e_zc_s = e2e_loop(pipe_zc)
         zc_faces = sum(pipe_zc._frames[i].n_faces for i in range(B))
         assert zc_faces == n_faces, "zero-copy path disagrees with the copy path"
-        zc_rect_bytes = float(np.mean([sum(roi_rect_bytes(pipe_zc._faces[i * pipe_zc.max_faces + f].face_roi)
+        on_dev = frozenset(letterbox_rows()) if os.environ.get("FDL_ZC_REUSE", "1") != "0" else frozenset()
+        zc_rect_bytes = float(np.mean([sum(roi_rect_bytes(pipe_zc._faces[i * pipe_zc.max_faces + f].face_roi, on_device=on_dev)
                                            for f in range(pipe_zc._frames[i].n_faces)) for i in range(B)]))
         pipe_zc.close()
     e2e_s = min(e2e_copy_s, e2e_zc_s) if e2e_zc_s is not None else e2e_copy_s

@@ -320,7 +320,12 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
     const bool crop = used_host && crop_env && lane->face_boxes.p && lane->frames.cap >= (size_t)fstride * n && (row & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(fptr) & 15) == 0;     // 16-byte row copies
     if (crop) {
-      FDL_CUDA_TRY(launch_roi_fill(fptr, lane->frames.p, fstride, row, lane->face_params.p, F, n_faces, lane->face_boxes.p, H, zc_ctas * 4, cs));
+      // rows of the rectangle that the letterbox gather already brought to the device (2 of every 7.5 at 1080p) are taken from there
+      static const int reuse_env = getenv("FDL_ZC_REUSE") ? atoi(getenv("FDL_ZC_REUSE")) : 1;
+      const bool reuse = gathered && reuse_env;
+      FDL_CUDA_TRY(launch_roi_fill(fptr, lane->frames.p, fstride, row, lane->face_params.p, F, n_faces, lane->face_boxes.p, H, zc_ctas * 4, cs,
+                                   reuse ? lane->rows.p : nullptr, reuse ? p->gather.row_pos.p : nullptr,
+                                   reuse ? (long long)p->gather.rows_per_frame * row : 0));
       FDL_CUDA_TRY(launch_i2t(lane->frames.p, fstride, row, lane->face_params.p, F, p->LS, p->LS, lane->lmk_in.p, (long long)p->LS * p->LS * 3, nullptr, n_faces, cs, 0, 0, 0));
     } else {
       FDL_CUDA_TRY(launch_i2t(fptr, fstride, row, lane->face_params.p, F, p->LS, p->LS, lane->lmk_in.p, (long long)p->LS * p->LS * 3, nullptr, n_faces, cs, 0, 0, zc_ctas));

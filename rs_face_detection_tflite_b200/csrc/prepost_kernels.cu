@@ -709,7 +709,8 @@ constexpr int kFillRows = 16;      // frame rows per work item of roi_fill_kerne
 
 __global__ void __launch_bounds__(256) roi_fill_kernel(const uint8_t* __restrict__ host_frames, uint8_t* __restrict__ dev_frames,
                                                        long long frame_stride, long long row_stride, const I2TParams* __restrict__ params,
-                                                       int n, const int* n_active, SrcBox* boxes, int frame_h, int fill_margin_pct) {
+                                                       int n, const int* n_active, SrcBox* boxes, int frame_h, int fill_margin_pct,
+                                                       const uint8_t* __restrict__ compact, const int* __restrict__ row_pos, long long compact_fstride) {
   if (n_active) n = min(n, *n_active);
   __shared__ SrcBox s_box;
   __shared__ int s_frame;
@@ -743,6 +744,10 @@ __global__ void __launch_bounds__(256) roi_fill_kernel(const uint8_t* __restrict
     const long long base = (long long)s_frame * frame_stride + sb;
     for (int r = r0 + warp; r <= r1; r += 8) {
       const uint4* src = reinterpret_cast<const uint4*>(host_frames + base + (long long)r * row_stride);
+      if (row_pos) {       // rows the copy engine already gathered for the letterbox are on the device: they do not cross PCIe again
+        const int cp = row_pos[r];
+        if (cp >= 0) src = reinterpret_cast<const uint4*>(compact + (long long)s_frame * compact_fstride + (long long)cp * row_stride + sb);
+      }
       uint4* dst = reinterpret_cast<uint4*>(dev_frames + base + (long long)r * row_stride);
       for (int q = lane; q < nq; q += 32) dst[q] = __ldg(src + q);
     }
@@ -912,12 +917,14 @@ cudaError_t launch_iris_metrics(const double* iris, int img_w, int img_h, double
 }
 
 cudaError_t launch_roi_fill(const uint8_t* host_frames, uint8_t* dev_frames, long long frame_stride, long long row_stride, const I2TParams* params,
-                            int n, const int* n_active, SrcBox* boxes, int frame_h, int max_ctas, cudaStream_t s) {
+                            int n, const int* n_active, SrcBox* boxes, int frame_h, int max_ctas, cudaStream_t s, const uint8_t* compact,
+                            const int* row_pos, long long compact_fstride) {
   if (n <= 0) return cudaSuccess;
   long long items = (long long)n * ((frame_h + kFillRows - 1) / kFillRows);
   if (max_ctas > 0 && items > max_ctas) items = max_ctas;
   static const int margin_env = getenv("FDL_ZC_MARGIN") ? atoi(getenv("FDL_ZC_MARGIN")) : 0;
-  roi_fill_kernel<<<(unsigned)items, 256, 0, s>>>(host_frames, dev_frames, frame_stride, row_stride, params, n, n_active, boxes, frame_h, margin_env);
+  roi_fill_kernel<<<(unsigned)items, 256, 0, s>>>(host_frames, dev_frames, frame_stride, row_stride, params, n, n_active, boxes, frame_h, margin_env,
+                                                  compact, row_pos, compact_fstride);
   return FDL_LAUNCHED();
 }
 cudaError_t launch_eye_split(const I2TParams* eye_params, const SrcBox* face_boxes, int n, const int* n_active, I2TParams* p_dev, I2TParams* p_host,

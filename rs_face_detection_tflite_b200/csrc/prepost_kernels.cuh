@@ -34,7 +34,8 @@ struct SrcBox { int x0, y0, x1, y1; };
 // Zero-copy host frames: copy the (margin-grown) source rectangle of every face warp from the pinned host frames into the device
 // frame buffer at the same offsets, and split the eye slots between the device copy and the host frames (see prepost_kernels.cu).
 cudaError_t launch_roi_fill(const uint8_t* host_frames, uint8_t* dev_frames, long long frame_stride, long long row_stride, const I2TParams* params,
-                            int n, const int* n_active, SrcBox* boxes, int frame_h, int max_ctas, cudaStream_t s);
+                            int n, const int* n_active, SrcBox* boxes, int frame_h, int max_ctas, cudaStream_t s,
+                            const uint8_t* compact = nullptr, const int* row_pos = nullptr, long long compact_fstride = 0);
 cudaError_t launch_eye_split(const I2TParams* eye_params, const SrcBox* face_boxes, int n, const int* n_active, I2TParams* p_dev, I2TParams* p_host,
                              cudaStream_t s);
 cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long row_stride, const I2TParams* params, int n,
