@@ -156,22 +156,45 @@ def letterbox_rows():
     return rows
 
 
-def roi_rect_bytes(roi, margin=2, on_device=frozenset()):
-    """Host bytes roi_fill_kernel copies for one face: the bounding rectangle of the rotated face ROI in frame pixels (+ the
-    warp's -1 / +2 tap slack and the 2 px margin), clipped to the frame, rows widened to 16-byte pieces; rows in `on_device`
-    (already gathered for the letterbox) are copied device-to-device and do not count."""
+def roi_rect_bytes(roi, margin=2, on_device=frozenset(), trim=True):
+    """Host bytes roi_fill_kernel copies for one face: per frame row, the span of the rotated face ROI (the quadrilateral its
+    samples lie in, over the rows [y - 1.25 - margin, y + 1.25 + margin]) + the warp's -1 / +2 tap slack and the margin, clipped
+    to the ROI's bounding rectangle and the frame, widened to 16-byte pieces (trim=False: the whole bounding rectangle); rows in
+    `on_device` (already gathered for the letterbox) are copied device-to-device and do not count."""
     import math
     w, h = roi.width * W, roi.height * H
-    c, s_ = abs(math.cos(roi.rotation)), abs(math.sin(roi.rotation))
-    bw, bh = w * c + h * s_, w * s_ + h * c
-    x0 = max(int(math.floor(roi.x_center * W - bw / 2)) - 1 - margin, 0)
-    x1 = min(int(math.ceil(roi.x_center * W + bw / 2)) + 2 + margin, W - 1)
-    y0 = max(int(math.floor(roi.y_center * H - bh / 2)) - 1 - margin, 0)
-    y1 = min(int(math.ceil(roi.y_center * H + bh / 2)) + 2 + margin, H - 1)
-    if x1 < x0 or y1 < y0:
+    cx, cy = roi.x_center * W, roi.y_center * H
+    c, s_ = math.cos(roi.rotation), math.sin(roi.rotation)
+    quad = [(cx + dx * c - dy * s_, cy + dx * s_ + dy * c) for dx, dy in ((-w / 2, -h / 2), (w / 2, -h / 2), (w / 2, h / 2), (-w / 2, h / 2))]
+    bx0 = max(int(math.floor(min(q[0] for q in quad))) - 1 - margin, 0)
+    bx1 = min(int(math.ceil(max(q[0] for q in quad))) + 2 + margin, W - 1)
+    y0 = max(int(math.floor(min(q[1] for q in quad))) - 1 - margin, 0)
+    y1 = min(int(math.ceil(max(q[1] for q in quad))) + 2 + margin, H - 1)
+    if bx1 < bx0 or y1 < y0:
         return 0
-    sb, eb = (3 * x0) & ~15, min((3 * (x1 + 1) + 15) & ~15, 3 * W)
-    return (eb - sb) * sum(1 for y in range(y0, y1 + 1) if y not in on_device)
+    total = 0
+    for y in range(y0, y1 + 1):
+        if y in on_device:
+            continue
+        x0, x1 = bx0, bx1
+        if trim:
+            ya, yb = y - 1.25 - margin, y + 1.25 + margin
+            xs = []
+            for e in range(4):
+                (px0, py0), (px1, py1) = quad[e], quad[(e + 1) & 3]
+                if ya <= py0 <= yb:
+                    xs.append(px0)
+                for yy in (ya, yb):
+                    if (py0 - yy) * (py1 - yy) < 0:
+                        xs.append(px0 + (yy - py0) / (py1 - py0) * (px1 - px0))
+            if not xs:
+                continue
+            x0, x1 = max(int(math.floor(min(xs))) - 1 - margin, bx0), min(int(math.ceil(max(xs))) + 2 + margin, bx1)
+            if x1 < x0:
+                continue
+        sb, eb = (3 * x0) & ~15, min((3 * (x1 + 1) + 15) & ~15, 3 * W)
+        total += eb - sb
+    return total
 
 
 def zero_copy_bytes_per_frame(face_rect_bytes=None):
@@ -370,7 +393,8 @@ def run_ours(args):
         zc_faces = sum(pipe_zc._frames[i].n_faces for i in range(B))
         assert zc_faces == n_faces, "zero-copy path disagrees with the copy path"
         on_dev = frozenset(letterbox_rows()) if os.environ.get("FDL_ZC_REUSE", "1") != "0" else frozenset()
-        zc_rect_bytes = float(np.mean([sum(roi_rect_bytes(pipe_zc._faces[i * pipe_zc.max_faces + f].face_roi, on_device=on_dev)
+        zc_rect_bytes = float(np.mean([sum(roi_rect_bytes(pipe_zc._faces[i * pipe_zc.max_faces + f].face_roi, on_device=on_dev,
+                                                          trim=os.environ.get("FDL_ZC_TRIM", "1") != "0")
                                            for f in range(pipe_zc._frames[i].n_faces)) for i in range(B)]))
         pipe_zc.close()
     e2e_s = min(e2e_copy_s, e2e_zc_s) if e2e_zc_s is not None else e2e_copy_s
