@@ -138,6 +138,40 @@ def test_batched_pipeline_matches_oracle(fdl, gpu, oracle_pipeline):
     zc.close()
 
 
+def test_zero_copy_roi_staging_is_exact_over_many_rois(fdl, gpu):
+    """Zero-copy host frames stage only the rotated face ROI's row spans on the device (and reuse the letterbox's gathered rows);
+    a missing byte would surface as a different landmark.  48 frames (seeded scales / rotations / positions) go twice through the
+    same lanes in a different order, so stale bytes of an earlier frame cannot stand in for a missing copy."""
+    import synth_frames
+    import torch
+    n = 48
+    frames = synth_frames.face_frames(n, start=100)
+    dev = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (1920, 1080), max_batch=16, max_faces=2, model_dir=MODELS, device=gpu)
+    ref = []
+    for i in range(0, n, 16):
+        ref += dev.collect(dev.submit(torch.from_numpy(frames[i:i + 16]).cuda()))
+    dev.close()
+    assert sum(1 for r in ref for f in r.faces if f.landmarks is not None) >= n // 2
+    zc = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (1920, 1080), max_batch=16, max_faces=2, model_dir=MODELS, device=gpu, zero_copy_host=True)
+    pinned = torch.from_numpy(frames).pin_memory()
+    for order in ((0, 16, 32), (32, 0, 16)):
+        tickets = [(o, zc.submit(pinned[o:o + 16])) for o in order]
+        for o, t in tickets:
+            got = zc.collect(t)
+            for a, b in zip(ref[o:o + 16], got):
+                assert [d.anchor for d in a.detections] == [d.anchor for d in b.detections]
+                assert len(a.faces) == len(b.faces)
+                for fa, fb in zip(a.faces, b.faces):
+                    assert (fa.landmarks is None) == (fb.landmarks is None)
+                    if fa.landmarks is not None:
+                        np.testing.assert_array_equal(fa.landmarks, fb.landmarks)
+                        np.testing.assert_array_equal(fa.left_contour, fb.left_contour)
+                        np.testing.assert_array_equal(fa.right_contour, fb.right_contour)
+                        np.testing.assert_array_equal(fa.left_iris, fb.left_iris)
+                        np.testing.assert_array_equal(fa.right_iris, fb.right_iris)
+    zc.close()
+
+
 def test_detection_only_pipeline_and_errors(fdl, gpu):
     import synth_frames
     frames = synth_frames.face_frames(2, 640, 480)
