@@ -269,7 +269,7 @@ def run_reference(args):
     cores = pool.workers
     sample = "%d G2 1080p frames per step, restated reference CPU path (cv2 + torch-CPU f32 + numpy), one single-threaded worker process per " \
              "host core (%d of %d cores), each frame through the reference's per-frame call sequence" % (per_step, cores, os.cpu_count())
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
@@ -472,10 +472,22 @@ def run_ours(args):
         }
         if cpu:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        emit(out)
     pipe.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+_JSON_FD = None
+
+
+def emit(obj):
+    """The result line, on the process's original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
@@ -495,6 +507,11 @@ def main():
     ap.add_argument("--dev-inflight", type=int, default=3, help="batches in flight in the device-resident loop (<= pipeline depth 4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly one JSON line: anything libraries write to fd 1 meanwhile (NCCL's version banner, ...) goes to stderr
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
