@@ -210,7 +210,8 @@ FDL_HD Px3 load_px(const ImgSrc& s, int x, int y) {
 }
 
 // cv::warpPerspective(INTER_LINEAR, BORDER_CONSTANT 0) at destination pixel (x,y): SURVEY.md B.2.
-FDL_HD Px3 warp_px(const I2TParams& P, const ImgSrc& src, int x, int y) {
+// source position of destination pixel (x,y) in 1/32-pixel fixed point: top-left tap (sx, sy) and the fractions (ax, ay) / 32
+FDL_HD void warp_coords(const I2TParams& P, int x, int y, int* sx_out, int* sy_out, int* ax_out, int* ay_out) {
   const double* Mi = P.Mi;
   double W = Mi[6] * x + Mi[7] * y + Mi[8];
   W = W != 0.0 ? 32.0 / W : 0.0;
@@ -220,9 +221,14 @@ FDL_HD Px3 warp_px(const I2TParams& P, const ImgSrc& src, int x, int y) {
   fY = dmax(-2147483648.0, dmin(2147483647.0, fY));
   int X = (int)rint(fX), Y = (int)rint(fY);            // clamped to the int32 range above: the conversion is exact
   int sxl = X >> 5, syl = Y >> 5;
-  int sx = sxl < -32768 ? -32768 : (sxl > 32767 ? 32767 : sxl);   // saturate_cast<short>
-  int sy = syl < -32768 ? -32768 : (syl > 32767 ? 32767 : syl);
-  int ax = X & 31, ay = Y & 31;
+  *sx_out = sxl < -32768 ? -32768 : (sxl > 32767 ? 32767 : sxl);   // saturate_cast<short>
+  *sy_out = syl < -32768 ? -32768 : (syl > 32767 ? 32767 : syl);
+  *ax_out = X & 31; *ay_out = Y & 31;
+}
+
+FDL_HD Px3 warp_px(const I2TParams& P, const ImgSrc& src, int x, int y) {
+  int sx, sy, ax, ay;
+  warp_coords(P, x, y, &sx, &sy, &ax, &ay);
   // OpenCV's bilinear table: float32 products of (1-fy),(fy) x (1-fx),(fx), scaled by 32768 and rounded
   float fx = (float)ax * (1.f / 32.f), fy = (float)ay * (1.f / 32.f);
   int w00 = (int)rintf((1.f - fy) * (1.f - fx) * 32768.f);
@@ -239,6 +245,102 @@ FDL_HD Px3 warp_px(const I2TParams& P, const ImgSrc& src, int x, int y) {
   Px3 o;
   o.r = (r + (1 << 14)) >> 15; o.g = (g + (1 << 14)) >> 15; o.b = (b + (1 << 14)) >> 15;
   return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Zero-copy host frames: which frame bytes a warp can touch (roi_fill_kernel / eye_split_kernel, prepost_kernels.cu; checked on
+// the host by tests/hostcheck against every tap of warp_px).
+// Source region of a warp in frame pixels: the bounding rectangle of its taps and, when `quad` is set, the convex quadrilateral
+// (corners of warp space through the inverse matrix, in polygon order) the samples themselves lie in.
+struct SrcBox { int x0, y0, x1, y1; int quad, _pad; double qx[4], qy[4]; };
+
+FDL_HD SrcBox warp_src_box(const I2TParams& P) {
+  // the corners of warp space through the inverse matrix: every tap of the warp lies in [floor(lo) - 1, ceil(hi) + 2]
+  SrcBox b; b.x0 = 0; b.y0 = 0; b.x1 = -1; b.y1 = -1; b.quad = 0; b._pad = 0;
+  for (int c = 0; c < 4; ++c) b.qx[c] = b.qy[c] = 0.0;
+  if (P.valid != 1) return b;
+  double lox = 1e30, loy = 1e30, hix = -1e30, hiy = -1e30;
+  for (int c = 0; c < 4; ++c) {
+    const int xr = (c == 1 || c == 2), yr = (c >= 2);              // polygon order: (0,0) (w-1,0) (w-1,h-1) (0,h-1)
+    const double x = xr ? (double)(P.warp_w - 1) : 0.0, y = yr ? (double)(P.warp_h - 1) : 0.0;
+    const double w = P.Mi[6] * x + P.Mi[7] * y + P.Mi[8];
+    if (!(w > 1e-6)) return b;
+    const double sx = (P.Mi[0] * x + P.Mi[1] * y + P.Mi[2]) / w, sy = (P.Mi[3] * x + P.Mi[4] * y + P.Mi[5]) / w;
+    b.qx[c] = sx; b.qy[c] = sy;
+    lox = dmin(lox, sx); hix = dmax(hix, sx); loy = dmin(loy, sy); hiy = dmax(hiy, sy);
+  }
+  if (!(hix - lox < 1e5 && hiy - loy < 1e5 && lox > -1e6 && loy > -1e6)) return b;
+  b.x0 = (int)floor(lox) - 1; b.y0 = (int)floor(loy) - 1; b.x1 = (int)ceil(hix) + 2; b.y1 = (int)ceil(hiy) + 2;
+  // every sample of the warp stage (whatever border / resize stages follow it) lies inside the image of warp space, a convex
+  // quadrilateral
+  b.quad = 1;
+  return b;
+}
+
+// x extent of the quadrilateral over the rows [ya, yb]: false when it does not reach the band
+FDL_HD bool quad_span(const SrcBox& b, double ya, double yb, double* xlo, double* xhi) {
+  double lo = 1e30, hi = -1e30;
+  for (int e = 0; e < 4; ++e) {
+    const double x0 = b.qx[e], y0 = b.qy[e], x1 = b.qx[(e + 1) & 3], y1 = b.qy[(e + 1) & 3];
+    if (y0 >= ya && y0 <= yb) { lo = dmin(lo, x0); hi = dmax(hi, x0); }
+    if ((y0 - ya) * (y1 - ya) < 0.0) { const double x = x0 + (ya - y0) / (y1 - y0) * (x1 - x0); lo = dmin(lo, x); hi = dmax(hi, x); }
+    if ((y0 - yb) * (y1 - yb) < 0.0) { const double x = x0 + (yb - y0) / (y1 - y0) * (x1 - x0); lo = dmin(lo, x); hi = dmax(hi, x); }
+  }
+  *xlo = lo; *xhi = hi;
+  return hi >= lo;
+}
+
+// signed distance-like test: is (x, y) inside the convex quadrilateral, at least `d` pixels from every edge?
+FDL_HD bool quad_contains(const SrcBox& b, double x, double y, double d) {
+  int pos = 0, neg = 0;
+  for (int e = 0; e < 4; ++e) {
+    const double x0 = b.qx[e], y0 = b.qy[e], ex = b.qx[(e + 1) & 3] - x0, ey = b.qy[(e + 1) & 3] - y0;
+    const double len = sqrt(ex * ex + ey * ey);
+    if (!(len > 1e-9)) return false;
+    const double dist = (ex * (y - y0) - ey * (x - x0)) / len;     // > 0 on one side of the edge for every edge of a convex polygon
+    if (dist >= d) ++pos; else if (dist <= -d) ++neg; else return false;
+  }
+  return pos == 4 || neg == 4;
+}
+
+// The region roi_fill_kernel stages for a face slot: the tap rectangle grown by margin m = pct % of its larger side + 2 px and
+// clipped to the frame; `trim`: rows are copied only over the quadrilateral's span (roi_row_span).
+FDL_HD SrcBox roi_stage_box(const I2TParams& P, int margin_pct, bool trim, int* margin) {
+  SrcBox b = warp_src_box(P);
+  *margin = 0;
+  if (b.x1 >= b.x0) {
+    const int m = (imax(b.x1 - b.x0, b.y1 - b.y0) * margin_pct) / 100 + 2;
+    b.x0 = imax(b.x0 - m, 0); b.y0 = imax(b.y0 - m, 0); b.x1 = imin(b.x1 + m, P.src_w - 1); b.y1 = imin(b.y1 + m, P.src_h - 1);
+    *margin = m;
+    if (!trim) b.quad = 0;
+  }
+  return b;
+}
+
+// Columns [x0, x1] of frame row r that are staged: taps of samples with |sy - r| <= 1 (+ the fixed-point rounding of the warp
+// coordinates and the margin), widened by the same -1 / +2 tap slack as the rectangle.  false: nothing of this row.
+FDL_HD bool roi_row_span(const SrcBox& b, int r, int margin, int* x0, int* x1) {
+  if (r < b.y0 || r > b.y1 || b.x1 < b.x0) return false;
+  *x0 = b.x0; *x1 = b.x1;
+  if (b.quad) {
+    double lo, hi;
+    if (!quad_span(b, (double)r - 1.25 - margin, (double)r + 1.25 + margin, &lo, &hi)) return false;
+    *x0 = imax((int)floor(lo) - 1 - margin, b.x0); *x1 = imin((int)ceil(hi) + 2 + margin, b.x1);
+  }
+  return *x1 >= *x0;
+}
+
+// May a warp with source region `e` (warp_src_box of an eye slot) run on the staged copy of face region `f`?  Its tap rectangle
+// must be inside the face's; when the face rows were trimmed, every sample of the eye warp must lie inside the face quadrilateral
+// (then its taps are taps the face warp's own samples could have, which is what the per-row spans cover).
+FDL_HD bool roi_stage_covers(const SrcBox& f, const SrcBox& e, int src_w, int src_h) {
+  if (!(e.x1 >= e.x0 && f.x1 >= f.x0)) return false;
+  if (!(imax(e.x0, 0) >= f.x0 && imax(e.y0, 0) >= f.y0 && imin(e.x1, src_w - 1) <= f.x1 && imin(e.y1, src_h - 1) <= f.y1)) return false;
+  if (f.quad) {
+    if (!e.quad) return false;
+    for (int c = 0; c < 4; ++c) if (!quad_contains(f, e.qx[c], e.qy[c], 0.25)) return false;
+  }
+  return true;
 }
 
 // cv::resize(INTER_LINEAR) coefficients for one axis. clamp_frac: x axis.  `scale` = (double)sn / (double)dn

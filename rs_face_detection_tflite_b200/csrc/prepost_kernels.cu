@@ -688,57 +688,6 @@ __global__ void iris_metrics_kernel(const double* iris, int img_w, int img_h, do
 // effective), the source rectangle of the face warp, grown by a margin, is copied ONCE with fully coalesced 16-byte loads into
 // the lane's device frame buffer AT THE SAME OFFSETS; the warps then run on that buffer with unchanged coordinates (so their
 // arithmetic is untouched).  Eye warps whose own source rectangle is not inside the copied one keep reading the host frame.
-__device__ __forceinline__ SrcBox warp_src_box(const I2TParams& P) {
-  // the corners of warp space through the inverse matrix: every tap of the warp lies in [floor(lo) - 1, ceil(hi) + 2]
-  SrcBox b; b.x0 = 0; b.y0 = 0; b.x1 = -1; b.y1 = -1; b.quad = 0; b._pad = 0;
-  for (int c = 0; c < 4; ++c) b.qx[c] = b.qy[c] = 0.0;
-  if (P.valid != 1) return b;
-  double lox = 1e30, loy = 1e30, hix = -1e30, hiy = -1e30;
-  for (int c = 0; c < 4; ++c) {
-    const int xr = (c == 1 || c == 2), yr = (c >= 2);              // polygon order: (0,0) (w-1,0) (w-1,h-1) (0,h-1)
-    const double x = xr ? (double)(P.warp_w - 1) : 0.0, y = yr ? (double)(P.warp_h - 1) : 0.0;
-    const double w = P.Mi[6] * x + P.Mi[7] * y + P.Mi[8];
-    if (!(w > 1e-6)) return b;
-    const double sx = (P.Mi[0] * x + P.Mi[1] * y + P.Mi[2]) / w, sy = (P.Mi[3] * x + P.Mi[4] * y + P.Mi[5]) / w;
-    b.qx[c] = sx; b.qy[c] = sy;
-    lox = dmin(lox, sx); hix = dmax(hix, sx); loy = dmin(loy, sy); hiy = dmax(hiy, sy);
-  }
-  if (!(hix - lox < 1e5 && hiy - loy < 1e5 && lox > -1e6 && loy > -1e6)) return b;
-  b.x0 = (int)floor(lox) - 1; b.y0 = (int)floor(loy) - 1; b.x1 = (int)ceil(hix) + 2; b.y1 = (int)ceil(hiy) + 2;
-  // every sample of the warp stage (whatever border / resize stages follow it) lies inside the image of warp space, a convex
-  // quadrilateral
-  b.quad = 1;
-  return b;
-}
-
-// x extent of the quadrilateral over the rows [ya, yb]: false when it does not reach the band
-__device__ __forceinline__ bool quad_span(const SrcBox& b, double ya, double yb, double* xlo, double* xhi) {
-  double lo = 1e30, hi = -1e30;
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const double x0 = b.qx[e], y0 = b.qy[e], x1 = b.qx[(e + 1) & 3], y1 = b.qy[(e + 1) & 3];
-    if (y0 >= ya && y0 <= yb) { lo = dmin(lo, x0); hi = dmax(hi, x0); }
-    if ((y0 - ya) * (y1 - ya) < 0.0) { const double x = x0 + (ya - y0) / (y1 - y0) * (x1 - x0); lo = dmin(lo, x); hi = dmax(hi, x); }
-    if ((y0 - yb) * (y1 - yb) < 0.0) { const double x = x0 + (yb - y0) / (y1 - y0) * (x1 - x0); lo = dmin(lo, x); hi = dmax(hi, x); }
-  }
-  *xlo = lo; *xhi = hi;
-  return hi >= lo;
-}
-
-// signed distance-like test: is (x, y) inside the convex quadrilateral, at least `d` pixels from every edge?
-__device__ __forceinline__ bool quad_contains(const SrcBox& b, double x, double y, double d) {
-  int pos = 0, neg = 0;
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const double x0 = b.qx[e], y0 = b.qy[e], ex = b.qx[(e + 1) & 3] - x0, ey = b.qy[(e + 1) & 3] - y0;
-    const double len = sqrt(ex * ex + ey * ey);
-    if (!(len > 1e-9)) return false;
-    const double dist = (ex * (y - y0) - ey * (x - x0)) / len;     // > 0 on one side of the edge for every edge of a convex polygon
-    if (dist >= d) ++pos; else if (dist <= -d) ++neg; else return false;
-  }
-  return pos == 4 || neg == 4;
-}
-
 constexpr int kFillRows = 16;      // frame rows per work item of roi_fill_kernel
 
 __global__ void __launch_bounds__(256) roi_fill_kernel(const uint8_t* __restrict__ host_frames, uint8_t* __restrict__ dev_frames,
@@ -756,15 +705,11 @@ __global__ void __launch_bounds__(256) roi_fill_kernel(const uint8_t* __restrict
     __syncthreads();
     if (threadIdx.x == 0) {
       const I2TParams& P = params[slot];
-      SrcBox b = warp_src_box(P);
-      if (b.x1 >= b.x0) {
-        // a small margin (the eye ROIs lie well inside the face ROI; an eye that does not keeps reading the host frame), clipped
-        // to the frame.  A 12 % margin cost more PCIe time than it saved: the face rectangles of 1080p frames are large.
-        const int m = (max(b.x1 - b.x0, b.y1 - b.y0) * fill_margin_pct) / 100 + 2;
-        b.x0 = max(b.x0 - m, 0); b.y0 = max(b.y0 - m, 0); b.x1 = min(b.x1 + m, P.src_w - 1); b.y1 = min(b.y1 + m, P.src_h - 1);
-        s_margin = m;
-        if (!quad_trim) b.quad = 0;
-      }
+      int m = 0;
+      // a small margin (the eye ROIs lie well inside the face ROI; an eye that does not keeps reading the host frame), clipped
+      // to the frame.  A 12 % margin cost more PCIe time than it saved: the face rectangles of 1080p frames are large.
+      SrcBox b = roi_stage_box(P, fill_margin_pct, quad_trim != 0, &m);
+      s_margin = m;
       s_box = b; s_frame = P.frame;
       if (ch == 0) boxes[slot] = b;
     }
@@ -774,15 +719,8 @@ __global__ void __launch_bounds__(256) roi_fill_kernel(const uint8_t* __restrict
     const int r0 = max(b.y0, ch * kFillRows), r1 = min(b.y1, ch * kFillRows + kFillRows - 1);
     if (r1 < r0) continue;
     for (int r = r0 + warp; r <= r1; r += 8) {
-      int x0 = b.x0, x1 = b.x1;
-      if (b.quad) {
-        // only the part of the row the rotated ROI reaches: taps of samples with |sy - r| <= 1 (+ the fixed-point rounding of the
-        // warp coordinates and the margin), widened by the same -1 / +2 tap slack as the rectangle
-        double lo, hi;
-        if (!quad_span(b, (double)r - 1.25 - s_margin, (double)r + 1.25 + s_margin, &lo, &hi)) continue;
-        x0 = max((int)floor(lo) - 1 - s_margin, b.x0); x1 = min((int)ceil(hi) + 2 + s_margin, b.x1);
-        if (x1 < x0) continue;
-      }
+      int x0, x1;
+      if (!roi_row_span(b, r, s_margin, &x0, &x1)) continue;     // only the part of the row the rotated ROI reaches
       const int sb = (3 * x0) & ~15;
       int eb = (3 * (x1 + 1) + 15) & ~15;
       if (eb > (int)row_stride) eb = (int)row_stride;
@@ -808,16 +746,8 @@ __global__ void eye_split_kernel(const I2TParams* __restrict__ eye_params, const
   if (i >= n) return;
   I2TParams P = eye_params[i];
   const SrcBox e = warp_src_box(P), f = face_boxes[i >> 1];
-  bool inside = P.valid != 1;                   // invalid slots just get their zero tensor from the device launch
-  if (!inside && e.x1 >= e.x0 && f.x1 >= f.x0) {
-    inside = max(e.x0, 0) >= f.x0 && max(e.y0, 0) >= f.y0 && min(e.x1, P.src_w - 1) <= f.x1 && min(e.y1, P.src_h - 1) <= f.y1;
-    // the face rectangle was trimmed to the rotated ROI: every sample of the eye warp must lie inside that quadrilateral (then its
-    // taps are taps the face warp's own samples could have, which is what the per-row spans cover)
-    if (inside && f.quad) {
-      inside = e.quad != 0;
-      for (int c = 0; c < 4 && inside; ++c) inside = quad_contains(f, e.qx[c], e.qy[c], 0.25);
-    }
-  }
+  const bool inside = P.valid != 1 ||           // invalid slots just get their zero tensor from the device launch
+                      roi_stage_covers(f, e, P.src_w, P.src_h);
   I2TParams Q = P;
   Q.valid = 2;
   p_dev[i] = inside ? P : Q;

@@ -30,9 +30,6 @@ cudaError_t launch_i2t_setup(const fdl_rect* rois, const int* slot_frame, const 
 // compact / row_pos / compact_fstride (optional, rows_mode only): a device-resident copy of just the source rows the
 // letterbox touches ([frame][compact row][row bytes], gathered by the copy engine); row_pos[src row] = compact row or -1.
 // Source rectangle of a warp in frame pixels (inclusive; x1 < x0: empty).
-// Source region of a warp in frame pixels: the bounding rectangle of its taps and, when `quad` is set, the convex quadrilateral
-// (corners of warp space through the inverse matrix, in polygon order) the samples themselves lie in.
-struct SrcBox { int x0, y0, x1, y1; int quad, _pad; double qx[4], qy[4]; };
 // Zero-copy host frames: copy the (margin-grown) source rectangle of every face warp from the pinned host frames into the device
 // frame buffer at the same offsets, and split the eye slots between the device copy and the host frames (see prepost_kernels.cu).
 cudaError_t launch_roi_fill(const uint8_t* host_frames, uint8_t* dev_frames, long long frame_stride, long long row_stride, const I2TParams* params,

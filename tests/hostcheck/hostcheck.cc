@@ -112,4 +112,49 @@ void hc_iris_metrics_f32(const float* iris15, int w, int h, double focal, double
   out2[1] = iris_depth(iris15, focal, out2[0], w, h);
 }
 
+
+// Zero-copy ROI staging (roi_fill_kernel / eye_split_kernel): every tap warp_px can read inside the frame for the face warp (and
+// for an eye warp that roi_stage_covers() admits) must lie in a staged row span.  Returns the number of taps that do not (0 is
+// the only acceptable answer), -1 if the face parameters are invalid, -2 if the eye is not admitted (nothing to check).
+// stats[0] = staged bytes with row trimming, stats[1] = bytes of the untrimmed rectangle.
+static long long uncovered_taps(const I2TParams& P, const SrcBox& b, int m) {
+  long long bad = 0;
+  for (int y = 0; y < P.warp_h; ++y)
+    for (int x = 0; x < P.warp_w; ++x) {
+      int sx, sy, ax, ay;
+      warp_coords(P, x, y, &sx, &sy, &ax, &ay);
+      for (int t = 0; t < 4; ++t) {
+        const int tx = sx + (t & 1), ty = sy + (t >> 1);
+        if (tx < 0 || tx >= P.src_w || ty < 0 || ty >= P.src_h) continue;      // border taps read nothing
+        int x0, x1;
+        if (!roi_row_span(b, ty, m, &x0, &x1) || tx < x0 || tx > x1) ++bad;
+      }
+    }
+  return bad;
+}
+long long hc_roi_stage_check(const fdl_rect* face, const fdl_rect* eye_or_null, int w, int h, int face_size, int eye_size, int trim,
+                             long long* stats) {
+  I2TParams F;
+  i2t_setup(face, w, h, face_size, face_size, false, 0.0, 1.0, false, 0, &F);
+  if (F.valid != 1) return -1;
+  int m = 0;
+  const SrcBox b = roi_stage_box(F, 0, trim != 0, &m);
+  if (b.x1 < b.x0) return -1;
+  if (stats) {
+    stats[0] = stats[1] = 0;
+    for (int r = b.y0; r <= b.y1; ++r) {
+      int x0, x1;
+      stats[1] += (imin((3 * (b.x1 + 1) + 15) & ~15, 3 * w) - ((3 * b.x0) & ~15));
+      if (roi_row_span(b, r, m, &x0, &x1)) stats[0] += (imin((3 * (x1 + 1) + 15) & ~15, 3 * w) - ((3 * x0) & ~15));
+    }
+  }
+  if (!eye_or_null) return uncovered_taps(F, b, m);
+  I2TParams E;
+  i2t_setup(eye_or_null, w, h, eye_size, eye_size, true, 0.0, 1.0, false, 0, &E);
+  if (E.valid != 1) return -2;
+  const SrcBox e = warp_src_box(E);
+  if (!roi_stage_covers(b, e, w, h)) return -2;
+  return uncovered_taps(E, b, m);
+}
+
 }

@@ -358,3 +358,53 @@ def test_sparse_model_densify_and_plan(fdl):
     bad = T.Tensor(t.index, t.name, t.shape, t.dtype, t.buffer, t.data, dict(t.sparsity, traversal_order=[3, 2, 1, 0]))
     with pytest.raises(NotImplementedError):
         T.densify(bad)
+
+
+def test_roi_staging_spans_cover_every_tap(hc):
+    """Zero-copy host frames: roi_fill_kernel stages, per frame row, only the span of the rotated face ROI; an eye warp runs on
+    the staged copy when roi_stage_covers() admits it.  Walk every destination pixel of the face warp (and of admitted eye warps)
+    through the kernels' own warp_coords() and require all four taps inside the frame to be staged (csrc/glue_math.h)."""
+    import ctypes as C
+    from rs_face_detection_tflite_b200._lib import CRect as fdl_rect
+    hc.hc_roi_stage_check.restype = C.c_longlong
+    hc.hc_roi_stage_check.argtypes = [C.POINTER(fdl_rect), C.POINTER(fdl_rect), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_longlong)]
+    W, H = 1920, 1080
+    rng = np.random.default_rng(11)
+
+    def rect(xc, yc, w_px, h_px, rot):
+        r = fdl_rect()
+        r.x_center, r.y_center, r.width, r.height, r.rotation, r.normalized = xc / W, yc / H, w_px / W, h_px / H, rot, 1
+        return r
+
+    stats = (C.c_longlong * 2)()
+    faces = eyes_checked = 0
+    saved = []
+    for i in range(40):
+        side = float(rng.uniform(60, 900))
+        rot = float(rng.uniform(-np.pi, np.pi)) if i % 4 == 0 else float(np.radians(rng.uniform(-35, 35)))
+        if i % 10 == 9:
+            rot = 0.0
+        xc, yc = float(rng.uniform(-50, W + 50)), float(rng.uniform(-50, H + 50))      # ROIs hanging over the frame edges too
+        face = rect(xc, yc, side, side, rot)
+        for trim in (1, 0):
+            bad = hc.hc_roi_stage_check(C.byref(face), None, W, H, 192, 64, trim, stats)
+            if bad == -1:
+                continue
+            assert bad == 0, (i, trim, bad)
+            if trim:
+                faces += 1
+                assert stats[0] <= stats[1]
+                saved.append(stats[0] / max(stats[1], 1))
+        # eye ROIs the way the pipeline makes them: squares of ~0.3 x the face side near the upper half of the face ROI, same
+        # rotation +- a few degrees; some are pushed outside on purpose (those must be rejected or still be covered)
+        c, s_ = np.cos(rot), np.sin(rot)
+        for k in range(6):
+            dx, dy = float(rng.uniform(-0.55, 0.55)) * side, float(rng.uniform(-0.55, 0.2)) * side
+            es = float(rng.uniform(0.15, 0.4)) * side
+            eye = rect(xc + dx * c - dy * s_, yc + dx * s_ + dy * c, es, es, rot + float(np.radians(rng.uniform(-8, 8))))
+            bad = hc.hc_roi_stage_check(C.byref(face), C.byref(eye), W, H, 192, 64, 1, None)
+            assert bad in (-1, -2, 0), (i, k, bad)
+            eyes_checked += bad == 0
+    assert faces >= 30 and eyes_checked >= 60
+    assert np.mean(saved) < 0.9        # the trimming does save bytes on rotated ROIs
