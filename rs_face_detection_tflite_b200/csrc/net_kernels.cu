@@ -22,7 +22,6 @@ unsigned long long launch_count_value() { return g_launches.load(std::memory_ord
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kBN = 64;
 
 __device__ __forceinline__ float apply_act(float v, int act, const float* alpha, int n) {
   if (act == ACT_RELU) return fmaxf(v, 0.f);
