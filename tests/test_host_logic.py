@@ -408,3 +408,34 @@ def test_roi_staging_spans_cover_every_tap(hc):
             eyes_checked += bad == 0
     assert faces >= 30 and eyes_checked >= 60
     assert np.mean(saved) < 0.9        # the trimming does save bytes on rotated ROIs
+
+
+def test_bench_h2d_accounting_matches_the_staging_kernel(hc):
+    """bench.py counts the host bytes of the zero-copy ROI staging from the face ROIs (roi_rect_bytes); the count must not be
+    below what roi_fill_kernel's own span function copies, and not more than a few percent above it."""
+    import ctypes as C
+    import bench
+    from rs_face_detection_tflite_b200._lib import CRect
+    hc.hc_roi_stage_check.restype = C.c_longlong
+    hc.hc_roi_stage_check.argtypes = [C.POINTER(CRect), C.POINTER(CRect), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+    W, H = 1920, 1080
+    rng = np.random.default_rng(3)
+    stats = (C.c_longlong * 2)()
+
+    class Roi:
+        pass
+
+    for _ in range(12):
+        side, rot = float(rng.uniform(150, 800)), float(np.radians(rng.uniform(-35, 35)))
+        xc, yc = float(rng.uniform(100, 1800)), float(rng.uniform(100, 1000))
+        r = CRect(xc / W, yc / H, side / W, side / H, rot, 1, 0)
+        assert hc.hc_roi_stage_check(C.byref(r), None, W, H, 192, 64, 1, stats) == 0
+        q = Roi()
+        q.x_center, q.y_center, q.width, q.height, q.rotation = xc / W, yc / H, side / W, side / H, rot
+        for trim, kernel_bytes in ((True, stats[0]), (False, stats[1])):
+            counted = bench.roi_rect_bytes(q, trim=trim)
+            assert kernel_bytes <= counted <= 1.05 * kernel_bytes + 4096, (trim, kernel_bytes, counted)
+    # rows already on the device (the letterbox gather) are not counted
+    rows = frozenset(bench.letterbox_rows())
+    assert len(rows) == 288
+    assert bench.roi_rect_bytes(q, on_device=rows) < 0.8 * bench.roi_rect_bytes(q)
