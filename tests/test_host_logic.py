@@ -439,3 +439,60 @@ def test_bench_h2d_accounting_matches_the_staging_kernel(hc):
     rows = frozenset(bench.letterbox_rows())
     assert len(rows) == 288
     assert bench.roi_rect_bytes(q, on_device=rows) < 0.8 * bench.roi_rect_bytes(q)
+
+
+# ---- the host mirrors above the C ABI (rust_shim/, include/fdl.hpp) stay in step with include/fdl.h ------------------------
+def _c_prototypes():
+    """name -> number of parameters, for every FDL_API function of include/fdl.h."""
+    import re
+    text = open(os.path.join(ROOT, "include", "fdl.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"FDL_API\s+[^;(]*?\b(fdl_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return protos
+
+
+def _c_struct_fields(name):
+    import re
+    text = open(os.path.join(ROOT, "include", "fdl.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    body = re.search(r"typedef struct %s\s*\{(.*?)\}\s*%s\s*;" % (name, name), text, flags=re.S).group(1)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = re.sub(r"^(const\s+)?\w+[\s\*]+", "", decl)          # drop the type
+        fields += [re.sub(r"\[.*?\]", "", n).strip(" *") for n in names.split(",")]
+    return fields
+
+
+def test_rust_shim_ffi_matches_the_c_header():
+    """rust_shim/ cannot be compiled here (no cargo): at least its extern block and #[repr(C)] structs must name the functions /
+    fields of include/fdl.h, in order and with the same arity."""
+    import re
+    src = open(os.path.join(ROOT, "rust_shim", "src", "face_detection_lite", "ffi.rs")).read()
+    protos = _c_prototypes()
+    assert len(protos) >= 40
+    fns = re.findall(r"pub fn (fdl_\w+)\s*\((.*?)\)\s*(?:->\s*[^;]+)?;", src, flags=re.S)
+    assert len(fns) >= 15
+    for name, args in fns:
+        assert name in protos, name + " is not declared in include/fdl.h"
+        n = 0 if not args.strip() else len([a for a in args.split(",") if a.strip()])
+        assert n == protos[name], (name, n, protos[name])
+    for name, body in re.findall(r"pub struct (fdl_\w+)\s*\{(.*?)\}", src, flags=re.S):
+        if not body.strip() or "_private" in body or "_opaque" in body:
+            continue                                                 # opaque handle types
+        rust_fields = [f.split(":")[0].replace("pub", "").strip() for f in body.split(",") if ":" in f]
+        rust_fields = [f for f in rust_fields if f]
+        assert rust_fields == _c_struct_fields(name), (name, rust_fields, _c_struct_fields(name))
+
+
+def test_cpp_mirror_header_compiles(tmp_path):
+    """include/fdl.hpp (the C++ mirror of the reference's API) is header-only: it must at least compile against include/fdl.h."""
+    import subprocess
+    tu = tmp_path / "tu.cc"
+    tu.write_text('#include "fdl.hpp"\nint main() { return 0; }\n')
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), str(tu)])
