@@ -1,0 +1,55 @@
+"""Frame ingest oracle: oracle/jpeg_decode.py against cv2.imdecode + BGR2RGB, i.e. against the very calls
+`convert_image_to_mat` makes (reference src/face_detection_lite/utils.rs:8-21).  Bit-exact is the bar (u8 output)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ref(buf: bytes) -> np.ndarray:
+    return cv2.cvtColor(cv2.imdecode(np.frombuffer(buf, np.uint8), cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+
+
+def test_reference_test_images_decode_bit_exact():
+    from oracle import jpeg_decode
+    files = sorted(glob.glob(os.path.join(ROOT, "test_data", "*.jpg")))
+    assert len(files) >= 3                       # man.jpg, russ_cox_1.jpg (restart interval 25), russ_cox_2.jpg (225 rows: partial MCU row)
+    for f in files:
+        buf = open(f, "rb").read()
+        np.testing.assert_array_equal(jpeg_decode.convert_image_to_mat(buf), _ref(buf), err_msg=f)
+
+
+@pytest.mark.parametrize("sampling", ["444", "422", "420"])
+def test_sampling_sizes_qualities_restarts(sampling):
+    from oracle import jpeg_decode
+    fac = getattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR_" + sampling)
+    img = cv2.imread(os.path.join(ROOT, "test_data", "man.jpg"))
+    rng = np.random.default_rng(int(sampling))
+    for (h, w) in ((360, 540), (97, 131), (8, 8), (1, 1), (17, 33), (250, 3), (16, 16), (15, 17)):
+        src = img[:h, :w] if h > 16 else rng.integers(0, 256, (h, w, 3), dtype=np.uint8)     # photo crops and pure noise
+        for q in (35, 90, 100):
+            for rst in (0, 3):
+                ok, enc = cv2.imencode(".jpg", src, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, fac,
+                                                    cv2.IMWRITE_JPEG_RST_INTERVAL, rst])
+                assert ok
+                buf = enc.tobytes()
+                np.testing.assert_array_equal(jpeg_decode.decode_jpeg_rgb(buf), _ref(buf), err_msg="%s %dx%d q%d rst%d" % (sampling, w, h, q, rst))
+
+
+def test_greyscale_optimised_tables_and_rejections():
+    from oracle import jpeg_decode
+    img = cv2.imread(os.path.join(ROOT, "test_data", "russ_cox_1.jpg"))
+    ok, enc = cv2.imencode(".jpg", cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), [cv2.IMWRITE_JPEG_QUALITY, 80])
+    np.testing.assert_array_equal(jpeg_decode.decode_jpeg_rgb(enc.tobytes()), _ref(enc.tobytes()))
+    noise = np.random.default_rng(5).integers(0, 256, (123, 77, 3), dtype=np.uint8)
+    ok, enc = cv2.imencode(".jpg", noise, [cv2.IMWRITE_JPEG_QUALITY, 100, cv2.IMWRITE_JPEG_OPTIMIZE, 1])      # per-image Huffman tables
+    np.testing.assert_array_equal(jpeg_decode.decode_jpeg_rgb(enc.tobytes()), _ref(enc.tobytes()))
+    ok, enc = cv2.imencode(".jpg", noise, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    with pytest.raises(ValueError):
+        jpeg_decode.decode_jpeg_rgb(enc.tobytes())
+    with pytest.raises(ValueError):
+        jpeg_decode.decode_jpeg_rgb(b"\x89PNG\r\n")
