@@ -2,6 +2,7 @@
 reader + planner agree with the oracle's independent reader, the glue arithmetic compiled for the host matches
 the oracle, calls that need a device fail loudly, and the rank-sharding used by bench.py works under gloo."""
 import ctypes as C
+import json
 import os
 import re
 import subprocess
@@ -496,3 +497,22 @@ def test_cpp_mirror_header_compiles(tmp_path):
     tu = tmp_path / "tu.cc"
     tu.write_text('#include "fdl.hpp"\nint main() { return 0; }\n')
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), str(tu)])
+
+
+def test_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours): one JSON line on stdout -- library chatter goes to
+    stderr -- with the contract's keys, the metric / unit of our own arm and a zero-copy-free e2e block."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-frames", "2"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    import bench
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["vs_baseline"] is None and d["gpu_launches"] == 0 and "workload" in d["config"]
