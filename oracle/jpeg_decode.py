@@ -12,7 +12,8 @@ ITU-T T.81 with libjpeg's default decompression choices, which is what `imdecode
   * dequantisation + the accurate integer inverse DCT `jpeg_idct_islow` (jidctint.c: CONST_BITS 13, PASS1_BITS 2, the Loeffler /
     Ligtenberg / Moschytz factorisation), range-limited around +128
   * "fancy" triangle-filter chroma upsampling for 2h2v / 2h1v components (jdsample.c: 3/4-1/4 weights in both directions, the
-    alternating +8 / +7 rounding, edge replication at the image -- not the padded block -- borders)
+    alternating +8 / +7 rounding, edge replication at the image -- not the padded block -- borders; plain replication when the
+    downsampled component is at most 2 samples wide, as jinit_upsampler chooses)
   * YCbCr -> RGB with the 16-bit fixed-point tables of jdcolor.c
 
 Pinned: bit-exact against `cv2.imdecode` + `cv2.cvtColor(BGR2RGB)` (OpenCV 4.13.0 in this container) on every JPEG under
@@ -132,6 +133,8 @@ def _idct_islow(coef: np.ndarray) -> np.ndarray:
 def _upsample_h2v2(c: np.ndarray) -> np.ndarray:
     """h2v2_fancy_upsample: c [h, w] uint8 (the REAL downsampled size) -> [2h, 2w]."""
     h, w = c.shape
+    if w <= 2:                                                     # jinit_upsampler: fancy only when downsampled_width > 2
+        return np.repeat(np.repeat(c, 2, axis=0), 2, axis=1)
     ci = c.astype(np.int64)
     above = np.vstack([ci[:1], ci[:-1]])                           # edge rows replicate
     below = np.vstack([ci[1:], ci[-1:]])
@@ -156,6 +159,8 @@ def _upsample_h2v2(c: np.ndarray) -> np.ndarray:
 def _upsample_h2v1(c: np.ndarray) -> np.ndarray:
     """h2v1_fancy_upsample: [h, w] -> [h, 2w]."""
     h, w = c.shape
+    if w <= 2:                                                     # jinit_upsampler: fancy only when downsampled_width > 2
+        return np.repeat(c, 2, axis=1)
     s = c.astype(np.int64)
     last = np.hstack([s[:, :1], s[:, :-1]])
     nxt = np.hstack([s[:, 1:], s[:, -1:]])
@@ -205,9 +210,10 @@ def _exif_orientation(tiff: bytes) -> int:
     return 0
 
 
-def decode_jpeg_rgb(data: bytes) -> np.ndarray:
-    """Baseline JPEG bytes -> uint8 [H, W, 3] in RGB order: what `convert_image_to_mat` returns (utils.rs:8-21).  Raises
-    ValueError for anything but 8-bit baseline Huffman files with 1 or 3 components and EXIF orientation 1 / none."""
+def entropy_decode(data: bytes) -> dict:
+    """Markers + Huffman stage: {"H", "W", "hmax", "vmax", "comps": [{"h", "v", "coef": int64 [blocks_y, blocks_x, 64] in natural
+    (row-major) order, quantised, "quant": int64 [64] natural order}, ...]}.  Raises ValueError for anything but 8-bit baseline
+    Huffman files with 1 or 3 components and EXIF orientation 1 / none."""
     if data[:2] != b"\xff\xd8":
         raise ValueError("not a JPEG")
     qt, ht = {}, {}
@@ -324,11 +330,18 @@ def decode_jpeg_rgb(data: bytes) -> np.ndarray:
                             blk[ZIGZAG[k]] = _extend(br.get(s), s)
                             k += 1
 
+    return dict(H=H, W=W, hmax=hmax, vmax=vmax, comps=[dict(h=c["h"], v=c["v"], coef=c["coef"], quant=qt[c["tq"]]) for c in comps])
+
+
+def decode_jpeg_rgb(data: bytes) -> np.ndarray:
+    """Baseline JPEG bytes -> uint8 [H, W, 3] in RGB order: what `convert_image_to_mat` returns (utils.rs:8-21)."""
+    f = entropy_decode(data)
+    H, W, hmax, vmax, comps = f["H"], f["W"], f["hmax"], f["vmax"], f["comps"]
     # ---- dequantise, inverse DCT, assemble the component planes (padded to whole blocks) ----
     planes = []
     for c in comps:
         by, bx, _ = c["coef"].shape
-        deq = (c["coef"] * qt[c["tq"]]).reshape(by * bx, 8, 8)
+        deq = (c["coef"] * c["quant"]).reshape(by * bx, 8, 8)
         px = _idct_islow(deq).reshape(by, bx, 8, 8).transpose(0, 2, 1, 3).reshape(by * 8, bx * 8)
         # the REAL downsampled size (jdmaster.c: ceil(image * samp / max_samp)): upsampling replicates ITS edges, not the padding's
         ch, cw = -(-H * c["v"] // vmax), -(-W * c["h"] // hmax)

@@ -9,7 +9,8 @@ SO = os.path.join(HERE, "_hostcheck.so")
 
 def load():
     src = os.path.join(HERE, "hostcheck.cc")
-    hdr = os.path.join(HERE, "..", "..", "rs_face_detection_tflite_b200", "csrc", "glue_math.h")
-    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    csrc = os.path.join(HERE, "..", "..", "rs_face_detection_tflite_b200", "csrc")
+    newest = max(os.path.getmtime(f) for f in (src, os.path.join(csrc, "glue_math.h"), os.path.join(csrc, "jpeg_math.h")))
+    if not os.path.exists(SO) or os.path.getmtime(SO) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", SO, src])
     return C.CDLL(SO)

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "../../rs_face_detection_tflite_b200/csrc/glue_math.h"
+#include "../../rs_face_detection_tflite_b200/csrc/jpeg_math.h"
 
 using namespace fdl;
 
@@ -155,6 +156,43 @@ long long hc_roi_stage_check(const fdl_rect* face, const fdl_rect* eye_or_null, 
   const SrcBox e = warp_src_box(E);
   if (!roi_stage_covers(b, e, w, h)) return -2;
   return uncovered_taps(E, b, m);
+}
+
+
+// JPEG back half (csrc/jpeg_math.h) on the host: quantised coefficient blocks of up to three components (natural order,
+// [blocks_y][blocks_x][64] per component) -> RGB, through the same per-block / per-pixel functions a device decoder will call.
+// samp[c] = (h, v) sampling factors; only 1x1, 2x1 and 2x2 chroma against full-resolution luma.
+int hc_jpeg_backend(int ncomp, const int16_t* const* coef, const uint16_t* const* quant, const int* samp_hv, int W, int H, uint8_t* rgb) {
+  int hmax = 1, vmax = 1;
+  for (int c = 0; c < ncomp; ++c) { hmax = imax(hmax, samp_hv[2 * c]); vmax = imax(vmax, samp_hv[2 * c + 1]); }
+  const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+  std::vector<std::vector<uint8_t>> planes((size_t)ncomp);
+  std::vector<int> pstride((size_t)ncomp), cw((size_t)ncomp), chh((size_t)ncomp), eh((size_t)ncomp), ev((size_t)ncomp);
+  for (int c = 0; c < ncomp; ++c) {
+    const int h = samp_hv[2 * c], v = samp_hv[2 * c + 1];
+    const int bx = mcux * h, by = mcuy * v;
+    pstride[c] = bx * 8;
+    planes[c].assign((size_t)bx * 8 * by * 8, 0);
+    for (int j = 0; j < by; ++j)
+      for (int i = 0; i < bx; ++i)
+        jpeg_idct_islow_8x8(coef[c] + ((size_t)j * bx + i) * 64, quant[c], planes[c].data() + (size_t)j * 8 * pstride[c] + i * 8, pstride[c]);
+    cw[c] = (W * h + hmax - 1) / hmax; chh[c] = (H * v + vmax - 1) / vmax;
+    eh[c] = hmax / h; ev[c] = vmax / v;
+    if (!((eh[c] == 1 && ev[c] == 1) || (eh[c] == 2 && ev[c] == 1) || (eh[c] == 2 && ev[c] == 2))) return -1;
+  }
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      int s[3] = {0, 128, 128};
+      for (int c = 0; c < ncomp; ++c) {
+        if (eh[c] == 1) s[c] = planes[c][(size_t)y * pstride[c] + x];
+        else if (ev[c] == 1) s[c] = jpeg_h2v1_fancy_at(planes[c].data(), pstride[c], cw[c], x, y);
+        else s[c] = jpeg_h2v2_fancy_at(planes[c].data(), pstride[c], cw[c], chh[c], x, y);
+      }
+      uint8_t* o = rgb + ((size_t)y * W + x) * 3;
+      if (ncomp == 1) { o[0] = o[1] = o[2] = (uint8_t)s[0]; }
+      else jpeg_ycc_to_rgb(s[0], s[1], s[2], o);
+    }
+  return 0;
 }
 
 }

@@ -29,8 +29,8 @@ def test_sampling_sizes_qualities_restarts(sampling):
     fac = getattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR_" + sampling)
     img = cv2.imread(os.path.join(ROOT, "test_data", "man.jpg"))
     rng = np.random.default_rng(int(sampling))
-    for (h, w) in ((360, 540), (97, 131), (8, 8), (1, 1), (17, 33), (250, 3), (16, 16), (15, 17)):
-        src = img[:h, :w] if h > 16 else rng.integers(0, 256, (h, w, 3), dtype=np.uint8)     # photo crops and pure noise
+    for (h, w) in ((360, 540), (97, 131), (8, 8), (1, 1), (17, 33), (250, 3), (3, 250), (16, 16), (15, 17), (9, 4), (9, 5), (2, 2)):
+        src = img[:h, :w] if h > 16 and w > 16 else rng.integers(0, 256, (h, w, 3), dtype=np.uint8)     # photo crops and pure noise
         for q in (35, 90, 100):
             for rst in (0, 3):
                 ok, enc = cv2.imencode(".jpg", src, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, fac,
@@ -53,3 +53,45 @@ def test_greyscale_optimised_tables_and_rejections():
         jpeg_decode.decode_jpeg_rgb(enc.tobytes())
     with pytest.raises(ValueError):
         jpeg_decode.decode_jpeg_rgb(b"\x89PNG\r\n")
+
+
+def _host_backend(buf: bytes) -> np.ndarray:
+    """csrc/jpeg_math.h on the host (tests/hostcheck): the oracle's entropy stage feeds quantised blocks to the per-block /
+    per-pixel functions a device decoder will call."""
+    import ctypes as C
+    import hostcheck
+    from oracle import jpeg_decode
+    hc = hostcheck.load()
+    f = jpeg_decode.entropy_decode(buf)
+    n = len(f["comps"])
+    coefs = [np.ascontiguousarray(c["coef"], np.int16) for c in f["comps"]]
+    quants = [np.ascontiguousarray(c["quant"], np.uint16) for c in f["comps"]]
+    for c, a in zip(f["comps"], coefs):
+        assert (a == c["coef"]).all()                      # baseline coefficients fit 16 bits
+    cp = (C.c_void_p * n)(*[a.ctypes.data for a in coefs])
+    qp = (C.c_void_p * n)(*[a.ctypes.data for a in quants])
+    samp = (C.c_int * (2 * n))(*[v for c in f["comps"] for v in (c["h"], c["v"])])
+    out = np.empty((f["H"], f["W"], 3), np.uint8)
+    hc.hc_jpeg_backend.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    assert hc.hc_jpeg_backend(n, cp, qp, samp, f["W"], f["H"], out.ctypes.data) == 0
+    return out
+
+
+def test_device_back_half_header_is_bit_exact_on_the_host():
+    """jpeg_math.h (inverse DCT, gather-form fancy upsampling, colour conversion) == cv2.imdecode on the reference's images and
+    on re-encoded variants of every supported sampling, including 1-pixel-wide / 1-pixel-high chroma planes."""
+    files = sorted(glob.glob(os.path.join(ROOT, "test_data", "*.jpg")))
+    for f in files:
+        buf = open(f, "rb").read()
+        np.testing.assert_array_equal(_host_backend(buf), _ref(buf), err_msg=f)
+    img = cv2.imread(os.path.join(ROOT, "test_data", "man.jpg"))
+    rng = np.random.default_rng(9)
+    for sampling in ("444", "422", "420"):
+        fac = getattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR_" + sampling)
+        for (h, w) in ((97, 131), (1, 1), (2, 2), (17, 33), (250, 3), (3, 250), (16, 16)):
+            src = img[:h, :w] if h > 16 and w > 16 else rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            for q in (50, 100):
+                ok, enc = cv2.imencode(".jpg", src, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, fac])
+                np.testing.assert_array_equal(_host_backend(enc.tobytes()), _ref(enc.tobytes()), err_msg="%s %dx%d q%d" % (sampling, w, h, q))
+    ok, enc = cv2.imencode(".jpg", cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), [cv2.IMWRITE_JPEG_QUALITY, 75])
+    np.testing.assert_array_equal(_host_backend(enc.tobytes()), _ref(enc.tobytes()))
