@@ -216,7 +216,7 @@ def entropy_decode(data: bytes) -> dict:
     Huffman files with 1 or 3 components and EXIF orientation 1 / none."""
     if data[:2] != b"\xff\xd8":
         raise ValueError("not a JPEG")
-    qt, ht = {}, {}
+    qt, ht, raw_ht = {}, {}, {}
     frame = None
     restart_interval = 0
     p = 2
@@ -257,6 +257,7 @@ def entropy_decode(data: bytes) -> dict:
                 counts = list(seg[q + 1:q + 17])
                 nsym = sum(counts)
                 ht[(tc, th)] = _huff_table(counts, list(seg[q + 17:q + 17 + nsym]))
+                raw_ht[(tc, th)] = (bytes(counts), bytes(seg[q + 17:q + 17 + nsym]))
                 q += 17 + nsym
         elif m == 0xDD:
             restart_interval = (seg[0] << 8) | seg[1]
@@ -278,6 +279,8 @@ def entropy_decode(data: bytes) -> dict:
         if c["id"] != cid:
             raise ValueError("scan component order")
         c["dc"], c["ac"] = ht[(0, td)], ht[(1, ta)]
+        c["raw_dc"], c["raw_ac"] = raw_ht[(0, td)], raw_ht[(1, ta)]
+    scan_offset = p
     H, W = frame["H"], frame["W"]
     hmax, vmax = max(c["h"] for c in comps), max(c["v"] for c in comps)
     mcux, mcuy = -(-W // (8 * hmax)), -(-H // (8 * vmax))
@@ -330,7 +333,8 @@ def entropy_decode(data: bytes) -> dict:
                             blk[ZIGZAG[k]] = _extend(br.get(s), s)
                             k += 1
 
-    return dict(H=H, W=W, hmax=hmax, vmax=vmax, comps=[dict(h=c["h"], v=c["v"], coef=c["coef"], quant=qt[c["tq"]]) for c in comps])
+    return dict(H=H, W=W, hmax=hmax, vmax=vmax, restart_interval=restart_interval, scan_offset=scan_offset,
+                comps=[dict(h=c["h"], v=c["v"], coef=c["coef"], quant=qt[c["tq"]], dht_dc=c["raw_dc"], dht_ac=c["raw_ac"]) for c in comps])
 
 
 def decode_jpeg_rgb(data: bytes) -> np.ndarray:

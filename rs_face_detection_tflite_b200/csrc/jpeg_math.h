@@ -5,8 +5,9 @@
 // This is the back half of the frame-ingest row: the reference decodes frames with
 // imgcodecs::imdecode(IMREAD_COLOR) + cvt_color(BGR2RGB) (src/face_detection_lite/utils.rs:8-21), i.e. OpenCV's bundled libjpeg
 // with its default choices (JDCT_ISLOW, do_fancy_upsampling).  Bit-exact with cv2.imdecode: tests/test_oracle_jpeg.py drives these
-// functions on the host through tests/hostcheck.  NOT yet wired into libfdl_b200.so: no kernel calls it, there is no device
-// entropy decoder -- frames still enter the library decoded.
+// functions on the host through tests/hostcheck.  NOT yet wired into libfdl_b200.so: no kernel calls it -- frames still enter
+// the library decoded.  The entropy-stage building blocks at the end (table, bit reader, one-block decoder) are the sequential
+// core a device decoder runs per restart interval / subsequence; they are checked on the host the same way.
 #pragma once
 #include <cstdint>
 
@@ -97,6 +98,99 @@ FDL_JHD void jpeg_ycc_to_rgb(int y, int cb, int cr, uint8_t* rgb) {
   rgb[0] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
   rgb[1] = (uint8_t)(g < 0 ? 0 : (g > 255 ? 255 : g));
   rgb[2] = (uint8_t)(b < 0 ? 0 : (b > 255 ? 255 : b));
+}
+
+// ---- entropy stage building blocks (T.81 F.2.2; sequential within one restart interval / subsequence) ----------------------
+// Huffman table in the two-level form libjpeg's decoder uses: a 9-bit lookahead table answers the common short codes in one
+// probe, longer codes walk maxcode[] (T.81 F.2.2.3 / Annex C).  600 bytes per table: four of them fit shared memory many times over.
+struct JpegHuff {
+  uint16_t look[512];      // (length << 8) | symbol for codes of <= 9 bits (by their 9-bit prefix), 0 otherwise
+  int32_t maxcode[18];     // largest code of each length (-1: none); [17] = sentinel
+  int32_t valoffset[17];   // huffval index of the first code of each length minus that code
+  uint8_t huffval[256];
+};
+
+// counts[16] / symbols as in a DHT segment
+FDL_JHD void jpeg_huff_build(const uint8_t* counts, const uint8_t* symbols, JpegHuff* t) {
+  for (int i = 0; i < 512; ++i) t->look[i] = 0;
+  int code = 0, k = 0;
+  for (int l = 1; l <= 16; ++l) {
+    t->valoffset[l] = k - code;
+    for (int i = 0; i < counts[l - 1]; ++i, ++k, ++code) {
+      t->huffval[k] = symbols[k];
+      if (l <= 9) {
+        const int lo = code << (9 - l);
+        for (int j = 0; j < (1 << (9 - l)); ++j) t->look[lo + j] = (uint16_t)((l << 8) | symbols[k]);
+      }
+    }
+    t->maxcode[l] = counts[l - 1] ? code - 1 : -1;
+    code <<= 1;
+  }
+  t->maxcode[17] = 0x7FFFFFFF;
+  t->maxcode[0] = -1; t->valoffset[0] = 0;
+  for (int i = k; i < 256; ++i) t->huffval[i] = 0;
+}
+
+// MSB-first bit reader over entropy-coded bytes: 0xFF00 -> 0xFF, any other marker stops the stream (zero bits from there on).
+struct JpegBits {
+  const uint8_t* p; const uint8_t* end;
+  uint64_t acc; int n;
+};
+FDL_JHD void jpeg_bits_init(JpegBits* b, const uint8_t* p, const uint8_t* end) { b->p = p; b->end = end; b->acc = 0; b->n = 0; }
+FDL_JHD void jpeg_bits_fill(JpegBits* b) {
+  while (b->n <= 48) {
+    unsigned v = 0;
+    if (b->p < b->end) {
+      v = *b->p;
+      if (v == 0xFF) {
+        const unsigned nx = b->p + 1 < b->end ? b->p[1] : 0xD9u;
+        if (nx == 0) b->p += 2; else v = 0;          // a marker: feed zeros, stay on it
+      } else {
+        ++b->p;
+      }
+    }
+    b->acc = (b->acc << 8) | v;
+    b->n += 8;
+  }
+}
+FDL_JHD int jpeg_bits_peek(JpegBits* b, int k) { if (b->n < k) jpeg_bits_fill(b); return (int)((b->acc >> (b->n - k)) & ((1u << k) - 1)); }
+FDL_JHD int jpeg_bits_get(JpegBits* b, int k) { if (k == 0) return 0; const int v = jpeg_bits_peek(b, k); b->n -= k; return v; }
+// RSTn: drop the remaining bits and step over the marker (T.81 E.2.4)
+FDL_JHD void jpeg_bits_restart(JpegBits* b) {
+  b->acc = 0; b->n = 0;
+  while (b->p + 1 < b->end && !(b->p[0] == 0xFF && b->p[1] >= 0xD0 && b->p[1] <= 0xD7)) ++b->p;
+  b->p += 2;
+}
+
+FDL_JHD int jpeg_huff_decode(JpegBits* b, const JpegHuff& t) {
+  const int look = t.look[jpeg_bits_peek(b, 9)];
+  if (look) { b->n -= look >> 8; return look & 255; }
+  int code = jpeg_bits_get(b, 10), l = 10;
+  while (code > t.maxcode[l]) { code = (code << 1) | jpeg_bits_get(b, 1); ++l; }
+  if (l > 16) return 0;                               // corrupt data: libjpeg substitutes a zero symbol
+  return t.huffval[(code + t.valoffset[l]) & 255];
+}
+FDL_JHD int jpeg_extend(int v, int t) { return v < (1 << (t - 1)) ? v - (1 << t) + 1 : v; }
+
+// One 8x8 block: coef[64] in natural order, zeroed by the caller; *pred is the component's running DC predictor.
+FDL_JHD void jpeg_decode_block(JpegBits* b, const JpegHuff& dc, const JpegHuff& ac, int* pred, int16_t* coef) {
+  const uint8_t zz[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                          35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+  const int t = jpeg_huff_decode(b, dc);
+  if (t) *pred += jpeg_extend(jpeg_bits_get(b, t), t);
+  coef[0] = (int16_t)*pred;
+  for (int k = 1; k < 64;) {
+    const int rs = jpeg_huff_decode(b, ac), r = rs >> 4, s = rs & 15;
+    if (s == 0) {
+      if (r != 15) break;                             // EOB
+      k += 16;                                        // ZRL
+      continue;
+    }
+    k += r;
+    if (k > 63) break;
+    coef[zz[k]] = (int16_t)jpeg_extend(jpeg_bits_get(b, s), s);
+    ++k;
+  }
 }
 
 }  // namespace fdl

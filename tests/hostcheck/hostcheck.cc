@@ -195,4 +195,35 @@ int hc_jpeg_backend(int ncomp, const int16_t* const* coef, const uint16_t* const
   return 0;
 }
 
+
+// JPEG entropy stage through csrc/jpeg_math.h: one interleaved scan, sequential over the MCUs (restart intervals honoured).
+// dht[2*c] / dht[2*c+1] = (counts[16] + symbols) of component c's DC / AC table; coef[c] receives [blocks_y][blocks_x][64].
+int hc_jpeg_entropy(const uint8_t* data, long long len, long long scan_offset, int ncomp, const int* samp_hv, const uint8_t* const* dht,
+                    int restart_interval, int W, int H, int16_t* const* coef) {
+  int hmax = 1, vmax = 1;
+  for (int c = 0; c < ncomp; ++c) { hmax = imax(hmax, samp_hv[2 * c]); vmax = imax(vmax, samp_hv[2 * c + 1]); }
+  const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+  std::vector<JpegHuff> tabs((size_t)2 * ncomp);
+  for (int i = 0; i < 2 * ncomp; ++i) jpeg_huff_build(dht[i], dht[i] + 16, &tabs[(size_t)i]);
+  JpegBits br;
+  jpeg_bits_init(&br, data + scan_offset, data + len);
+  int pred[4] = {0, 0, 0, 0};
+  long long count = 0;
+  for (int my = 0; my < mcuy; ++my)
+    for (int mx = 0; mx < mcux; ++mx) {
+      if (restart_interval && count && count % restart_interval == 0) { jpeg_bits_restart(&br); pred[0] = pred[1] = pred[2] = 0; }
+      ++count;
+      for (int c = 0; c < ncomp; ++c) {
+        const int h = samp_hv[2 * c], v = samp_hv[2 * c + 1], bxn = mcux * h;
+        for (int by = 0; by < v; ++by)
+          for (int bx = 0; bx < h; ++bx) {
+            int16_t* blk = coef[c] + (((size_t)my * v + by) * bxn + (size_t)mx * h + bx) * 64;
+            std::memset(blk, 0, 64 * sizeof(int16_t));
+            jpeg_decode_block(&br, tabs[(size_t)2 * c], tabs[(size_t)2 * c + 1], &pred[c], blk);
+          }
+      }
+    }
+  return 0;
+}
+
 }

@@ -95,3 +95,37 @@ def test_device_back_half_header_is_bit_exact_on_the_host():
                 np.testing.assert_array_equal(_host_backend(enc.tobytes()), _ref(enc.tobytes()), err_msg="%s %dx%d q%d" % (sampling, w, h, q))
     ok, enc = cv2.imencode(".jpg", cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), [cv2.IMWRITE_JPEG_QUALITY, 75])
     np.testing.assert_array_equal(_host_backend(enc.tobytes()), _ref(enc.tobytes()))
+
+
+def test_entropy_building_blocks_match_the_oracle():
+    """csrc/jpeg_math.h's Huffman table / bit reader / block decoder (the sequential core of a device entropy stage), run on
+    the host over whole scans, reproduce the oracle's quantised coefficients exactly -- restart intervals, optimised tables,
+    4:4:4 / 4:2:2 / 4:2:0 / greyscale."""
+    import ctypes as C
+    import hostcheck
+    from oracle import jpeg_decode
+    hc = hostcheck.load()
+    hc.hc_jpeg_entropy.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    bufs = [open(f, "rb").read() for f in sorted(glob.glob(os.path.join(ROOT, "test_data", "*.jpg")))]
+    img = cv2.imread(os.path.join(ROOT, "test_data", "man.jpg"))
+    noise = np.random.default_rng(4).integers(0, 256, (61, 83, 3), dtype=np.uint8)
+    for sampling in ("444", "422", "420"):
+        fac = getattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR_" + sampling)
+        for src, q, rst, opt in ((img[:200, :300], 85, 0, 0), (img[:97, :131], 40, 2, 1), (noise, 100, 5, 0), (noise, 60, 0, 1)):
+            ok, enc = cv2.imencode(".jpg", src, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, fac, cv2.IMWRITE_JPEG_RST_INTERVAL, rst,
+                                                cv2.IMWRITE_JPEG_OPTIMIZE, opt])
+            bufs.append(enc.tobytes())
+    ok, enc = cv2.imencode(".jpg", cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), [cv2.IMWRITE_JPEG_QUALITY, 75])
+    bufs.append(enc.tobytes())
+    for buf in bufs:
+        f = jpeg_decode.entropy_decode(buf)
+        n = len(f["comps"])
+        tabs = [np.frombuffer(t[0] + t[1], np.uint8).copy() for c in f["comps"] for t in (c["dht_dc"], c["dht_ac"])]
+        tp = (C.c_void_p * (2 * n))(*[t.ctypes.data for t in tabs])
+        outs = [np.full(c["coef"].shape, 12345, np.int16) for c in f["comps"]]
+        op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        samp = (C.c_int * (2 * n))(*[v for c in f["comps"] for v in (c["h"], c["v"])])
+        data = np.frombuffer(buf, np.uint8)
+        assert hc.hc_jpeg_entropy(data.ctypes.data, len(buf), f["scan_offset"], n, samp, tp, f["restart_interval"], f["W"], f["H"], op) == 0
+        for c, o in zip(f["comps"], outs):
+            np.testing.assert_array_equal(o, c["coef"])
