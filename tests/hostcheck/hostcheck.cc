@@ -226,4 +226,47 @@ int hc_jpeg_entropy(const uint8_t* data, long long len, long long scan_offset, i
   return 0;
 }
 
+
+// The parallel schedule a device entropy stage can use when the file has restart markers: the scan is cut at the RSTn markers
+// (a byte scan), and every interval is decoded on its own -- fresh bit reader at its first byte, DC predictors 0, output position
+// from the interval index alone.  Intervals are visited in REVERSE order here to show that nothing flows between them.
+// Returns the number of intervals, or -1 if the marker count does not match the MCU count.
+int hc_jpeg_entropy_by_interval(const uint8_t* data, long long len, long long scan_offset, int ncomp, const int* samp_hv,
+                                const uint8_t* const* dht, int restart_interval, int W, int H, int16_t* const* coef) {
+  if (restart_interval <= 0) return -1;
+  int hmax = 1, vmax = 1;
+  for (int c = 0; c < ncomp; ++c) { hmax = imax(hmax, samp_hv[2 * c]); vmax = imax(vmax, samp_hv[2 * c + 1]); }
+  const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+  const long long mcus = (long long)mcux * mcuy;
+  std::vector<long long> start(1, scan_offset);
+  for (long long i = scan_offset; i + 1 < len; ++i) {
+    if (data[i] != 0xFF) continue;
+    if (data[i + 1] >= 0xD0 && data[i + 1] <= 0xD7) start.push_back(i + 2);
+    else if (data[i + 1] != 0x00 && data[i + 1] != 0xFF) break;               // EOI or another segment: end of the scan
+  }
+  const long long intervals = (mcus + restart_interval - 1) / restart_interval;
+  if ((long long)start.size() != intervals) return -1;
+  std::vector<JpegHuff> tabs((size_t)2 * ncomp);
+  for (int i = 0; i < 2 * ncomp; ++i) jpeg_huff_build(dht[i], dht[i] + 16, &tabs[(size_t)i]);
+  for (long long iv = intervals - 1; iv >= 0; --iv) {
+    JpegBits br;
+    jpeg_bits_init(&br, data + start[(size_t)iv], data + len);
+    int pred[4] = {0, 0, 0, 0};
+    const long long m0 = iv * restart_interval, m1 = m0 + restart_interval < mcus ? m0 + restart_interval : mcus;
+    for (long long m = m0; m < m1; ++m) {
+      const int my = (int)(m / mcux), mx = (int)(m % mcux);
+      for (int c = 0; c < ncomp; ++c) {
+        const int h = samp_hv[2 * c], v = samp_hv[2 * c + 1], bxn = mcux * h;
+        for (int by = 0; by < v; ++by)
+          for (int bx = 0; bx < h; ++bx) {
+            int16_t* blk = coef[c] + (((size_t)my * v + by) * bxn + (size_t)mx * h + bx) * 64;
+            std::memset(blk, 0, 64 * sizeof(int16_t));
+            jpeg_decode_block(&br, tabs[(size_t)2 * c], tabs[(size_t)2 * c + 1], &pred[c], blk);
+          }
+      }
+    }
+  }
+  return (int)intervals;
+}
+
 }

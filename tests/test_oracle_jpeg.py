@@ -117,6 +117,7 @@ def test_entropy_building_blocks_match_the_oracle():
             bufs.append(enc.tobytes())
     ok, enc = cv2.imencode(".jpg", cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), [cv2.IMWRITE_JPEG_QUALITY, 75])
     bufs.append(enc.tobytes())
+    checked_intervals = []
     for buf in bufs:
         f = jpeg_decode.entropy_decode(buf)
         n = len(f["comps"])
@@ -129,3 +130,15 @@ def test_entropy_building_blocks_match_the_oracle():
         assert hc.hc_jpeg_entropy(data.ctypes.data, len(buf), f["scan_offset"], n, samp, tp, f["restart_interval"], f["W"], f["H"], op) == 0
         for c, o in zip(f["comps"], outs):
             np.testing.assert_array_equal(o, c["coef"])
+        if f["restart_interval"]:
+            # the parallel schedule: every restart interval decoded independently (in reverse order), located by a byte scan
+            for o in outs:
+                o.fill(12345)
+            mcus = (-(-f["W"] // (8 * f["hmax"]))) * (-(-f["H"] // (8 * f["vmax"])))
+            hc.hc_jpeg_entropy_by_interval.argtypes = hc.hc_jpeg_entropy.argtypes
+            n_iv = hc.hc_jpeg_entropy_by_interval(data.ctypes.data, len(buf), f["scan_offset"], n, samp, tp, f["restart_interval"], f["W"], f["H"], op)
+            assert n_iv == -(-mcus // f["restart_interval"])
+            for c, o in zip(f["comps"], outs):
+                np.testing.assert_array_equal(o, c["coef"])
+            checked_intervals.append(n_iv)
+    assert len(checked_intervals) >= 7 and max(checked_intervals) > 20
