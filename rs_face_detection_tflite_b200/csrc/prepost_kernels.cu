@@ -1,11 +1,25 @@
 // prepost_kernels.cu -- see prepost_kernels.cuh.  Compiled with -fmad=false.
 #include "prepost_kernels.cuh"
 
+#include <atomic>
+
 namespace fdl {
 
 void count_launch();
 
 namespace {
+
+// Opt-in shared memory sizes are a per-device function attribute: remember per device (a process may hold handles on several
+// GPUs through the C ABI's `device` argument), set it before the first launch there.  Two racing first callers both set it.
+template <typename K>
+void opt_in_smem_once(std::atomic<unsigned long long>& done, K kernel, int bytes) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const unsigned long long bit = 1ull << (d & 63);
+  if (done.load(std::memory_order_acquire) & bit) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  done.fetch_or(bit, std::memory_order_release);
+}
 
 // ------------------------------------------------------------------------------------------------
 __global__ void anchors_kernel(SsdOptions opt, float* out, int n) {
@@ -818,11 +832,8 @@ cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long 
     }
   }
   if (max_ctas > 0 && !out_u8) {
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncSetAttribute(i2t_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
-      attr_done = true;
-    }
+    static std::atomic<unsigned long long> tile_attr{0};
+    opt_in_smem_once(tile_attr, i2t_tile_kernel, kTileSmem);
     long long items = (long long)n * ((out_w + kTileW - 1) / kTileW) * ((out_h + kTileH - 1) / kTileH);
     if (items > max_ctas) items = max_ctas;
     i2t_tile_kernel<<<(unsigned)items, 256, kTileSmem, s>>>(frames, frame_stride, row_stride, params, n, out_w, out_h, out, out_bstride, n_active);
@@ -844,11 +855,8 @@ cudaError_t launch_i2t(const uint8_t* frames, long long frame_stride, long long 
 cudaError_t launch_ssd_postprocess(const SsdPostArgs& a, cudaStream_t s) {
   if (a.B <= 0) return cudaSuccess;
   size_t smem = (size_t)a.N * 5 * sizeof(int);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(ssd_postprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> post_attr{0};
+  opt_in_smem_once(post_attr, ssd_postprocess_kernel, 160 * 1024);
   ssd_postprocess_kernel<<<a.B, kPostThreads, smem, s>>>(a);
   return FDL_LAUNCHED();
 }
