@@ -6,6 +6,7 @@
 
 #include "../../rs_face_detection_tflite_b200/csrc/glue_math.h"
 #include "../../rs_face_detection_tflite_b200/csrc/jpeg_math.h"
+#include "../../rs_face_detection_tflite_b200/csrc/jpeg_parse.h"
 
 using namespace fdl;
 
@@ -267,6 +268,35 @@ int hc_jpeg_entropy_by_interval(const uint8_t* data, long long len, long long sc
     }
   }
   return (int)intervals;
+}
+
+
+// Whole decode on the host through csrc/jpeg_parse.h + csrc/jpeg_math.h: bytes -> RGB.  Two calls: rgb == nullptr returns the
+// size; returns 0, or -1 with the parser's message in err.
+int hc_jpeg_decode(const uint8_t* data, long long len, uint8_t* rgb, int* w, int* h, char* err, int errcap) {
+  JpegHeader hd;
+  std::string msg;
+  if (!jpeg_parse_header(data, (size_t)len, &hd, &msg)) {
+    if (err && errcap > 0) { std::strncpy(err, msg.c_str(), (size_t)errcap - 1); err[errcap - 1] = 0; }
+    return -1;
+  }
+  *w = hd.width; *h = hd.height;
+  if (!rgb) return 0;
+  int samp[6];
+  const uint8_t* dht[6];
+  const uint16_t* quant[3];
+  std::vector<std::vector<int16_t>> coef((size_t)hd.ncomp);
+  int16_t* cp[3];
+  for (int c = 0; c < hd.ncomp; ++c) {
+    samp[2 * c] = hd.comp[c].h; samp[2 * c + 1] = hd.comp[c].v;
+    dht[2 * c] = hd.dht[0][hd.comp[c].td]; dht[2 * c + 1] = hd.dht[1][hd.comp[c].ta];
+    quant[c] = hd.quant[hd.comp[c].tq];
+    coef[(size_t)c].assign((size_t)hd.mcus_x * hd.comp[c].h * hd.mcus_y * hd.comp[c].v * 64, 0);
+    cp[c] = coef[(size_t)c].data();
+  }
+  hc_jpeg_entropy(data, len, (long long)hd.scan_offset, hd.ncomp, samp, dht, hd.restart_interval, hd.width, hd.height, cp);
+  const int16_t* ccp[3] = {cp[0], hd.ncomp > 1 ? cp[1] : nullptr, hd.ncomp > 2 ? cp[2] : nullptr};
+  return hc_jpeg_backend(hd.ncomp, ccp, quant, samp, hd.width, hd.height, rgb);
 }
 
 }

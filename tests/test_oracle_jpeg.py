@@ -142,3 +142,42 @@ def test_entropy_building_blocks_match_the_oracle():
                 np.testing.assert_array_equal(o, c["coef"])
             checked_intervals.append(n_iv)
     assert len(checked_intervals) >= 7 and max(checked_intervals) > 20
+
+
+def test_host_decoder_end_to_end_and_rejections():
+    """jpeg_parse.h + jpeg_math.h chained on the host (parse -> entropy -> back half): bytes in, cv2.imdecode's pixels out;
+    what the oracle rejects, the parser rejects too."""
+    import ctypes as C
+    import hostcheck
+    from oracle import jpeg_decode
+    hc = hostcheck.load()
+    hc.hc_jpeg_decode.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_int]
+
+    def decode(buf):
+        data = np.frombuffer(buf, np.uint8)
+        w, h = C.c_int(), C.c_int()
+        err = C.create_string_buffer(128)
+        if hc.hc_jpeg_decode(data.ctypes.data, len(buf), None, C.byref(w), C.byref(h), err, 128) != 0:
+            raise ValueError(err.value.decode())
+        out = np.empty((h.value, w.value, 3), np.uint8)
+        assert hc.hc_jpeg_decode(data.ctypes.data, len(buf), out.ctypes.data, C.byref(w), C.byref(h), err, 128) == 0
+        return out
+
+    for f in sorted(glob.glob(os.path.join(ROOT, "test_data", "*.jpg"))):
+        buf = open(f, "rb").read()
+        np.testing.assert_array_equal(decode(buf), _ref(buf), err_msg=f)
+    frame = np.random.default_rng(2).integers(0, 256, (270, 480, 3), dtype=np.uint8)
+    frame[60:200, 100:380] = cv2.resize(cv2.imread(os.path.join(ROOT, "test_data", "man.jpg")), (280, 140))
+    for fac in ("444", "422", "420"):
+        ok, enc = cv2.imencode(".jpg", frame, [cv2.IMWRITE_JPEG_QUALITY, 92, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, getattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR_" + fac),
+                                               cv2.IMWRITE_JPEG_RST_INTERVAL, 7])
+        np.testing.assert_array_equal(decode(enc.tobytes()), _ref(enc.tobytes()))
+    ok, enc = cv2.imencode(".jpg", frame, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    for bad in (enc.tobytes(), b"\x89PNG\r\n\x1a\n", open(os.path.join(ROOT, "test_data", "man.jpg"), "rb").read()[:300]):
+        with pytest.raises(ValueError) as e_c:
+            decode(bad)
+        with pytest.raises(ValueError):
+            jpeg_decode.decode_jpeg_rgb(bad)
+        assert str(e_c.value)
+    with pytest.raises(ValueError, match="baseline"):
+        decode(enc.tobytes())
