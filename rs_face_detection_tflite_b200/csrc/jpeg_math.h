@@ -193,4 +193,65 @@ FDL_JHD void jpeg_decode_block(JpegBits* b, const JpegHuff& dc, const JpegHuff& 
   }
 }
 
+// ---- self-synchronising parallel entropy decoding (files without restart markers) ----------------------------------------
+// Huffman streams resynchronise: a decoder started at an arbitrary bit with a guessed state soon falls into step with the true
+// symbol sequence.  The scan (byte-unstuffed into a clean buffer first) is cut into fixed windows; every window is decoded from
+// a guessed entry state, the exit states are handed to the next windows, and windows whose entry changed are decoded again
+// until nothing changes (Weissenberger & Schmidt, "Massively Parallel Huffman Decoding on GPUs", ICPP 2018, and its JPEG
+// follow-up).  These are the per-window primitives; tests/hostcheck runs the schedule on the host.
+struct JpegSyncState {
+  long long pos;   // bit position in the unstuffed scan
+  int b;           // block index inside the MCU (scan order)
+  int k;           // next zig-zag index of that block (0: the DC symbol is next)
+};
+FDL_JHD bool operator==(const JpegSyncState& x, const JpegSyncState& y) { return x.pos == y.pos && x.b == y.b && x.k == y.k; }
+
+FDL_JHD unsigned jpeg_peek_clean(const uint8_t* buf, long long nbits, long long pos, int k) {   // k <= 24; zeros past the end
+  unsigned long long w = 0;
+  const long long byte = pos >> 3;
+  for (int i = 0; i < 5; ++i) { const long long j = byte + i; w = (w << 8) | (unsigned long long)((j << 3) < nbits ? buf[j] : 0); }
+  return (unsigned)((w >> (40 - (int)(pos & 7) - k)) & ((1u << k) - 1));
+}
+
+// One symbol (Huffman code + its extra bits) at st->pos for the block / zig-zag position in st.  Advances st; reports what the
+// symbol meant: *zz = zig-zag index of the coefficient it carries (-1: none, i.e. EOB / ZRL / zero DC difference), *value = the
+// coefficient (AC) or DC difference, *block_done = the symbol ended its block.
+FDL_JHD void jpeg_sync_step(const uint8_t* buf, long long nbits, const JpegHuff* tabs /*[2*comp + {0 dc, 1 ac}]*/, const uint8_t* comp_of_block,
+                            int blocks_per_mcu, JpegSyncState* st, int* zz, int* value, bool* block_done) {
+  const JpegHuff& t = tabs[2 * comp_of_block[st->b] + (st->k ? 1 : 0)];
+  int sym, len;
+  const int look = t.look[jpeg_peek_clean(buf, nbits, st->pos, 9)];
+  if (look) { len = look >> 8; sym = look & 255; }
+  else {
+    const unsigned w = jpeg_peek_clean(buf, nbits, st->pos, 16);
+    len = 10;
+    int code = (int)(w >> 6);
+    while (len <= 16 && code > t.maxcode[len]) { ++len; code = (int)(w >> (16 - len)); }
+    if (len > 16) { len = 16; sym = 0; } else sym = t.huffval[(code + t.valoffset[len]) & 255];
+  }
+  st->pos += len;
+  *zz = -1; *value = 0; *block_done = false;
+  if (st->k == 0) {                                   // DC: sym = number of extra bits
+    if (sym) { const int sz = sym > 16 ? 16 : sym; *value = jpeg_extend((int)jpeg_peek_clean(buf, nbits, st->pos, sz), sz); st->pos += sz; }
+    *zz = 0;
+    st->k = 1;
+    return;
+  }
+  const int r = sym >> 4, s2 = sym & 15;
+  if (s2 == 0) {
+    if (r != 15) *block_done = true;                  // EOB
+    else { st->k += 16; if (st->k > 63) *block_done = true; }
+  } else {
+    st->k += r;
+    if (st->k > 63) *block_done = true;               // corrupt run: the block ends (as the sequential decoder does)
+    else {
+      *zz = st->k;
+      *value = jpeg_extend((int)jpeg_peek_clean(buf, nbits, st->pos, s2), s2);
+      st->pos += s2;
+      if (++st->k > 63) *block_done = true;
+    }
+  }
+  if (*block_done) { st->k = 0; st->b = st->b + 1 == blocks_per_mcu ? 0 : st->b + 1; }
+}
+
 }  // namespace fdl

@@ -299,4 +299,89 @@ int hc_jpeg_decode(const uint8_t* data, long long len, uint8_t* rgb, int* w, int
   return hc_jpeg_backend(hd.ncomp, ccp, quant, samp, hd.width, hd.height, rgb);
 }
 
+
+// The self-synchronising schedule (jpeg_math.h) on the host, for scans WITHOUT restart markers: unstuff, cut into windows of
+// `window_bits`, decode every window from a guessed entry state, hand exit states forward until a fixed point (every round is
+// one parallel step on a device), then one output pass with block offsets from a prefix sum and DC values from a per-component
+// prefix sum of the differences.  Returns the number of rounds the fixed point took (>= 1), or -1.
+int hc_jpeg_entropy_selfsync(const uint8_t* data, long long len, long long scan_offset, int ncomp, const int* samp_hv, const uint8_t* const* dht,
+                             int W, int H, int window_bits, int16_t* const* coef, int* windows_out, int* redecoded_out) {
+  int hmax = 1, vmax = 1;
+  for (int c = 0; c < ncomp; ++c) { hmax = imax(hmax, samp_hv[2 * c]); vmax = imax(vmax, samp_hv[2 * c + 1]); }
+  const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+  uint8_t comp_of_block[16];
+  int bpm = 0;
+  for (int c = 0; c < ncomp; ++c) for (int i = 0; i < samp_hv[2 * c] * samp_hv[2 * c + 1]; ++i) { if (bpm >= 16) return -1; comp_of_block[bpm++] = (uint8_t)c; }
+  const long long total_blocks = (long long)mcux * mcuy * bpm;
+  std::vector<JpegHuff> tabs((size_t)2 * ncomp);
+  for (int i = 0; i < 2 * ncomp; ++i) jpeg_huff_build(dht[i], dht[i] + 16, &tabs[(size_t)i]);
+  // unstuff (a stream compaction on a device)
+  std::vector<uint8_t> clean;
+  for (long long i = scan_offset; i < len; ++i) {
+    if (data[i] == 0xFF) { if (i + 1 < len && data[i + 1] == 0x00) { clean.push_back(0xFF); ++i; continue; } break; }
+    clean.push_back(data[i]);
+  }
+  const long long nbits = (long long)clean.size() * 8;
+  const int nwin = (int)((nbits + window_bits - 1) / window_bits);
+  if (nwin < 1) return -1;
+  std::vector<JpegSyncState> entry((size_t)nwin), exit_((size_t)nwin);
+  std::vector<long long> blocks((size_t)nwin, 0);
+  auto run = [&](int i, bool write, long long block0) {
+    JpegSyncState st = entry[(size_t)i];
+    const long long end = (long long)(i + 1) * window_bits < nbits ? (long long)(i + 1) * window_bits : nbits;
+    long long nb = 0;
+    while (st.pos < end) {
+      int zz, value; bool done;
+      const int b = st.b;
+      jpeg_sync_step(clean.data(), nbits, tabs.data(), comp_of_block, bpm, &st, &zz, &value, &done);
+      if (write && zz >= 0) {
+        const long long g = block0 + nb;
+        if (g < total_blocks) {
+          const long long m = g / bpm;
+          const int c = comp_of_block[b], h = samp_hv[2 * c], v = samp_hv[2 * c + 1];
+          int first = 0; while (comp_of_block[first] != c) ++first;
+          const int j = b - first, by = j / h, bx = j % h, my = (int)(m / mcux), mx = (int)(m % mcux);
+          static const uint8_t zzt[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                                          35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+          coef[c][((((size_t)my * v + by) * ((size_t)mcux * h)) + (size_t)mx * h + bx) * 64 + zzt[zz]] = (int16_t)value;   // DC: the difference for now
+        }
+      }
+      if (done) ++nb;
+    }
+    exit_[(size_t)i] = st; blocks[(size_t)i] = nb;
+  };
+  for (int i = 0; i < nwin; ++i) { entry[(size_t)i].pos = (long long)i * window_bits; entry[(size_t)i].b = 0; entry[(size_t)i].k = 0; run(i, false, 0); }
+  int rounds = 1, redecoded = 0;
+  for (;; ++rounds) {
+    std::vector<JpegSyncState> next(entry);
+    for (int i = 1; i < nwin; ++i) next[(size_t)i] = exit_[(size_t)i - 1];        // all from the previous round: one parallel step
+    bool changed = false;
+    for (int i = 1; i < nwin; ++i)
+      if (!(next[(size_t)i] == entry[(size_t)i])) { entry[(size_t)i] = next[(size_t)i]; run(i, false, 0); changed = true; ++redecoded; }
+    if (!changed) break;
+    if (rounds > nwin + 2) return -1;
+  }
+  // output pass
+  for (int c = 0; c < ncomp; ++c) std::memset(coef[c], 0, (size_t)mcux * samp_hv[2 * c] * mcuy * samp_hv[2 * c + 1] * 64 * sizeof(int16_t));
+  long long before = 0;
+  for (int i = 0; i < nwin; ++i) { const long long nb = blocks[(size_t)i]; run(i, true, before); before += nb; }
+  if (before < total_blocks) return -1;
+  // DC differences -> values: per-component running sum in scan order
+  int pred[4] = {0, 0, 0, 0};
+  for (int my = 0; my < mcuy; ++my)
+    for (int mx = 0; mx < mcux; ++mx)
+      for (int c = 0; c < ncomp; ++c) {
+        const int h = samp_hv[2 * c], v = samp_hv[2 * c + 1];
+        for (int by = 0; by < v; ++by)
+          for (int bx = 0; bx < h; ++bx) {
+            int16_t* blk = coef[c] + ((((size_t)my * v + by) * ((size_t)mcux * h)) + (size_t)mx * h + bx) * 64;
+            pred[c] += blk[0];
+            blk[0] = (int16_t)pred[c];
+          }
+      }
+  if (windows_out) *windows_out = nwin;
+  if (redecoded_out) *redecoded_out = redecoded;
+  return rounds;
+}
+
 }

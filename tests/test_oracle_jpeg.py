@@ -181,3 +181,47 @@ def test_host_decoder_end_to_end_and_rejections():
         assert str(e_c.value)
     with pytest.raises(ValueError, match="baseline"):
         decode(enc.tobytes())
+
+
+def test_self_synchronising_schedule_matches_sequential_decode():
+    """Files without restart markers (two of the reference's three test images): the scan is cut into fixed windows that are
+    decoded from guessed states and re-decoded until the hand-over of exit states reaches a fixed point (csrc/jpeg_math.h
+    jpeg_sync_step; the schedule itself runs on the host here).  The result must equal the sequential decode, and the fixed point
+    must come after a few rounds -- the property that makes the scheme parallel."""
+    import ctypes as C
+    import hostcheck
+    from oracle import jpeg_decode
+    hc = hostcheck.load()
+    hc.hc_jpeg_entropy_selfsync.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                            C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    bufs = [open(os.path.join(ROOT, "test_data", n), "rb").read() for n in ("man.jpg", "russ_cox_2.jpg")]
+    img = cv2.imread(os.path.join(ROOT, "test_data", "man.jpg"))
+    noise = np.random.default_rng(8).integers(0, 256, (120, 200, 3), dtype=np.uint8)
+    for sampling in ("444", "422", "420"):
+        fac = getattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR_" + sampling)
+        for src, q, opt in ((img, 90, 0), (img[:97, :131], 30, 1), (noise, 95, 0)):
+            ok, enc = cv2.imencode(".jpg", src, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, fac, cv2.IMWRITE_JPEG_OPTIMIZE, opt])
+            bufs.append(enc.tobytes())
+    ok, enc = cv2.imencode(".jpg", cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), [cv2.IMWRITE_JPEG_QUALITY, 75])
+    bufs.append(enc.tobytes())
+    worst = 0
+    for buf in bufs:
+        f = jpeg_decode.entropy_decode(buf)
+        assert f["restart_interval"] == 0
+        n = len(f["comps"])
+        tabs = [np.frombuffer(t[0] + t[1], np.uint8).copy() for c in f["comps"] for t in (c["dht_dc"], c["dht_ac"])]
+        tp = (C.c_void_p * (2 * n))(*[t.ctypes.data for t in tabs])
+        samp = (C.c_int * (2 * n))(*[v for c in f["comps"] for v in (c["h"], c["v"])])
+        data = np.frombuffer(buf, np.uint8)
+        for window_bits in (1024, 256):
+            outs = [np.full(c["coef"].shape, 12345, np.int16) for c in f["comps"]]
+            op = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+            nwin, redone = C.c_int(), C.c_int()
+            rounds = hc.hc_jpeg_entropy_selfsync(data.ctypes.data, len(buf), f["scan_offset"], n, samp, tp, f["W"], f["H"], window_bits, op,
+                                                 C.byref(nwin), C.byref(redone))
+            assert rounds >= 1, rounds
+            for c, o in zip(f["comps"], outs):
+                np.testing.assert_array_equal(o, c["coef"])
+            worst = max(worst, rounds)
+            assert rounds <= 12 or rounds < nwin.value // 4, (rounds, nwin.value, redone.value)     # nowhere near sequential
+    assert worst >= 2          # the guesses were wrong somewhere: the hand-over was exercised
