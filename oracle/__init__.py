@@ -23,6 +23,9 @@ What it restates (all citations relative to /root/reference):
 Parity pin: the reference's own tests assert nothing, so the
 oracle is pinned to the only golden artefacts the reference holds -- the three
 rendered PNGs in ``assets/`` written by ``src/lib.rs:42-83`` -- pixel-exactly
-(``tests/test_oracle_kat.py``), and to cv2 for the OpenCV half.  Beyond that
+(``tests/test_oracle_kat.py``; ``tests/test_golden.py`` re-renders the oracle's
+results with ``oracle/render.py``, a restatement of ``render.rs`` + imageproc's
+drawing routines, and requires the painted pixel sets to equal the PNGs'), and
+to cv2 for the OpenCV half and the JPEG ingest (``oracle/jpeg_decode.py``).  Beyond that
 parity is "unpinned by the reference's tests" and DESIGN.md says so.
 """
