@@ -41,6 +41,14 @@ METRIC = "frames/sec detect+landmark+iris"
 UNIT = "frames/s"
 
 
+def _config(B):
+    """The workload both arms report (identical dicts: the driver compares them)."""
+    return {"workload": "full detect(back-256)->landmark(192)->iris(64, L+R) pipeline on synthetic 1080p G2 frames (BASELINE config 5; "
+                        "contains config 2 as its detection stage)",
+            "frames_per_step_per_gpu": B, "frame": "1920x1080x3 u8",
+            "l2_policy": "inputs larger than L2: %.2f GB of frames per step" % (B * W * H * 3 / 1e9)}
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -257,7 +265,7 @@ def run_reference(args):
     if rank != 0:
         return
     pool = CpuPool()
-    per_step = args.ref_frames if args.ref_frames > 0 else 8 * pool.workers
+    per_step = args.ref_frames if args.ref_frames > 0 else args.batch
     times = []
     for s in range(args.warmup + args.steps):
         _, dt = pool.fps(per_step)
@@ -273,12 +281,32 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "full detect(back-256)->landmark(192)->iris(64, L+R) pipeline on synthetic 1080p G2 frames, CPU, one frame per core at a time",
-                   "frames_per_step": per_step},
+        "config": _config(per_step),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def _parity_spot_check(kept, base, uniq):
+    """After the timed region (checker only, never timed): a seeded sample of the last timed batch's results against the oracle's
+    per-frame call sequence on the same frames -- kept anchors exact, box / keypoint coordinates 1e-3, landmarks and iris 0.5 px."""
+    from oracle import glue, pipeline
+    op = pipeline.Pipeline(glue.BACK_CAMERA, MODELS)
+    scale = np.array([W, H])
+    for slot, got in kept.items():
+        ref_faces, ref = op.run(base[slot % uniq])
+        assert [d.anchor for d in got.detections] == [d.anchor for d in ref_faces], "bench parity: kept anchors differ from the oracle (slot %d)" % slot
+        for o, e in zip(got.detections, ref_faces):
+            assert np.abs(o.data - e.data).max() <= 1e-3 and abs(o.score - float(e.score)) <= 1e-3, "bench parity: detection coordinates (slot %d)" % slot
+        f, r = got.faces[0], ref[0]
+        assert (f.landmarks is not None) == (len(r["landmarks"]) > 0)
+        if f.landmarks is not None:
+            assert np.abs(f.landmarks[:, :2] * scale - r["landmarks"][:, :2] * scale).max() < 0.5, "bench parity: landmarks (slot %d)" % slot
+            for ours_c, ours_i, key in ((f.left_contour, f.left_iris, "left"), (f.right_contour, f.right_iris, "right")):
+                assert np.abs(ours_c[:, :2] * scale - r[key][0][:, :2] * scale).max() < 0.5, "bench parity: eye contour (slot %d)" % slot
+                assert np.abs(ours_i[:, :2] * scale - r[key][1][:, :2] * scale).max() < 0.5, "bench parity: iris (slot %d)" % slot
+    return len(kept)
 
 
 def run_ours(args):
@@ -358,6 +386,10 @@ def run_ours(args):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = fdl.launch_count() - launches0
+
+    # Results of the last timed device-resident batch, kept for the parity spot check below (frame i of a batch is base[i % uniq]).
+    checked_slots = sorted(int(s) for s in np.random.default_rng(2024).choice(B, size=min(args.parity_frames, B), replace=False))
+    kept = {s: pipe._frame(s) for s in checked_slots} if rank == 0 else {}
 
     # ---------------- host-sourced: `e2e` ----------------
     # Two ways to get pinned host frames to the kernels, both timed, the faster one reported as `e2e`:
@@ -441,15 +473,16 @@ def run_ours(args):
             cpu = {"value": v, "unit": UNIT, "cores": pool.workers, "kind": "port",
                    "sample": "%d G2 1080p frames, restated reference CPU path (oracle: cv2 + torch-CPU f32 + numpy; the Rust/TFLite reference cannot "
                              "be built offline), one single-threaded worker process per host core (%d of %d cores)" % (n_cpu, pool.workers, os.cpu_count())}
+        parity_checked = 0
+        if not args.no_cpu_baseline and kept:
+            parity_checked = _parity_spot_check(kept, base, uniq)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "full detect(back-256)->landmark(192)->iris(64, L+R) pipeline on synthetic 1080p G2 frames (BASELINE config 5; "
-                                   "contains config 2 as its detection stage)",
-                       "frames_per_step_per_gpu": B, "frame": "1920x1080x3 u8", "faces_per_frame": n_faces / B, "landmark_sets_per_frame": n_lm / B,
-                       "l2_policy": "inputs larger than L2: %.2f GB of frames per step" % (B * W * H * 3 / 1e9), "parallelism": "frames sharded by rank, no collective",
-                       "batches_in_flight": args.dev_inflight, "cpu_affinity": ("GPU-local cores (%d)" % numa) if numa else "inherited"},
+            "config": _config(B),
+            "run": {"faces_per_frame": n_faces / B, "landmark_sets_per_frame": n_lm / B, "parallelism": "frames sharded by rank, no collective",
+                    "batches_in_flight": args.dev_inflight, "cpu_affinity": ("GPU-local cores (%d)" % numa) if numa else "inherited"},
             "e2e": {"value": e2e, "unit": UNIT,
                     "h2d_bytes_per_step": B * W * H * 3 if (e2e_zc_s is None or e2e_copy_s <= e2e_zc_s) else B * zero_copy_bytes_per_frame(zc_rect_bytes),
                     "d2h_bytes_per_step": B * (ctypes.sizeof(_lib.CFrameResult) + ctypes.sizeof(_lib.CFaceResult)),
@@ -457,6 +490,7 @@ def run_ours(args):
                     "copy_mode_value": frames_total / e2e_copy_max, "copy_mode_h2d_ms_per_step": h2d_ms,
                     "zero_copy_mode_value": (frames_total / e2e_zc_max) if e2e_zc_s is not None else None},
             "gpu_launches": int(launches),
+            "parity_checked": parity_checked,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": dom["traffic"],
                          "kernel": dom["kernel"], "launches_per_step": dom["launches"], "algorithmic_bytes_per_launch": dom["algo_bytes"],
@@ -499,9 +533,10 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="frames per step per GPU")
     ap.add_argument("--unique-frames", type=int, default=16)
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the cpu_baseline sample (0: 24 per host core)")
-    ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of --impl reference (0: 8 per host core)")
+    ap.add_argument("--ref-frames", type=int, default=0, help="frames per step of --impl reference (0: --batch, the same step as the GPU arm)")
     ap.add_argument("--latency-iters", type=int, default=40)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs: the cpu_baseline sample and the oracle parity spot check")
+    ap.add_argument("--parity-frames", type=int, default=8, help="frames of the last timed batch checked against the oracle after the timed region")
     ap.add_argument("--no-zero-copy", action="store_true", help="skip the zero-copy e2e leg")
     ap.add_argument("--inflight", type=int, default=4, help="batches in flight in the e2e loop (<= pipeline depth 4)")
     ap.add_argument("--dev-inflight", type=int, default=3, help="batches in flight in the device-resident loop (<= pipeline depth 4)")

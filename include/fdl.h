@@ -278,8 +278,11 @@ typedef struct fdl_face_result {
 } fdl_face_result;
 
 typedef struct fdl_frame_result {
-  int32_t n_detections;
+  int32_t n_detections;              /* entries of detections[]: min(n_total_detections, FDL_MAX_DETECTIONS) */
   int32_t n_faces;                   /* min(n_detections, max_faces) */
+  int32_t n_total_detections;        /* detections weighted NMS produced for this frame; the reference returns an unbounded Vec
+                                        (face_detection.rs:267) -- when this exceeds FDL_MAX_DETECTIONS the record is truncated
+                                        and fdl_pipeline_collect reports FDL_ERR_CAPACITY (the results are still delivered) */
   fdl_detection detections[FDL_MAX_DETECTIONS];
 } fdl_frame_result;
 
@@ -290,7 +293,10 @@ FDL_API int fdl_pipeline_run(fdl_pipeline*, const fdl_image* frames, int n, fdl_
                              fdl_face_result* face_results);
 /* Asynchronous double-buffered form: submit enqueues H2D + all kernels + D2H on the pipeline's
  * streams and returns a ticket; collect waits for that ticket and copies the results out.  Up to
- * `fdl_pipeline_depth()` submits may be in flight. */
+ * `fdl_pipeline_depth()` submits may be in flight.  collect (and run) return FDL_ERR_CAPACITY -- after
+ * delivering the results and releasing the ticket -- when a frame produced more than FDL_MAX_DETECTIONS
+ * detections (fdl_frame_result.n_total_detections says how many; fdl_detector_infer with a larger
+ * buffer returns all of them), as fdl_detector_infer does for a short caller buffer. */
 FDL_API int fdl_pipeline_depth(const fdl_pipeline*);
 FDL_API int fdl_pipeline_submit(fdl_pipeline*, const fdl_image* frames, int n, int* ticket);
 FDL_API int fdl_pipeline_collect(fdl_pipeline*, int ticket, fdl_frame_result* frame_results,

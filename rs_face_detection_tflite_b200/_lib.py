@@ -56,7 +56,8 @@ class CFaceResult(C.Structure):
 
 
 class CFrameResult(C.Structure):
-    _fields_ = [("n_detections", C.c_int32), ("n_faces", C.c_int32), ("detections", CDetection * MAX_DETECTIONS)]
+    _fields_ = [("n_detections", C.c_int32), ("n_faces", C.c_int32), ("n_total_detections", C.c_int32),
+                ("detections", CDetection * MAX_DETECTIONS)]
 
 
 # every symbol include/fdl.h declares: name -> (restype, argtypes)

@@ -507,6 +507,7 @@ class FaceResult:
 class FrameResult:
     detections: list
     faces: list
+    n_total_detections: int = 0    # what weighted NMS produced; > len(detections) when the record was truncated at 32
 
 
 class Pipeline:
@@ -514,8 +515,9 @@ class Pipeline:
 
     def __init__(self, detector_model: FaceDetectionModel = FaceDetectionModel.BackCamera, frame_size=(1920, 1080), max_batch: int = 64,
                  max_faces: int = 1, run_landmarks: bool = True, run_iris: bool = True, model_dir: str | None = None, device: int = 0,
-                 zero_copy_host: bool = False, refine_landmarks: bool = False, focal_length_mm: float = 0.0):
+                 zero_copy_host: bool = False, refine_landmarks: bool = False, focal_length_mm: float = 0.0, allow_truncated: bool = False):
         self._h = C.c_void_p()
+        self.allow_truncated = bool(allow_truncated)   # collect() raises FdlError(FDL_ERR_CAPACITY) for > 32 detections in a frame unless set
         self._dir = os.fsencode(model_dir) if model_dir else None
         cfg = CPipelineConfig(int(detector_model), device, max_batch, max_faces, int(frame_size[0]), int(frame_size[1]),
                               1 if run_landmarks else 0, 1 if (run_iris and run_landmarks) else 0, self._dir, 1 if zero_copy_host else 0,
@@ -571,8 +573,11 @@ class Pipeline:
     def collect_raw(self, ticket: int) -> int:
         """Waits for `ticket`; results stay in the ctypes arrays (self._frames / self._faces). Returns n."""
         n = C.c_int()
-        check(lib().fdl_pipeline_collect(self._h, ticket, self._frames, self._faces, C.byref(n)))
+        rc = lib().fdl_pipeline_collect(self._h, ticket, self._frames, self._faces, C.byref(n))
         self._keep.pop(ticket, None)
+        if rc == _lib.FDL_ERR_CAPACITY and self.allow_truncated:
+            return n.value          # the records are delivered; FrameResult.n_total_detections tells which frames overflowed
+        check(rc)
         return n.value
 
     def collect(self, ticket: int):
@@ -600,7 +605,7 @@ class Pipeline:
                                         g(c.refined_landmarks) if (iris_ok and self.refine_landmarks) else None,
                                         (c.iris_diameter_px[0], c.iris_diameter_px[1]) if iris_ok else None,
                                         (c.iris_depth_mm[0], c.iris_depth_mm[1]) if (iris_ok and self.focal_length_mm > 0) else None))
-        return FrameResult(dets, faces)
+        return FrameResult(dets, faces, int(fr.n_total_detections))
 
     @property
     def last_device_ms(self) -> float:

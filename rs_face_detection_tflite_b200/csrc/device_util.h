@@ -9,6 +9,29 @@
 
 namespace fdl {
 
+// Every ABI call selects its handle's device; this guard puts the calling thread's current device back on exit, so a
+// host process that drives several GPUs (its own CUDA work, torch, other handles) never sees its device changed by a call.
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// CUDA events that are destroyed on every exit path.
+struct EventSet {
+  cudaEvent_t* ev = nullptr;
+  int n = 0;
+  ~EventSet() { for (int i = 0; i < n; ++i) if (ev[i]) cudaEventDestroy(ev[i]); delete[] ev; }
+  cudaError_t create(int count) {
+    ev = new cudaEvent_t[(size_t)count]();
+    n = count;
+    for (int i = 0; i < count; ++i) { cudaError_t e = cudaEventCreate(&ev[i]); if (e != cudaSuccess) return e; }
+    return cudaSuccess;
+  }
+};
+
 // Grow-only device buffer.
 template <typename T>
 struct DevBuf {
@@ -52,6 +75,7 @@ inline int stage_frames(const fdl_image* images, int n, DevBuf<uint8_t>* dst, cu
   for (int i = 0; i < n; ++i) {
     if (!images[i].data) return set_error(FDL_ERR_INVALID, "image data pointer is null");
     if (images[i].width != w || images[i].height != h) return set_error(FDL_ERR_INVALID, "all images of a batch must have the same size");
+    if (images[i].row_stride < 0) return set_error(FDL_ERR_INVALID, "negative row_stride (bottom-up images are not supported: pass a top-down copy)");
     if (images[i].row_stride != 0 && (size_t)images[i].row_stride < row) return set_error(FDL_ERR_INVALID, "row_stride smaller than width*3");
   }
   if (direct) {

@@ -97,11 +97,12 @@ extern "C" {
 
 const char* fdl_last_error(void) { return g_last_error.c_str(); }
 const char* fdl_version(void) { return "fdl-b200 0.1 (sm_100a)"; }
-int fdl_device_count(void) {
+int fdl_device_count(void) try {
+  DeviceGuard _device_guard;
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
-}
+} FDL_ABI_CATCH
 uint64_t fdl_launch_count(void) { return launch_count_value(); }
 
 // ------------------------------------------------------------------------------------------ net
@@ -124,7 +125,8 @@ static int net_forward_host(Net* net, cudaStream_t stream, const float* in, int 
   return FDL_OK;
 }
 
-int fdl_net_create(const char* tflite_file, int device, fdl_net** out) {
+int fdl_net_create(const char* tflite_file, int device, fdl_net** out) try {
+  DeviceGuard _device_guard;
   if (!tflite_file || !out) return set_error(FDL_ERR_INVALID, "null argument");
   *out = nullptr;
   if (device >= 0) { int rc = check_device(device); if (rc) return rc; }
@@ -140,9 +142,11 @@ int fdl_net_create(const char* tflite_file, int device, fdl_net** out) {
   }
   *out = h;
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 void fdl_net_destroy(fdl_net* h) {
   if (!h) return;
+  DeviceGuard _device_guard;
+  if (h->net && h->net->device() >= 0) cudaSetDevice(h->net->device());
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   if (h->owned) delete h->net;
   delete h;
@@ -151,16 +155,19 @@ fdl_net* fdl_detector_net(fdl_detector* d) { return d ? &d->nh : nullptr; }
 fdl_net* fdl_landmark_net(fdl_landmark_model* m) { return m ? &m->nh : nullptr; }
 fdl_net* fdl_iris_net(fdl_iris_model* m) { return m ? &m->nh : nullptr; }
 int fdl_net_num_outputs(const fdl_net* h) { return h && h->net ? h->net->num_outputs() : 0; }
-int64_t fdl_net_io_elems(const fdl_net* h, int i) {
+int64_t fdl_net_io_elems(const fdl_net* h, int i) try {
+  DeviceGuard _device_guard;
   if (!h || !h->net) return 0;
   if (i < 0) return h->net->in_elems();
   return i < h->net->num_outputs() ? h->net->out_elems(i) : 0;
-}
-int fdl_net_forward(fdl_net* h, const float* in, int batch, float* const* outs, int n_outs) {
+} FDL_ABI_CATCH
+int fdl_net_forward(fdl_net* h, const float* in, int batch, float* const* outs, int n_outs) try {
+  DeviceGuard _device_guard;
   if (!h || !h->net) return set_error(FDL_ERR_INVALID, "null handle");
   return net_forward_host(h->net, h->stream, in, batch, outs, n_outs);
-}
-int64_t fdl_net_describe(const fdl_net* h, char* buf, int64_t cap) {
+} FDL_ABI_CATCH
+int64_t fdl_net_describe(const fdl_net* h, char* buf, int64_t cap) try {
+  DeviceGuard _device_guard;
   if (!h || !h->net) return 0;
   std::string s = h->net->plan().describe();
   if (buf && cap > 0) {
@@ -169,15 +176,17 @@ int64_t fdl_net_describe(const fdl_net* h, char* buf, int64_t cap) {
     buf[n] = 0;
   }
   return (int64_t)s.size() + 1;
-}
+} FDL_ABI_CATCH
 int fdl_net_num_steps(const fdl_net* h) { return h && h->net ? (int)h->net->plan().steps.size() : 0; }
-int fdl_net_set_mode(fdl_net* h, int mode) {
+int fdl_net_set_mode(fdl_net* h, int mode) try {
+  DeviceGuard _device_guard;
   if (!h || !h->net) return set_error(FDL_ERR_INVALID, "null handle");
   if (mode < 0 || mode > 2) return set_error(FDL_ERR_INVALID, "mode must be 0 (fp32), 1 (split-TF32 tensor cores) or 2 (same, serial BlazeBlock kernel only)");
   h->net->set_mode(mode);
   return FDL_OK;
-}
-int fdl_net_time_forward(fdl_net* h, const float* in, int batch, int iters, float* ms_per_pass) {
+} FDL_ABI_CATCH
+int fdl_net_time_forward(fdl_net* h, const float* in, int batch, int iters, float* ms_per_pass) try {
+  DeviceGuard _device_guard;
   if (!h || !h->net || batch <= 0 || iters <= 0 || !ms_per_pass) return set_error(FDL_ERR_INVALID, "bad arguments");
   Net* net = h->net;
   std::string err;
@@ -187,21 +196,21 @@ int fdl_net_time_forward(fdl_net* h, const float* in, int batch, int iters, floa
   TView iv = net->input_view(batch);
   if (in) FDL_CUDA_TRY(cudaMemcpyAsync(iv.p, in, (size_t)batch * net->in_elems() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   FDL_CUDA_TRY(net->forward(batch, h->stream));  // warm-up
-  cudaEvent_t e0, e1;
-  FDL_CUDA_TRY(cudaEventCreate(&e0));
-  FDL_CUDA_TRY(cudaEventCreate(&e1));
+  EventSet evs;
+  FDL_CUDA_TRY(evs.create(2));
+  cudaEvent_t e0 = evs.ev[0], e1 = evs.ev[1];
   FDL_CUDA_TRY(cudaEventRecord(e0, h->stream));
   for (int i = 0; i < iters; ++i) FDL_CUDA_TRY(net->forward(batch, h->stream));
   FDL_CUDA_TRY(cudaEventRecord(e1, h->stream));
   FDL_CUDA_TRY(cudaEventSynchronize(e1));
   float ms = 0.f;
   FDL_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   *ms_per_pass = ms / (float)iters;
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
-int fdl_net_time_steps(fdl_net* h, const float* in, int batch, int iters, float* ms_per_step, int cap) {
+int fdl_net_time_steps(fdl_net* h, const float* in, int batch, int iters, float* ms_per_step, int cap) try {
+  DeviceGuard _device_guard;
   if (!h || !h->net || batch <= 0 || iters <= 0 || !ms_per_step) return set_error(FDL_ERR_INVALID, "bad arguments");
   Net* net = h->net;
   const int n = (int)net->plan().steps.size();
@@ -213,11 +222,12 @@ int fdl_net_time_steps(fdl_net* h, const float* in, int batch, int iters, float*
   TView iv = net->input_view(batch);
   if (in) FDL_CUDA_TRY(cudaMemcpyAsync(iv.p, in, (size_t)batch * net->in_elems() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   FDL_CUDA_TRY(net->forward(batch, h->stream));  // warm-up
-  std::vector<cudaEvent_t> ev((size_t)n + 1);
-  for (auto& e : ev) FDL_CUDA_TRY(cudaEventCreate(&e));
+  EventSet evs;
+  FDL_CUDA_TRY(evs.create(n + 1));
+  cudaEvent_t* ev = evs.ev;
   for (int i = 0; i < n; ++i) ms_per_step[i] = 0.f;
   for (int it = 0; it < iters; ++it) {
-    FDL_CUDA_TRY(net->forward(batch, h->stream, nullptr, nullptr, ev.data()));
+    FDL_CUDA_TRY(net->forward(batch, h->stream, nullptr, nullptr, ev));
     FDL_CUDA_TRY(cudaEventSynchronize(ev[n]));
     for (int i = 0; i < n; ++i) {
       float ms = 0.f;
@@ -225,12 +235,12 @@ int fdl_net_time_steps(fdl_net* h, const float* in, int batch, int iters, float*
       ms_per_step[i] += ms / (float)iters;
     }
   }
-  for (auto& e : ev) cudaEventDestroy(e);
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
 // ------------------------------------------------------------------------------------- detector
-int fdl_detector_create(int model, const char* model_dir, int device, fdl_detector** out) {
+int fdl_detector_create(int model, const char* model_dir, int device, fdl_detector** out) try {
+  DeviceGuard _device_guard;
   if (!out) return set_error(FDL_ERR_INVALID, "null argument");
   *out = nullptr;
   const char* file = detector_file(model);
@@ -259,9 +269,10 @@ int fdl_detector_create(int model, const char* model_dir, int device, fdl_detect
   d->nh.stream = d->stream;
   *out = d;
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 void fdl_detector_destroy(fdl_detector* d) {
   if (!d) return;
+  DeviceGuard _device_guard;
   cudaSetDevice(d->device);
   if (d->stream) { cudaStreamSynchronize(d->stream); cudaStreamDestroy(d->stream); }
   delete d->nh.net;
@@ -269,13 +280,14 @@ void fdl_detector_destroy(fdl_detector* d) {
 }
 int fdl_detector_input_size(const fdl_detector* d) { return d ? d->S : 0; }
 int fdl_detector_num_anchors(const fdl_detector* d) { return d ? d->N : 0; }
-int fdl_detector_anchors(const fdl_detector* d, float* out_xy, int cap_anchors) {
+int fdl_detector_anchors(const fdl_detector* d, float* out_xy, int cap_anchors) try {
+  DeviceGuard _device_guard;
   if (!d || !out_xy) return set_error(FDL_ERR_INVALID, "null argument");
   if (cap_anchors < d->N) return set_error(FDL_ERR_CAPACITY, "anchor buffer too small");
   FDL_CUDA_TRY(cudaSetDevice(d->device));
   FDL_CUDA_TRY(cudaMemcpy(out_xy, d->anchors.p, (size_t)d->N * 2 * sizeof(float), cudaMemcpyDeviceToHost));
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
 // shared tail: SSD post-processing on device tensors + copy-out
 static int detector_post(fdl_detector* d, const float* reg, long long reg_bs, const float* cls, long long cls_bs, int batch,
@@ -344,23 +356,37 @@ static int detector_infer_impl(fdl_detector* d, const fdl_image* images, int bat
                           nullptr, d->stream, 1, w));
   FDL_CUDA_TRY(net->forward(batch, d->stream));
   TView reg = net->output_view(0, batch), cls = net->output_view(1, batch);
-  return detector_post(d, reg.p, reg.bstride, cls.p, cls.bstride, batch, d->params.p, nullptr, out, cap, n_out, nullptr, nullptr, 0, nullptr);
+  // a caller ROI of zero / negative size (or a singular transform) leaves an all-zero tensor behind: the reference errors there
+  // (OpenCV throws; detection_letterbox_removal asserts its scales, transform.rs:121-122), so read the setup kernel's verdict back
+  std::vector<I2TParams> hp((size_t)batch);
+  FDL_CUDA_TRY(cudaMemcpyAsync(hp.data(), d->params.p, hp.size() * sizeof(I2TParams), cudaMemcpyDeviceToHost, d->stream));
+  rc = detector_post(d, reg.p, reg.bstride, cls.p, cls.bstride, batch, d->params.p, nullptr, out, cap, n_out, nullptr, nullptr, 0, nullptr);
+  for (int b = 0; b < batch; ++b) {
+    if (!hp[(size_t)b].valid) return set_error(FDL_ERR_INVALID, "degenerate ROI: perspective transform is singular or empty");
+    if (!(1.0 - (hp[(size_t)b].pad[0] + hp[(size_t)b].pad[2]) > 2.220446049250313e-16) || !(1.0 - (hp[(size_t)b].pad[1] + hp[(size_t)b].pad[3]) > 2.220446049250313e-16))
+      return set_error(FDL_ERR_INVALID, "letterbox scale is too small");
+  }
+  return rc;
 }
 
-int fdl_detector_infer(fdl_detector* d, const fdl_image* image, const fdl_rect* roi, fdl_detection* out, int cap, int* n_out) {
+int fdl_detector_infer(fdl_detector* d, const fdl_image* image, const fdl_rect* roi, fdl_detection* out, int cap, int* n_out) try {
+  DeviceGuard _device_guard;
   return detector_infer_impl(d, image, 1, roi, out, cap, n_out);
-}
-int fdl_detector_infer_batch(fdl_detector* d, const fdl_image* images, int batch, fdl_detection* out, int cap_per_image, int* n_out) {
+} FDL_ABI_CATCH
+int fdl_detector_infer_batch(fdl_detector* d, const fdl_image* images, int batch, fdl_detection* out, int cap_per_image, int* n_out) try {
+  DeviceGuard _device_guard;
   return detector_infer_impl(d, images, batch, nullptr, out, cap_per_image, n_out);
-}
-int fdl_detector_forward(fdl_detector* d, const float* in, int batch, float* regressors, float* classificators) {
+} FDL_ABI_CATCH
+int fdl_detector_forward(fdl_detector* d, const float* in, int batch, float* regressors, float* classificators) try {
+  DeviceGuard _device_guard;
   if (!d) return set_error(FDL_ERR_INVALID, "null handle");
   float* outs[2] = {regressors, classificators};
   return net_forward_host(d->nh.net, d->stream, in, batch, outs, 2);
-}
+} FDL_ABI_CATCH
 int fdl_detector_postprocess(fdl_detector* d, const float* regressors, const float* classificators, int batch, const double* padding4,
                              fdl_detection* out, int cap_per_image, int* n_out, int32_t* survivor_anchor, int32_t* survivor_cluster,
-                             int cap_surv, int* n_surv) {
+                             int cap_surv, int* n_surv) try {
+  DeviceGuard _device_guard;
   if (!d || !regressors || !classificators || batch <= 0 || !n_out) return set_error(FDL_ERR_INVALID, "bad arguments");
   FDL_CUDA_TRY(cudaSetDevice(d->device));
   FDL_CUDA_TRY(d->raw_reg.reserve((size_t)batch * d->N * 16));
@@ -369,16 +395,23 @@ int fdl_detector_postprocess(fdl_detector* d, const float* regressors, const flo
   FDL_CUDA_TRY(cudaMemcpyAsync(d->raw_cls.p, classificators, (size_t)batch * d->N * sizeof(float), cudaMemcpyHostToDevice, d->stream));
   const double* d_pad = nullptr;
   if (padding4) {
+    // detection_letterbox_removal asserts both scales > f64::EPSILON (transform.rs:121-122)
+    for (int b = 0; b < batch; ++b) {
+      const double* q = padding4 + 4 * (size_t)b;
+      if (!(1.0 - (q[0] + q[2]) > 2.220446049250313e-16)) return set_error(FDL_ERR_INVALID, "Horizontal scale is too small");
+      if (!(1.0 - (q[1] + q[3]) > 2.220446049250313e-16)) return set_error(FDL_ERR_INVALID, "Vertical scale is too small");
+    }
     FDL_CUDA_TRY(d->padding.reserve((size_t)batch * 4));
     FDL_CUDA_TRY(cudaMemcpyAsync(d->padding.p, padding4, (size_t)batch * 4 * sizeof(double), cudaMemcpyHostToDevice, d->stream));
     d_pad = d->padding.p;
   }
   return detector_post(d, d->raw_reg.p, (long long)d->N * 16, d->raw_cls.p, d->N, batch, nullptr, d_pad, out, cap_per_image, n_out,
                        survivor_anchor, survivor_cluster, cap_surv, n_surv);
-}
+} FDL_ABI_CATCH
 
 // ------------------------------------------------------------------------------------- landmark
-int fdl_landmark_create(const char* model_file, int device, fdl_landmark_model** out) {
+int fdl_landmark_create(const char* model_file, int device, fdl_landmark_model** out) try {
+  DeviceGuard _device_guard;
   if (!out) return set_error(FDL_ERR_INVALID, "null argument");
   *out = nullptr;
   int rc = check_device(device);
@@ -398,9 +431,10 @@ int fdl_landmark_create(const char* model_file, int device, fdl_landmark_model**
   m->nh.stream = m->stream;
   *out = m;
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 void fdl_landmark_destroy(fdl_landmark_model* m) {
   if (!m) return;
+  DeviceGuard _device_guard;
   cudaSetDevice(m->device);
   if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
   delete m->nh.net;
@@ -413,7 +447,8 @@ __global__ void flag_gate_kernel(const float* flag, int* has) {
 }
 
 int fdl_landmark_infer(fdl_landmark_model* m, const fdl_image* image, const fdl_rect* roi, fdl_landmark* out, int* n_out,
-                       float* face_flag_logit) {
+                       float* face_flag_logit) try {
+  DeviceGuard _device_guard;
   if (!m || !image || !out || !n_out) return set_error(FDL_ERR_INVALID, "bad arguments");
   FDL_CUDA_TRY(cudaSetDevice(m->device));
   int w, h;
@@ -458,15 +493,17 @@ int fdl_landmark_infer(fdl_landmark_model* m, const fdl_image* image, const fdl_
   for (int k = 0; k < FDL_NUM_FACE_LANDMARKS; ++k) { out[k].x = pts[3 * k]; out[k].y = pts[3 * k + 1]; out[k].z = pts[3 * k + 2]; }
   *n_out = FDL_NUM_FACE_LANDMARKS;
   return FDL_OK;
-}
-int fdl_landmark_forward(fdl_landmark_model* m, const float* in, int batch, float* landmarks, float* flag) {
+} FDL_ABI_CATCH
+int fdl_landmark_forward(fdl_landmark_model* m, const float* in, int batch, float* landmarks, float* flag) try {
+  DeviceGuard _device_guard;
   if (!m) return set_error(FDL_ERR_INVALID, "null handle");
   float* outs[2] = {landmarks, flag};
   return net_forward_host(m->nh.net, m->stream, in, batch, outs, 2);
-}
+} FDL_ABI_CATCH
 
 // ----------------------------------------------------------------------------------------- iris
-int fdl_iris_create(const char* model_file, int device, fdl_iris_model** out) {
+int fdl_iris_create(const char* model_file, int device, fdl_iris_model** out) try {
+  DeviceGuard _device_guard;
   if (!out) return set_error(FDL_ERR_INVALID, "null argument");
   *out = nullptr;
   int rc = check_device(device);
@@ -487,16 +524,18 @@ int fdl_iris_create(const char* model_file, int device, fdl_iris_model** out) {
   m->nh.stream = m->stream;
   *out = m;
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 void fdl_iris_destroy(fdl_iris_model* m) {
   if (!m) return;
+  DeviceGuard _device_guard;
   cudaSetDevice(m->device);
   if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
   delete m->nh.net;
   delete m;
 }
 int fdl_iris_infer(fdl_iris_model* m, const fdl_image* image, const fdl_rect* roi, int is_right_eye, fdl_landmark* contour,
-                   fdl_landmark* iris) {
+                   fdl_landmark* iris) try {
+  DeviceGuard _device_guard;
   if (!m || !image || !contour || !iris) return set_error(FDL_ERR_INVALID, "bad arguments");
   FDL_CUDA_TRY(cudaSetDevice(m->device));
   int w, h;
@@ -539,12 +578,13 @@ int fdl_iris_infer(fdl_iris_model* m, const fdl_image* image, const fdl_rect* ro
     iris[k].x = q[0]; iris[k].y = q[1]; iris[k].z = q[2];
   }
   return FDL_OK;
-}
-int fdl_iris_forward(fdl_iris_model* m, const float* in, int batch, float* contours, float* iris) {
+} FDL_ABI_CATCH
+int fdl_iris_forward(fdl_iris_model* m, const float* in, int batch, float* contours, float* iris) try {
+  DeviceGuard _device_guard;
   if (!m) return set_error(FDL_ERR_INVALID, "null handle");
   float* outs[2] = {contours, iris};
   return net_forward_host(m->nh.net, m->stream, in, batch, outs, 2);
-}
+} FDL_ABI_CATCH
 
 // ------------------------------------------------------------------------------- free functions
 // Small per-call scratch; the work itself is one thread on the device (same code as the pipeline).
@@ -561,7 +601,8 @@ struct Scratch {
   }
 };
 
-int fdl_face_detection_to_roi(int device, const fdl_detection* det, int image_width, int image_height, int size_mode, fdl_rect* out) {
+int fdl_face_detection_to_roi(int device, const fdl_detection* det, int image_width, int image_height, int size_mode, fdl_rect* out) try {
+  DeviceGuard _device_guard;
   if (!det || !out) return set_error(FDL_ERR_INVALID, "null argument");
   if (size_mode < FDL_SIZE_MODE_NONE || size_mode > FDL_SIZE_MODE_SQUARE_SHORT) return set_error(FDL_ERR_INVALID, "bad size mode");
   int rc = check_device(device);
@@ -580,10 +621,11 @@ int fdl_face_detection_to_roi(int device, const fdl_detection* det, int image_wi
   if (e != cudaSuccess) return set_error(FDL_ERR_CUDA, cudaGetErrorString(e));
   if (!ok) return set_error(FDL_ERR_INVALID, "bbox must be normalized");   // transform.rs:52
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
 int fdl_iris_roi_from_face_landmarks(int device, const fdl_landmark* landmarks, int n, int image_width, int image_height, fdl_rect* left,
-                                     fdl_rect* right) {
+                                     fdl_rect* right) try {
+  DeviceGuard _device_guard;
   if (!landmarks || !left || !right) return set_error(FDL_ERR_INVALID, "null argument");
   if (n <= 362) return set_error(FDL_ERR_INVALID, "landmarks must contain the 468 face landmarks (indices 33,133,362,263 are read)");
   int rc = check_device(device);
@@ -606,10 +648,11 @@ int fdl_iris_roi_from_face_landmarks(int device, const fdl_landmark* landmarks, 
   if (!ok) return set_error(FDL_ERR_INVALID, "bbox must be normalized");
   *left = r[0]; *right = r[1];
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
 int fdl_update_face_landmarks_with_iris_results(int device, const fdl_landmark* face_landmarks, int n, const fdl_landmark* left_contour, int n_left,
-                                                const fdl_landmark* right_contour, int n_right, fdl_landmark* refined) {
+                                                const fdl_landmark* right_contour, int n_right, fdl_landmark* refined) try {
+  DeviceGuard _device_guard;
   if (!face_landmarks || !refined || (n_left > 0 && !left_contour) || (n_right > 0 && !right_contour)) return set_error(FDL_ERR_INVALID, "null argument");
   if (n != FDL_NUM_FACE_LANDMARKS) return set_error(FDL_ERR_INVALID, "unexpected number of items in face_landmarks");   // iris_landmark.rs:383-385
   if (n_left < 0 || n_left > FDL_NUM_EYE_CONTOUR || n_right < 0 || n_right > FDL_NUM_EYE_CONTOUR)
@@ -627,13 +670,14 @@ int fdl_update_face_landmarks_with_iris_results(int device, const fdl_landmark* 
   FDL_CUDA_TRY(launch_refine_landmarks(d_face, d_left, n_left, d_right, n_right, d_out, 0));
   FDL_CUDA_TRY(cudaMemcpy(refined, d_out, nf * sizeof(double), cudaMemcpyDeviceToHost));
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
-int fdl_eye_to_face_landmark_index(int is_right_eye, int32_t* out71) {
+int fdl_eye_to_face_landmark_index(int is_right_eye, int32_t* out71) try {
+  DeviceGuard _device_guard;
   if (!out71) return set_error(FDL_ERR_INVALID, "null argument");
   for (int k = 0; k < FDL_NUM_EYE_CONTOUR; ++k) out71[k] = eye_to_face_landmark_index(is_right_eye ? 1 : 0, k);
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
 static int iris_metrics(int device, const fdl_landmark* iris, int n, double focal_length_mm, double iris_size_px, int w, int h, double* out2) {
   if (!iris) return set_error(FDL_ERR_INVALID, "null argument");
@@ -649,17 +693,19 @@ static int iris_metrics(int device, const fdl_landmark* iris, int n, double foca
   return FDL_OK;
 }
 
-int fdl_iris_diameter(int device, const fdl_landmark* iris, int n, int image_width, int image_height, double* diameter_px) {
+int fdl_iris_diameter(int device, const fdl_landmark* iris, int n, int image_width, int image_height, double* diameter_px) try {
+  DeviceGuard _device_guard;
   if (!diameter_px) return set_error(FDL_ERR_INVALID, "null argument");
   double o[2];
   int rc = iris_metrics(device, iris, n, 0.0, 0.0, image_width, image_height, o);
   if (rc) return rc;
   *diameter_px = o[0];
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
 int fdl_iris_depth(int device, const fdl_landmark* iris, int n, double focal_length_mm, double iris_size_px, int image_width, int image_height,
-                   double* depth_mm) {
+                   double* depth_mm) try {
+  DeviceGuard _device_guard;
   if (!depth_mm) return set_error(FDL_ERR_INVALID, "null argument");
   if (!(iris_size_px > 0.0)) return set_error(FDL_ERR_INVALID, "iris_size_px must be positive");
   double o[2];
@@ -667,10 +713,11 @@ int fdl_iris_depth(int device, const fdl_landmark* iris, int n, double focal_len
   if (rc) return rc;
   *depth_mm = o[1];
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
 int fdl_image_to_tensor(int device, const fdl_image* image, const fdl_rect* roi, int out_w, int out_h, int keep_aspect_ratio,
-                        double range_min, double range_max, int flip_horizontal, float* out_tensor, uint8_t* out_u8, double* padding4) {
+                        double range_min, double range_max, int flip_horizontal, float* out_tensor, uint8_t* out_u8, double* padding4) try {
+  DeviceGuard _device_guard;
   if (!image || !out_tensor || out_w <= 0 || out_h <= 0) return set_error(FDL_ERR_INVALID, "bad arguments");
   if (keep_aspect_ratio && out_w != out_h)
     return set_error(FDL_ERR_INVALID, "keep_aspect_ratio requires a square output (the reference divides the sizes as integers, transform.rs:240)");
@@ -700,10 +747,11 @@ int fdl_image_to_tensor(int device, const fdl_image* image, const fdl_rect* roi,
   if (!P.valid) return set_error(FDL_ERR_INVALID, "degenerate ROI: perspective transform is singular or empty");
   if (padding4) for (int i = 0; i < 4; ++i) padding4[i] = P.pad[i];
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
 int fdl_project_landmarks(int device, const float* raw, int n, int tensor_w, int tensor_h, int image_w, int image_h, const double* padding4,
-                          const fdl_rect* roi, int flip_horizontal, fdl_landmark* out) {
+                          const fdl_rect* roi, int flip_horizontal, fdl_landmark* out) try {
+  DeviceGuard _device_guard;
   if (!raw || !out || n <= 0 || !padding4) return set_error(FDL_ERR_INVALID, "bad arguments");
   int rc = check_device(device);
   if (rc) return rc;
@@ -722,6 +770,6 @@ int fdl_project_landmarks(int device, const float* raw, int n, int tensor_w, int
   FDL_CUDA_TRY(cudaMemcpy(pts.data(), d_out.p, pts.size() * sizeof(float), cudaMemcpyDeviceToHost));
   for (int k = 0; k < n; ++k) { out[k].x = pts[3 * k]; out[k].y = pts[3 * k + 1]; out[k].z = pts[3 * k + 2]; }
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
 }  // extern "C"

@@ -1,5 +1,7 @@
 // fdl_status.h -- error plumbing shared by the C-ABI translation units.
 #pragma once
+#include <new>
+#include <exception>
 #include <string>
 
 #include "../../include/fdl.h"
@@ -15,3 +17,9 @@ void clear_error();
     cudaError_t _e = (expr);                                                                           \
     if (_e != cudaSuccess) return ::fdl::set_error(FDL_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(_e) + " at " #expr); \
   } while (0)
+
+// Nothing throws across the C ABI (include/fdl.h): every extern "C" entry point is a function-try-block ending in this handler.
+#define FDL_ABI_CATCH                                                                                   \
+  catch (const std::bad_alloc&) { return ::fdl::set_error(FDL_ERR_INTERNAL, "out of host memory"); }    \
+  catch (const std::exception& e) { return ::fdl::set_error(FDL_ERR_INTERNAL, std::string("internal error: ") + e.what()); } \
+  catch (...) { return ::fdl::set_error(FDL_ERR_INTERNAL, "internal error"); }

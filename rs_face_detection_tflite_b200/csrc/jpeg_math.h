@@ -110,17 +110,32 @@ struct JpegHuff {
   uint8_t huffval[256];
 };
 
-// counts[16] / symbols as in a DHT segment
+// A DHT segment is usable when its code lengths describe a prefix code (no length over-subscribed: T.81 Annex C generates
+// codes by counting, so `code` must stay below 2^l at every length) with at most 256 symbols.  libjpeg's jpeg_make_d_derived_tbl
+// rejects the same tables ("Bogus Huffman table definition").
+FDL_JHD bool jpeg_huff_valid(const uint8_t* counts) {
+  int code = 0, k = 0;
+  for (int l = 1; l <= 16; ++l) {
+    code += counts[l - 1];
+    k += counts[l - 1];
+    if (code > (1 << l)) return false;
+    code <<= 1;
+  }
+  return k <= 256;
+}
+
+// counts[16] / symbols as in a DHT segment (callers check jpeg_huff_valid first; an invalid table is still built without
+// writing out of bounds)
 FDL_JHD void jpeg_huff_build(const uint8_t* counts, const uint8_t* symbols, JpegHuff* t) {
   for (int i = 0; i < 512; ++i) t->look[i] = 0;
   int code = 0, k = 0;
   for (int l = 1; l <= 16; ++l) {
     t->valoffset[l] = k - code;
-    for (int i = 0; i < counts[l - 1]; ++i, ++k, ++code) {
+    for (int i = 0; i < counts[l - 1] && k < 256; ++i, ++k, ++code) {
       t->huffval[k] = symbols[k];
       if (l <= 9) {
         const int lo = code << (9 - l);
-        for (int j = 0; j < (1 << (9 - l)); ++j) t->look[lo + j] = (uint16_t)((l << 8) | symbols[k]);
+        for (int j = 0; j < (1 << (9 - l)) && lo + j < 512; ++j) t->look[lo + j] = (uint16_t)((l << 8) | symbols[k]);
       }
     }
     t->maxcode[l] = counts[l - 1] ? code - 1 : -1;
@@ -176,7 +191,8 @@ FDL_JHD int jpeg_extend(int v, int t) { return v < (1 << (t - 1)) ? v - (1 << t)
 FDL_JHD void jpeg_decode_block(JpegBits* b, const JpegHuff& dc, const JpegHuff& ac, int* pred, int16_t* coef) {
   const uint8_t zz[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
                           35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
-  const int t = jpeg_huff_decode(b, dc);
+  int t = jpeg_huff_decode(b, dc);
+  if (t > 16) t = 16;                                  // corrupt table symbol: the same clamp as jpeg_sync_step (no over-wide shifts)
   if (t) *pred += jpeg_extend(jpeg_bits_get(b, t), t);
   coef[0] = (int16_t)*pred;
   for (int k = 1; k < 64;) {

@@ -89,6 +89,7 @@ inline bool jpeg_parse_header(const uint8_t* d, size_t n, JpegHeader* h, std::st
         size_t nsym = 0;
         for (int i = 0; i < 16; ++i) nsym += s[q + 1 + i];
         if (nsym > 256 || q + 17 + nsym > sl) return fail("bad DHT");
+        if (!jpeg_huff_valid(s + q + 1)) return fail("bad DHT: code lengths over-subscribed");
         std::memset(h->dht[tc][th], 0, sizeof(h->dht[tc][th]));
         std::memcpy(h->dht[tc][th], s + q + 1, 16 + nsym);
         h->have_dht[tc][th] = true;

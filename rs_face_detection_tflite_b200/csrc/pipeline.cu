@@ -133,6 +133,7 @@ struct fdl_pipeline {
 
 static void pipeline_free(fdl_pipeline* p) {
   if (!p) return;
+  DeviceGuard _device_guard;
   cudaSetDevice(p->cfg.device);
   cudaDeviceSynchronize();
   for (auto& l : p->lanes) {
@@ -148,7 +149,8 @@ static void pipeline_free(fdl_pipeline* p) {
 
 extern "C" {
 
-int fdl_pipeline_create(const fdl_pipeline_config* cfg, fdl_pipeline** out) {
+int fdl_pipeline_create(const fdl_pipeline_config* cfg, fdl_pipeline** out) try {
+  DeviceGuard _device_guard;
   if (!cfg || !out) return set_error(FDL_ERR_INVALID, "null argument");
   *out = nullptr;
   if (cfg->max_batch <= 0 || cfg->max_faces <= 0 || cfg->max_faces > FDL_MAX_DETECTIONS || cfg->frame_width <= 0 || cfg->frame_height <= 0)
@@ -242,12 +244,13 @@ int fdl_pipeline_create(const fdl_pipeline_config* cfg, fdl_pipeline** out) {
   if (e != cudaSuccess) return bail(FDL_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
   *out = p;
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
 void fdl_pipeline_destroy(fdl_pipeline* p) { pipeline_free(p); }
 int fdl_pipeline_depth(const fdl_pipeline*) { return kDepth; }
 
-int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ticket) {
+int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ticket) try {
+  DeviceGuard _device_guard;
   if (!p || !frames || !ticket) return set_error(FDL_ERR_INVALID, "null argument");
   if (n <= 0 || n > p->cfg.max_batch) return set_error(FDL_ERR_INVALID, "batch size out of range (1..max_batch)");
   FDL_CUDA_TRY(cudaSetDevice(p->cfg.device));
@@ -303,6 +306,9 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
     a.ndet_base = reinterpret_cast<char*>(lane->d_frames.p) + offsetof(fdl_frame_result, n_detections);
     a.ndet_stride = sizeof(fdl_frame_result);
     a.max_out = FDL_MAX_DETECTIONS;
+    static_assert(sizeof(fdl_frame_result) % sizeof(int) == 0 && offsetof(fdl_frame_result, n_total_detections) % sizeof(int) == 0, "int-strided counters");
+    a.n_total = reinterpret_cast<int*>(reinterpret_cast<char*>(lane->d_frames.p) + offsetof(fdl_frame_result, n_total_detections));
+    a.n_total_stride = sizeof(fdl_frame_result) / sizeof(int);
     FDL_CUDA_TRY(launch_ssd_postprocess(a, cs));
   }
   FDL_CUDA_TRY(cudaEventRecord(p->guard[0], cs));
@@ -379,9 +385,10 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
   lane->ticket = p->next_ticket++;
   *ticket = lane->ticket;
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
-int fdl_pipeline_collect(fdl_pipeline* p, int ticket, fdl_frame_result* frame_results, fdl_face_result* face_results, int* n_out) {
+int fdl_pipeline_collect(fdl_pipeline* p, int ticket, fdl_frame_result* frame_results, fdl_face_result* face_results, int* n_out) try {
+  DeviceGuard _device_guard;
   if (!p) return set_error(FDL_ERR_INVALID, "null argument");
   Lane* lane = nullptr;
   for (auto& l : p->lanes) if (l.busy && l.ticket == ticket) { lane = &l; break; }
@@ -401,17 +408,24 @@ int fdl_pipeline_collect(fdl_pipeline* p, int ticket, fdl_frame_result* frame_re
   cudaEventElapsedTime(&p->stage_ms[9], lane->ev_stage[8], lane->ev_done);
   cudaEventElapsedTime(&p->last_device_ms, lane->ev_stage[0], lane->ev_stage[8]);
   lane->busy = false;
+  // the reference returns every detection (an unbounded Vec, face_detection.rs:267); a truncated record is reported, not hidden
+  for (int i = 0; i < n; ++i)
+    if (lane->h_frames.p[i].n_total_detections > FDL_MAX_DETECTIONS)
+      return set_error(FDL_ERR_CAPACITY, "frame " + std::to_string(i) + " produced " + std::to_string(lane->h_frames.p[i].n_total_detections) +
+                                             " detections: only the first FDL_MAX_DETECTIONS (32, in NMS order) are in its record");
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
-int fdl_pipeline_run(fdl_pipeline* p, const fdl_image* frames, int n, fdl_frame_result* frame_results, fdl_face_result* face_results) {
+int fdl_pipeline_run(fdl_pipeline* p, const fdl_image* frames, int n, fdl_frame_result* frame_results, fdl_face_result* face_results) try {
+  DeviceGuard _device_guard;
   int ticket = -1;
   int rc = fdl_pipeline_submit(p, frames, n, &ticket);
   if (rc) return rc;
   return fdl_pipeline_collect(p, ticket, frame_results, face_results, nullptr);
-}
+} FDL_ABI_CATCH
 
-int fdl_letterbox_row_plan(int frame_width, int frame_height, int input_size, int32_t* row_pos, int32_t* info4) {
+int fdl_letterbox_row_plan(int frame_width, int frame_height, int input_size, int32_t* row_pos, int32_t* info4) try {
+  DeviceGuard _device_guard;
   if (frame_width <= 0 || frame_height <= 0 || input_size <= 0) return set_error(FDL_ERR_INVALID, "bad arguments");
   RowGather g;
   std::vector<int> rp;
@@ -422,15 +436,16 @@ int fdl_letterbox_row_plan(int frame_width, int frame_height, int input_size, in
   if (row_pos) for (int i = 0; i < frame_height; ++i) row_pos[i] = rp[(size_t)i];
   if (info4) { info4[0] = g.rows_per_frame; info4[1] = g.period_src_rows; info4[2] = g.periods_per_frame; info4[3] = (int)g.fam.size(); }
   return 1;
-}
+} FDL_ABI_CATCH
 
 float fdl_pipeline_last_device_ms(const fdl_pipeline* p) { return p ? p->last_device_ms : 0.f; }
-int fdl_pipeline_stage_ms(const fdl_pipeline* p, float* out10) {
+int fdl_pipeline_stage_ms(const fdl_pipeline* p, float* out10) try {
+  DeviceGuard _device_guard;
   if (!p || !out10) return set_error(FDL_ERR_INVALID, "null argument");
   // [0] H2D, [1] detector preprocess, [2] detector net, [3] SSD post, [4] face ROI + warp, [5] landmark net,
   // [6] landmark post + eye warp, [7] iris net, [8] iris post, [9] D2H
   for (int i = 0; i < kStages; ++i) out10[i] = p->stage_ms[i];
   return FDL_OK;
-}
+} FDL_ABI_CATCH
 
 }  // extern "C"

@@ -77,6 +77,8 @@ struct Builder {
     for (size_t i = 0; i < m.ops.size(); ++i) {
       const TfOp& op = m.ops[i];
       if (op.outputs.size() != 1) return fail("op with != 1 output is unsupported");
+      // TFLite marks an omitted optional input with -1; none of the supported graphs has one, and the planner indexes by input
+      for (int t : op.inputs) if (t < 0) return fail("operator with an omitted optional input (-1) is unsupported");
       if (producer[op.outputs[0]] != -1) return fail("tensor produced twice");
       producer[op.outputs[0]] = (int)i;
       for (int t : op.inputs) if (t >= 0 && !is_const[t]) consumers[t].push_back((int)i);

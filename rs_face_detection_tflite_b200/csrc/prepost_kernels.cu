@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(kPostThreads) ssd_postprocess_kernel(const Ssd
   }
   if (tid == 0) {
     *reinterpret_cast<int32_t*>(a.ndet_base + (long long)b * a.ndet_stride) = min(n_out, a.max_out);
-    if (a.n_total) a.n_total[b] = n_out;
+    if (a.n_total) a.n_total[(long long)b * a.n_total_stride] = n_out;
   }
 }
 

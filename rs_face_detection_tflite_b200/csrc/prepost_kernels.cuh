@@ -55,7 +55,7 @@ struct SsdPostArgs {
   char* det_base = nullptr; long long det_stride = 0;      // frame b: fdl_detection[max_out] at det_base + b*det_stride
   char* ndet_base = nullptr; long long ndet_stride = 0;    // frame b: int32 count (clamped to max_out) at ndet_base + b*ndet_stride
   int max_out = FDL_MAX_DETECTIONS;
-  int* n_total = nullptr;                                  // [B] optional: number of clusters before the max_out cap
+  int* n_total = nullptr; long long n_total_stride = 1;    // optional: frame b's number of clusters before the max_out cap at n_total[b*n_total_stride]
   int32_t* surv_anchor = nullptr; int32_t* surv_cluster = nullptr; int cap_surv = 0; int* n_surv = nullptr;  // optional debug outputs
 };
 cudaError_t launch_ssd_postprocess(const SsdPostArgs& a, cudaStream_t s);

@@ -170,6 +170,17 @@ bool TfModel::load(const std::string& path, std::string* err) {
     tt.buffer = fb.scalar<uint32_t>(t, 2, 0);
     tt.name = fb.str(t, 3);
     tt.has_sparsity = fb.field(t, 6) != 0;
+    // sizes that come from the file reach std::vector and the arena planner: every dimension must be positive and the element
+    // count bounded (the largest tensor of the shipped graphs has 3.1 M elements)
+    {
+      int64_t total = 1;
+      for (int d : tt.shape) {
+        if (d <= 0 || d > (1 << 24)) { *err = "malformed model: tensor '" + tt.name + "' has a non-positive or oversized dimension: " + path; return false; }
+        total *= d;
+        if (total > (int64_t)1 << 31) { *err = "malformed model: tensor '" + tt.name + "' is too large: " + path; return false; }
+      }
+      if (tt.shape.size() > 8) { *err = "malformed model: tensor rank > 8: " + path; return false; }
+    }
     if (tt.has_sparsity) {
       // SparsityParameters{0: traversal_order, 1: block_map, 2: dim_metadata[]};
       // DimensionMetadata{0: format (0 DENSE, 1 SPARSE_CSR), 1: dense_size, 2/3: array_segments (union), 4/5: array_indices (union)};
@@ -205,7 +216,7 @@ bool TfModel::load(const std::string& path, std::string* err) {
       if (good) {
         int64_t rows = 1;
         for (size_t d = 0; d + 1 < rank; ++d) rows *= tt.shape[d];
-        good = (int64_t)tt.sp_segments.size() == rows + 1 && tt.sp_segments.front() == 0 && tt.sp_segments.back() == (int32_t)tt.sp_indices.size();
+        good = rows >= 1 && !tt.sp_segments.empty() && (int64_t)tt.sp_segments.size() == rows + 1 && tt.sp_segments.front() == 0 && tt.sp_segments.back() == (int32_t)tt.sp_indices.size();
         for (size_t i = 0; good && i + 1 < tt.sp_segments.size(); ++i) good = tt.sp_segments[i] <= tt.sp_segments[i + 1];
         for (size_t i = 0; good && i < tt.sp_indices.size(); ++i) good = tt.sp_indices[i] >= 0 && tt.sp_indices[i] < tt.shape[rank - 1];
       }

@@ -69,3 +69,48 @@ def face_frames(n: int, width: int = 1920, height: int = 1080, start: int = 0, f
     for i in range(n):
         out[i] = face_frame(start + i, width, height, faces[(start + i) % len(faces)])
     return out
+
+
+def multi_face_frame(index: int, width: int = 1920, height: int = 1080, faces=("man.jpg", "russ_cox_1.jpg")) -> np.ndarray:
+    """A G2-style frame that carries len(faces) faces: the frame is cut into equal vertical strips and one test image is pasted
+    (seeded scale / rotation / position, seed = frame index) inside each strip, so the faces never overlap.  Exercises the
+    max_faces fan-out and multi-cluster NMS of the pipeline."""
+    import cv2
+    rng = np.random.default_rng(5000 + index)
+    n = len(faces)
+    yy = np.linspace(0.0, 1.0, height, dtype=np.float32)[:, None, None]
+    xx = np.linspace(0.0, 1.0, width, dtype=np.float32)[None, :, None]
+    bg = rng.uniform(60, 180, 3).astype(np.float32) + rng.uniform(-30, 30, 3).astype(np.float32) * xx + rng.uniform(-30, 30, 3).astype(np.float32) * yy
+    frame = np.clip(bg + rng.normal(0.0, 2.0, (height, width, 3)).astype(np.float32), 0, 255).astype(np.uint8)
+    strip = width // n
+    for k, name in enumerate(faces):
+        src = load_rgb(name)
+        sh, sw = src.shape[:2]
+        theta = float(rng.uniform(-20.0, 20.0))
+        # largest scale whose rotated bounding circle fits the strip and the frame height
+        smax = min(strip, height) / float(np.hypot(sw, sh))
+        scale = float(rng.uniform(0.75 * smax, 0.98 * smax))
+        half = 0.5 * scale * float(np.hypot(sw, sh))
+        cx = k * strip + float(rng.uniform(half, max(strip - half, half)))
+        cy = float(rng.uniform(half, max(height - half, half)))
+        m = cv2.getRotationMatrix2D((sw / 2.0, sh / 2.0), theta, scale)
+        m[0, 2] += cx - sw / 2.0
+        m[1, 2] += cy - sh / 2.0
+        warped = cv2.warpAffine(src, m, (width, height), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+        mask = cv2.warpAffine(np.full((sh, sw), 255, np.uint8), m, (width, height), flags=cv2.INTER_NEAREST, borderMode=cv2.BORDER_CONSTANT,
+                              borderValue=0)
+        frame[mask > 0] = warped[mask > 0]
+    return frame
+
+
+def grid_frame(grid: int = 6, cell: int = 256) -> np.ndarray:
+    """A square frame tiled with grid x grid copies of the face of man.jpg: more detections than FDL_MAX_DETECTIONS (32) for
+    grid >= 6 -- the pipeline's overflow report is tested with it."""
+    import cv2
+    man = load_rgb("man.jpg")
+    crop = cv2.resize(np.ascontiguousarray(man[20:260, 150:390]), (cell - 16, cell - 16))
+    frame = np.full((grid * cell, grid * cell, 3), 120, np.uint8)
+    for i in range(grid):
+        for j in range(grid):
+            frame[i * cell + 8:i * cell + cell - 8, j * cell + 8:j * cell + cell - 8] = crop
+    return frame

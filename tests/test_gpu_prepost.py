@@ -49,39 +49,61 @@ def test_letterbox_bit_exact(fdl, gpu, man, size):
         np.testing.assert_array_equal(t, ref.tensor_data)
 
 
-def test_rotated_warp_matches_opencv(fdl, gpu, man):
-    """Landmark mode (keep_aspect=false, (0,1)): rotated ROI warped straight to 192x192.  The 3x3 solve
-    differs from OpenCV's SVD in the last bits, so allow <= 1e-4 of the pixels to differ by one level."""
+def test_rotated_warp_matches_opencv(fdl, gpu, man, capsys):
+    """Landmark mode (keep_aspect=false, (0,1)): rotated ROI warped straight to 192x192.  The 8x8 perspective solve is f64
+    Gaussian elimination where the reference's OpenCV runs DECOMP_SVD (LAPACK in this container's cv2, Jacobi in builds without
+    it -- the reference does not pin which): the two matrices differ in the last bits, which moves a sample across a 1/32-px
+    rounding boundary once in a few million pixels.  SURVEY 8c(1) allows <= 1e-5 of the pixels to differ by one level: measured
+    over 48 seeded ROIs (1.77 M pixels) and bounded there; every pixel that agrees must give the identical tensor value."""
     from oracle import glue
     import synth_frames
     r = rng(11)
     frames = [man, synth_frames.face_frame(1)]
-    for k in range(12):
+    bad = tot = 0
+    for k in range(48):
         img = frames[k % 2]
         roi = glue.Rect(r.uniform(0.2, 0.8), r.uniform(0.2, 0.8), r.uniform(0.1, 0.9), r.uniform(0.1, 0.9), r.uniform(-math.pi, math.pi), True)
         ref, t, pad, u8 = _i2t_case(fdl, img, roi, (192, 192), False, (0.0, 1.0), False)
         diff = np.abs(u8.astype(int) - ref.u8.astype(int))
-        assert diff.max() <= 1 and (diff > 0).mean() <= 1e-4, (k, diff.max(), (diff > 0).mean())
+        n = int((diff > 0).any(axis=2).sum())
+        assert diff.max() <= 1 and n <= 4, (k, diff.max(), n)
+        bad += n
+        tot += 192 * 192
         assert pad == tuple(ref.padding)
         same = diff == 0
         np.testing.assert_array_equal(t[same], ref.tensor_data[same])
+    with capsys.disabled():
+        print("\n[warp parity] landmark mode: %d of %d pixels differ by one level from cv2 (rate %.2e, bound 1e-5)" % (bad, tot, bad / tot))
+    assert bad / tot <= 1e-5
 
 
-def test_iris_mode_matches_opencv(fdl, gpu, man):
-    """Iris mode (keep_aspect, (0,1), flip): warp to the ROI's native integer size, resize to 64x64, flip."""
+def test_iris_mode_matches_opencv(fdl, gpu, man, capsys):
+    """Iris mode (keep_aspect, (0,1), flip): warp to the ROI's native integer size, resize to 64x64, flip.  Same solve as above;
+    here a warp pixel that differs is spread by the resize over the output pixels it feeds ((64 / side + 2)^2 of them when a
+    small ROI is enlarged), so the per-image bound is two such footprints, and the 1e-5 bound is applied to the ROIs that are
+    reduced (side >= 64 px), where one warp pixel reaches at most four output pixels."""
     from oracle import glue
     import synth_frames
     r = rng(12)
     frames = [man, synth_frames.face_frame(2)]
-    for k in range(16):
+    bad = tot = 0
+    for k in range(96):
         img = frames[k % 2]
         h, w = img.shape[:2]
-        side = r.uniform(20, 300)  # px, square in pixels like SquareLong ROIs
+        side = r.uniform(20, 300) if k < 32 else r.uniform(64, 400)  # px, square in pixels like SquareLong ROIs
         roi = glue.Rect(r.uniform(0.3, 0.7), r.uniform(0.3, 0.7), side / w, side / h, r.uniform(-0.6, 0.6), True)
         ref, t, pad, u8 = _i2t_case(fdl, img, roi, (64, 64), True, (0.0, 1.0), bool(k & 1))
         diff = np.abs(u8.astype(int) - ref.u8.astype(int))
-        assert diff.max() <= 1 and (diff > 0).mean() <= 2e-3, (k, diff.max(), (diff > 0).mean())
+        n = int((diff > 0).any(axis=2).sum())
+        footprint = (int(math.ceil(64.0 / side)) + 2) ** 2
+        assert diff.max() <= 1 and n <= 2 * footprint, (k, side, diff.max(), n)
         assert pad == tuple(ref.padding)
+        if side >= 64:
+            bad += n
+            tot += 64 * 64
+    with capsys.disabled():
+        print("\n[warp parity] iris mode (ROI side >= 64 px): %d of %d pixels differ by one level from cv2 (rate %.2e, bound 1e-5)" % (bad, tot, bad / tot))
+    assert bad / tot <= 1e-5
 
 
 def test_letterboxed_roi_with_border_stage(fdl, gpu, man):
@@ -90,7 +112,7 @@ def test_letterboxed_roi_with_border_stage(fdl, gpu, man):
     for roi in (glue.Rect(0.5, 0.5, 0.6, 0.3, 0.0, True), glue.Rect(0.45, 0.55, 0.3, 0.7, 0.2, True), glue.Rect(0.5, 0.5, 0.31, 0.47, -0.4, True)):
         ref, t, pad, u8 = _i2t_case(fdl, man, roi, (128, 128), True, (-1.0, 1.0), False)
         diff = np.abs(u8.astype(int) - ref.u8.astype(int))
-        assert diff.max() <= 1 and (diff > 0).mean() <= 2e-3
+        assert diff.max() <= 1 and int((diff > 0).any(axis=2).sum()) <= 8
         assert pad == tuple(ref.padding)
 
 
