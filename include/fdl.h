@@ -108,6 +108,7 @@ typedef struct fdl_landmark_model fdl_landmark_model;
 typedef struct fdl_iris_model fdl_iris_model;
 typedef struct fdl_net fdl_net;
 typedef struct fdl_pipeline fdl_pipeline;
+typedef struct fdl_jpeg_decoder fdl_jpeg_decoder;
 
 /* ---------------------------------------------------------------- library */
 FDL_API const char* fdl_last_error(void);
@@ -213,6 +214,26 @@ FDL_API int fdl_iris_diameter(int device, const fdl_landmark* iris, int n, int i
 FDL_API int fdl_iris_depth(int device, const fdl_landmark* iris, int n, double focal_length_mm, double iris_size_px,
                            int image_width, int image_height, double* depth_mm);
 
+/* ---------------------------------------------------------------- frame ingest */
+/* utils.rs:8-21 `convert_image_to_mat(im_bytes)`: imgcodecs::imdecode(IMREAD_COLOR) + cvt_color(BGR2RGB) -- here a baseline JPEG
+ * decoder on the device (Huffman stage, jpeg_idct_islow, fancy chroma upsampling, fixed-point YCbCr -> RGB: libjpeg's defaults,
+ * bit-exact with cv2.imdecode).  Accepted: 8-bit baseline (SOF0 / SOF1 Huffman) files with one interleaved scan, 1 or 3
+ * components, luma at full resolution, chroma at 1x1, 2x1 or 2x2, with or without restart intervals, EXIF orientation 1 or
+ * none.  Everything else (progressive, arithmetic, CMYK, rotated by EXIF, truncated scans) is FDL_ERR_INVALID with a message:
+ * never a silent approximation, never a CPU fallback. */
+/* Header only (host): size and component count.  No GPU needed. */
+FDL_API int fdl_jpeg_info(const uint8_t* data, size_t len, int* width, int* height, int* components);
+FDL_API int fdl_jpeg_decoder_create(int device, fdl_jpeg_decoder** out);
+FDL_API void fdl_jpeg_decoder_destroy(fdl_jpeg_decoder*);
+/* Decodes n files into tightly packed RGB images (rows of width*3 bytes) written back to back into `out` (host memory, or device
+ * memory on the decoder's device when out_mem == FDL_MEM_DEVICE).  offsets[i] (optional) receives the byte offset of image i in
+ * `out`, widths / heights (optional) its size.  FDL_ERR_CAPACITY when `cap` bytes do not hold the batch (offsets / sizes are
+ * filled, so the caller can size the buffer from a first call with cap == 0). */
+FDL_API int fdl_jpeg_decode(fdl_jpeg_decoder*, const uint8_t* const* data, const size_t* len, int n, uint8_t* out, size_t cap, int out_mem,
+                            int64_t* offsets, int32_t* widths, int32_t* heights);
+/* One-shot form of convert_image_to_mat: one file -> RGB in host memory (cap >= width*height*3; *width / *height always filled). */
+FDL_API int fdl_decode_jpeg(int device, const uint8_t* data, size_t len, uint8_t* out_rgb, size_t cap, int* width, int* height);
+
 /* ---------------------------------------------------------------- generic network handle */
 /* A planned .tflite graph on one device (what replaces the TFLite interpreter). */
 FDL_API int fdl_net_create(const char* tflite_file, int device, fdl_net** out);
@@ -301,6 +322,12 @@ FDL_API int fdl_pipeline_depth(const fdl_pipeline*);
 FDL_API int fdl_pipeline_submit(fdl_pipeline*, const fdl_image* frames, int n, int* ticket);
 FDL_API int fdl_pipeline_collect(fdl_pipeline*, int ticket, fdl_frame_result* frame_results,
                                  fdl_face_result* face_results, int* n);
+/* The lib.rs:20-40 sequence from where it really starts -- encoded bytes (`convert_image_to_mat`, utils.rs:8-21): n JPEG files
+ * of the pipeline's frame size are copied to the device COMPRESSED (a 1080p frame is ~0.2 MB instead of 6.2 MB over PCIe),
+ * decoded there (see fdl_jpeg_decode) into the lane's frame buffer and run through the same stages as fdl_pipeline_submit.
+ * Pinned caller memory that holds the files close together in ascending order is read in place by the copy engine.  Errors of
+ * the entropy-coded data (truncated scan, missing restart markers) surface from fdl_pipeline_collect as FDL_ERR_INVALID. */
+FDL_API int fdl_pipeline_submit_jpeg(fdl_pipeline*, const uint8_t* const* data, const size_t* len, int n, int* ticket);
 /* Device time of the last collected ticket's kernels (excludes copies), milliseconds. */
 /* Host-only introspection of the zero-copy ingest plan (no GPU needed): which source rows of a
  * frame_width x frame_height frame the detector's letterbox (image_to_tensor with roi = None,
@@ -311,7 +338,7 @@ FDL_API int fdl_pipeline_collect(fdl_pipeline*, int ticket, fdl_frame_result* fr
  * frames; 0 when the pipeline reads the frames in place instead; negative on error. */
 FDL_API int fdl_letterbox_row_plan(int frame_width, int frame_height, int input_size, int32_t* row_pos, int32_t* info4);
 FDL_API float fdl_pipeline_last_device_ms(const fdl_pipeline*);
-/* Stage breakdown of the last collected ticket, ms: [0] H2D, [1] detector preprocess, [2] detector
+/* Stage breakdown of the last collected ticket, ms: [0] H2D (submit_jpeg: H2D of the compressed bytes + device decode), [1] detector preprocess, [2] detector
  * net, [3] SSD post-process, [4] face ROI + warp, [5] landmark net, [6] landmark post + eye warp,
  * [7] iris net, [8] iris post, [9] D2H. */
 FDL_API int fdl_pipeline_stage_ms(const fdl_pipeline*, float* out10);

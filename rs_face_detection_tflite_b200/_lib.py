@@ -117,6 +117,12 @@ SYMBOLS = {
     "fdl_pipeline_depth": (C.c_int, [_vp]),
     "fdl_pipeline_submit": (C.c_int, [_vp, _P(CImage), C.c_int, _P(C.c_int)]),
     "fdl_pipeline_collect": (C.c_int, [_vp, C.c_int, _P(CFrameResult), _P(CFaceResult), _P(C.c_int)]),
+    "fdl_pipeline_submit_jpeg": (C.c_int, [_vp, _P(_vp), _P(C.c_size_t), C.c_int, _P(C.c_int)]),
+    "fdl_jpeg_info": (C.c_int, [_vp, C.c_size_t, _P(C.c_int), _P(C.c_int), _P(C.c_int)]),
+    "fdl_jpeg_decoder_create": (C.c_int, [C.c_int, _P(_vp)]),
+    "fdl_jpeg_decoder_destroy": (None, [_vp]),
+    "fdl_jpeg_decode": (C.c_int, [_vp, _P(_vp), _P(C.c_size_t), C.c_int, _vp, C.c_size_t, C.c_int, _P(C.c_int64), _P(C.c_int32), _P(C.c_int32)]),
+    "fdl_decode_jpeg": (C.c_int, [C.c_int, _vp, C.c_size_t, _vp, C.c_size_t, _P(C.c_int), _P(C.c_int)]),
     "fdl_pipeline_last_device_ms": (C.c_float, [_vp]),
     "fdl_pipeline_stage_ms": (C.c_int, [_vp, _P(C.c_float)]),
 }

@@ -570,6 +570,18 @@ class Pipeline:
         self._keep[t.value] = keep
         return t.value
 
+    def submit_jpeg(self, files) -> int:
+        """``files``: JPEG byte strings (bytes / bytearray / uint8 arrays), or one ``(uint8 buffer, offsets, lengths)`` triple for files
+        that already sit in one (ideally pinned) arena -- the form that lets the copy engine read them in place."""
+        ptrs, lens, n, keep = _jpeg_args(files)
+        t = C.c_int()
+        check(lib().fdl_pipeline_submit_jpeg(self._h, ptrs, lens, n, C.byref(t)))
+        self._keep[t.value] = keep
+        return t.value
+
+    def run_jpeg(self, files):
+        return self.collect(self.submit_jpeg(files))
+
     def collect_raw(self, ticket: int) -> int:
         """Waits for `ticket`; results stay in the ctypes arrays (self._frames / self._faces). Returns n."""
         n = C.c_int()
@@ -616,6 +628,100 @@ class Pipeline:
         out = (C.c_float * 10)()
         check(lib().fdl_pipeline_stage_ms(self._h, out))
         return list(out)
+
+
+# ------------------------------------------------------------------------------------------------
+# frame ingest: utils.rs:8-21 convert_image_to_mat (imdecode + BGR2RGB), decoded on the device
+def _buffer_address(b):
+    """(address, length, keepalive) of bytes / bytearray / numpy uint8 / torch uint8 (host)."""
+    if isinstance(b, np.ndarray):
+        a = np.ascontiguousarray(b, np.uint8)
+        return a.ctypes.data, a.size, a
+    if hasattr(b, "data_ptr"):
+        return b.data_ptr(), b.numel(), b
+    a = np.frombuffer(b, np.uint8)
+    return a.ctypes.data, a.size, (a, b)
+
+
+def _jpeg_args(files):
+    if isinstance(files, tuple) and len(files) == 3 and not isinstance(files[0], (bytes, bytearray)):
+        base, blen, keep = _buffer_address(files[0])
+        offs, lens_ = np.asarray(files[1], np.int64), np.asarray(files[2], np.int64)
+        if len(offs) != len(lens_) or (len(offs) and (offs.min() < 0 or (offs + lens_).max() > blen)):
+            raise FdlError(_lib.FDL_ERR_INVALID, "JPEG arena: offsets / lengths out of range")
+        n = len(offs)
+        ptrs = (C.c_void_p * max(n, 1))(*[base + int(o) for o in offs])
+        lens = (C.c_size_t * max(n, 1))(*[int(x) for x in lens_])
+        return ptrs, lens, n, keep
+    keeps, n = [], len(files)
+    ptrs, lens = (C.c_void_p * max(n, 1))(), (C.c_size_t * max(n, 1))()
+    for i, f in enumerate(files):
+        a, ln, k = _buffer_address(f)
+        ptrs[i], lens[i] = a, ln
+        keeps.append(k)
+    return ptrs, lens, n, keeps
+
+
+def jpeg_info(data):
+    """(width, height, components) from the header alone (host; no GPU needed)."""
+    a, ln, _k = _buffer_address(data)
+    w, h, c = C.c_int(), C.c_int(), C.c_int()
+    check(lib().fdl_jpeg_info(a, ln, C.byref(w), C.byref(h), C.byref(c)))
+    return w.value, h.value, c.value
+
+
+def convert_image_to_mat(im_bytes, device: int = 0) -> np.ndarray:
+    """utils.rs:8-21: JPEG bytes -> RGB uint8 [H,W,3] (imdecode(IMREAD_COLOR) + cvt_color(BGR2RGB)), decoded on the device."""
+    a, ln, _k = _buffer_address(im_bytes)
+    w, h = C.c_int(), C.c_int()
+    check(lib().fdl_jpeg_info(a, ln, C.byref(w), C.byref(h), None))
+    out = np.empty((h.value, w.value, 3), np.uint8)
+    check(lib().fdl_decode_jpeg(device, a, ln, out.ctypes.data, out.size, C.byref(w), C.byref(h)))
+    return out
+
+
+class JpegDecoder:
+    """Batched device decoder (fdl_jpeg_decode): ``decode(files)`` -> list of RGB uint8 arrays; ``decode_to_device(files)`` -> one
+    CUDA uint8 tensor holding the images back to back + (offsets, widths, heights)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().fdl_jpeg_decoder_create(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fdl_jpeg_decoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _sizes(self, ptrs, lens, n):
+        offs, ws, hs = (C.c_int64 * n)(), (C.c_int32 * n)(), (C.c_int32 * n)()
+        rc = lib().fdl_jpeg_decode(self._h, ptrs, lens, n, None, 0, _lib.MEM_HOST, offs, ws, hs)
+        if rc != _lib.FDL_ERR_CAPACITY:
+            check(rc)
+        total = (int(offs[n - 1]) + int(ws[n - 1]) * int(hs[n - 1]) * 3 + 3) & ~3
+        return offs, ws, hs, total
+
+    def decode(self, files):
+        ptrs, lens, n, _keep = _jpeg_args(files)
+        offs, ws, hs, total = self._sizes(ptrs, lens, n)
+        out = np.empty(total, np.uint8)
+        check(lib().fdl_jpeg_decode(self._h, ptrs, lens, n, out.ctypes.data, out.size, _lib.MEM_HOST, offs, ws, hs))
+        return [out[offs[i]:offs[i] + ws[i] * hs[i] * 3].reshape(hs[i], ws[i], 3) for i in range(n)]
+
+    def decode_to_device(self, files):
+        import torch
+        ptrs, lens, n, _keep = _jpeg_args(files)
+        offs, ws, hs, total = self._sizes(ptrs, lens, n)
+        out = torch.empty(total, dtype=torch.uint8, device="cuda:%d" % self.device)
+        check(lib().fdl_jpeg_decode(self._h, ptrs, lens, n, out.data_ptr(), total, _lib.MEM_DEVICE, offs, ws, hs))
+        return out, list(offs), list(ws), list(hs)
 
 
 def letterbox_row_plan(frame_size, input_size: int):

@@ -33,6 +33,8 @@ SOURCES = {
     "pw_kernel.cu": [],
     # the glue arithmetic must not contract a*b+c into FMA (the reference's scalar Rust never does)
     "prepost_kernels.cu": ["-fmad=false"],
+    "jpeg_kernels.cu": [],
+    "jpeg_decode.cu": [],
     "fdl_api.cu": [],
     "pipeline.cu": [],
 }

@@ -4,11 +4,14 @@
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "device_util.h"
 #include "fdl_status.h"
+#include "jpeg_decode.h"
+#include "jpeg_parse.h"
 #include "net.h"
 #include "prepost_kernels.cuh"
 
@@ -91,6 +94,13 @@ struct fdl_iris_model {
   DevBuf<I2TParams> params;
   DevBuf<fdl_rect> rois;
   DevBuf<float> out;
+};
+
+struct fdl_jpeg_decoder {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  JpegDecoder dec;
+  DevBuf<uint8_t> out;
 };
 
 extern "C" {
@@ -770,6 +780,84 @@ int fdl_project_landmarks(int device, const float* raw, int n, int tensor_w, int
   FDL_CUDA_TRY(cudaMemcpy(pts.data(), d_out.p, pts.size() * sizeof(float), cudaMemcpyDeviceToHost));
   for (int k = 0; k < n; ++k) { out[k].x = pts[3 * k]; out[k].y = pts[3 * k + 1]; out[k].z = pts[3 * k + 2]; }
   return FDL_OK;
+} FDL_ABI_CATCH
+
+// ---------------------------------------------------------------------------------- frame ingest
+int fdl_jpeg_info(const uint8_t* data, size_t len, int* width, int* height, int* components) try {
+  if (!data) return set_error(FDL_ERR_INVALID, "null argument");
+  JpegHeader hd;
+  std::string msg;
+  if (!jpeg_parse_header(data, len, &hd, &msg)) return set_error(FDL_ERR_INVALID, msg);
+  if (width) *width = hd.width;
+  if (height) *height = hd.height;
+  if (components) *components = hd.ncomp;
+  return FDL_OK;
+} FDL_ABI_CATCH
+
+int fdl_jpeg_decoder_create(int device, fdl_jpeg_decoder** out) try {
+  DeviceGuard _device_guard;
+  if (!out) return set_error(FDL_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int rc = check_device(device);
+  if (rc) return rc;
+  fdl_jpeg_decoder* d = new fdl_jpeg_decoder();
+  d->device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete d; return set_error(FDL_ERR_CUDA, cudaGetErrorString(e)); }
+  *out = d;
+  return FDL_OK;
+} FDL_ABI_CATCH
+
+void fdl_jpeg_decoder_destroy(fdl_jpeg_decoder* d) {
+  if (!d) return;
+  DeviceGuard _device_guard;
+  cudaSetDevice(d->device);
+  if (d->stream) { cudaStreamSynchronize(d->stream); cudaStreamDestroy(d->stream); }
+  delete d;
+}
+
+int fdl_jpeg_decode(fdl_jpeg_decoder* d, const uint8_t* const* data, const size_t* len, int n, uint8_t* out, size_t cap, int out_mem,
+                    int64_t* offsets, int32_t* widths, int32_t* heights) try {
+  DeviceGuard _device_guard;
+  if (!d) return set_error(FDL_ERR_INVALID, "null handle");
+  FDL_CUDA_TRY(cudaSetDevice(d->device));
+  int rc = d->dec.plan(data, len, n, 0, 0);
+  if (rc) return rc;
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    const int w = d->dec.width(i), h = d->dec.height(i);
+    if (offsets) offsets[i] = (int64_t)total;
+    if (widths) widths[i] = w;
+    if (heights) heights[i] = h;
+    d->dec.set_output(i, (long long)total, w * 3);
+    total += (size_t)w * 3 * (size_t)h;
+    total = (total + 3) & ~size_t(3);            // every image starts 4-byte aligned (word stores of the colour kernel)
+  }
+  if (!out || cap < total) return set_error(FDL_ERR_CAPACITY, "output buffer too small: " + std::to_string(total) + " bytes needed");
+  uint8_t* dst = out;
+  if (out_mem != FDL_MEM_DEVICE) { FDL_CUDA_TRY(d->out.reserve(total)); dst = d->out.p; }
+  rc = d->dec.enqueue(dst, d->stream);
+  if (rc) return rc;
+  if (out_mem != FDL_MEM_DEVICE) FDL_CUDA_TRY(cudaMemcpyAsync(out, d->out.p, total, cudaMemcpyDeviceToHost, d->stream));
+  FDL_CUDA_TRY(cudaStreamSynchronize(d->stream));
+  return d->dec.check_status();
+} FDL_ABI_CATCH
+
+int fdl_decode_jpeg(int device, const uint8_t* data, size_t len, uint8_t* out_rgb, size_t cap, int* width, int* height) try {
+  DeviceGuard _device_guard;
+  int w = 0, h = 0;
+  int rc = fdl_jpeg_info(data, len, &w, &h, nullptr);
+  if (rc) return rc;
+  if (width) *width = w;
+  if (height) *height = h;
+  if (!out_rgb || cap < (size_t)w * 3 * (size_t)h) return set_error(FDL_ERR_CAPACITY, "output buffer too small for " + std::to_string(w) + "x" + std::to_string(h) + " RGB");
+  // convert_image_to_mat is a free function in the reference (utils.rs:8): one cached decoder per device serves it
+  static std::mutex mu;
+  static fdl_jpeg_decoder* cache[64] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  if (device < 0 || device >= 64) return set_error(FDL_ERR_INVALID, "device index out of range");
+  if (!cache[device]) { rc = fdl_jpeg_decoder_create(device, &cache[device]); if (rc) return rc; }
+  return fdl_jpeg_decode(cache[device], &data, &len, 1, out_rgb, cap, FDL_MEM_HOST, nullptr, nullptr, nullptr);
 } FDL_ABI_CATCH
 
 }  // extern "C"

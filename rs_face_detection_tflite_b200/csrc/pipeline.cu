@@ -22,6 +22,7 @@
 #include "device_util.h"
 #include "fdl_status.h"
 #include "glue_math.h"
+#include "jpeg_decode.h"
 #include "net.h"
 #include "prepost_kernels.cuh"
 
@@ -108,6 +109,8 @@ struct Lane {
   PinBuf<fdl_frame_result> h_frames;
   PinBuf<fdl_face_result> h_faces;
   cudaEvent_t ev_h2d_start = nullptr, ev_stage[kStages] = {}, ev_done = nullptr;
+  JpegDecoder jpeg;                            // fdl_pipeline_submit_jpeg: the lane's device decoder (frames land in `frames`)
+  bool jpeg_pending = false;
   int n = 0;
   int ticket = -1;
   bool busy = false;
@@ -249,27 +252,13 @@ int fdl_pipeline_create(const fdl_pipeline_config* cfg, fdl_pipeline** out) try 
 void fdl_pipeline_destroy(fdl_pipeline* p) { pipeline_free(p); }
 int fdl_pipeline_depth(const fdl_pipeline*) { return kDepth; }
 
-int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ticket) try {
-  DeviceGuard _device_guard;
-  if (!p || !frames || !ticket) return set_error(FDL_ERR_INVALID, "null argument");
-  if (n <= 0 || n > p->cfg.max_batch) return set_error(FDL_ERR_INVALID, "batch size out of range (1..max_batch)");
-  FDL_CUDA_TRY(cudaSetDevice(p->cfg.device));
-  Lane* lane = nullptr;
-  for (auto& l : p->lanes) if (!l.busy) { lane = &l; break; }
-  if (!lane) return set_error(FDL_ERR_INVALID, "all pipeline lanes are in flight: collect a ticket first");
+}  // extern "C"
+
+// Everything after the frames are where the kernels can read them (`fptr`: the lane's frame buffer, the caller's device frames, or --
+// zero-copy host mode -- the caller's pinned frames, `host_base` their host address for the copy engine's row gather).
+static int pipeline_enqueue(fdl_pipeline* p, Lane* lane, int n, const uint8_t* fptr, bool used_host, const uint8_t* host_base, int* ticket) {
   const int W = p->cfg.frame_width, H = p->cfg.frame_height, MF = p->cfg.max_faces;
-  for (int i = 0; i < n; ++i)
-    if (frames[i].width != W || frames[i].height != H) return set_error(FDL_ERR_INVALID, "frame size differs from the pipeline configuration");
   cudaStream_t cs = lane->stream;
-
-  // ---- copy-in (skipped for contiguous device frames and, in zero-copy mode, for pinned host frames)
-  FDL_CUDA_TRY(cudaEventRecord(lane->ev_h2d_start, cs));
-  int w, h;
-  const uint8_t* fptr = nullptr;
-  bool used_host = false;
-  int rc = stage_frames(frames, n, &lane->frames, cs, &w, &h, &fptr, p->cfg.zero_copy_host != 0, &used_host);
-  if (rc) return rc;
-
   const long long row = (long long)W * 3, fstride = row * H;
   static const int zc_env = getenv("FDL_ZC_CTAS") ? atoi(getenv("FDL_ZC_CTAS")) : 148;
   const int zc_ctas = used_host ? zc_env : 0;   // persistent CTAs for kernels that read host memory over PCIe
@@ -278,7 +267,7 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
     // the copy engine gathers the source rows of the letterbox: one strided 2-D copy per row family for the whole batch
     const RowGather& g = p->gather;
     for (const RowFamily& f : g.fam)
-      FDL_CUDA_TRY(cudaMemcpy2DAsync(lane->rows.p + (size_t)f.dst_row0 * row, (size_t)g.rows_per_period * row, frames[0].data + (size_t)f.src_row0 * row,
+      FDL_CUDA_TRY(cudaMemcpy2DAsync(lane->rows.p + (size_t)f.dst_row0 * row, (size_t)g.rows_per_period * row, host_base + (size_t)f.src_row0 * row,
                                      (size_t)g.period_src_rows * row, (size_t)f.rows * row, (size_t)n * g.periods_per_frame, cudaMemcpyHostToDevice, cs));
   }
   const int F = n * MF, E = 2 * F;
@@ -385,6 +374,52 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
   lane->ticket = p->next_ticket++;
   *ticket = lane->ticket;
   return FDL_OK;
+}
+
+extern "C" {
+
+int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ticket) try {
+  DeviceGuard _device_guard;
+  if (!p || !frames || !ticket) return set_error(FDL_ERR_INVALID, "null argument");
+  if (n <= 0 || n > p->cfg.max_batch) return set_error(FDL_ERR_INVALID, "batch size out of range (1..max_batch)");
+  FDL_CUDA_TRY(cudaSetDevice(p->cfg.device));
+  Lane* lane = nullptr;
+  for (auto& l : p->lanes) if (!l.busy) { lane = &l; break; }
+  if (!lane) return set_error(FDL_ERR_INVALID, "all pipeline lanes are in flight: collect a ticket first");
+  for (int i = 0; i < n; ++i)
+    if (frames[i].width != p->cfg.frame_width || frames[i].height != p->cfg.frame_height)
+      return set_error(FDL_ERR_INVALID, "frame size differs from the pipeline configuration");
+  // ---- copy-in (skipped for contiguous device frames and, in zero-copy mode, for pinned host frames)
+  FDL_CUDA_TRY(cudaEventRecord(lane->ev_h2d_start, lane->stream));
+  int w, h;
+  const uint8_t* fptr = nullptr;
+  bool used_host = false;
+  int rc = stage_frames(frames, n, &lane->frames, lane->stream, &w, &h, &fptr, p->cfg.zero_copy_host != 0, &used_host);
+  if (rc) return rc;
+  lane->jpeg_pending = false;
+  return pipeline_enqueue(p, lane, n, fptr, used_host, frames[0].data, ticket);
+} FDL_ABI_CATCH
+
+int fdl_pipeline_submit_jpeg(fdl_pipeline* p, const uint8_t* const* data, const size_t* len, int n, int* ticket) try {
+  DeviceGuard _device_guard;
+  if (!p || !data || !len || !ticket) return set_error(FDL_ERR_INVALID, "null argument");
+  if (n <= 0 || n > p->cfg.max_batch) return set_error(FDL_ERR_INVALID, "batch size out of range (1..max_batch)");
+  FDL_CUDA_TRY(cudaSetDevice(p->cfg.device));
+  Lane* lane = nullptr;
+  for (auto& l : p->lanes) if (!l.busy) { lane = &l; break; }
+  if (!lane) return set_error(FDL_ERR_INVALID, "all pipeline lanes are in flight: collect a ticket first");
+  const int W = p->cfg.frame_width, H = p->cfg.frame_height;
+  // convert_image_to_mat (utils.rs:8-21) for the whole batch, on the device: parse the headers here, copy the files compressed
+  int rc = lane->jpeg.plan(data, len, n, W, H);
+  if (rc) return rc;
+  const size_t frame = (size_t)W * 3 * H;
+  for (int i = 0; i < n; ++i) lane->jpeg.set_output(i, (long long)(frame * i), W * 3);
+  FDL_CUDA_TRY(lane->frames.reserve(frame * (size_t)n));
+  FDL_CUDA_TRY(cudaEventRecord(lane->ev_h2d_start, lane->stream));
+  rc = lane->jpeg.enqueue(lane->frames.p, lane->stream);
+  if (rc) return rc;
+  lane->jpeg_pending = true;
+  return pipeline_enqueue(p, lane, n, lane->frames.p, false, nullptr, ticket);
 } FDL_ABI_CATCH
 
 int fdl_pipeline_collect(fdl_pipeline* p, int ticket, fdl_frame_result* frame_results, fdl_face_result* face_results, int* n_out) try {
@@ -408,6 +443,11 @@ int fdl_pipeline_collect(fdl_pipeline* p, int ticket, fdl_frame_result* frame_re
   cudaEventElapsedTime(&p->stage_ms[9], lane->ev_stage[8], lane->ev_done);
   cudaEventElapsedTime(&p->last_device_ms, lane->ev_stage[0], lane->ev_stage[8]);
   lane->busy = false;
+  if (lane->jpeg_pending) {
+    lane->jpeg_pending = false;
+    const int jrc = lane->jpeg.check_status();
+    if (jrc) return jrc;
+  }
   // the reference returns every detection (an unbounded Vec, face_detection.rs:267); a truncated record is reported, not hidden
   for (int i = 0; i < n; ++i)
     if (lane->h_frames.p[i].n_total_detections > FDL_MAX_DETECTIONS)

@@ -4,7 +4,7 @@ the batched pipeline, against the oracle.  Tolerances: kept anchors exact (excep
 import numpy as np
 import pytest
 
-from conftest import MODELS
+from conftest import MODELS, rng
 
 pytestmark = pytest.mark.gpu
 
