@@ -83,6 +83,8 @@ def _huff_table(counts, symbols):
     lut_sym = np.zeros(65536, np.uint8)
     code, k = 0, 0
     for length in range(1, 17):
+        if code + counts[length - 1] > (1 << length):          # libjpeg: "Bogus Huffman table definition"
+            raise ValueError("bad DHT: code lengths over-subscribed")
         for _ in range(counts[length - 1]):
             lo = code << (16 - length)
             hi = lo + (1 << (16 - length))

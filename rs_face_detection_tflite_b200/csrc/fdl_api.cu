@@ -96,6 +96,8 @@ struct fdl_iris_model {
   DevBuf<float> out;
 };
 
+namespace fdl { cudaError_t jpeg_debug_phases(long long out[8]); }
+
 struct fdl_jpeg_decoder {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -842,6 +844,12 @@ int fdl_jpeg_decode(fdl_jpeg_decoder* d, const uint8_t* const* data, const size_
   FDL_CUDA_TRY(cudaStreamSynchronize(d->stream));
   return d->dec.check_status();
 } FDL_ABI_CATCH
+
+// not in fdl.h: debugging aid (phase timestamps of CTA 0 of the last entropy-stage launch on the current device)
+FDL_API int fdl_debug_jpeg_phases(long long* out8) {
+  if (!out8) return FDL_ERR_INVALID;
+  return fdl::jpeg_debug_phases(out8) == cudaSuccess ? FDL_OK : FDL_ERR_CUDA;
+}
 
 int fdl_decode_jpeg(int device, const uint8_t* data, size_t len, uint8_t* out_rgb, size_t cap, int* width, int* height) try {
   DeviceGuard _device_guard;

@@ -1,6 +1,7 @@
 // jpeg_decode.cu -- see jpeg_decode.h.
 #include "jpeg_decode.h"
 
+#include <cstdlib>
 #include <cstring>
 
 #include "fdl_status.h"
@@ -26,7 +27,7 @@ int JpegDecoder::plan(const uint8_t* const* data, const size_t* len, int n, int 
   FDL_CUDA_TRY(h_status_.reserve((size_t)n));
   dht_blobs_.clear();
   total_bytes_ = clean_bytes_ = coef_elems_ = plane_bytes_ = iv_entries_ = 0;
-  max_windows_ = 1; max_quads_ = 0; max_w_ = max_h_ = 0;
+  max_windows_ = 1; max_quads_ = 0; max_w_ = max_h_ = 0; max_tiles_ = 1;
 
   // Where the compressed bytes come from: if the caller's buffers are pinned and lie close together in ascending order (one
   // arena of encoded frames), the H2D copy reads them in place as one span; otherwise they are packed into a pinned staging buffer.
@@ -104,15 +105,18 @@ int JpegDecoder::plan(const uint8_t* const* data, const size_t* len, int n, int 
     d.iv_off = (long long)iv_entries_;
     iv_entries_ += (size_t)d.n_intervals;
     d.clean_off = (long long)clean_bytes_;
-    clean_bytes_ += align_up((size_t)d.raw_len + 32, 16);
+    clean_bytes_ += align_up((size_t)d.raw_len + 64, 128);     // 128-byte aligned: a 1024-bit window is one L1 line
     const long long bits = (long long)d.raw_len * 8;
     long long wb = (bits + kJpegMaxWindows - 1) / kJpegMaxWindows;
     wb = (wb + 31) / 32 * 32;
-    d.window_bits = (int)(wb < kJpegMinWindowBits ? kJpegMinWindowBits : wb);
+    static const int min_bits = [] { const char* e = getenv("FDL_JPEG_WINDOW_BITS"); const int v = e ? atoi(e) : 0; return v >= 64 ? v / 32 * 32 : kJpegMinWindowBits; }();
+    d.window_bits = (int)(wb < min_bits ? min_bits : wb);
     d.nwin_cap = (int)((bits + d.window_bits - 1) / d.window_bits);
     if (d.nwin_cap < 1) d.nwin_cap = 1;
     if (d.restart_interval == 0 && d.nwin_cap > max_windows_) max_windows_ = d.nwin_cap;
     if (quads > max_quads_) max_quads_ = quads;
+    const int tiles = jpeg_scan_tiles(d.raw_off, d.raw_len);
+    if (tiles > max_tiles_) max_tiles_ = tiles;
     if (d.width > max_w_) max_w_ = d.width;
     if (d.height > max_h_) max_h_ = d.height;
     d.out_off = 0; d.out_stride = d.width * 3;
@@ -126,20 +130,32 @@ int JpegDecoder::plan(const uint8_t* const* data, const size_t* len, int n, int 
 int JpegDecoder::enqueue(uint8_t* out_device, cudaStream_t s) {
   if (n_ <= 0) return set_error(FDL_ERR_INVALID, "no planned JPEG batch");
   FDL_CUDA_TRY(d_bytes_.reserve(span_bytes_ + 64));
-  FDL_CUDA_TRY(d_clean_.reserve(clean_bytes_ + 64));
+  FDL_CUDA_TRY(d_clean_.reserve(clean_bytes_ + 256));
   FDL_CUDA_TRY(d_coef_.reserve(coef_elems_));
-  FDL_CUDA_TRY(d_planes_.reserve(plane_bytes_));
+  FDL_CUDA_TRY(d_planes_.reserve(plane_bytes_ + 64));      // the colour kernel's word loads may run a few bytes past the last row
   FDL_CUDA_TRY(d_iv_.reserve(iv_entries_ + 1));
   FDL_CUDA_TRY(d_status_.reserve((size_t)n_));
+  FDL_CUDA_TRY(d_tile_info_.reserve((size_t)n_ * max_tiles_ * 3));
+  FDL_CUDA_TRY(d_scan_len_.reserve((size_t)n_ * 2));
   FDL_CUDA_TRY(d_descs_.reserve((size_t)n_));
   FDL_CUDA_TRY(d_tabs_.reserve(dht_blobs_.size()));
+  // which colour kernel takes which image (the output placement is known only now)
+  int color_flags = 0;
+  for (int i = 0; i < n_; ++i) {
+    JpegImageDesc& d = h_descs_.p[i];
+    const bool same = d.ncomp == 3 && d.hs[0] == d.hmax && d.vs[0] == d.vmax && d.hs[1] == d.hs[2] && d.vs[1] == d.vs[2] && d.hmax / d.hs[1] == 2 &&
+                      d.cw[1] > 2 && d.cw[1] == d.cw[2] && d.ch[1] == d.ch[2];
+    const bool aligned = d.out_stride % 16 == 0 && d.out_off % 16 == 0 && (reinterpret_cast<uintptr_t>(out_device) & 15) == 0;
+    d.color_fast = same && aligned ? 1 : 0;
+    color_flags |= d.color_fast ? 1 : 2;
+  }
   FDL_CUDA_TRY(cudaMemcpyAsync(d_bytes_.p, direct_src_ ? direct_src_ : h_bytes_.p, span_bytes_, cudaMemcpyHostToDevice, s));
   FDL_CUDA_TRY(cudaMemcpyAsync(d_descs_.p, h_descs_.p, (size_t)n_ * sizeof(JpegImageDesc), cudaMemcpyHostToDevice, s));
   FDL_CUDA_TRY(cudaMemcpyAsync(d_tabs_.p, h_tabs_.p, dht_blobs_.size() * sizeof(JpegHuff), cudaMemcpyHostToDevice, s));
   FDL_CUDA_TRY(cudaMemsetAsync(d_coef_.p, 0, coef_elems_ * sizeof(int16_t), s));
-  FDL_CUDA_TRY(launch_jpeg_entropy(d_descs_.p, n_, d_tabs_.p, d_bytes_.p, d_clean_.p, d_coef_.p, d_iv_.p, d_status_.p, max_windows_, s));
+  FDL_CUDA_TRY(launch_jpeg_entropy(d_descs_.p, n_, d_tabs_.p, d_bytes_.p, d_clean_.p, d_coef_.p, d_iv_.p, d_status_.p, d_tile_info_.p, max_tiles_, d_scan_len_.p, max_windows_, s));
   FDL_CUDA_TRY(launch_jpeg_idct(d_descs_.p, n_, max_quads_, d_coef_.p, d_planes_.p, s));
-  FDL_CUDA_TRY(launch_jpeg_color(d_descs_.p, n_, max_w_, max_h_, d_planes_.p, out_device, s));
+  FDL_CUDA_TRY(launch_jpeg_color(d_descs_.p, n_, max_w_, max_h_, color_flags, d_planes_.p, out_device, s));
   FDL_CUDA_TRY(cudaMemcpyAsync(h_status_.p, d_status_.p, (size_t)n_ * sizeof(int), cudaMemcpyDeviceToHost, s));
   return FDL_OK;
 }

@@ -35,12 +35,12 @@ class JpegDecoder {
   int intern_table(const uint8_t* dht);
   int n_ = 0;
   size_t total_bytes_ = 0, span_bytes_ = 0, clean_bytes_ = 0, coef_elems_ = 0, plane_bytes_ = 0, iv_entries_ = 0;
-  int max_windows_ = 1, max_quads_ = 0, max_w_ = 0, max_h_ = 0;
+  int max_windows_ = 1, max_quads_ = 0, max_w_ = 0, max_h_ = 0, max_tiles_ = 1;
   const uint8_t* direct_src_ = nullptr;     // pinned caller memory copied without staging (one span), or null
   std::vector<std::vector<uint8_t>> dht_blobs_;
   DevBuf<uint8_t> d_bytes_, d_clean_, d_planes_;
   DevBuf<int16_t> d_coef_;
-  DevBuf<int> d_iv_, d_status_;
+  DevBuf<int> d_iv_, d_status_, d_tile_info_, d_scan_len_;
   DevBuf<JpegImageDesc> d_descs_;
   DevBuf<JpegHuff> d_tabs_;
   PinBuf<uint8_t> h_bytes_;

@@ -4,10 +4,11 @@
 // csrc/jpeg_math.h (pinned bit-exact against cv2.imdecode on the host); this header holds the batch descriptors the host planner
 // (jpeg_decode.cu) fills and the three kernels (jpeg_kernels.cu) read:
 //
-//   jpeg_entropy_kernel   one CTA per image: byte-unstuffing + RSTn removal as a stream compaction, then either one thread per
-//                         restart interval, or -- files without restart markers -- self-synchronising decoding: the clean scan is
-//                         cut into windows, every window is decoded from a guessed state, exit states are handed forward until
-//                         nothing changes, block / DC prefix sums place every window, a last pass writes the coefficients.
+//   jpeg_scan_*_kernel    byte-unstuffing + RSTn removal as a stream compaction over the whole batch (count per 4 KB tile, then write).
+//   jpeg_entropy_kernel   one CTA per image: either one thread per restart interval, or -- files without restart markers --
+//                         self-synchronising decoding: the clean scan is cut into windows, every window is decoded from a guessed
+//                         state, exit states are handed forward until nothing changes, block / DC prefix sums place every thread's
+//                         windows, a last pass writes the coefficients.
 //   jpeg_idct_kernel      dequantise + jpeg_idct_islow, 8 lanes per block (one row / one column each), component planes out.
 //   jpeg_color_kernel     fancy h2v2 / h2v1 chroma upsampling + fixed-point YCbCr -> RGB, 4 pixels per thread, into the frame buffer
 //                         the letterbox and ROI kernels read.
@@ -21,9 +22,9 @@
 namespace fdl {
 
 constexpr int kJpegMaxBlocksPerMcu = 10;   // T.81 B.2.3
-constexpr int kJpegMaxWindows = 4096;      // windows per image kept in shared memory (28 B each)
-constexpr int kJpegMinWindowBits = 1024;
-constexpr int kJpegEntropyThreads = 1024;
+constexpr int kJpegMaxWindows = 2304;      // windows per image kept in shared memory (32 B each): two CTAs (images) fit one SM
+constexpr int kJpegMinWindowBits = 1024;   // measured: 544 .. 1536 bits give the same time (3-4 hand-over rounds, each one window long)
+constexpr int kJpegEntropyThreads = 512;
 
 enum { JPEG_OK = 0, JPEG_ERR_BLOCKS = 1, JPEG_ERR_RESTARTS = 2 };
 
@@ -46,15 +47,18 @@ struct JpegImageDesc {
   int cw[3], ch[3];           // the REAL down-sampled size ceil(image * samp / max_samp): the edges fancy upsampling replicates
   int window_bits, nwin_cap;
   int out_stride;             // bytes per output row
-  int _pad;
+  int color_fast;             // 1: jpeg_color_kernel's fast path takes this image (set by the host once the output placement is known)
   uint16_t quant[3][64];      // natural order
 };
 
 // Launchers (jpeg_kernels.cu).  All buffers are the batch's; `status` receives one JPEG_* code per image.
 size_t jpeg_entropy_smem_bytes(int max_windows);
+int jpeg_scan_tiles(long long raw_off, int raw_len);   // 4 KB tiles of the compaction pass for one image
+// compaction (two launches) + the entropy kernel; tile_info: [n][max_tiles][3] ints, scan_len: [n][2] ints of scratch
 cudaError_t launch_jpeg_entropy(const JpegImageDesc* descs, int n, const JpegHuff* tabs, const uint8_t* bytes, uint8_t* clean, int16_t* coef,
-                                int* iv, int* status, int max_windows, cudaStream_t s);
+                                int* iv, int* status, int* tile_info, int max_tiles, int* scan_len, int max_windows, cudaStream_t s);
 cudaError_t launch_jpeg_idct(const JpegImageDesc* descs, int n, int max_quads, const int16_t* coef, uint8_t* planes, cudaStream_t s);
-cudaError_t launch_jpeg_color(const JpegImageDesc* descs, int n, int max_w, int max_h, const uint8_t* planes, uint8_t* out, cudaStream_t s);
+// flags: 1 = some image takes the fast path, 2 = some image takes the generic path
+cudaError_t launch_jpeg_color(const JpegImageDesc* descs, int n, int max_w, int max_h, int flags, const uint8_t* planes, uint8_t* out, cudaStream_t s);
 
 }  // namespace fdl

@@ -20,28 +20,31 @@
 namespace fdl {
 
 // jidctint.c (CONST_BITS 13, PASS1_BITS 2): one 1-D pass over 8 values spaced `stride` apart, in place on int32.
+// All sums and products are taken modulo 2^32 (unsigned): for the coefficients of a valid file nothing overflows and the bits are
+// libjpeg's; for corrupt data (coefficient x quantiser products up to 2^27) the result is garbage but defined -- no signed overflow.
 FDL_JHD void jpeg_idct_1d(int* d, int stride, int in_shift, int descale) {
-  const int i0 = d[0], i1 = d[stride], i2 = d[2 * stride], i3 = d[3 * stride], i4 = d[4 * stride], i5 = d[5 * stride], i6 = d[6 * stride],
-            i7 = d[7 * stride];
+  typedef unsigned U;
+  const U i0 = (U)d[0], i1 = (U)d[stride], i2 = (U)d[2 * stride], i3 = (U)d[3 * stride], i4 = (U)d[4 * stride], i5 = (U)d[5 * stride],
+          i6 = (U)d[6 * stride], i7 = (U)d[7 * stride];
   // even part
-  int z1 = (i2 + i6) * 4433;                        // FIX_0_541196100
-  const int tmp2 = z1 + i6 * (-15137);              // FIX_1_847759065
-  const int tmp3 = z1 + i2 * 6270;                  // FIX_0_765366865
-  const int tmp0 = (int)((unsigned)(i0 + i4) << in_shift), tmp1 = (int)((unsigned)(i0 - i4) << in_shift);
-  const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+  U z1 = (i2 + i6) * 4433u;                         // FIX_0_541196100
+  const U tmp2 = z1 + i6 * (U)(-15137);             // FIX_1_847759065
+  const U tmp3 = z1 + i2 * 6270u;                   // FIX_0_765366865
+  const U tmp0 = (i0 + i4) << in_shift, tmp1 = (i0 - i4) << in_shift;
+  const U tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
   // odd part
-  int t0 = i7, t1 = i5, t2 = i3, t3 = i1;
+  U t0 = i7, t1 = i5, t2 = i3, t3 = i1;
   z1 = t0 + t3;
-  int z2 = t1 + t2, z3 = t0 + t2, z4 = t1 + t3;
-  const int z5 = (z3 + z4) * 9633;                  // FIX_1_175875602
-  t0 *= 2446; t1 *= 16819; t2 *= 25172; t3 *= 12299;
-  z1 *= -7373; z2 *= -20995; z3 = z3 * (-16069) + z5; z4 = z4 * (-3196) + z5;
+  U z2 = t1 + t2, z3 = t0 + t2, z4 = t1 + t3;
+  const U z5 = (z3 + z4) * 9633u;                   // FIX_1_175875602
+  t0 *= 2446u; t1 *= 16819u; t2 *= 25172u; t3 *= 12299u;
+  z1 *= (U)(-7373); z2 *= (U)(-20995); z3 = z3 * (U)(-16069) + z5; z4 = z4 * (U)(-3196) + z5;
   t0 += z1 + z3; t1 += z2 + z4; t2 += z2 + z3; t3 += z1 + z4;
-  const int half = 1 << (descale - 1);
-  d[0] = (tmp10 + t3 + half) >> descale;            d[7 * stride] = (tmp10 - t3 + half) >> descale;
-  d[stride] = (tmp11 + t2 + half) >> descale;       d[6 * stride] = (tmp11 - t2 + half) >> descale;
-  d[2 * stride] = (tmp12 + t1 + half) >> descale;   d[5 * stride] = (tmp12 - t1 + half) >> descale;
-  d[3 * stride] = (tmp13 + t0 + half) >> descale;   d[4 * stride] = (tmp13 - t0 + half) >> descale;
+  const U half = 1u << (descale - 1);
+  d[0] = (int)(tmp10 + t3 + half) >> descale;            d[7 * stride] = (int)(tmp10 - t3 + half) >> descale;
+  d[stride] = (int)(tmp11 + t2 + half) >> descale;       d[6 * stride] = (int)(tmp11 - t2 + half) >> descale;
+  d[2 * stride] = (int)(tmp12 + t1 + half) >> descale;   d[5 * stride] = (int)(tmp12 - t1 + half) >> descale;
+  d[3 * stride] = (int)(tmp13 + t0 + half) >> descale;   d[4 * stride] = (int)(tmp13 - t0 + half) >> descale;
 }
 
 // range_limit[(v) & RANGE_MASK] of jdmaster.c's table, centred on +128
@@ -53,7 +56,7 @@ FDL_JHD uint8_t jpeg_range_limit(int v) {
 // jpeg_idct_islow: quantised coefficients (natural order) x quantisation table (natural order) -> 8x8 samples
 FDL_JHD void jpeg_idct_islow_8x8(const int16_t* coef, const uint16_t* quant, uint8_t* out, int out_stride) {
   int ws[64];
-  for (int i = 0; i < 64; ++i) ws[i] = (int)coef[i] * (int)quant[i];
+  for (int i = 0; i < 64; ++i) ws[i] = (int)((unsigned)(int)coef[i] * (unsigned)quant[i]);
   for (int c = 0; c < 8; ++c) jpeg_idct_1d(ws + c, 8, 13, 13 - 2);               // columns
   for (int r = 0; r < 8; ++r) {
     jpeg_idct_1d(ws + 8 * r, 1, 13, 13 + 2 + 3);                                  // rows
@@ -107,6 +110,8 @@ struct JpegHuff {
   uint16_t look[512];      // (length << 8) | symbol for codes of <= 9 bits (by their 9-bit prefix), 0 otherwise
   int32_t maxcode[18];     // largest code of each length (-1: none); [17] = sentinel
   int32_t valoffset[17];   // huffval index of the first code of each length minus that code
+  uint32_t limit[17];      // limit[l] = the first unused code of length l, left-aligned to 16 bits: a 16-bit peek v holds a code of
+                           // at most l bits iff v < limit[l] (non-decreasing in l; 0x10000 when the code space is full)
   uint8_t huffval[256];
 };
 
@@ -139,10 +144,11 @@ FDL_JHD void jpeg_huff_build(const uint8_t* counts, const uint8_t* symbols, Jpeg
       }
     }
     t->maxcode[l] = counts[l - 1] ? code - 1 : -1;
+    t->limit[l] = (uint32_t)code << (16 - l);
     code <<= 1;
   }
   t->maxcode[17] = 0x7FFFFFFF;
-  t->maxcode[0] = -1; t->valoffset[0] = 0;
+  t->maxcode[0] = -1; t->valoffset[0] = 0; t->limit[0] = 0;
   for (int i = k; i < 256; ++i) t->huffval[i] = 0;
 }
 
@@ -242,7 +248,7 @@ FDL_JHD void jpeg_sync_step(const uint8_t* buf, long long nbits, const JpegHuff*
     const unsigned w = jpeg_peek_clean(buf, nbits, st->pos, 16);
     len = 10;
     int code = (int)(w >> 6);
-    while (len <= 16 && code > t.maxcode[len]) { ++len; code = (int)(w >> (16 - len)); }
+    while (len <= 16 && code > t.maxcode[len]) { ++len; if (len <= 16) code = (int)(w >> (16 - len)); }
     if (len > 16) { len = 16; sym = 0; } else sym = t.huffval[(code + t.valoffset[len]) & 255];
   }
   st->pos += len;

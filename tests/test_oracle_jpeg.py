@@ -225,3 +225,25 @@ def test_self_synchronising_schedule_matches_sequential_decode():
             worst = max(worst, rounds)
             assert rounds <= 12 or rounds < nwin.value // 4, (rounds, nwin.value, redone.value)     # nowhere near sequential
     assert worst >= 2          # the guesses were wrong somewhere: the hand-over was exercised
+
+
+def test_malformed_tables_and_damaged_scans_under_asan_and_ubsan(tmp_path):
+    """a DHT whose code lengths are over-subscribed used to write past the 512-entry look-up table, and a DC
+    symbol > 16 shifted by a negative amount.  tests/hostcheck/jpeg_fuzz.cc drives csrc/jpeg_parse.h + csrc/jpeg_math.h (parser,
+    table build, sequential and window decoders, IDCT) over > 1500 damaged copies of the reference's test images -- targeted DHT
+    damage, random header / scan damage, truncated scans -- compiled with -fsanitize=address,undefined: any out-of-bounds access,
+    signed overflow or bad shift aborts the child process."""
+    import subprocess
+    exe = str(tmp_path / "jpeg_fuzz")
+    src = os.path.join(ROOT, "tests", "hostcheck", "jpeg_fuzz.cc")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", src, "-o", exe])
+    files = sorted(glob.glob(os.path.join(ROOT, "test_data", "*.jpg")))
+    r = subprocess.run([exe] + files, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "no sanitizer report" in r.stdout, (r.stdout[-500:], r.stderr[-3000:])
+    # and the oracle agrees with the parser on the textbook case: three 1-bit codes
+    from oracle import jpeg_decode
+    buf = bytearray(open(files[0], "rb").read())
+    p = buf.index(b"\xff\xc4")
+    buf[p + 5] = 3
+    with pytest.raises(ValueError):
+        jpeg_decode.decode_jpeg_rgb(bytes(buf))
