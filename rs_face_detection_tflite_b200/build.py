@@ -56,8 +56,19 @@ def _deps_mtime() -> float:
     return m
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+# Variant builds for A/B measurements (never the product library): name -> extra nvcc flags.  They land in build_<name>/ and
+# libfdl_b200_<name>.so and are loaded with FDL_LIB=<path>.
+VARIANTS = {"trace": ["-DFDL_WS_TRACE"]}
+
+
+def build(force: bool = False, verbose: bool = False, variant: str | None = None) -> str:
+    global OBJ, LIB
     nvcc = _nvcc()
+    extra_all = []
+    if variant:
+        extra_all = VARIANTS[variant]
+        OBJ = os.path.join(HERE, "build_" + variant)
+        LIB = os.path.join(HERE, "libfdl_b200_%s.so" % variant)
     os.makedirs(OBJ, exist_ok=True)
     hdr = max(_deps_mtime(), os.path.getmtime(os.path.abspath(__file__)))
     jobs = []
@@ -69,7 +80,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         op = os.path.join(OBJ, src.rsplit(".", 1)[0] + ".o")
         objs.append(op)
         if force or not os.path.exists(op) or os.path.getmtime(op) < max(os.path.getmtime(sp), hdr):
-            cmd = [nvcc, "-c", sp, "-o", op, "-x", "cu"] + ARCH + COMMON + extra
+            cmd = [nvcc, "-c", sp, "-o", op, "-x", "cu"] + ARCH + COMMON + extra + extra_all
             if verbose:
                 cmd += ["-Xptxas", "-v"]
             jobs.append(cmd)
@@ -95,4 +106,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
+                variant=sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None))

@@ -36,6 +36,28 @@ namespace fdl {
 void count_launch();
 bool encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, long long bstride, int box_h, int box_w, int box_c = 0);
 
+// FDL_WS_TRACE (variant build only, `python -m rs_face_detection_tflite_b200.build --variant trace`): globaltimer stamps of the first CTAs'
+// first tiles -- [cta][tile][event]: 0 load issued, 1 depthwise sees the tile, 2 depthwise thread 0 done, 3 all depthwise threads done,
+// 4 MMAs issued, 5 epilogue sees the accumulator, 6 epilogue done with the tile, 7 the tile's TMA store issued.
+#ifdef FDL_WS_TRACE
+constexpr int kTraceCtas = 4, kTraceTiles = 48;
+__device__ unsigned long long g_ws_trace[kTraceCtas][kTraceTiles][8];
+#define WS_T(it_, ev_)                                                                                              \
+  do {                                                                                                              \
+    if (blockIdx.x < kTraceCtas && (it_) >= 0 && (it_) < kTraceTiles) {                                            \
+      unsigned long long t_;                                                                                        \
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                                        \
+      g_ws_trace[blockIdx.x][(it_)][(ev_)] = t_;                                                                   \
+    }                                                                                                               \
+  } while (0)
+cudaError_t ws_trace_read(unsigned long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, g_ws_trace, sizeof(unsigned long long) * (size_t)(n < kTraceCtas * kTraceTiles * 8 ? n : kTraceCtas * kTraceTiles * 8));
+}
+#else
+#define WS_T(it_, ev_) do { } while (0)
+cudaError_t ws_trace_read(unsigned long long*, int) { return cudaErrorNotSupported; }
+#endif
+
 namespace {
 
 typedef unsigned long long ull;
@@ -107,7 +129,7 @@ __device__ __forceinline__ float2 unpack_f16x2(uint32_t d) {
   return r;
 }
 
-template <int kMaxT, int kMinB, bool kF16>
+template <int kMaxT, int kMinB, bool kF16, bool kNarrow = false>
 __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                                                                   const BlockTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -126,19 +148,25 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
   uint64_t* acc_full = a_empty + kMaxGroups;                         // [kMaxGroups]  accumulator complete
   uint64_t* acc_empty = acc_full + kMaxGroups;                       // [kMaxGroups]  accumulator drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kMaxGroups);
+  uint64_t* s_desc = reinterpret_cast<uint64_t*>(smem + 160);         // [6] UMMA descriptors + [2] K-step increments, built once (group 0's)
+  int* s_lstep = reinterpret_cast<int*>(smem + 232);                  // [3] tile-coordinate step of consecutive loads (image, row, column)
   float* s_w = reinterpret_cast<float*>(smem + L.w);
 
   const int tiles_per_img = a.tiles_x * a.tiles_y;
 
   const int CP = a.in_pad ? (((C >> 2) | 1) << 2) : C;   // pixel stride (floats) of the input tile in shared memory
   const uint32_t in_bytes = (uint32_t)(ITH * ITW * CP * 4);
-  auto issue_load = [&](int it) {               // the CTA's it-th tile -> stage it % NS
-    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-    const int s = it % NS;
-    const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
-    const int ty = r / a.tiles_x, tx = r - ty * a.tiles_x;
-    ptx::mbar_arrive_expect_tx(&in_full[s], in_bytes);
-    ptx::tma_load_4d(smem + L.in0 + s * L.in_stage, &tm_in, &in_full[s], 0, tx * TW - 1, ty * TH - 1, b);
+  // Loads are issued by ONE thread (tid 0) strictly in tile order, so the tile coordinates advance by a fixed (image, row, column)
+  // step per load: no divisions on the issuing thread's path (it sits in the epilogue's per-tile chain).
+  int l_b = 0, l_ty = 0, l_tx = 0, l_s = 0;     // (live in tid 0 only)
+  auto issue_load = [&](int it) {               // the CTA's it-th tile -> stage it % NS (called with it = 0, 1, 2, ... in order)
+    ptx::mbar_arrive_expect_tx(&in_full[l_s], in_bytes);
+    ptx::tma_load_4d(smem + L.in0 + l_s * L.in_stage, &tm_in, &in_full[l_s], 0, l_tx * TW - 1, l_ty * TH - 1, l_b);
+    WS_T(it, 0);
+    if (++l_s == NS) l_s = 0;
+    l_tx += s_lstep[2]; l_ty += s_lstep[1]; l_b += s_lstep[0];
+    if (l_tx >= a.tiles_x) { l_tx -= a.tiles_x; ++l_ty; }
+    if (l_ty >= a.tiles_y) { l_ty -= a.tiles_y; ++l_b; }
   };
 
   // ---- one-time setup: nothing here depends on the previous launch (PDL, see pdl.h) ----
@@ -149,6 +177,19 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     for (int g = 0; g < G; ++g) { ptx::mbar_init(&a_full[g], (uint32_t)ndwg); ptx::mbar_init(&a_empty[g], 1); }
     for (int t = 0; t < T; ++t) { ptx::mbar_init(&acc_full[t], 1); ptx::mbar_init(&acc_empty[t], 4); }
     ptx::fence_mbar_init();
+    const int t0 = (int)blockIdx.x, r0 = t0 % tiles_per_img;
+    l_b = t0 / tiles_per_img; l_ty = r0 / a.tiles_x; l_tx = r0 - l_ty * a.tiles_x;
+    const int sb = (int)gridDim.x / tiles_per_img, sr = (int)gridDim.x - sb * tiles_per_img;
+    s_lstep[0] = sb; s_lstep[1] = sr / a.tiles_x; s_lstep[2] = sr - (sr / a.tiles_x) * a.tiles_x;
+    const uint32_t w_a = ptx::smem_u32(smem + L.w), lbo_w = (uint32_t)Np * 16u;
+    s_desc[0] = ptx::umma_desc_kmajor(ptx::smem_u32(smem + L.a0), kPlaneBytes, 128);
+    s_desc[1] = ptx::umma_desc_kmajor(ptx::smem_u32(smem + L.a0) + (uint32_t)(Q * kPlaneBytes), kPlaneBytes, 128);
+    s_desc[2] = ptx::umma_desc_kmajor(w_a, lbo_w, 128);
+    s_desc[3] = ptx::umma_desc_kmajor(w_a + (uint32_t)(Q * Np * 16), lbo_w, 128);
+    s_desc[4] = ptx::umma_desc_kmajor(ptx::smem_u32(smem + L.ones), kPlaneBytes, 128);
+    s_desc[5] = ptx::umma_desc_kmajor(ptx::smem_u32(smem + L.wb), lbo_w, 128);
+    s_desc[6] = (uint64_t)((2 * kPlaneBytes) >> 4);
+    s_desc[7] = (uint64_t)((2u * lbo_w) >> 4);
   }
   if (warp == 0) ptx::tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   if (!f16) {
@@ -203,8 +244,88 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     }
     const int step_b = (int)gridDim.x / tiles_per_img, step_r = (int)gridDim.x - step_b * tiles_per_img;
     const int step_y = step_r / a.tiles_x, step_x = step_r - step_y * a.tiles_x;
+    // ---- narrow blocks (N <= 32, residual from the resident input tile, two staging buffers): the epilogue sets the CTA's pace (measured
+    // with FDL_WS_TRACE: ~1.9 us per tile, most of it index arithmetic, runtime-bounded loops and one TMEM round trip per 16
+    // columns), so this path keeps its indices in counters, its residual in six registers and both accumulator halves in flight.
+    if constexpr (kNarrow) {
+      int s = 0, t = 0, ph_in = 0, ph_acc = 0;
+      const int sq = a.skip_c >> 2;
+      const bool relu = a.act == ACT_RELU, prelu = a.act == ACT_PRELU;
+      const float* skip0 = reinterpret_cast<const float*>(smem + L.in0) + ((py + 1) * ITW + (px + 1)) * CP;
+      float* s_o0 = reinterpret_cast<float*>(smem + L.out0) + p * NPf;
+      const int in_stage_f = L.in_stage >> 2, out_stage_f = L.out_stage >> 2;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(warp * 32) << 16);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int ob = it & 1;
+        if (it > 0) {
+          tx += step_x; ty += step_y; b += step_b;
+          if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
+          if (ty >= a.tiles_y) { ty -= a.tiles_y; ++b; }
+        }
+        ptx::mbar_wait(&in_full[s], (uint32_t)ph_in);
+        const float* sk = skip0 + s * in_stage_f;
+        float4 res[4];                                        // residual of the first 16 channels; the second half follows below
+#pragma unroll
+        for (int j = 0; j < 4; ++j) res[j] = j < sq ? ld4(sk + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ptx::mbar_wait(&acc_full[t], (uint32_t)ph_acc);
+        ptx::tc_fence_after_sync();
+        if (tid == 0) WS_T(it, 5);
+        uint32_t r0[16], r1[16];
+        const uint32_t taddr = taddr0 + (uint32_t)(t * acc_cols);
+        ptx::tmem_ld16_issue(taddr, r0);
+        if (Np > 16) ptx::tmem_ld16_issue(taddr + 16u, r1);
+        ptx::fence_proxy_async_smem();
+        if (tid == 0) ptx::tma_store_wait_read0();            // the store of tile it-2 has finished reading buffer `ob`
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0) {
+          if (it > 0) {
+            ptx::tma_store_4d(&tm_out, smem + L.out0 + (ob ^ 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
+            ptx::tma_store_commit();
+            WS_T(it - 1, 7);
+          }
+          // every epilogue warp is past its residual reads of the previous tile's stage: refill it.  (Refilling the CURRENT tile's
+          // stage one tile earlier was measured again in round 2, with this epilogue and the f16 operand: 217 vs 192 us.  More loads
+          // in flight make the launch slower, as in round 1: the memory system prefers the shallower queue.)
+          if (it > 0 && it - 1 + NS < my_tiles) issue_load(it - 1 + NS);
+        }
+        pb = b; pty = ty; ptx_ = tx;
+        ptx::tmem_ld_wait16(r0);
+        if (Np > 16) ptx::tmem_ld_wait16(r1);
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[t]);
+        float* so = s_o0 + ob * out_stage_f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = 16 * h + 4 * j;
+            if (n < N) {
+              const uint32_t* r = h ? r1 : r0;
+              float4 rs = res[j];
+              if (f16) { rs.x += a.bias_c[n]; rs.y += a.bias_c[n + 1]; rs.z += a.bias_c[n + 2]; rs.w += a.bias_c[n + 3]; }
+              float4 o = make_float4(__uint_as_float(r[4 * j]) + rs.x, __uint_as_float(r[4 * j + 1]) + rs.y, __uint_as_float(r[4 * j + 2]) + rs.z,
+                                     __uint_as_float(r[4 * j + 3]) + rs.w);
+              if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              else if (prelu) {                       // slopes come from the kernel parameters (constant bank)
+                o.x = o.x >= 0.f ? o.x : o.x * a.alpha_c[n]; o.y = o.y >= 0.f ? o.y : o.y * a.alpha_c[n + 1];
+                o.z = o.z >= 0.f ? o.z : o.z * a.alpha_c[n + 2]; o.w = o.w >= 0.f ? o.w : o.w * a.alpha_c[n + 3];
+              }
+              *reinterpret_cast<float4*>(so + n) = o;
+            }
+          }
+          if (h == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res[j] = 4 + j < sq ? ld4(sk + 16 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (tid == 0) WS_T(it, 6);
+        if (++s == NS) { s = 0; ph_in ^= 1; }
+        if (++t == T) { t = 0; ph_acc ^= 1; }
+      }
+    } else {
     for (int it = 0; it < my_tiles; ++it) {
-      const int s = it % NS, t = it % T, ob = it & 1;
+      const int s = it % NS, t = it % T, ob = a.out_bufs == 2 ? (it & 1) : 0;
       if (it > 0) {
         tx += step_x; ty += step_y; b += step_b;
         if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
@@ -233,22 +354,24 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       load_res(0, res);
       ptx::mbar_wait(&acc_full[t], (uint32_t)((it / T) & 1));
       ptx::tc_fence_after_sync();
+      if (tid == 0) WS_T(it, 5);
       // ---- deferred TMA store of the PREVIOUS tile: its staging writes have had a whole tile to drain ----
+      // (one staging buffer: the store is issued here too, and this tile's staging writes wait below until it has read the buffer)
       {
         ptx::fence_proxy_async_smem();
-        if (tid == 0) ptx::tma_store_wait_read0();            // the store of tile it-2 has finished reading buffer `ob`
+        if (tid == 0 && a.out_bufs == 2) ptx::tma_store_wait_read0();   // the store of tile it-2 has finished reading buffer `ob`
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (tid == 0 && it > 0) {
-          ptx::tma_store_4d(&tm_out, smem + L.out0 + (ob ^ 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
+          ptx::tma_store_4d(&tm_out, smem + L.out0 + (a.out_bufs == 2 ? (ob ^ 1) : 0) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
           ptx::tma_store_commit();
-          // every epilogue warp is past its residual reads of the previous tile's stage: refill it.  (Refilling the CURRENT
-          // tile's stage here -- legal once its accumulator is complete and its residual is in registers -- or a fourth stage
-          // both measured SLOWER, 246 / 243 vs 237 us: the kernel is not short of loads in flight.)
+          WS_T(it - 1, 7);
+          // every epilogue warp is past its residual reads of the previous tile's stage: refill it
           if (it - 1 + NS < my_tiles) issue_load(it - 1 + NS);
         }
       }
       pb = b; pty = ty; ptx_ = tx;
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * acc_cols);
+      bool staging_free = a.out_bufs == 2;
       for (int c0 = 0; c0 < Np; c0 += 32) {
         if (c0 + 32 < Np) load_res(c0 + 32, resn);
 #pragma unroll
@@ -258,6 +381,11 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
           uint32_t r[16];
           ptx::tmem_ld16_issue(taddr + (uint32_t)ch, r);
           ptx::tmem_ld_wait16(r);
+          if (!staging_free) {                    // single staging buffer: the previous tile's store (issued above) must have read it
+            if (tid == 0) ptx::tma_store_wait_read0();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            staging_free = true;
+          }
           if (ch + 16 >= Np) {                    // accumulator drained: hand it back to the issuing thread
             ptx::tc_fence_before_sync();
             __syncwarp();
@@ -283,13 +411,15 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 8; ++j) res[j] = resn[j];
       }
+      if (tid == 0) WS_T(it, 6);
+    }
     }
     // the last tile's store
     ptx::fence_proxy_async_smem();
     if (tid == 0) ptx::tma_store_wait_read0();
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (tid == 0) {
-      ptx::tma_store_4d(&tm_out, smem + L.out0 + ((my_tiles - 1) & 1) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
+      ptx::tma_store_4d(&tm_out, smem + L.out0 + (a.out_bufs == 2 ? ((my_tiles - 1) & 1) : 0) * L.out_stage, 0, ptx_ * TW, pty * TH, pb);
       ptx::tma_store_commit();
       ptx::tma_store_wait_all0();
     }
@@ -299,8 +429,8 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     const int g = dtid / ndwg, gt = dtid - g * ndwg;
     // Q == 6, one item per thread: with the plain 6-quad pixel stride the items are remapped for conflict-free stores (kMapQ6);
     // with the padded 7-quad stride (f16 mode: shared memory allows it) "x fastest" is conflict-free for loads AND stores.
-    const bool xfast = Q == 6 && ndwg == 192 && a.in_pad;
-    const bool map6 = Q == 6 && ndwg == 192 && !a.in_pad;
+    const bool xfast = Q == 6 && (ndwg == 192 || ndwg == 96) && a.in_pad;
+    const bool map6 = Q == 6 && (ndwg == 192 || ndwg == 96) && !a.in_pad;
     const int m6 = map6 ? kMapQ6[gt % 96] : 0;
     const int q = map6 ? (m6 & 15) : (xfast ? (gt / TW) % Q : gt % Q);    // the channel quad is fixed per thread
     ull wd[9][2], bd[2];
@@ -321,12 +451,16 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     const int nitems = Q * 2 * TW;
     // MMA issue state (used by the group's first thread only)
     const uint32_t idesc = f16 ? ptx::umma_idesc_f16(128, Np) : ptx::umma_idesc_tf32(128, Np);
-    const uint32_t w_addr = ptx::smem_u32(s_w), wb_addr = ptx::smem_u32(smem + L.wb), ones_addr = ptx::smem_u32(smem + L.ones);
-    const uint32_t w_lbo = (uint32_t)Np * 16u;
-    const uint32_t ahi_addr = ptx::smem_u32(s_ahi), alo_addr = ahi_addr + (uint32_t)(Q * kPlaneBytes);
+    // The MMA chain is issued by the group's first thread between two of its own depthwise items: every instruction it spends
+    // there delays the whole group's next tile (measured: 0.75 us per tile with the descriptors rebuilt per instruction).  The
+    // descriptors are built once; a K step only adds to their 14-bit address fields.
+    // (kept in shared memory -- only the issuing thread needs them, and the depthwise loop is at the register cap -- as group 0's
+    // A descriptors; group g's differ by its buffer offset in the address field)
+    const uint64_t a_goff = (uint64_t)((uint32_t)(g * L.a_buf) >> 4);
     for (int it = g; it < my_tiles; it += G) {
       const int s = it % NS, kg = it / G, t = it % T;
       ptx::mbar_wait(&in_full[s], (uint32_t)((it / NS) & 1));
+      if (gt == 0) WS_T(it, 1);
       const float* s_in = reinterpret_cast<const float*>(smem + L.in0 + s * L.in_stage);
       for (int item = gt, ii = 0; item < nitems; item += ndwg, ++ii) {
         int x, half;                            // (runtime divisions by Q only on the generic path)
@@ -393,42 +527,38 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       ptx::fence_proxy_async_smem();            // generic-proxy writes of A -> visible to the tensor core (async proxy)
       mbar_arrive(&a_full[g]);
       if (gt == 0) {
+        WS_T(it, 2);
         // ---- this tile's MMA chain, issued by one thread ----
         ptx::mbar_wait(&a_full[g], (uint32_t)(kg & 1));
+        WS_T(it, 3);
         if (it >= T) ptx::mbar_wait(&acc_empty[t], (uint32_t)(((it / T) - 1) & 1));
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(t * acc_cols);
+        const uint64_t d_ahi = s_desc[0] + a_goff, d_alo = s_desc[1] + a_goff, d_w = s_desc[2], d_w2 = s_desc[3], a_step = s_desc[6], b_step = s_desc[7];
         if (f16) {
           // kind::f16, K = 16 = two planes = two channel quads x (hi, lo); pass 0: (A_hi, A_lo) * (W, W), pass 1: (A_hi, A_lo) * (W_lo, 0)
           const int ksteps16 = Q >> 1;
           for (int pass = 0; pass < a.wsplit16; ++pass) {
-            const uint32_t b_base = w_addr + (uint32_t)(pass * Q * Np * 16);
-            for (int ks = 0; ks < ksteps16; ++ks) {
-              const uint64_t ad = ptx::umma_desc_kmajor(ahi_addr + (uint32_t)(ks * 2 * kPlaneBytes), kPlaneBytes, 128);
-              const uint64_t bdsc = ptx::umma_desc_kmajor(b_base + (uint32_t)ks * 2u * w_lbo, w_lbo, 128);
-              ptx::mma_f16(d_tmem, ad, bdsc, idesc, (pass | ks) ? 1u : 0u);
-            }
+            uint64_t ad = d_ahi, bdsc = pass ? d_w2 : d_w;
+            for (int ks = 0; ks < ksteps16; ++ks, ad += a_step, bdsc += b_step) ptx::mma_f16(d_tmem, ad, bdsc, idesc, (pass | ks) ? 1u : 0u);
           }
           ptx::mma_commit(&acc_full[t]);
           ptx::mma_commit(&a_empty[g]);
+          WS_T(it, 4);
           continue;
         }
         // bias K step first (overwrites the accumulator), then the hi / lo passes accumulate
-        ptx::mma_tf32(d_tmem, ptx::umma_desc_kmajor(ones_addr, kPlaneBytes, 128), ptx::umma_desc_kmajor(wb_addr, w_lbo, 128), idesc, 0u);
+        ptx::mma_tf32(d_tmem, s_desc[4], s_desc[5], idesc, 0u);
         const int ksteps = C >> 3;
         const int npass = a.wsplit == 2 ? 3 : 2;
         for (int pass = 0; pass < npass; ++pass) {
           // pass 0: A_lo * W_hi, pass 1: A_hi * W_hi, pass 2: A_hi * W_lo
-          const uint32_t a_base = pass == 0 ? alo_addr : ahi_addr;
-          const uint32_t b_base = pass == 2 ? w_addr + (uint32_t)(Q * Np * 16) : w_addr;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t ad = ptx::umma_desc_kmajor(a_base + (uint32_t)(ks * 2 * kPlaneBytes), kPlaneBytes, 128);
-            const uint64_t bdsc = ptx::umma_desc_kmajor(b_base + (uint32_t)ks * 2u * w_lbo, w_lbo, 128);
-            ptx::mma_tf32(d_tmem, ad, bdsc, idesc, 1u);
-          }
+          uint64_t ad = pass == 0 ? d_alo : d_ahi, bdsc = pass == 2 ? d_w2 : d_w;
+          for (int ks = 0; ks < ksteps; ++ks, ad += a_step, bdsc += b_step) ptx::mma_tf32(d_tmem, ad, bdsc, idesc, 1u);
         }
         ptx::mma_commit(&acc_full[t]);
         ptx::mma_commit(&a_empty[g]);
+        WS_T(it, 4);
       }
     }
   }
@@ -445,16 +575,20 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
 // wavefronts and all its bank conflicts, and measures no faster (229.9 vs 227.6 us on the 128x128x24 stage, 47 vs 45 us at 32x32x48):
 // the kernel is not bound by shared-memory bandwidth.  The serial kernel does use it (room for a second stage).
 bool ws_f16_enabled() {
-  static const bool on = [] { const char* e = getenv("FDL_WS_F16"); return e ? atoi(e) != 0 : false; }();
+  static const bool on = [] { const char* e = getenv("FDL_WS_F16"); return e ? atoi(e) != 0 : true; }();
   return on;
 }
 
 bool pick_cfg(int C, int N, int Np, int wsplit, int f16, WsCfg* cfg) {
   const int Q = C / 4;
   int G = 1, ipt = 1, ctas = 1;
+  // FDL_WS_CTAS=3 (f16 operand only): three smaller CTAs per SM for the narrow blocks -- 96 depthwise threads (two items each), two input
+  // stages, one staging buffer: six tiles in flight per SM instead of four.
+  static const int ctas_env = getenv("FDL_WS_CTAS") ? atoi(getenv("FDL_WS_CTAS")) : 2;
+  const bool three = ctas_env == 3 && f16 && (Q == 4 || Q == 6);
   switch (Q) {
-    case 4: G = 1; ipt = 1; ctas = 2; break;
-    case 6: G = 1; ipt = 1; ctas = 2; break;
+    case 4: G = 1; ipt = three ? 2 : 1; ctas = three ? 3 : 2; break;
+    case 6: G = 1; ipt = three ? 2 : 1; ctas = three ? 3 : 2; break;
     case 8: G = 3; ipt = 2; break;
     default:
       ipt = 1;
@@ -469,15 +603,17 @@ bool pick_cfg(int C, int N, int Np, int wsplit, int f16, WsCfg* cfg) {
   static const int pad6 = getenv("FDL_WS_PAD6") ? atoi(getenv("FDL_WS_PAD6")) : 1;   // A/B: padded stride + 3 stages vs plain stride + 4 stages
   const int in_pad = (Q % 8 == 0 || (f16 && Q == 6 && pad6)) ? 1 : 0;
   static const int ns_cap = getenv("FDL_WS_NS") ? atoi(getenv("FDL_WS_NS")) : 0;
-  const int budget = ctas == 2 ? (233472 / 2 - 1024) : kMaxSmemWs;
+  const int budget = ctas == 3 ? (233472 / 3 - 1024) : (ctas == 2 ? (233472 / 2 - 1024) : kMaxSmemWs);
+  static const int ob_env = getenv("FDL_WS_OB") ? atoi(getenv("FDL_WS_OB")) : 0;
+  const int OB = ob_env == 1 || ob_env == 2 ? ob_env : (ctas == 3 ? 1 : 2);
   for (; G >= 1; --G) {
     const int ndwg = 32 * Q / ipt;
-    if (kEpiThreads + G * ndwg > (ctas == 2 ? 320 : kMaxThreads)) continue;
-    for (int NS = (G + 3 < kMaxStages ? G + 3 : kMaxStages); NS >= G + 2; --NS) {   // the refill of a stage trails its tile by one epilogue
+    if (kEpiThreads + G * ndwg > (ctas == 3 ? 224 : (ctas == 2 ? 320 : kMaxThreads))) continue;
+    for (int NS = (G + 3 < kMaxStages ? G + 3 : kMaxStages); NS >= (ctas == 3 ? 2 : G + 2); --NS) {   // the refill of a stage trails its tile by one epilogue
       if (ns_cap && NS > ns_cap && NS > G + 2) continue;
-      WsLayout L = ws_layout(C, N, Np, wsplit, NS, G, 2, in_pad, f16);
+      WsLayout L = ws_layout(C, N, Np, wsplit, NS, G, OB, in_pad, f16);
       if (L.total <= budget) {
-        cfg->G = G; cfg->ipt = ipt; cfg->ndwg = ndwg; cfg->NS = NS; cfg->OB = 2; cfg->threads = kEpiThreads + G * ndwg; cfg->total = L.total;
+        cfg->G = G; cfg->ipt = ipt; cfg->ndwg = ndwg; cfg->NS = NS; cfg->OB = OB; cfg->threads = kEpiThreads + G * ndwg; cfg->total = L.total;
         cfg->ctas = ctas; cfg->in_pad = in_pad; cfg->f16 = f16;
         return true;
       }
@@ -492,6 +628,9 @@ cudaError_t block_ws_init() {
   cudaError_t e = cudaFuncSetAttribute(block_ws_kernel<512, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<512, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<320, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<224, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<320, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<320, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(block_ws_kernel<320, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
 }
@@ -535,7 +674,12 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   int grid = persist_sms() * cfg.ctas;
   if (grid > ntiles) grid = ntiles;
   cudaError_t e;
-  if (cfg.ctas == 2 && a.f16) e = launch_pdl(block_ws_kernel<320, 2, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
+  static const int narrow_env = getenv("FDL_WS_NARROW") ? atoi(getenv("FDL_WS_NARROW")) : 1;
+  const bool narrow = narrow_env && cfg.ctas == 2 && a.Np <= 32 && a.skip_mode == 1 && cfg.OB == 2;
+  if (narrow && a.f16) e = launch_pdl(block_ws_kernel<320, 2, true, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
+  else if (narrow) e = launch_pdl(block_ws_kernel<320, 2, false, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
+  else if (cfg.ctas == 3) e = launch_pdl(block_ws_kernel<224, 3, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
+  else if (cfg.ctas == 2 && a.f16) e = launch_pdl(block_ws_kernel<320, 2, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
   else if (cfg.ctas == 2) e = launch_pdl(block_ws_kernel<320, 2, false>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
   else if (a.f16) e = launch_pdl(block_ws_kernel<512, 1, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
   else e = launch_pdl(block_ws_kernel<512, 1, false>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);

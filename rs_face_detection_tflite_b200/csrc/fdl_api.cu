@@ -96,7 +96,7 @@ struct fdl_iris_model {
   DevBuf<float> out;
 };
 
-namespace fdl { cudaError_t jpeg_debug_phases(long long out[8]); }
+namespace fdl { cudaError_t jpeg_debug_phases(long long out[8]); cudaError_t ws_trace_read(unsigned long long* out, int n); }
 
 struct fdl_jpeg_decoder {
   int device = 0;
@@ -849,6 +849,12 @@ int fdl_jpeg_decode(fdl_jpeg_decoder* d, const uint8_t* const* data, const size_
 FDL_API int fdl_debug_jpeg_phases(long long* out8) {
   if (!out8) return FDL_ERR_INVALID;
   return fdl::jpeg_debug_phases(out8) == cudaSuccess ? FDL_OK : FDL_ERR_CUDA;
+}
+
+// not in fdl.h: timeline of block_ws_kernel's first CTAs (variant build with -DFDL_WS_TRACE only; FDL_ERR_INVALID otherwise)
+FDL_API int fdl_debug_ws_trace(unsigned long long* out, int n) {
+  if (!out) return FDL_ERR_INVALID;
+  return fdl::ws_trace_read(out, n) == cudaSuccess ? FDL_OK : FDL_ERR_INVALID;
 }
 
 int fdl_decode_jpeg(int device, const uint8_t* data, size_t len, uint8_t* out_rgb, size_t cap, int* width, int* height) try {

@@ -28,10 +28,10 @@ __global__ void ldg_copy(const float4* __restrict__ in, float4* __restrict__ out
 constexpr int TH = 8, TW = 16, ITH = 10, ITW = 18;
 
 __global__ void __launch_bounds__(64) tile_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, int B, int H, int W, int C,
-                                                  int NS, int do_store) {
+                                                  int NS, int do_store, int CPin) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-  const int stage_bytes = (ITH * ITW * C * 4 + 127) / 128 * 128;
+  const int stage_bytes = (ITH * ITW * CPin * 4 + 127) / 128 * 128;
   uint8_t* buf = smem + 1024;
   const int tx_n = W / TW, ty_n = H / TH, per_img = tx_n * ty_n, ntiles = B * per_img;
   if (threadIdx.x == 0) {
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(64) tile_kernel(const __grid_constant__ CUtens
     auto issue = [&](int it) {
       const int tile = blockIdx.x + it * gridDim.x, s = it % NS;
       const int b = tile / per_img, r = tile % per_img, ty = r / tx_n, tx = r % tx_n;
-      ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(ITH * ITW * C * 4));
+      ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)(ITH * ITW * CPin * 4));
       ptx::tma_load_4d(buf + s * stage_bytes, &tm_in, &full[s], 0, tx * TW - 1, ty * TH - 1, b);
     };
     for (int it = 0; it < NS && it < my; ++it) issue(it);
@@ -112,17 +112,19 @@ int main(int argc, char** argv) {
   EncodeFn enc = nullptr;
   cudaDriverEntryPointQueryResult qr;
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&enc, cudaEnableDefault, &qr));
-  auto make = [&](float* base, int bh, int bw) {
+  auto make = [&](float* base, int bh, int bw, int bc = 0) {
     CUtensorMap m;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)bw, (cuuint32_t)bh, 1}, es[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)(bc ? bc : C), (cuuint32_t)bw, (cuuint32_t)bh, 1}, es[4] = {1, 1, 1, 1};
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); exit(1); }
     return m;
   };
   CUtensorMap tm_in = make(in, ITH, ITW), tm_out = make(out, TH, TW);
+  const int CP = ((C / 4) | 1) * 4;
+  CUtensorMap tm_in_pad = make(in, ITH, ITW, CP), tm_out_pad = make(out, TH, TW, CP);
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   auto timeit = [&](const char* name, double bytes, auto&& launch) {
@@ -148,9 +150,16 @@ int main(int argc, char** argv) {
       if (sm * ctas > 220 * 1024) continue;
       char name[96];
       snprintf(name, sizeof name, "tile loads   ctas/SM=%d NS=%d", ctas, NS);
-      timeit(name, rd, [&] { tile_kernel<<<148 * ctas, 64, sm>>>(tm_in, tm_out, B, H, W, C, NS, 0); });
+      timeit(name, rd, [&] { tile_kernel<<<148 * ctas, 64, sm>>>(tm_in, tm_out, B, H, W, C, NS, 0, C); });
       snprintf(name, sizeof name, "tile ld+st   ctas/SM=%d NS=%d", ctas, NS);
-      timeit(name, 2 * rd, [&] { tile_kernel<<<148 * ctas, 64, sm>>>(tm_in, tm_out, B, H, W, C, NS, 1); });
+      timeit(name, 2 * rd, [&] { tile_kernel<<<148 * ctas, 64, sm>>>(tm_in, tm_out, B, H, W, C, NS, 1, C); });
+      const size_t smp = 1024 + (size_t)NS * ((ITH * ITW * CP * 4 + 127) / 128 * 128);
+      if (smp * ctas <= 220 * 1024) {
+        snprintf(name, sizeof name, "tile ld+st(pad-box st) c=%d NS=%d", ctas, NS);
+        timeit(name, 2 * rd, [&] { tile_kernel<<<148 * ctas, 64, sm>>>(tm_in, tm_out_pad, B, H, W, C, NS, 1, C); });
+        snprintf(name, sizeof name, "tile ld+st(pad-box ld+st) c=%d NS=%d", ctas, NS);
+        timeit(name, 2 * rd, [&] { tile_kernel<<<148 * ctas, 64, smp>>>(tm_in_pad, tm_out_pad, B, H, W, C, NS, 1, CP); });
+      }
     }
   const int row_bytes = W * C * 4;
   for (int ctas = 1; ctas <= 4; ctas *= 2)
