@@ -109,6 +109,8 @@ typedef struct fdl_iris_model fdl_iris_model;
 typedef struct fdl_net fdl_net;
 typedef struct fdl_pipeline fdl_pipeline;
 typedef struct fdl_jpeg_decoder fdl_jpeg_decoder;
+typedef struct fdl_pool fdl_pool;
+typedef struct fdl_frame fdl_frame;
 
 /* ---------------------------------------------------------------- library */
 FDL_API const char* fdl_last_error(void);
@@ -342,6 +344,35 @@ FDL_API float fdl_pipeline_last_device_ms(const fdl_pipeline*);
  * net, [3] SSD post-process, [4] face ROI + warp, [5] landmark net, [6] landmark post + eye warp,
  * [7] iris net, [8] iris post, [9] D2H. */
 FDL_API int fdl_pipeline_stage_ms(const fdl_pipeline*, float* out10);
+
+/* ---------------------------------------------------------------- all GPUs of a box behind one handle */
+/* The path shards by frame and has no exchange step (face_detection.rs:205 `infer(&self, ..)` is pure given the weights), so a box
+ * of N GPUs is N independent pipelines.  fdl_pool owns one fdl_pipeline per listed device (a device may be listed more than once)
+ * and one host worker thread per pipeline, pinned to the CPU cores local to that GPU: fdl_pool_submit* hands the batch to the
+ * least-loaded device's worker and returns at once, so one application thread keeps every GPU fed -- header parsing, staging and
+ * the ~300 stream operations of a batch run on the workers, in parallel.  Tickets are pool-wide.  `cfg->device` is ignored.
+ * Frame memory given to fdl_pool_submit must stay valid until the ticket is collected; results come back in submit order per
+ * ticket, exactly as from fdl_pipeline_collect (including FDL_ERR_CAPACITY / FDL_ERR_INVALID reports). */
+FDL_API int fdl_pool_create(const fdl_pipeline_config* cfg, const int* devices, int n_devices, fdl_pool** out);
+FDL_API void fdl_pool_destroy(fdl_pool*);
+FDL_API int fdl_pool_devices(const fdl_pool*);             /* pipelines in the pool */
+FDL_API int fdl_pool_depth(const fdl_pool*);               /* tickets that may be in flight: devices x fdl_pipeline_depth */
+FDL_API int fdl_pool_submit(fdl_pool*, const fdl_image* frames, int n, int* ticket);
+FDL_API int fdl_pool_submit_jpeg(fdl_pool*, const uint8_t* const* data, const size_t* len, int n, int* ticket);
+/* device_index (optional) receives the index (into `devices`) of the pipeline that ran the ticket. */
+FDL_API int fdl_pool_collect(fdl_pool*, int ticket, fdl_frame_result* frame_results, fdl_face_result* face_results, int* n,
+                             int* device_index);
+
+/* ---------------------------------------------------------------- a frame staged once for the per-frame API */
+/* lib.rs:20-40 passes the same `&Mat` to FaceDetection::infer, FaceLandmark::infer and IrisLandmark::infer (x2).  With host images
+ * every one of those calls uploads the frame again; an fdl_frame uploads it once (or decodes it on the device from JPEG bytes,
+ * utils.rs:8-21) and fdl_frame_image() describes the device copy as an fdl_image (mem = FDL_MEM_DEVICE) that the infer calls
+ * read in place.  The image stays valid until fdl_frame_destroy or the next upload into the same handle. */
+FDL_API int fdl_frame_create(int device, fdl_frame** out);
+FDL_API void fdl_frame_destroy(fdl_frame*);
+FDL_API int fdl_frame_upload(fdl_frame*, const fdl_image* image);
+FDL_API int fdl_frame_upload_jpeg(fdl_frame*, const uint8_t* data, size_t len);
+FDL_API int fdl_frame_image(const fdl_frame*, fdl_image* out);
 
 #ifdef __cplusplus
 }

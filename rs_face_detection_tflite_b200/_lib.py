@@ -123,6 +123,18 @@ SYMBOLS = {
     "fdl_jpeg_decoder_destroy": (None, [_vp]),
     "fdl_jpeg_decode": (C.c_int, [_vp, _P(_vp), _P(C.c_size_t), C.c_int, _vp, C.c_size_t, C.c_int, _P(C.c_int64), _P(C.c_int32), _P(C.c_int32)]),
     "fdl_decode_jpeg": (C.c_int, [C.c_int, _vp, C.c_size_t, _vp, C.c_size_t, _P(C.c_int), _P(C.c_int)]),
+    "fdl_pool_create": (C.c_int, [_P(CPipelineConfig), _P(C.c_int), C.c_int, _P(_vp)]),
+    "fdl_pool_destroy": (None, [_vp]),
+    "fdl_pool_devices": (C.c_int, [_vp]),
+    "fdl_pool_depth": (C.c_int, [_vp]),
+    "fdl_pool_submit": (C.c_int, [_vp, _P(CImage), C.c_int, _P(C.c_int)]),
+    "fdl_pool_submit_jpeg": (C.c_int, [_vp, _P(_vp), _P(C.c_size_t), C.c_int, _P(C.c_int)]),
+    "fdl_pool_collect": (C.c_int, [_vp, C.c_int, _P(CFrameResult), _P(CFaceResult), _P(C.c_int), _P(C.c_int)]),
+    "fdl_frame_create": (C.c_int, [C.c_int, _P(_vp)]),
+    "fdl_frame_destroy": (None, [_vp]),
+    "fdl_frame_upload": (C.c_int, [_vp, _P(CImage)]),
+    "fdl_frame_upload_jpeg": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "fdl_frame_image": (C.c_int, [_vp, _P(CImage)]),
     "fdl_pipeline_last_device_ms": (C.c_float, [_vp]),
     "fdl_pipeline_stage_ms": (C.c_int, [_vp, _P(C.c_float)]),
 }

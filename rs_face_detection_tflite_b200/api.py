@@ -135,8 +135,57 @@ class IrisResults:  # iris_landmark.rs:115-129
 
 
 # ------------------------------------------------------------------------------------------------
+class Frame:
+    """A frame staged once on the device for the per-frame API (fdl_frame): lib.rs:20-40 hands the same ``&Mat`` to four ``infer``
+    calls; with a ``Frame`` the pixels cross PCIe once -- or never uncompressed: ``Frame(jpeg=bytes)`` is ``convert_image_to_mat``
+    (utils.rs:8-21) decoded on the device.  Pass it wherever an image is accepted."""
+
+    def __init__(self, image=None, jpeg=None, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().fdl_frame_create(device, C.byref(self._h)))
+        self.device = device
+        if image is not None:
+            self.upload(image)
+        elif jpeg is not None:
+            self.upload_jpeg(jpeg)
+
+    def upload(self, image):
+        img, _keep = _image(image)
+        check(lib().fdl_frame_upload(self._h, C.byref(img)))
+        return self
+
+    def upload_jpeg(self, data):
+        a, ln, _k = _buffer_address(data)
+        check(lib().fdl_frame_upload_jpeg(self._h, a, ln))
+        return self
+
+    def _cimage(self) -> CImage:
+        img = CImage()
+        check(lib().fdl_frame_image(self._h, C.byref(img)))
+        return img
+
+    @property
+    def size(self):
+        """(width, height), as ``Mat::size()``."""
+        img = self._cimage()
+        return img.width, img.height
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fdl_frame_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _image(image):
-    """-> (CImage, keepalive).  numpy uint8 [H,W,3] (host) or CUDA torch uint8 tensor [H,W,3]."""
+    """-> (CImage, keepalive).  numpy uint8 [H,W,3] (host), CUDA torch uint8 tensor [H,W,3], or a Frame."""
+    if isinstance(image, Frame):
+        return image._cimage(), image
     if isinstance(image, np.ndarray):
         if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] != 3:
             raise FdlError(_lib.FDL_ERR_INVALID, "image must be uint8 [H,W,3] RGB")
@@ -722,6 +771,73 @@ class JpegDecoder:
         out = torch.empty(total, dtype=torch.uint8, device="cuda:%d" % self.device)
         check(lib().fdl_jpeg_decode(self._h, ptrs, lens, n, out.data_ptr(), total, _lib.MEM_DEVICE, offs, ws, hs))
         return out, list(offs), list(ws), list(hs)
+
+
+class Pool(Pipeline):
+    """Every GPU of a box behind one handle (fdl_pool): one pipeline + one host worker thread per device, least-loaded dispatch,
+    pool-wide tickets.  Same ``submit`` / ``submit_jpeg`` / ``collect`` / ``run`` as ``Pipeline``; up to ``depth`` tickets in flight."""
+
+    def __init__(self, devices, detector_model: FaceDetectionModel = FaceDetectionModel.BackCamera, frame_size=(1920, 1080), max_batch: int = 64,
+                 max_faces: int = 1, run_landmarks: bool = True, run_iris: bool = True, model_dir: str | None = None,
+                 zero_copy_host: bool = False, refine_landmarks: bool = False, focal_length_mm: float = 0.0, allow_truncated: bool = False):
+        self._h = C.c_void_p()
+        self.allow_truncated = bool(allow_truncated)
+        self._dir = os.fsencode(model_dir) if model_dir else None
+        cfg = CPipelineConfig(int(detector_model), 0, max_batch, max_faces, int(frame_size[0]), int(frame_size[1]),
+                              1 if run_landmarks else 0, 1 if (run_iris and run_landmarks) else 0, self._dir, 1 if zero_copy_host else 0,
+                              1 if refine_landmarks else 0, float(focal_length_mm))
+        self.refine_landmarks, self.focal_length_mm = bool(refine_landmarks), float(focal_length_mm)
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        check(lib().fdl_pool_create(C.byref(cfg), devs, len(devices), C.byref(self._h)))
+        self.devices = list(devices)
+        self.max_batch, self.max_faces = max_batch, max_faces
+        self.frame_size = (int(frame_size[0]), int(frame_size[1]))
+        self.run_landmarks, self.run_iris = run_landmarks, run_iris and run_landmarks
+        self._frames = (CFrameResult * max_batch)()
+        self._faces = (CFaceResult * (max_batch * max_faces))()
+        self._keep = {}
+        self.last_device_index = None
+
+    @property
+    def depth(self) -> int:
+        return lib().fdl_pool_depth(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fdl_pool_destroy(self._h)
+            self._h = None
+
+    def submit(self, frames) -> int:
+        arr, n, keep = self._images(frames)
+        t = C.c_int()
+        check(lib().fdl_pool_submit(self._h, arr, n, C.byref(t)))
+        self._keep[t.value] = (keep, arr)
+        return t.value
+
+    def submit_jpeg(self, files) -> int:
+        ptrs, lens, n, keep = _jpeg_args(files)
+        t = C.c_int()
+        check(lib().fdl_pool_submit_jpeg(self._h, ptrs, lens, n, C.byref(t)))
+        self._keep[t.value] = (keep, ptrs, lens)
+        return t.value
+
+    def collect_raw(self, ticket: int) -> int:
+        n, dev = C.c_int(), C.c_int()
+        rc = lib().fdl_pool_collect(self._h, ticket, self._frames, self._faces, C.byref(n), C.byref(dev))
+        self._keep.pop(ticket, None)
+        self.last_device_index = dev.value
+        if rc == _lib.FDL_ERR_CAPACITY and self.allow_truncated:
+            return n.value
+        check(rc)
+        return n.value
+
+    @property
+    def last_device_ms(self):
+        raise AttributeError("per-device timings are not exposed by the pool")
+
+    @property
+    def stage_ms(self):
+        raise AttributeError("per-device timings are not exposed by the pool")
 
 
 def letterbox_row_plan(frame_size, input_size: int):

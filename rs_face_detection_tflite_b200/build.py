@@ -37,6 +37,7 @@ SOURCES = {
     "jpeg_decode.cu": [],
     "fdl_api.cu": [],
     "pipeline.cu": [],
+    "pool.cu": [],
 }
 
 

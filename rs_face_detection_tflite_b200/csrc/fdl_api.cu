@@ -67,6 +67,7 @@ struct fdl_detector {
   DevBuf<uint8_t> frames;
   DevBuf<I2TParams> params;
   DevBuf<fdl_rect> rois;
+  PinBuf<fdl_rect> h_rois;
   DevBuf<fdl_detection> dets;
   DevBuf<int> counts;      // [2B]: clamped count, total count
   DevBuf<double> padding;
@@ -82,6 +83,7 @@ struct fdl_landmark_model {
   DevBuf<uint8_t> frames;
   DevBuf<I2TParams> params;
   DevBuf<fdl_rect> rois;
+  PinBuf<fdl_rect> h_rois;
   DevBuf<float> out;   // projected landmarks
   DevBuf<int> flags;
 };
@@ -93,10 +95,19 @@ struct fdl_iris_model {
   DevBuf<uint8_t> frames;
   DevBuf<I2TParams> params;
   DevBuf<fdl_rect> rois;
+  PinBuf<fdl_rect> h_rois;
   DevBuf<float> out;
 };
 
 namespace fdl { cudaError_t jpeg_debug_phases(long long out[8]); cudaError_t ws_trace_read(unsigned long long* out, int n); }
+
+struct fdl_frame {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf<uint8_t> buf;
+  int w = 0, h = 0;
+  JpegDecoder dec;
+};
 
 struct fdl_jpeg_decoder {
   int device = 0;
@@ -347,7 +358,8 @@ static int detector_infer_impl(fdl_detector* d, const fdl_image* images, int bat
   if (!d || !images || !n_out || batch <= 0 || cap < 0 || (cap > 0 && !out)) return set_error(FDL_ERR_INVALID, "bad arguments");
   FDL_CUDA_TRY(cudaSetDevice(d->device));
   int w, h;
-  int rc = stage_frames(images, batch, &d->frames, d->stream, &w, &h);
+  const uint8_t* fptr = nullptr;                  // device-resident, tightly packed images (an fdl_frame) are read in place
+  int rc = stage_frames(images, batch, &d->frames, d->stream, &w, &h, &fptr);
   if (rc) return rc;
   Net* net = d->nh.net;
   std::string err;
@@ -356,15 +368,17 @@ static int detector_infer_impl(fdl_detector* d, const fdl_image* images, int bat
   const fdl_rect* d_roi = nullptr;
   if (roi) {
     FDL_CUDA_TRY(d->rois.reserve((size_t)batch));
-    std::vector<fdl_rect> r((size_t)batch, *roi);
-    FDL_CUDA_TRY(cudaMemcpyAsync(d->rois.p, r.data(), r.size() * sizeof(fdl_rect), cudaMemcpyHostToDevice, d->stream));
-    FDL_CUDA_TRY(cudaStreamSynchronize(d->stream));
+    // staged through a pinned slot: the copy is ordered on the stream, and the slot is free again when this call returns (every
+    // infer ends with a stream synchronize) -- no extra synchronize per ROI
+    FDL_CUDA_TRY(d->h_rois.reserve((size_t)batch));
+    for (int b = 0; b < batch; ++b) d->h_rois.p[b] = *roi;
+    FDL_CUDA_TRY(cudaMemcpyAsync(d->rois.p, d->h_rois.p, (size_t)batch * sizeof(fdl_rect), cudaMemcpyHostToDevice, d->stream));
     d_roi = d->rois.p;
   }
   // image_to_tensor(image, roi, (S,S), keep_aspect_ratio=true, (-1,1), flip=false)  face_detection.rs:219
   FDL_CUDA_TRY(launch_i2t_setup(d_roi, nullptr, nullptr, batch, w, h, d->S, d->S, 1, -1.0, 1.0, 0, d->params.p, nullptr, d->stream));
   TView iv = net->input_view(batch);
-  FDL_CUDA_TRY(launch_i2t(d->frames.p, (long long)w * 3 * h, (long long)w * 3, d->params.p, batch, d->S, d->S, iv.p, iv.bstride, nullptr,
+  FDL_CUDA_TRY(launch_i2t(fptr, (long long)w * 3 * h, (long long)w * 3, d->params.p, batch, d->S, d->S, iv.p, iv.bstride, nullptr,
                           nullptr, d->stream, 1, w));
   FDL_CUDA_TRY(net->forward(batch, d->stream));
   TView reg = net->output_view(0, batch), cls = net->output_view(1, batch);
@@ -464,7 +478,8 @@ int fdl_landmark_infer(fdl_landmark_model* m, const fdl_image* image, const fdl_
   if (!m || !image || !out || !n_out) return set_error(FDL_ERR_INVALID, "bad arguments");
   FDL_CUDA_TRY(cudaSetDevice(m->device));
   int w, h;
-  int rc = stage_frames(image, 1, &m->frames, m->stream, &w, &h);
+  const uint8_t* fptr = nullptr;                  // a device-resident image (an fdl_frame) is read in place
+  int rc = stage_frames(image, 1, &m->frames, m->stream, &w, &h, &fptr);
   if (rc) return rc;
   Net* net = m->nh.net;
   std::string err;
@@ -475,14 +490,15 @@ int fdl_landmark_infer(fdl_landmark_model* m, const fdl_image* image, const fdl_
   FDL_CUDA_TRY(m->flags.reserve(2));
   const fdl_rect* d_roi = nullptr;
   if (roi) {
-    FDL_CUDA_TRY(cudaMemcpyAsync(m->rois.p, roi, sizeof(fdl_rect), cudaMemcpyHostToDevice, m->stream));
-    FDL_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    FDL_CUDA_TRY(m->h_rois.reserve(1));
+    m->h_rois.p[0] = *roi;                       // pinned slot, free again when this call returns
+    FDL_CUDA_TRY(cudaMemcpyAsync(m->rois.p, m->h_rois.p, sizeof(fdl_rect), cudaMemcpyHostToDevice, m->stream));
     d_roi = m->rois.p;
   }
   // image_to_tensor(image, roi, (S,S), keep_aspect_ratio=false, (0,1), flip=false)  face_landmark.rs:250
   FDL_CUDA_TRY(launch_i2t_setup(d_roi, nullptr, nullptr, 1, w, h, m->S, m->S, 0, 0.0, 1.0, 0, m->params.p, nullptr, m->stream));
   TView iv = net->input_view(1);
-  FDL_CUDA_TRY(launch_i2t(m->frames.p, (long long)w * 3 * h, (long long)w * 3, m->params.p, 1, m->S, m->S, iv.p, iv.bstride, nullptr, nullptr,
+  FDL_CUDA_TRY(launch_i2t(fptr, (long long)w * 3 * h, (long long)w * 3, m->params.p, 1, m->S, m->S, iv.p, iv.bstride, nullptr, nullptr,
                           m->stream));
   FDL_CUDA_TRY(net->forward(1, m->stream));
   TView raw = net->output_view(0, 1), flag = net->output_view(1, 1);
@@ -551,7 +567,8 @@ int fdl_iris_infer(fdl_iris_model* m, const fdl_image* image, const fdl_rect* ro
   if (!m || !image || !contour || !iris) return set_error(FDL_ERR_INVALID, "bad arguments");
   FDL_CUDA_TRY(cudaSetDevice(m->device));
   int w, h;
-  int rc = stage_frames(image, 1, &m->frames, m->stream, &w, &h);
+  const uint8_t* fptr = nullptr;                  // a device-resident image (an fdl_frame) is read in place
+  int rc = stage_frames(image, 1, &m->frames, m->stream, &w, &h, &fptr);
   if (rc) return rc;
   Net* net = m->nh.net;
   std::string err;
@@ -562,15 +579,16 @@ int fdl_iris_infer(fdl_iris_model* m, const fdl_image* image, const fdl_rect* ro
   FDL_CUDA_TRY(m->out.reserve(3 * K));
   const fdl_rect* d_roi = nullptr;
   if (roi) {
-    FDL_CUDA_TRY(cudaMemcpyAsync(m->rois.p, roi, sizeof(fdl_rect), cudaMemcpyHostToDevice, m->stream));
-    FDL_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    FDL_CUDA_TRY(m->h_rois.reserve(1));
+    m->h_rois.p[0] = *roi;                       // pinned slot, free again when this call returns
+    FDL_CUDA_TRY(cudaMemcpyAsync(m->rois.p, m->h_rois.p, sizeof(fdl_rect), cudaMemcpyHostToDevice, m->stream));
     d_roi = m->rois.p;
   }
   // image_to_tensor(image, roi, (S,S), keep_aspect_ratio=true, (0,1), flip=is_right_eye)  iris_landmark.rs:188-189
   FDL_CUDA_TRY(launch_i2t_setup(d_roi, nullptr, nullptr, 1, w, h, m->S, m->S, 1, 0.0, 1.0, is_right_eye ? 1 : 0, m->params.p, nullptr,
                                 m->stream));
   TView iv = net->input_view(1);
-  FDL_CUDA_TRY(launch_i2t(m->frames.p, (long long)w * 3 * h, (long long)w * 3, m->params.p, 1, m->S, m->S, iv.p, iv.bstride, nullptr, nullptr,
+  FDL_CUDA_TRY(launch_i2t(fptr, (long long)w * 3 * h, (long long)w * 3, m->params.p, 1, m->S, m->S, iv.p, iv.bstride, nullptr, nullptr,
                           m->stream));
   FDL_CUDA_TRY(net->forward(1, m->stream));
   TView eye = net->output_view(0, 1), ir = net->output_view(1, 1);
@@ -872,6 +890,68 @@ int fdl_decode_jpeg(int device, const uint8_t* data, size_t len, uint8_t* out_rg
   if (device < 0 || device >= 64) return set_error(FDL_ERR_INVALID, "device index out of range");
   if (!cache[device]) { rc = fdl_jpeg_decoder_create(device, &cache[device]); if (rc) return rc; }
   return fdl_jpeg_decode(cache[device], &data, &len, 1, out_rgb, cap, FDL_MEM_HOST, nullptr, nullptr, nullptr);
+} FDL_ABI_CATCH
+
+// ---------------------------------------------------------------------------------- fdl_frame
+int fdl_frame_create(int device, fdl_frame** out) try {
+  DeviceGuard _device_guard;
+  if (!out) return set_error(FDL_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int rc = check_device(device);
+  if (rc) return rc;
+  fdl_frame* f = new fdl_frame();
+  f->device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete f; return set_error(FDL_ERR_CUDA, cudaGetErrorString(e)); }
+  *out = f;
+  return FDL_OK;
+} FDL_ABI_CATCH
+
+void fdl_frame_destroy(fdl_frame* f) {
+  if (!f) return;
+  DeviceGuard _device_guard;
+  cudaSetDevice(f->device);
+  if (f->stream) { cudaStreamSynchronize(f->stream); cudaStreamDestroy(f->stream); }
+  delete f;
+}
+
+int fdl_frame_upload(fdl_frame* f, const fdl_image* image) try {
+  DeviceGuard _device_guard;
+  if (!f || !image) return set_error(FDL_ERR_INVALID, "null argument");
+  FDL_CUDA_TRY(cudaSetDevice(f->device));
+  f->w = f->h = 0;
+  int w, h;
+  int rc = stage_frames(image, 1, &f->buf, f->stream, &w, &h);
+  if (rc) return rc;
+  FDL_CUDA_TRY(cudaStreamSynchronize(f->stream));
+  f->w = w; f->h = h;
+  return FDL_OK;
+} FDL_ABI_CATCH
+
+int fdl_frame_upload_jpeg(fdl_frame* f, const uint8_t* data, size_t len) try {
+  DeviceGuard _device_guard;
+  if (!f || !data) return set_error(FDL_ERR_INVALID, "null argument");
+  FDL_CUDA_TRY(cudaSetDevice(f->device));
+  f->w = f->h = 0;
+  int rc = f->dec.plan(&data, &len, 1, 0, 0);
+  if (rc) return rc;
+  const int w = f->dec.width(0), h = f->dec.height(0);
+  f->dec.set_output(0, 0, w * 3);
+  FDL_CUDA_TRY(f->buf.reserve((size_t)w * 3 * h));
+  rc = f->dec.enqueue(f->buf.p, f->stream);
+  if (rc) return rc;
+  FDL_CUDA_TRY(cudaStreamSynchronize(f->stream));
+  rc = f->dec.check_status();
+  if (rc) return rc;
+  f->w = w; f->h = h;
+  return FDL_OK;
+} FDL_ABI_CATCH
+
+int fdl_frame_image(const fdl_frame* f, fdl_image* out) try {
+  if (!f || !out) return set_error(FDL_ERR_INVALID, "null argument");
+  if (f->w <= 0) return set_error(FDL_ERR_INVALID, "nothing uploaded into this frame yet");
+  out->data = f->buf.p; out->width = f->w; out->height = f->h; out->row_stride = (int64_t)f->w * 3; out->mem = FDL_MEM_DEVICE; out->_pad = 0;
+  return FDL_OK;
 } FDL_ABI_CATCH
 
 }  // extern "C"

@@ -16,6 +16,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -129,6 +130,9 @@ struct fdl_pipeline {
   DevBuf<float> anchors;
   RowGather gather;
   Lane lanes[kDepth];
+  // One thread may submit while another collects (fdl_pool's worker and the application thread): the lane table is guarded, and
+  // the guard is NOT held while collect waits for the GPU.
+  std::mutex mu;
   int next_ticket = 0;
   float last_device_ms = 0.f;
   float stage_ms[kStages] = {};
@@ -383,6 +387,7 @@ int fdl_pipeline_submit(fdl_pipeline* p, const fdl_image* frames, int n, int* ti
   if (!p || !frames || !ticket) return set_error(FDL_ERR_INVALID, "null argument");
   if (n <= 0 || n > p->cfg.max_batch) return set_error(FDL_ERR_INVALID, "batch size out of range (1..max_batch)");
   FDL_CUDA_TRY(cudaSetDevice(p->cfg.device));
+  std::lock_guard<std::mutex> guard(p->mu);
   Lane* lane = nullptr;
   for (auto& l : p->lanes) if (!l.busy) { lane = &l; break; }
   if (!lane) return set_error(FDL_ERR_INVALID, "all pipeline lanes are in flight: collect a ticket first");
@@ -405,6 +410,7 @@ int fdl_pipeline_submit_jpeg(fdl_pipeline* p, const uint8_t* const* data, const 
   if (!p || !data || !len || !ticket) return set_error(FDL_ERR_INVALID, "null argument");
   if (n <= 0 || n > p->cfg.max_batch) return set_error(FDL_ERR_INVALID, "batch size out of range (1..max_batch)");
   FDL_CUDA_TRY(cudaSetDevice(p->cfg.device));
+  std::lock_guard<std::mutex> guard(p->mu);
   Lane* lane = nullptr;
   for (auto& l : p->lanes) if (!l.busy) { lane = &l; break; }
   if (!lane) return set_error(FDL_ERR_INVALID, "all pipeline lanes are in flight: collect a ticket first");
@@ -426,10 +432,14 @@ int fdl_pipeline_collect(fdl_pipeline* p, int ticket, fdl_frame_result* frame_re
   DeviceGuard _device_guard;
   if (!p) return set_error(FDL_ERR_INVALID, "null argument");
   Lane* lane = nullptr;
-  for (auto& l : p->lanes) if (l.busy && l.ticket == ticket) { lane = &l; break; }
+  {
+    std::lock_guard<std::mutex> guard(p->mu);
+    for (auto& l : p->lanes) if (l.busy && l.ticket == ticket) { lane = &l; break; }
+  }
   if (!lane) return set_error(FDL_ERR_INVALID, "unknown ticket");
   FDL_CUDA_TRY(cudaSetDevice(p->cfg.device));
-  FDL_CUDA_TRY(cudaEventSynchronize(lane->ev_done));
+  FDL_CUDA_TRY(cudaEventSynchronize(lane->ev_done));     // (a busy lane is not touched by submit)
+  std::lock_guard<std::mutex> guard(p->mu);
   const int n = lane->n, F = n * p->cfg.max_faces;
   if (frame_results) std::memcpy(frame_results, lane->h_frames.p, (size_t)n * sizeof(fdl_frame_result));
   if (face_results && p->lmk) std::memcpy(face_results, lane->h_faces.p, (size_t)F * sizeof(fdl_face_result));

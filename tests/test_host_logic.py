@@ -48,7 +48,9 @@ def test_no_device_is_an_error_not_a_fallback(fdl):
     for make in (lambda: fdl.FaceDetection(fdl.FaceDetectionModel.BackCamera, MODELS), lambda: fdl.FaceLandmark(MODELS + "/face_landmark.tflite"),
                  lambda: fdl.IrisLandmark(MODELS + "/iris_landmark.tflite"), lambda: fdl.Pipeline(model_dir=MODELS),
                  lambda: fdl.face_detection_to_roi(fdl.Detection(np.zeros((8, 2), np.float32), 0.9), (10, 10)),
-                 lambda: fdl.image_to_tensor(np.zeros((8, 8, 3), np.uint8), None, (4, 4), True)):
+                 lambda: fdl.image_to_tensor(np.zeros((8, 8, 3), np.uint8), None, (4, 4), True),
+                 lambda: fdl.Pool([0], model_dir=MODELS), lambda: fdl.Frame(np.zeros((8, 8, 3), np.uint8)),
+                 lambda: fdl.convert_image_to_mat(open(os.path.join(ROOT, "test_data", "man.jpg"), "rb").read())):
         with pytest.raises(fdl.FdlError) as e:
             make()
         assert e.value.code == -4 and "no CPU fallback" in e.value.message
