@@ -419,8 +419,9 @@ def run_ours(args):
     h2d_ms = pipe.stage_ms[0]
     e2e_zc_s, zc_rect_bytes = None, None
     if not args.no_zero_copy:
-        pipe_zc = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (W, H), max_batch=B, max_faces=1, model_dir=MODELS, device=local,
-                               zero_copy_host=True)
+        # through fdl_pool with this rank's GPU: the pool's worker thread does the submit-side host work (staging plan, ~300 stream
+        # operations per batch) while this thread collects -- the way an application keeps a GPU fed from one thread
+        pipe_zc = fdl.Pool([local], fdl.FaceDetectionModel.BackCamera, (W, H), max_batch=B, max_faces=1, model_dir=MODELS, zero_copy_host=True)
         e2e_zc_s = e2e_loop(pipe_zc)
         zc_faces = sum(pipe_zc._frames[i].n_faces for i in range(B))
         assert zc_faces == n_faces, "zero-copy path disagrees with the copy path"
@@ -448,18 +449,22 @@ def run_ours(args):
             arenas.append((a, offs[:-1], lens))
         jpeg_bytes = int(sum(lens))
 
+        pool_j = fdl.Pool([local], fdl.FaceDetectionModel.BackCamera, (W, H), max_batch=B, max_faces=1, model_dir=MODELS)
+
         class _JpegPipe:                      # the e2e loop calls submit / collect_raw
             def submit(self, arena):
-                return pipe.submit_jpeg(arena)
+                return pool_j.submit_jpeg(arena)
 
             def collect_raw(self, t):
-                return pipe.collect_raw(t)
+                return pool_j.collect_raw(t)
         raw_bufs = bufs
         bufs = arenas
         e2e_jpeg_s = e2e_loop(_JpegPipe())
         bufs = raw_bufs
+        assert sum(pool_j._frames[i].n_faces for i in range(B)) == n_faces, "the JPEG path lost a face"
+        pool_j.close()
+        pipe.collect_raw(pipe.submit_jpeg(arenas[0]))          # one serial batch for the stage timing
         jpeg_stage = pipe.stage_ms[0]
-        assert sum(pipe._frames[i].n_faces for i in range(B)) == n_faces, "the JPEG path lost a face"
     e2e_s = min(x for x in (e2e_copy_s, e2e_zc_s, e2e_jpeg_s) if x is not None)
     clocks = sampler.summary()
 
@@ -479,7 +484,7 @@ def run_ours(args):
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     total_ms_max, e2e_s_max, e2e_copy_max, e2e_zc_max, e2e_jpeg_max = (float(v) for v in t_dev)
     modes = {"copy": e2e_copy_s, "zero-copy (kernels read pinned host frames in place)": e2e_zc_s,
-             "jpeg (compressed H2D from a pinned arena + device decode, fdl_pipeline_submit_jpeg)": e2e_jpeg_s}
+             "jpeg (compressed H2D from a pinned arena + device decode, fdl_pool_submit_jpeg)": e2e_jpeg_s}
     best_mode = min((k for k in modes if modes[k] is not None), key=lambda k: modes[k])
     frames_total = world * B * args.steps
     value = frames_total / (total_ms_max / 1e3)
