@@ -10,6 +10,7 @@ pub struct fdl_detection { pub data: [f32; 16], pub score: f32, pub anchor: i32 
 pub struct fdl_landmark { pub x: f64, pub y: f64, pub z: f64 }
 #[repr(C)]
 pub struct fdl_image { pub data: *const u8, pub width: i32, pub height: i32, pub row_stride: i64, pub mem: i32, pub _pad: i32 }
+pub enum fdl_frame {}
 pub enum fdl_detector {}
 pub enum fdl_landmark_model {}
 pub enum fdl_iris_model {}
@@ -29,9 +30,18 @@ extern "C" {
     pub fn fdl_iris_roi_from_face_landmarks(device: c_int, lm: *const fdl_landmark, n: c_int, w: c_int, h: c_int, left: *mut fdl_rect, right: *mut fdl_rect) -> c_int;
     pub fn fdl_update_face_landmarks_with_iris_results(device: c_int, face: *const fdl_landmark, n: c_int, left: *const fdl_landmark, n_left: c_int,
                                                        right: *const fdl_landmark, n_right: c_int, refined: *mut fdl_landmark) -> c_int;
+    pub fn fdl_jpeg_info(data: *const u8, len: usize, width: *mut c_int, height: *mut c_int, components: *mut c_int) -> c_int;
+    pub fn fdl_decode_jpeg(device: c_int, data: *const u8, len: usize, out_rgb: *mut u8, cap: usize, width: *mut c_int, height: *mut c_int) -> c_int;
+    pub fn fdl_frame_create(device: c_int, out: *mut *mut fdl_frame) -> c_int;
+    pub fn fdl_frame_destroy(f: *mut fdl_frame);
+    pub fn fdl_frame_upload(f: *mut fdl_frame, image: *const fdl_image) -> c_int;
+    pub fn fdl_frame_upload_jpeg(f: *mut fdl_frame, data: *const u8, len: usize) -> c_int;
+    pub fn fdl_frame_image(f: *const fdl_frame, out: *mut fdl_image) -> c_int;
     pub fn fdl_iris_diameter(device: c_int, iris: *const fdl_landmark, n: c_int, w: c_int, h: c_int, out: *mut f64) -> c_int;
     pub fn fdl_iris_depth(device: c_int, iris: *const fdl_landmark, n: c_int, focal_length_mm: f64, iris_size_px: f64, w: c_int, h: c_int, out: *mut f64) -> c_int;
 }
+
+pub const FDL_ERR_CAPACITY: c_int = -5;
 
 pub fn check(rc: c_int) -> Result<(), anyhow::Error> {
     if rc == 0 { return Ok(()); }

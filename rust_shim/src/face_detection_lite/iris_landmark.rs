@@ -1,22 +1,29 @@
 //! iris_roi_from_face_landmarks, IrisLandmark::new / infer, IrisResults, update_face_landmarks_with_iris_results and the iris
 //! diameter / depth helpers (reference iris_landmark.rs:115-433) over the C ABI.
-use super::{ffi, types::{Landmark, Rect}};
+use super::{ffi, types::{Landmark, Rect}, utils::{default_device, Frame}};
 use anyhow::Error;
 use opencv::core::Mat;
 use std::ffi::CString;
 
+/// iris_landmark.rs:104-110.
+#[repr(i32)]
+#[derive(Debug, Copy, Clone, PartialEq, Eq)]
+pub enum IrisIndex { Center = 0, Left = 1, Top = 2, Right = 3, Bottom = 4 }
+
+/// 71 contour points of the eye region + 5 iris points (iris_landmark.rs:115-129).
 pub struct IrisResults { contour: Vec<Landmark>, iris: Vec<Landmark> }
 impl IrisResults {
+    pub fn new(contour: Vec<Landmark>, iris: Vec<Landmark>) -> Self { IrisResults { contour, iris } }
     pub fn eyeball_contour(&self) -> Vec<Landmark> { self.contour[..15].to_vec() }
     pub fn contour(&self) -> &[Landmark] { &self.contour }
     pub fn iris(&self) -> &[Landmark] { &self.iris }
 }
 
 pub fn iris_roi_from_face_landmarks(face_landmarks: Vec<Landmark>, image_size: (i32, i32)) -> Result<(Rect, Rect), Error> {
-    let lm: Vec<ffi::fdl_landmark> = face_landmarks.iter().map(|l| ffi::fdl_landmark { x: l.x, y: l.y, z: l.z }).collect();
-    let zero = Rect { x_center: 0.0, y_center: 0.0, width: 0.0, height: 0.0, rotation: 0.0, normalized: true }.to_c();
+    let lm = to_c(&face_landmarks);
+    let zero = Rect::new(0.0, 0.0, 0.0, 0.0, 0.0, true).to_c();
     let (mut l, mut r) = (zero, zero);
-    ffi::check(unsafe { ffi::fdl_iris_roi_from_face_landmarks(0, lm.as_ptr(), lm.len() as i32, image_size.0, image_size.1, &mut l, &mut r) })?;
+    ffi::check(unsafe { ffi::fdl_iris_roi_from_face_landmarks(default_device(), lm.as_ptr(), lm.len() as i32, image_size.0, image_size.1, &mut l, &mut r) })?;
     Ok((Rect::from_c(&l), Rect::from_c(&r)))
 }
 
@@ -27,23 +34,28 @@ impl IrisLandmark {
     pub fn new(model_path: Option<String>) -> Result<IrisLandmark, Error> {
         let file = model_path.map(|p| CString::new(p).unwrap());
         let mut h = std::ptr::null_mut();
-        ffi::check(unsafe { ffi::fdl_iris_create(file.as_ref().map_or(std::ptr::null(), |c| c.as_ptr()), 0, &mut h) })?;
+        ffi::check(unsafe { ffi::fdl_iris_create(file.as_ref().map_or(std::ptr::null(), |c| c.as_ptr()), default_device(), &mut h) })?;
         Ok(IrisLandmark { handle: h })
     }
     pub fn infer(&self, image: &Mat, roi: Option<Rect>, is_right_eye: Option<bool>) -> Result<IrisResults, Error> {
-        let img = ffi::image_of(image)?;
+        self.infer_image(&ffi::image_of(image)?, roi, is_right_eye)
+    }
+    pub fn infer_frame(&self, frame: &Frame, roi: Option<Rect>, is_right_eye: Option<bool>) -> Result<IrisResults, Error> {
+        self.infer_image(&frame.image()?, roi, is_right_eye)
+    }
+    fn infer_image(&self, img: &ffi::fdl_image, roi: Option<Rect>, is_right_eye: Option<bool>) -> Result<IrisResults, Error> {
         let croi = roi.map(|r| r.to_c());
         let mut contour = vec![ffi::fdl_landmark::default(); 71];
         let mut iris = vec![ffi::fdl_landmark::default(); 5];
-        ffi::check(unsafe { ffi::fdl_iris_infer(self.handle, &img, croi.as_ref().map_or(std::ptr::null(), |r| r as *const _), is_right_eye.unwrap_or(false) as i32,
+        ffi::check(unsafe { ffi::fdl_iris_infer(self.handle, img, croi.as_ref().map_or(std::ptr::null(), |r| r as *const _), is_right_eye.unwrap_or(false) as i32,
                                                  contour.as_mut_ptr(), iris.as_mut_ptr()) })?;
-        let f = |v: &Vec<ffi::fdl_landmark>| v.iter().map(|l| Landmark { x: l.x, y: l.y, z: l.z }).collect();
-        Ok(IrisResults { contour: f(&contour), iris: f(&iris) })
+        let f = |v: &Vec<ffi::fdl_landmark>| v.iter().map(Landmark::from_c).collect();
+        Ok(IrisResults::new(f(&contour), f(&iris)))
     }
 }
 impl Drop for IrisLandmark { fn drop(&mut self) { unsafe { ffi::fdl_iris_destroy(self.handle) } } }
 
-fn to_c(v: &[Landmark]) -> Vec<ffi::fdl_landmark> { v.iter().map(|l| ffi::fdl_landmark { x: l.x, y: l.y, z: l.z }).collect() }
+fn to_c(v: &[Landmark]) -> Vec<ffi::fdl_landmark> { v.iter().map(|l| l.to_c()).collect() }
 
 /// Update face landmarks with iris detection results (reference iris_landmark.rs:380-398).
 pub fn update_face_landmarks_with_iris_results(
@@ -52,22 +64,22 @@ pub fn update_face_landmarks_with_iris_results(
     let (face, left, right) = (to_c(&face_landmarks), to_c(&iris_data_left.contour), to_c(&iris_data_right.contour));
     let mut out = vec![ffi::fdl_landmark::default(); 468];
     ffi::check(unsafe {
-        ffi::fdl_update_face_landmarks_with_iris_results(0, face.as_ptr(), face.len() as i32, left.as_ptr(), left.len() as i32, right.as_ptr(),
+        ffi::fdl_update_face_landmarks_with_iris_results(default_device(), face.as_ptr(), face.len() as i32, left.as_ptr(), left.len() as i32, right.as_ptr(),
                                                          right.len() as i32, out.as_mut_ptr())
     })?;
-    Ok(out.iter().map(|l| Landmark { x: l.x, y: l.y, z: l.z }).collect())
+    Ok(out.iter().map(Landmark::from_c).collect())
 }
 
 /// Iris diameter in pixels (reference iris_landmark.rs:401-418; private there).
 pub fn get_iris_diameter(iris_landmarks: &Vec<Landmark>, image_size: (i32, i32)) -> Result<f64, Error> {
     let (iris, mut d) = (to_c(iris_landmarks), 0.0f64);
-    ffi::check(unsafe { ffi::fdl_iris_diameter(0, iris.as_ptr(), iris.len() as i32, image_size.0, image_size.1, &mut d) })?;
+    ffi::check(unsafe { ffi::fdl_iris_diameter(default_device(), iris.as_ptr(), iris.len() as i32, image_size.0, image_size.1, &mut d) })?;
     Ok(d)
 }
 
 /// Iris depth in mm from the lens focal length in mm (reference iris_landmark.rs:421-433; private there).
 pub fn get_iris_depth(iris_landmarks: Vec<Landmark>, focal_length_mm: f64, iris_size_px: f64, image_size: (i32, i32)) -> Result<f64, Error> {
     let (iris, mut d) = (to_c(&iris_landmarks), 0.0f64);
-    ffi::check(unsafe { ffi::fdl_iris_depth(0, iris.as_ptr(), iris.len() as i32, focal_length_mm, iris_size_px, image_size.0, image_size.1, &mut d) })?;
+    ffi::check(unsafe { ffi::fdl_iris_depth(default_device(), iris.as_ptr(), iris.len() as i32, focal_length_mm, iris_size_px, image_size.0, image_size.1, &mut d) })?;
     Ok(d)
 }

@@ -4,6 +4,8 @@
 pub mod face_detection_lite {
     pub mod ffi;
     pub mod types;
+    pub mod transform;
+    pub mod utils;
     pub mod face_detection;
     pub mod face_landmark;
     pub mod iris_landmark;

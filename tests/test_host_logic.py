@@ -592,3 +592,41 @@ def test_hostile_model_files_never_cross_the_abi_as_exceptions_or_crashes(fdl, t
         "print('survived')\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), files))
     out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "survived" in out.stdout, out.stderr[-2000:]
+
+
+def test_rust_shim_keeps_the_reference_public_surface():
+    """The shim must compile user code written against the reference: every public item of the reference's hot-path modules
+    (names listed here from types.rs:5-246, transform.rs:15-40, face_detection.rs:89-123/:146-205, face_landmark.rs:180-232,
+    iris_landmark.rs:104-158/:268/:380, utils.rs:8) has to exist in rust_shim/ with the same name."""
+    shim = os.path.join(ROOT, "rust_shim", "src", "face_detection_lite")
+    read = lambda f: open(os.path.join(shim, f)).read()
+    want = {
+        "types.rs": ["pub struct ImageTensor", "pub struct Rect", "pub fn new(x_center: f64, y_center: f64, width: f64, height: f64, rotation: f64, normalized: bool)",
+                     "pub fn size(&self) -> (f64, f64)", "pub fn scaled(&self, size: (f64, f64), normalize: bool) -> Rect", "pub fn points(&self) -> Vec<(f64, f64)>",
+                     "pub struct BBox", "pub fn as_tuple", "pub fn width", "pub fn height", "pub fn empty", "pub fn normalized", "pub fn area",
+                     "pub fn intersect(&self, other: &BBox) -> Option<BBox>", "pub fn scale(&self, size: (f64, f64)) -> BBox",
+                     "pub fn absolute(&self, size: (i32, i32)) -> BBox", "pub struct Landmark", "pub fn new(x: f64, y: f64, z: f64)",
+                     "pub struct Detection", "pub data: Array2<f32>", "pub fn new(data: Vec<f32>, score: f32)", "pub fn keypoint_count(&self) -> usize",
+                     "pub fn keypoint(&self, key: usize) -> (f32, f32)", "pub fn bbox(&self) -> BBox", "pub fn scaled(&self, factor: f32) -> Detection",
+                     "pub fn scaled_by_image_size(&self, image_size: (i32, i32)) -> Detection"],
+        "transform.rs": ["pub enum SizeMode", "SquareLong = 1", "SquareShort = 2", "impl From<i32> for SizeMode", "pub fn to_int(self) -> i32"],
+        "face_detection.rs": ["pub enum FaceIndex", "impl TryFrom<i32> for FaceIndex", "pub enum FaceDetectionModel", "FullSparse = 4",
+                              "pub fn new(model_type: FaceDetectionModel, model_path: Option<String>) -> Result<FaceDetection, Error>",
+                              "pub fn infer(&self, image: &Mat, roi: Option<Rect>) -> Result<Vec<Detection>, Error>"],
+        "face_landmark.rs": ["pub fn face_detection_to_roi(face_detection: Detection, image_size: (i32, i32), size_mode: Option<SizeMode>) -> Result<Rect, Error>",
+                             "pub fn new(model_path: Option<String>) -> Result<FaceLandmark, Error>",
+                             "pub fn infer(&self, image: &Mat, roi: Option<Rect>) -> Result<Vec<Landmark>, Error>"],
+        "iris_landmark.rs": ["pub enum IrisIndex", "pub struct IrisResults", "pub fn new(contour: Vec<Landmark>, iris: Vec<Landmark>) -> Self",
+                             "pub fn eyeball_contour(&self) -> Vec<Landmark>", "pub fn new(model_path: Option<String>) -> Result<IrisLandmark, Error>",
+                             "pub fn infer(&self, image: &Mat, roi: Option<Rect>, is_right_eye: Option<bool>) -> Result<IrisResults, Error>",
+                             "pub fn iris_roi_from_face_landmarks(face_landmarks: Vec<Landmark>, image_size: (i32, i32)) -> Result<(Rect, Rect), Error>",
+                             "pub fn update_face_landmarks_with_iris_results("],
+        "utils.rs": ["pub fn convert_image_to_mat(im_bytes: &[u8]) -> Result<Mat, Error>"],
+    }
+    for f, items in want.items():
+        src = re.sub(r"\s+", " ", read(f))
+        for it in items:
+            assert re.sub(r"\s+", " ", it) in src, (f, it)
+    lib = open(os.path.join(ROOT, "rust_shim", "src", "lib.rs")).read()
+    for m in ("ffi", "types", "transform", "utils", "face_detection", "face_landmark", "iris_landmark"):
+        assert "pub mod %s;" % m in lib
