@@ -345,6 +345,30 @@ FDL_API float fdl_pipeline_last_device_ms(const fdl_pipeline*);
  * [7] iris net, [8] iris post, [9] D2H. */
 FDL_API int fdl_pipeline_stage_ms(const fdl_pipeline*, float* out10);
 
+/* ---------------------------------------------------------------- drawing */
+/* render.rs:361-479 `render_to_image(annotations, image, blend_mode)`: annotations painted over the frame in order (no blending --
+ * the reference ignores blend_mode), with the pixel rules of the `imageproc` crate it calls.  An `Annotation` (render.rs:208-213:
+ * data items + normalized_positions + thickness + colour) is flattened here into one fdl_primitive per data item:
+ *   POINT        a, b = x, y                      -> filled square of side 2 * max(thickness / 2, 1) at (x - w, y - w)   (:421-430)
+ *   LINE         a, b, c, d = x0, y0, x1, y1      -> one-pixel Bresenham segment between the truncated end points        (:431-442)
+ *   RECT         a, b, c, d = left, top, right, bottom -> one-pixel outline of Rect::at(left, top).of_size(right - left, bottom - top) (:443-461)
+ *   FILLED_RECT  the same rectangle, filled                                                                              (:462-474)
+ * (ovals are drawn as rectangles by the reference.)  `normalized` coordinates are multiplied by the image size first.  The output is
+ * RGBA8 [height][width][4] (DynamicImage::ImageRgba8), in host memory or -- out_mem == FDL_MEM_DEVICE -- on `device`.  The helpers
+ * that build annotations from results (detections_to_render_data :262, landmarks_to_render_data :315, face_ / eye_landmarks_to_render_data,
+ * the connection tables) are host-side bookkeeping and live in the mirrors (api.py, fdl.hpp). */
+enum { FDL_PRIM_POINT = 0, FDL_PRIM_LINE = 1, FDL_PRIM_RECT = 2, FDL_PRIM_FILLED_RECT = 3 };
+typedef struct fdl_primitive {
+  int32_t kind;          /* FDL_PRIM_* */
+  int32_t normalized;    /* Annotation.normalized_positions */
+  double a, b, c, d;
+  double thickness;      /* Annotation.thickness */
+  uint8_t r, g, b_, alpha;   /* Annotation.color (`b_`: blue; alpha 255 when the reference's Option is None) */
+  int32_t _pad;
+} fdl_primitive;
+FDL_API int fdl_render_to_image(int device, const fdl_image* image, const fdl_primitive* primitives, int n, uint8_t* out_rgba, size_t cap,
+                                int out_mem);
+
 /* ---------------------------------------------------------------- all GPUs of a box behind one handle */
 /* The path shards by frame and has no exchange step (face_detection.rs:205 `infer(&self, ..)` is pure given the weights), so a box
  * of N GPUs is N independent pipelines.  fdl_pool owns one fdl_pipeline per listed device (a device may be listed more than once)

@@ -129,4 +129,27 @@ class IrisLandmark {              // iris_landmark.rs:131-248
   fdl_iris_model* h_ = nullptr;
 };
 
+// render.rs: Color (:7-27), Annotation (:208-213, flattened: every item carries its kind) and render_to_image (:361-479) -> RGBA8.
+struct Color { int r = 0, g = 0, b = 0; std::optional<int> a; };
+struct AnnotationItem { int kind; double a, b, c, d; std::optional<Color> fill; };   // kind: FDL_PRIM_*; fill: FilledRectOrOval's own colour
+struct Annotation { std::vector<AnnotationItem> data; bool normalized_positions = true; double thickness = 1.0; Color color; };
+inline Annotation landmark_points(const std::vector<Landmark>& lm, Color color, double thickness = 2.0) {   // landmarks_to_render_data, the points
+  Annotation a{{}, true, thickness, color};
+  for (const auto& l : lm) a.data.push_back({FDL_PRIM_POINT, l.x, l.y, 0.0, 0.0, std::nullopt});
+  return a;
+}
+inline std::vector<uint8_t> render_to_image(const std::vector<Annotation>& annotations, const Image& image, int device = 0) {
+  std::vector<fdl_primitive> prims;
+  for (const auto& an : annotations)
+    for (const auto& it : an.data) {
+      const Color& c = it.fill ? *it.fill : an.color;
+      prims.push_back(fdl_primitive{it.kind, an.normalized_positions ? 1 : 0, it.a, it.b, it.c, it.d, an.thickness, (uint8_t)c.r, (uint8_t)c.g, (uint8_t)c.b,
+                                    (uint8_t)c.a.value_or(255), 0});
+    }
+  std::vector<uint8_t> out((size_t)image.width * image.height * 4);
+  fdl_image img = image.c();
+  check(fdl_render_to_image(device, &img, prims.data(), (int)prims.size(), out.data(), out.size(), FDL_MEM_HOST));
+  return out;
+}
+
 }  // namespace fdl

@@ -55,6 +55,11 @@ class CFaceResult(C.Structure):
                 ("iris_depth_mm", C.c_double * 2)]
 
 
+class CPrimitive(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("normalized", C.c_int32), ("a", C.c_double), ("b", C.c_double), ("c", C.c_double), ("d", C.c_double),
+                ("thickness", C.c_double), ("r", C.c_uint8), ("g", C.c_uint8), ("b_", C.c_uint8), ("alpha", C.c_uint8), ("_pad", C.c_int32)]
+
+
 class CFrameResult(C.Structure):
     _fields_ = [("n_detections", C.c_int32), ("n_faces", C.c_int32), ("n_total_detections", C.c_int32),
                 ("detections", CDetection * MAX_DETECTIONS)]
@@ -123,6 +128,7 @@ SYMBOLS = {
     "fdl_jpeg_decoder_destroy": (None, [_vp]),
     "fdl_jpeg_decode": (C.c_int, [_vp, _P(_vp), _P(C.c_size_t), C.c_int, _vp, C.c_size_t, C.c_int, _P(C.c_int64), _P(C.c_int32), _P(C.c_int32)]),
     "fdl_decode_jpeg": (C.c_int, [C.c_int, _vp, C.c_size_t, _vp, C.c_size_t, _P(C.c_int), _P(C.c_int)]),
+    "fdl_render_to_image": (C.c_int, [C.c_int, _P(CImage), _P(CPrimitive), C.c_int, _vp, C.c_size_t, C.c_int]),
     "fdl_pool_create": (C.c_int, [_P(CPipelineConfig), _P(C.c_int), C.c_int, _P(_vp)]),
     "fdl_pool_destroy": (None, [_vp]),
     "fdl_pool_devices": (C.c_int, [_vp]),

@@ -773,6 +773,129 @@ class JpegDecoder:
         return out, list(offs), list(ws), list(hs)
 
 
+# ------------------------------------------------------------------------------------------------
+# drawing: render.rs (Color / Colors / Annotation, detections_to_render_data, landmarks_to_render_data, render_to_image) and the
+# connection tables of face_landmark.rs:35-160 / iris_landmark.rs:44-60.  The bookkeeping is host side; the pixels are painted on the device.
+@dataclass
+class Color:  # render.rs:7-27
+    r: int = 0
+    g: int = 0
+    b: int = 0
+    a: int | None = None
+
+
+class Colors:  # render.rs:29-68 (the ones lib.rs uses and the primaries)
+    BLACK = Color(0, 0, 0)
+    RED = Color(255, 0, 0)
+    GREEN = Color(0, 255, 0)
+    BLUE = Color(0, 0, 255)
+    PINK = Color(255, 0, 255)
+    WHITE = Color(255, 255, 255)
+
+
+@dataclass
+class Annotation:  # render.rs:208-213: data = [("point", x, y) | ("line", x0, y0, x1, y1) | ("rect", l, t, r, b) | ("filled_rect", l, t, r, b)]
+    data: list
+    normalized_positions: bool
+    thickness: float
+    color: Color
+
+
+FACE_LANDMARK_CONNECTIONS = [
+    (61, 146), (146, 91), (91, 181), (181, 84), (84, 17), (17, 314), (314, 405), (405, 321), (321, 375), (375, 291), (61, 185), (185, 40), (40, 39),
+    (39, 37), (37, 0), (0, 267), (267, 269), (269, 270), (270, 409), (409, 291), (78, 95), (95, 88), (88, 178), (178, 87), (87, 14), (14, 317),
+    (317, 402), (402, 318), (318, 324), (324, 308), (78, 191), (191, 80), (80, 81), (81, 82), (82, 13), (13, 312), (312, 311), (311, 310), (310, 415),
+    (415, 308), (33, 7), (7, 163), (163, 144), (144, 145), (145, 153), (153, 154), (154, 155), (155, 133), (33, 246), (246, 161), (161, 160),
+    (160, 159), (159, 158), (158, 157), (157, 173), (173, 133), (46, 53), (53, 52), (52, 65), (65, 55), (70, 63), (63, 105), (105, 66), (66, 107),
+    (263, 249), (249, 390), (390, 373), (373, 374), (374, 380), (380, 381), (381, 382), (382, 362), (263, 466), (466, 388), (388, 387), (387, 386),
+    (386, 385), (385, 384), (384, 398), (398, 362), (276, 283), (283, 282), (282, 295), (295, 285), (300, 293), (293, 334), (334, 296), (296, 336),
+    (10, 338), (338, 297), (297, 332), (332, 284), (284, 251), (251, 389), (389, 356), (356, 454), (454, 323), (323, 361), (361, 288), (288, 397),
+    (397, 365), (365, 379), (379, 378), (378, 400), (400, 377), (377, 152), (152, 148), (148, 176), (176, 149), (149, 150), (150, 136), (136, 172),
+    (172, 58), (58, 132), (132, 93), (93, 234), (234, 127), (127, 162), (162, 21), (21, 54), (54, 103), (103, 67), (67, 109), (109, 10)]
+EYE_LANDMARK_CONNECTIONS = [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (6, 7), (7, 8), (9, 10), (10, 11), (11, 12), (12, 13), (13, 14), (0, 9), (8, 14)]
+MAX_EYE_LANDMARK = len(EYE_LANDMARK_CONNECTIONS)
+
+
+def detections_to_render_data(detections, bounds_color=None, keypoint_color=None, line_width: int = 1, point_width: int = 3,
+                              normalized_positions: bool = True, output=None):
+    """render.rs:262-313: one annotation with every detection's bounds (if bounds_color and line_width > 0), one with every row of
+    every detection as a point (if keypoint_color and point_width > 0)."""
+    out = list(output) if output is not None else []
+    if bounds_color is not None and line_width > 0:
+        rects = []
+        for d in detections:
+            b = d.bbox()
+            rects.append(("rect", b.xmin, b.ymin, b.xmax, b.ymax))
+        out.append(Annotation(rects, normalized_positions, float(line_width), bounds_color))
+    if keypoint_color is not None and point_width > 0:
+        pts = [("point", float(row[0]), float(row[1])) for d in detections for row in np.asarray(d.data).reshape(-1, 2)]
+        out.append(Annotation(pts, normalized_positions, float(point_width), keypoint_color))
+    return out
+
+
+def landmarks_to_render_data(landmarks, landmark_connections, landmark_color=None, connection_color=None, thickness=None,
+                             normalized_positions=None, output=None):
+    """render.rs:315-359: the connection lines, then the points."""
+    lc = landmark_color if landmark_color is not None else Colors.RED
+    cc = connection_color if connection_color is not None else Colors.RED
+    th = float(np.float32(thickness)) if thickness is not None else 1.0
+    norm = True if normalized_positions is None else bool(normalized_positions)
+    xy = [(l.x, l.y) if hasattr(l, "x") else (float(l[0]), float(l[1])) for l in landmarks]
+    lines = [("line", xy[a][0], xy[a][1], xy[b][0], xy[b][1]) for a, b in landmark_connections]
+    points = [("point", x, y) for x, y in xy]
+    out = list(output) if output is not None else []
+    out += [Annotation(lines, norm, th, cc), Annotation(points, norm, th, lc)]
+    return out
+
+
+def face_landmarks_to_render_data(face_landmarks, landmark_color, connection_color, thickness=None, output=None):
+    """face_landmark.rs:324-340."""
+    return landmarks_to_render_data(face_landmarks, FACE_LANDMARK_CONNECTIONS, landmark_color, connection_color, 2.0 if thickness is None else thickness,
+                                    True, output)
+
+
+def eye_landmarks_to_render_data(eye_contour, landmark_color, connection_color, thickness=None, output=None):
+    """iris_landmark.rs:312-328: the first 15 contour points and their connections."""
+    return landmarks_to_render_data(list(eye_contour)[:MAX_EYE_LANDMARK], EYE_LANDMARK_CONNECTIONS, landmark_color, connection_color,
+                                    2.0 if thickness is None else thickness, True, output)
+
+
+def iris_landmarks_to_render_data(iris_landmarks, landmark_color=None, oval_color=None, thickness=None, image_size=None, output=None, device: int = 0):
+    """iris_landmark.rs:330-376: the iris circle as an "oval" (which render.rs:447-462 draws as a hollow rectangle) and the 5 points."""
+    w, h = image_size if image_size is not None else (-1, -1)
+    th = 1.0 if thickness is None else float(thickness)
+    ann = []
+    if oval_color is not None:
+        if w < 2 or h < 2:
+            raise FdlError(_lib.FDL_ERR_INVALID, "oval_color requires a valid image_size arg")
+        rad = get_iris_diameter(iris_landmarks, (w, h), device=device) / 2.0
+        c = iris_landmarks[0]
+        ann.append(Annotation([("rect", c.x - rad / w, c.y - rad / h, c.x + rad / w, c.y + rad / h)], True, th, oval_color))
+    if landmark_color is not None:
+        ann.append(Annotation([("point", l.x, l.y) for l in iris_landmarks], True, th, landmark_color))
+    return (list(output) if output is not None else []) + ann
+
+
+_PRIM_KIND = {"point": 0, "line": 1, "rect": 2, "filled_rect": 3}
+
+
+def render_to_image(annotations, image, blend_mode=None, device: int = 0) -> np.ndarray:
+    """render.rs:361-479 -> RGBA uint8 [H,W,4] (the reference's DynamicImage::ImageRgba8); painted on the device."""
+    img, _keep = _image(image)
+    items = [(a, it) for a in annotations for it in a.data]
+    prims = (_lib.CPrimitive * max(len(items), 1))()
+    for k, (a, it) in enumerate(items):
+        p = prims[k]
+        p.kind, p.normalized, p.thickness = _PRIM_KIND[it[0]], 1 if a.normalized_positions else 0, float(a.thickness)
+        vals = list(it[1:5]) + [0.0, 0.0]
+        p.a, p.b, p.c, p.d = (float(v) for v in vals[:4])
+        col = it[5] if it[0] == "filled_rect" and len(it) > 5 else a.color        # FilledRectOrOval carries its own fill (render.rs:131-135)
+        p.r, p.g, p.b_, p.alpha = col.r & 255, col.g & 255, col.b & 255, (255 if col.a is None else col.a) & 255
+    out = np.empty((img.height, img.width, 4), np.uint8)
+    check(lib().fdl_render_to_image(device, C.byref(img), prims, len(items), out.ctypes.data, out.size, _lib.MEM_HOST))
+    return out
+
+
 class Pool(Pipeline):
     """Every GPU of a box behind one handle (fdl_pool): one pipeline + one host worker thread per device, least-loaded dispatch,
     pool-wide tickets.  Same ``submit`` / ``submit_jpeg`` / ``collect`` / ``run`` as ``Pipeline``; up to ``depth`` tickets in flight."""

@@ -38,6 +38,7 @@ SOURCES = {
     "fdl_api.cu": [],
     "pipeline.cu": [],
     "pool.cu": [],
+    "render.cu": ["-fmad=false"],
 }
 
 

@@ -10,6 +10,11 @@ pub struct fdl_detection { pub data: [f32; 16], pub score: f32, pub anchor: i32 
 pub struct fdl_landmark { pub x: f64, pub y: f64, pub z: f64 }
 #[repr(C)]
 pub struct fdl_image { pub data: *const u8, pub width: i32, pub height: i32, pub row_stride: i64, pub mem: i32, pub _pad: i32 }
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct fdl_primitive { pub kind: i32, pub normalized: i32, pub a: f64, pub b: f64, pub c: f64, pub d: f64, pub thickness: f64,
+                           pub r: u8, pub g: u8, pub b_: u8, pub alpha: u8, pub _pad: i32 }
+pub const FDL_PRIM_POINT: i32 = 0; pub const FDL_PRIM_LINE: i32 = 1; pub const FDL_PRIM_RECT: i32 = 2; pub const FDL_PRIM_FILLED_RECT: i32 = 3;
+pub const FDL_MEM_HOST: i32 = 0; pub const FDL_MEM_DEVICE: i32 = 1;
 pub enum fdl_frame {}
 pub enum fdl_detector {}
 pub enum fdl_landmark_model {}
@@ -38,6 +43,7 @@ extern "C" {
     pub fn fdl_frame_upload_jpeg(f: *mut fdl_frame, data: *const u8, len: usize) -> c_int;
     pub fn fdl_frame_image(f: *const fdl_frame, out: *mut fdl_image) -> c_int;
     pub fn fdl_iris_diameter(device: c_int, iris: *const fdl_landmark, n: c_int, w: c_int, h: c_int, out: *mut f64) -> c_int;
+    pub fn fdl_render_to_image(device: c_int, image: *const fdl_image, primitives: *const fdl_primitive, n: c_int, out_rgba: *mut u8, cap: usize, out_mem: c_int) -> c_int;
     pub fn fdl_iris_depth(device: c_int, iris: *const fdl_landmark, n: c_int, focal_length_mm: f64, iris_size_px: f64, w: c_int, h: c_int, out: *mut f64) -> c_int;
 }
 

@@ -1,6 +1,6 @@
 //! iris_roi_from_face_landmarks, IrisLandmark::new / infer, IrisResults, update_face_landmarks_with_iris_results and the iris
 //! diameter / depth helpers (reference iris_landmark.rs:115-433) over the C ABI.
-use super::{ffi, types::{Landmark, Rect}, utils::{default_device, Frame}};
+use super::{ffi, render::{landmarks_to_render_data, Annotation, AnnotationData, Color, Point, RectOrOval}, types::{Landmark, Rect}, utils::{default_device, Frame}};
 use anyhow::Error;
 use opencv::core::Mat;
 use std::ffi::CString;
@@ -82,4 +82,37 @@ pub fn get_iris_depth(iris_landmarks: Vec<Landmark>, focal_length_mm: f64, iris_
     let (iris, mut d) = (to_c(&iris_landmarks), 0.0f64);
     ffi::check(unsafe { ffi::fdl_iris_depth(default_device(), iris.as_ptr(), iris.len() as i32, focal_length_mm, iris_size_px, image_size.0, image_size.1, &mut d) })?;
     Ok(d)
+}
+
+/// Eye contour connections and the number of contour points drawn (reference iris_landmark.rs:44-62).
+pub const EYE_LANDMARK_CONNECTIONS: [(i32, i32); 15] = [
+    (0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6), (6, 7), (7, 8), (9, 10), (10, 11), (11, 12), (12, 13), (13, 14), (0, 9), (8, 14),
+];
+pub const MAX_EYE_LANDMARK: usize = EYE_LANDMARK_CONNECTIONS.len();
+
+pub fn eye_landmarks_to_render_data(
+    eye_contour: Vec<Landmark>, landmark_color: Color, connection_color: Color, thickness: Option<f32>, output: Option<Vec<Annotation>>,
+) -> Vec<Annotation> {
+    landmarks_to_render_data(eye_contour[0..MAX_EYE_LANDMARK].to_vec(), EYE_LANDMARK_CONNECTIONS.to_vec(), Some(landmark_color),
+                             Some(connection_color), Some(thickness.unwrap_or(2.0)), Some(true), output)
+}
+
+pub fn iris_landmarks_to_render_data(
+    iris_landmarks: Vec<Landmark>, landmark_color: Option<Color>, oval_color: Option<Color>, thickness: Option<f64>,
+    image_size: Option<(i32, i32)>, output: Option<Vec<Annotation>>,
+) -> Result<Vec<Annotation>, Error> {
+    let (width, height) = image_size.unwrap_or((-1, -1));
+    let thickness = thickness.unwrap_or(1.0);
+    let mut out = output.unwrap_or_default();
+    if let Some(c) = oval_color {
+        if width < 2 || height < 2 { return Err(Error::msg("oval_color requires a valid image_size arg")); }
+        let radius = get_iris_diameter(&iris_landmarks, (width, height))? / 2.0;
+        let (rh, rv) = (radius / width as f64, radius / height as f64);
+        let ctr = iris_landmarks[IrisIndex::Center as usize];
+        out.push(Annotation::new(vec![AnnotationData::RectOrOval(RectOrOval::new(ctr.x - rh, ctr.y - rv, ctr.x + rh, ctr.y + rv, true))], true, thickness, c));
+    }
+    if let Some(c) = landmark_color {
+        out.push(Annotation::new(iris_landmarks.iter().map(|l| AnnotationData::Point(Point::new(l.x, l.y))).collect(), true, thickness, c));
+    }
+    Ok(out)
 }

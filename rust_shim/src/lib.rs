@@ -9,4 +9,5 @@ pub mod face_detection_lite {
     pub mod face_detection;
     pub mod face_landmark;
     pub mod iris_landmark;
+    pub mod render;
 }

@@ -622,11 +622,20 @@ def test_rust_shim_keeps_the_reference_public_surface():
                              "pub fn iris_roi_from_face_landmarks(face_landmarks: Vec<Landmark>, image_size: (i32, i32)) -> Result<(Rect, Rect), Error>",
                              "pub fn update_face_landmarks_with_iris_results("],
         "utils.rs": ["pub fn convert_image_to_mat(im_bytes: &[u8]) -> Result<Mat, Error>"],
+        "render.rs": ["pub struct Color", "pub fn new(r: Option<i32>, g: Option<i32>, b: Option<i32>, a: Option<i32>) -> Self", "pub struct Colors",
+                      "pub const PINK: Color", "pub struct Point", "pub struct RectOrOval", "pub struct FilledRectOrOval", "pub struct Line",
+                      "pub enum AnnotationData", "pub struct Annotation",
+                      "pub fn new(data: Vec<AnnotationData>, normalized_positions: bool, thickness: f64, color: Color) -> Self",
+                      "pub fn scaled(&self, factor: (f64, f64)) -> Result<Self, Error>", "pub fn detections_to_render_data(",
+                      "pub fn landmarks_to_render_data(",
+                      "pub fn render_to_image(annotations: &Vec<Annotation>, image: &DynamicImage, _blend_mode: Option<bool>) -> DynamicImage"],
     }
     for f, items in want.items():
         src = re.sub(r"\s+", " ", read(f))
         for it in items:
             assert re.sub(r"\s+", " ", it) in src, (f, it)
     lib = open(os.path.join(ROOT, "rust_shim", "src", "lib.rs")).read()
-    for m in ("ffi", "types", "transform", "utils", "face_detection", "face_landmark", "iris_landmark"):
+    for m in ("ffi", "types", "transform", "utils", "face_detection", "face_landmark", "iris_landmark", "render"):
         assert "pub mod %s;" % m in lib
+    assert "pub fn face_landmarks_to_render_data(" in read("face_landmark.rs") and "pub const FACE_LANDMARK_CONNECTIONS" in read("face_landmark.rs")
+    assert "pub fn eye_landmarks_to_render_data(" in read("iris_landmark.rs") and "pub fn iris_landmarks_to_render_data(" in read("iris_landmark.rs")
