@@ -31,6 +31,8 @@ SOURCES = {
     "stem_kernel.cu": [],
     "conv_tc_kernel.cu": [],
     "pw_kernel.cu": [],
+    "chain_plan.cc": [],
+    "chain_kernel.cu": [],
     # the glue arithmetic must not contract a*b+c into FMA (the reference's scalar Rust never does)
     "prepost_kernels.cu": ["-fmad=false"],
     "jpeg_kernels.cu": [],

@@ -99,7 +99,8 @@ struct fdl_iris_model {
   DevBuf<float> out;
 };
 
-namespace fdl { cudaError_t jpeg_debug_phases(long long out[8]); cudaError_t ws_trace_read(unsigned long long* out, int n); }
+namespace fdl { cudaError_t jpeg_debug_phases(long long out[8]); cudaError_t ws_trace_read(unsigned long long* out, int n);
+cudaError_t chain_trace_read(unsigned long long* out, int n); }
 
 struct fdl_frame {
   int device = 0;
@@ -873,6 +874,12 @@ FDL_API int fdl_debug_jpeg_phases(long long* out8) {
 FDL_API int fdl_debug_ws_trace(unsigned long long* out, int n) {
   if (!out) return FDL_ERR_INVALID;
   return fdl::ws_trace_read(out, n) == cudaSuccess ? FDL_OK : FDL_ERR_INVALID;
+}
+
+// not in fdl.h: per-op timeline of the tail-chain kernel's CTA 0 (variant build with -DFDL_WS_TRACE only)
+FDL_API int fdl_debug_chain_trace(unsigned long long* out, int n) {
+  if (!out) return FDL_ERR_INVALID;
+  return fdl::chain_trace_read(out, n) == cudaSuccess ? FDL_OK : FDL_ERR_INVALID;
 }
 
 int fdl_decode_jpeg(int device, const uint8_t* data, size_t len, uint8_t* out_rgb, size_t cap, int* width, int* height) try {

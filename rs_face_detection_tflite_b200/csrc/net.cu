@@ -5,6 +5,7 @@
 #include <utility>
 
 #include "fdl_status.h"
+#include "chain_kernel.cuh"
 #include "mma_kernels.cuh"
 
 namespace fdl {
@@ -22,6 +23,7 @@ Net* Net::create(const std::string& path, int device, std::string* err, int* cod
     if (e == cudaSuccess) e = conv_tc_init();
     if (e == cudaSuccess) e = block_ws_init();
     if (e == cudaSuccess) e = pw_stream_init();
+    if (e == cudaSuccess) e = chain_init();
     if (e == cudaSuccess) e = cudaMalloc(&n->d_weights_, n->plan_.weights.size() * sizeof(float));
     if (e == cudaSuccess)
       e = cudaMemcpy(n->d_weights_, n->plan_.weights.data(), n->plan_.weights.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -89,10 +91,25 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const 
   std::vector<std::pair<int64_t, int>> main_writes;  // (root buffer, step) written on the main stream so far
   int main_last = -1;                                // last step enqueued on the main stream
   int si = -1;
+  const bool chained = mode_ == 1 && plan_.chain.valid && chain_enabled();
   for (const Step& s : plan_.steps) {
     cudaError_t e;
     ++si;
     stream = main_stream;
+    if (chained && si >= plan_.chain.first_step && si <= plan_.chain.last_step) {
+      // the tail chain: ONE launch on the caller's stream at the position of its first step (everything before it is on that
+      // stream too); the steps after it see its stores as main-stream writes of its last step
+      if (step_events && (e = cudaEventRecord(step_events[step_index++], stream)) != cudaSuccess) return e;
+      if (multi) { main_writes.push_back({s.out.buf_offset, plan_.chain.last_step}); main_last = plan_.chain.last_step; }
+      if (si != plan_.chain.first_step) continue;
+      ChainArgs a;
+      for (size_t k = 0; k < plan_.chain.ops.size(); ++k) a.ops[k] = plan_.chain.ops[k];
+      for (size_t k = 0; k < plan_.chain.loads.size(); ++k) a.loads[k] = plan_.chain.loads[k];
+      a.n_ops = (int)plan_.chain.ops.size(); a.n_loads = (int)plan_.chain.loads.size();
+      a.weights = d_weights_; a.arena = d_arena_; a.B = B; a.items = plan_.chain.items; a.n_active = n_active;
+      if ((e = launch_chain(a, stream)) != cudaSuccess) return e;
+      continue;
+    }
     if (multi && s.stream >= 1 && s.stream <= (int)aux_.size()) {
       const int k = s.stream;
       stream = aux_[k - 1];

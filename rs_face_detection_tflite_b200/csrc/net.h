@@ -53,6 +53,7 @@ class Net {
   // into the caller's stream with events, so the two heads of the landmark / iris / detector graphs run side by side.
   std::vector<cudaStream_t> aux_;
   std::vector<cudaEvent_t> ev_fork_, ev_join_;
+
 };
 
 }  // namespace fdl

@@ -657,6 +657,7 @@ bool Plan::build(const TfModel& m, std::string* err) {
     s.text = buf;
     if (s.stream > 0) s.text += " stream=" + std::to_string(s.stream);
   }
+  build_chain(*this);
   return true;
 }
 
@@ -668,6 +669,7 @@ std::string Plan::describe() const {
                 weights.size(), (long long)algo_bytes_per_item, (long long)flops_per_item);
   out += buf;
   for (const auto& s : steps) { out += s.text; out += "\n"; }
+  if (chain.valid) out += chain.text;
   return out;
 }
 
