@@ -29,6 +29,7 @@ SOURCES = {
     "mma_kernels.cu": [],
     "block_ws_kernel.cu": [],
     "stem_kernel.cu": [],
+    "stem_tc_kernel.cu": [],
     "conv_tc_kernel.cu": [],
     "pw_kernel.cu": [],
     "chain_plan.cc": [],

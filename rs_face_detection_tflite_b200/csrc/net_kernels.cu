@@ -259,12 +259,15 @@ cudaError_t net_kernels_init() {
   if (e != cudaSuccess) return e;
   e = stem_kernels_init();
   if (e != cudaSuccess) return e;
+  e = stem_tc_init();
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(fused_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
 }
 
 cudaError_t launch_fused_conv(const ConvArgs& a, cudaStream_t stream) {
   const long long M = (long long)a.B * a.out.H * a.out.W;
   if (M <= 0) return cudaSuccess;
+  if (stem_tc_supported(a)) return launch_stem_tc(a, stream);
   if (stem_supported(a)) return launch_stem_conv(a, stream);
   const int ldA = a.K4 + 4;
   // pick the pixel tile: as large as shared memory allows, smaller when the problem is tiny

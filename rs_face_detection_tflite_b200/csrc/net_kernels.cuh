@@ -58,6 +58,10 @@ cudaError_t launch_elementwise(const EltArgs& a, cudaStream_t stream);
 bool stem_supported(const ConvArgs& a);
 cudaError_t launch_stem_conv(const ConvArgs& a, cudaStream_t stream);
 cudaError_t stem_kernels_init();
+// the same on the tensor cores (stem_tc_kernel.cu): Cout <= 32, output size a multiple of 8 x 16, ConvArgs::mma set
+bool stem_tc_supported(const ConvArgs& a);
+cudaError_t launch_stem_tc(const ConvArgs& a, cudaStream_t stream);
+cudaError_t stem_tc_init();
 cudaError_t net_kernels_init();   // opt-in shared memory sizes; call once per device
 
 void count_launch();              // bumps the library-wide launch counter (fdl_launch_count)
