@@ -77,7 +77,8 @@ constexpr int kPlaneData = TH * TW * 16;      // one channel-quad plane of A: 12
 // Plane stride (== LBO) = kPlaneData + 16 B of bank skew between consecutive channel-quad planes.
 __host__ __device__ inline int plane_bytes(int) { return kPlaneData + 16; }
 constexpr int kEpiThreads = 128;               // 4 epilogue warps: one per TMEM lane quarter
-constexpr int kMaxThreads = 512;
+constexpr int kMaxThreads = 512;              // epilogue + depthwise threads (the MMA warp comes on top)
+constexpr int kMmaThreads = 32;
 constexpr int kMaxStages = 6, kMaxGroups = 3;
 constexpr int kMaxSmemWs = 227 * 1024;
 
@@ -129,7 +130,7 @@ __device__ __forceinline__ float2 unpack_f16x2(uint32_t d) {
   return r;
 }
 
-template <int kMaxT, int kMinB, bool kF16, bool kNarrow = false>
+template <int kMaxT, int kMinB, bool kF16, bool kNarrow = false, bool kMmaWarp = false>
 __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                                                                   const BlockTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // (provably warp-uniform for the MMA warp)
   const int acc_cols = a.acc_cols;              // columns per accumulator buffer
   pdl_launch_dependents();
   pdl_wait();                                   // the previous launch's activations (and *n_active) are visible from here on
@@ -423,8 +424,8 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       ptx::tma_store_commit();
       ptx::tma_store_wait_all0();
     }
-  } else {
-    // ================= depthwise 3x3 -> A operand (hi / lo planes) -> MMA issue =================
+  } else if (tid - kEpiThreads < G * ndwg) {
+    // ================= depthwise 3x3 -> A operand (hi / lo planes) =================
     const int dtid = tid - kEpiThreads;
     const int g = dtid / ndwg, gt = dtid - g * ndwg;
     // Q == 6, one item per thread: with the plain 6-quad pixel stride the items are remapped for conflict-free stores (kMapQ6);
@@ -526,11 +527,13 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       }
       ptx::fence_proxy_async_smem();            // generic-proxy writes of A -> visible to the tensor core (async proxy)
       mbar_arrive(&a_full[g]);
-      if (gt == 0) {
-        WS_T(it, 2);
-        // ---- this tile's MMA chain, issued by one thread ----
+      if (gt == 0) WS_T(it, 2);
+      if constexpr (!kMmaWarp) {
+      if (gt < 32) {
+        // ---- this tile's MMA chain: the group's first warp, converged; one elected lane issues (operands stay uniform: no per-
+        // instruction ELECT / R2UR retry loop as in an `if (thread == 0)` region) ----
         ptx::mbar_wait(&a_full[g], (uint32_t)(kg & 1));
-        WS_T(it, 3);
+        if (gt == 0) WS_T(it, 3);
         if (it >= T) ptx::mbar_wait(&acc_empty[t], (uint32_t)(((it / T) - 1) & 1));
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(t * acc_cols);
@@ -540,26 +543,66 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
           const int ksteps16 = Q >> 1;
           for (int pass = 0; pass < a.wsplit16; ++pass) {
             uint64_t ad = d_ahi, bdsc = pass ? d_w2 : d_w;
-            for (int ks = 0; ks < ksteps16; ++ks, ad += a_step, bdsc += b_step) ptx::mma_f16(d_tmem, ad, bdsc, idesc, (pass | ks) ? 1u : 0u);
+            for (int ks = 0; ks < ksteps16; ++ks, ad += a_step, bdsc += b_step) ptx::mma_f16_elect(d_tmem, ad, bdsc, idesc, (pass | ks) ? 1u : 0u);
           }
-          ptx::mma_commit(&acc_full[t]);
-          ptx::mma_commit(&a_empty[g]);
-          WS_T(it, 4);
+          ptx::mma_commit_elect(&acc_full[t]);
+          ptx::mma_commit_elect(&a_empty[g]);
+          if (gt == 0) WS_T(it, 4);
           continue;
         }
         // bias K step first (overwrites the accumulator), then the hi / lo passes accumulate
-        ptx::mma_tf32(d_tmem, s_desc[4], s_desc[5], idesc, 0u);
+        ptx::mma_tf32_elect(d_tmem, s_desc[4], s_desc[5], idesc, 0u);
         const int ksteps = C >> 3;
         const int npass = a.wsplit == 2 ? 3 : 2;
         for (int pass = 0; pass < npass; ++pass) {
           // pass 0: A_lo * W_hi, pass 1: A_hi * W_hi, pass 2: A_hi * W_lo
           uint64_t ad = pass == 0 ? d_alo : d_ahi, bdsc = pass == 2 ? d_w2 : d_w;
-          for (int ks = 0; ks < ksteps; ++ks, ad += a_step, bdsc += b_step) ptx::mma_tf32(d_tmem, ad, bdsc, idesc, 1u);
+          for (int ks = 0; ks < ksteps; ++ks, ad += a_step, bdsc += b_step) ptx::mma_tf32_elect(d_tmem, ad, bdsc, idesc, 1u);
         }
-        ptx::mma_commit(&acc_full[t]);
-        ptx::mma_commit(&a_empty[g]);
-        WS_T(it, 4);
+        ptx::mma_commit_elect(&acc_full[t]);
+        ptx::mma_commit_elect(&a_empty[g]);
+        if (gt == 0) WS_T(it, 4);
       }
+      }
+    }
+  } else if constexpr (kMmaWarp) {
+    // ================= the last warp: MMA issue.  The whole warp runs the loop converged and one elected lane issues, so the
+    // operands stay on the uniform datapath (an `if (thread == 0)` region makes ptxas move every operand register -> uniform
+    // register with an ELECT / R2UR retry loop per instruction, ~50 ns each); and no depthwise warp is held up by the issue.
+    // Used where the extra warp costs no registers (C = 16: 9 warps per CTA): 119 -> 100 us on the 96 x 96 x 16 blocks.  For C = 24
+    // (11 warps, 96 -> 80 registers) it measured slower (192 -> 200 us), so there the depthwise group's first thread issues. =================
+    const uint32_t idesc = f16 ? ptx::umma_idesc_f16(128, Np) : ptx::umma_idesc_tf32(128, Np);
+    const uint64_t a_step = s_desc[6], b_step = s_desc[7];
+    for (int it = 0; it < my_tiles; ++it) {
+      const int g = it % G, kg = it / G, t = it % T;
+      ptx::mbar_wait(&a_full[g], (uint32_t)(kg & 1));
+      if (lane == 0) WS_T(it, 3);
+      if (it >= T) ptx::mbar_wait(&acc_empty[t], (uint32_t)(((it / T) - 1) & 1));
+      ptx::tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(t * acc_cols);
+      const uint64_t a_goff = (uint64_t)((uint32_t)(g * L.a_buf) >> 4);
+      const uint64_t d_ahi = s_desc[0] + a_goff, d_alo = s_desc[1] + a_goff, d_w = s_desc[2], d_w2 = s_desc[3];
+      if (f16) {
+        // kind::f16, K = 16 = two planes = two channel quads x (hi, lo); pass 0: (A_hi, A_lo) * (W, W), pass 1: (A_hi, A_lo) * (W_lo, 0)
+        const int ksteps16 = Q >> 1;
+        for (int pass = 0; pass < a.wsplit16; ++pass) {
+          uint64_t ad = d_ahi, bdsc = pass ? d_w2 : d_w;
+          for (int ks = 0; ks < ksteps16; ++ks, ad += a_step, bdsc += b_step) ptx::mma_f16_elect(d_tmem, ad, bdsc, idesc, (pass | ks) ? 1u : 0u);
+        }
+      } else {
+        // bias K step first (overwrites the accumulator), then the hi / lo passes accumulate
+        ptx::mma_tf32_elect(d_tmem, s_desc[4], s_desc[5], idesc, 0u);
+        const int ksteps = C >> 3;
+        const int npass = a.wsplit == 2 ? 3 : 2;
+        for (int pass = 0; pass < npass; ++pass) {
+          // pass 0: A_lo * W_hi, pass 1: A_hi * W_hi, pass 2: A_hi * W_lo
+          uint64_t ad = pass == 0 ? d_alo : d_ahi, bdsc = pass == 2 ? d_w2 : d_w;
+          for (int ks = 0; ks < ksteps; ++ks, ad += a_step, bdsc += b_step) ptx::mma_tf32_elect(d_tmem, ad, bdsc, idesc, 1u);
+        }
+      }
+      ptx::mma_commit_elect(&acc_full[t]);
+      ptx::mma_commit_elect(&a_empty[g]);
+      if (lane == 0) WS_T(it, 4);
     }
   }
 
@@ -630,6 +673,7 @@ cudaError_t block_ws_init() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<320, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<224, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<320, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<288, 2, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<320, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(block_ws_kernel<320, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
@@ -676,7 +720,10 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   cudaError_t e;
   static const int narrow_env = getenv("FDL_WS_NARROW") ? atoi(getenv("FDL_WS_NARROW")) : 1;
   const bool narrow = narrow_env && cfg.ctas == 2 && a.Np <= 32 && a.skip_mode == 1 && cfg.OB == 2;
-  if (narrow && a.f16) e = launch_pdl(block_ws_kernel<320, 2, true, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
+  static const int mmaw_env = getenv("FDL_WS_MMA_WARP") ? atoi(getenv("FDL_WS_MMA_WARP")) : 1;
+  if (narrow && a.f16 && mmaw_env && cfg.threads + kMmaThreads <= 288)
+    e = launch_pdl(block_ws_kernel<288, 2, true, true, true>, dim3(grid), dim3(cfg.threads + kMmaThreads), (size_t)cfg.total, stream, tm_in, tm_out, a);
+  else if (narrow && a.f16) e = launch_pdl(block_ws_kernel<320, 2, true, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
   else if (narrow) e = launch_pdl(block_ws_kernel<320, 2, false, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
   else if (cfg.ctas == 3) e = launch_pdl(block_ws_kernel<224, 3, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
   else if (cfg.ctas == 2 && a.f16) e = launch_pdl(block_ws_kernel<320, 2, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
