@@ -63,7 +63,8 @@ def _deps_mtime() -> float:
 
 # Variant builds for A/B measurements (never the product library): name -> extra nvcc flags.  They land in build_<name>/ and
 # libfdl_b200_<name>.so and are loaded with FDL_LIB=<path>.
-VARIANTS = {"trace": ["-DFDL_WS_TRACE"]}
+VARIANTS = {"trace": ["-DFDL_WS_TRACE"], "trace_c32h32": ["-DFDL_WS_TRACE", "-DFDL_TRACE_C=32", "-DFDL_TRACE_H=32"],
+            "trace_c64h16": ["-DFDL_WS_TRACE", "-DFDL_TRACE_C=64", "-DFDL_TRACE_H=16"]}
 
 
 def build(force: bool = False, verbose: bool = False, variant: str | None = None) -> str:

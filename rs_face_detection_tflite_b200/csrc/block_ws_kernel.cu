@@ -40,11 +40,17 @@ bool encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, 
 // first tiles -- [cta][tile][event]: 0 load issued, 1 depthwise sees the tile, 2 depthwise thread 0 done, 3 all depthwise threads done,
 // 4 MMAs issued, 5 epilogue sees the accumulator, 6 epilogue done with the tile, 7 the tile's TMA store issued.
 #ifdef FDL_WS_TRACE
+// (-DFDL_TRACE_C=32 -DFDL_TRACE_H=32: only launches of that block shape write the trace; default: every launch, the last one stays)
+#if defined(FDL_TRACE_C) && defined(FDL_TRACE_H)
+#define FDL_TRACE_MATCH (a.C == FDL_TRACE_C && a.H == FDL_TRACE_H)
+#else
+#define FDL_TRACE_MATCH true
+#endif
 constexpr int kTraceCtas = 4, kTraceTiles = 48;
 __device__ unsigned long long g_ws_trace[kTraceCtas][kTraceTiles][8];
 #define WS_T(it_, ev_)                                                                                              \
   do {                                                                                                              \
-    if (blockIdx.x < kTraceCtas && (it_) >= 0 && (it_) < kTraceTiles) {                                            \
+    if (blockIdx.x < kTraceCtas && (it_) >= 0 && (it_) < kTraceTiles && FDL_TRACE_MATCH) {                         \
       unsigned long long t_;                                                                                        \
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                                        \
       g_ws_trace[blockIdx.x][(it_)][(ev_)] = t_;                                                                   \
@@ -79,10 +85,10 @@ __host__ __device__ inline int plane_bytes(int) { return kPlaneData + 16; }
 constexpr int kEpiThreads = 128;               // 4 epilogue warps: one per TMEM lane quarter
 constexpr int kMaxThreads = 512;              // epilogue + depthwise threads (the MMA warp comes on top)
 constexpr int kMmaThreads = 32;
-constexpr int kMaxStages = 6, kMaxGroups = 3;
+constexpr int kMaxStages = 6, kMaxGroups = 3, kMaxAcc = 4;
 constexpr int kMaxSmemWs = 227 * 1024;
 
-struct WsCfg { int G, ipt, ndwg, NS, OB, threads, total, ctas, in_pad, f16; };
+struct WsCfg { int G, ipt, ndwg, NS, OB, threads, total, ctas, in_pad, f16, teams; };
 struct WsLayout { int alpha, w, wb, ones, in0, in_stage, a0, a_buf, out0, out_stage, total; };
 
 __host__ __device__ inline int align_up_w(int v, int a) { return (v + a - 1) / a * a; }
@@ -130,27 +136,29 @@ __device__ __forceinline__ float2 unpack_f16x2(uint32_t d) {
   return r;
 }
 
-template <int kMaxT, int kMinB, bool kF16, bool kNarrow = false, bool kMmaWarp = false>
+template <int kMaxT, int kMinB, bool kF16, bool kNarrow = false, bool kMmaWarp = false, int kTeams = 1>
 __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
                                                                   const BlockTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kEpi = kTeams * kEpiThreads;    // epilogue threads: one or two teams of four warps (a warp per TMEM lane quarter)
   const int C = a.C, N = a.N, Np = a.Np, Q = C >> 2;
   const int NS = a.stages, G = a.groups, ndwg = a.dw_threads;
   const int kPlaneBytes = plane_bytes(C);
   constexpr bool f16 = kF16;                    // compile-time: the two operand formats must not share registers / code
   const int wcopies = f16 ? a.wsplit16 : a.wsplit;
   const WsLayout L = ws_layout(C, N, Np, wcopies, NS, G, a.out_bufs, a.in_pad, f16 ? 1 : 0);
-  const int T = G > 2 ? G : 2;                  // TMEM accumulators: tile it -> buffer it % T (== its group when G >= 2, so each
-                                                // buffer has ONE issuing thread and its full/empty phases stay in lockstep)
+  // TMEM accumulators: tile it -> buffer it % T.  Two epilogue teams: four, so that the depthwise / MMA side runs two tiles ahead of
+  // each team instead of stalling on the drain of the tile two places back (every phase is tracked per tile: any issuer order works).
+  const int T = kTeams == 2 ? kMaxAcc : (G > 2 ? G : 2);
   uint64_t* in_full = reinterpret_cast<uint64_t*>(smem);             // [kMaxStages]  TMA tile landed
   uint64_t* a_full = in_full + kMaxStages;                           // [kMaxGroups]  A operand of the group written
   uint64_t* a_empty = a_full + kMaxGroups;                           // [kMaxGroups]  MMAs done reading the group's A buffer
-  uint64_t* acc_full = a_empty + kMaxGroups;                         // [kMaxGroups]  accumulator complete
-  uint64_t* acc_empty = acc_full + kMaxGroups;                       // [kMaxGroups]  accumulator drained by the epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kMaxGroups);
-  uint64_t* s_desc = reinterpret_cast<uint64_t*>(smem + 160);         // [6] UMMA descriptors + [2] K-step increments, built once (group 0's)
-  int* s_lstep = reinterpret_cast<int*>(smem + 232);                  // [3] tile-coordinate step of consecutive loads (image, row, column)
+  uint64_t* acc_full = a_empty + kMaxGroups;                         // [kMaxAcc]  accumulator complete
+  uint64_t* acc_empty = acc_full + kMaxAcc;                          // [kMaxAcc]  accumulator drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kMaxAcc);
+  uint64_t* s_desc = reinterpret_cast<uint64_t*>(smem + 176);         // [6] UMMA descriptors + [2] K-step increments, built once (group 0's)
+  int* s_lstep = reinterpret_cast<int*>(smem + 240);                  // [3] tile-coordinate step of consecutive loads (image, row, column)
   float* s_w = reinterpret_cast<float*>(smem + L.w);
 
   const int tiles_per_img = a.tiles_x * a.tiles_y;
@@ -168,6 +176,15 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     l_tx += s_lstep[2]; l_ty += s_lstep[1]; l_b += s_lstep[0];
     if (l_tx >= a.tiles_x) { l_tx -= a.tiles_x; ++l_ty; }
     if (l_ty >= a.tiles_y) { l_ty -= a.tiles_y; ++l_b; }
+  };
+
+  // the same for any tile, by any thread (two epilogue teams: the refills are not issued in tile order by one thread)
+  auto issue_load_at = [&](int it) {          // (divisions: one thread, once per tile)
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x, st = it % NS;
+    const int lb = tile / tiles_per_img, r = tile - lb * tiles_per_img, lty = r / a.tiles_x, ltx = r - lty * a.tiles_x;
+    ptx::mbar_arrive_expect_tx(&in_full[st], in_bytes);
+    ptx::tma_load_4d(smem + L.in0 + st * L.in_stage, &tm_in, &in_full[st], 0, ltx * TW - 1, lty * TH - 1, lb);
+    WS_T(it, 0);
   };
 
   // ---- one-time setup: nothing here depends on the previous launch (PDL, see pdl.h) ----
@@ -228,12 +245,12 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
 
   if (my_tiles == 0) {
     // nothing to do (fewer active items than CTAs)
-  } else if (warp < 4) {
+  } else if (warp < 4 * kTeams) {
     // ================= epilogue: TMEM -> (+skip, act) -> staging tile -> TMA store; refills the input ring =================
     // thread == TMEM lane == pixel.  Both the input tile (TMA load with a box wider than the tensor: the tail of each
     // pixel is zero-filled) and the output staging tile (TMA store with the same trick: the tail is clipped) have a
     // pixel stride of an ODD number of 16-byte quads, so the per-pixel 16-byte accesses are bank-conflict free.
-    const int p = tid;                          // TMEM lane (warp w may access lanes 32w..32w+31)
+    const int p = tid & 127;                    // TMEM lane (warp w may access lanes 32 (w % 4) .. + 31)
     const int py = p / TW, px = p - py * TW;
     const int NPf = ((N >> 2) | 1) << 2;        // staging pixel stride (floats)
     int pb = 0, pty = 0, ptx_ = 0;              // coordinates of the previous tile (its TMA store is issued one tile late)
@@ -248,6 +265,94 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     // ---- narrow blocks (N <= 32, residual from the resident input tile, two staging buffers): the epilogue sets the CTA's pace (measured
     // with FDL_WS_TRACE: ~1.9 us per tile, most of it index arithmetic, runtime-bounded loops and one TMEM round trip per 16
     // columns), so this path keeps its indices in counters, its residual in six registers and both accumulator halves in flight.
+    // ---- two epilogue teams (wide blocks, one CTA per SM): on the 32 x 32 x 48 detector stage the timeline (FDL_WS_TRACE) has the
+    // depthwise group done with a tile in 0.65 us and ONE team of four warps busy 2.4 us per tile (1.5 us of epilogue arithmetic for
+    // 128 pixels x 48 channels, the store hand-over, the refill): the epilogue sets the pace.  Two teams take alternate tiles; each
+    // owns a staging buffer, issues its own TMA stores and refills the input stage of the tile it has just finished.
+    if constexpr (kTeams == 2) {
+      const int team = warp >> 2, bar_id = 1 + team;
+      const bool leader = p == 0;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      float* s_o = reinterpret_cast<float*>(smem + L.out0 + team * L.out_stage) + p * NPf;
+      for (int it = 0; it < my_tiles; ++it) {
+        if (it > 0) {
+          tx += step_x; ty += step_y; b += step_b;
+          if (tx >= a.tiles_x) { tx -= a.tiles_x; ++ty; }
+          if (ty >= a.tiles_y) { ty -= a.tiles_y; ++b; }
+        }
+        if ((it & 1) != team) continue;
+        const int s = it % NS, t = it % T;
+        const int oy = ty * TH + py, ox = tx * TW + px;
+        const bool inside = oy < a.H && ox < a.W;
+        const float* skip_smem = reinterpret_cast<const float*>(smem + L.in0 + s * L.in_stage) + ((py + 1) * ITW + (px + 1)) * CP;
+        const float* skip_g = (a.skip_mode == 2 && inside) ? a.skip + (long long)b * a.skip_bstride + ((long long)oy * a.W + ox) * a.skip_c : nullptr;
+        float4 res[8], resn[8];
+        auto load_res = [&](int c0, float4 (&d)[8]) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int n = c0 + 4 * j;
+            d[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < a.skip_c) {
+              if (a.skip_mode == 1) d[j] = ld4(skip_smem + n);
+              else if (skip_g) d[j] = __ldg(reinterpret_cast<const float4*>(skip_g + n));
+            }
+          }
+        };
+        if (a.skip_mode == 1) ptx::mbar_wait(&in_full[s], (uint32_t)((it / NS) & 1));
+        load_res(0, res);
+        ptx::mbar_wait(&acc_full[t], (uint32_t)((it / T) & 1));
+        ptx::tc_fence_after_sync();
+        if (tid == 0) WS_T(it, 5);
+        if (leader) ptx::tma_store_wait_read0();      // this team's previous store has read its staging buffer
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        const uint32_t taddr = taddr0 + (uint32_t)(t * acc_cols);
+        for (int c0 = 0; c0 < Np; c0 += 32) {
+          if (c0 + 32 < Np) load_res(c0 + 32, resn);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int ch = c0 + 16 * h;
+            if (ch >= Np) break;
+            uint32_t r[16];
+            ptx::tmem_ld16_issue(taddr + (uint32_t)ch, r);
+            ptx::tmem_ld_wait16(r);
+            if (ch + 16 >= Np) {                    // accumulator drained: hand it back to the issuing thread
+              ptx::tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&acc_empty[t]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = ch + 4 * j;
+              if (n >= N) break;
+              float4 rs = res[4 * h + j];
+              if (f16) { rs.x += a.bias_c[n]; rs.y += a.bias_c[n + 1]; rs.z += a.bias_c[n + 2]; rs.w += a.bias_c[n + 3]; }
+              float4 o = make_float4(__uint_as_float(r[4 * j]) + rs.x, __uint_as_float(r[4 * j + 1]) + rs.y, __uint_as_float(r[4 * j + 2]) + rs.z,
+                                     __uint_as_float(r[4 * j + 3]) + rs.w);
+              if (a.act == ACT_RELU) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+              } else if (a.act == ACT_PRELU) {
+                o.x = o.x >= 0.f ? o.x : o.x * a.alpha_c[n]; o.y = o.y >= 0.f ? o.y : o.y * a.alpha_c[n + 1];
+                o.z = o.z >= 0.f ? o.z : o.z * a.alpha_c[n + 2]; o.w = o.w >= 0.f ? o.w : o.w * a.alpha_c[n + 3];
+              }
+              *reinterpret_cast<float4*>(s_o + n) = o;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) res[j] = resn[j];
+        }
+        if (tid == 0) WS_T(it, 6);
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (leader) {
+          ptx::tma_store_4d(&tm_out, smem + L.out0 + team * L.out_stage, 0, tx * TW, ty * TH, b);
+          ptx::tma_store_commit();
+          // residual from the resident input tile: the team is past its reads of this tile's stage (and the depthwise finished with it
+          // before the MMAs): refill.  (Otherwise the depthwise group refills as soon as IT is done with the stage, see there.)
+          if (a.skip_mode == 1 && it + NS < my_tiles) issue_load_at(it + NS);
+        }
+      }
+      if (leader) ptx::tma_store_wait_all0();
+    } else
     if constexpr (kNarrow) {
       int s = 0, t = 0, ph_in = 0, ph_acc = 0;
       const int sq = a.skip_c >> 2;
@@ -415,6 +520,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       if (tid == 0) WS_T(it, 6);
     }
     }
+    if constexpr (kTeams == 1) {
     // the last tile's store
     ptx::fence_proxy_async_smem();
     if (tid == 0) ptx::tma_store_wait_read0();
@@ -424,9 +530,10 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       ptx::tma_store_commit();
       ptx::tma_store_wait_all0();
     }
-  } else if (tid - kEpiThreads < G * ndwg) {
+    }
+  } else if (tid - kEpi < G * ndwg) {
     // ================= depthwise 3x3 -> A operand (hi / lo planes) =================
-    const int dtid = tid - kEpiThreads;
+    const int dtid = tid - kEpi;
     const int g = dtid / ndwg, gt = dtid - g * ndwg;
     // Q == 6, one item per thread: with the plain 6-quad pixel stride the items are remapped for conflict-free stores (kMapQ6);
     // with the padded 7-quad stride (f16 mode: shared memory allows it) "x fastest" is conflict-free for loads AND stores.
@@ -534,6 +641,12 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
         // instruction ELECT / R2UR retry loop as in an `if (thread == 0)` region) ----
         ptx::mbar_wait(&a_full[g], (uint32_t)(kg & 1));
         if (gt == 0) WS_T(it, 3);
+        if constexpr (kTeams == 2) {
+          // nobody else reads this tile's input stage (residual from global memory, or none): refill it now, not after the epilogue --
+          // on the iris 32 x 32 blocks the trace had the next load issued 5 us late and the depthwise waiting 3 us for it
+          if (a.skip_mode != 1 && gt == 0 && it + NS < my_tiles) issue_load_at(it + NS);
+          __syncwarp();
+        }
         if (it >= T) ptx::mbar_wait(&acc_empty[t], (uint32_t)(((it / T) - 1) & 1));
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(t * acc_cols);
@@ -629,13 +742,17 @@ bool pick_cfg(int C, int N, int Np, int wsplit, int f16, WsCfg* cfg) {
   // stages, one staging buffer: six tiles in flight per SM instead of four.
   static const int ctas_env = getenv("FDL_WS_CTAS") ? atoi(getenv("FDL_WS_CTAS")) : 2;
   const bool three = ctas_env == 3 && f16 && (Q == 4 || Q == 6);
+  // Wide blocks (one CTA per SM): two epilogue teams, paid for with depthwise threads (see the kernel).  FDL_WS_TEAMS=1: one team.
+  static const int teams_env = getenv("FDL_WS_TEAMS") ? atoi(getenv("FDL_WS_TEAMS")) : 2;
+  const int teams = (Q == 4 || Q == 6 || teams_env != 2) ? 1 : 2;
+  const int epi = teams * kEpiThreads;
   switch (Q) {
     case 4: G = 1; ipt = three ? 2 : 1; ctas = three ? 3 : 2; break;
     case 6: G = 1; ipt = three ? 2 : 1; ctas = three ? 3 : 2; break;
     case 8: G = 3; ipt = 2; break;
     default:
       ipt = 1;
-      while ((32 * Q) / ipt > kMaxThreads - kEpiThreads || (32 * Q) % ipt != 0 || ((32 * Q) / ipt) % 32 != 0 || ((32 * Q) / ipt) % Q != 0) {
+      while ((32 * Q) / ipt > kMaxThreads - epi || (32 * Q) % ipt != 0 || ((32 * Q) / ipt) % 32 != 0 || ((32 * Q) / ipt) % Q != 0) {
         if (++ipt > 8) return false;
       }
       break;
@@ -651,12 +768,12 @@ bool pick_cfg(int C, int N, int Np, int wsplit, int f16, WsCfg* cfg) {
   const int OB = ob_env == 1 || ob_env == 2 ? ob_env : (ctas == 3 ? 1 : 2);
   for (; G >= 1; --G) {
     const int ndwg = 32 * Q / ipt;
-    if (kEpiThreads + G * ndwg > (ctas == 3 ? 224 : (ctas == 2 ? 320 : kMaxThreads))) continue;
+    if (epi + G * ndwg > (ctas == 3 ? 224 : (ctas == 2 ? 320 : kMaxThreads))) continue;
     for (int NS = (G + 3 < kMaxStages ? G + 3 : kMaxStages); NS >= (ctas == 3 ? 2 : G + 2); --NS) {   // the refill of a stage trails its tile by one epilogue
       if (ns_cap && NS > ns_cap && NS > G + 2) continue;
       WsLayout L = ws_layout(C, N, Np, wsplit, NS, G, OB, in_pad, f16);
       if (L.total <= budget) {
-        cfg->G = G; cfg->ipt = ipt; cfg->ndwg = ndwg; cfg->NS = NS; cfg->OB = OB; cfg->threads = kEpiThreads + G * ndwg; cfg->total = L.total;
+        cfg->G = G; cfg->ipt = ipt; cfg->ndwg = ndwg; cfg->NS = NS; cfg->OB = OB; cfg->threads = epi + G * ndwg; cfg->total = L.total; cfg->teams = teams;
         cfg->ctas = ctas; cfg->in_pad = in_pad; cfg->f16 = f16;
         return true;
       }
@@ -671,6 +788,8 @@ cudaError_t block_ws_init() {
   cudaError_t e = cudaFuncSetAttribute(block_ws_kernel<512, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<512, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<320, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<512, 1, true, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<512, 1, false, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<224, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<320, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(block_ws_kernel<288, 2, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemWs);
@@ -710,7 +829,7 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   a.tiles_y = (a.H + TH - 1) / TH;
   a.acc_cols = a.Np <= 32 ? 32 : (a.Np <= 64 ? 64 : 128);
   {
-    const int need = (cfg.G > 2 ? cfg.G : 2) * a.acc_cols;
+    const int need = (cfg.teams == 2 ? kMaxAcc : (cfg.G > 2 ? cfg.G : 2)) * a.acc_cols;
     a.tmem_cols = 32;
     while (a.tmem_cols < need) a.tmem_cols *= 2;
   }
@@ -728,13 +847,15 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   else if (cfg.ctas == 3) e = launch_pdl(block_ws_kernel<224, 3, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
   else if (cfg.ctas == 2 && a.f16) e = launch_pdl(block_ws_kernel<320, 2, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
   else if (cfg.ctas == 2) e = launch_pdl(block_ws_kernel<320, 2, false>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
+  else if (cfg.teams == 2 && a.f16) e = launch_pdl(block_ws_kernel<512, 1, true, false, false, 2>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
+  else if (cfg.teams == 2) e = launch_pdl(block_ws_kernel<512, 1, false, false, false, 2>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
   else if (a.f16) e = launch_pdl(block_ws_kernel<512, 1, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
   else e = launch_pdl(block_ws_kernel<512, 1, false>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
   count_launch();
   static const bool verbose = getenv("FDL_WS_VERBOSE") != nullptr;
   if (verbose)
-    fprintf(stderr, "[ws C=%d N=%d %dx%d G=%d NS=%d ctas=%d thr=%d smem=%d in_pad=%d f16=%d]\n", a.C, a.N, a.H, a.W, cfg.G, cfg.NS, cfg.ctas, cfg.threads,
-            cfg.total, cfg.in_pad, cfg.f16);
+    fprintf(stderr, "[ws C=%d N=%d %dx%d G=%d NS=%d ctas=%d thr=%d smem=%d in_pad=%d f16=%d teams=%d]\n", a.C, a.N, a.H, a.W, cfg.G, cfg.NS, cfg.ctas,
+            cfg.threads, cfg.total, cfg.in_pad, cfg.f16, cfg.teams);
   return e;
 }
 

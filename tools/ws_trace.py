@@ -5,8 +5,10 @@ import numpy as np
 import rs_face_detection_tflite_b200 as fdl
 from rs_face_detection_tflite_b200 import _lib
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-net = fdl.Net("models/face_detection_back.tflite", 0)
-x = np.random.default_rng(0).uniform(-1, 1, (B, 256, 256, 3)).astype(np.float32)
+name = sys.argv[2] if len(sys.argv) > 2 else "face_detection_back"
+S = {"face_detection_back": 256, "face_landmark": 192, "iris_landmark": 64}[name]
+net = fdl.Net("models/%s.tflite" % name, 0)
+x = np.random.default_rng(0).uniform(-1, 1, (B, S, S, 3)).astype(np.float32)
 ms = net.time_steps(B, 3, x)
 print("step times (us):", [round(1e3 * float(v), 1) for v in ms[:9]])
 # the trace buffer now holds the LAST block_ws launch of the pass; run the net only up to step 2 is not possible, so read what is there
