@@ -32,6 +32,7 @@ SOURCES = {
     "stem_tc_kernel.cu": [],
     "conv_tc_kernel.cu": [],
     "pw_kernel.cu": [],
+    "pw_tc_kernel.cu": [],
     "chain_plan.cc": [],
     "chain_kernel.cu": [],
     # the glue arithmetic must not contract a*b+c into FMA (the reference's scalar Rust never does)

@@ -152,6 +152,14 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const 
         else { a.skip_mode = 2; a.skip = sk.p; a.skip_bstride = sk.bstride; }
       }
       e = (mode_ == 1 && block_ws_supported(s)) ? launch_block_ws(l, stream) : launch_block_tc(l, stream);
+    } else if (mode_ >= 1 && pw_tc_supported(s, B)) {
+      ConvArgs a;
+      a.in = in_view(s); a.out = view(s.out, B);
+      a.kh = a.kw = 1; a.K = s.K; a.K4 = s.K4; a.N = s.N; a.Npad = s.Npad;
+      a.w = d_weights_ + s.w; a.bias = d_weights_ + s.b;
+      if (s.alpha >= 0) a.alpha = d_weights_ + s.alpha;
+      a.act = s.act; a.B = B; a.n_active = n_active;
+      e = launch_pw_tc(a, stream);
     } else if (mode_ >= 1 && pw_stream_supported(s, B)) {
       ConvArgs a;
       a.in = in_view(s); a.out = view(s.out, B);

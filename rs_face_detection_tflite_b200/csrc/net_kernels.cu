@@ -261,6 +261,8 @@ cudaError_t net_kernels_init() {
   if (e != cudaSuccess) return e;
   e = stem_tc_init();
   if (e != cudaSuccess) return e;
+  e = pw_tc_init();
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(fused_conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
 }
 

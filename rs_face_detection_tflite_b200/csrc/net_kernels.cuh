@@ -62,6 +62,11 @@ cudaError_t stem_kernels_init();
 bool stem_tc_supported(const ConvArgs& a);
 cudaError_t launch_stem_tc(const ConvArgs& a, cudaStream_t stream);
 cudaError_t stem_tc_init();
+// large-map 1x1 convolutions as a streaming tensor-core GEMM (pw_tc_kernel.cu): Cin 64 / 128, Cout <= 64, dense tensors
+struct Step;
+bool pw_tc_supported(const Step& s, int B);
+cudaError_t launch_pw_tc(const ConvArgs& a, cudaStream_t stream);
+cudaError_t pw_tc_init();
 cudaError_t net_kernels_init();   // opt-in shared memory sizes; call once per device
 
 void count_launch();              // bumps the library-wide launch counter (fdl_launch_count)
