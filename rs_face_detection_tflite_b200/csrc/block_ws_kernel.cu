@@ -97,7 +97,7 @@ __host__ __device__ inline int align_up_w(int v, int a) { return (v + a - 1) / a
 // the bias is added in the epilogue (no bias K step: no `wb` / `ones` regions).
 __host__ __device__ inline WsLayout ws_layout(int C, int N, int Np, int wsplit, int NS, int G, int OB, int in_pad, int f16) {
   WsLayout L;
-  int off = 256;                                // barriers + tmem slot
+  int off = 384;                                // barriers, tmem slot, descriptors
   L.alpha = off; off += Np * 4;
   off = align_up_w(off, 128);
   L.w = off; off += wsplit * (C / 4) * Np * 16;
@@ -138,7 +138,7 @@ __device__ __forceinline__ float2 unpack_f16x2(uint32_t d) {
 
 template <int kMaxT, int kMinB, bool kF16, bool kNarrow = false, bool kMmaWarp = false, int kTeams = 1>
 __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
-                                                                  const BlockTcArgs a) {
+                                                                  const __grid_constant__ CUtensorMap tm_skip, const BlockTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int kEpi = kTeams * kEpiThreads;    // epilogue threads: one or two teams of four warps (a warp per TMEM lane quarter)
@@ -157,8 +157,9 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
   uint64_t* acc_full = a_empty + kMaxGroups;                         // [kMaxAcc]  accumulator complete
   uint64_t* acc_empty = acc_full + kMaxAcc;                          // [kMaxAcc]  accumulator drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kMaxAcc);
-  uint64_t* s_desc = reinterpret_cast<uint64_t*>(smem + 176);         // [6] UMMA descriptors + [2] K-step increments, built once (group 0's)
-  int* s_lstep = reinterpret_cast<int*>(smem + 240);                  // [3] tile-coordinate step of consecutive loads (image, row, column)
+  uint64_t* skip_full = reinterpret_cast<uint64_t*>(smem + 168);      // [2] a team's residual tile landed in its staging buffer (two teams)
+  uint64_t* s_desc = reinterpret_cast<uint64_t*>(smem + 192);         // [6] UMMA descriptors + [2] K-step increments, built once (group 0's)
+  int* s_lstep = reinterpret_cast<int*>(smem + 256);                  // [3] tile-coordinate step of consecutive loads (image, row, column)
   float* s_w = reinterpret_cast<float*>(smem + L.w);
 
   const int tiles_per_img = a.tiles_x * a.tiles_y;
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
     for (int s = 0; s < NS; ++s) ptx::mbar_init(&in_full[s], 1);
     for (int g = 0; g < G; ++g) { ptx::mbar_init(&a_full[g], (uint32_t)ndwg); ptx::mbar_init(&a_empty[g], 1); }
     for (int t = 0; t < T; ++t) { ptx::mbar_init(&acc_full[t], 1); ptx::mbar_init(&acc_empty[t], 4); }
+    ptx::mbar_init(&skip_full[0], 1); ptx::mbar_init(&skip_full[1], 1);
     ptx::fence_mbar_init();
     const int t0 = (int)blockIdx.x, r0 = t0 % tiles_per_img;
     l_b = t0 / tiles_per_img; l_ty = r0 / a.tiles_x; l_tx = r0 - l_ty * a.tiles_x;
@@ -274,6 +276,7 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       const bool leader = p == 0;
       const uint32_t taddr0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
       float* s_o = reinterpret_cast<float*>(smem + L.out0 + team * L.out_stage) + p * NPf;
+      const bool skip_tma = a.skip_mode == 2 && a.skip_tma != 0;
       for (int it = 0; it < my_tiles; ++it) {
         if (it > 0) {
           tx += step_x; ty += step_y; b += step_b;
@@ -292,19 +295,32 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
           for (int j = 0; j < 8; ++j) {
             const int n = c0 + 4 * j;
             d[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n < a.skip_c) {
+            if (skip_tma) { if (n < N) d[j] = ld4(s_o + n); }
+            else if (n < a.skip_c) {
               if (a.skip_mode == 1) d[j] = ld4(skip_smem + n);
               else if (skip_g) d[j] = __ldg(reinterpret_cast<const float4*>(skip_g + n));
             }
           }
         };
+        if (skip_tma) {
+          // the residual tile travels by TMA straight into the team's staging buffer (same pixel stride as the output tile; channels
+          // beyond skip_c are zero-filled: the channel PAD) and the epilogue updates it in place -- no per-thread global loads
+          if (leader) {
+            ptx::tma_store_wait_read0();                // this team's previous store has read its staging buffer
+            ptx::mbar_arrive_expect_tx(&skip_full[team], (uint32_t)(TH * TW * NPf * 4));
+            ptx::tma_load_4d(smem + L.out0 + team * L.out_stage, &tm_skip, &skip_full[team], 0, tx * TW, ty * TH, b);
+          }
+          ptx::mbar_wait(&skip_full[team], (uint32_t)((it >> 1) & 1));
+        }
         if (a.skip_mode == 1) ptx::mbar_wait(&in_full[s], (uint32_t)((it / NS) & 1));
         load_res(0, res);
         ptx::mbar_wait(&acc_full[t], (uint32_t)((it / T) & 1));
         ptx::tc_fence_after_sync();
         if (tid == 0) WS_T(it, 5);
-        if (leader) ptx::tma_store_wait_read0();      // this team's previous store has read its staging buffer
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (!skip_tma) {
+          if (leader) ptx::tma_store_wait_read0();      // this team's previous store has read its staging buffer
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        }
         const uint32_t taddr = taddr0 + (uint32_t)(t * acc_cols);
         for (int c0 = 0; c0 < Np; c0 += 32) {
           if (c0 + 32 < Np) load_res(c0 + 32, resn);
@@ -825,6 +841,11 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   CUtensorMap tm_in, tm_out;
   if (!encode_nhwc(&tm_in, l.in, a.B, a.H, a.W, a.C, (long long)a.H * a.W * a.C, ITH, ITW, cfg.in_pad ? ((a.C / 4) | 1) * 4 : a.C)) return cudaErrorInvalidValue;
   if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW, ((a.N / 4) | 1) * 4)) return cudaErrorInvalidValue;
+  CUtensorMap tm_skip = tm_in;                  // (a valid map when the residual does not travel by TMA)
+  a.skip_tma = 0;
+  if (cfg.teams == 2 && a.skip_mode == 2 && a.skip != nullptr && a.skip_bstride == (long long)a.H * a.W * a.skip_c && a.skip_c % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(a.skip) & 15) == 0 && encode_nhwc(&tm_skip, a.skip, a.B, a.H, a.W, a.skip_c, a.skip_bstride, TH, TW, ((a.N / 4) | 1) * 4))
+    a.skip_tma = 1;
   a.tiles_x = (a.W + TW - 1) / TW;
   a.tiles_y = (a.H + TH - 1) / TH;
   a.acc_cols = a.Np <= 32 ? 32 : (a.Np <= 64 ? 64 : 128);
@@ -841,16 +862,16 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   const bool narrow = narrow_env && cfg.ctas == 2 && a.Np <= 32 && a.skip_mode == 1 && cfg.OB == 2;
   static const int mmaw_env = getenv("FDL_WS_MMA_WARP") ? atoi(getenv("FDL_WS_MMA_WARP")) : 1;
   if (narrow && a.f16 && mmaw_env && cfg.threads + kMmaThreads <= 288)
-    e = launch_pdl(block_ws_kernel<288, 2, true, true, true>, dim3(grid), dim3(cfg.threads + kMmaThreads), (size_t)cfg.total, stream, tm_in, tm_out, a);
-  else if (narrow && a.f16) e = launch_pdl(block_ws_kernel<320, 2, true, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
-  else if (narrow) e = launch_pdl(block_ws_kernel<320, 2, false, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
-  else if (cfg.ctas == 3) e = launch_pdl(block_ws_kernel<224, 3, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
-  else if (cfg.ctas == 2 && a.f16) e = launch_pdl(block_ws_kernel<320, 2, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
-  else if (cfg.ctas == 2) e = launch_pdl(block_ws_kernel<320, 2, false>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
-  else if (cfg.teams == 2 && a.f16) e = launch_pdl(block_ws_kernel<512, 1, true, false, false, 2>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
-  else if (cfg.teams == 2) e = launch_pdl(block_ws_kernel<512, 1, false, false, false, 2>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
-  else if (a.f16) e = launch_pdl(block_ws_kernel<512, 1, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
-  else e = launch_pdl(block_ws_kernel<512, 1, false>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, a);
+    e = launch_pdl(block_ws_kernel<288, 2, true, true, true>, dim3(grid), dim3(cfg.threads + kMmaThreads), (size_t)cfg.total, stream, tm_in, tm_out, tm_skip, a);
+  else if (narrow && a.f16) e = launch_pdl(block_ws_kernel<320, 2, true, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, tm_skip, a);
+  else if (narrow) e = launch_pdl(block_ws_kernel<320, 2, false, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, tm_skip, a);
+  else if (cfg.ctas == 3) e = launch_pdl(block_ws_kernel<224, 3, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, tm_skip, a);
+  else if (cfg.ctas == 2 && a.f16) e = launch_pdl(block_ws_kernel<320, 2, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, tm_skip, a);
+  else if (cfg.ctas == 2) e = launch_pdl(block_ws_kernel<320, 2, false>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, tm_skip, a);
+  else if (cfg.teams == 2 && a.f16) e = launch_pdl(block_ws_kernel<512, 1, true, false, false, 2>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, tm_skip, a);
+  else if (cfg.teams == 2) e = launch_pdl(block_ws_kernel<512, 1, false, false, false, 2>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, tm_skip, a);
+  else if (a.f16) e = launch_pdl(block_ws_kernel<512, 1, true>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, tm_skip, a);
+  else e = launch_pdl(block_ws_kernel<512, 1, false>, dim3(grid), dim3(cfg.threads), (size_t)cfg.total, stream, tm_in, tm_out, tm_skip, a);
   count_launch();
   static const bool verbose = getenv("FDL_WS_VERBOSE") != nullptr;
   if (verbose)

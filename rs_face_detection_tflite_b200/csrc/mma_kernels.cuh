@@ -32,6 +32,7 @@ struct BlockTcArgs {
   int out_bufs = 1;                // block_ws_kernel: output staging buffers (TMA store of tile i overlaps the epilogue of i+1)
   int acc_cols = 32;               // block_ws_kernel: TMEM columns per accumulator buffer
   int in_pad = 0;                  // block_ws_kernel: input tile pixel stride padded to an odd number of quads
+  int skip_tma = 0;                // block_ws_kernel, two epilogue teams: the residual tile (skip_mode 2) is loaded by TMA into the staging buffer
   int tc_cp = 0, tc_np = 0;        // blaze_block_tc_kernel: pixel strides (floats) of the input / output staging tiles (>= C / N)
   // block_ws_kernel, f16-split mode: the depthwise result is written as ONE plane set of (f16 hi, f16 lo) pairs and multiplied
   // with tcgen05 kind::f16 (half the A-operand bytes in shared memory of the tf32 hi / lo planes, same 2^-22 fidelity)

@@ -37,13 +37,12 @@ constexpr int TH = 8, TW = 16;                 // output tile: 128 pixels == UMM
 constexpr int kEpiThreads = 256, kBuildThreads = 256, kThreads = kEpiThreads + kBuildThreads + 32;
 constexpr int NS = 3;                          // input patches in flight
 constexpr int kPlane = TH * TW * 16 + 16;      // one 8-value plane of A: 128 rows x 16 B (+ 16 B of bank skew)
-constexpr int Np = 32;                         // accumulator columns (Cout <= 32)
 
 struct StemTcArgs {
   const float* w = nullptr;      // [K4][Npad] fp32, k = (ky * KW + kx) * 3 + c
   const float* bias = nullptr;
   const float* alpha = nullptr;
-  int N = 0, Npad = 0, act = 0, wsplit = 1;
+  int N = 0, Npad = 0, Np = 32, act = 0, wsplit = 1;   // Np: accumulator columns (32 or 64)
   int KH = 5, KW = 5, pad_t = 0, pad_l = 0;
   int B = 0, tiles_x = 0, tiles_y = 0;
   int patch_rows = 0, patch_floats = 0;    // shared-memory patch: rows x floats per row (a multiple of 4)
@@ -53,7 +52,7 @@ struct StemTcArgs {
 
 struct Layout { int bias, w, in0, in_stage, a0, out0, out_stage, total; };
 __host__ __device__ inline int align_up_s(int v, int a) { return (v + a - 1) / a * a; }
-__host__ __device__ inline Layout layout(int KH, int patch_rows, int patch_floats, int N) {
+__host__ __device__ inline Layout layout(int KH, int patch_rows, int patch_floats, int N, int Np) {
   Layout L;
   int off = 128;                               // barriers + tmem slot
   L.bias = off; off += Np * 4;
@@ -98,7 +97,8 @@ __global__ void __launch_bounds__(kThreads, 2) stem_tc_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-  const Layout L = layout(KH, a.patch_rows, a.patch_floats, a.N);
+  const int Np = a.Np;
+  const Layout L = layout(KH, a.patch_rows, a.patch_floats, a.N, Np);
   uint64_t* in_full = reinterpret_cast<uint64_t*>(smem);       // [NS]  patch landed
   uint64_t* a_full = in_full + NS;                             // [KH]  the two A planes of kernel row ky written by every builder
   uint64_t* a_empty = a_full + KH;                             //       the MMAs have read the A planes
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_tc_kernel(const __grid_const
     for (int t = 0; t < 2; ++t) { ptx::mbar_init(&acc_full[t], 1); ptx::mbar_init(&acc_empty[t], 4); }
     ptx::fence_mbar_init();
   }
-  if (warp == 0) ptx::tmem_alloc(tmem_slot, 64);
+  if (warp == 0) ptx::tmem_alloc(tmem_slot, (uint32_t)(2 * Np));
   __syncthreads();
   {
     // weights: fp32 [k][n] in global memory -> f16 hi / lo planes in the K' order of the A operand (k' = 16 ky + j, j = 3 kx + c < 3 KW)
@@ -169,31 +169,39 @@ __global__ void __launch_bounds__(kThreads, 2) stem_tc_kernel(const __grid_const
       ptx::mbar_wait(&acc_full[e], (uint32_t)(k & 1));
       ptx::tc_fence_after_sync();
       uint32_t r0[16], r1[16];
-      ptx::tmem_ld16_issue(taddr, r0);
+      ptx::tmem_ld16_issue(taddr, r0);                         // (in flight across the hand-over of the staging buffer)
       ptx::tmem_ld16_issue(taddr + 16u, r1);
       if (leader) ptx::tma_store_wait_read0();                 // this team's previous store has read the staging buffer
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      ptx::tmem_ld_wait16(r0);
-      ptx::tmem_ld_wait16(r1);
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[e]);
+      for (int c0 = 0; c0 < Np; c0 += 32) {
+        if (c0 > 0) {
+          ptx::tmem_ld16_issue(taddr + (uint32_t)c0, r0);
+          ptx::tmem_ld16_issue(taddr + (uint32_t)c0 + 16u, r1);
+        }
+        ptx::tmem_ld_wait16(r0);
+        ptx::tmem_ld_wait16(r1);
+        if (c0 + 32 >= Np) {                                   // accumulator drained
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[e]);
+        }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int n = 16 * h + 4 * j;
-          if (n < a.N) {
-            const uint32_t* r = h ? r1 : r0;
-            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n);
-            float4 o = make_float4(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y, __uint_as_float(r[4 * j + 2]) + b4.z,
-                                   __uint_as_float(r[4 * j + 3]) + b4.w);
-            if (a.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            else if (a.act == ACT_PRELU) {
-              const float4 al = __ldg(reinterpret_cast<const float4*>(a.alpha + n));
-              o.x = o.x >= 0.f ? o.x : o.x * al.x; o.y = o.y >= 0.f ? o.y : o.y * al.y; o.z = o.z >= 0.f ? o.z : o.z * al.z; o.w = o.w >= 0.f ? o.w : o.w * al.w;
+          for (int j = 0; j < 4; ++j) {
+            const int n = c0 + 16 * h + 4 * j;
+            if (n < a.N) {
+              const uint32_t* r = h ? r1 : r0;
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + n);
+              float4 o = make_float4(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y, __uint_as_float(r[4 * j + 2]) + b4.z,
+                                     __uint_as_float(r[4 * j + 3]) + b4.w);
+              if (a.act == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              else if (a.act == ACT_PRELU) {
+                const float4 al = __ldg(reinterpret_cast<const float4*>(a.alpha + n));
+                o.x = o.x >= 0.f ? o.x : o.x * al.x; o.y = o.y >= 0.f ? o.y : o.y * al.y; o.z = o.z >= 0.f ? o.z : o.z * al.z; o.w = o.w >= 0.f ? o.w : o.w * al.w;
+              }
+              *reinterpret_cast<float4*>(s_o + n) = o;
             }
-            *reinterpret_cast<float4*>(s_o + n) = o;
           }
         }
       }
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem_tc_kernel(const __grid_const
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem_base, 64);
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, (uint32_t)(2 * Np));
 }
 
 struct Cfg { int patch_rows, patch_floats, tiles_x, tiles_y, total; };
@@ -313,15 +321,15 @@ Cfg cfg_of(const ConvArgs& a) {
   c.patch_floats = 108;
   c.tiles_x = a.out.W / TW;
   c.tiles_y = a.out.H / TH;
-  c.total = layout(a.kh, c.patch_rows, c.patch_floats, a.N).total;
+  c.total = layout(a.kh, c.patch_rows, c.patch_floats, a.N, a.N <= 32 ? 32 : 64).total;
   return c;
 }
 
 }  // namespace
 
 cudaError_t stem_tc_init() {
-  cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(stem_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   return e;
 }
 
@@ -329,18 +337,18 @@ bool stem_tc_supported(const ConvArgs& a) {
   static const bool on = [] { const char* e = getenv("FDL_STEM_TC"); return e ? atoi(e) != 0 : true; }();
   if (!on || !a.mma) return false;
   if (a.mode != 0 || a.in.C != 3 || a.stride != 2 || a.kh != a.kw || (a.kh != 3 && a.kh != 5) || a.has_skip) return false;
-  if (a.N % 4 != 0 || a.N > 32 || a.N < 8) return false;
+  if (a.N % 4 != 0 || a.N > 64 || a.N < 8) return false;
   if (a.out.H % TH != 0 || a.out.W % TW != 0) return false;
   if (a.out.bstride != (long long)a.out.H * a.out.W * a.N || a.in.bstride != (long long)a.in.H * a.in.W * 3) return false;
   if ((a.in.W * 3) % 4 != 0 || (reinterpret_cast<uintptr_t>(a.in.p) & 15) != 0 || (reinterpret_cast<uintptr_t>(a.out.p) & 15) != 0) return false;
   if (a.pad_t < 0 || a.pad_t > 2 || a.pad_l < 0 || a.pad_l > 2) return false;
-  return cfg_of(a).total <= 113 * 1024;
+  return cfg_of(a).total <= 227 * 1024;
 }
 
 cudaError_t launch_stem_tc(const ConvArgs& a, cudaStream_t stream) {
   const Cfg c = cfg_of(a);
   StemTcArgs k;
-  k.w = a.w; k.bias = a.bias; k.alpha = a.alpha; k.N = a.N; k.Npad = a.Npad; k.act = a.act; k.wsplit = 2;
+  k.w = a.w; k.bias = a.bias; k.alpha = a.alpha; k.N = a.N; k.Npad = a.Npad; k.Np = a.N <= 32 ? 32 : 64; k.act = a.act; k.wsplit = 2;
   k.KH = a.kh; k.KW = a.kw; k.pad_t = a.pad_t; k.pad_l = a.pad_l; k.B = a.B; k.tiles_x = c.tiles_x; k.tiles_y = c.tiles_y;
   k.patch_rows = c.patch_rows; k.patch_floats = c.patch_floats; k.n_active = a.n_active;
   k.shift = (4 - (a.pad_l * 3) % 4) % 4;     // (2 tx TW - pad_l) * 3 - shift is a multiple of 4 floats
@@ -350,7 +358,7 @@ cudaError_t launch_stem_tc(const ConvArgs& a, cudaStream_t stream) {
   if (!encode_nhwc(&tm_out, a.out.p, a.B, a.out.H, a.out.W, a.N, a.out.bstride, TH, TW, ((a.N / 4) | 1) * 4)) return cudaErrorInvalidValue;
   const int ntiles = a.B * c.tiles_x * c.tiles_y;
   if (ntiles == 0) return cudaSuccess;
-  int grid = persist_sms() * 2;
+  int grid = persist_sms() * (c.total <= 113 * 1024 ? 2 : 1);       // two CTAs per SM when they fit
   if (grid > ntiles) grid = ntiles;
   cudaError_t e;
   if (a.kh == 5) e = launch_pdl(stem_tc_kernel<5>, dim3(grid), dim3(kThreads), (size_t)c.total, stream, tm_in, tm_out, k);
