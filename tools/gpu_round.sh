@@ -14,12 +14,16 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --
 # the dominant kernel: block_ws_kernel on the detector's 128x128x24 stage (third block_ws launch of a detector pass)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:block_ws -s 2 -c 1 -o $O/prof_block_ws_128 \
     python tools/net_bench.py face_detection_back 256 1 1 > $O/ncu_block_ws.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:stem_conv -c 1 -o $O/prof_stem \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:stem_tc -c 1 -o $O/prof_stem_tc \
     python tools/net_bench.py face_detection_back 256 1 1 > $O/ncu_stem.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:chain_kernel -c 1 -o $O/prof_chain \
+    python tools/net_bench.py iris_landmark 512 1 1 > $O/ncu_chain.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:pw_tc -c 1 -o $O/prof_pw_tc \
+    python tools/net_bench.py iris_landmark 512 1 1 > $O/ncu_pw_tc.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:block_ws -s 1 -c 1 -o $O/prof_block_ws_iris32 \
+    python tools/net_bench.py iris_landmark 512 1 1 > $O/ncu_block_ws_iris.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:blaze_block_tc -s 8 -c 1 -o $O/prof_blaze_tc \
     python tools/net_bench.py iris_landmark 512 1 1 > $O/ncu_blaze.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 20 -c 1 -o $O/prof_conv_tc \
-    python tools/net_bench.py iris_landmark 512 1 1 > $O/ncu_conv.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:jpeg_ -s 5 -c 5 -o $O/prof_jpeg \
     python tools/jpeg_bench.py 256 1 90 > $O/ncu_jpeg.log 2>&1
 tail -3 $O/pytest_gpu.log; cat $O/smoke.log | tail -2; cut -c1-3000 $O/bench.json; tail -3 $O/bench.err; cut -c1-600 $O/bench_ref.json
