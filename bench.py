@@ -399,8 +399,13 @@ def run_ours(args):
     bufs = [host, host2] + [host.clone().pin_memory() for _ in range(max(0, args.inflight - 2))]
 
     def e2e_loop(p):
-        for i in range(max(2, args.warmup // 2)):
-            p.collect_raw(p.submit(bufs[i % 2]))
+        # warm-up with as many batches in flight as the timed loop: every lane of the pipeline is used once (a lane sizes its work
+        # buffers -- for the JPEG mode 4 GB of coefficient / plane / frame buffers -- at its first batch, and a lane that first
+        # runs inside the timed region puts those allocations there: 5 k .. 22 k instead of 26 k frames/s, run to run)
+        for _ in range(max(2, args.warmup // 2)):
+            warm = [p.submit(bufs[i % len(bufs)]) for i in range(args.inflight)]
+            for t in warm:
+                p.collect_raw(t)
         barrier()
         t0 = time.perf_counter()
         pending = []

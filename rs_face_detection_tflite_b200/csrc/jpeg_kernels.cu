@@ -492,6 +492,8 @@ jpeg_entropy_kernel(const JpegImageDesc* __restrict__ descs, const JpegHuff* __r
   if (tid == 0) status[img] = tot_nb >= total_blocks ? JPEG_OK : JPEG_ERR_BLOCKS;
 }
 
+std::atomic<unsigned long long> g_entropy_optin{0};
+
 // ------------------------------------------------------------------------------------------------ dequantise + IDCT
 // range_limit[x & 0x3FF] of jdmaster.c (the table is centred on +128) == clamp(sign-extended low 10 bits of x + 128, 0, 255)
 __device__ __forceinline__ uint32_t range_limit_dev(int x) {
@@ -581,6 +583,76 @@ __global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegImageDesc* __r
       hi |= range_limit_dev(x[4 + i]) << (8 * i);
     }
     *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+  }
+}
+
+// One THREAD per block: the 64 dequantised coefficients live in registers, eight column passes and eight row passes run on
+// compile-time indices (no shared-memory transposes, no shuffles), and a column / row whose AC terms are all zero takes jidctint.c's
+// short cut (identical results: DESCALE of a multiple of 2^13).  Consecutive threads take consecutive blocks of a block row, so the
+// eight 8-byte row stores of a warp are 256 contiguous bytes each.  20 executed instructions per coefficient against the 36 of the
+// eight-lanes-per-block kernel above (which stays for A/B: FDL_JPEG_IDCT=0).
+__global__ void __launch_bounds__(128) jpeg_idct_block_kernel(const JpegImageDesc* __restrict__ descs, const int16_t* __restrict__ coef,
+                                                              uint8_t* __restrict__ planes) {
+  __shared__ uint16_t s_quant[3][64];
+  __shared__ long long s_coef_off[3], s_plane_off[3];
+  __shared__ int s_bcols[3], s_count[3], s_ncomp;
+  const int tid = threadIdx.x;
+  {
+    const JpegImageDesc& d = descs[blockIdx.y];
+    for (int i = tid; i < 192; i += 128) s_quant[i >> 6][i & 63] = d.quant[i >> 6][i & 63];
+    if (tid < 3) {
+      s_coef_off[tid] = d.coef_off[tid]; s_plane_off[tid] = d.plane_off[tid]; s_bcols[tid] = d.bcols[tid];
+      s_count[tid] = tid < d.ncomp ? d.brows[tid] * d.bcols[tid] : 0;
+    }
+    if (tid == 0) s_ncomp = d.ncomp;
+  }
+  __syncthreads();
+  int g = blockIdx.x * 128 + tid, c = 0;
+  for (; c < s_ncomp; ++c) {
+    if (g < s_count[c]) break;
+    g -= s_count[c];
+  }
+  if (c >= s_ncomp) return;
+  const int bcols = s_bcols[c], row = g / bcols, bx = g - row * bcols;
+  const int4* src = reinterpret_cast<const int4*>(coef + s_coef_off[c] + (long long)g * 64);
+  int ws[64];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int4 u = __ldg(src + r);
+    const int p[4] = {u.x, u.y, u.z, u.w};
+    const uint4 qa = *reinterpret_cast<const uint4*>(&s_quant[c][r * 8]);
+    const uint32_t qq[4] = {qa.x, qa.y, qa.z, qa.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ws[8 * r + 2 * i] = (int)(int16_t)(p[i] & 0xFFFF) * (int)(qq[i] & 0xFFFFu);
+      ws[8 * r + 2 * i + 1] = (p[i] >> 16) * (int)(qq[i] >> 16);
+    }
+  }
+#pragma unroll
+  for (int col = 0; col < 8; ++col) {
+    const int ac = ws[8 + col] | ws[16 + col] | ws[24 + col] | ws[32 + col] | ws[40 + col] | ws[48 + col] | ws[56 + col];
+    if (ac == 0) {
+      const int dc = (int)((unsigned)ws[col] << 2);       // PASS1_BITS
+#pragma unroll
+      for (int r = 0; r < 8; ++r) ws[8 * r + col] = dc;
+    } else {
+      jpeg_idct_1d(ws + col, 8, 13, 13 - 2);
+    }
+  }
+  uint8_t* dst = planes + s_plane_off[c] + (long long)(row * 8) * (bcols * 8) + bx * 8;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    int* x = ws + 8 * r;
+    uint32_t lo, hi;
+    if ((x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7]) == 0) {
+      const uint32_t b = range_limit_dev((x[0] + 16) >> 5) * 0x01010101u;   // DESCALE(x0 << 13, 13 + PASS1_BITS + 3)
+      lo = hi = b;
+    } else {
+      jpeg_idct_1d(x, 1, 13, 13 + 2 + 3);
+      lo = range_limit_dev(x[0]) | range_limit_dev(x[1]) << 8 | range_limit_dev(x[2]) << 16 | range_limit_dev(x[3]) << 24;
+      hi = range_limit_dev(x[4]) | range_limit_dev(x[5]) << 8 | range_limit_dev(x[6]) << 16 | range_limit_dev(x[7]) << 24;
+    }
+    *reinterpret_cast<uint2*>(dst + (long long)r * (bcols * 8)) = make_uint2(lo, hi);
   }
 }
 
@@ -757,7 +829,7 @@ __global__ void __launch_bounds__(256) jpeg_color_kernel(const JpegImageDesc* __
   }
 }
 
-std::atomic<unsigned long long> g_entropy_optin{0};
+
 
 }  // namespace
 
@@ -785,7 +857,9 @@ cudaError_t launch_jpeg_entropy(const JpegImageDesc* descs, int n, const JpegHuf
 
 cudaError_t launch_jpeg_idct(const JpegImageDesc* descs, int n, int max_quads, const int16_t* coef, uint8_t* planes, cudaStream_t s) {
   if (n <= 0 || max_quads <= 0) return cudaSuccess;
-  jpeg_idct_kernel<<<dim3((unsigned)((max_quads + 7) / 8), (unsigned)n), 256, 0, s>>>(descs, coef, planes);
+  static const bool per_block = getenv("FDL_JPEG_IDCT") ? atoi(getenv("FDL_JPEG_IDCT")) != 0 : true;
+  if (per_block) jpeg_idct_block_kernel<<<dim3((unsigned)((4 * max_quads + 127) / 128), (unsigned)n), 128, 0, s>>>(descs, coef, planes);
+  else jpeg_idct_kernel<<<dim3((unsigned)((max_quads + 7) / 8), (unsigned)n), 256, 0, s>>>(descs, coef, planes);
   count_launch();
   return cudaGetLastError();
 }

@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   pdl_launch_dependents();
   pdl_wait();                                       // the previous launch's activations (and *n_active) are visible from here on
   int nb = a.B;
@@ -234,8 +235,9 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
     ptx::tc_fence_before_sync();
     __syncthreads();
 
-    // ---- pointwise 1x1 on the tensor cores: one thread issues, completion arrives on mma_bar ----
-    if (tid == 0) {
+    // ---- pointwise 1x1 on the tensor cores: warp 0 (converged) runs the issue loop, one elected lane issues -- the operands stay on
+    // the uniform datapath (see mma_f16_elect) -- completion arrives on mma_bar ----
+    if (warp_u == 0) {
       ptx::tc_fence_after_sync();
       uint32_t acc_flag = 0;
       if (f16) {
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
           for (int ks = 0; ks < (Q >> 1); ++ks) {
             uint64_t ad = ptx::umma_desc_kmajor(ahi_addr + (uint32_t)(ks * 2 * kPlaneBytes), kPlaneBytes, 128);
             uint64_t bdsc = ptx::umma_desc_kmajor(b_base + (uint32_t)ks * 2u * w_lbo, w_lbo, 128);
-            ptx::mma_f16(tmem_base, ad, bdsc, idesc, acc_flag);
+            ptx::mma_f16_elect(tmem_base, ad, bdsc, idesc, acc_flag);
             acc_flag = 1;
           }
         }
@@ -258,11 +260,11 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
         for (int ks = 0; ks < ksteps; ++ks) {
           uint64_t ad = ptx::umma_desc_kmajor(a_base + (uint32_t)(ks * 2 * kPlaneBytes), kPlaneBytes, 128);
           uint64_t bdsc = ptx::umma_desc_kmajor(b_base + (uint32_t)ks * 2u * w_lbo, w_lbo, 128);
-          ptx::mma_tf32(tmem_base, ad, bdsc, idesc, acc_flag);
+          ptx::mma_tf32_elect(tmem_base, ad, bdsc, idesc, acc_flag);
           acc_flag = 1;
         }
       }
-      ptx::mma_commit(mma_bar);
+      ptx::mma_commit_elect(mma_bar);
     }
 
     // ---- epilogue: TMEM -> registers -> (+bias, +skip, act) -> smem -> TMA store ----

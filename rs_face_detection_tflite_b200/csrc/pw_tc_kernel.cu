@@ -311,6 +311,7 @@ cudaError_t launch_pw_tc(const ConvArgs& a, cudaStream_t stream) {
   k.pixels_per_item = (long long)a.in.H * a.in.W; k.B = a.B; k.n_active = a.n_active;
   if (k.NS < 2) return cudaErrorInvalidConfiguration;
   const long long npix = (long long)a.B * k.pixels_per_item;
+  if (npix > 0x7fffff00LL) return cudaErrorInvalidValue;      // tile indices and TMA coordinates are 32-bit
   CUtensorMap tm_in, tm_out;
   // the tensors as [pixels][C] matrices: dims {C, pixels, 1, 1}, boxes {C chunk (+ 4 floats of padding), 128 pixels}
   if (!encode_nhwc(&tm_in, a.in.p, 1, 1, (int)npix, k.C, npix * k.C, 1, kTile, kInStride)) return cudaErrorInvalidValue;
