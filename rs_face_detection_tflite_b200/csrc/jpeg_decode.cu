@@ -131,7 +131,9 @@ int JpegDecoder::enqueue(uint8_t* out_device, cudaStream_t s) {
   if (n_ <= 0) return set_error(FDL_ERR_INVALID, "no planned JPEG batch");
   FDL_CUDA_TRY(d_bytes_.reserve(span_bytes_ + 64));
   FDL_CUDA_TRY(d_clean_.reserve(clean_bytes_ + 256));
+  const int16_t* coef_before = d_coef_.p;
   FDL_CUDA_TRY(d_coef_.reserve(coef_elems_));
+  const bool coef_is_new = d_coef_.p != coef_before;
   FDL_CUDA_TRY(d_planes_.reserve(plane_bytes_ + 64));      // the colour kernel's word loads may run a few bytes past the last row
   FDL_CUDA_TRY(d_iv_.reserve(iv_entries_ + 1));
   FDL_CUDA_TRY(d_status_.reserve((size_t)n_));
@@ -152,7 +154,9 @@ int JpegDecoder::enqueue(uint8_t* out_device, cudaStream_t s) {
   FDL_CUDA_TRY(cudaMemcpyAsync(d_bytes_.p, direct_src_ ? direct_src_ : h_bytes_.p, span_bytes_, cudaMemcpyHostToDevice, s));
   FDL_CUDA_TRY(cudaMemcpyAsync(d_descs_.p, h_descs_.p, (size_t)n_ * sizeof(JpegImageDesc), cudaMemcpyHostToDevice, s));
   FDL_CUDA_TRY(cudaMemcpyAsync(d_tabs_.p, h_tabs_.p, dht_blobs_.size() * sizeof(JpegHuff), cudaMemcpyHostToDevice, s));
-  FDL_CUDA_TRY(cudaMemsetAsync(d_coef_.p, 0, coef_elems_ * sizeof(int16_t), s));
+  // the entropy stage writes non-zero coefficients into a zeroed buffer; the IDCT kernel leaves it zeroed again
+  if (coef_is_new) FDL_CUDA_TRY(cudaMemsetAsync(d_coef_.p, 0, d_coef_.cap * sizeof(int16_t), s));
+  else if (!jpeg_idct_clears_coef()) FDL_CUDA_TRY(cudaMemsetAsync(d_coef_.p, 0, coef_elems_ * sizeof(int16_t), s));
   FDL_CUDA_TRY(launch_jpeg_entropy(d_descs_.p, n_, d_tabs_.p, d_bytes_.p, d_clean_.p, d_coef_.p, d_iv_.p, d_status_.p, d_tile_info_.p, max_tiles_, d_scan_len_.p, max_windows_, s));
   FDL_CUDA_TRY(launch_jpeg_idct(d_descs_.p, n_, max_quads_, d_coef_.p, d_planes_.p, s));
   FDL_CUDA_TRY(launch_jpeg_color(d_descs_.p, n_, max_w_, max_h_, color_flags, d_planes_.p, out_device, s));

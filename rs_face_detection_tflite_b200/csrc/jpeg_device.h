@@ -57,7 +57,9 @@ int jpeg_scan_tiles(long long raw_off, int raw_len);   // 4 KB tiles of the comp
 // compaction (two launches) + the entropy kernel; tile_info: [n][max_tiles][3] ints, scan_len: [n][2] ints of scratch
 cudaError_t launch_jpeg_entropy(const JpegImageDesc* descs, int n, const JpegHuff* tabs, const uint8_t* bytes, uint8_t* clean, int16_t* coef,
                                 int* iv, int* status, int* tile_info, int max_tiles, int* scan_len, int max_windows, cudaStream_t s);
-cudaError_t launch_jpeg_idct(const JpegImageDesc* descs, int n, int max_quads, const int16_t* coef, uint8_t* planes, cudaStream_t s);
+// (the per-block kernel zeroes every coefficient row it has read: the buffer needs a memset only when it is new)
+cudaError_t launch_jpeg_idct(const JpegImageDesc* descs, int n, int max_quads, int16_t* coef, uint8_t* planes, cudaStream_t s);
+bool jpeg_idct_clears_coef();
 // flags: 1 = some image takes the fast path, 2 = some image takes the generic path
 cudaError_t launch_jpeg_color(const JpegImageDesc* descs, int n, int max_w, int max_h, int flags, const uint8_t* planes, uint8_t* out, cudaStream_t s);
 

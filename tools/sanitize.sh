@@ -14,6 +14,8 @@ for net in face_detection_back face_landmark iris_landmark face_detection_full_r
   run racecheck net_$net python tools/net_bench.py $net 3 1 1
 done
 run synccheck net_back python tools/net_bench.py face_detection_back 3 1 1
+run synccheck net_iris python tools/net_bench.py iris_landmark 5 1 1
+run memcheck  jpeg python tools/jpeg_bench.py 4 1 90
 run memcheck  pipeline python tools/pipe_once.py 3 1
 run racecheck pipeline python tools/pipe_once.py 3 1
 cat $O/summary.txt
