@@ -103,7 +103,8 @@ __device__ __forceinline__ float2 unpack_f16x2(uint32_t d) {
 
 template <int S, int kThreads>
 __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block_tc_kernel(const __grid_constant__ CUtensorMap tm_in,
-                                                                  const __grid_constant__ CUtensorMap tm_out, const BlockTcArgs a) {
+                                                                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_skip,
+                                                                  const BlockTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int ITH = (TH - 1) * S + 3, ITW = (TW - 1) * S + 3;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
   const SmemLayout L = smem_layout(C, N, Np, S, a.stages, wcopies, a.alias_out, a.tc_cp, a.tc_np, a.f16);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);          // [2]
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + 16);
+  uint64_t* skip_bar = reinterpret_cast<uint64_t*>(smem + 24);     // the residual tile landed in the output staging tile (skip_tma)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 32);
   float* s_bias = reinterpret_cast<float*>(smem + L.bias);
   float* s_alpha = reinterpret_cast<float*>(smem + L.alpha);
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
     ptx::mbar_init(&full_bar[0], 1);
     ptx::mbar_init(&full_bar[1], 1);
     ptx::mbar_init(mma_bar, 1);
+    ptx::mbar_init(skip_bar, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
@@ -161,6 +164,8 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
   const int tiles_per_img = a.tiles_x * a.tiles_y;
   const int ntiles = nb * tiles_per_img;
 
+  const bool early_load = a.stages == 1 && (a.skip_mode == 0 || a.skip_mode == 2);   // (with the pooled global residual, mode 3, it measured slower: 138 -> 147 us)
+  const bool skip_tma = a.skip_tma != 0;
   const int CP = a.tc_cp, NPf = a.tc_np;            // pixel strides (floats) of the input / output staging tiles
   const uint32_t in_bytes = (uint32_t)(ITH * ITW * CP * 4);
   auto issue_load = [&](int tile, int stage) {
@@ -186,6 +191,14 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
       // the previous tile's TMA store reads the region the depthwise is about to overwrite
       if (tid == 0) ptx::tma_store_wait_read0();
       __syncthreads();
+    }
+    if (skip_tma && tid == 0) {
+      // the residual tile (another tensor: the iris bottlenecks) travels by TMA into the output staging tile -- same pixel stride,
+      // missing channels zero-filled -- while the depthwise and the MMAs run; the epilogue then updates the tile in place
+      ptx::tma_store_wait_read0();                    // the previous tile's store has read the staging tile
+      ptx::mbar_arrive_expect_tx(skip_bar, (uint32_t)(TH * TW * NPf * 4));
+      int b = tile / tiles_per_img, rr = tile - b * tiles_per_img, ty = rr / a.tiles_x, tx = rr - ty * a.tiles_x;
+      ptx::tma_load_4d(s_out, &tm_skip, skip_bar, 0, tx * TW, ty * TH, b);
     }
     ptx::mbar_wait(&full_bar[stage], full_parity);
     const float* s_in = reinterpret_cast<const float*>(smem + L.in0 + stage * L.in_stage);
@@ -234,6 +247,9 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
     ptx::fence_proxy_async_smem();
     ptx::tc_fence_before_sync();
     __syncthreads();
+    // one input buffer and nobody reads it after the depthwise (no residual from the resident tile): the next tile's load starts now,
+    // under the MMAs and the epilogue, not after them
+    if (early_load && tid == 0 && next < ntiles) issue_load(next, 0);
 
     // ---- pointwise 1x1 on the tensor cores: warp 0 (converged) runs the issue loop, one elected lane issues -- the operands stay on
     // the uniform datapath (see mma_f16_elect) -- completion arrives on mma_bar ----
@@ -271,7 +287,8 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
     if (warp < 4) {
       ptx::mbar_wait(mma_bar, (uint32_t)(it & 1));
       ptx::tc_fence_after_sync();
-      if (!a.alias_out) {
+      if (skip_tma) ptx::mbar_wait(skip_bar, (uint32_t)(it & 1));
+      else if (!a.alias_out) {
         if (tid == 0) ptx::tma_store_wait_read0();   // the previous tile's store has finished reading s_out
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
@@ -299,7 +316,8 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
           for (int j = 0; j < 16; ++j) {
             sk[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             const int n = b0 + 4 * j;
-            if (skip_g && a.skip_mode == 2 && n < a.skip_c) sk[j] = __ldg(reinterpret_cast<const float4*>(skip_g + n));
+            if (skip_tma) { if (n < N) sk[j] = ld4(s_out + p * NPf + n); }
+            else if (skip_g && a.skip_mode == 2 && n < a.skip_c) sk[j] = __ldg(reinterpret_cast<const float4*>(skip_g + n));
           }
 #pragma unroll
           for (int cc = 0; cc < 64; cc += 16) {
@@ -374,7 +392,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
       }
     }
     __syncthreads();   // input stage, A planes and the TMEM accumulator are free again
-    if (a.stages == 1 && tid == 0 && next < ntiles) issue_load(next, 0);
+    if (a.stages == 1 && !early_load && tid == 0 && next < ntiles) issue_load(next, 0);
   }
 
   if (tid == 0) ptx::tma_store_wait_all0();
@@ -495,6 +513,12 @@ cudaError_t launch_block_tc(const BlockTcLaunch& l, cudaStream_t stream) {
   if (!encode_nhwc(&tm_in, l.in, a.B, a.H * S, a.W * S, a.C, (long long)a.H * S * a.W * S * a.C, in_tile_h(S), in_tile_w(S), a.tc_cp))
     return cudaErrorInvalidValue;
   if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW, a.tc_np)) return cudaErrorInvalidValue;
+  CUtensorMap tm_skip = tm_in;                      // (a valid map when the residual does not travel by TMA)
+  a.skip_tma = 0;
+  static const bool skip_tma_on = getenv("FDL_TC_SKIP_TMA") ? atoi(getenv("FDL_TC_SKIP_TMA")) != 0 : true;
+  if (skip_tma_on && a.skip_mode == 2 && !a.alias_out && a.skip != nullptr && a.skip_bstride == (long long)a.H * a.W * a.skip_c && a.skip_c % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(a.skip) & 15) == 0 && encode_nhwc(&tm_skip, a.skip, a.B, a.H, a.W, a.skip_c, a.skip_bstride, TH, TW, a.tc_np))
+    a.skip_tma = 1;
   a.tiles_x = (a.W + TW - 1) / TW;
   a.tiles_y = (a.H + TH - 1) / TH;
   a.tmem_cols = a.Np <= 32 ? 32 : (a.Np <= 64 ? 64 : 128);
@@ -507,10 +531,10 @@ cudaError_t launch_block_tc(const BlockTcLaunch& l, cudaStream_t stream) {
   static const int big_env = getenv("FDL_TC_THREADS") ? atoi(getenv("FDL_TC_THREADS")) : kThreadsSmall;   // 384 measured no faster (r01v)
   const bool big = per_sm == 1 && big_env == kThreadsBig;
   cudaError_t e;
-  if (S == 1 && big) e = launch_pdl(blaze_block_tc_kernel<1, kThreadsBig>, dim3(grid), dim3(kThreadsBig), (size_t)total, stream, tm_in, tm_out, a);
-  else if (S == 1) e = launch_pdl(blaze_block_tc_kernel<1, kThreadsSmall>, dim3(grid), dim3(kThreadsSmall), (size_t)total, stream, tm_in, tm_out, a);
-  else if (big) e = launch_pdl(blaze_block_tc_kernel<2, kThreadsBig>, dim3(grid), dim3(kThreadsBig), (size_t)total, stream, tm_in, tm_out, a);
-  else e = launch_pdl(blaze_block_tc_kernel<2, kThreadsSmall>, dim3(grid), dim3(kThreadsSmall), (size_t)total, stream, tm_in, tm_out, a);
+  if (S == 1 && big) e = launch_pdl(blaze_block_tc_kernel<1, kThreadsBig>, dim3(grid), dim3(kThreadsBig), (size_t)total, stream, tm_in, tm_out, tm_skip, a);
+  else if (S == 1) e = launch_pdl(blaze_block_tc_kernel<1, kThreadsSmall>, dim3(grid), dim3(kThreadsSmall), (size_t)total, stream, tm_in, tm_out, tm_skip, a);
+  else if (big) e = launch_pdl(blaze_block_tc_kernel<2, kThreadsBig>, dim3(grid), dim3(kThreadsBig), (size_t)total, stream, tm_in, tm_out, tm_skip, a);
+  else e = launch_pdl(blaze_block_tc_kernel<2, kThreadsSmall>, dim3(grid), dim3(kThreadsSmall), (size_t)total, stream, tm_in, tm_out, tm_skip, a);
   count_launch();
   return e;
 }
