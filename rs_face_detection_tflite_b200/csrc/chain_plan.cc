@@ -86,9 +86,6 @@ bool build_chain(Plan& plan) {
   for (int i = s0; i <= s1; ++i) order.push_back(i);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return steps[a].stream < steps[b].stream; });
 
-  // producer / consumers of every tensor the chain touches
-  std::map<int, int> producer;                         // tensor -> chain step that writes it
-  for (int i = s0; i <= s1; ++i) producer[steps[i].out.tensor] = i;
   auto used_outside = [&](int tensor, int stream) {    // read by a step outside the chain, by another stream's run, or a graph output
     for (const TensorRef& o : plan.outputs) if (o.tensor == tensor) return true;
     for (int i = 0; i < ns; ++i) {
@@ -103,7 +100,6 @@ bool build_chain(Plan& plan) {
 
   std::vector<ChainOp> ops;
   std::vector<Inst> inst;
-  std::vector<std::pair<int, int>> op_reads;           // (op, inst) for liveness
   auto new_inst = [&](int fmt, int C, int H, int W, int tensor) {
     Inst in;
     in.rows = align_up_i(G * H * W, 8);
@@ -212,17 +208,15 @@ bool build_chain(Plan& plan) {
       touch((int)ops.size() - 1, src); touch((int)ops.size() - 1, a_inst);
     }
     // ---- output formats: what the consumers inside this run need ----
-    bool want_f32 = false, want_p16 = false, other = false;
+    bool want_f32 = false, want_p16 = false;
     for (int sj : order) {
       const Step& c = steps[sj];
       if (c.stream != s.stream || sj <= si) continue;
       const int ck = classify(c);
       if (c.in.tensor == s.out.tensor) { if (ck == 3) want_f32 = true; else want_p16 = true; }
-      if (c.skip.tensor == s.out.tensor) other = true;
     }
     const bool store = used_outside(s.out.tensor, s.stream);
-    if (!want_f32 && !want_p16) want_f32 = true;       // residual-only / store-only tensors
-    (void)other;
+    if (!want_f32 && !want_p16) want_f32 = true;       // residual-only / store-only tensors (a residual is read from either format)
     const int o1 = new_inst(want_p16 ? CH_P16 : CH_F32, N, s.out.H, s.out.W, s.out.tensor);
     const int o2 = (want_p16 && want_f32) ? new_inst(CH_F32, N, s.out.H, s.out.W, s.out.tensor) : -1;
     // ---- the GEMM and its weight chunks ----
