@@ -782,16 +782,24 @@ bool pick_cfg(int C, int N, int Np, int wsplit, int f16, WsCfg* cfg) {
   const int budget = ctas == 3 ? (233472 / 3 - 1024) : (ctas == 2 ? (233472 / 2 - 1024) : kMaxSmemWs);
   static const int ob_env = getenv("FDL_WS_OB") ? atoi(getenv("FDL_WS_OB")) : 0;
   const int OB = ob_env == 1 || ob_env == 2 ? ob_env : (ctas == 3 ? 1 : 2);
-  for (; G >= 1; --G) {
-    const int ndwg = 32 * Q / ipt;
-    if (epi + G * ndwg > (ctas == 3 ? 224 : (ctas == 2 ? 320 : kMaxThreads))) continue;
-    for (int NS = (G + 3 < kMaxStages ? G + 3 : kMaxStages); NS >= (ctas == 3 ? 2 : G + 2); --NS) {   // the refill of a stage trails its tile by one epilogue
-      if (ns_cap && NS > ns_cap && NS > G + 2) continue;
-      WsLayout L = ws_layout(C, N, Np, wsplit, NS, G, OB, in_pad, f16);
-      if (L.total <= budget) {
-        cfg->G = G; cfg->ipt = ipt; cfg->ndwg = ndwg; cfg->NS = NS; cfg->OB = OB; cfg->threads = epi + G * ndwg; cfg->total = L.total; cfg->teams = teams;
-        cfg->ctas = ctas; cfg->in_pad = in_pad; cfg->f16 = f16;
-        return true;
+  const int G0 = G;
+  // Preferred: the padded tile and a refill that trails its tile by one epilogue (NS >= G + 2).  With two epilogue teams a block that
+  // does not fit that way (64 -> 64 at 24 x 24: the landmark net) may still run pipelined with the plain pixel stride and two stages.
+  static const int tight_env = getenv("FDL_WS_TIGHT") ? atoi(getenv("FDL_WS_TIGHT")) : 1;
+  for (int attempt = 0; attempt < (teams == 2 && tight_env ? 2 : 1); ++attempt) {
+    const int pad = attempt == 0 ? in_pad : 0;
+    for (G = G0; G >= 1; --G) {
+      const int ndwg = 32 * Q / ipt;
+      if (epi + G * ndwg > (ctas == 3 ? 224 : (ctas == 2 ? 320 : kMaxThreads))) continue;
+      const int ns_min = attempt == 1 ? 2 : (ctas == 3 ? 2 : G + 2);
+      for (int NS = (G + 3 < kMaxStages ? G + 3 : kMaxStages); NS >= ns_min; --NS) {
+        if (ns_cap && NS > ns_cap && NS > G + 2) continue;
+        WsLayout L = ws_layout(C, N, Np, wsplit, NS, G, OB, pad, f16);
+        if (L.total <= budget) {
+          cfg->G = G; cfg->ipt = ipt; cfg->ndwg = ndwg; cfg->NS = NS; cfg->OB = OB; cfg->threads = epi + G * ndwg; cfg->total = L.total; cfg->teams = teams;
+          cfg->ctas = ctas; cfg->in_pad = pad; cfg->f16 = f16;
+          return true;
+        }
       }
     }
   }
