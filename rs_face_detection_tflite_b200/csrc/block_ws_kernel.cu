@@ -277,6 +277,9 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
       const uint32_t taddr0 = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
       float* s_o = reinterpret_cast<float*>(smem + L.out0 + team * L.out_stage) + p * NPf;
       const bool skip_tma = a.skip_mode == 2 && a.skip_tma != 0;
+      // No staging tile at all (out_bufs == 0: wide outputs whose two 67 KB staging tiles would not fit): a thread owns a pixel, i.e.
+      // N contiguous floats of the NHWC output, and stores them straight to global memory, whole 128-byte lines over the column loop.
+      const bool direct = a.out_bufs == 0;
       for (int it = 0; it < my_tiles; ++it) {
         if (it > 0) {
           tx += step_x; ty += step_y; b += step_b;
@@ -317,10 +320,11 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
         ptx::mbar_wait(&acc_full[t], (uint32_t)((it / T) & 1));
         ptx::tc_fence_after_sync();
         if (tid == 0) WS_T(it, 5);
-        if (!skip_tma) {
+        if (!skip_tma && !direct) {
           if (leader) ptx::tma_store_wait_read0();      // this team's previous store has read its staging buffer
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         }
+        float* out_g = (direct && inside) ? a.out_direct + (((long long)b * a.H + oy) * a.W + ox) * N : nullptr;
         const uint32_t taddr = taddr0 + (uint32_t)(t * acc_cols);
         for (int c0 = 0; c0 < Np; c0 += 32) {
           if (c0 + 32 < Np) load_res(c0 + 32, resn);
@@ -350,24 +354,27 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
                 o.x = o.x >= 0.f ? o.x : o.x * a.alpha_c[n]; o.y = o.y >= 0.f ? o.y : o.y * a.alpha_c[n + 1];
                 o.z = o.z >= 0.f ? o.z : o.z * a.alpha_c[n + 2]; o.w = o.w >= 0.f ? o.w : o.w * a.alpha_c[n + 3];
               }
-              *reinterpret_cast<float4*>(s_o + n) = o;
+              if (direct) { if (out_g) *reinterpret_cast<float4*>(out_g + n) = o; }
+              else *reinterpret_cast<float4*>(s_o + n) = o;
             }
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) res[j] = resn[j];
         }
         if (tid == 0) WS_T(it, 6);
-        ptx::fence_proxy_async_smem();
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (!direct) ptx::fence_proxy_async_smem();
+        if (!direct || a.skip_mode == 1) asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (leader) {
-          ptx::tma_store_4d(&tm_out, smem + L.out0 + team * L.out_stage, 0, tx * TW, ty * TH, b);
-          ptx::tma_store_commit();
+          if (!direct) {
+            ptx::tma_store_4d(&tm_out, smem + L.out0 + team * L.out_stage, 0, tx * TW, ty * TH, b);
+            ptx::tma_store_commit();
+          }
           // residual from the resident input tile: the team is past its reads of this tile's stage (and the depthwise finished with it
           // before the MMAs): refill.  (Otherwise the depthwise group refills as soon as IT is done with the stage, see there.)
           if (a.skip_mode == 1 && it + NS < my_tiles) issue_load_at(it + NS);
         }
       }
-      if (leader) ptx::tma_store_wait_all0();
+      if (leader && !direct) ptx::tma_store_wait_all0();
     } else
     if constexpr (kNarrow) {
       int s = 0, t = 0, ph_in = 0, ph_acc = 0;
@@ -781,17 +788,19 @@ bool pick_cfg(int C, int N, int Np, int wsplit, int f16, WsCfg* cfg) {
   static const int ns_cap = getenv("FDL_WS_NS") ? atoi(getenv("FDL_WS_NS")) : 0;
   const int budget = ctas == 3 ? (233472 / 3 - 1024) : (ctas == 2 ? (233472 / 2 - 1024) : kMaxSmemWs);
   static const int ob_env = getenv("FDL_WS_OB") ? atoi(getenv("FDL_WS_OB")) : 0;
-  const int OB = ob_env == 1 || ob_env == 2 ? ob_env : (ctas == 3 ? 1 : 2);
+  const int OB0 = ob_env == 1 || ob_env == 2 ? ob_env : (ctas == 3 ? 1 : 2);
   const int G0 = G;
   // Preferred: the padded tile and a refill that trails its tile by one epilogue (NS >= G + 2).  With two epilogue teams a block that
   // does not fit that way (64 -> 64 at 24 x 24: the landmark net) may still run pipelined with the plain pixel stride and two stages.
   static const int tight_env = getenv("FDL_WS_TIGHT") ? atoi(getenv("FDL_WS_TIGHT")) : 1;
-  for (int attempt = 0; attempt < (teams == 2 && tight_env ? 2 : 1); ++attempt) {
-    const int pad = attempt == 0 ? in_pad : 0;
+  // Last resort for the widest outputs (64 -> 128, 96 -> 96): no output staging at all, the epilogue stores to global memory (OB = 0).
+  for (int attempt = 0; attempt < (teams == 2 && tight_env ? 4 : 1); ++attempt) {
+    const int pad = (attempt == 0 || attempt == 2) ? in_pad : 0;
+    const int OB = attempt >= 2 ? 0 : OB0;
     for (G = G0; G >= 1; --G) {
       const int ndwg = 32 * Q / ipt;
       if (epi + G * ndwg > (ctas == 3 ? 224 : (ctas == 2 ? 320 : kMaxThreads))) continue;
-      const int ns_min = attempt == 1 ? 2 : (ctas == 3 ? 2 : G + 2);
+      const int ns_min = attempt >= 1 ? 2 : (ctas == 3 ? 2 : G + 2);
       for (int NS = (G + 3 < kMaxStages ? G + 3 : kMaxStages); NS >= ns_min; --NS) {
         if (ns_cap && NS > ns_cap && NS > G + 2) continue;
         WsLayout L = ws_layout(C, N, Np, wsplit, NS, G, OB, pad, f16);
@@ -825,7 +834,7 @@ cudaError_t block_ws_init() {
 bool block_ws_supported(const Step& s) {
   if (s.kind != STEP_BLOCK || s.w_umma < 0 || s.stride != 1) return false;
   const int C = s.in.C, N = s.out.C;
-  if (C % 8 != 0 || N % 4 != 0 || C < 16 || C > 64) return false;
+  if (C % 8 != 0 || N % 4 != 0 || C < 16 || C > 96) return false;
   if (s.Np > 128 || s.out.H < TH || s.out.W < TW) return false;
   if (s.pad_t != 1 || s.pad_l != 1 || s.in.H != s.out.H || s.in.W != s.out.W) return false;
   if (s.in.offset != 0 || s.out.offset != 0 || s.in.batch_stride != (int64_t)s.in.H * s.in.W * C ||
@@ -843,6 +852,7 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   a.f16 = (ws_f16_enabled() && a.w_f16 != nullptr && l.bias_host != nullptr) ? 1 : 0;
   if (!pick_cfg(a.C, a.N, a.Np, a.f16 ? a.wsplit16 : a.wsplit, a.f16, &cfg)) return cudaErrorInvalidConfiguration;
   a.stages = cfg.NS; a.groups = cfg.G; a.dw_threads = cfg.ndwg; a.out_bufs = cfg.OB; a.in_pad = cfg.in_pad;
+  a.out_direct = l.out;
   a.pad = 1;
   for (int i = 0; i < 128; ++i) a.alpha_c[i] = (l.alpha_host && i < a.N) ? l.alpha_host[i] : 0.f;
   for (int i = 0; i < 128; ++i) a.bias_c[i] = (a.f16 && i < a.N) ? l.bias_host[i] : 0.f;
@@ -851,7 +861,7 @@ cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
   if (!encode_nhwc(&tm_out, l.out, a.B, a.H, a.W, a.N, (long long)a.H * a.W * a.N, TH, TW, ((a.N / 4) | 1) * 4)) return cudaErrorInvalidValue;
   CUtensorMap tm_skip = tm_in;                  // (a valid map when the residual does not travel by TMA)
   a.skip_tma = 0;
-  if (cfg.teams == 2 && a.skip_mode == 2 && a.skip != nullptr && a.skip_bstride == (long long)a.H * a.W * a.skip_c && a.skip_c % 4 == 0 &&
+  if (cfg.teams == 2 && cfg.OB == 2 && a.skip_mode == 2 && a.skip != nullptr && a.skip_bstride == (long long)a.H * a.W * a.skip_c && a.skip_c % 4 == 0 &&
       (reinterpret_cast<uintptr_t>(a.skip) & 15) == 0 && encode_nhwc(&tm_skip, a.skip, a.B, a.H, a.W, a.skip_c, a.skip_bstride, TH, TW, ((a.N / 4) | 1) * 4))
     a.skip_tma = 1;
   a.tiles_x = (a.W + TW - 1) / TW;

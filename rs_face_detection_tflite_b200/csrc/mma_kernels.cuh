@@ -29,7 +29,9 @@ struct BlockTcArgs {
   int tmem_cols = 32;
   int groups = 1;                  // block_ws_kernel: depthwise warp groups (tiles in flight on the CUDA cores)
   int dw_threads = 0;              // block_ws_kernel: threads per depthwise group
-  int out_bufs = 1;                // block_ws_kernel: output staging buffers (TMA store of tile i overlaps the epilogue of i+1)
+  int out_bufs = 1;                // block_ws_kernel: output staging buffers (TMA store of tile i overlaps the epilogue of i+1); 0: none, the
+                                   // epilogue stores to `out_direct`
+  float* out_direct = nullptr;
   int acc_cols = 32;               // block_ws_kernel: TMEM columns per accumulator buffer
   int in_pad = 0;                  // block_ws_kernel: input tile pixel stride padded to an odd number of quads
   int skip_tma = 0;                // block_ws_kernel, two epilogue teams: the residual tile (skip_mode 2) is loaded by TMA into the staging buffer
