@@ -124,6 +124,9 @@ __device__ __forceinline__ ull fma2(ull a, ull b, ull c) {
   return d;
 }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
 // (c0, c1) -> f16x2 with c0 in the low half (the lower address), round to nearest even, saturating instead of overflowing
 __device__ __forceinline__ uint32_t pack_f16x2(float c0, float c1) {
   uint32_t d;
@@ -292,6 +295,9 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
         const bool inside = oy < a.H && ox < a.W;
         const float* skip_smem = reinterpret_cast<const float*>(smem + L.in0 + s * L.in_stage) + ((py + 1) * ITW + (px + 1)) * CP;
         const float* skip_g = (a.skip_mode == 2 && inside) ? a.skip + (long long)b * a.skip_bstride + ((long long)oy * a.W + ox) * a.skip_c : nullptr;
+        // MAX_POOL 2x2 of a map twice as large (skip_mode 3): the window's four pixels, per-thread loads
+        const float* skip_p = (a.skip_mode == 3 && inside) ? a.skip + (long long)b * a.skip_bstride + ((long long)(2 * oy) * (2 * a.W) + 2 * ox) * a.skip_c : nullptr;
+        const long long prs = (long long)2 * a.W * a.skip_c;
         float4 res[8], resn[8];
         auto load_res = [&](int c0, float4 (&d)[8]) {
 #pragma unroll
@@ -302,6 +308,9 @@ __global__ void __launch_bounds__(kMaxT, kMinB) block_ws_kernel(const __grid_con
             else if (n < a.skip_c) {
               if (a.skip_mode == 1) d[j] = ld4(skip_smem + n);
               else if (skip_g) d[j] = __ldg(reinterpret_cast<const float4*>(skip_g + n));
+              else if (skip_p)
+                d[j] = max4(max4(__ldg(reinterpret_cast<const float4*>(skip_p + n)), __ldg(reinterpret_cast<const float4*>(skip_p + a.skip_c + n))),
+                            max4(__ldg(reinterpret_cast<const float4*>(skip_p + prs + n)), __ldg(reinterpret_cast<const float4*>(skip_p + prs + a.skip_c + n))));
             }
           }
         };
@@ -840,10 +849,15 @@ bool block_ws_supported(const Step& s) {
   if (s.in.offset != 0 || s.out.offset != 0 || s.in.batch_stride != (int64_t)s.in.H * s.in.W * C ||
       s.out.batch_stride != (int64_t)s.out.H * s.out.W * N)
     return false;
-  if (s.skip.tensor >= 0 && (s.skip_pool || s.skip_c % 4 != 0 || s.skip.offset != 0)) return false;
+  if (s.skip.tensor >= 0 && (s.skip_c % 4 != 0 || s.skip.offset != 0)) return false;
   WsCfg cfg;
   const int f16 = (ws_f16_enabled() && s.w_f16 >= 0) ? 1 : 0;
-  return pick_cfg(C, N, s.Np, f16 ? s.wsplit16 : s.wsplit, f16, &cfg);
+  if (!pick_cfg(C, N, s.Np, f16 ? s.wsplit16 : s.wsplit, f16, &cfg)) return false;
+  // a MAX_POOL 2x2 residual from another (twice as large) map: the two-team epilogue reads it with per-thread loads; the others do not
+  if (s.skip.tensor >= 0 && s.skip_pool &&
+      !(cfg.teams == 2 && s.skip.tensor != s.in.tensor && s.skip.H == 2 * s.out.H && s.skip.W == 2 * s.out.W && s.skip.batch_stride == (int64_t)s.skip.H * s.skip.W * s.skip_c))
+    return false;
+  return true;
 }
 
 cudaError_t launch_block_ws(const BlockTcLaunch& l, cudaStream_t stream) {
