@@ -420,6 +420,17 @@ bool encode_nhwc(CUtensorMap* m, const float* base, int B, int H, int W, int C, 
   return r == CUDA_SUCCESS;
 }
 
+// A 4-D tiled map over an arbitrary strided view (innermost dimension contiguous; strides in bytes, multiples of 16).
+bool encode_tiled4(CUtensorMap* m, const float* base, const unsigned long long dims[4], const unsigned long long strides_bytes[3], const unsigned box[4]) {
+  if (!g_encode) return false;
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t s[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t b[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), d, s, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 namespace {
 
 // f16-split A operand in the serial kernel too (FDL_TC_F16, default on): half the A-plane bytes -> room for a second input stage /

@@ -155,7 +155,7 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const 
     } else if (mode_ >= 1 && pw_tc_supported(s, B)) {
       ConvArgs a;
       a.in = in_view(s); a.out = view(s.out, B);
-      a.kh = a.kw = 1; a.K = s.K; a.K4 = s.K4; a.N = s.N; a.Npad = s.Npad;
+      a.kh = s.kh; a.kw = s.kw; a.stride = s.stride; a.K = s.K; a.K4 = s.K4; a.N = s.N; a.Npad = s.Npad;
       a.w = d_weights_ + s.w; a.bias = d_weights_ + s.b;
       if (s.alpha >= 0) a.alpha = d_weights_ + s.alpha;
       a.act = s.act; a.B = B; a.n_active = n_active;
