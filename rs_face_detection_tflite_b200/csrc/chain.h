@@ -99,8 +99,9 @@ struct ChainPlan {
   std::string text;
 };
 
-// Appends the chain's packed weights to plan.weights and fills plan.chain.  Returns false (chain.valid == false) when the
-// graph has no chainable tail; never fails the plan.
+// Appends the chains' packed weights to plan.weights and fills plan.chains (two chains when the maps shrink along the run: the
+// second packs four times as many items into a group).  Returns false (no chains) when the graph has no chainable tail; never
+// fails the plan.
 bool build_chain(Plan& plan);
 
 }  // namespace fdl

@@ -55,29 +55,21 @@ struct Inst {            // one shared-memory tensor instance
 
 }  // namespace
 
-bool build_chain(Plan& plan) {
-  ChainPlan& ch = plan.chain;
+namespace {
+
+int step_rows(const Step& s) {
+  int r = std::max(s.in.H * s.in.W, s.out.H * s.out.W);
+  if (s.skip.tensor >= 0) r = std::max(r, s.skip.H * s.skip.W);
+  return r;
+}
+
+// One chain over the plan steps [s0, s1] (all chainable).
+bool build_one(Plan& plan, int s0, int s1, ChainPlan& ch) {
   ch = ChainPlan();
   const std::vector<Step>& steps = plan.steps;
   const int ns = (int)steps.size();
-  // ---- the longest run of chainable steps ----
-  int best0 = 0, best1 = -1;
-  for (int i = 0; i < ns;) {
-    if (!classify(steps[i])) { ++i; continue; }
-    int j = i;
-    while (j + 1 < ns && classify(steps[j + 1])) ++j;
-    if (j - i > best1 - best0) { best0 = i; best1 = j; }
-    i = j + 1;
-  }
-  if (best1 - best0 + 1 < 6) return false;
-  for (int i = 0; i < best0; ++i) if (steps[i].stream != 0) return false;
-  const int s0 = best0, s1 = best1;
   int maxrows = 1;
-  for (int i = s0; i <= s1; ++i) {
-    const Step& s = steps[i];
-    maxrows = std::max(maxrows, std::max(s.in.H * s.in.W, s.out.H * s.out.W));
-    if (s.skip.tensor >= 0) maxrows = std::max(maxrows, s.skip.H * s.skip.W);
-  }
+  for (int i = s0; i <= s1; ++i) maxrows = std::max(maxrows, step_rows(steps[i]));
   const int G = 128 / maxrows;
   if (G < 1) return false;
 
@@ -330,6 +322,48 @@ bool build_chain(Plan& plan) {
                   o.K, o.N, o.nchunks);
     ch.text += buf;
   }
+  return true;
+}
+
+}  // namespace
+
+bool build_chain(Plan& plan) {
+  plan.chains.clear();
+  const std::vector<Step>& steps = plan.steps;
+  const int ns = (int)steps.size();
+  // ---- the longest run of chainable steps ----
+  int best0 = 0, best1 = -1;
+  for (int i = 0; i < ns;) {
+    if (!classify(steps[i])) { ++i; continue; }
+    int j = i;
+    while (j + 1 < ns && classify(steps[j + 1])) ++j;
+    if (j - i > best1 - best0) { best0 = i; best1 = j; }
+    i = j + 1;
+  }
+  if (best1 - best0 + 1 < 6) return false;
+  for (int i = 0; i < best0; ++i) if (steps[i].stream != 0) return false;
+  // ---- two chains when the maps shrink along the run: an op costs the same ~3 us of latency whether its 128 rows are full or
+  // not, and after two halvings a group of the first chain's size fills 8 .. 32 of them.  The run is cut after the last step that
+  // touches a map of more than a quarter of the largest one; the second chain packs four times as many items into a group. ----
+  int maxrows = 1;
+  for (int i = best0; i <= best1; ++i) maxrows = std::max(maxrows, step_rows(steps[i]));
+  int cut = -1;
+  for (int i = best0; i <= best1; ++i) if (step_rows(steps[i]) * 4 > maxrows) cut = i;
+  static const bool split_on = [] { const char* e = getenv("FDL_CHAIN_SPLIT"); return e ? atoi(e) != 0 : true; }();
+  // (worth it for a long second part only -- iris: 20 steps, 384 -> 327 us; the landmark graph's 5 + 5 steps measured slower apart)
+  if (split_on && cut >= best0 + 1 && best1 - cut >= 12) {
+    std::vector<float> saved = plan.weights;
+    ChainPlan a, b;
+    if (build_one(plan, best0, cut, a) && build_one(plan, cut + 1, best1, b) && b.items >= 2 * a.items) {
+      plan.chains.push_back(a);
+      plan.chains.push_back(b);
+      return true;
+    }
+    plan.weights = saved;
+  }
+  ChainPlan one;
+  if (!build_one(plan, best0, best1, one)) return false;
+  plan.chains.push_back(one);
   return true;
 }
 

@@ -91,22 +91,25 @@ cudaError_t Net::forward(int B, cudaStream_t stream, const int* n_active, const 
   std::vector<std::pair<int64_t, int>> main_writes;  // (root buffer, step) written on the main stream so far
   int main_last = -1;                                // last step enqueued on the main stream
   int si = -1;
-  const bool chained = mode_ == 1 && plan_.chain.valid && chain_enabled();
+  const bool chained = mode_ == 1 && !plan_.chains.empty() && chain_enabled();
   for (const Step& s : plan_.steps) {
     cudaError_t e;
     ++si;
     stream = main_stream;
-    if (chained && si >= plan_.chain.first_step && si <= plan_.chain.last_step) {
-      // the tail chain: ONE launch on the caller's stream at the position of its first step (everything before it is on that
+    const ChainPlan* ch = nullptr;
+    if (chained)
+      for (const ChainPlan& c : plan_.chains) if (si >= c.first_step && si <= c.last_step) ch = &c;
+    if (ch) {
+      // a tail chain: ONE launch on the caller's stream at the position of its first step (everything before it is on that
       // stream too); the steps after it see its stores as main-stream writes of its last step
       if (step_events && (e = cudaEventRecord(step_events[step_index++], stream)) != cudaSuccess) return e;
-      if (multi) { main_writes.push_back({s.out.buf_offset, plan_.chain.last_step}); main_last = plan_.chain.last_step; }
-      if (si != plan_.chain.first_step) continue;
+      if (multi) { main_writes.push_back({s.out.buf_offset, ch->last_step}); main_last = ch->last_step; }
+      if (si != ch->first_step) continue;
       ChainArgs a;
-      for (size_t k = 0; k < plan_.chain.ops.size(); ++k) a.ops[k] = plan_.chain.ops[k];
-      for (size_t k = 0; k < plan_.chain.loads.size(); ++k) a.loads[k] = plan_.chain.loads[k];
-      a.n_ops = (int)plan_.chain.ops.size(); a.n_loads = (int)plan_.chain.loads.size();
-      a.weights = d_weights_; a.arena = d_arena_; a.B = B; a.items = plan_.chain.items; a.n_active = n_active;
+      for (size_t k = 0; k < ch->ops.size(); ++k) a.ops[k] = ch->ops[k];
+      for (size_t k = 0; k < ch->loads.size(); ++k) a.loads[k] = ch->loads[k];
+      a.n_ops = (int)ch->ops.size(); a.n_loads = (int)ch->loads.size();
+      a.weights = d_weights_; a.arena = d_arena_; a.B = B; a.items = ch->items; a.n_active = n_active;
       if ((e = launch_chain(a, stream)) != cudaSuccess) return e;
       continue;
     }

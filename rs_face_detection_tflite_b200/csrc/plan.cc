@@ -669,7 +669,7 @@ std::string Plan::describe() const {
                 weights.size(), (long long)algo_bytes_per_item, (long long)flops_per_item);
   out += buf;
   for (const auto& s : steps) { out += s.text; out += "\n"; }
-  if (chain.valid) out += chain.text;
+  for (const ChainPlan& c : chains) out += c.text;
   return out;
 }
 

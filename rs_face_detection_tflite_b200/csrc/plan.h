@@ -93,7 +93,7 @@ struct Plan {
   int64_t flops_per_item = 0;
   int num_tflite_ops = 0;
   int num_streams = 1;            // 1 + number of auxiliary branches (see Step::stream)
-  ChainPlan chain;                // the steps on maps of at most 8 x 8 pixels as ONE launch (chain.h); valid == false: none
+  std::vector<ChainPlan> chains;  // the steps on maps of at most 8 x 8 pixels as one launch per chain (chain.h): none, one or two
 
   bool build(const TfModel& m, std::string* err);
   std::string describe() const;

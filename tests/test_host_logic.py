@@ -644,26 +644,29 @@ def test_rust_shim_keeps_the_reference_public_surface():
 
 
 def test_tail_chain_is_planned_for_the_landmark_and_iris_graphs(fdl):
-    """chain.h: the steps on maps of at most 8 x 8 pixels become ONE launch (chain_kernel.cu).  The plan is host data: the FaceMesh
-    graph chains its 6 x 6 / 3 x 3 blocks (3 faces per 128-row group), the iris graph its 8 x 8 .. 2 x 2 bottlenecks (2 eyes per
-    group), both branches of each; the detectors have no such tail.  Every GEMM reads a P16 operand, every depthwise an F32 one, and
-    the program fits the kernel's fixed tables."""
+    """chain.h: the steps on maps of at most 8 x 8 pixels become one launch per chain (chain_kernel.cu).  The plan is host data: the
+    FaceMesh graph chains its 6 x 6 / 3 x 3 blocks (3 faces per 128-row group); the iris graph its 8 x 8 bottlenecks (2 eyes per group)
+    and, in a second chain, its 4 x 4 .. 2 x 2 ones (8 eyes per group: an op costs the same whether its rows are full or not); both
+    branches of each;
+    the detectors have no such tail.  Every GEMM reads a P16 operand, every depthwise an F32 one, the chains are contiguous and every
+    program fits the kernel's fixed tables."""
     import re
-    want = {"face_landmark": (13, 22, 3), "iris_landmark": (21, 52, 2)}
-    for name, (s0, s1, items) in want.items():
+    want = {"face_landmark": [(13, 22, 3)], "iris_landmark": [(21, 32, 2), (33, 52, 8)]}
+    pat = r"chain: steps #(\d+)\.\.#(\d+) -> one launch, (\d+) items per group, (\d+) ops, (\d+) weight chunks, (\d+) parameter blocks"
+    for name, chains in want.items():
         d = fdl.Net(MODELS + "/%s.tflite" % name, -1).describe()
-        m = re.search(r"chain: steps #(\d+)\.\.#(\d+) -> one launch, (\d+) items per group, (\d+) ops, (\d+) weight chunks, (\d+) parameter blocks", d)
-        assert m, name
-        assert (int(m.group(1)), int(m.group(2)), int(m.group(3))) == (s0, s1, items)
-        assert int(m.group(4)) <= 64 and int(m.group(5)) + int(m.group(6)) <= 96
-        assert int(m.group(6)) == s1 - s0 + 1                       # one parameter block per chained step
+        found = re.findall(pat, d)
+        assert [(int(m[0]), int(m[1]), int(m[2])) for m in found] == chains, (name, found)
+        for m in found:
+            assert int(m[3]) <= 64 and int(m[4]) + int(m[5]) <= 96
+            assert int(m[5]) == int(m[1]) - int(m[0]) + 1                # one parameter block per chained step
         ops = [l.split() for l in d.splitlines() if l.startswith("  ") and l.split()[0] in ("LOAD", "STORE", "POOL", "GATHER", "DW", "GEMM")]
-        assert len(ops) == int(m.group(4))
+        assert len(ops) == sum(int(m[3]) for m in found)
         for o in ops:
             if o[0] == "GEMM":
                 assert "(P16" in o[3], o
             if o[0] == "DW":
                 assert "(F32" in o[3], o
-        assert sum(1 for o in ops if o[0] == "STORE") >= 2           # both graph branches leave the chain
+        assert sum(1 for o in ops if o[0] == "STORE") >= 2 * len(chains)   # both graph branches leave every chain
     for name in ("face_detection_back", "face_detection_short_range", "face_detection_full_range", "face_detection_full_range_sparse"):
         assert "chain:" not in fdl.Net(MODELS + "/%s.tflite" % name, -1).describe()
