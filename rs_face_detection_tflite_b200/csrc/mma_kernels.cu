@@ -164,7 +164,10 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
   const int tiles_per_img = a.tiles_x * a.tiles_y;
   const int ntiles = nb * tiles_per_img;
 
-  const bool early_load = a.stages == 1 && (a.skip_mode == 0 || a.skip_mode == 2);   // (with the pooled global residual, mode 3, it measured slower: 138 -> 147 us)
+  // Stride-2 blocks whose residual is the MAX_POOL 2x2 of their own input: the depthwise threads hold exactly those pixels, so they
+  // leave the pooled residual in the output staging tile; nobody reads the input tile after the depthwise then.
+  const bool pool_in_dw = S == 2 && a.skip_mode == 4 && !a.alias_out;
+  const bool early_load = a.stages == 1 && (a.skip_mode == 0 || a.skip_mode == 2 || pool_in_dw);   // (with the pooled global residual, mode 3, it measured slower: 138 -> 147 us)
   const bool skip_tma = a.skip_tma != 0;
   const int CP = a.tc_cp, NPf = a.tc_np;            // pixel strides (floats) of the input / output staging tiles
   const uint32_t in_bytes = (uint32_t)(ITH * ITW * CP * 4);
@@ -200,6 +203,10 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
       int b = tile / tiles_per_img, rr = tile - b * tiles_per_img, ty = rr / a.tiles_x, tx = rr - ty * a.tiles_x;
       ptx::tma_load_4d(s_out, &tm_skip, skip_bar, 0, tx * TW, ty * TH, b);
     }
+    if (pool_in_dw) {
+      if (tid == 0) ptx::tma_store_wait_read0();      // the previous tile's store has read the staging tile the depthwise writes into
+      __syncthreads();
+    }
     ptx::mbar_wait(&full_bar[stage], full_parity);
     const float* s_in = reinterpret_cast<const float*>(smem + L.in0 + stage * L.in_stage);
 
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
     for (int item = tid; item < nitems; item += kThreads) {
       const int xr = item / Q;           // item % Q == q
       const int x = xr % TW, half = xr / TW;
-      float4 acc[4];
+      float4 acc[4], pool[4];
 #pragma unroll
       for (int o = 0; o < 4; ++o) acc[o] = bd;
       const float* base = s_in + ((half * 4 * S) * ITW + x * S) * CP + 4 * q;
@@ -223,7 +230,13 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
             fma4(acc[o], v1, wd[ky * 3 + 1]);
             fma4(acc[o], v2, wd[ky * 3 + 2]);
           }
+          if (S == 2 && ky == 0) pool[o] = max4(v0, v1);                     // the 2x2 window of output (o, x): rows 2o, 2o + 1,
+          if (S == 2 && ky == 1) pool[o] = max4(pool[o], max4(v0, v1));      // columns 2x, 2x + 1 (SAME pad 0 before)
         }
+      }
+      if (pool_in_dw && 4 * q < a.skip_c) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) *reinterpret_cast<float4*>(s_out + ((half * 4 + o) * TW + x) * NPf + 4 * q) = pool[o];
       }
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
@@ -288,6 +301,7 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
       ptx::mbar_wait(mma_bar, (uint32_t)(it & 1));
       ptx::tc_fence_after_sync();
       if (skip_tma) ptx::mbar_wait(skip_bar, (uint32_t)(it & 1));
+      else if (pool_in_dw) { }                       // (the staging tile was handed over before the depthwise wrote the residual into it)
       else if (!a.alias_out) {
         if (tid == 0) ptx::tma_store_wait_read0();   // the previous tile's store has finished reading s_out
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -366,6 +380,9 @@ __global__ void __launch_bounds__(kThreads, kThreads == 192 ? 2 : 1) blaze_block
             if (n < a.skip_c) {
               if (a.skip_mode == 1) {
                 float4 s = ld4(skip_smem + n);
+                o4[0] += s.x; o4[1] += s.y; o4[2] += s.z; o4[3] += s.w;
+              } else if (pool_in_dw) {
+                const float4 s = ld4(s_out + p * NPf + n);
                 o4[0] += s.x; o4[1] += s.y; o4[2] += s.z; o4[3] += s.w;
               } else if (a.skip_mode == 4) {
                 float4 s = max4(max4(ld4(skip_smem + n), ld4(skip_smem + CP + n)), max4(ld4(skip_smem + ITW * CP + n), ld4(skip_smem + (ITW + 1) * CP + n)));
