@@ -85,6 +85,10 @@ __device__ __forceinline__ float4 join4(const uint2& hi, const uint2& lo) {
   const float2 h01 = unpack_f16x2(hi.x), h23 = unpack_f16x2(hi.y), l01 = unpack_f16x2(lo.x), l23 = unpack_f16x2(lo.y);
   return make_float4(h01.x + l01.x, h01.y + l01.y, h23.x + l23.x, h23.y + l23.y);
 }
+__device__ __forceinline__ float4 ld4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void fma4c(float4& a, const float4& x, const float4& w) {
+  a.x = fmaf(x.x, w.x, a.x); a.y = fmaf(x.y, w.y, a.y); a.z = fmaf(x.z, w.z, a.z); a.w = fmaf(x.w, w.w, a.w);
+}
 __device__ __forceinline__ float4 max4(const float4& a, const float4& b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
@@ -305,13 +309,42 @@ __global__ void __launch_bounds__(kChainThreads + 32, 1) chain_kernel(const __gr
           // rows < 128 and divisors <= 64: floor(n / d) == (n * ceil(2^16 / d)) >> 16
           const unsigned m_hw = (65536u + hw - 1) / hw, m_w = (65536u + Wo - 1) / Wo;
           const int q = tid % Q, row0 = tid / Q, rstep = kChainThreads / Q;   // kChainThreads % Q == 0: the channel quad is fixed per thread
-          float4 wd[9];
-#pragma unroll
-          for (int kk = 0; kk < 9; ++kk) wd[kk] = *reinterpret_cast<const float4*>(par + kk * C + 4 * q);
           const float4 bd = *reinterpret_cast<const float4*>(par + 9 * C + 4 * q);
           const float* in_q = reinterpret_cast<const float*>(arena + ti.off) + 4 * q;
           const int nrows = n / Q;
           CH_T2(grp, oi, 1);
+          if (S == 1 && pad_t == 1 && pad_l == 1 && Hi == to.H && Wi == Wo) {
+            // stride 1: a thread walks one COLUMN of one item down the map with the three rows of its 3 x 3 window in registers --
+            // three loads per output instead of nine, no border tests inside the window (the missing neighbours are zeros)
+            const int ncols = G * Wo;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4* wq = reinterpret_cast<const float4*>(par) + q;     // (weights re-read from shared memory: the register budget is 96)
+#define W(k_) wq[(k_) * Q]
+            for (int cx = row0; cx < ncols; cx += rstep) {
+              const int i = (int)(((unsigned)cx * m_w) >> 16), x = cx - i * Wo;
+              const bool vl = x > 0, vr = x + 1 < Wi;
+              const float* col = in_q + (size_t)(i * Hi * Wi + x) * ipl;
+              // row r is the bottom row of output r - 1's window, the middle row of output r's and the top row of output r + 1's:
+              // three running sums, one finished per row
+              float4 o_m1 = bd, o_0 = bd, o_p1 = bd;
+              for (int r = 0; r < Hi; ++r) {
+                const float* rp = col + (size_t)r * Wi * ipl;
+                const float4 v0 = vl ? ld4f(rp - ipl) : z4, v1 = ld4f(rp), v2 = vr ? ld4f(rp + ipl) : z4;
+                if (r >= 1) {
+                  fma4c(o_m1, v0, W(6)); fma4c(o_m1, v1, W(7)); fma4c(o_m1, v2, W(8));
+                  write_quad(arena, to, i * hw + (r - 1) * Wo + x, q, o_m1);
+                }
+                fma4c(o_0, v0, W(3)); fma4c(o_0, v1, W(4)); fma4c(o_0, v2, W(5));
+                fma4c(o_p1, v0, W(0)); fma4c(o_p1, v1, W(1)); fma4c(o_p1, v2, W(2));
+                o_m1 = o_0; o_0 = o_p1; o_p1 = bd;
+              }
+              write_quad(arena, to, i * hw + (Hi - 1) * Wo + x, q, o_m1);     // (its bottom row is the zero padding)
+            }
+#undef W
+          } else {
+          float4 wd[9];
+#pragma unroll
+          for (int kk = 0; kk < 9; ++kk) wd[kk] = *reinterpret_cast<const float4*>(par + kk * C + 4 * q);
           for (int row = row0; row < nrows; row += rstep) {
             const int i = (int)(((unsigned)row * m_hw) >> 16), r = row - i * hw, y = (int)(((unsigned)r * m_w) >> 16), x = r - y * Wo;
             const int iy0 = y * S - pad_t, ix0 = x * S - pad_l;
@@ -331,6 +364,7 @@ __global__ void __launch_bounds__(kChainThreads + 32, 1) chain_kernel(const __gr
               }
             }
             write_quad(arena, to, row, q, acc);
+          }
           }
         } else {
           // ---- GEMM: [128 rows x K] x [K x Np] -> TMEM, then the epilogue ----

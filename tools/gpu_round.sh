@@ -22,8 +22,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:pw_t
     python tools/net_bench.py iris_landmark 512 1 1 > $O/ncu_pw_tc.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:block_ws -s 1 -c 1 -o $O/prof_block_ws_iris32 \
     python tools/net_bench.py iris_landmark 512 1 1 > $O/ncu_block_ws_iris.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:blaze_block_tc -s 8 -c 1 -o $O/prof_blaze_tc \
-    python tools/net_bench.py iris_landmark 512 1 1 > $O/ncu_blaze.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:blaze_block_tc -s 0 -c 1 -o $O/prof_blaze_tc \
+    python tools/net_bench.py face_detection_back 256 1 1 > $O/ncu_blaze.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:jpeg_ -s 5 -c 5 -o $O/prof_jpeg \
     python tools/jpeg_bench.py 256 1 90 > $O/ncu_jpeg.log 2>&1
 tail -3 $O/pytest_gpu.log; cat $O/smoke.log | tail -2; cut -c1-3000 $O/bench.json; tail -3 $O/bench.err; cut -c1-600 $O/bench_ref.json
