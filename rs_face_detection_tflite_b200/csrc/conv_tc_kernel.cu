@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(kThreads, QC == 4 ? 3 : 0) conv_tc_kernel(cons
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   pdl_launch_dependents();
   pdl_wait();                                      // the previous launch's activations (and *n_active) are visible from here on
   int nb = a.B;
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, QC == 4 ? 3 : 0) conv_tc_kernel(cons
     ptx::fence_proxy_async_smem();
     ptx::tc_fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0) {                               // warp 0, converged: one elected lane issues (operands stay uniform, see mma_f16_elect)
       ptx::mbar_wait(&w_bar[buf], (uint32_t)((c >> 1) & 1));
       ptx::tc_fence_after_sync();
       const uint32_t ahi = ptx::smem_u32(s_a), alo = ahi + kABytes, wb = ptx::smem_u32(s_w);
@@ -263,10 +264,10 @@ __global__ void __launch_bounds__(kThreads, QC == 4 ? 3 : 0) conv_tc_kernel(cons
         for (int ks = 0; ks < KC / 8; ++ks) {
           uint64_t ad = ptx::umma_desc_kmajor(a_base + (uint32_t)(ks * 2 * kPlaneBytes), kPlaneBytes, 128);
           uint64_t bd = ptx::umma_desc_kmajor(b_base + (uint32_t)ks * 2u * w_lbo, w_lbo, 128);
-          ptx::mma_tf32(tmem_base, ad, bd, idesc, (c > 0 || pass > 0 || ks > 0) ? 1u : 0u);
+          ptx::mma_tf32_elect(tmem_base, ad, bd, idesc, (c > 0 || pass > 0 || ks > 0) ? 1u : 0u);
         }
       }
-      ptx::mma_commit(&mma_bar[buf]);               // frees this buffer; the last commit also signals the epilogue
+      ptx::mma_commit_elect(&mma_bar[buf]);         // frees this buffer; the last commit also signals the epilogue
     }
   }
 
