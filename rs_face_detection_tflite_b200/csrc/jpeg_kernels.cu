@@ -726,8 +726,9 @@ __global__ void __launch_bounds__(256) jpeg_color_generic_kernel(const JpegImage
 }
 
 // Fast path: the usual files (colour with both chroma components at 2x2 or at 2x1, more than 2 chroma samples wide) into 16-byte
-// aligned rows.  A warp takes 128 pixels x 2 rows (one chroma row + its two neighbours), a lane 4 pixels x 2 rows: aligned word
-// loads, the chroma column sums shared by both rows, RGB staged through shared memory so that each lane stores 16 aligned bytes.
+// aligned rows.  A warp walks 128 pixels x 2 rows at a time down 2 * kColorPairs rows (one chroma row + its two neighbours per
+// pair, carried over to the next pair), a lane 4 pixels x 2 rows: aligned word loads, the near-row products shared by both rows,
+// RGB staged through shared memory so that each lane stores 16 aligned bytes.
 struct ColorShared {
   const uint8_t* py; const uint8_t* pcb; const uint8_t* pcr;
   uint8_t* out;
@@ -741,16 +742,33 @@ __device__ __forceinline__ uint32_t row4(const uint8_t* __restrict__ row, int c)
   const uint32_t* p = reinterpret_cast<const uint32_t*>(row + (a & ~3));
   return __funnelshift_r(__ldg(p), __ldg(p + 1), (a & 3) * 8);
 }
-__device__ __forceinline__ int byte_of(uint32_t w, int i) { return (int)((w >> (8 * i)) & 255u); }
-
-// jdcolor.c ycc_rgb_convert for one pixel -> r | g << 8 | b << 16
-__device__ __forceinline__ uint32_t ycc_px(int y, int cb, int cr) {
-  const int xb = cb - 128, xr = cr - 128;
-  const int r = y + ((91881 * xr + 32768) >> 16);
-  const int g = y + ((-22554 * xb + 32768 + (-46802) * xr) >> 16);
-  const int b = y + ((116130 * xb + 32768) >> 16);
-  return (uint32_t)min(max(r, 0), 255) | (uint32_t)min(max(g, 0), 255) << 8 | (uint32_t)min(max(b, 0), 255) << 16;
+// jdcolor.c ycc_rgb_convert for four pixels -> 12 bytes r g b r g b ... in three words.  The operations are regrouped, not changed:
+// y + ((k * x + ONE_HALF) >> 16) == ((y << 16) + ONE_HALF + k * x) >> 16 (arithmetic shift = floor), `yh` is (y << 16) + ONE_HALF
+// built by one byte permute, x = Cb - 128 / Cr - 128 arrive already centred, the clamp to 0..255 is the saturating pack.
+__device__ __forceinline__ uint32_t pack_sat_u8(int hi, int lo) {       // sat_u8(lo) | sat_u8(hi) << 8
+  uint32_t d;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(0));
+  return d;
 }
+template <int kByte>
+__device__ __forceinline__ void ycc_px(uint32_t yw, int xb, int xr, int& r, int& g, int& b) {
+  const int yh = (int)__byte_perm(yw, 0x00008000u, 0x6054 | (kByte << 8));
+  r = (91881 * xr + yh) >> 16;
+  g = (-22554 * xb + (-46802) * xr + yh) >> 16;
+  b = (116130 * xb + yh) >> 16;
+}
+__device__ __forceinline__ void ycc_px4(uint32_t yw, const int* xb, const int* xr, uint32_t* out) {
+  int r0, g0, b0, r1, g1, b1, r2, g2, b2, r3, g3, b3;
+  ycc_px<0>(yw, xb[0], xr[0], r0, g0, b0);
+  ycc_px<1>(yw, xb[1], xr[1], r1, g1, b1);
+  ycc_px<2>(yw, xb[2], xr[2], r2, g2, b2);
+  ycc_px<3>(yw, xb[3], xr[3], r3, g3, b3);
+  out[0] = __byte_perm(pack_sat_u8(g0, r0), pack_sat_u8(r1, b0), 0x5410);
+  out[1] = __byte_perm(pack_sat_u8(b1, g1), pack_sat_u8(g2, r2), 0x5410);
+  out[2] = __byte_perm(pack_sat_u8(r3, b2), pack_sat_u8(b3, g3), 0x5410);
+}
+
+constexpr int kColorPairs = 4;     // row pairs a warp of jpeg_color_kernel walks down (a CTA: 256 pixels x 8 * kColorPairs rows)
 
 __global__ void __launch_bounds__(256) jpeg_color_kernel(const JpegImageDesc* __restrict__ descs, const uint8_t* __restrict__ planes,
                                                          uint8_t* __restrict__ out) {
@@ -769,71 +787,90 @@ __global__ void __launch_bounds__(256) jpeg_color_kernel(const JpegImageDesc* __
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int xw = blockIdx.x * 256 + (warp & 1) * 128, x0 = xw + 4 * lane;     // first pixel of the warp / of the lane
-  const int y0 = blockIdx.y * 8 + (warp >> 1) * 2;
+  const int y0 = blockIdx.y * (8 * kColorPairs) + (warp >> 1) * (2 * kColorPairs);     // the warp's first row (even)
   if (xw >= P.width || y0 >= P.height) return;
   const bool active = x0 < P.width;
-  uint32_t rgb[2][3] = {{0, 0, 0}, {0, 0, 0}};
-  if (active) {
-    const int cx = x0 >> 1, cw = P.cw;
-    const uint32_t ya = __ldg(reinterpret_cast<const uint32_t*>(P.py + (long long)y0 * P.sy + x0));
-    const uint32_t yb = __ldg(reinterpret_cast<const uint32_t*>(P.py + (long long)(y0 + 1) * P.sy + x0));
-    int cbv[2][4], crv[2][4];
+  const bool v2 = P.v2 != 0;
+  const int cx = x0 >> 1, cw = P.cw, sy = P.sy, sc = P.sc, chm1 = P.ch - 1;
+  // jdsample.c's fancy upsampling as dot products over the row words (bytes: samples c-1, c, c+1, c+2).  Far-row weights of the
+  // four outputs; the near row takes three times them (h2v2) or is the only row (h2v1).  The image edges replace the missing
+  // neighbour by the sample itself: weight 4 on it.  The rounding constant carries -128 (scaled), so the shift yields Cb - 128.
+  const uint32_t k0 = cx == 0 ? 0x00000400u : 0x00000301u, k1 = cx == cw - 1 ? 0x00000400u : 0x00010300u, k2 = 0x00030100u,
+                 k3 = cx + 1 >= cw - 1 ? 0x00040000u : 0x01030000u;
+  const uint8_t* py = P.py + (long long)y0 * sy + x0;
+  const int cy0 = v2 ? y0 >> 1 : y0;
+  // h2v2: the chroma rows above / at / below the row pair, carried from pair to pair (one new row per pair and component)
+  uint32_t w_up[2] = {0, 0}, w_at[2] = {0, 0}, w_dn[2] = {0, 0};
+  if (active && v2) {
 #pragma unroll
     for (int comp = 0; comp < 2; ++comp) {
       const uint8_t* pl = comp ? P.pcr : P.pcb;
-      int (*o)[4] = comp ? crv : cbv;
-      if (P.v2) {
-        const int cy = y0 >> 1, up = max(cy - 1, 0), dn = min(cy + 1, P.ch - 1);
-        const uint32_t wn = row4(pl + (long long)cy * P.sc, cx), wu = row4(pl + (long long)up * P.sc, cx), wd = row4(pl + (long long)dn * P.sc, cx);
+      w_up[comp] = row4(pl + (long long)max(cy0 - 1, 0) * sc, cx);
+      w_at[comp] = row4(pl + (long long)cy0 * sc, cx);
+      w_dn[comp] = row4(pl + (long long)min(cy0 + 1, chm1) * sc, cx);
+    }
+  }
+  const int row_bytes = 3 * min(128, P.width - xw);
+  uint8_t* orow = P.out + (long long)y0 * P.out_stride + 3LL * xw + 16 * lane;
+  const int npairs = min(kColorPairs, (P.height - y0 + 1) >> 1);
+  for (int j = 0; j < npairs; ++j) {
+    uint32_t rgb[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    if (active) {
+      const uint32_t ya = __ldg(reinterpret_cast<const uint32_t*>(py)), yb = __ldg(reinterpret_cast<const uint32_t*>(py + sy));
+      int xbv[2][4], xrv[2][4];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const uint32_t wf = r ? wd : wu;
-          const int s0 = 3 * byte_of(wn, 0) + byte_of(wf, 0), s1 = 3 * byte_of(wn, 1) + byte_of(wf, 1), s2 = 3 * byte_of(wn, 2) + byte_of(wf, 2),
-                    s3 = 3 * byte_of(wn, 3) + byte_of(wf, 3);
-          o[r][0] = cx == 0 ? (4 * s1 + 8) >> 4 : (3 * s1 + s0 + 8) >> 4;
-          o[r][1] = cx == cw - 1 ? (4 * s1 + 7) >> 4 : (3 * s1 + s2 + 7) >> 4;
-          o[r][2] = (3 * s2 + s1 + 8) >> 4;
-          o[r][3] = cx + 1 >= cw - 1 ? (4 * s2 + 7) >> 4 : (3 * s2 + s3 + 7) >> 4;
-        }
-      } else {
+      for (int comp = 0; comp < 2; ++comp) {
+        const uint8_t* pl = comp ? P.pcr : P.pcb;
+        int (*o)[4] = comp ? xrv : xbv;
+        if (v2) {
+          const uint32_t wn = w_at[comp];
+          const uint32_t b8 = (uint32_t)(8 - 128 * 16), b7 = (uint32_t)(7 - 128 * 16);
+          const uint32_t n0 = __dp4a(wn, 3u * k0, b8), n1 = __dp4a(wn, 3u * k1, b7), n2 = __dp4a(wn, 3u * k2, b8), n3 = __dp4a(wn, 3u * k3, b7);
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const uint32_t wn = row4(pl + (long long)(y0 + r) * P.sc, cx);
-          const int s0 = byte_of(wn, 0), s1 = byte_of(wn, 1), s2 = byte_of(wn, 2), s3 = byte_of(wn, 3);
-          o[r][0] = cx == 0 ? s1 : (3 * s1 + s0 + 1) >> 2;
-          o[r][1] = cx == cw - 1 ? s1 : (3 * s1 + s2 + 2) >> 2;
-          o[r][2] = (3 * s2 + s1 + 1) >> 2;
-          o[r][3] = cx + 1 >= cw - 1 ? s2 : (3 * s2 + s3 + 2) >> 2;
+          for (int r = 0; r < 2; ++r) {
+            const uint32_t wf = r ? w_dn[comp] : w_up[comp];
+            o[r][0] = (int)__dp4a(wf, k0, n0) >> 4;
+            o[r][1] = (int)__dp4a(wf, k1, n1) >> 4;
+            o[r][2] = (int)__dp4a(wf, k2, n2) >> 4;
+            o[r][3] = (int)__dp4a(wf, k3, n3) >> 4;
+          }
+          w_up[comp] = wn; w_at[comp] = w_dn[comp];
+          if (j + 1 < npairs) w_dn[comp] = row4(pl + (long long)min(cy0 + j + 2, chm1) * sc, cx);
+        } else {
+          const uint32_t b1 = (uint32_t)(1 - 128 * 4), b2 = (uint32_t)(2 - 128 * 4);
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const uint32_t wn = row4(pl + (long long)(cy0 + 2 * j + r) * sc, cx);
+            o[r][0] = (int)__dp4a(wn, k0, b1) >> 2;
+            o[r][1] = (int)__dp4a(wn, k1, b2) >> 2;
+            o[r][2] = (int)__dp4a(wn, k2, b1) >> 2;
+            o[r][3] = (int)__dp4a(wn, k3, b2) >> 2;
+          }
         }
       }
+      ycc_px4(ya, xbv[0], xrv[0], rgb[0]);
+      ycc_px4(yb, xbv[1], xrv[1], rgb[1]);
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      const uint32_t yw = r ? yb : ya;
-      const uint32_t p0 = ycc_px(byte_of(yw, 0), cbv[r][0], crv[r][0]), p1 = ycc_px(byte_of(yw, 1), cbv[r][1], crv[r][1]),
-                     p2 = ycc_px(byte_of(yw, 2), cbv[r][2], crv[r][2]), p3 = ycc_px(byte_of(yw, 3), cbv[r][3], crv[r][3]);
-      rgb[r][0] = p0 | p1 << 24; rgb[r][1] = p1 >> 8 | p2 << 16; rgb[r][2] = p2 >> 16 | p3 << 8;
+      s_rgb[warp][r][3 * lane] = rgb[r][0]; s_rgb[warp][r][3 * lane + 1] = rgb[r][1]; s_rgb[warp][r][3 * lane + 2] = rgb[r][2];
     }
-  }
+    __syncwarp();
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    s_rgb[warp][r][3 * lane] = rgb[r][0]; s_rgb[warp][r][3 * lane + 1] = rgb[r][1]; s_rgb[warp][r][3 * lane + 2] = rgb[r][2];
-  }
-  __syncwarp();
-  const int row_bytes = 3 * min(128, P.width - xw);
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    if (y0 + r >= P.height || lane >= 24) continue;
-    uint8_t* o = P.out + (long long)(y0 + r) * P.out_stride + 3LL * xw + 16 * lane;
-    if (16 * lane + 16 <= row_bytes) *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(&s_rgb[warp][r][4 * lane]);
-    else {
-      const uint8_t* sb = reinterpret_cast<const uint8_t*>(&s_rgb[warp][r][4 * lane]);
-      for (int i = 0; 16 * lane + i < row_bytes; ++i) o[i] = sb[i];
+    for (int r = 0; r < 2; ++r) {
+      if (y0 + 2 * j + r >= P.height || lane >= 24) continue;
+      uint8_t* o = orow + (long long)r * P.out_stride;
+      if (16 * lane + 16 <= row_bytes) *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(&s_rgb[warp][r][4 * lane]);
+      else {
+        const uint8_t* sb = reinterpret_cast<const uint8_t*>(&s_rgb[warp][r][4 * lane]);
+        for (int i = 0; 16 * lane + i < row_bytes; ++i) o[i] = sb[i];
+      }
     }
+    __syncwarp();
+    py += 2 * sy;
+    orow += 2LL * P.out_stride;
   }
 }
-
-
 
 }  // namespace
 
@@ -875,7 +912,7 @@ cudaError_t launch_jpeg_idct(const JpegImageDesc* descs, int n, int max_quads, i
 
 cudaError_t launch_jpeg_color(const JpegImageDesc* descs, int n, int max_w, int max_h, int flags, const uint8_t* planes, uint8_t* out, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  if (flags & 1) { jpeg_color_kernel<<<dim3((unsigned)((max_w + 255) / 256), (unsigned)((max_h + 7) / 8), (unsigned)n), 256, 0, s>>>(descs, planes, out); count_launch(); }
+  if (flags & 1) { jpeg_color_kernel<<<dim3((unsigned)((max_w + 255) / 256), (unsigned)((max_h + 8 * kColorPairs - 1) / (8 * kColorPairs)), (unsigned)n), 256, 0, s>>>(descs, planes, out); count_launch(); }
   if (flags & 2) { jpeg_color_generic_kernel<<<dim3((unsigned)((max_w + 1023) / 1024), (unsigned)max_h, (unsigned)n), 256, 0, s>>>(descs, planes, out); count_launch(); }
   return cudaGetLastError();
 }
