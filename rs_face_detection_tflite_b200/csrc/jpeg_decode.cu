@@ -127,7 +127,7 @@ int JpegDecoder::plan(const uint8_t* const* data, const size_t* len, int n, int 
   return FDL_OK;
 }
 
-int JpegDecoder::enqueue(uint8_t* out_device, cudaStream_t s) {
+int JpegDecoder::enqueue(uint8_t* out_device, cudaStream_t s, const int* rows, int nrows, const uint8_t* rows_done, bool* sparse) {
   if (n_ <= 0) return set_error(FDL_ERR_INVALID, "no planned JPEG batch");
   FDL_CUDA_TRY(d_bytes_.reserve(span_bytes_ + 64));
   FDL_CUDA_TRY(d_clean_.reserve(clean_bytes_ + 256));
@@ -159,9 +159,18 @@ int JpegDecoder::enqueue(uint8_t* out_device, cudaStream_t s) {
   else if (!jpeg_idct_clears_coef()) FDL_CUDA_TRY(cudaMemsetAsync(d_coef_.p, 0, coef_elems_ * sizeof(int16_t), s));
   FDL_CUDA_TRY(launch_jpeg_entropy(d_descs_.p, n_, d_tabs_.p, d_bytes_.p, d_clean_.p, d_coef_.p, d_iv_.p, d_status_.p, d_tile_info_.p, max_tiles_, d_scan_len_.p, max_windows_, s));
   FDL_CUDA_TRY(launch_jpeg_idct(d_descs_.p, n_, max_quads_, d_coef_.p, d_planes_.p, s));
-  FDL_CUDA_TRY(launch_jpeg_color(d_descs_.p, n_, max_w_, max_h_, color_flags, d_planes_.p, out_device, s));
+  const bool do_sparse = rows && nrows > 0 && color_flags == 1;
+  if (sparse) *sparse = do_sparse;
+  out_device_ = out_device;
+  rows_done_ = do_sparse ? rows_done : nullptr;
+  if (do_sparse) FDL_CUDA_TRY(launch_jpeg_color_rows(d_descs_.p, n_, rows, nrows, d_planes_.p, out_device, s));
+  else FDL_CUDA_TRY(launch_jpeg_color(d_descs_.p, n_, max_w_, max_h_, color_flags, d_planes_.p, out_device, s));
   FDL_CUDA_TRY(cudaMemcpyAsync(h_status_.p, d_status_.p, (size_t)n_ * sizeof(int), cudaMemcpyDeviceToHost, s));
   return FDL_OK;
+}
+
+cudaError_t JpegDecoder::color_roi(const I2TParams* params, int n, const int* n_active, const I2TParams* parents, cudaStream_t s) {
+  return launch_jpeg_color_roi(d_descs_.p, n_, params, n, n_active, parents, rows_done_, d_planes_.p, out_device_, s);
 }
 
 int JpegDecoder::check_status() {

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "device_util.h"
+#include "glue_math.h"
 #include "jpeg_device.h"
 
 namespace fdl {
@@ -27,12 +28,21 @@ class JpegDecoder {
   // Where image i goes in the output buffer handed to enqueue() (bytes; rows of out_stride bytes).
   void set_output(int i, long long out_off, int out_stride) { h_descs_.p[i].out_off = out_off; h_descs_.p[i].out_stride = out_stride; }
   // H2D of the compressed bytes / descriptors / tables, coefficient clear, entropy + IDCT + colour kernels, status D2H -- all on `s`.
-  int enqueue(uint8_t* out_device, cudaStream_t s);
+  // `rows` (device list of `nrows` frame rows) != null asks for the sparse conversion: only those rows of every image are converted
+  // here, the caller converts the regions its warps read with color_roi() once it knows them.  *sparse tells whether that was
+  // possible (every image on the colour fast path); otherwise the whole frames were converted as usual.
+  // `rows_done`: the same rows as a byte mask over the frame rows (color_roi skips them).
+  int enqueue(uint8_t* out_device, cudaStream_t s, const int* rows = nullptr, int nrows = 0, const uint8_t* rows_done = nullptr, bool* sparse = nullptr);
+  // After a sparse enqueue: convert the source regions of `n` image_to_tensor slots (device parameters; *n_active bounds n).
+  // `parents`: the slots (one per two of `params`: a face and its eyes) whose regions an earlier call converted.
+  cudaError_t color_roi(const I2TParams* params, int n, const int* n_active, const I2TParams* parents, cudaStream_t s);
   // After `s` has been waited for: FDL_OK, or FDL_ERR_INVALID naming the first image whose entropy-coded data was inconsistent.
   int check_status();
 
  private:
   int intern_table(const uint8_t* dht);
+  uint8_t* out_device_ = nullptr;
+  const uint8_t* rows_done_ = nullptr;
   int n_ = 0;
   size_t total_bytes_ = 0, span_bytes_ = 0, clean_bytes_ = 0, coef_elems_ = 0, plane_bytes_ = 0, iv_entries_ = 0;
   int max_windows_ = 1, max_quads_ = 0, max_w_ = 0, max_h_ = 0, max_tiles_ = 1;

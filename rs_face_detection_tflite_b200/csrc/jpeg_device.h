@@ -11,7 +11,8 @@
 //                         windows, a last pass writes the coefficients.
 //   jpeg_idct_kernel      dequantise + jpeg_idct_islow, 8 lanes per block (one row / one column each), component planes out.
 //   jpeg_color_kernel     fancy h2v2 / h2v1 chroma upsampling + fixed-point YCbCr -> RGB, 4 pixels per thread, into the frame buffer
-//                         the letterbox and ROI kernels read.
+//                         the letterbox and ROI kernels read (jpeg_color_rows_kernel / jpeg_color_roi_kernel: only the rows and
+//                         row spans the pipeline's letterbox and warps read).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -62,5 +63,13 @@ cudaError_t launch_jpeg_idct(const JpegImageDesc* descs, int n, int max_quads, i
 bool jpeg_idct_clears_coef();
 // flags: 1 = some image takes the fast path, 2 = some image takes the generic path
 cudaError_t launch_jpeg_color(const JpegImageDesc* descs, int n, int max_w, int max_h, int flags, const uint8_t* planes, uint8_t* out, cudaStream_t s);
+// Sparse conversion for the pipeline (fast-path images only): the rows of a device list for every image / the row spans of the
+// source quadrilaterals of `n` image_to_tensor slots (roi_stage_box + roi_row_span of glue_math.h, as roi_fill_kernel); `parents`
+// != null: slot i is skipped when slot i / 2 of `parents` (its face, converted before) covers it; `rows_done` != null: one byte per
+// frame row, non-zero for the rows launch_jpeg_color_rows converted.
+struct I2TParams;
+cudaError_t launch_jpeg_color_rows(const JpegImageDesc* descs, int n, const int* rows, int nrows, const uint8_t* planes, uint8_t* out, cudaStream_t s);
+cudaError_t launch_jpeg_color_roi(const JpegImageDesc* descs, int n_images, const I2TParams* params, int n, const int* n_active,
+                                  const I2TParams* parents, const uint8_t* rows_done, const uint8_t* planes, uint8_t* out, cudaStream_t s);
 
 }  // namespace fdl

@@ -1,5 +1,6 @@
 // jpeg_kernels.cu -- see jpeg_device.h.  The three kernels of the device JPEG decoder (frame ingest, utils.rs:8-21).
 #include "jpeg_device.h"
+#include "glue_math.h"
 
 #include <atomic>
 #include <climits>
@@ -872,6 +873,125 @@ __global__ void __launch_bounds__(256) jpeg_color_kernel(const JpegImageDesc* __
   }
 }
 
+// ---- sparse colour conversion (the pipeline's JPEG ingest).  The pipeline never shows the decoded frame to anybody: the letterbox
+// reads the two source rows of every output row, the face and eye warps read the taps of their ROIs.  Only those pixels are
+// converted: the rows of a list (jpeg_color_rows_kernel, before the detector) and the row spans roi_row_span gives for a warp's
+// source quadrilateral (jpeg_color_roi_kernel, once the ROIs are known) -- the same spans roi_fill_kernel stages for zero-copy host
+// frames, so the warps' arithmetic and their coverage argument are unchanged.  The pixel arithmetic is jpeg_color_kernel's.
+__device__ __forceinline__ void color_shared_fill(ColorShared& P, const JpegImageDesc& d, const uint8_t* planes, uint8_t* out) {
+  P.py = planes + d.plane_off[0]; P.pcb = planes + d.plane_off[1]; P.pcr = planes + d.plane_off[2];
+  P.out = out + d.out_off;
+  P.sy = d.bcols[0] * 8; P.sc = d.bcols[1] * 8; P.width = d.width; P.height = d.height; P.out_stride = d.out_stride;
+  P.cw = d.cw[1]; P.ch = d.ch[1]; P.v2 = d.vmax / d.vs[1] == 2;
+}
+
+// One warp: pixels [xa, xb) of row y (xa a multiple of 16: 48 bytes, so every 16-byte store is aligned; xb <= width).
+__device__ __forceinline__ void color_row_span(const ColorShared& P, int y, int xa, int xb, uint32_t* stage, int lane) {
+  const bool v2 = P.v2 != 0;
+  const int cw = P.cw, sc = P.sc;
+  const int cy = v2 ? y >> 1 : y;
+  const int fy = v2 ? ((y & 1) ? min(cy + 1, P.ch - 1) : max(cy - 1, 0)) : cy;
+  const uint8_t* yrow = P.py + (long long)y * P.sy;
+  const uint8_t* nb = P.pcb + (long long)cy * sc; const uint8_t* nr = P.pcr + (long long)cy * sc;
+  const uint8_t* fb = P.pcb + (long long)fy * sc; const uint8_t* fr = P.pcr + (long long)fy * sc;
+  uint8_t* orow = P.out + (long long)y * P.out_stride;
+  for (int xw = xa; xw < xb; xw += 128) {
+    const int x0 = xw + 4 * lane;
+    uint32_t rgb[3] = {0, 0, 0};
+    if (x0 < xb) {
+      const int cx = x0 >> 1;
+      const uint32_t k0 = cx == 0 ? 0x00000400u : 0x00000301u, k1 = cx == cw - 1 ? 0x00000400u : 0x00010300u, k2 = 0x00030100u,
+                     k3 = cx + 1 >= cw - 1 ? 0x00040000u : 0x01030000u;
+      const uint32_t yw = __ldg(reinterpret_cast<const uint32_t*>(yrow + x0));
+      int xbv[4], xrv[4];
+      if (v2) {
+        const uint32_t b8 = (uint32_t)(8 - 128 * 16), b7 = (uint32_t)(7 - 128 * 16);
+        const uint32_t wnb = row4(nb, cx), wfb = row4(fb, cx), wnr = row4(nr, cx), wfr = row4(fr, cx);
+        xbv[0] = (int)__dp4a(wfb, k0, __dp4a(wnb, 3u * k0, b8)) >> 4; xbv[1] = (int)__dp4a(wfb, k1, __dp4a(wnb, 3u * k1, b7)) >> 4;
+        xbv[2] = (int)__dp4a(wfb, k2, __dp4a(wnb, 3u * k2, b8)) >> 4; xbv[3] = (int)__dp4a(wfb, k3, __dp4a(wnb, 3u * k3, b7)) >> 4;
+        xrv[0] = (int)__dp4a(wfr, k0, __dp4a(wnr, 3u * k0, b8)) >> 4; xrv[1] = (int)__dp4a(wfr, k1, __dp4a(wnr, 3u * k1, b7)) >> 4;
+        xrv[2] = (int)__dp4a(wfr, k2, __dp4a(wnr, 3u * k2, b8)) >> 4; xrv[3] = (int)__dp4a(wfr, k3, __dp4a(wnr, 3u * k3, b7)) >> 4;
+      } else {
+        const uint32_t b1 = (uint32_t)(1 - 128 * 4), b2 = (uint32_t)(2 - 128 * 4);
+        const uint32_t wnb = row4(nb, cx), wnr = row4(nr, cx);
+        xbv[0] = (int)__dp4a(wnb, k0, b1) >> 2; xbv[1] = (int)__dp4a(wnb, k1, b2) >> 2;
+        xbv[2] = (int)__dp4a(wnb, k2, b1) >> 2; xbv[3] = (int)__dp4a(wnb, k3, b2) >> 2;
+        xrv[0] = (int)__dp4a(wnr, k0, b1) >> 2; xrv[1] = (int)__dp4a(wnr, k1, b2) >> 2;
+        xrv[2] = (int)__dp4a(wnr, k2, b1) >> 2; xrv[3] = (int)__dp4a(wnr, k3, b2) >> 2;
+      }
+      ycc_px4(yw, xbv, xrv, rgb);
+    }
+    stage[3 * lane] = rgb[0]; stage[3 * lane + 1] = rgb[1]; stage[3 * lane + 2] = rgb[2];
+    __syncwarp();
+    const int row_bytes = 3 * min(128, xb - xw);
+    if (lane < 24 && 16 * lane < row_bytes) {
+      uint8_t* o = orow + 3LL * xw + 16 * lane;
+      if (16 * lane + 16 <= row_bytes) *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(&stage[4 * lane]);
+      else {
+        const uint8_t* sb = reinterpret_cast<const uint8_t*>(&stage[4 * lane]);
+        for (int i = 0; 16 * lane + i < row_bytes; ++i) o[i] = sb[i];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256) jpeg_color_rows_kernel(const JpegImageDesc* __restrict__ descs, const uint8_t* __restrict__ planes,
+                                                              uint8_t* __restrict__ out, const int* __restrict__ rows, int nrows) {
+  __shared__ ColorShared P;
+  __shared__ __align__(16) uint32_t s_rgb[8][96];
+  if (threadIdx.x == 0) color_shared_fill(P, descs[blockIdx.y], planes, out);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * 8 + warp;
+  if (idx >= nrows) return;
+  const int y = rows[idx];
+  if (y < 0 || y >= P.height) return;
+  color_row_span(P, y, 0, P.width, s_rgb[warp], lane);
+}
+
+// CTA k of a slot's gridDim.x CTAs takes the rows y0 + 8 * k + warp (+ 8 * gridDim.x, ...): 8 CTAs for a face, 2 for an eye (the
+// box arithmetic is one thread's serial f64 work per CTA)
+
+__global__ void __launch_bounds__(256) jpeg_color_roi_kernel(const JpegImageDesc* __restrict__ descs, const uint8_t* __restrict__ planes,
+                                                             uint8_t* __restrict__ out, const I2TParams* __restrict__ params, int n,
+                                                             const int* n_active, int n_images, const I2TParams* __restrict__ parents,
+                                                             const uint8_t* __restrict__ rows_done) {
+  if (n_active) n = min(n, *n_active);
+  const int slot = blockIdx.y;
+  if (slot >= n) return;
+  __shared__ ColorShared P;
+  __shared__ SrcBox s_box;
+  __shared__ int s_margin;
+  __shared__ __align__(16) uint32_t s_rgb[8][96];
+  if (threadIdx.x == 0) {
+    const I2TParams& Q = params[slot];
+    int m = 0;
+    SrcBox b = roi_stage_box(Q, 0, true, &m);
+    if (Q.frame < 0 || Q.frame >= n_images) { b.x1 = -1; b.y1 = -1; }
+    else if (parents && b.x1 >= b.x0) {
+      // an eye slot whose source region lies inside what its face's pass converted (the test eye_split_kernel makes for zero-copy
+      // frames) has nothing left to do
+      int fm = 0;
+      const SrcBox f = roi_stage_box(parents[slot >> 1], 0, true, &fm);
+      if (parents[slot >> 1].frame == Q.frame && roi_stage_covers(f, warp_src_box(Q), Q.src_w, Q.src_h)) { b.x1 = -1; b.y1 = -1; }
+    }
+    if (b.x1 >= b.x0) color_shared_fill(P, descs[Q.frame], planes, out);
+    s_box = b; s_margin = m;
+  }
+  __syncthreads();
+  if (s_box.x1 < s_box.x0 || s_box.y1 < s_box.y0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r1 = min(s_box.y1, P.height - 1);
+  for (int r = s_box.y0 + 8 * (int)blockIdx.x + warp; r <= r1; r += 8 * (int)gridDim.x) {
+    int x0, x1;
+    if (rows_done && rows_done[r]) continue;             // a whole row the rows pass converted
+    if (!roi_row_span(s_box, r, s_margin, &x0, &x1)) continue;
+    const int xa = max(x0, 0) & ~15, xb = min((x1 + 16) & ~15, P.width);
+    if (xb > xa) color_row_span(P, r, xa, xb, s_rgb[warp], lane);
+  }
+}
+
 }  // namespace
 
 // debugging aid: phase timestamps (ns) of the last entropy launch's CTA 0
@@ -914,6 +1034,21 @@ cudaError_t launch_jpeg_color(const JpegImageDesc* descs, int n, int max_w, int 
   if (n <= 0) return cudaSuccess;
   if (flags & 1) { jpeg_color_kernel<<<dim3((unsigned)((max_w + 255) / 256), (unsigned)((max_h + 8 * kColorPairs - 1) / (8 * kColorPairs)), (unsigned)n), 256, 0, s>>>(descs, planes, out); count_launch(); }
   if (flags & 2) { jpeg_color_generic_kernel<<<dim3((unsigned)((max_w + 1023) / 1024), (unsigned)max_h, (unsigned)n), 256, 0, s>>>(descs, planes, out); count_launch(); }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_jpeg_color_rows(const JpegImageDesc* descs, int n, const int* rows, int nrows, const uint8_t* planes, uint8_t* out, cudaStream_t s) {
+  if (n <= 0 || nrows <= 0) return cudaSuccess;
+  jpeg_color_rows_kernel<<<dim3((unsigned)((nrows + 7) / 8), (unsigned)n), 256, 0, s>>>(descs, planes, out, rows, nrows);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_jpeg_color_roi(const JpegImageDesc* descs, int n_images, const I2TParams* params, int n, const int* n_active,
+                                  const I2TParams* parents, const uint8_t* rows_done, const uint8_t* planes, uint8_t* out, cudaStream_t s) {
+  if (n <= 0 || n_images <= 0) return cudaSuccess;
+  jpeg_color_roi_kernel<<<dim3(parents ? 2 : 8, (unsigned)n), 256, 0, s>>>(descs, planes, out, params, n, n_active, n_images, parents, rows_done);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -49,6 +49,29 @@ struct RowGather {
   DevBuf<int> row_pos;         // [H] source row -> compact row (-1: not gathered)
 };
 
+// The frame rows the detector's letterbox reads (the plain-letterbox path of i2t_rows_kernel: two source rows per output row), or
+// false when the slot transform is not the plain letterbox.
+bool letterbox_rows(int W, int H, int S, std::vector<int>* rows) {
+  I2TParams P;
+  i2t_setup(nullptr, W, H, S, S, true, -1.0, 1.0, false, 0, &P);
+  const int bw = P.warp_w + 2 * P.pad_h, bh = P.warp_h + 2 * P.pad_v;
+  const bool simple = P.valid && P.has_r2 && !P.flip && P.warp_w == P.src_w && P.warp_h == P.src_h && (!P.has_r1 || (bw == P.r1_w && bh == P.r1_h)) &&
+                      !(P.r1_w == S && P.r1_h == S);
+  if (!simple) return false;
+  const int pv = P.has_r1 ? P.pad_v : 0;
+  std::vector<char> need((size_t)H, 0);
+  for (int oy = 0; oy < S; ++oy) {
+    int y0, y1, b0, b1;
+    resize_coeff(oy, S, P.r1_h, false, &y0, &y1, &b0, &b1);
+    const int sy0 = y0 - pv, sy1 = y1 - pv;
+    if (sy0 >= 0 && sy0 < H) need[(size_t)sy0] = 1;
+    if (sy1 >= 0 && sy1 < H) need[(size_t)sy1] = 1;
+  }
+  rows->clear();
+  for (int r = 0; r < H; ++r) if (need[(size_t)r]) rows->push_back(r);
+  return !rows->empty();
+}
+
 bool plan_row_gather(int W, int H, int S, RowGather* g, std::vector<int>* row_pos_host) {
   I2TParams P;
   i2t_setup(nullptr, W, H, S, S, true, -1.0, 1.0, false, 0, &P);
@@ -129,6 +152,9 @@ struct fdl_pipeline {
   int S = 0, N = 0, LS = 0, IS = 0;
   DevBuf<float> anchors;
   RowGather gather;
+  DevBuf<uint8_t> jpeg_rows_done;   // the same rows as a byte mask over the frame rows
+  DevBuf<int> jpeg_rows;       // frame rows the letterbox reads (sparse colour conversion of JPEG batches); empty: convert whole frames
+  int n_jpeg_rows = 0;
   Lane lanes[kDepth];
   // One thread may submit while another collects (fdl_pool's worker and the application thread): the lane table is guarded, and
   // the guard is NOT held while collect waits for the GPU.
@@ -243,6 +269,20 @@ int fdl_pipeline_create(const fdl_pipeline_config* cfg, fdl_pipeline** out) try 
         if (e == cudaSuccess) e = l.rows.reserve((size_t)B * p->gather.rows_per_frame * cfg->frame_width * 3);
     }
   }
+  {
+    // JPEG batches: nobody but the letterbox and the ROI warps reads the decoded frames, so only what they read is colour-converted
+    static const int lazy_env = getenv("FDL_JPEG_SPARSE") ? atoi(getenv("FDL_JPEG_SPARSE")) : 1;
+    std::vector<int> rows;
+    if (e == cudaSuccess && lazy_env && letterbox_rows(cfg->frame_width, cfg->frame_height, p->S, &rows)) {
+      e = p->jpeg_rows.reserve(rows.size());
+      if (e == cudaSuccess) e = cudaMemcpy(p->jpeg_rows.p, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice);
+      std::vector<uint8_t> mask((size_t)cfg->frame_height, 0);
+      for (int r : rows) mask[(size_t)r] = 1;
+      if (e == cudaSuccess) e = p->jpeg_rows_done.reserve(mask.size());
+      if (e == cudaSuccess) e = cudaMemcpy(p->jpeg_rows_done.p, mask.data(), mask.size(), cudaMemcpyHostToDevice);
+      p->n_jpeg_rows = e == cudaSuccess ? (int)rows.size() : 0;
+    }
+  }
   if (e == cudaSuccess) e = launch_anchors(p->opt, p->anchors.p, p->N, p->lanes[0].stream);
   if (e != cudaSuccess) return bail(FDL_ERR_CUDA, std::string("CUDA: ") + cudaGetErrorString(e));
   if (!p->det->reserve(B, &err) || (p->lmk && !p->lmk->reserve(F, &err)) || (p->iris && !p->iris->reserve(E, &err)))
@@ -260,7 +300,8 @@ int fdl_pipeline_depth(const fdl_pipeline*) { return kDepth; }
 
 // Everything after the frames are where the kernels can read them (`fptr`: the lane's frame buffer, the caller's device frames, or --
 // zero-copy host mode -- the caller's pinned frames, `host_base` their host address for the copy engine's row gather).
-static int pipeline_enqueue(fdl_pipeline* p, Lane* lane, int n, const uint8_t* fptr, bool used_host, const uint8_t* host_base, int* ticket) {
+static int pipeline_enqueue(fdl_pipeline* p, Lane* lane, int n, const uint8_t* fptr, bool used_host, const uint8_t* host_base, int* ticket,
+                            JpegDecoder* sparse_jpeg = nullptr) {
   const int W = p->cfg.frame_width, H = p->cfg.frame_height, MF = p->cfg.max_faces;
   cudaStream_t cs = lane->stream;
   const long long row = (long long)W * 3, fstride = row * H;
@@ -315,6 +356,8 @@ static int pipeline_enqueue(fdl_pipeline* p, Lane* lane, int n, const uint8_t* f
                                   lane->face_params.p, n_faces, cs));
     // zero-copy host frames: stage the faces' source rectangles on the device once; the face warp and (normally) both eye warps
     // then read the device copy instead of fetching their taps over PCIe
+    // sparsely converted JPEG frames: the source regions of the face warps are converted now that they are known
+    if (sparse_jpeg) FDL_CUDA_TRY(sparse_jpeg->color_roi(lane->face_params.p, F, n_faces, nullptr, cs));
     static const int crop_env = getenv("FDL_ZC_CROP") ? atoi(getenv("FDL_ZC_CROP")) : 1;
     const bool crop = used_host && crop_env && lane->face_boxes.p && lane->frames.cap >= (size_t)fstride * n && (row & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(fptr) & 15) == 0;     // 16-byte row copies
@@ -343,6 +386,7 @@ static int pipeline_enqueue(fdl_pipeline* p, Lane* lane, int n, const uint8_t* f
       // IrisLandmark::infer for both eyes: image_to_tensor(keep_aspect, (0,1), flip = right eye)
       FDL_CUDA_TRY(launch_i2t_setup(lane->eye_rois.p, lane->eye_frame.p, lane->eye_valid.p, E, W, H, p->IS, p->IS, 1, 0.0, 1.0, 2,
                                     lane->eye_params.p, n_eyes, cs));
+      if (sparse_jpeg) FDL_CUDA_TRY(sparse_jpeg->color_roi(lane->eye_params.p, E, n_eyes, lane->face_params.p, cs));     // (an eye ROI may leave its face's)
       if (crop) {
         FDL_CUDA_TRY(launch_eye_split(lane->eye_params.p, lane->face_boxes.p, E, n_eyes, lane->eye_params_dev.p, lane->eye_params_host.p, cs));
         FDL_CUDA_TRY(launch_i2t(lane->frames.p, fstride, row, lane->eye_params_dev.p, E, p->IS, p->IS, lane->iris_in.p, (long long)p->IS * p->IS * 3, nullptr, n_eyes, cs, 0, 0, 0));
@@ -422,10 +466,13 @@ int fdl_pipeline_submit_jpeg(fdl_pipeline* p, const uint8_t* const* data, const 
   for (int i = 0; i < n; ++i) lane->jpeg.set_output(i, (long long)(frame * i), W * 3);
   FDL_CUDA_TRY(lane->frames.reserve(frame * (size_t)n));
   FDL_CUDA_TRY(cudaEventRecord(lane->ev_h2d_start, lane->stream));
-  rc = lane->jpeg.enqueue(lane->frames.p, lane->stream);
+  static const int poison_env = getenv("FDL_JPEG_POISON") ? atoi(getenv("FDL_JPEG_POISON")) : 0;     // tests: no stale pixel may be read
+  if (poison_env) FDL_CUDA_TRY(cudaMemsetAsync(lane->frames.p, 0xA5, frame * (size_t)n, lane->stream));
+  bool sparse = false;
+  rc = lane->jpeg.enqueue(lane->frames.p, lane->stream, p->n_jpeg_rows > 0 ? p->jpeg_rows.p : nullptr, p->n_jpeg_rows, p->jpeg_rows_done.p, &sparse);
   if (rc) return rc;
   lane->jpeg_pending = true;
-  return pipeline_enqueue(p, lane, n, lane->frames.p, false, nullptr, ticket);
+  return pipeline_enqueue(p, lane, n, lane->frames.p, false, nullptr, ticket, sparse ? &lane->jpeg : nullptr);
 } FDL_ABI_CATCH
 
 int fdl_pipeline_collect(fdl_pipeline* p, int ticket, fdl_frame_result* frame_results, fdl_face_result* face_results, int* n_out) try {

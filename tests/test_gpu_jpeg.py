@@ -128,3 +128,16 @@ def test_pipeline_from_jpeg_bytes_equals_pipeline_from_decoded_frames(fdl, gpu):
     assert "premature end" in e.value.message
     assert len(pipe.run_jpeg(files[:2])) == 2                                                 # and the lane is free again
     pipe.close()
+
+
+def test_sparse_colour_conversion_reads_no_unconverted_pixel(gpu):
+    """Pipeline.submit_jpeg converts only the letterbox rows and the ROI spans of the decoded frames (pipeline.cu, jpeg_color_rows /
+    jpeg_color_roi kernels).  With the frame buffer poisoned before every decode (FDL_JPEG_POISON=1, a fresh process: the switch is
+    read once) the results must still equal the pipeline's on the frames cv2 decodes: one and two faces per frame, 4:2:0 / 4:2:2,
+    restart markers, two frame sizes."""
+    import subprocess
+    import sys
+    env = dict(os.environ, FDL_JPEG_POISON="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "jpeg_sparse_check.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "sparse ok" in r.stdout
