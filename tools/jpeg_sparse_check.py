@@ -45,6 +45,7 @@ def same(want, got):
 
 def main():
     total = 0
+    quick = len(sys.argv) > 1 and sys.argv[1] == "quick"      # under compute-sanitizer: the two-face batch only
     # one face per frame, faces of three sizes / rotations, 4:2:0 and 4:2:2, one file with restart markers
     frames = synth_frames.face_frames(8, start=40, faces=("man.jpg", "russ_cox_1.jpg", "russ_cox_2.jpg"))
     files = []
@@ -56,13 +57,14 @@ def main():
             extra += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422]
         files.append(encode(frames[i], 90 if i % 2 else 75, extra))
     decoded = np.stack([decode(b) for b in files])
-    ref = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (1920, 1080), max_batch=8, max_faces=1, model_dir=MODELS, device=0)
-    want = ref.run(decoded)
-    ref.close()
-    pipe = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (1920, 1080), max_batch=8, max_faces=1, model_dir=MODELS, device=0)
-    for _ in range(3):       # every lane
-        total += same(want, pipe.run_jpeg(files))
-    pipe.close()
+    if not quick:
+        ref = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (1920, 1080), max_batch=8, max_faces=1, model_dir=MODELS, device=0)
+        want = ref.run(decoded)
+        ref.close()
+        pipe = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (1920, 1080), max_batch=8, max_faces=1, model_dir=MODELS, device=0)
+        for _ in range(3):       # every lane
+            total += same(want, pipe.run_jpeg(files))
+        pipe.close()
     # frames with two faces through the fan-out
     frames2 = [synth_frames.multi_face_frame(i) for i in range(4)]
     files2 = [encode(f) for f in frames2]
@@ -73,6 +75,9 @@ def main():
     pipe = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (1920, 1080), max_batch=4, max_faces=2, model_dir=MODELS, device=0)
     total += same(want2, pipe.run_jpeg(files2))
     pipe.close()
+    if quick:
+        print("sparse ok", total)
+        return
     # a small frame size whose rows are not a multiple of 128 pixels wide
     small = [np.ascontiguousarray(synth_frames.face_frame(i, 1920, 1080)[200:920, 320:1600]) for i in range(3)]       # 1280 x 720
     files3 = [encode(f) for f in small]

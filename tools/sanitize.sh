@@ -16,6 +16,9 @@ done
 run synccheck net_back python tools/net_bench.py face_detection_back 3 1 1
 run synccheck net_iris python tools/net_bench.py iris_landmark 5 1 1
 run memcheck  jpeg python tools/jpeg_bench.py 4 1 90
+run racecheck jpeg python tools/jpeg_bench.py 4 1 90
+FDL_JPEG_POISON=1 run memcheck  jpeg_sparse python tools/jpeg_sparse_check.py quick
+FDL_JPEG_POISON=1 run racecheck jpeg_sparse python tools/jpeg_sparse_check.py quick
 run memcheck  pipeline python tools/pipe_once.py 3 1
 run racecheck pipeline python tools/pipe_once.py 3 1
 cat $O/summary.txt
