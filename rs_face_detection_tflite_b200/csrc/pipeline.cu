@@ -273,7 +273,8 @@ int fdl_pipeline_create(const fdl_pipeline_config* cfg, fdl_pipeline** out) try 
     // JPEG batches: nobody but the letterbox and the ROI warps reads the decoded frames, so only what they read is colour-converted
     static const int lazy_env = getenv("FDL_JPEG_SPARSE") ? atoi(getenv("FDL_JPEG_SPARSE")) : 1;
     std::vector<int> rows;
-    if (e == cudaSuccess && lazy_env && letterbox_rows(cfg->frame_width, cfg->frame_height, p->S, &rows)) {
+    if (e == cudaSuccess && lazy_env && letterbox_rows(cfg->frame_width, cfg->frame_height, p->S, &rows) &&
+        rows.size() * 10 <= (size_t)cfg->frame_height * 6) {     // (small frames: most rows are read, nothing to gain)
       e = p->jpeg_rows.reserve(rows.size());
       if (e == cudaSuccess) e = cudaMemcpy(p->jpeg_rows.p, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice);
       std::vector<uint8_t> mask((size_t)cfg->frame_height, 0);

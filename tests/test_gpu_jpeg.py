@@ -134,7 +134,7 @@ def test_sparse_colour_conversion_reads_no_unconverted_pixel(gpu):
     """Pipeline.submit_jpeg converts only the letterbox rows and the ROI spans of the decoded frames (pipeline.cu, jpeg_color_rows /
     jpeg_color_roi kernels).  With the frame buffer poisoned before every decode (FDL_JPEG_POISON=1, a fresh process: the switch is
     read once) the results must still equal the pipeline's on the frames cv2 decodes: one and two faces per frame, 4:2:0 / 4:2:2,
-    restart markers, two frame sizes."""
+    restart markers, two frame sizes, a batch off the colour fast path (4:4:4: whole frames), the short-range detector alone."""
     import subprocess
     import sys
     env = dict(os.environ, FDL_JPEG_POISON="1")

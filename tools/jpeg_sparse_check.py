@@ -88,6 +88,26 @@ def main():
     pipe = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (1280, 720), max_batch=4, max_faces=1, model_dir=MODELS, device=0)
     total += same(want3, pipe.run_jpeg(files3))
     pipe.close()
+    # a batch with a 4:4:4 file is off the colour fast path: whole frames are converted, as before
+    if hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):
+        files4 = [encode(small[0], 90, [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]), files3[1]]
+        dec4 = np.stack([decode(b) for b in files4])
+        ref = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (1280, 720), max_batch=4, max_faces=1, model_dir=MODELS, device=0)
+        want4 = ref.run(dec4)
+        ref.close()
+        pipe = fdl.Pipeline(fdl.FaceDetectionModel.BackCamera, (1280, 720), max_batch=4, max_faces=1, model_dir=MODELS, device=0)
+        total += same(want4, pipe.run_jpeg(files4))
+        pipe.close()
+    # the short-range detector (128 x 128 input: another row set) on its own
+    pipe = fdl.Pipeline(fdl.FaceDetectionModel.Short, (1920, 1080), max_batch=8, max_faces=1, model_dir=MODELS, device=0, run_landmarks=False,
+                        run_iris=False)
+    a, b = pipe.run(decoded), pipe.run_jpeg(files)
+    assert sum(len(x.detections) for x in a) > 0
+    for x, y in zip(a, b):
+        assert [d.anchor for d in x.detections] == [d.anchor for d in y.detections]
+        for da, db in zip(x.detections, y.detections):
+            np.testing.assert_array_equal(da.data, db.data)
+    pipe.close()
     assert total >= 8 * 3
     print("sparse ok", total)
 
