@@ -1,6 +1,7 @@
 // jpeg_kernels.cu -- see jpeg_device.h.  The three kernels of the device JPEG decoder (frame ingest, utils.rs:8-21).
 #include "jpeg_device.h"
 #include "glue_math.h"
+#include "jpeg_color.cuh"
 
 #include <atomic>
 #include <climits>
@@ -730,45 +731,6 @@ __global__ void __launch_bounds__(256) jpeg_color_generic_kernel(const JpegImage
 // aligned rows.  A warp walks 128 pixels x 2 rows at a time down 2 * kColorPairs rows (one chroma row + its two neighbours per
 // pair, carried over to the next pair), a lane 4 pixels x 2 rows: aligned word loads, the near-row products shared by both rows,
 // RGB staged through shared memory so that each lane stores 16 aligned bytes.
-struct ColorShared {
-  const uint8_t* py; const uint8_t* pcb; const uint8_t* pcr;
-  uint8_t* out;
-  int sy, sc, width, height, out_stride, cw, ch, v2;
-};
-
-// bytes (c-1, c, c+1, c+2) of a plane row as one word (byte 0 = c-1); c even.  For c == 0 byte 0 is unspecified (the edge rule never uses it).
-__device__ __forceinline__ uint32_t row4(const uint8_t* __restrict__ row, int c) {
-  if (c == 0) return __ldg(reinterpret_cast<const uint32_t*>(row)) << 8;
-  const int a = c - 1;
-  const uint32_t* p = reinterpret_cast<const uint32_t*>(row + (a & ~3));
-  return __funnelshift_r(__ldg(p), __ldg(p + 1), (a & 3) * 8);
-}
-// jdcolor.c ycc_rgb_convert for four pixels -> 12 bytes r g b r g b ... in three words.  The operations are regrouped, not changed:
-// y + ((k * x + ONE_HALF) >> 16) == ((y << 16) + ONE_HALF + k * x) >> 16 (arithmetic shift = floor), `yh` is (y << 16) + ONE_HALF
-// built by one byte permute, x = Cb - 128 / Cr - 128 arrive already centred, the clamp to 0..255 is the saturating pack.
-__device__ __forceinline__ uint32_t pack_sat_u8(int hi, int lo) {       // sat_u8(lo) | sat_u8(hi) << 8
-  uint32_t d;
-  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(0));
-  return d;
-}
-template <int kByte>
-__device__ __forceinline__ void ycc_px(uint32_t yw, int xb, int xr, int& r, int& g, int& b) {
-  const int yh = (int)__byte_perm(yw, 0x00008000u, 0x6054 | (kByte << 8));
-  r = (91881 * xr + yh) >> 16;
-  g = (-22554 * xb + (-46802) * xr + yh) >> 16;
-  b = (116130 * xb + yh) >> 16;
-}
-__device__ __forceinline__ void ycc_px4(uint32_t yw, const int* xb, const int* xr, uint32_t* out) {
-  int r0, g0, b0, r1, g1, b1, r2, g2, b2, r3, g3, b3;
-  ycc_px<0>(yw, xb[0], xr[0], r0, g0, b0);
-  ycc_px<1>(yw, xb[1], xr[1], r1, g1, b1);
-  ycc_px<2>(yw, xb[2], xr[2], r2, g2, b2);
-  ycc_px<3>(yw, xb[3], xr[3], r3, g3, b3);
-  out[0] = __byte_perm(pack_sat_u8(g0, r0), pack_sat_u8(r1, b0), 0x5410);
-  out[1] = __byte_perm(pack_sat_u8(b1, g1), pack_sat_u8(g2, r2), 0x5410);
-  out[2] = __byte_perm(pack_sat_u8(r3, b2), pack_sat_u8(b3, g3), 0x5410);
-}
-
 constexpr int kColorPairs = 4;     // row pairs a warp of jpeg_color_kernel walks down (a CTA: 256 pixels x 8 * kColorPairs rows)
 
 __global__ void __launch_bounds__(256) jpeg_color_kernel(const JpegImageDesc* __restrict__ descs, const uint8_t* __restrict__ planes,
@@ -878,49 +840,15 @@ __global__ void __launch_bounds__(256) jpeg_color_kernel(const JpegImageDesc* __
 // converted: the rows of a list (jpeg_color_rows_kernel, before the detector) and the row spans roi_row_span gives for a warp's
 // source quadrilateral (jpeg_color_roi_kernel, once the ROIs are known) -- the same spans roi_fill_kernel stages for zero-copy host
 // frames, so the warps' arithmetic and their coverage argument are unchanged.  The pixel arithmetic is jpeg_color_kernel's.
-__device__ __forceinline__ void color_shared_fill(ColorShared& P, const JpegImageDesc& d, const uint8_t* planes, uint8_t* out) {
-  P.py = planes + d.plane_off[0]; P.pcb = planes + d.plane_off[1]; P.pcr = planes + d.plane_off[2];
-  P.out = out + d.out_off;
-  P.sy = d.bcols[0] * 8; P.sc = d.bcols[1] * 8; P.width = d.width; P.height = d.height; P.out_stride = d.out_stride;
-  P.cw = d.cw[1]; P.ch = d.ch[1]; P.v2 = d.vmax / d.vs[1] == 2;
-}
-
 // One warp: pixels [xa, xb) of row y (xa a multiple of 16: 48 bytes, so every 16-byte store is aligned; xb <= width).
 __device__ __forceinline__ void color_row_span(const ColorShared& P, int y, int xa, int xb, uint32_t* stage, int lane) {
-  const bool v2 = P.v2 != 0;
-  const int cw = P.cw, sc = P.sc;
-  const int cy = v2 ? y >> 1 : y;
-  const int fy = v2 ? ((y & 1) ? min(cy + 1, P.ch - 1) : max(cy - 1, 0)) : cy;
-  const uint8_t* yrow = P.py + (long long)y * P.sy;
-  const uint8_t* nb = P.pcb + (long long)cy * sc; const uint8_t* nr = P.pcr + (long long)cy * sc;
-  const uint8_t* fb = P.pcb + (long long)fy * sc; const uint8_t* fr = P.pcr + (long long)fy * sc;
+  const uint8_t *yrow, *nb, *nr, *fb, *fr;
+  color_row_ptrs(P, y, &yrow, &nb, &nr, &fb, &fr);
   uint8_t* orow = P.out + (long long)y * P.out_stride;
   for (int xw = xa; xw < xb; xw += 128) {
     const int x0 = xw + 4 * lane;
     uint32_t rgb[3] = {0, 0, 0};
-    if (x0 < xb) {
-      const int cx = x0 >> 1;
-      const uint32_t k0 = cx == 0 ? 0x00000400u : 0x00000301u, k1 = cx == cw - 1 ? 0x00000400u : 0x00010300u, k2 = 0x00030100u,
-                     k3 = cx + 1 >= cw - 1 ? 0x00040000u : 0x01030000u;
-      const uint32_t yw = __ldg(reinterpret_cast<const uint32_t*>(yrow + x0));
-      int xbv[4], xrv[4];
-      if (v2) {
-        const uint32_t b8 = (uint32_t)(8 - 128 * 16), b7 = (uint32_t)(7 - 128 * 16);
-        const uint32_t wnb = row4(nb, cx), wfb = row4(fb, cx), wnr = row4(nr, cx), wfr = row4(fr, cx);
-        xbv[0] = (int)__dp4a(wfb, k0, __dp4a(wnb, 3u * k0, b8)) >> 4; xbv[1] = (int)__dp4a(wfb, k1, __dp4a(wnb, 3u * k1, b7)) >> 4;
-        xbv[2] = (int)__dp4a(wfb, k2, __dp4a(wnb, 3u * k2, b8)) >> 4; xbv[3] = (int)__dp4a(wfb, k3, __dp4a(wnb, 3u * k3, b7)) >> 4;
-        xrv[0] = (int)__dp4a(wfr, k0, __dp4a(wnr, 3u * k0, b8)) >> 4; xrv[1] = (int)__dp4a(wfr, k1, __dp4a(wnr, 3u * k1, b7)) >> 4;
-        xrv[2] = (int)__dp4a(wfr, k2, __dp4a(wnr, 3u * k2, b8)) >> 4; xrv[3] = (int)__dp4a(wfr, k3, __dp4a(wnr, 3u * k3, b7)) >> 4;
-      } else {
-        const uint32_t b1 = (uint32_t)(1 - 128 * 4), b2 = (uint32_t)(2 - 128 * 4);
-        const uint32_t wnb = row4(nb, cx), wnr = row4(nr, cx);
-        xbv[0] = (int)__dp4a(wnb, k0, b1) >> 2; xbv[1] = (int)__dp4a(wnb, k1, b2) >> 2;
-        xbv[2] = (int)__dp4a(wnb, k2, b1) >> 2; xbv[3] = (int)__dp4a(wnb, k3, b2) >> 2;
-        xrv[0] = (int)__dp4a(wnr, k0, b1) >> 2; xrv[1] = (int)__dp4a(wnr, k1, b2) >> 2;
-        xrv[2] = (int)__dp4a(wnr, k2, b1) >> 2; xrv[3] = (int)__dp4a(wnr, k3, b2) >> 2;
-      }
-      ycc_px4(yw, xbv, xrv, rgb);
-    }
+    if (x0 < xb) color_px4(P, yrow, nb, nr, fb, fr, x0, rgb);
     stage[3 * lane] = rgb[0]; stage[3 * lane + 1] = rgb[1]; stage[3 * lane + 2] = rgb[2];
     __syncwarp();
     const int row_bytes = 3 * min(128, xb - xw);
