@@ -524,7 +524,7 @@ def run_ours(args):
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     total_ms_max, e2e_s_max, e2e_copy_max, e2e_zc_max, e2e_jpeg_max = (float(v) for v in t_dev)
     modes = {"copy": e2e_copy_s, "zero-copy (kernels read pinned host frames in place)": e2e_zc_s,
-             "jpeg (compressed H2D from a pinned arena + device decode, fdl_pool_submit_jpeg)": e2e_jpeg_s}
+             "jpeg (compressed H2D from a pinned arena + device decode, colour-converting only the pixels the pipeline reads; fdl_pool_submit_jpeg)": e2e_jpeg_s}
     best_mode = min((k for k in modes if modes[k] is not None), key=lambda k: modes[k])
     frames_total = world * B * args.steps
     value = frames_total / (total_ms_max / 1e3)

@@ -58,6 +58,11 @@ bool letterbox_rows(int W, int H, int S, std::vector<int>* rows) {
   const bool simple = P.valid && P.has_r2 && !P.flip && P.warp_w == P.src_w && P.warp_h == P.src_h && (!P.has_r1 || (bw == P.r1_w && bh == P.r1_h)) &&
                       !(P.r1_w == S && P.r1_h == S);
   if (!simple) return false;
+  // the kernel's own test of the identity warp (i2t_rows_kernel): a slot that fails it is evaluated pixel by pixel anywhere in the frame
+  const double e = 1e-9;
+  if (!(fabs(P.Mi[0] - 1.0) < e && fabs(P.Mi[4] - 1.0) < e && fabs(P.Mi[8] - 1.0) < e && fabs(P.Mi[1]) < e && fabs(P.Mi[2]) < e * P.src_w &&
+        fabs(P.Mi[3]) < e && fabs(P.Mi[5]) < e * P.src_h && fabs(P.Mi[6]) < e && fabs(P.Mi[7]) < e))
+    return false;
   const int pv = P.has_r1 ? P.pad_v : 0;
   std::vector<char> need((size_t)H, 0);
   for (int oy = 0; oy < S; ++oy) {
