@@ -247,3 +247,60 @@ def test_malformed_tables_and_damaged_scans_under_asan_and_ubsan(tmp_path):
     buf[p + 5] = 3
     with pytest.raises(ValueError):
         jpeg_decode.decode_jpeg_rgb(bytes(buf))
+
+
+def test_colour_kernel_regrouping_is_exact():
+    """jpeg_color.cuh evaluates jdsample.c / jdcolor.c with the operations regrouped (byte dot products whose rounding constant
+    carries -128, `((y << 16) + ONE_HALF + k * x) >> 16`, a saturating pack as the clamp).  The regrouped integer expressions,
+    restated here in numpy, must equal the oracle's straight forms: every (y, cb, cr) for the colour step, random and extreme
+    planes of odd and even sizes for both upsamplers."""
+    from oracle import jpeg_decode as J
+
+    # ---- YCbCr -> RGB, all 2^24 inputs
+    y, cb, cr = np.meshgrid(np.arange(256, dtype=np.int64), np.arange(256, dtype=np.int64), np.arange(0, 256, 1, dtype=np.int64), indexing="ij")
+    xb, xr = cb - 128, cr - 128
+    yh = (y << 16) + 32768
+    r = (91881 * xr + yh) >> 16
+    g = (-22554 * xb - 46802 * xr + yh) >> 16
+    b = (116130 * xb + yh) >> 16
+    got = np.clip(np.stack([r, g, b], axis=-1), 0, 255).astype(np.uint8)
+    want = J._ycc_to_rgb(y.astype(np.uint8), cb, cr)
+    assert np.array_equal(got, want)
+
+    # ---- fancy upsampling as weighted sums with the centring folded into the rounding constant
+    def up_h2v2(c):
+        h, w = c.shape
+        ci = c.astype(np.int64)
+        out = np.empty((2 * h, 2 * w), np.int64)
+        for Y in range(2 * h):
+            cy = Y >> 1
+            fy = min(cy + 1, h - 1) if Y & 1 else max(cy - 1, 0)
+            n, f = ci[cy], ci[fy]
+            left_n, left_f = np.roll(n, 1), np.roll(f, 1)
+            right_n, right_f = np.roll(n, -1), np.roll(f, -1)
+            even = (9 * n + 3 * f + 3 * left_n + left_f + (8 - 2048)) >> 4          # weights 3x(3,1) near, (3,1) far
+            odd = (9 * n + 3 * f + 3 * right_n + right_f + (7 - 2048)) >> 4
+            even[0] = (12 * n[0] + 4 * f[0] + (8 - 2048)) >> 4                       # edges: weight 4 on the sample itself
+            odd[-1] = (12 * n[-1] + 4 * f[-1] + (7 - 2048)) >> 4
+            out[Y, 0::2] = even + 128
+            out[Y, 1::2] = odd + 128
+        return out.astype(np.uint8)
+
+    def up_h2v1(c):
+        ci = c.astype(np.int64)
+        left, right = np.roll(ci, 1, axis=1), np.roll(ci, -1, axis=1)
+        even = (3 * ci + left + (1 - 512)) >> 2
+        odd = (3 * ci + right + (2 - 512)) >> 2
+        even[:, 0] = (4 * ci[:, 0] + (1 - 512)) >> 2
+        odd[:, -1] = (4 * ci[:, -1] + (2 - 512)) >> 2
+        out = np.empty((c.shape[0], 2 * c.shape[1]), np.int64)
+        out[:, 0::2] = even + 128
+        out[:, 1::2] = odd + 128
+        return out.astype(np.uint8)
+
+    rng = np.random.default_rng(5)
+    for h, w in ((1, 3), (2, 3), (5, 4), (8, 17), (33, 64)):
+        for plane in (rng.integers(0, 256, (h, w), dtype=np.uint8), np.zeros((h, w), np.uint8), np.full((h, w), 255, np.uint8),
+                      (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)):
+            assert np.array_equal(up_h2v2(plane), J._upsample_h2v2(plane))
+            assert np.array_equal(up_h2v1(plane), J._upsample_h2v1(plane))
