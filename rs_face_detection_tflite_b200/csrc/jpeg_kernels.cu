@@ -911,12 +911,24 @@ __global__ void __launch_bounds__(256) jpeg_color_roi_kernel(const JpegImageDesc
   if (s_box.x1 < s_box.x0 || s_box.y1 < s_box.y0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r1 = min(s_box.y1, P.height - 1);
-  for (int r = s_box.y0 + 8 * (int)blockIdx.x + warp; r <= r1; r += 8 * (int)gridDim.x) {
-    int x0, x1;
-    if (rows_done && rows_done[r]) continue;             // a whole row the rows pass converted
-    if (!roi_row_span(s_box, r, s_margin, &x0, &x1)) continue;
-    const int xa = max(x0, 0) & ~15, xb = min((x1 + 16) & ~15, P.width);
-    if (xb > xa) color_row_span(P, r, xa, xb, s_rgb[warp], lane);
+  // The warp's rows are y0 + 8 * k + warp + j * step.  Their spans (roi_row_span: a few hundred f64 instructions, more than the
+  // pixels of a face-sized row cost) are computed 32 rows at a time, one row per lane, and handed round by shuffle.
+  const int rstep = 8 * (int)gridDim.x;
+  for (int rb = s_box.y0 + 8 * (int)blockIdx.x + warp; rb <= r1; rb += 32 * rstep) {
+    const int rl = rb + lane * rstep;
+    int x0l = 0, x1l = -1;
+    if (rl <= r1 && !(rows_done && rows_done[rl])) {     // (rows_done: a whole row the rows pass converted)
+      int a, b;
+      if (roi_row_span(s_box, rl, s_margin, &a, &b)) { x0l = a; x1l = b; }
+    }
+    for (int j = 0; j < 32; ++j) {
+      const int r = rb + j * rstep;
+      if (r > r1) break;
+      const int x0 = __shfl_sync(0xffffffffu, x0l, j), x1 = __shfl_sync(0xffffffffu, x1l, j);
+      if (x1 < x0) continue;
+      const int xa = max(x0, 0) & ~15, xb = min((x1 + 16) & ~15, P.width);
+      if (xb > xa) color_row_span(P, r, xa, xb, s_rgb[warp], lane);
+    }
   }
 }
 
